@@ -1,0 +1,170 @@
+/*
+ * smartcal_b200.h -- C ABI of libsmartcal_b200.so (sm_100a).
+ *
+ * The reference (SarodYatawatta/smart-calibration) has NO native/FFI layer: callers use the Python
+ * classes of elasticnet/enet_sac.py and enet_td3.py directly.  This header is therefore the boundary a
+ * maintainer binds INSTEAD of the torch-eager bodies of those classes; each entry point cites the
+ * reference method whose body it replaces.  The Python facade in
+ * smart-calibration_b200/elasticnet/{enet_sac,enet_td3}.py is a ctypes binding of exactly these symbols
+ * (INTEGRATION.md shows the stub).
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure (never throws, never aborts);
+ * sc_last_error() returns a thread-local message.  All work is enqueued on the CUDA stream passed to
+ * sc_agent_create (cudaStream_t as void*; NULL = legacy default stream).  Pointers named *_host are
+ * host memory (pinned or pageable), everything else is device memory.  Plain pointers and sizes only.
+ * There is NO CPU fallback: creating an agent without a CUDA device fails with SC_ERR_CUDA.
+ */
+#ifndef SMARTCAL_B200_H
+#define SMARTCAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SC_ABI_VERSION 1
+
+enum { SC_OK = 0, SC_ERR_ARG = 1, SC_ERR_CUDA = 2, SC_ERR_STATE = 3, SC_ERR_UNSUPPORTED = 4 };
+
+/* agent kind: which reference Agent the handle mirrors */
+enum { SC_KIND_SAC = 0 /* enet_sac.py:478 */, SC_KIND_TD3 = 1 /* enet_td3.py:124 */ };
+
+/* network ids (reference attribute names) */
+enum {
+  SC_NET_ACTOR = 0,           /* agent.actor            */
+  SC_NET_CRITIC_1 = 1,        /* agent.critic_1         */
+  SC_NET_CRITIC_2 = 2,        /* agent.critic_2         */
+  SC_NET_TARGET_CRITIC_1 = 3, /* agent.target_critic_1  */
+  SC_NET_TARGET_CRITIC_2 = 4, /* agent.target_critic_2  */
+  SC_NET_TARGET_ACTOR = 5     /* agent.target_actor (TD3 only) */
+};
+
+/* which copy of a network's tensors */
+enum { SC_SLOT_PARAM = 0, SC_SLOT_ADAM_M = 1 /* exp_avg */, SC_SLOT_ADAM_V = 2 /* exp_avg_sq */ };
+
+/* constructor kwargs of the reference Agent (enet_sac.py:479-480, enet_td3.py:125-126) */
+typedef struct sc_config {
+  int32_t abi_version;   /* = SC_ABI_VERSION */
+  int32_t kind;          /* SC_KIND_*                                   */
+  int32_t state_dim;     /* input_dims[0] (= N + N*M = 420 elastic net)  */
+  int32_t n_actions;     /* n_actions                                   */
+  int32_t batch_size;    /* batch_size                                  */
+  int32_t mem_size;      /* max_mem_size (power of two when prioritized) */
+  int32_t prioritized;   /* prioritized (SAC: derived TD3-style wiring) */
+  int32_t use_hint;      /* use_hint                                    */
+  int32_t update_actor_interval; /* TD3 only (enet_td3.py:137)          */
+  int32_t reserved0;
+  /* Python floats of the reference constructor stay doubles so that every derived scalar
+   * (lr/(1-beta1^t), 1-tau, ...) rounds to float32 exactly where torch rounds it */
+  double gamma, tau, lr_actor, lr_critic;
+  double reward_scale;   /* SAC `scale` (enet_sac.py:503); TD3 ignores   */
+  double alpha;          /* SAC temperature (enet_sac.py:501)            */
+  float max_action;      /* 1 in the reference (enet_sac.py:486)         */
+  float per_clip;        /* PER.absolute_error_upper (100, enet_sac.py:212) */
+  float hint_threshold;  /* 0.1  (enet_sac.py:514)                       */
+  float admm_rho;        /* 0.01 (enet_sac.py:516)                       */
+  uint64_t rng_seed;     /* device Philox stream (used when noise pointers are NULL) */
+} sc_config;
+
+typedef struct sc_agent sc_agent;
+
+/* a 2-D view of a tensor inside the agent's HBM arena (row-major, `pitch` floats between rows) */
+typedef struct sc_tensor_info {
+  void* dev_ptr;
+  int64_t rows, cols, pitch;
+  int32_t elem_bytes; /* 4 = float32, 8 = float64 (sum tree), 1 = u8 */
+  int32_t reserved;
+} sc_tensor_info;
+
+/* per-step diagnostics, written to host by sc_agent_learn when `stats_host` != NULL (forces a sync) */
+typedef struct sc_learn_stats {
+  float critic_1_loss, critic_2_loss, actor_loss; /* F.mse_loss / actor_loss of enet_sac.py:580-602 */
+  float q1_mean, q2_mean, target_mean, logp_mean; /* batch means, diagnostics only                   */
+  float gfun, rho;                                /* hint penalty state (enet_sac.py:601,617)        */
+  int32_t learn_counter;                          /* agent.learn_counter AFTER this call             */
+  int32_t did_learn;                              /* 0 when mem_cntr < batch_size (enet_sac.py:556)  */
+  int32_t actor_step;                             /* TD3: whether the delayed actor update ran       */
+} sc_learn_stats;
+
+/* randomness for one learn(); NULL pointers select the on-device Philox stream.
+ * Host arrays reproduce the reference's own RNG streams (see oracle/sac_ref.py header). */
+typedef struct sc_noise {
+  const float* eps_next_host;    /* (B,A) N(0,1): Normal.sample  on s'   (enet_sac.py:570)      */
+  const float* eps_cur_host;     /* (B,A) N(0,1): Normal.rsample on s    (enet_sac.py:589)      */
+  const float* eps_dual_host;    /* (B,A) N(0,1): dual update, every 10th call (enet_sac.py:611) */
+  double td3_target_noise;       /* np.random.normal(scale=0.2) scalar   (enet_td3.py:249)      */
+  int32_t has_td3_target_noise;
+  int32_t reserved;
+} sc_noise;
+
+const char* sc_last_error(void);
+int sc_abi_version(void);
+
+/* ---- lifetime: replaces Agent.__init__ (enet_sac.py:479-521 / enet_td3.py:125-164) ------------------ */
+/* Bytes of HBM the agent needs (nets, Adam moments, targets, replay, sum tree, activation workspace). */
+size_t sc_agent_arena_bytes(const sc_config* cfg);
+/* `arena` may be caller-owned device memory of at least sc_agent_arena_bytes() (e.g. a torch tensor,
+ * 256-byte aligned) or NULL to let the library cudaMalloc it.  Parameters start zeroed: the caller
+ * uploads initial weights through sc_agent_tensor() views, then calls sc_agent_soft_update(tau=1). */
+int sc_agent_create(const sc_config* cfg, void* arena, size_t arena_bytes, void* cuda_stream, sc_agent** out);
+int sc_agent_destroy(sc_agent* a);
+int sc_agent_sync(sc_agent* a); /* cudaStreamSynchronize on the agent's stream */
+
+/* ---- state-dict interop: nn.Module.state_dict()/load_state_dict() of the reference networks ---------- */
+/* `name` is a reference state_dict key ("fc11.weight", "bn3.bias", "fc4mu.weight", ...).  The special
+ * name "*" returns the whole contiguous block of the network (1 x n_floats) -- used for one-shot NCCL
+ * broadcast of actor weights (replaces Learner.get_actor_params, distributed_per_sac.py:84-90). */
+int sc_agent_tensor(sc_agent* a, int net, int slot, const char* name, sc_tensor_info* out);
+/* replay arrays ("state_memory", "new_state_memory", "action_memory", "reward_memory",
+ * "terminal_memory", "hint_memory", "tree" = float64 sum tree) and, for tests, activation workspace
+ * buffers ("c1.h11", "c1.dz12", "y", "q1", ...). */
+int sc_agent_buffer(sc_agent* a, const char* name, sc_tensor_info* out);
+int sc_agent_get_counters(sc_agent* a, int64_t* mem_cntr, int64_t* learn_counter, int64_t* data_pointer, double* per_beta);
+int sc_agent_set_counters(sc_agent* a, int64_t mem_cntr, int64_t learn_counter, int64_t data_pointer, double per_beta);
+int sc_agent_set_scalars(sc_agent* a, float alpha, float rho, float admm_rho);
+
+/* ---- replay: replaces ReplayBuffer.store_transition (enet_sac.py:35-44) and
+ *      PER.store_transition / store_transition_from_buffer (enet_sac.py:237-268) -------------------- */
+/* One packed transition = [state(S) | new_state(S) | action(A) | hint(A) | reward | done] float32.
+ * priority_mode: 0 = uniform buffer (no tree), 1 = PER with error==None (max leaf, or clip if empty),
+ * 2 = PER with `priority` already evaluated by the caller (min((|err|+eps)^alpha, clip)),
+ * 3 = like 2 but the propagated change is formed in float32 (reference behaviour when the reward
+ *     handed to TD3.store_transition is a float32 torch scalar, enet_td3.py:205). */
+int sc_replay_store_host(sc_agent* a, const float* transition_host, int priority_mode, double priority);
+/* n packed transitions already in HBM (e.g. landed by an NCCL gather); stores transition `index`. */
+int sc_replay_store_dev(sc_agent* a, const float* transitions_dev, int index, int priority_mode, double priority);
+/* bulk fill of slots [0,n) from packed host transitions (synthetic benchmarks / checkpoint load) */
+int sc_replay_fill_host(sc_agent* a, const float* transitions_host, int n, const double* priorities_host_or_null);
+
+/* ---- sampling: replaces ReplayBuffer.sample_buffer (enet_sac.py:46-57) and PER.sample_buffer (:270-312) */
+/* indices drawn by the caller's numpy stream (np.random.choice(max_mem,B,replace=False)) */
+int sc_replay_set_batch_host(sc_agent* a, const int32_t* idx_host, int n);
+/* on-device draw without replacement (Philox keys + selection), no host traffic */
+int sc_replay_sample_uniform_dev(sc_agent* a);
+/* stratified proportional sampling on the device sum tree.  u01_host: B float64 uniforms in [0,1) from the
+ * caller's numpy stream, or NULL for device Philox.  Optional host outputs (force a sync when non-NULL). */
+int sc_per_sample(sc_agent* a, const double* u01_host, int32_t* tree_idx_host_out, float* is_weights_host_out);
+/* replaces PER.batch_update (enet_sac.py:314-323): abs errors (B) -> priorities -> tree.  Host arrays. */
+int sc_per_update_host(sc_agent* a, const int32_t* tree_idx_host, const float* abs_err_host, int n, float* priorities_host_out);
+
+/* ---- inference: replaces Agent.choose_action (enet_sac.py:547-553, enet_td3.py:207-220 post-warm-up) */
+/* obs_host: (S) already concatenated (eig|A); eps_host: (A) N(0,1) (SAC) or additive noise (TD3), or NULL
+ * (SAC: device Philox; TD3: no noise).  action_host_out: (A). */
+int sc_agent_act(sc_agent* a, const float* obs_host, const float* eps_host, float* action_host_out);
+
+/* ---- update: replaces Agent.learn (enet_sac.py:555-628, enet_td3.py:222-364) and
+ *      Agent.update_network_parameters (enet_sac.py:523-542) ------------------------------------------ */
+int sc_agent_learn(sc_agent* a, const sc_noise* noise_or_null, sc_learn_stats* stats_host_or_null);
+int sc_agent_soft_update(sc_agent* a, float tau);
+/* kernels launched by this library since the handle was created (bench.py "gpu_launches") */
+int64_t sc_agent_launch_count(sc_agent* a);
+/* CUDA-event time (ms) of the dominant kernel accumulated since the last call with reset!=0 */
+int sc_agent_kernel_time(sc_agent* a, int which, int reset, double* ms_total, int64_t* launches);
+int sc_agent_enable_kernel_timing(sc_agent* a, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMARTCAL_B200_H */

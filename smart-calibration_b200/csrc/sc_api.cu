@@ -1,0 +1,943 @@
+// C ABI of libsmartcal_b200 (see include/smartcal_b200.h): arena layout, step sequencing, host<->device staging.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/smartcal_b200.h"
+#include "sc_params.h"
+
+namespace sc {
+size_t rowphase_smem_bytes();
+int rowphase_pick_cluster_size(int want_clusters);
+cudaError_t launch_rowphase(const RowPhaseParams& p, int cluster_size, int nclusters, cudaStream_t st);
+size_t wgrad_smem_bytes();
+cudaError_t launch_wgrad(const WgradParams& p, int grid, cudaStream_t st);
+cudaError_t launch_soft_update(const float* src, float* dst, size_t n, float tau, cudaStream_t st);
+cudaError_t launch_replay_store(const ReplayP& rp, const float* tr, int slot, int mode, double priority, double clip, cudaStream_t st);
+cudaError_t launch_replay_fill(const ReplayP& rp, const float* tr, int n, cudaStream_t st);
+cudaError_t launch_tree_build(double* tree, int C, const double* pr, int n, cudaStream_t st);
+cudaError_t launch_per_sample(const double* tree, int C, int B, const double* u01, uint64_t seed, uint64_t ctr, double beta,
+                              int* tree_idx, int* data_idx, float* is_w, float* is_wsum, cudaStream_t st);
+cudaError_t launch_per_update(double* tree, int C, int B, const int* idx, const float* err, float clip, float* ps_out, cudaStream_t st);
+cudaError_t launch_sample_uniform(int n, int B, uint64_t seed, uint64_t ctr, int* out, cudaStream_t st);
+cudaError_t launch_fill_normal(float* out, int n, uint64_t seed, uint64_t stream, cudaStream_t st);
+cudaError_t launch_hint_coef(const float* pi, const float* hint, int Ap, const int* bidx, int B, int A, float thr, float admm_rho,
+                             const float* rho, float* out, float* rho_update, cudaStream_t st);
+}  // namespace sc
+
+using namespace sc;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                 \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) return fail(SC_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+static inline int round4i(int x) { return (x + 3) & ~3; }
+
+// ---- network tensor tables (reference state_dict order) -------------------------------
+struct TDesc {
+  std::string name;
+  int rows, cols, pitch;
+  size_t off;   // floats from the start of the network block
+};
+struct NetLayout {
+  std::vector<TDesc> t;
+  size_t size = 0;
+  void add(const char* name, int rows, int cols) {
+    TDesc d{name, rows, cols, round4i(cols), size};
+    size += (size_t)rows * d.pitch;
+    t.push_back(d);
+  }
+  const TDesc* find(const char* name) const {
+    for (auto& d : t)
+      if (d.name == name) return &d;
+    return nullptr;
+  }
+  size_t off(const char* name) const { return find(name)->off; }
+};
+static NetLayout critic_layout(int S, int A) {
+  NetLayout L;
+  L.add("fc11.weight", H1, S); L.add("fc11.bias", 1, H1);
+  L.add("fc12.weight", H2, H1); L.add("fc12.bias", 1, H2);
+  L.add("fc21.weight", HA1, A); L.add("fc21.bias", 1, HA1);
+  L.add("fc22.weight", HA2, HA1); L.add("fc22.bias", 1, HA2);
+  L.add("fc3.weight", 1, HCAT); L.add("fc3.bias", 1, 1);
+  L.add("bn11.weight", 1, H1); L.add("bn11.bias", 1, H1);
+  L.add("bn12.weight", 1, H2); L.add("bn12.bias", 1, H2);
+  L.add("bn21.weight", 1, HA1); L.add("bn21.bias", 1, HA1);
+  L.add("bn22.weight", 1, HA2); L.add("bn22.bias", 1, HA2);
+  return L;
+}
+static NetLayout actor_layout(int S, int A, int kind) {
+  NetLayout L;
+  L.add("fc1.weight", H1, S); L.add("fc1.bias", 1, H1);
+  L.add("fc2.weight", H2, H1); L.add("fc2.bias", 1, H2);
+  L.add("fc3.weight", H3, H2); L.add("fc3.bias", 1, H3);
+  if (kind == SC_KIND_SAC) {
+    L.add("fc4mu.weight", A, H3); L.add("fc4mu.bias", 1, A);
+    L.add("fc4logsigma.weight", A, H3); L.add("fc4logsigma.bias", 1, A);
+  } else {
+    L.add("fc4.weight", A, H3); L.add("fc4.bias", 1, A);
+  }
+  L.add("bn1.weight", 1, H1); L.add("bn1.bias", 1, H1);
+  L.add("bn2.weight", 1, H2); L.add("bn2.bias", 1, H2);
+  L.add("bn3.weight", 1, H3); L.add("bn3.bias", 1, H3);
+  return L;
+}
+static CriticP critic_ptrs(float* b, const NetLayout& L) {
+  CriticP c;
+  c.w11 = b + L.off("fc11.weight"); c.b11 = b + L.off("fc11.bias");
+  c.w12 = b + L.off("fc12.weight"); c.b12 = b + L.off("fc12.bias");
+  c.w21 = b + L.off("fc21.weight"); c.b21 = b + L.off("fc21.bias");
+  c.w22 = b + L.off("fc22.weight"); c.b22 = b + L.off("fc22.bias");
+  c.w3 = b + L.off("fc3.weight"); c.b3 = b + L.off("fc3.bias");
+  c.g11 = b + L.off("bn11.weight"); c.be11 = b + L.off("bn11.bias");
+  c.g12 = b + L.off("bn12.weight"); c.be12 = b + L.off("bn12.bias");
+  c.g21 = b + L.off("bn21.weight"); c.be21 = b + L.off("bn21.bias");
+  c.g22 = b + L.off("bn22.weight"); c.be22 = b + L.off("bn22.bias");
+  return c;
+}
+static ActorP actor_ptrs(float* b, const NetLayout& L, int kind) {
+  ActorP a;
+  a.w1 = b + L.off("fc1.weight"); a.b1 = b + L.off("fc1.bias");
+  a.w2 = b + L.off("fc2.weight"); a.b2 = b + L.off("fc2.bias");
+  a.w3 = b + L.off("fc3.weight"); a.b3 = b + L.off("fc3.bias");
+  if (kind == SC_KIND_SAC) {
+    a.wmu = b + L.off("fc4mu.weight"); a.bmu = b + L.off("fc4mu.bias");
+    a.wls = b + L.off("fc4logsigma.weight"); a.bls = b + L.off("fc4logsigma.bias");
+  } else {
+    a.wmu = b + L.off("fc4.weight"); a.bmu = b + L.off("fc4.bias");
+    a.wls = nullptr; a.bls = nullptr;
+  }
+  a.g1 = b + L.off("bn1.weight"); a.be1 = b + L.off("bn1.bias");
+  a.g2 = b + L.off("bn2.weight"); a.be2 = b + L.off("bn2.bias");
+  a.g3 = b + L.off("bn3.weight"); a.be3 = b + L.off("bn3.bias");
+  return a;
+}
+
+// ---- arena carving ---------------------------------------------------------------------------------------
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base((char*)b) {}
+  void* take(size_t bytes) {
+    off = (off + 255) & ~(size_t)255;
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+  float* f(size_t n) { return (float*)take(n * sizeof(float)); }
+};
+
+struct KernelTimer {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+  double ms = 0;
+  int64_t launches = 0;
+};
+
+struct sc_agent {
+  sc_config cfg;
+  cudaStream_t st;
+  void* arena;
+  bool owns_arena;
+  size_t arena_bytes;
+  int S, Sp, A, Ap, B, C, T;          // T = packed transition length
+  NetLayout Lc, La;
+  size_t online_floats;               // actor + c1 + c2
+  float *params, *adam_m, *adam_v;    // online blocks
+  float* targets;                     // SAC: t1,t2 ; TD3: ta,t1,t2
+  size_t off_actor, off_c1, off_c2;   // within the online block
+  size_t toff_actor, toff_c1, toff_c2;// within the target block
+  ReplayP rp;
+  CriticWs cw[2];
+  TargetWs tw[2];
+  ActorWs aw;
+  std::map<std::string, sc_tensor_info> buffers;
+  float *y, *err, *part, *is_w, *is_wsum, *eps[3], *stats, *hint_out, *rho_dev, *ps_out;
+  int *bidx, *tree_idx;
+  double* u01;
+  float *obs_dev, *act_eps, *act_out, *act_aux, *store_stage;
+  WgradOp *critic_ops, *actor_ops;
+  VecOp *critic_vops, *actor_vops;
+  int n_critic_ops, n_critic_vops, n_actor_ops, n_actor_vops, critic_tiles, actor_tiles;
+  // pinned host staging
+  float* h_stage;                     // max(3*B*A, T, Sp) floats
+  float* h_stats;
+  int32_t* h_idx;
+  double* h_u01;
+  float* h_act;
+  // state
+  int cluster_size, nclusters, wgrad_grid;
+  int64_t mem_cntr, learn_counter, data_pointer, data_length;
+  int64_t t_actor, t_critic;          // Adam step counts
+  double per_beta;
+  bool batch_ready;
+  float alpha, rho, admm_rho;
+  uint64_t noise_ctr;
+  int64_t launches;
+  bool timing;
+  KernelTimer timers[6];
+};
+
+static void timer_begin(sc_agent* a, int which, cudaEvent_t* ev0, cudaEvent_t* ev1) {
+  if (!a->timing) return;
+  KernelTimer& t = a->timers[which];
+  if (t.pool.empty()) {
+    cudaEventCreate(ev0);
+    cudaEventCreate(ev1);
+  } else {
+    *ev0 = t.pool.back().first;
+    *ev1 = t.pool.back().second;
+    t.pool.pop_back();
+  }
+  cudaEventRecord(*ev0, a->st);
+}
+static void timer_end(sc_agent* a, int which, cudaEvent_t ev0, cudaEvent_t ev1) {
+  if (!a->timing) return;
+  cudaEventRecord(ev1, a->st);
+  a->timers[which].pending.push_back({ev0, ev1});
+  a->timers[which].launches++;
+}
+
+// Builds the whole arena layout; with base == nullptr only measures.
+static size_t carve(sc_agent* a, void* base) {
+  Carver cv(base);
+  const int S = a->S, Sp = a->Sp, A = a->A, Ap = a->Ap, B = a->B, C = a->C;
+  const bool td3 = a->cfg.kind == SC_KIND_TD3;
+  a->off_actor = 0;
+  a->off_c1 = a->La.size;
+  a->off_c2 = a->La.size + a->Lc.size;
+  a->online_floats = a->La.size + 2 * a->Lc.size;
+  a->params = cv.f(a->online_floats);
+  a->adam_m = cv.f(a->online_floats);
+  a->adam_v = cv.f(a->online_floats);
+  a->toff_actor = 0;
+  a->toff_c1 = td3 ? a->La.size : 0;
+  a->toff_c2 = a->toff_c1 + a->Lc.size;
+  a->targets = cv.f((td3 ? a->La.size : 0) + 2 * a->Lc.size);
+  // replay
+  ReplayP& rp = a->rp;
+  rp.C = C; rp.S = S; rp.Sp = Sp; rp.A = A; rp.Ap = Ap;
+  rp.state = cv.f((size_t)C * Sp);
+  rp.new_state = cv.f((size_t)C * Sp);
+  rp.action = cv.f((size_t)C * Ap);
+  rp.hint = cv.f((size_t)C * Ap);
+  rp.reward = cv.f(C);
+  rp.done = (uint8_t*)cv.take(C);
+  rp.tree = a->cfg.prioritized ? (double*)cv.take(sizeof(double) * (2 * (size_t)C)) : nullptr;
+  // workspace
+  auto reg = [&](const std::string& name, void* p, int64_t rows, int64_t cols, int64_t pitch, int eb) {
+    sc_tensor_info ti;
+    ti.dev_ptr = p; ti.rows = rows; ti.cols = cols; ti.pitch = pitch; ti.elem_bytes = eb; ti.reserved = 0;
+    a->buffers[name] = ti;
+  };
+  auto mat = [&](const std::string& name, int width) {
+    float* p = cv.f((size_t)B * width);
+    reg(name, p, B, width, width, 4);
+    return p;
+  };
+  for (int k = 0; k < 2; ++k) {
+    const std::string c = k == 0 ? "c1." : "c2.";
+    CriticWs& w = a->cw[k];
+    w.h11 = mat(c + "h11", H1); w.zh11 = mat(c + "zh11", H1); w.rs11 = mat(c + "rs11", 1); w.du11 = mat(c + "du11", H1); w.dz11 = mat(c + "dz11", H1);
+    w.h12 = mat(c + "h12", H2); w.zh12 = mat(c + "zh12", H2); w.rs12 = mat(c + "rs12", 1); w.du12 = mat(c + "du12", H2); w.dz12 = mat(c + "dz12", H2);
+    w.h21 = mat(c + "h21", HA1); w.zh21 = mat(c + "zh21", HA1); w.rs21 = mat(c + "rs21", 1); w.du21 = mat(c + "du21", HA1); w.dz21 = mat(c + "dz21", HA1);
+    w.h22 = mat(c + "h22", HA2); w.zh22 = mat(c + "zh22", HA2); w.rs22 = mat(c + "rs22", 1); w.du22 = mat(c + "du22", HA2); w.dz22 = mat(c + "dz22", HA2);
+    w.q = mat(c + "q", 1); w.dq = mat(c + "dq", 1);
+    w.p_h11 = mat(c + "p_h11", H1); w.p_h12 = mat(c + "p_h12", H2);
+    const std::string t = k == 0 ? "t1." : "t2.";
+    a->tw[k].h11 = mat(t + "h11", H1); a->tw[k].h12 = mat(t + "h12", H2);
+  }
+  ActorWs& aw = a->aw;
+  aw.t_h1 = mat("a.t_h1", H1); aw.t_h2 = mat("a.t_h2", H2);
+  aw.h1 = mat("a.h1", H1); aw.zh1 = mat("a.zh1", H1); aw.rs1 = mat("a.rs1", 1); aw.du1 = mat("a.du1", H1); aw.dz1 = mat("a.dz1", H1);
+  aw.h2 = mat("a.h2", H2); aw.zh2 = mat("a.zh2", H2); aw.rs2 = mat("a.rs2", 1); aw.du2 = mat("a.du2", H2); aw.dz2 = mat("a.dz2", H2);
+  aw.h3 = mat("a.h3", H3); aw.zh3 = mat("a.zh3", H3); aw.rs3 = mat("a.rs3", 1); aw.du3 = mat("a.du3", H3); aw.dz3 = mat("a.dz3", H3);
+  aw.dhead = mat("a.dhead", 2 * A); aw.pi = mat("a.pi", A); aw.logp = mat("a.logp", 1);
+  a->y = mat("y", 1);
+  a->err = mat("err", 1);
+  a->is_w = mat("is_weights", 1);
+  a->ps_out = mat("per_ps", 1);
+  a->part = cv.f((size_t)8 * B * 16 * 2);
+  a->is_wsum = cv.f(4);
+  for (int i = 0; i < 3; ++i) a->eps[i] = cv.f((size_t)B * A);
+  reg("eps_next", a->eps[0], B, A, A, 4);
+  reg("eps_cur", a->eps[1], B, A, A, 4);
+  a->stats = cv.f(16);
+  a->hint_out = cv.f(4);
+  a->rho_dev = cv.f(4);
+  a->bidx = (int*)cv.take(sizeof(int) * B);
+  a->tree_idx = (int*)cv.take(sizeof(int) * B);
+  reg("batch_idx", a->bidx, B, 1, 1, 4);
+  reg("tree_idx", a->tree_idx, B, 1, 1, 4);
+  a->u01 = (double*)cv.take(sizeof(double) * B);
+  a->obs_dev = cv.f(Sp);
+  a->act_eps = cv.f(round4i(A));
+  a->act_out = cv.f(round4i(A));
+  a->act_aux = cv.f(H1 + H2);
+  a->store_stage = cv.f((size_t)a->T * 1);
+  a->critic_ops = (WgradOp*)cv.take(sizeof(WgradOp) * 16);
+  a->actor_ops = (WgradOp*)cv.take(sizeof(WgradOp) * 8);
+  a->critic_vops = (VecOp*)cv.take(sizeof(VecOp) * 32);
+  a->actor_vops = (VecOp*)cv.take(sizeof(VecOp) * 16);
+  reg("state_memory", rp.state, C, S, Sp, 4);
+  reg("new_state_memory", rp.new_state, C, S, Sp, 4);
+  reg("action_memory", rp.action, C, A, Ap, 4);
+  reg("hint_memory", rp.hint, C, A, Ap, 4);
+  reg("reward_memory", rp.reward, C, 1, 1, 4);
+  reg("terminal_memory", rp.done, C, 1, 1, 1);
+  if (rp.tree) reg("tree", rp.tree, 2 * (int64_t)C - 1, 1, 1, 8);
+  return (cv.off + 255) & ~(size_t)255;
+}
+
+static int check_cfg(const sc_config* c) {
+  if (!c) return fail(SC_ERR_ARG, "null config");
+  if (c->abi_version != SC_ABI_VERSION) return fail(SC_ERR_ARG, "abi_version %d != %d", c->abi_version, SC_ABI_VERSION);
+  if (c->kind != SC_KIND_SAC && c->kind != SC_KIND_TD3) return fail(SC_ERR_ARG, "unknown kind %d", c->kind);
+  if (c->state_dim < 1 || c->n_actions < 1 || c->n_actions > AMAX) return fail(SC_ERR_ARG, "state_dim>=1 and 1<=n_actions<=%d required", AMAX);
+  if (c->batch_size < 1 || c->batch_size > 8192) return fail(SC_ERR_ARG, "batch_size must be in [1,8192]");
+  if (c->mem_size < 1) return fail(SC_ERR_ARG, "mem_size must be positive");
+  if (c->prioritized && (c->mem_size & (c->mem_size - 1))) return fail(SC_ERR_ARG, "Capacity must be power of 2.");
+  return SC_OK;
+}
+static void init_dims(sc_agent* a, const sc_config* cfg) {
+  a->cfg = *cfg;
+  a->S = cfg->state_dim; a->Sp = round4i(a->S);
+  a->A = cfg->n_actions; a->Ap = round4i(a->A);
+  a->B = cfg->batch_size; a->C = cfg->mem_size;
+  a->T = 2 * a->S + 2 * a->A + 2;
+  a->Lc = critic_layout(a->S, a->A);
+  a->La = actor_layout(a->S, a->A, cfg->kind);
+}
+
+extern "C" {
+
+const char* sc_last_error(void) { return g_err; }
+int sc_abi_version(void) { return SC_ABI_VERSION; }
+
+size_t sc_agent_arena_bytes(const sc_config* cfg) {
+  if (check_cfg(cfg) != SC_OK) return 0;
+  sc_agent tmp;
+  init_dims(&tmp, cfg);
+  return carve(&tmp, nullptr);
+}
+
+static void add_w(std::vector<WgradOp>& v, int& tiles, const float* D, int ldd, const float* X, int ldx, int gather, int N, int K,
+                  float* W, float* M, float* V, float* T, int ldw, int opt) {
+  WgradOp o;
+  o.D = D; o.ldd = ldd; o.X = X; o.ldx = ldx; o.gather = gather; o.N = N; o.K = K;
+  o.W = W; o.M = M; o.V = V; o.T = T; o.ldw = ldw;
+  o.tiles_k = (K + 31) / 32;
+  o.tile_base = tiles;
+  o.tile_count = ((N + 31) / 32) * o.tiles_k;
+  o.opt = opt;
+  tiles += o.tile_count;
+  v.push_back(o);
+}
+static void add_v(std::vector<VecOp>& v, int& tiles, const float* D, const float* E, int ld, int N, float* P, float* M, float* V,
+                  float* T, int opt) {
+  VecOp o;
+  o.D = D; o.E = E; o.ld = ld; o.N = N; o.P = P; o.M = M; o.V = V; o.T = T;
+  o.tile_base = tiles;
+  o.tile_count = (N + 31) / 32;
+  o.opt = opt;
+  tiles += o.tile_count;
+  v.push_back(o);
+}
+
+static int build_op_tables(sc_agent* a) {
+  const bool td3 = a->cfg.kind == SC_KIND_TD3;
+  std::vector<WgradOp> cw;
+  std::vector<VecOp> cv;
+  int tiles = 0;
+  for (int k = 0; k < 2; ++k) {
+    const size_t off = k == 0 ? a->off_c1 : a->off_c2;
+    const size_t toff = k == 0 ? a->toff_c1 : a->toff_c2;
+    CriticP P = critic_ptrs(a->params + off, a->Lc), M = critic_ptrs(a->adam_m + off, a->Lc), V = critic_ptrs(a->adam_v + off, a->Lc),
+            T = critic_ptrs(a->targets + toff, a->Lc);
+    const CriticWs& w = a->cw[k];
+    const int opt = 1 + k;
+    add_w(cw, tiles, w.dz11, H1, a->rp.state, a->Sp, 1, H1, a->S, P.w11, M.w11, V.w11, T.w11, a->Sp, opt);
+    add_w(cw, tiles, w.dz12, H2, w.h11, H1, 0, H2, H1, P.w12, M.w12, V.w12, T.w12, H1, opt);
+    add_w(cw, tiles, w.dz21, HA1, a->rp.action, a->Ap, 1, HA1, a->A, P.w21, M.w21, V.w21, T.w21, a->Ap, opt);
+    add_w(cw, tiles, w.dz22, HA2, w.h21, HA1, 0, HA2, HA1, P.w22, M.w22, V.w22, T.w22, HA1, opt);
+    add_w(cw, tiles, w.dq, 1, w.h12, H2, 0, 1, H2, P.w3, M.w3, V.w3, T.w3, HCAT, opt);
+    add_w(cw, tiles, w.dq, 1, w.h22, HA2, 0, 1, HA2, P.w3 + H2, M.w3 + H2, V.w3 + H2, T.w3 + H2, HCAT, opt);
+    add_v(cv, tiles, w.dz11, nullptr, H1, H1, P.b11, M.b11, V.b11, T.b11, opt);
+    add_v(cv, tiles, w.du11, w.zh11, H1, H1, P.g11, M.g11, V.g11, T.g11, opt);
+    add_v(cv, tiles, w.du11, nullptr, H1, H1, P.be11, M.be11, V.be11, T.be11, opt);
+    add_v(cv, tiles, w.dz12, nullptr, H2, H2, P.b12, M.b12, V.b12, T.b12, opt);
+    add_v(cv, tiles, w.du12, w.zh12, H2, H2, P.g12, M.g12, V.g12, T.g12, opt);
+    add_v(cv, tiles, w.du12, nullptr, H2, H2, P.be12, M.be12, V.be12, T.be12, opt);
+    add_v(cv, tiles, w.dz21, nullptr, HA1, HA1, P.b21, M.b21, V.b21, T.b21, opt);
+    add_v(cv, tiles, w.du21, w.zh21, HA1, HA1, P.g21, M.g21, V.g21, T.g21, opt);
+    add_v(cv, tiles, w.du21, nullptr, HA1, HA1, P.be21, M.be21, V.be21, T.be21, opt);
+    add_v(cv, tiles, w.dz22, nullptr, HA2, HA2, P.b22, M.b22, V.b22, T.b22, opt);
+    add_v(cv, tiles, w.du22, w.zh22, HA2, HA2, P.g22, M.g22, V.g22, T.g22, opt);
+    add_v(cv, tiles, w.du22, nullptr, HA2, HA2, P.be22, M.be22, V.be22, T.be22, opt);
+    add_v(cv, tiles, w.dq, nullptr, 1, 1, P.b3, M.b3, V.b3, T.b3, opt);
+  }
+  a->n_critic_ops = (int)cw.size(); a->n_critic_vops = (int)cv.size(); a->critic_tiles = tiles;
+  CK(cudaMemcpyAsync(a->critic_ops, cw.data(), cw.size() * sizeof(WgradOp), cudaMemcpyHostToDevice, a->st));
+  CK(cudaMemcpyAsync(a->critic_vops, cv.data(), cv.size() * sizeof(VecOp), cudaMemcpyHostToDevice, a->st));
+
+  std::vector<WgradOp> awv;
+  std::vector<VecOp> avv;
+  tiles = 0;
+  {
+    ActorP P = actor_ptrs(a->params + a->off_actor, a->La, a->cfg.kind), M = actor_ptrs(a->adam_m + a->off_actor, a->La, a->cfg.kind),
+           V = actor_ptrs(a->adam_v + a->off_actor, a->La, a->cfg.kind);
+    ActorP T;
+    memset(&T, 0, sizeof(T));
+    if (td3) T = actor_ptrs(a->targets + a->toff_actor, a->La, a->cfg.kind);
+    const ActorWs& w = a->aw;
+    const int A = a->A, ldh = td3 ? A : 2 * A;
+    add_w(awv, tiles, w.dz1, H1, a->rp.state, a->Sp, 1, H1, a->S, P.w1, M.w1, V.w1, T.w1, a->Sp, 0);
+    add_w(awv, tiles, w.dz2, H2, w.h1, H1, 0, H2, H1, P.w2, M.w2, V.w2, T.w2, H1, 0);
+    add_w(awv, tiles, w.dz3, H3, w.h2, H2, 0, H3, H2, P.w3, M.w3, V.w3, T.w3, H2, 0);
+    add_w(awv, tiles, w.dhead, ldh, w.h3, H3, 0, A, H3, P.wmu, M.wmu, V.wmu, T.wmu, H3, 0);
+    if (!td3) add_w(awv, tiles, w.dhead + A, ldh, w.h3, H3, 0, A, H3, P.wls, M.wls, V.wls, T.wls, H3, 0);
+    add_v(avv, tiles, w.dz1, nullptr, H1, H1, P.b1, M.b1, V.b1, T.b1, 0);
+    add_v(avv, tiles, w.du1, w.zh1, H1, H1, P.g1, M.g1, V.g1, T.g1, 0);
+    add_v(avv, tiles, w.du1, nullptr, H1, H1, P.be1, M.be1, V.be1, T.be1, 0);
+    add_v(avv, tiles, w.dz2, nullptr, H2, H2, P.b2, M.b2, V.b2, T.b2, 0);
+    add_v(avv, tiles, w.du2, w.zh2, H2, H2, P.g2, M.g2, V.g2, T.g2, 0);
+    add_v(avv, tiles, w.du2, nullptr, H2, H2, P.be2, M.be2, V.be2, T.be2, 0);
+    add_v(avv, tiles, w.dz3, nullptr, H3, H3, P.b3, M.b3, V.b3, T.b3, 0);
+    add_v(avv, tiles, w.du3, w.zh3, H3, H3, P.g3, M.g3, V.g3, T.g3, 0);
+    add_v(avv, tiles, w.du3, nullptr, H3, H3, P.be3, M.be3, V.be3, T.be3, 0);
+    add_v(avv, tiles, w.dhead, nullptr, ldh, A, P.bmu, M.bmu, V.bmu, T.bmu, 0);
+    if (!td3) add_v(avv, tiles, w.dhead + A, nullptr, ldh, A, P.bls, M.bls, V.bls, T.bls, 0);
+  }
+  a->n_actor_ops = (int)awv.size(); a->n_actor_vops = (int)avv.size(); a->actor_tiles = tiles;
+  CK(cudaMemcpyAsync(a->actor_ops, awv.data(), awv.size() * sizeof(WgradOp), cudaMemcpyHostToDevice, a->st));
+  CK(cudaMemcpyAsync(a->actor_vops, avv.data(), avv.size() * sizeof(VecOp), cudaMemcpyHostToDevice, a->st));
+  CK(cudaStreamSynchronize(a->st));
+  return SC_OK;
+}
+
+int sc_agent_create(const sc_config* cfg, void* arena, size_t arena_bytes, void* cuda_stream, sc_agent** out) {
+  if (!out) return fail(SC_ERR_ARG, "null out");
+  *out = nullptr;
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(SC_ERR_CUDA, "no CUDA device: libsmartcal_b200 has no CPU fallback");
+  }
+  cudaDeviceProp prop;
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  CK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 9) return fail(SC_ERR_CUDA, "compute capability %d.%d lacks thread-block clusters (built for sm_100a)", prop.major, prop.minor);
+  sc_agent* a = new sc_agent();
+  init_dims(a, cfg);
+  a->st = (cudaStream_t)cuda_stream;
+  const size_t need = carve(a, nullptr);
+  if (arena) {
+    if (arena_bytes < need) { delete a; return fail(SC_ERR_ARG, "arena too small: %zu < %zu", arena_bytes, need); }
+    if (((uintptr_t)arena) & 255) { delete a; return fail(SC_ERR_ARG, "arena must be 256-byte aligned"); }
+    a->arena = arena; a->owns_arena = false;
+  } else {
+    cudaError_t e = cudaMalloc(&a->arena, need);
+    if (e != cudaSuccess) { delete a; return fail(SC_ERR_CUDA, "cudaMalloc(%zu): %s", need, cudaGetErrorString(e)); }
+    a->owns_arena = true;
+  }
+  a->arena_bytes = need;
+  a->buffers.clear();
+  carve(a, a->arena);
+  CK(cudaMemsetAsync(a->arena, 0, need, a->st));
+  const size_t stage_floats = (size_t)3 * a->B * a->A + a->T + a->Sp + 64;
+  CK(cudaHostAlloc((void**)&a->h_stage, stage_floats * sizeof(float), cudaHostAllocDefault));
+  CK(cudaHostAlloc((void**)&a->h_stats, 16 * sizeof(float), cudaHostAllocDefault));
+  CK(cudaHostAlloc((void**)&a->h_idx, (size_t)a->B * sizeof(int32_t), cudaHostAllocDefault));
+  CK(cudaHostAlloc((void**)&a->h_u01, (size_t)a->B * sizeof(double), cudaHostAllocDefault));
+  CK(cudaHostAlloc((void**)&a->h_act, 64 * sizeof(float), cudaHostAllocDefault));
+  a->cluster_size = rowphase_pick_cluster_size(8);
+  a->nclusters = a->cluster_size == 16 ? 8 : 16;        // ~128 CTAs on the 148 SMs
+  while ((a->B + a->nclusters - 1) / a->nclusters > 128) a->nclusters *= 2;
+  if (a->cluster_size == 0) { sc_agent_destroy(a); return fail(SC_ERR_CUDA, "device cannot host an 8-CTA cluster with %zu B of shared memory", rowphase_smem_bytes()); }
+  a->wgrad_grid = prop.multiProcessorCount * 2;
+  a->mem_cntr = a->learn_counter = a->data_pointer = a->data_length = 0;
+  a->t_actor = a->t_critic = 0;
+  a->per_beta = 0.4;   // PER.beta, enet_sac.py:210
+  a->batch_ready = false;
+  a->alpha = (float)cfg->alpha;
+  a->rho = 0.f;
+  a->admm_rho = cfg->admm_rho;
+  a->noise_ctr = 0;
+  a->launches = 0;
+  a->timing = false;
+  rc = build_op_tables(a);
+  if (rc) { sc_agent_destroy(a); return rc; }
+  *out = a;
+  return SC_OK;
+}
+
+int sc_agent_destroy(sc_agent* a) {
+  if (!a) return SC_OK;
+  cudaStreamSynchronize(a->st);
+  for (auto& t : a->timers) {
+    for (auto& p : t.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto& p : t.pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  }
+  if (a->h_stage) cudaFreeHost(a->h_stage);
+  if (a->h_stats) cudaFreeHost(a->h_stats);
+  if (a->h_idx) cudaFreeHost(a->h_idx);
+  if (a->h_u01) cudaFreeHost(a->h_u01);
+  if (a->h_act) cudaFreeHost(a->h_act);
+  if (a->owns_arena && a->arena) cudaFree(a->arena);
+  delete a;
+  return SC_OK;
+}
+
+int sc_agent_sync(sc_agent* a) {
+  if (!a) return fail(SC_ERR_ARG, "null agent");
+  CK(cudaStreamSynchronize(a->st));
+  return SC_OK;
+}
+
+static float* net_base(sc_agent* a, int net, int slot, const NetLayout** L) {
+  const bool td3 = a->cfg.kind == SC_KIND_TD3;
+  float* online = slot == SC_SLOT_PARAM ? a->params : slot == SC_SLOT_ADAM_M ? a->adam_m : a->adam_v;
+  switch (net) {
+    case SC_NET_ACTOR: *L = &a->La; return online + a->off_actor;
+    case SC_NET_CRITIC_1: *L = &a->Lc; return online + a->off_c1;
+    case SC_NET_CRITIC_2: *L = &a->Lc; return online + a->off_c2;
+    case SC_NET_TARGET_CRITIC_1: *L = &a->Lc; return slot == SC_SLOT_PARAM ? a->targets + a->toff_c1 : nullptr;
+    case SC_NET_TARGET_CRITIC_2: *L = &a->Lc; return slot == SC_SLOT_PARAM ? a->targets + a->toff_c2 : nullptr;
+    case SC_NET_TARGET_ACTOR: *L = &a->La; return (td3 && slot == SC_SLOT_PARAM) ? a->targets + a->toff_actor : nullptr;
+  }
+  return nullptr;
+}
+
+int sc_agent_tensor(sc_agent* a, int net, int slot, const char* name, sc_tensor_info* out) {
+  if (!a || !name || !out) return fail(SC_ERR_ARG, "null argument");
+  if (slot < 0 || slot > 2) return fail(SC_ERR_ARG, "bad slot %d", slot);
+  const NetLayout* L = nullptr;
+  float* base = net_base(a, net, slot, &L);
+  if (!base) return fail(SC_ERR_ARG, "network %d / slot %d does not exist for this agent kind", net, slot);
+  if (strcmp(name, "*") == 0) {
+    out->dev_ptr = base; out->rows = 1; out->cols = (int64_t)L->size; out->pitch = (int64_t)L->size; out->elem_bytes = 4; out->reserved = 0;
+    return SC_OK;
+  }
+  const TDesc* d = L->find(name);
+  if (!d) return fail(SC_ERR_ARG, "unknown tensor '%s'", name);
+  out->dev_ptr = base + d->off; out->rows = d->rows; out->cols = d->cols; out->pitch = d->pitch; out->elem_bytes = 4; out->reserved = 0;
+  return SC_OK;
+}
+
+int sc_agent_buffer(sc_agent* a, const char* name, sc_tensor_info* out) {
+  if (!a || !name || !out) return fail(SC_ERR_ARG, "null argument");
+  auto it = a->buffers.find(name);
+  if (it == a->buffers.end()) return fail(SC_ERR_ARG, "unknown buffer '%s'", name);
+  *out = it->second;
+  return SC_OK;
+}
+
+int sc_agent_get_counters(sc_agent* a, int64_t* mem_cntr, int64_t* learn_counter, int64_t* data_pointer, double* per_beta) {
+  if (!a) return fail(SC_ERR_ARG, "null agent");
+  if (mem_cntr) *mem_cntr = a->mem_cntr;
+  if (learn_counter) *learn_counter = a->learn_counter;
+  if (data_pointer) *data_pointer = a->data_pointer;
+  if (per_beta) *per_beta = a->per_beta;
+  return SC_OK;
+}
+int sc_agent_set_counters(sc_agent* a, int64_t mem_cntr, int64_t learn_counter, int64_t data_pointer, double per_beta) {
+  if (!a) return fail(SC_ERR_ARG, "null agent");
+  a->mem_cntr = mem_cntr; a->learn_counter = learn_counter; a->data_pointer = data_pointer; a->per_beta = per_beta;
+  a->data_length = mem_cntr < a->C ? mem_cntr : a->C;
+  return SC_OK;
+}
+int sc_agent_set_scalars(sc_agent* a, float alpha, float rho, float admm_rho) {
+  if (!a) return fail(SC_ERR_ARG, "null agent");
+  a->alpha = alpha; a->rho = rho; a->admm_rho = admm_rho;
+  CK(cudaStreamSynchronize(a->st));
+  CK(cudaMemcpy(a->rho_dev, &rho, sizeof(float), cudaMemcpyHostToDevice));   // rho evolves on the device
+  return SC_OK;
+}
+
+// ---- replay ----------------------------------------------------------------------------------------------
+static int store_common(sc_agent* a, const float* tr_dev, int priority_mode, double priority) {
+  int slot;
+  if (a->cfg.prioritized) {
+    if (priority_mode == 0) priority_mode = 1;
+    slot = (int)a->data_pointer;
+    a->data_pointer = (a->data_pointer + 1) % a->C;
+    if (a->data_length < a->C) a->data_length++;
+  } else {
+    priority_mode = 0;
+    slot = (int)(a->mem_cntr % a->C);
+  }
+  CK(launch_replay_store(a->rp, tr_dev, slot, priority_mode, priority, (double)a->cfg.per_clip, a->st));
+  a->launches++;
+  a->mem_cntr++;
+  return SC_OK;
+}
+int sc_replay_store_host(sc_agent* a, const float* transition_host, int priority_mode, double priority) {
+  if (!a || !transition_host) return fail(SC_ERR_ARG, "null argument");
+  // the staging slot is reused by the next call: wait for the previous copy-out kernel (one tiny sync per env step)
+  CK(cudaStreamSynchronize(a->st));
+  memcpy(a->h_stage, transition_host, (size_t)a->T * sizeof(float));
+  CK(cudaMemcpyAsync(a->store_stage, a->h_stage, (size_t)a->T * sizeof(float), cudaMemcpyHostToDevice, a->st));
+  return store_common(a, a->store_stage, priority_mode, priority);
+}
+int sc_replay_store_dev(sc_agent* a, const float* transitions_dev, int index, int priority_mode, double priority) {
+  if (!a || !transitions_dev || index < 0) return fail(SC_ERR_ARG, "bad argument");
+  return store_common(a, transitions_dev + (size_t)index * a->T, priority_mode, priority);
+}
+int sc_replay_fill_host(sc_agent* a, const float* transitions_host, int n, const double* priorities_host) {
+  if (!a || !transitions_host || n < 0 || n > a->C) return fail(SC_ERR_ARG, "bad argument");
+  float* tmp = nullptr;
+  CK(cudaMalloc(&tmp, (size_t)n * a->T * sizeof(float)));
+  CK(cudaMemcpyAsync(tmp, transitions_host, (size_t)n * a->T * sizeof(float), cudaMemcpyHostToDevice, a->st));
+  CK(launch_replay_fill(a->rp, tmp, n, a->st));
+  a->launches++;
+  if (a->rp.tree) {
+    double* pr = nullptr;
+    CK(cudaMalloc(&pr, (size_t)a->C * sizeof(double)));
+    std::vector<double> h(a->C, 0.0);
+    for (int i = 0; i < n; ++i) h[i] = priorities_host ? priorities_host[i] : (double)a->cfg.per_clip;
+    CK(cudaMemcpyAsync(pr, h.data(), (size_t)a->C * sizeof(double), cudaMemcpyHostToDevice, a->st));
+    CK(launch_tree_build(a->rp.tree, a->C, pr, n, a->st));
+    a->launches++;
+    CK(cudaStreamSynchronize(a->st));
+    cudaFree(pr);
+  }
+  CK(cudaStreamSynchronize(a->st));
+  cudaFree(tmp);
+  a->mem_cntr = n;
+  a->data_pointer = n % a->C;
+  a->data_length = n;
+  return SC_OK;
+}
+
+int sc_replay_set_batch_host(sc_agent* a, const int32_t* idx_host, int n) {
+  if (!a || !idx_host || n != a->B) return fail(SC_ERR_ARG, "expected %d indices", a ? a->B : 0);
+  CK(cudaStreamSynchronize(a->st));   // h_idx may still be in flight from the previous step
+  memcpy(a->h_idx, idx_host, (size_t)n * sizeof(int32_t));
+  CK(cudaMemcpyAsync(a->bidx, a->h_idx, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, a->st));
+  a->batch_ready = true;
+  return SC_OK;
+}
+int sc_replay_sample_uniform_dev(sc_agent* a) {
+  if (!a) return fail(SC_ERR_ARG, "null agent");
+  const int n = (int)(a->mem_cntr < a->C ? a->mem_cntr : a->C);
+  if (n < a->B) return fail(SC_ERR_STATE, "only %d transitions stored, batch is %d", n, a->B);
+  CK(launch_sample_uniform(n, a->B, a->cfg.rng_seed, 0x5000000000ull + (a->noise_ctr++), a->bidx, a->st));
+  a->launches++;
+  a->batch_ready = true;
+  return SC_OK;
+}
+int sc_per_sample(sc_agent* a, const double* u01_host, int32_t* tree_idx_host_out, float* is_weights_host_out) {
+  if (!a) return fail(SC_ERR_ARG, "null agent");
+  if (!a->rp.tree) return fail(SC_ERR_STATE, "agent was created with prioritized=0");
+  const double* u = nullptr;
+  if (u01_host) {
+    CK(cudaStreamSynchronize(a->st));
+    memcpy(a->h_u01, u01_host, (size_t)a->B * sizeof(double));
+    CK(cudaMemcpyAsync(a->u01, a->h_u01, (size_t)a->B * sizeof(double), cudaMemcpyHostToDevice, a->st));
+    u = a->u01;
+  }
+  a->per_beta = fmin(1.0, a->per_beta + 1e-4);   // enet_sac.py:288
+  cudaEvent_t e0, e1;
+  timer_begin(a, 4, &e0, &e1);
+  CK(launch_per_sample(a->rp.tree, a->C, a->B, u, a->cfg.rng_seed, 0x6000000000ull + (a->noise_ctr++), a->per_beta, a->tree_idx,
+                       a->bidx, a->is_w, a->is_wsum, a->st));
+  timer_end(a, 4, e0, e1);
+  a->launches++;
+  a->batch_ready = true;
+  if (tree_idx_host_out) CK(cudaMemcpyAsync(tree_idx_host_out, a->tree_idx, (size_t)a->B * sizeof(int32_t), cudaMemcpyDeviceToHost, a->st));
+  if (is_weights_host_out) CK(cudaMemcpyAsync(is_weights_host_out, a->is_w, (size_t)a->B * sizeof(float), cudaMemcpyDeviceToHost, a->st));
+  if (tree_idx_host_out || is_weights_host_out) CK(cudaStreamSynchronize(a->st));
+  return SC_OK;
+}
+int sc_per_update_host(sc_agent* a, const int32_t* tree_idx_host, const float* abs_err_host, int n, float* priorities_host_out) {
+  if (!a || !tree_idx_host || !abs_err_host || n != a->B) return fail(SC_ERR_ARG, "bad argument");
+  if (!a->rp.tree) return fail(SC_ERR_STATE, "agent was created with prioritized=0");
+  CK(cudaMemcpyAsync(a->tree_idx, tree_idx_host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, a->st));
+  CK(cudaMemcpyAsync(a->err, abs_err_host, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, a->st));
+  CK(launch_per_update(a->rp.tree, a->C, n, a->tree_idx, a->err, a->cfg.per_clip, a->ps_out, a->st));
+  a->launches++;
+  if (priorities_host_out) CK(cudaMemcpyAsync(priorities_host_out, a->ps_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, a->st));
+  CK(cudaStreamSynchronize(a->st));
+  return SC_OK;
+}
+
+// ---- kernel parameter assembly -----------------------------------------------------------------------------
+static void fill_common(sc_agent* a, RowPhaseParams& p) {
+  memset(&p, 0, sizeof(p));
+  p.kind = a->cfg.kind;
+  p.B = a->B; p.S = a->S; p.Sp = a->Sp; p.A = a->A; p.Ap = a->Ap;
+  p.crit[0] = critic_ptrs(a->params + a->off_c1, a->Lc);
+  p.crit[1] = critic_ptrs(a->params + a->off_c2, a->Lc);
+  p.targ[0] = critic_ptrs(a->targets + a->toff_c1, a->Lc);
+  p.targ[1] = critic_ptrs(a->targets + a->toff_c2, a->Lc);
+  p.cw[0] = a->cw[0]; p.cw[1] = a->cw[1];
+  p.tw[0] = a->tw[0]; p.tw[1] = a->tw[1];
+  p.aw = a->aw;
+  p.rp = a->rp;
+  p.bidx = a->bidx;
+  p.is_wsum = a->cfg.prioritized ? a->is_wsum : nullptr;
+  p.y = a->y; p.err = a->err; p.part = a->part;
+  p.gamma = (float)a->cfg.gamma;
+  p.scale = (float)a->cfg.reward_scale;
+  p.alpha = a->alpha;
+  p.maxa = a->cfg.max_action;
+  p.n_q = a->cfg.kind == SC_KIND_SAC ? 2 : 1;
+}
+static AdamHyper adam_hyper(double lr, int64_t t) {
+  // torch/optim/adam.py::_single_tensor_adam scalar math, in double like Python floats
+  const double b1 = 0.9, b2 = 0.999;
+  const double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
+  AdamHyper h;
+  h.lr_neg_step = (float)(-(lr / bc1));
+  h.bc2_sqrt = (float)sqrt(bc2);
+  h.one_minus_b1 = (float)(1.0 - b1);
+  h.b2 = (float)b2;
+  h.one_minus_b2 = (float)(1.0 - b2);
+  h.eps = 1e-8f;
+  return h;
+}
+static void fill_wgrad(sc_agent* a, WgradParams& w, bool actor, int do_soft, int stats_mode) {
+  memset(&w, 0, sizeof(w));
+  w.ops = actor ? a->actor_ops : a->critic_ops;
+  w.nops = actor ? a->n_actor_ops : a->n_critic_ops;
+  w.vops = actor ? a->actor_vops : a->critic_vops;
+  w.nvops = actor ? a->n_actor_vops : a->n_critic_vops;
+  w.total_tiles = actor ? a->actor_tiles : a->critic_tiles;
+  w.B = a->B;
+  w.bidx = a->bidx;
+  w.hyper[0] = adam_hyper(a->cfg.lr_actor, a->t_actor);
+  w.hyper[1] = adam_hyper(a->cfg.lr_critic, a->t_critic);
+  w.hyper[2] = w.hyper[1];
+  w.tau = (float)a->cfg.tau;
+  w.one_minus_tau = (float)(1.0 - a->cfg.tau);
+  w.do_soft = do_soft;
+  w.stats_mode = stats_mode;
+  w.q1 = a->cw[0].q; w.q2 = a->cw[1].q; w.y = a->y;
+  w.logp = a->cfg.kind == SC_KIND_SAC ? a->aw.logp : nullptr;
+  w.pi_q = a->cw[0].q;
+  w.is_wsum = a->cfg.prioritized ? a->is_wsum : nullptr;
+  w.stats = a->stats;
+  w.alpha = a->cfg.kind == SC_KIND_SAC ? a->alpha : 0.f;
+}
+
+static int run_rowphase(sc_agent* a, const RowPhaseParams& p, int timer_id) {
+  cudaEvent_t e0, e1;
+  if (timer_id >= 0) timer_begin(a, timer_id, &e0, &e1);
+  const int ncl = p.program == PROG_ACT ? 1 : a->nclusters;
+  CK(launch_rowphase(p, a->cluster_size, ncl, a->st));
+  if (timer_id >= 0) timer_end(a, timer_id, e0, e1);
+  a->launches++;
+  return SC_OK;
+}
+static int run_wgrad(sc_agent* a, const WgradParams& w, int timer_id) {
+  cudaEvent_t e0, e1;
+  timer_begin(a, timer_id, &e0, &e1);
+  int grid = a->wgrad_grid;
+  if (grid > w.total_tiles + 1) grid = w.total_tiles + 1;
+  CK(launch_wgrad(w, grid, a->st));
+  timer_end(a, timer_id, e0, e1);
+  a->launches++;
+  return SC_OK;
+}
+
+int sc_agent_act(sc_agent* a, const float* obs_host, const float* eps_host, float* action_host_out) {
+  if (!a || !obs_host || !action_host_out) return fail(SC_ERR_ARG, "null argument");
+  CK(cudaStreamSynchronize(a->st));
+  float* h = a->h_stage;
+  memset(h, 0, (size_t)a->Sp * sizeof(float));
+  memcpy(h, obs_host, (size_t)a->S * sizeof(float));
+  CK(cudaMemcpyAsync(a->obs_dev, h, (size_t)a->Sp * sizeof(float), cudaMemcpyHostToDevice, a->st));
+  RowPhaseParams p;
+  fill_common(a, p);
+  p.program = PROG_ACT;
+  p.B = 1;
+  p.actor = actor_ptrs(a->params + a->off_actor, a->La, a->cfg.kind);
+  p.obs = a->obs_dev;
+  p.act_out = a->act_out;
+  p.act_aux = a->act_aux;
+  if (eps_host) {
+    memcpy(a->h_act, eps_host, (size_t)a->A * sizeof(float));
+    CK(cudaMemcpyAsync(a->act_eps, a->h_act, (size_t)a->A * sizeof(float), cudaMemcpyHostToDevice, a->st));
+    p.eps = a->act_eps;
+  } else if (a->cfg.kind == SC_KIND_SAC) {
+    CK(launch_fill_normal(a->act_eps, a->A, a->cfg.rng_seed, 0x7000000000ull + (a->noise_ctr++), a->st));
+    a->launches++;
+    p.eps = a->act_eps;
+  }
+  int rc = run_rowphase(a, p, -1);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(a->h_act + 32, a->act_out, (size_t)a->A * sizeof(float), cudaMemcpyDeviceToHost, a->st));
+  CK(cudaStreamSynchronize(a->st));
+  memcpy(action_host_out, a->h_act + 32, (size_t)a->A * sizeof(float));
+  return SC_OK;
+}
+
+int sc_agent_soft_update(sc_agent* a, float tau) {
+  if (!a) return fail(SC_ERR_ARG, "null agent");
+  const bool td3 = a->cfg.kind == SC_KIND_TD3;
+  CK(launch_soft_update(a->params + a->off_c1, a->targets + a->toff_c1, a->Lc.size, tau, a->st));
+  CK(launch_soft_update(a->params + a->off_c2, a->targets + a->toff_c2, a->Lc.size, tau, a->st));
+  a->launches += 2;
+  if (td3) {
+    CK(launch_soft_update(a->params + a->off_actor, a->targets + a->toff_actor, a->La.size, tau, a->st));
+    a->launches++;
+  }
+  return SC_OK;
+}
+
+static int upload_noise(sc_agent* a, const float* host, int slot, uint64_t stream_tag) {
+  const size_t n = (size_t)a->B * a->A;
+  if (host) {
+    float* h = a->h_stage + (size_t)slot * n;
+    memcpy(h, host, n * sizeof(float));
+    CK(cudaMemcpyAsync(a->eps[slot], h, n * sizeof(float), cudaMemcpyHostToDevice, a->st));
+  } else {
+    CK(launch_fill_normal(a->eps[slot], (int)n, a->cfg.rng_seed, stream_tag + (a->noise_ctr++), a->st));
+    a->launches++;
+  }
+  return SC_OK;
+}
+
+int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_host) {
+  if (!a) return fail(SC_ERR_ARG, "null agent");
+  if (stats_host) memset(stats_host, 0, sizeof(*stats_host));
+  if (a->mem_cntr < a->B) {   // enet_sac.py:556-557
+    if (stats_host) stats_host->learn_counter = (int32_t)a->learn_counter;
+    return SC_OK;
+  }
+  const bool sac = a->cfg.kind == SC_KIND_SAC;
+  const bool per = a->cfg.prioritized != 0;
+  int rc;
+  if (!a->batch_ready) {
+    rc = per ? sc_per_sample(a, nullptr, nullptr, nullptr) : sc_replay_sample_uniform_dev(a);
+    if (rc) return rc;
+  }
+  a->batch_ready = false;
+  const bool host_noise = noise && (noise->eps_next_host || noise->eps_cur_host || noise->eps_dual_host);
+  if (host_noise) CK(cudaStreamSynchronize(a->st));   // staging buffers may be in flight
+  if (sac) {
+    if ((rc = upload_noise(a, noise ? noise->eps_next_host : nullptr, 0, 0x1000000000ull))) return rc;
+    if ((rc = upload_noise(a, noise ? noise->eps_cur_host : nullptr, 1, 0x2000000000ull))) return rc;
+  }
+  // ---- critic phase ----
+  RowPhaseParams p;
+  fill_common(a, p);
+  p.program = PROG_CRITIC;
+  if (sac) {
+    p.actor = actor_ptrs(a->params + a->off_actor, a->La, a->cfg.kind);
+    p.eps = a->eps[0];
+  } else {
+    p.actor = actor_ptrs(a->targets + a->toff_actor, a->La, a->cfg.kind);
+    double nz = 0.0;
+    if (noise && noise->has_td3_target_noise) nz = noise->td3_target_noise;
+    nz = nz < -0.5 ? -0.5 : (nz > 0.5 ? 0.5 : nz);          // enet_td3.py:249 clamp in float64, cast with the add
+    p.td3_noise_c = (float)nz;
+  }
+  if ((rc = run_rowphase(a, p, 0))) return rc;
+  if (per) {
+    cudaEvent_t e0, e1;
+    timer_begin(a, 5, &e0, &e1);
+    CK(launch_per_update(a->rp.tree, a->C, a->B, a->tree_idx, a->err, a->cfg.per_clip, a->ps_out, a->st));
+    timer_end(a, 5, e0, e1);
+    a->launches++;
+  }
+  bool actor_step = true;
+  if (!sac) actor_step = ((a->learn_counter + 1) % (a->cfg.update_actor_interval > 0 ? a->cfg.update_actor_interval : 1)) == 0;
+  a->t_critic++;
+  WgradParams w;
+  fill_wgrad(a, w, false, actor_step ? 1 : 0, 1);
+  if ((rc = run_wgrad(a, w, 1))) return rc;
+  // ---- actor phase ----
+  if (actor_step) {
+    fill_common(a, p);
+    p.program = PROG_ACTOR;
+    p.actor = actor_ptrs(a->params + a->off_actor, a->La, a->cfg.kind);
+    p.eps = sac ? a->eps[1] : nullptr;
+    if (sac && a->cfg.use_hint) {
+      // pre-pass: forward only matters (pi), then the batch-wide penalty scalar (enet_sac.py:601-602)
+      if ((rc = run_rowphase(a, p, -1))) return rc;
+      CK(launch_hint_coef(a->aw.pi, a->rp.hint, a->Ap, a->bidx, a->B, a->A, a->cfg.hint_threshold, a->admm_rho, a->rho_dev, a->hint_out, nullptr, a->st));
+      a->launches++;
+      p.hint_coef = a->hint_out;
+    }
+    if ((rc = run_rowphase(a, p, 2))) return rc;
+    a->t_actor++;
+    fill_wgrad(a, w, true, 1, 2);
+    if ((rc = run_wgrad(a, w, 3))) return rc;
+    if (sac && a->cfg.use_hint && a->learn_counter % 10 == 0) {
+      // dual ascent on the hint multiplier with a fresh no-grad sample from the UPDATED actor (enet_sac.py:608-617)
+      if (noise && noise->eps_dual_host) CK(cudaStreamSynchronize(a->st));
+      if ((rc = upload_noise(a, noise ? noise->eps_dual_host : nullptr, 2, 0x3000000000ull))) return rc;
+      p.eps = a->eps[2];
+      p.hint_coef = nullptr;
+      if ((rc = run_rowphase(a, p, -1))) return rc;
+      CK(launch_hint_coef(a->aw.pi, a->rp.hint, a->Ap, a->bidx, a->B, a->A, a->cfg.hint_threshold, a->admm_rho, a->rho_dev, a->hint_out + 2, a->rho_dev, a->st));
+      a->launches++;
+    }
+  }
+  a->learn_counter++;
+  if (stats_host) {
+    CK(cudaMemcpyAsync(a->h_stats, a->stats, 16 * sizeof(float), cudaMemcpyDeviceToHost, a->st));
+    CK(cudaStreamSynchronize(a->st));
+    stats_host->critic_1_loss = a->h_stats[0];
+    stats_host->critic_2_loss = a->h_stats[1];
+    stats_host->actor_loss = a->h_stats[2];
+    stats_host->q1_mean = a->h_stats[3];
+    stats_host->q2_mean = a->h_stats[4];
+    stats_host->target_mean = a->h_stats[5];
+    stats_host->logp_mean = a->h_stats[6];
+    CK(cudaMemcpy(&a->rho, a->rho_dev, sizeof(float), cudaMemcpyDeviceToHost));
+    stats_host->rho = a->rho;
+    stats_host->gfun = 0.f;
+    if (sac && a->cfg.use_hint) CK(cudaMemcpy(&stats_host->gfun, a->hint_out + 1, sizeof(float), cudaMemcpyDeviceToHost));
+    stats_host->learn_counter = (int32_t)a->learn_counter;
+    stats_host->did_learn = 1;
+    stats_host->actor_step = actor_step ? 1 : 0;
+  }
+  return SC_OK;
+}
+
+int64_t sc_agent_launch_count(sc_agent* a) { return a ? a->launches : -1; }
+
+int sc_agent_enable_kernel_timing(sc_agent* a, int on) {
+  if (!a) return fail(SC_ERR_ARG, "null agent");
+  a->timing = on != 0;
+  return SC_OK;
+}
+int sc_agent_kernel_time(sc_agent* a, int which, int reset, double* ms_total, int64_t* launches) {
+  if (!a || which < 0 || which >= 6) return fail(SC_ERR_ARG, "bad argument");
+  CK(cudaStreamSynchronize(a->st));
+  KernelTimer& t = a->timers[which];
+  for (auto& pr : t.pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) t.ms += ms;
+    t.pool.push_back(pr);
+  }
+  t.pending.clear();
+  if (ms_total) *ms_total = t.ms;
+  if (launches) *launches = t.launches;
+  if (reset) { t.ms = 0; t.launches = 0; }
+  return SC_OK;
+}
+
+}  // extern "C"

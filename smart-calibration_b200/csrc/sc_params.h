@@ -1,0 +1,117 @@
+// Kernel parameter blocks shared by host (sc_api.cu) and device code.  Plain pointers into the agent arena.
+#pragma once
+#include <stdint.h>
+
+namespace sc {
+
+// hidden widths of the reference elastic-net MLPs (ref enet_sac.py:357-363,415-419)
+constexpr int H1 = 512, H2 = 256, H3 = 128, HA1 = 128, HA2 = 64, HCAT = H2 + HA2;
+constexpr int AMAX = 32;          // max n_actions supported by the row-local tail
+constexpr int RT = 2;             // rows a CTA carries through the row-local tail at once
+
+struct CriticP {                   // one CriticNetwork: PyTorch-native row-major W[out][in], pitch = roundup4(in)
+  float *w11, *b11, *w12, *b12, *w21, *b21, *w22, *b22, *w3, *b3;
+  float *g11, *be11, *g12, *be12, *g21, *be21, *g22, *be22;
+};
+struct ActorP {                    // SAC: wmu/bmu + wls/bls heads; TD3: single head in wmu/bmu (fc4), wls = nullptr
+  float *w1, *b1, *w2, *b2, *w3, *b3, *wmu, *bmu, *wls, *bls;
+  float *g1, *be1, *g2, *be2, *g3, *be3;
+};
+
+struct CriticWs {                  // activation / gradient workspace of one ONLINE critic, all [B][width]
+  float *h11, *zh11, *rs11, *du11, *dz11;    // width H1   (h = ELU(LN(z)), zh = normalised z, rs = 1/std per row)
+  float *h12, *zh12, *rs12, *du12, *dz12;    // width H2
+  float *h21, *zh21, *rs21, *du21, *dz21;    // width HA1
+  float *h22, *zh22, *rs22, *du22, *dz22;    // width HA2
+  float *q, *dq;                             // [B]
+  float *p_h11, *p_h12;                      // state-branch forward with the UPDATED weights (actor phase)
+};
+struct TargetWs { float *h11, *h12; };
+struct ActorWs {
+  float *t_h1, *t_h2;                        // pass on s' (critic phase): SAC online actor / TD3 target actor
+  float *h1, *zh1, *rs1, *du1, *dz1;         // pass on s (actor phase)
+  float *h2, *zh2, *rs2, *du2, *dz2;
+  float *h3, *zh3, *rs3, *du3, *dz3;
+  float *dhead;                              // [B][2A] (SAC: dmu | dlogsigma) or [B][A] (TD3: d pre-tanh)
+  float *pi, *logp;                          // [B][A], [B]
+};
+
+struct ReplayP {
+  float *state, *new_state;                  // [C][Sp]
+  float *action, *hint;                      // [C][Ap]
+  float *reward;                             // [C]
+  uint8_t* done;                             // [C]
+  double* tree;                              // [2C-1] float64 sum tree (PER) or nullptr
+  int C, S, Sp, A, Ap;
+};
+
+enum RowProgram { PROG_CRITIC = 0, PROG_ACTOR = 1, PROG_ACT = 2 };
+
+struct RowPhaseParams {
+  int program, kind;                         // RowProgram, SC_KIND_*
+  int B, S, Sp, A, Ap;
+  ActorP actor;                              // actor evaluated in this phase
+  CriticP crit[2];                           // online critics
+  CriticP targ[2];                           // target critics
+  CriticWs cw[2];
+  TargetWs tw[2];
+  ActorWs aw;
+  ReplayP rp;
+  const int* bidx;                           // [B] replay slots of the minibatch
+  const float* eps;                          // [B][A] N(0,1) for this phase (nullptr: none)
+  const float* is_wsum;                      // device scalar: sum of IS weights (PER) or nullptr
+  float* y;                                  // [B] TD target
+  float* err;                                // [B] 0.5(|q1-y|+|q2-y|) (PER priorities)
+  float* part;                               // LN partial statistics [slot][B][CS][2]
+  float gamma, scale, alpha, maxa, td3_noise_c;
+  int n_q;                                   // critics used by the actor phase (SAC 2, TD3 1)
+  // hint penalty (SAC, enet_sac.py:601-602): coefficient already folded by the host-side pre-pass
+  const float* hint_coef;                    // device scalar: (admm_rho*g + rho) * 2*max(0,m-thr) * 2/(B*A), or nullptr
+  // PROG_ACT
+  const float* obs;                          // [Sp]
+  float* act_out;                            // [A]
+  float* act_aux;                            // scratch [H1 + H2] activations for the single row
+};
+
+// ---- wgrad + Adam (+ target soft update) work list ------------------------------------------------------
+struct AdamHyper {                 // torch.optim.Adam scalars evaluated on the host in double like torch does
+  float lr_neg_step;               // -(lr / (1 - beta1^t))
+  float bc2_sqrt;                  // sqrt(1 - beta2^t)
+  float one_minus_b1, b2, one_minus_b2, eps;
+};
+struct WgradOp {
+  const float* D; int ldd;         // [B][N] upstream pre-activation gradient (this step)
+  const float* X; int ldx;         // [B][K] layer input; gather != 0: X is a replay array indexed by bidx
+  int gather;
+  int N, K;
+  float *W, *M, *V, *T;            // parameter, Adam moments, target (nullptr: none); row pitch ldw
+  int ldw;
+  int tiles_k;                     // number of 32-wide k tiles
+  int tile_base, tile_count;       // position in the flat tile list
+  int opt;                         // index into AdamHyper[3] (0 actor, 1 critic_1, 2 critic_2)
+};
+struct VecOp {                     // g[n] = sum_b D[b][n] * (E ? E[b][n] : 1): biases and LayerNorm affine
+  const float* D; const float* E; int ld;
+  int N;
+  float *P, *M, *V, *T;
+  int tile_base, tile_count;       // 32 columns per tile
+  int opt;
+};
+struct WgradParams {
+  const WgradOp* ops; int nops;
+  const VecOp* vops; int nvops;
+  int total_tiles;
+  int B;
+  const int* bidx;
+  AdamHyper hyper[3];
+  float tau, one_minus_tau;        // soft update of T (enet_sac.py:531): tau*p + (1-tau)*t
+  int do_soft;                     // 0: leave targets alone (TD3 off-steps)
+  // loss/diagnostic reduction done by the CTA that draws tile index total_tiles
+  int stats_mode;                  // 0 none, 1 critic phase, 2 actor phase
+  const float *q1, *q2, *y, *logp, *pi_q;   // [B]
+  const float* is_wsum;
+  float* stats;                    // device float[16]
+  float alpha;
+};
+
+}  // namespace sc

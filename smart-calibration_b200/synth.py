@@ -1,0 +1,24 @@
+"""Synthetic transitions of the elastic-net shape: state, new_state ~ N(0,1) (C,S) f32,
+action, hint ~ U(-1,1) (C,A), reward ~ N(0,1) (SAC) or U(0,1) (TD3/PER), terminal False (optionally a fraction True).
+Shared by tests/, bench.py and the golden-vector generator so that every side sees identical inputs."""
+import numpy as np
+
+
+def make_transitions(seed, n, S, A, reward="normal", done_frac=0.0):
+    rs = np.random.RandomState(seed)
+    state = rs.standard_normal((n, S)).astype(np.float32)
+    new_state = rs.standard_normal((n, S)).astype(np.float32)
+    action = rs.uniform(-1, 1, (n, A)).astype(np.float32)
+    hint = rs.uniform(-1, 1, (n, A)).astype(np.float32)
+    if reward == "normal":
+        rew = rs.standard_normal(n).astype(np.float32)
+    else:
+        rew = rs.uniform(0, 1, n).astype(np.float32)
+    done = rs.uniform(0, 1, n) < done_frac
+    return dict(state=state, new_state=new_state, action=action, hint=hint, reward=rew, done=done)
+
+
+def pack(tr):
+    """(n, 2S+2A+2) float32 rows [s | s2 | a | hint | r | done] -- the C ABI's packed transition"""
+    return np.concatenate([tr["state"], tr["new_state"], tr["action"], tr["hint"], tr["reward"][:, None],
+                           tr["done"].astype(np.float32)[:, None]], axis=1).astype(np.float32)
