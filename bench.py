@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""bench.py -- SAC Agent.learn() steps/s on the B200 (BASELINE.json metric), with roofline, CPU baseline and e2e.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Own arm: a "step" is one Agent.learn() of the elastic-net SAC agent (S=420, A=2) at batch 256 on synthetic
+transitions, prioritized replay of capacity 4096 (BASELINE.json configs[1]).  `value` is measured with the replay
+resident in HBM and on-device sampling/noise; L2 is flushed (256 MiB write) between timed steps and each step is
+timed with its own CUDA-event pair on the launching stream, so flush time is excluded.  `e2e` goes through the public
+facade with HOST buffers: agent.store_transition(host obs) + agent.learn() + a device->host read of the step's losses,
+in the default rng='reference' mode (indices/uniforms/noise drawn on the host and copied in every step).
+N > 1 (torchrun): one replica agent per GPU (the reference's seed-ensemble axis, elasticnet/do.sh), no data-path
+collective; value = N*K / max-over-ranks device time.
+
+--impl reference: the reference's own CPU path.  The reference is pure Python and does not travel to the GPU box, so
+this times the oracle port (oracle/sac_ref.py, op-for-op the reference's learn(), validated bit-exact against it by
+tests/golden) with all host threads; rank 0 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S, A, B, C = 420, 2, 256, 4096
+HP = dict(gamma=0.99, lr_a=1e-3, lr_c=1e-3, input_dims=[S], batch_size=B, n_actions=A, max_mem_size=C, tau=0.005,
+          reward_scale=20, alpha=0.03)
+WORKLOAD = "elastic-net SAC Agent.learn(): S=420 A=2 batch=256 PER capacity=4096 (prioritized=True, derived TD3-style wiring), synthetic transitions"
+PA, PC = 382084, 357761                      # actor / critic parameter counts
+# algorithmic bytes: whole step, and the dominant kernel (critic row-phase: minibatch + actor + 4 critics read once)
+STEP_BYTES = B * ((2 * S + A + 1) * 4 + 1) + (PA + 4 * PC) * 4 + (PA + 2 * PC) * 20 + 2 * PC * 4
+CRITIC_PHASE_BYTES = B * ((2 * S + A + 1) * 4 + 1) + (PA + 4 * PC) * 4
+CRITIC_PHASE_FLOP = 2 * B * (379392 + 4 * 354880 + 2 * (131072 + 8192 + 320))   # fwd actor + 4 critic fwd + 2 critic dgrad (fc12, fc22, fc3)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index),
+                 "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_agent(seed, rng):
+    from smartcal_b200.elasticnet import enet_sac
+    from smartcal_b200.synth import make_transitions, pack
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    agent = enet_sac.Agent(**HP, prioritized=True, use_hint=False, rng=rng)
+    tr = make_transitions(seed + 100, C, S, A, "normal", 0.0)
+    agent._dev.fill(pack(tr), None)          # all leaves at the PER clip (what error=None stores give on a fresh tree)
+    return agent, tr
+
+
+def timed_steps(dev, steps, flush, timing=False):
+    """K learn() steps, each bracketed by its own event pair; L2 flushed in between (outside the pairs)"""
+    st = torch.cuda.current_stream()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        if flush is not None:
+            flush.zero_()
+        a.record(st)
+        dev.learn()
+        b.record(st)
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs)      # ms
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    agent, tr = make_agent(100 + rank, "device")
+    dev = agent._dev
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        dev.learn()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = dev.launch_count()
+    barrier()
+    ms_cold = timed_steps(dev, args.steps, flush)
+    barrier()
+    launches = dev.launch_count() - l0
+    # L2-warm, back-to-back (steady-state production shape: the 46 MB working set lives in the 126 MB L2)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        dev.learn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_warm = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_cold, ms_warm], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_cold, ms_warm = float(t[0]), float(t[1])
+
+    # per-kernel CUDA-event timing (second pass so that the event records do not perturb the headline)
+    dev.enable_timing(True)
+    for w in range(6):
+        dev.kernel_time(w, reset=True)
+    timed_steps(dev, min(args.steps, 100), flush)
+    kt = [dev.kernel_time(w, reset=True) for w in range(6)]
+    dev.enable_timing(False)
+    names = ["critic_rowphase", "critic_wgrad_adam", "actor_rowphase", "actor_wgrad_adam", "per_sample", "per_update"]
+    kern = {n: {"avg_us": (ms / max(cnt, 1)) * 1e3, "launches": cnt} for n, (ms, cnt) in zip(names, kt)}
+
+    # end-to-end through the public API with host buffers (reference-RNG mode: host draws + H2D every step)
+    e2e = None
+    if True:
+        agent2, tr2 = make_agent(200 + rank, "reference")
+        obs = [{"eig": torch.from_numpy(tr2["state"][i, :20].copy()), "A": torch.from_numpy(tr2["state"][i, 20:].copy())} for i in range(64)]
+        obs2 = [{"eig": torch.from_numpy(tr2["new_state"][i, :20].copy()), "A": torch.from_numpy(tr2["new_state"][i, 20:].copy())} for i in range(64)]
+
+        def one(i):
+            j = i % 64
+            agent2.store_transition(obs[j], tr2["action"][j], float(tr2["reward"][j]), obs2[j], False, tr2["hint"][j])
+            return agent2.learn(want_stats=True)
+
+        for i in range(max(args.warmup, 3)):
+            one(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            one(i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * args.steps / float(tt[0]), "unit": "learn steps/s",
+               "h2d_bytes_per_step": (2 * S + 2 * A + 2) * 4 + B * 8 + 2 * B * A * 4, "d2h_bytes_per_step": 48,
+               "mode": "store_transition(host obs) + learn() + loss readback, rng='reference' (host numpy/torch draws)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    crit_s = kern["critic_rowphase"]["avg_us"] * 1e-6
+    roof = {"bound": "hbm", "kernel": "k_rowphase<PROG_CRITIC>", "achieved": CRITIC_PHASE_BYTES / crit_s / 1e9, "peak": peak,
+            "unit": "GB/s", "frac": CRITIC_PHASE_BYTES / crit_s / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": CRITIC_PHASE_BYTES,
+            "fp32_ffma": {"achieved_tflops": CRITIC_PHASE_FLOP / crit_s / 1e12, "peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12,
+                          "note": "the kernel is FP32-FFMA-bound, not HBM-bound (DESIGN.md)"},
+            "step": {"algorithmic_bytes": STEP_BYTES, "achieved": STEP_BYTES / (ms_cold / args.steps * 1e-3) / 1e9,
+                     "frac": STEP_BYTES / (ms_cold / args.steps * 1e-3) / 1e9 / peak}}
+    cpu = cpu_baseline(sample_seconds=12.0)
+    out = {"metric": "SAC learn() steps/sec (batch=256)", "value": world * args.steps / (ms_cold * 1e-3), "unit": "learn steps/s",
+           "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_cold / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "l2": "flushed between timed steps (256 MiB write outside the event pairs)",
+                      "rng": "device Philox", "parallelism": "replicas" if world > 1 else "single agent"},
+           "l2_warm": {"value": world * args.steps / (ms_warm * 1e-3), "ms_per_step": ms_warm / args.steps},
+           "e2e": e2e, "gpu_launches": int(launches), "kernels": kern, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(sample_seconds=12.0, steps=None, warmup=5):
+    """oracle port of the reference learn() on the host cores (all threads torch will use)"""
+    from oracle.sac_ref import SacRef
+    from smartcal_b200.synth import make_transitions
+    torch.manual_seed(0)
+    np.random.seed(0)
+    orc = SacRef(**HP, prioritized=True)
+    tr = make_transitions(100, C, S, A, "normal", 0.0)
+    for i in range(C):
+        orc.store_flat(tr["state"][i], tr["action"][i], float(tr["reward"][i]), tr["new_state"][i], False, tr["hint"][i])
+    for _ in range(warmup):
+        orc.learn()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        orc.learn()
+        n += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and n >= steps) or (steps is None and el >= sample_seconds):
+            break
+    return {"value": n / el, "unit": "learn steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} learn() steps of the same workload in {el:.1f} s (oracle/sac_ref.py, torch {torch.__version__} CPU, "
+                      f"{torch.get_num_threads()} threads of {os.cpu_count()} logical cores)", "ms_per_step": el / n * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cpu = cpu_baseline(steps=args.steps, warmup=max(args.warmup, 3))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    out = {"impl": "reference", "metric": "SAC learn() steps/sec (batch=256)", "value": cpu["value"], "unit": "learn steps/s",
+           "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": cpu["ms_per_step"],
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOAD}, "cpu_baseline": cpu,
+           "e2e": {"value": cpu["value"], "unit": "learn steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -269,7 +269,7 @@ static size_t carve(sc_agent* a, void* base) {
   aw.h1 = mat("a.h1", H1); aw.zh1 = mat("a.zh1", H1); aw.rs1 = mat("a.rs1", 1); aw.du1 = mat("a.du1", H1); aw.dz1 = mat("a.dz1", H1);
   aw.h2 = mat("a.h2", H2); aw.zh2 = mat("a.zh2", H2); aw.rs2 = mat("a.rs2", 1); aw.du2 = mat("a.du2", H2); aw.dz2 = mat("a.dz2", H2);
   aw.h3 = mat("a.h3", H3); aw.zh3 = mat("a.zh3", H3); aw.rs3 = mat("a.rs3", 1); aw.du3 = mat("a.du3", H3); aw.dz3 = mat("a.dz3", H3);
-  aw.dhead = mat("a.dhead", 2 * A); aw.pi = mat("a.pi", A); aw.logp = mat("a.logp", 1);
+  aw.dhead = mat("a.dhead", 2 * A); aw.pi = mat("a.pi", A); aw.logp = mat("a.logp", 1); aw.qmin = mat("a.qmin", 1);
   a->y = mat("y", 1);
   a->err = mat("err", 1);
   a->is_w = mat("is_weights", 1);
@@ -280,7 +280,7 @@ static size_t carve(sc_agent* a, void* base) {
   reg("eps_next", a->eps[0], B, A, A, 4);
   reg("eps_cur", a->eps[1], B, A, A, 4);
   a->stats = cv.f(16);
-  a->hint_out = cv.f(4);
+  a->hint_out = cv.f(8);
   a->rho_dev = cv.f(4);
   a->bidx = (int*)cv.take(sizeof(int) * B);
   a->tree_idx = (int*)cv.take(sizeof(int) * B);
@@ -734,7 +734,7 @@ static void fill_wgrad(sc_agent* a, WgradParams& w, bool actor, int do_soft, int
   w.stats_mode = stats_mode;
   w.q1 = a->cw[0].q; w.q2 = a->cw[1].q; w.y = a->y;
   w.logp = a->cfg.kind == SC_KIND_SAC ? a->aw.logp : nullptr;
-  w.pi_q = a->cw[0].q;
+  w.pi_q = a->aw.qmin;
   w.is_wsum = a->cfg.prioritized ? a->is_wsum : nullptr;
   w.stats = a->stats;
   w.alpha = a->cfg.kind == SC_KIND_SAC ? a->alpha : 0.f;
@@ -891,7 +891,7 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
       p.eps = a->eps[2];
       p.hint_coef = nullptr;
       if ((rc = run_rowphase(a, p, -1))) return rc;
-      CK(launch_hint_coef(a->aw.pi, a->rp.hint, a->Ap, a->bidx, a->B, a->A, a->cfg.hint_threshold, a->admm_rho, a->rho_dev, a->hint_out + 2, a->rho_dev, a->st));
+      CK(launch_hint_coef(a->aw.pi, a->rp.hint, a->Ap, a->bidx, a->B, a->A, a->cfg.hint_threshold, a->admm_rho, a->rho_dev, a->hint_out + 4, a->rho_dev, a->st));
       a->launches++;
     }
   }
@@ -909,7 +909,12 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
     CK(cudaMemcpy(&a->rho, a->rho_dev, sizeof(float), cudaMemcpyDeviceToHost));
     stats_host->rho = a->rho;
     stats_host->gfun = 0.f;
-    if (sac && a->cfg.use_hint) CK(cudaMemcpy(&stats_host->gfun, a->hint_out + 1, sizeof(float), cudaMemcpyDeviceToHost));
+    if (sac && a->cfg.use_hint) {
+      float pen[2] = {0.f, 0.f};
+      CK(cudaMemcpy(pen, a->hint_out + 1, 2 * sizeof(float), cudaMemcpyDeviceToHost));
+      stats_host->gfun = pen[0];
+      stats_host->actor_loss += pen[1];
+    }
     stats_host->learn_counter = (int32_t)a->learn_counter;
     stats_host->did_learn = 1;
     stats_host->actor_step = actor_step ? 1 : 0;

@@ -33,7 +33,7 @@ struct ActorWs {
   float *h2, *zh2, *rs2, *du2, *dz2;
   float *h3, *zh3, *rs3, *du3, *dz3;
   float *dhead;                              // [B][2A] (SAC: dmu | dlogsigma) or [B][A] (TD3: d pre-tanh)
-  float *pi, *logp;                          // [B][A], [B]
+  float *pi, *logp, *qmin;                   // [B][A], [B], [B] (min_k Q_k(s,pi(s)) or Q_1 for TD3)
 };
 
 struct ReplayP {

@@ -292,6 +292,7 @@ __global__ void k_hint_coef(const float* __restrict__ pi, const float* __restric
     const float g = ex * ex;
     out[0] = (admm_rho * g + *rho) * 2.f * ex * 2.f / (float)(B * A);
     out[1] = g;
+    out[2] = 0.5f * admm_rho * g * g + *rho * g;                               // penalty added to actor_loss (enet_sac.py:602)
     if (rho_update != nullptr) *rho_update = *rho_update + admm_rho * g;       // rho += admm_rho*gfun (enet_sac.py:617)
   }
 }

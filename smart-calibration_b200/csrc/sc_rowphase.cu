@@ -715,10 +715,10 @@ __device__ void tail_actor(const RowPhaseParams& p, const TailSm& t, const RowSe
     if (rs.row[tid] >= 0) {
       if (p.n_q == 2) {   // torch.min backward: gradient to the smaller, halves on ties
         if (s[SC_Q1] < s[SC_Q2]) g1 = -coef; else if (s[SC_Q2] < s[SC_Q1]) g2 = -coef; else { g1 = -0.5f * coef; g2 = -0.5f * coef; }
-        p.cw[0].q[rs.row[tid]] = fminf(s[SC_Q1], s[SC_Q2]);       // reuse q as "critic_value" for the loss readout
+        p.aw.qmin[rs.row[tid]] = fminf(s[SC_Q1], s[SC_Q2]);       // critic_value (enet_sac.py:592)
       } else {
         g1 = -coef;
-        p.cw[0].q[rs.row[tid]] = s[SC_Q1];
+        p.aw.qmin[rs.row[tid]] = s[SC_Q1];
       }
     }
     s[SC_DQ1] = g1;

@@ -122,6 +122,12 @@ class NetView:
     def adam_state(self):
         return OrderedDict((k, (self._t(k, L.SLOT_ADAM_M).clone(), self._t(k, L.SLOT_ADAM_V).clone())) for k in self._keys)
 
+    def load_adam_state(self, moments):
+        """moments: {key: (exp_avg, exp_avg_sq)} -> torch.optim.Adam state of the reference optimizer"""
+        for k, (m, v) in moments.items():
+            self._t(k, L.SLOT_ADAM_M).copy_(T.as_tensor(m).to(self.device))
+            self._t(k, L.SLOT_ADAM_V).copy_(T.as_tensor(v).to(self.device))
+
     def flat(self):
         """the whole contiguous parameter block (one NCCL broadcast moves the network)"""
         return self._dev.tensor(self._net, "*")[0]

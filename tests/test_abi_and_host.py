@@ -1,0 +1,90 @@
+"""CPU: the C-ABI library loads and exports every symbol include/smartcal_b200.h declares (no compute without a GPU),
+the product path fails loudly without a device, and the host-side logic (reference-order init, packing, state-dict
+key tables) behaves."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import smartcal_b200
+from smartcal_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "smartcal_b200.h")).read()
+    declared = set(re.findall(r"\b(sc_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"sc_agent"}
+    lib = L.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in L.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
+    assert lib.sc_abi_version() == L.SC_ABI_VERSION
+
+
+def test_config_struct_layout_and_arena_size():
+    lib = L.load()
+    cfg = L.ScConfig(abi_version=1, kind=0, state_dim=420, n_actions=2, batch_size=256, mem_size=4096, prioritized=1,
+                     gamma=0.99, tau=0.005, lr_actor=1e-3, lr_critic=1e-3, reward_scale=20, alpha=0.03, max_action=1, per_clip=100)
+    n = lib.sc_agent_arena_bytes(C.byref(cfg))
+    # nets+Adam+targets 16.0 MB, replay 14.0 MB, workspace ~15 MB
+    assert 30e6 < n < 80e6
+    bad = L.ScConfig(abi_version=1, kind=0, state_dim=420, n_actions=2, batch_size=256, mem_size=1000, prioritized=1)
+    assert lib.sc_agent_arena_bytes(C.byref(bad)) == 0
+    assert b"power of 2" in lib.sc_last_error()       # same message as the reference assert (enet_sac.py:99)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from smartcal_b200.elasticnet import enet_sac
+    with pytest.raises(L.SmartcalError, match="no CPU fallback"):
+        enet_sac.Agent(gamma=0.99, lr_a=1e-3, lr_c=1e-3, input_dims=[24], batch_size=8, n_actions=2)
+    lib = L.load()
+    cfg = L.ScConfig(abi_version=1, kind=0, state_dim=24, n_actions=2, batch_size=8, mem_size=16)
+    h = C.c_void_p()
+    assert lib.sc_agent_create(C.byref(cfg), None, 0, None, C.byref(h)) == 2      # SC_ERR_CUDA
+    assert b"no CPU fallback" in lib.sc_last_error()
+
+
+def test_initial_weights_follow_the_reference_draw_order():
+    """facade init == golden digests of the real reference's freshly constructed nets (same torch seed)"""
+    from smartcal_b200.elasticnet import _host as H
+    z = np.load(os.path.join(ROOT, "tests", "golden", "sac_s24_b32.npz"))
+    S, A, B, Cc, steps, seed, _ = [int(x) for x in z["cfg"]]
+    torch.manual_seed(seed)
+    nets = [("actor", H.actor_initial_state(S, A, L.SC_KIND_SAC)), ("critic_1", H.critic_initial_state(S, A)),
+            ("critic_2", H.critic_initial_state(S, A))]
+    for nm, sd in nets:
+        for k, v in sd.items():
+            a = v.numpy().astype(np.float64).reshape(-1)
+            idx = np.linspace(0, a.size - 1, min(32, a.size)).astype(np.int64)
+            got = np.concatenate([[a.sum(), np.abs(a).sum()], a[idx]])
+            assert np.array_equal(got, z[f"init/{nm}/{k}/p"]), f"{nm}.{k}"
+
+
+def test_key_tables_and_packing():
+    from smartcal_b200.elasticnet import _host as H
+    from smartcal_b200.synth import make_transitions, pack
+    assert len(H.critic_keys()) == 18 and len(H.actor_keys(L.SC_KIND_SAC)) == 16 and len(H.actor_keys(L.SC_KIND_TD3)) == 14
+    tr = make_transitions(0, 5, 7, 2)
+    p = pack(tr)
+    assert p.shape == (5, 2 * 7 + 2 * 2 + 2) and p.dtype == np.float32
+    assert np.array_equal(p[:, :7], tr["state"]) and np.array_equal(p[:, 14:16], tr["action"])
+    obs = {"eig": torch.arange(3.0), "A": torch.arange(4.0)}
+    assert np.array_equal(H.flat_state(obs), np.array([0, 1, 2, 0, 1, 2, 3], np.float32))
+
+
+def test_standalone_host_replaybuffer_matches_reference_shape():
+    from smartcal_b200.elasticnet.enet_sac import ReplayBuffer
+    rb = ReplayBuffer(8, [5], 2)
+    o = {"eig": torch.zeros(2), "A": torch.ones(3)}
+    for i in range(11):
+        rb.store_transition(o, np.array([i, -i], np.float32), float(i), o, i % 2 == 0, np.zeros(2, np.float32))
+    assert rb.mem_cntr == 11 and rb.reward_memory[2] == 10.0 and rb.state_memory.shape == (8, 5)
+    np.random.seed(0)
+    s, a, r, s2, d, h = rb.sample_buffer(4)
+    assert s.shape == (4, 5) and a.shape == (4, 2) and d.dtype == bool

@@ -1,0 +1,120 @@
+"""CPU: the oracle restatement (oracle/) against the golden vectors recorded from the UNMODIFIED reference
+(tests/golden/*.npz, made by tests/golden/make_golden.py).  On the generating image the match is bit-exact; other
+hosts may block their sgemm differently, hence the small tolerances below (relative to 1+|x|)."""
+import os
+import numpy as np
+import pytest
+import torch
+
+from oracle.per_ref import PerRef
+from oracle.sac_ref import SacRef
+from oracle.td3_ref import Td3Ref
+from smartcal_b200.synth import make_transitions
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NSAMP = 32
+TOL = 5e-5       # digests after an Adam step: a handful of near-zero-gradient elements may move by ~lr
+
+
+def digest(t):
+    a = t.detach().cpu().numpy().astype(np.float64).reshape(-1)
+    idx = np.linspace(0, a.size - 1, min(NSAMP, a.size)).astype(np.int64)
+    return np.concatenate([[a.sum(), np.abs(a).sum()], a[idx]])
+
+
+def close(got, ref, tol, what):
+    # sums (entries 0,1) scale with the tensor; compare relative to the abs-sum, samples relative to 1+|x|
+    scale = np.concatenate([[1 + abs(ref[1])] * 2, 1 + np.abs(ref[2:])])
+    d = np.max(np.abs(got - ref) / scale)
+    assert d <= tol, f"{what}: {d}"
+
+
+def check_nets(z, prefix, nets, tol):
+    for nm, prm, opt in nets:
+        for k, p in prm.items():
+            close(digest(p), z[f"{prefix}/{nm}/{k}/p"], tol, f"{prefix}/{nm}/{k}/p")
+            st = opt.state.get(p) if opt is not None else None
+            if st:
+                close(digest(st["exp_avg"]), z[f"{prefix}/{nm}/{k}/m"], tol, f"{prefix}/{nm}/{k}/m")
+                close(digest(st["exp_avg_sq"]), z[f"{prefix}/{nm}/{k}/v"], tol, f"{prefix}/{nm}/{k}/v")
+
+
+@pytest.mark.parametrize("name", ["per_c64_b16", "per_c4096_b256"])
+def test_per_oracle_bit_exact(name):
+    z = np.load(os.path.join(G, name + ".npz"))
+    C, B, rounds, seed = [int(x) for x in z["cfg"]]
+    orc = PerRef(C, 100.0)
+    for e, none in zip(z["store_err"], z["store_none"]):
+        orc.store(None if none else float(e))
+    assert np.array_equal(orc.tree.tree, z["tree_after_store"])
+    for r in range(rounds):
+        idx, data, w = orc.sample(z[f"r{r}/u01"])
+        assert np.array_equal(idx, z[f"r{r}/idx"])
+        assert np.array_equal(data, z[f"r{r}/idx"] - (C - 1))
+        assert np.array_equal(w, z[f"r{r}/w"])
+        assert float(orc.beta) == float(z[f"r{r}/beta"][0])
+        ps = orc.update(idx, z[f"r{r}/abs_err"])
+        # float32 power is libm/SVML dependent across hosts: allow 2 ulp, then pin the tree through the recorded priorities
+        d = np.abs(ps.view(np.int32).astype(np.int64) - z[f"r{r}/ps"].view(np.int32).astype(np.int64))
+        assert d.max() <= 2
+        if d.max() == 0:
+            assert np.array_equal(orc.tree.tree, z[f"r{r}/tree"])
+        else:
+            orc.tree.tree[:] = z[f"r{r}/tree"]
+    # idxs non-decreasing for stratified draws (what the CUDA per-level fold relies on; it has an exact fallback)
+    for r in range(rounds):
+        assert np.all(np.diff(z[f"r{r}/idx"]) >= 0)
+    orc.tree.tree[:] = z[f"r{rounds - 1}/tree"]
+    ps = orc.update(z["unsorted/idx"], z["unsorted/abs_err"])
+    np.testing.assert_allclose(orc.tree.tree, z["unsorted/tree"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["sac_s24_b32", "sac_s22_hint_b32", "sac_enet_b256"])
+def test_sac_oracle_matches_reference(name):
+    z = np.load(os.path.join(G, name + ".npz"))
+    S, A, B, C, steps, seed, use_hint = [int(x) for x in z["cfg"]]
+    hp = dict(gamma=0.99, lr_a=1e-3, lr_c=1e-3, input_dims=[S], batch_size=B, n_actions=A, max_mem_size=C, tau=0.005,
+              reward_scale=20, alpha=0.03)
+    tr = make_transitions(seed + 100, C, S, A, "normal", float(z["done_frac"][0]))
+    torch.manual_seed(seed)
+    orc = SacRef(**hp, use_hint=bool(use_hint))
+    check_nets(z, "init", [("actor", orc.actor, None), ("critic_1", orc.critic_1, None), ("critic_2", orc.critic_2, None)], 0.0)
+    for i in range(C):
+        orc.store_flat(tr["state"][i], tr["action"][i], tr["reward"][i], tr["new_state"][i], tr["done"][i], tr["hint"][i])
+    for s in range(steps):
+        e3 = z[f"step{s}/eps3"] if f"step{s}/eps3" in z else None
+        res = orc.learn_on_batch(orc.replay.gather(z[f"step{s}/idx"]), z[f"step{s}/eps1"], z[f"step{s}/eps2"], e3)
+        tol = TOL * (s + 1)
+        check_nets(z, f"step{s}", [("actor", orc.actor, orc.opt_a), ("critic_1", orc.critic_1, orc.opt_1), ("critic_2", orc.critic_2, orc.opt_2),
+                                   ("target_critic_1", orc.target_critic_1, None), ("target_critic_2", orc.target_critic_2, None)], tol)
+        np.testing.assert_allclose([res["critic_1_loss"], res["critic_2_loss"], res["actor_loss"]], z[f"step{s}/losses"], rtol=1e-4)
+        if use_hint:
+            np.testing.assert_allclose(float(orc.rho), z[f"step{s}/rho"][0], rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["td3_per_s24_b32", "td3_uniform_s24_b32", "td3_per_enet_b64"])
+def test_td3_oracle_matches_reference(name):
+    z = np.load(os.path.join(G, name + ".npz"))
+    S, A, B, C, steps, seed, prioritized = [int(x) for x in z["cfg"]]
+    hp = dict(gamma=0.99, lr_a=1e-3, lr_c=1e-3, input_dims=[S], batch_size=B, n_actions=A, max_mem_size=C, tau=0.005,
+              update_actor_interval=2, warmup=100, noise=0.1)
+    tr = make_transitions(seed + 100, C, S, A, "uniform", float(z["done_frac"][0]))
+    torch.manual_seed(seed)
+    orc = Td3Ref(**hp, prioritized=bool(prioritized), use_hint=False)
+    for i in range(C):
+        orc.store_flat(tr["state"][i], tr["action"][i], float(tr["reward"][i]), tr["new_state"][i], bool(tr["done"][i]), tr["hint"][i])
+    if prioritized:
+        assert np.array_equal(orc.per.tree.tree, z["tree_after_fill"])
+    for s in range(steps):
+        nz = float(z[f"step{s}/noise"][0])
+        if prioritized:
+            idxs, data, w = orc.per.sample(z[f"step{s}/u01"])
+            assert np.array_equal(idxs, z[f"step{s}/tree_idx"])
+            res = orc.learn_on_batch(orc.replay.gather(data), nz, is_weights=w, tree_idx=idxs)
+            np.testing.assert_allclose(orc.per.tree.tree, z[f"step{s}/tree"], rtol=1e-5)
+            orc.per.tree.tree[:] = z[f"step{s}/tree"]
+        else:
+            res = orc.learn_on_batch(orc.replay.gather(z[f"step{s}/idx"]), nz)
+        check_nets(z, f"step{s}", [("actor", orc.actor, orc.opt_a), ("critic_1", orc.critic_1, orc.opt_1), ("critic_2", orc.critic_2, orc.opt_2),
+                                   ("target_actor", orc.target_actor, None), ("target_critic_1", orc.target_critic_1, None),
+                                   ("target_critic_2", orc.target_critic_2, None)], TOL * (s + 1))
