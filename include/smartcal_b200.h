@@ -75,7 +75,7 @@ typedef struct sc_tensor_info {
   void* dev_ptr;
   int64_t rows, cols, pitch;
   int32_t elem_bytes; /* 4 = float32, 8 = float64 (sum tree), 1 = u8 */
-  int32_t reserved;
+  int32_t is_int;     /* 1: elements are int32 (index buffers) */
 } sc_tensor_info;
 
 /* per-step diagnostics, written to host by sc_agent_learn when `stats_host` != NULL (forces a sync) */

@@ -30,7 +30,7 @@ class ScConfig(C.Structure):
 
 class ScTensorInfo(C.Structure):
     _fields_ = [("dev_ptr", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int64), ("pitch", C.c_int64),
-                ("elem_bytes", C.c_int32), ("reserved", C.c_int32)]
+                ("elem_bytes", C.c_int32), ("is_int", C.c_int32)]
 
 
 class ScLearnStats(C.Structure):

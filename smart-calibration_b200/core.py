@@ -57,7 +57,7 @@ class DeviceAgent:
 
     # ---- views ------------------------------------------------------------------------------------------
     def _view(self, info):
-        dt = _TORCH_DT[info.elem_bytes]
+        dt = torch.int32 if info.is_int else _TORCH_DT[info.elem_bytes]
         off = info.dev_ptr - self.arena.data_ptr()
         nbytes = ((info.rows - 1) * info.pitch + info.cols) * info.elem_bytes
         flat = self.arena[off:off + nbytes].view(dt)

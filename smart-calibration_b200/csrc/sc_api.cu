@@ -244,7 +244,7 @@ static size_t carve(sc_agent* a, void* base) {
   // workspace
   auto reg = [&](const std::string& name, void* p, int64_t rows, int64_t cols, int64_t pitch, int eb) {
     sc_tensor_info ti;
-    ti.dev_ptr = p; ti.rows = rows; ti.cols = cols; ti.pitch = pitch; ti.elem_bytes = eb; ti.reserved = 0;
+    ti.dev_ptr = p; ti.rows = rows; ti.cols = cols; ti.pitch = pitch; ti.elem_bytes = eb; ti.is_int = 0;
     a->buffers[name] = ti;
   };
   auto mat = [&](const std::string& name, int width) {
@@ -286,6 +286,8 @@ static size_t carve(sc_agent* a, void* base) {
   a->tree_idx = (int*)cv.take(sizeof(int) * B);
   reg("batch_idx", a->bidx, B, 1, 1, 4);
   reg("tree_idx", a->tree_idx, B, 1, 1, 4);
+  a->buffers["batch_idx"].is_int = 1;   // int32
+  a->buffers["tree_idx"].is_int = 1;
   a->u01 = (double*)cv.take(sizeof(double) * B);
   a->obs_dev = cv.f(Sp);
   a->act_eps = cv.f(round4i(A));
@@ -535,12 +537,12 @@ int sc_agent_tensor(sc_agent* a, int net, int slot, const char* name, sc_tensor_
   float* base = net_base(a, net, slot, &L);
   if (!base) return fail(SC_ERR_ARG, "network %d / slot %d does not exist for this agent kind", net, slot);
   if (strcmp(name, "*") == 0) {
-    out->dev_ptr = base; out->rows = 1; out->cols = (int64_t)L->size; out->pitch = (int64_t)L->size; out->elem_bytes = 4; out->reserved = 0;
+    out->dev_ptr = base; out->rows = 1; out->cols = (int64_t)L->size; out->pitch = (int64_t)L->size; out->elem_bytes = 4; out->is_int = 0;
     return SC_OK;
   }
   const TDesc* d = L->find(name);
   if (!d) return fail(SC_ERR_ARG, "unknown tensor '%s'", name);
-  out->dev_ptr = base + d->off; out->rows = d->rows; out->cols = d->cols; out->pitch = d->pitch; out->elem_bytes = 4; out->reserved = 0;
+  out->dev_ptr = base + d->off; out->rows = d->rows; out->cols = d->cols; out->pitch = d->pitch; out->elem_bytes = 4; out->is_int = 0;
   return SC_OK;
 }
 
