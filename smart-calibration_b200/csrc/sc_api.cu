@@ -1,8 +1,10 @@
 // C ABI of libsmartcal_b200 (see include/smartcal_b200.h): arena layout, step sequencing, host<->device staging.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -14,8 +16,8 @@
 
 namespace sc {
 size_t rowphase_smem_bytes();
-int rowphase_pick_cluster_size(int want_clusters);
-cudaError_t launch_rowphase(const RowPhaseParams& p, int cluster_size, int nclusters, cudaStream_t st);
+void rowphase_cluster_capacity(int* n16, int* n8);
+cudaError_t launch_rowphase(const RowPhaseParams& p, int cluster_size, int nclusters, int tm, cudaStream_t st);
 size_t wgrad_smem_bytes();
 cudaError_t launch_wgrad(const WgradParams& p, int grid, cudaStream_t st);
 cudaError_t launch_soft_update(const float* src, float* dst, size_t n, float tau, cudaStream_t st);
@@ -48,6 +50,7 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 
 static inline int round4i(int x) { return (x + 3) & ~3; }
+static inline int round32i(int x) { return (x + 31) & ~31; }
 
 // ---- network tensor tables (reference state_dict order) -------------------------------
 struct TDesc {
@@ -58,8 +61,8 @@ struct TDesc {
 struct NetLayout {
   std::vector<TDesc> t;
   size_t size = 0;
-  void add(const char* name, int rows, int cols) {
-    TDesc d{name, rows, cols, round4i(cols), size};
+  void add(const char* name, int rows, int cols, int pitch = 0) {
+    TDesc d{name, rows, cols, pitch ? pitch : round4i(cols), size};
     size += (size_t)rows * d.pitch;
     t.push_back(d);
   }
@@ -72,7 +75,7 @@ struct NetLayout {
 };
 static NetLayout critic_layout(int S, int A) {
   NetLayout L;
-  L.add("fc11.weight", H1, S); L.add("fc11.bias", 1, H1);
+  L.add("fc11.weight", H1, S, round32i(S)); L.add("fc11.bias", 1, H1);   // layer-1 rows padded to whole 32-float TMA k-blocks
   L.add("fc12.weight", H2, H1); L.add("fc12.bias", 1, H2);
   L.add("fc21.weight", HA1, A); L.add("fc21.bias", 1, HA1);
   L.add("fc22.weight", HA2, HA1); L.add("fc22.bias", 1, HA2);
@@ -85,7 +88,7 @@ static NetLayout critic_layout(int S, int A) {
 }
 static NetLayout actor_layout(int S, int A, int kind) {
   NetLayout L;
-  L.add("fc1.weight", H1, S); L.add("fc1.bias", 1, H1);
+  L.add("fc1.weight", H1, S, round32i(S)); L.add("fc1.bias", 1, H1);
   L.add("fc2.weight", H2, H1); L.add("fc2.bias", 1, H2);
   L.add("fc3.weight", H3, H2); L.add("fc3.bias", 1, H3);
   if (kind == SC_KIND_SAC) {
@@ -157,7 +160,10 @@ struct sc_agent {
   void* arena;
   bool owns_arena;
   size_t arena_bytes;
-  int S, Sp, A, Ap, B, C, T;          // T = packed transition length
+  int S, Sp, Sp32, A, Ap, B, C, T;    // T = packed transition length; Sp32 = S padded to whole 32-float k-blocks
+  float *mb_s, *mb_s2;                // [B][Sp32] minibatch gather buffers
+  unsigned char* tmaps;               // device table of CUtensorMap (128 B each)
+  TensorMaps tm_critic, tm_actor, tm_act;   // per-program map pointer sets
   NetLayout Lc, La;
   size_t online_floats;               // actor + c1 + c2
   float *params, *adam_m, *adam_v;    // online blocks
@@ -171,6 +177,7 @@ struct sc_agent {
   std::map<std::string, sc_tensor_info> buffers;
   float *y, *err, *part, *is_w, *is_wsum, *eps[3], *stats, *hint_out, *rho_dev, *ps_out;
   int *bidx, *tree_idx;
+  unsigned long long* tstamp;
   double* u01;
   float *obs_dev, *act_eps, *act_out, *act_aux, *store_stage;
   WgradOp *critic_ops, *actor_ops;
@@ -183,7 +190,7 @@ struct sc_agent {
   double* h_u01;
   float* h_act;
   // state
-  int cluster_size, nclusters, wgrad_grid;
+  int cluster_size, nclusters, tile_tm, wgrad_grid;
   int64_t mem_cntr, learn_counter, data_pointer, data_length;
   int64_t t_actor, t_critic;          // Adam step counts
   double per_beta;
@@ -289,11 +296,18 @@ static size_t carve(sc_agent* a, void* base) {
   a->buffers["batch_idx"].is_int = 1;   // int32
   a->buffers["tree_idx"].is_int = 1;
   a->u01 = (double*)cv.take(sizeof(double) * B);
-  a->obs_dev = cv.f(Sp);
+  a->mb_s = cv.f((size_t)B * a->Sp32);
+  a->mb_s2 = cv.f((size_t)B * a->Sp32);
+  reg("mb_state", a->mb_s, B, S, a->Sp32, 4);
+  reg("mb_new_state", a->mb_s2, B, S, a->Sp32, 4);
+  a->tmaps = (unsigned char*)cv.take(128 * 64);
+  a->obs_dev = cv.f(a->Sp32);
   a->act_eps = cv.f(round4i(A));
   a->act_out = cv.f(round4i(A));
   a->act_aux = cv.f(H1 + H2);
   a->store_stage = cv.f((size_t)a->T * 1);
+  a->tstamp = (unsigned long long*)cv.take(sizeof(unsigned long long) * 8 * 1536);
+  reg("debug_ts", a->tstamp, 1536, 8, 8, 8);
   a->critic_ops = (WgradOp*)cv.take(sizeof(WgradOp) * 16);
   a->actor_ops = (WgradOp*)cv.take(sizeof(WgradOp) * 8);
   a->critic_vops = (VecOp*)cv.take(sizeof(VecOp) * 32);
@@ -320,7 +334,7 @@ static int check_cfg(const sc_config* c) {
 }
 static void init_dims(sc_agent* a, const sc_config* cfg) {
   a->cfg = *cfg;
-  a->S = cfg->state_dim; a->Sp = round4i(a->S);
+  a->S = cfg->state_dim; a->Sp = round4i(a->S); a->Sp32 = round32i(a->S);
   a->A = cfg->n_actions; a->Ap = round4i(a->A);
   a->B = cfg->batch_size; a->C = cfg->mem_size;
   a->T = 2 * a->S + 2 * a->A + 2;
@@ -363,6 +377,90 @@ static void add_v(std::vector<VecOp>& v, int& tiles, const float* D, const float
   v.push_back(o);
 }
 
+// ---- TMA tensor maps ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// row-major float matrix [rows][ld] (ld a multiple of 32), box {32 floats = 128 B, box_rows}, 128-byte swizzle
+static int encode_map(CUtensorMap* out, const void* base, int ld, int rows, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(SC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SC_ERR_CUDA, "cuTensorMapEncodeTiled(ld=%d rows=%d box_rows=%d) failed: %d", ld, rows, box_rows, (int)r);
+  return SC_OK;
+}
+
+static int build_tensor_maps(sc_agent* a) {
+  std::vector<CUtensorMap> host;
+  host.reserve(64);
+  int rc = SC_OK;
+  auto add = [&](const void* base, int ld, int rows, int box_rows) -> const void* {
+    alignas(64) CUtensorMap m;
+    if (rc == SC_OK) rc = encode_map(&m, base, ld, rows, box_rows);
+    host.push_back(m);
+    return a->tmaps + (host.size() - 1) * sizeof(CUtensorMap);
+  };
+  const bool td3 = a->cfg.kind == SC_KIND_TD3;
+  const int B = a->B, K1 = a->Sp32;
+  TensorMaps t;
+  memset(&t, 0, sizeof(t));
+  t.mb_s = add(a->mb_s, K1, B, 32);
+  t.mb_s2 = add(a->mb_s2, K1, B, 32);
+  t.t_h1 = add(a->aw.t_h1, H1, B, 32);
+  t.h1 = add(a->aw.h1, H1, B, 32);
+  t.dz2 = add(a->aw.dz2, H2, B, 32);
+  t.obs = add(a->obs_dev, K1, 1, 32);
+  t.aux = add(a->act_aux, H1, 1, 32);
+  CriticP C[2] = {critic_ptrs(a->params + a->off_c1, a->Lc), critic_ptrs(a->params + a->off_c2, a->Lc)};
+  CriticP T[2] = {critic_ptrs(a->targets + a->toff_c1, a->Lc), critic_ptrs(a->targets + a->toff_c2, a->Lc)};
+  for (int k = 0; k < 2; ++k) {
+    t.th11[k] = add(a->tw[k].h11, H1, B, 32);
+    t.ch11[k] = add(a->cw[k].h11, H1, B, 32);
+    t.ph11[k] = add(a->cw[k].p_h11, H1, B, 32);
+    t.dz12[k] = add(a->cw[k].dz12, H2, B, 32);
+    t.crit_w11[k] = add(C[k].w11, K1, H1, 32);
+    t.crit_w12[k] = add(C[k].w12, H1, H2, 32);
+    t.targ_w11[k] = add(T[k].w11, K1, H1, 32);
+    t.targ_w12[k] = add(T[k].w12, H1, H2, 32);
+    t.crit_w12p[k] = add(C[k].w12, H1, H2, 128);
+  }
+  ActorP on = actor_ptrs(a->params + a->off_actor, a->La, a->cfg.kind);
+  const void* on_w1 = add(on.w1, K1, H1, 32);
+  const void* on_w2 = add(on.w2, H1, H2, 32);
+  t.actor_w2p = add(on.w2, H1, H2, 128);
+  const void *tg_w1 = on_w1, *tg_w2 = on_w2;
+  if (td3) {
+    ActorP tg = actor_ptrs(a->targets + a->toff_actor, a->La, a->cfg.kind);
+    tg_w1 = add(tg.w1, K1, H1, 32);
+    tg_w2 = add(tg.w2, H1, H2, 32);
+  }
+  if (rc != SC_OK) return rc;
+  if (host.size() > 64) return fail(SC_ERR_STATE, "tensor map table overflow");
+  a->tm_critic = t; a->tm_actor = t; a->tm_act = t;
+  a->tm_critic.actor_w1 = td3 ? tg_w1 : on_w1;      // critic phase evaluates the TD3 target actor / the SAC online actor on s'
+  a->tm_critic.actor_w2 = td3 ? tg_w2 : on_w2;
+  a->tm_actor.actor_w1 = on_w1; a->tm_actor.actor_w2 = on_w2;
+  a->tm_act.actor_w1 = on_w1; a->tm_act.actor_w2 = on_w2;
+  CK(cudaMemcpyAsync(a->tmaps, host.data(), host.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, a->st));
+  CK(cudaStreamSynchronize(a->st));
+  return SC_OK;
+}
+
 static int build_op_tables(sc_agent* a) {
   const bool td3 = a->cfg.kind == SC_KIND_TD3;
   std::vector<WgradOp> cw;
@@ -375,7 +473,7 @@ static int build_op_tables(sc_agent* a) {
             T = critic_ptrs(a->targets + toff, a->Lc);
     const CriticWs& w = a->cw[k];
     const int opt = 1 + k;
-    add_w(cw, tiles, w.dz11, H1, a->rp.state, a->Sp, 1, H1, a->S, P.w11, M.w11, V.w11, T.w11, a->Sp, opt);
+    add_w(cw, tiles, w.dz11, H1, a->mb_s, a->Sp32, 0, H1, a->S, P.w11, M.w11, V.w11, T.w11, a->Sp32, opt);
     add_w(cw, tiles, w.dz12, H2, w.h11, H1, 0, H2, H1, P.w12, M.w12, V.w12, T.w12, H1, opt);
     add_w(cw, tiles, w.dz21, HA1, a->rp.action, a->Ap, 1, HA1, a->A, P.w21, M.w21, V.w21, T.w21, a->Ap, opt);
     add_w(cw, tiles, w.dz22, HA2, w.h21, HA1, 0, HA2, HA1, P.w22, M.w22, V.w22, T.w22, HA1, opt);
@@ -410,7 +508,7 @@ static int build_op_tables(sc_agent* a) {
     if (td3) T = actor_ptrs(a->targets + a->toff_actor, a->La, a->cfg.kind);
     const ActorWs& w = a->aw;
     const int A = a->A, ldh = td3 ? A : 2 * A;
-    add_w(awv, tiles, w.dz1, H1, a->rp.state, a->Sp, 1, H1, a->S, P.w1, M.w1, V.w1, T.w1, a->Sp, 0);
+    add_w(awv, tiles, w.dz1, H1, a->mb_s, a->Sp32, 0, H1, a->S, P.w1, M.w1, V.w1, T.w1, a->Sp32, 0);
     add_w(awv, tiles, w.dz2, H2, w.h1, H1, 0, H2, H1, P.w2, M.w2, V.w2, T.w2, H1, 0);
     add_w(awv, tiles, w.dz3, H3, w.h2, H2, 0, H3, H2, P.w3, M.w3, V.w3, T.w3, H2, 0);
     add_w(awv, tiles, w.dhead, ldh, w.h3, H3, 0, A, H3, P.wmu, M.wmu, V.wmu, T.wmu, H3, 0);
@@ -466,15 +564,40 @@ int sc_agent_create(const sc_config* cfg, void* arena, size_t arena_bytes, void*
   a->buffers.clear();
   carve(a, a->arena);
   CK(cudaMemsetAsync(a->arena, 0, need, a->st));
-  const size_t stage_floats = (size_t)3 * a->B * a->A + a->T + a->Sp + 64;
+  const size_t stage_floats = (size_t)3 * a->B * a->A + a->T + a->Sp32 + 64;
   CK(cudaHostAlloc((void**)&a->h_stage, stage_floats * sizeof(float), cudaHostAllocDefault));
   CK(cudaHostAlloc((void**)&a->h_stats, 16 * sizeof(float), cudaHostAllocDefault));
   CK(cudaHostAlloc((void**)&a->h_idx, (size_t)a->B * sizeof(int32_t), cudaHostAllocDefault));
   CK(cudaHostAlloc((void**)&a->h_u01, (size_t)a->B * sizeof(double), cudaHostAllocDefault));
   CK(cudaHostAlloc((void**)&a->h_act, 64 * sizeof(float), cudaHostAllocDefault));
-  a->cluster_size = rowphase_pick_cluster_size(8);
-  a->nclusters = a->cluster_size == 16 ? 8 : 16;        // ~128 CTAs on the 148 SMs
-  while ((a->B + a->nclusters - 1) / a->nclusters > 128) a->nclusters *= 2;
+  {
+    // cluster geometry: 16-CTA clusters (32-row slabs at B=256) when 8 of them are co-resident, otherwise as many
+    // portable 8-CTA clusters as fit on the SMs (16-row tiles, TM=2)
+    int n16 = 0, n8 = 0;
+    rowphase_cluster_capacity(&n16, &n8);
+    const char* force = getenv("SMARTCAL_CLUSTER");
+    if ((n16 >= 8 && !(force && atoi(force) == 8)) || (force && atoi(force) == 16 && n16 >= 1)) {
+      a->cluster_size = 16; a->nclusters = 8;
+    } else if (n8 >= 1) {
+      a->cluster_size = 8; a->nclusters = n8 < 18 ? n8 : 18;
+    } else {
+      a->cluster_size = 0; a->nclusters = 0;
+    }
+    if (a->cluster_size) {
+      while ((a->B + a->nclusters - 1) / a->nclusters > 128) a->nclusters *= 2;
+      if (a->nclusters > a->B) a->nclusters = a->B;
+      // row tile (8*TM rows) that wastes the fewest padded rows for this slab height; ties go to the larger tile
+      const int per = (a->B + a->nclusters - 1) / a->nclusters;
+      int best = 1 << 30;
+      for (int tm = 2; tm <= 4; ++tm) {
+        const int padded = ((per + 8 * tm - 1) / (8 * tm)) * 8 * tm;
+        if (padded <= best) { best = padded; a->tile_tm = tm; }
+      }
+    }
+    if (getenv("SMARTCAL_DEBUG"))
+      fprintf(stderr, "[smartcal] SMs=%d active clusters: 16-CTA=%d 8-CTA=%d -> cluster %d x %d, TM=%d\n", prop.multiProcessorCount,
+              n16, n8, a->cluster_size, a->nclusters, a->tile_tm);
+  }
   if (a->cluster_size == 0) { sc_agent_destroy(a); return fail(SC_ERR_CUDA, "device cannot host an 8-CTA cluster with %zu B of shared memory", rowphase_smem_bytes()); }
   a->wgrad_grid = prop.multiProcessorCount * 2;
   a->mem_cntr = a->learn_counter = a->data_pointer = a->data_length = 0;
@@ -488,6 +611,8 @@ int sc_agent_create(const sc_config* cfg, void* arena, size_t arena_bytes, void*
   a->launches = 0;
   a->timing = false;
   rc = build_op_tables(a);
+  if (rc) { sc_agent_destroy(a); return rc; }
+  rc = build_tensor_maps(a);
   if (rc) { sc_agent_destroy(a); return rc; }
   *out = a;
   return SC_OK;
@@ -704,6 +829,9 @@ static void fill_common(sc_agent* a, RowPhaseParams& p) {
   p.alpha = a->alpha;
   p.maxa = a->cfg.max_action;
   p.n_q = a->cfg.kind == SC_KIND_SAC ? 2 : 1;
+  p.mb_s = a->mb_s; p.mb_s2 = a->mb_s2; p.Sp32 = a->Sp32;
+  p.tstamp = getenv("SMARTCAL_STAMPS") ? a->tstamp : nullptr;
+  p.dbg = getenv("SMARTCAL_DBG") ? atoi(getenv("SMARTCAL_DBG")) : 0;
 }
 static AdamHyper adam_hyper(double lr, int64_t t) {
   // torch/optim/adam.py::_single_tensor_adam scalar math, in double like Python floats
@@ -746,7 +874,7 @@ static int run_rowphase(sc_agent* a, const RowPhaseParams& p, int timer_id) {
   cudaEvent_t e0, e1;
   if (timer_id >= 0) timer_begin(a, timer_id, &e0, &e1);
   const int ncl = p.program == PROG_ACT ? 1 : a->nclusters;
-  CK(launch_rowphase(p, a->cluster_size, ncl, a->st));
+  CK(launch_rowphase(p, a->cluster_size, ncl, p.program == PROG_ACT ? 2 : a->tile_tm, a->st));
   if (timer_id >= 0) timer_end(a, timer_id, e0, e1);
   a->launches++;
   return SC_OK;
@@ -766,12 +894,13 @@ int sc_agent_act(sc_agent* a, const float* obs_host, const float* eps_host, floa
   if (!a || !obs_host || !action_host_out) return fail(SC_ERR_ARG, "null argument");
   CK(cudaStreamSynchronize(a->st));
   float* h = a->h_stage;
-  memset(h, 0, (size_t)a->Sp * sizeof(float));
+  memset(h, 0, (size_t)a->Sp32 * sizeof(float));
   memcpy(h, obs_host, (size_t)a->S * sizeof(float));
-  CK(cudaMemcpyAsync(a->obs_dev, h, (size_t)a->Sp * sizeof(float), cudaMemcpyHostToDevice, a->st));
+  CK(cudaMemcpyAsync(a->obs_dev, h, (size_t)a->Sp32 * sizeof(float), cudaMemcpyHostToDevice, a->st));
   RowPhaseParams p;
   fill_common(a, p);
   p.program = PROG_ACT;
+  p.tm = a->tm_act;
   p.B = 1;
   p.actor = actor_ptrs(a->params + a->off_actor, a->La, a->cfg.kind);
   p.obs = a->obs_dev;
@@ -845,6 +974,7 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
   RowPhaseParams p;
   fill_common(a, p);
   p.program = PROG_CRITIC;
+  p.tm = a->tm_critic;
   if (sac) {
     p.actor = actor_ptrs(a->params + a->off_actor, a->La, a->cfg.kind);
     p.eps = a->eps[0];
@@ -873,6 +1003,7 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
   if (actor_step) {
     fill_common(a, p);
     p.program = PROG_ACTOR;
+    p.tm = a->tm_actor;
     p.actor = actor_ptrs(a->params + a->off_actor, a->La, a->cfg.kind);
     p.eps = sac ? a->eps[1] : nullptr;
     if (sac && a->cfg.use_hint) {

@@ -3,8 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define SC_THREADS 256          // threads per CTA in every compute kernel
+#define SC_THREADS 256          // compute ("consumer") threads per CTA in every kernel
 #define SC_WARPS 8
+#define SC_ROW_THREADS 288      // row-phase kernel: 8 consumer warps + 1 TMA producer warp
 #define SC_MT 32                // batch rows per GEMM sub-tile
 #define SC_MAX_CLUSTER 16
 #define SC_LN_EPS 1e-5f         // nn.LayerNorm default eps (ref enet_sac.py:365-368)
@@ -35,8 +36,49 @@ __device__ __forceinline__ unsigned num_clusters() {
 // Release/acquire barrier over every thread of the cluster: global-memory writes made before it by any CTA
 // of the cluster are visible to every CTA of the cluster after it.
 __device__ __forceinline__ void cluster_sync() {
+  // generic-proxy global writes made before the barrier are later read through the async proxy (TMA bulk copies)
+  asm volatile("fence.proxy.async;\n" ::: "memory");
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+// barrier over the 256 consumer threads only (the producer warp never joins it)
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+
+// ---- mbarrier + TMA bulk copy (1-D cp.async.bulk, global -> shared, completion counted in bytes) -----------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(float* smem_dst, const float* gsrc, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// 2-D tiled TMA load through a CUtensorMap that lives in global memory: box {32 floats, rows} with 128-byte swizzle
+__device__ __forceinline__ void tma_load_2d(float* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // ---- loads ------------------------------------------------------------------------------------------

@@ -7,7 +7,7 @@ namespace sc {
 // hidden widths of the reference elastic-net MLPs (ref enet_sac.py:357-363,415-419)
 constexpr int H1 = 512, H2 = 256, H3 = 128, HA1 = 128, HA2 = 64, HCAT = H2 + HA2;
 constexpr int AMAX = 32;          // max n_actions supported by the row-local tail
-constexpr int RT = 2;             // rows a CTA carries through the row-local tail at once
+constexpr int RT = 4;             // rows a CTA carries through the row-local tail at once (the tail is latency-bound: one pass)
 
 struct CriticP {                   // one CriticNetwork: PyTorch-native row-major W[out][in], pitch = roundup4(in)
   float *w11, *b11, *w12, *b12, *w21, *b21, *w22, *b22, *w3, *b3;
@@ -47,6 +47,20 @@ struct ReplayP {
 
 enum RowProgram { PROG_CRITIC = 0, PROG_ACTOR = 1, PROG_ACT = 2 };
 
+// CUtensorMap descriptors (device pointers into a host-encoded table) of every matrix the cluster-tiled stages stream
+// through TMA.  "A" maps: activations [rows][ld] box {32 floats, 32 rows}; "W" maps: weights [N][ld] same box;
+// "P" maps: weight panels for dgrad, box {32 floats, 128 rows}.
+struct TensorMaps {
+  const void *mb_s, *mb_s2;                  // gathered minibatch states / next states [B][Sp32]
+  const void *t_h1, *th11[2], *ch11[2];      // critic phase, layer-1 outputs
+  const void *h1, *ph11[2];                  // actor phase, layer-1 outputs
+  const void *dz12[2], *dz2;                 // dgrad inputs
+  const void *obs, *aux;                     // PROG_ACT
+  const void *actor_w1, *actor_w2;           // actor evaluated in this phase (online or target)
+  const void *crit_w11[2], *crit_w12[2], *targ_w11[2], *targ_w12[2];
+  const void *actor_w2p, *crit_w12p[2];      // dgrad panels
+};
+
 struct RowPhaseParams {
   int program, kind;                         // RowProgram, SC_KIND_*
   int B, S, Sp, A, Ap;
@@ -57,6 +71,9 @@ struct RowPhaseParams {
   TargetWs tw[2];
   ActorWs aw;
   ReplayP rp;
+  TensorMaps tm;
+  float *mb_s, *mb_s2;                       // [B][Sp32] minibatch gather buffers (zero padded to a multiple of 32 columns)
+  int Sp32;
   const int* bidx;                           // [B] replay slots of the minibatch
   const float* eps;                          // [B][A] N(0,1) for this phase (nullptr: none)
   const float* is_wsum;                      // device scalar: sum of IS weights (PER) or nullptr
@@ -71,6 +88,8 @@ struct RowPhaseParams {
   const float* obs;                          // [Sp]
   float* act_out;                            // [A]
   float* act_aux;                            // scratch [H1 + H2] activations for the single row
+  int dbg;                                   // profiling experiments: 1 = skip the FFMA work, 2 = skip the operand copies
+  unsigned long long* tstamp;                // optional [CTAs][8] globaltimer stamps at stage boundaries (debug/profiling)
 };
 
 // ---- wgrad + Adam (+ target soft update) work list ------------------------------------------------------

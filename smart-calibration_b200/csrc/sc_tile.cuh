@@ -11,58 +11,79 @@
 
 namespace sc {
 
-// ---- forward: rows rg+8i (i<4), cols cg+4j (j<TN); operands read as float4 along k --------------------
-// sA: [32][pa] activations, sW: [4*TN][pw] weight slice; pa, pw = smem_pitch(K) -> conflict-free LDS.128.
-template <int TN>
-__device__ __forceinline__ void mma_nt(const float* __restrict__ sA, int pa, const float* __restrict__ sW, int pw,
-                                       int q0, int q1, float (&acc)[4][TN]) {
+// ---- K-chunked operand ring ------------------------------------------------------------------------------------
+// Both GEMM operands stream through a NSTAGE-deep ring of shared-memory slots.  A dedicated producer warp fills a
+// slot with 2-D tiled TMA loads (cp.async.bulk.tensor, one box of 32 rows x 32 floats per op, 128-byte swizzle)
+// that complete on the slot's "full" mbarrier; the 8 consumer warps release it through the "empty" mbarrier.
+// Slot layout: A part [8 k-blocks][32 rows][32 floats], W part the same (dgrad: [256 n][32 cols] as two 128-row panels).
+// With SWIZZLE_128B the 16-byte chunk c of row r sits at chunk position c ^ (r & 7), which is exactly what makes the
+// register-tile reads below conflict-free: lanes that read rows r, r+1, .., r+7 at the same k hit 8 different chunks.
+constexpr int KC = 256;            // reduction elements per slot (8 k-blocks of 32 floats = 128 bytes)
+constexpr int KBLK = KC / 32;
+constexpr int NSTAGE = 2;          // slots (64 KB each): the producer fills one while the consumers work on the other
+constexpr int BOXF = 32 * 32;      // floats per TMA box
+constexpr int SLOT_A = KBLK * BOXF;
+constexpr int SLOT_W = KBLK * BOXF;   // dgrad: two [128 n][32 cols] panels
+constexpr int SLOT = SLOT_A + SLOT_W;
+
+// ---- forward: rows rg+8i (i<TM), cols cg+4j (j<TN); operands read as float4 along k -------------------------
+template <int TM, int TN>
+__device__ __forceinline__ void mma_nt(const float* __restrict__ sA, const float* __restrict__ sW, int q0, int q1,
+                                       float (&acc)[TM][TN]) {
   const int lane = threadIdx.x & 31, rg = lane >> 2, cg = lane & 3;
-  const float* a0 = sA + rg * pa;
-  const float* b0 = sW + cg * pw;
 #pragma unroll 2
   for (int q = q0; q < q1; ++q) {
-    float4 a[4];
+    const int kb = q >> 3, c = q & 7;
+    const float* ab = sA + kb * BOXF + rg * 32 + ((c ^ rg) << 2);              // (row & 7) == rg for rows rg + 8i
+    const float* bb = sW + kb * BOXF + cg * 32;
+    const int x0 = (c ^ cg) << 2, x1 = (c ^ (cg + 4)) << 2;                    // (row & 7) for rows cg + 4j
+    float4 a[TM];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + (8 * i) * pa + 4 * q);
+    for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(ab + 256 * i);
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
-      const float4 b = *reinterpret_cast<const float4*>(b0 + (4 * j) * pw + 4 * q);
+      const float4 b = *reinterpret_cast<const float4*>(bb + 128 * j + ((j & 1) ? x1 : x0));
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i][j] = dot4(a[i], b, acc[i][j]);
+      for (int i = 0; i < TM; ++i) acc[i][j] = dot4(a[i], b, acc[i][j]);
     }
   }
 }
 __device__ __forceinline__ int nt_row(int lane, int i) { return (lane >> 2) + 8 * i; }
 __device__ __forceinline__ int nt_col(int lane, int j) { return (lane & 3) + 4 * j; }
 
-// ---- dgrad: rows rg+8i, cols cg*TN+j; A read as float4 along n, W panel sW[n][4*TN] -------------------
-template <int TN>
-__device__ __forceinline__ void mma_nn(const float* __restrict__ sA, int pa, const float* __restrict__ sW, int pw,
-                                       int q0, int q1, float (&acc)[4][TN]) {
+// ---- dgrad: rows rg+8i, cols cg*TN+j; A read as float4 along n, W panel sW[n][32 cols] (swizzled rows) -----------
+template <int TM, int TN>
+__device__ __forceinline__ void mma_nn(const float* __restrict__ sA, const float* __restrict__ sW, int q0, int q1,
+                                       float (&acc)[TM][TN]) {
   const int lane = threadIdx.x & 31, rg = lane >> 2, cg = lane & 3;
-  const float* a0 = sA + rg * pa;
-  const float* b0 = sW + cg * TN;
 #pragma unroll 1
   for (int q = q0; q < q1; ++q) {
-    float4 a[4];
+    const int kb = q >> 3, c = q & 7;
+    const float* ab = sA + kb * BOXF + rg * 32 + ((c ^ rg) << 2);
+    float4 a[TM];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + (8 * i) * pa + 4 * q);
+    for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(ab + 256 * i);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
+      const int n = 4 * q + s;                       // panel row (reduction index inside the chunk)
+      const float* bp = sW + n * 32;
+      const int sw = n & 7;
       float b[TN];
-      const float* bp = b0 + (4 * q + s) * pw;
       if constexpr (TN % 4 == 0) {
 #pragma unroll
         for (int j = 0; j < TN; j += 4) {
-          const float4 v = *reinterpret_cast<const float4*>(bp + j);
+          const float4 v = *reinterpret_cast<const float4*>(bp + ((((cg * TN + j) >> 2) ^ sw) << 2));
           b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < TN; ++j) b[j] = bp[j];
+        for (int j = 0; j < TN; ++j) {
+          const int col = cg * TN + j;
+          b[j] = bp[(((col >> 2) ^ sw) << 2) + (col & 3)];
+        }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < TM; ++i) {
         const float av = s == 0 ? a[i].x : s == 1 ? a[i].y : s == 2 ? a[i].z : a[i].w;
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av, b[j], acc[i][j]);
@@ -92,50 +113,31 @@ __device__ __forceinline__ void mma_tn(const float* __restrict__ sD, const float
 }
 
 // ---- split-reduction combine: every warp parks its partial tile, then 256 threads add the 8 partials -----
-// red: [8][32][NT+4] floats.  Result (plus optional bias over columns) lands in sZ[32][NT] (pitch NT).
-template <int TN, bool NN>
-__device__ __forceinline__ void park_partial(float* red, const float (&acc)[4][TN]) {
+// red: [8][32][NT+4] floats.  Result (plus optional bias over columns) lands in sZ[8*TM][NT] (pitch NT).
+template <int TM, int TN, bool NN>
+__device__ __forceinline__ void park_partial(float* red, const float (&acc)[TM][TN]) {
   constexpr int NT = 4 * TN, P = NT + 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* base = red + warp * 32 * P;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int c = NN ? nn_col<TN>(lane, j) : nt_col(lane, j);
       base[nt_row(lane, i) * P + c] = acc[i][j];
     }
 }
-template <int TN>
+template <int TM, int TN>
 __device__ __forceinline__ void combine_partials(const float* red, float* sZ, const float* __restrict__ bias_slice,
                                                  int ncv) {
   constexpr int NT = 4 * TN, P = NT + 4;
-  for (int e = threadIdx.x; e < 32 * NT; e += SC_THREADS) {
+  for (int e = threadIdx.x; e < 8 * TM * NT; e += SC_THREADS) {   // consumer threads only (tid < 256)
     const int r = e / NT, c = e % NT;
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < SC_WARPS; ++w) s += red[(w * 32 + r) * P + c];
     if (bias_slice != nullptr && c < ncv) s += ld_w(bias_slice + c);
     sZ[r * NT + c] = s;
-  }
-}
-
-// ---- staging: copy `nrows_valid` rows of `k4` float4 into a [32][pitch] smem tile, zero-filling the rest ----
-// row_ptr(r) returns the global address of row r.  Warp w serves rows w, w+8, w+16, w+24 (no integer division).
-template <bool ACT, typename RowPtr>
-__device__ __forceinline__ void stage_rows(float* sm, int pitch, int nrows_total, int nrows_valid, int k4, RowPtr row_ptr) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int r = warp; r < nrows_total; r += SC_WARPS) {
-    float* dst = sm + r * pitch;
-    if (r < nrows_valid) {
-      const float* src = row_ptr(r);
-      for (int c = lane; c < k4; c += 32) {
-        const float4 v = ACT ? ld_act4(src + 4 * c) : ld_w4(src + 4 * c);
-        *reinterpret_cast<float4*>(dst + 4 * c) = v;
-      }
-    } else {
-      for (int c = lane; c < k4; c += 32) *reinterpret_cast<float4*>(dst + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
   }
 }
 

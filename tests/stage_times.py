@@ -1,0 +1,37 @@
+"""Stage-boundary timestamps of the critic row-phase kernel (SMARTCAL_STAMPS=1): where does a CTA spend its time?"""
+import os, sys
+os.environ["SMARTCAL_STAMPS"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, bench
+agent, _ = bench.make_agent(100, "device")
+dev = agent._dev
+for _ in range(5):
+    dev.learn()
+torch.cuda.synchronize()
+# the actor phase also stamps slot 0 only; run the critic phase alone by reading after a full step (slots 1..5 are critic-only)
+ts = dev.buffer("debug_ts").view(torch.int64).cpu().numpy()
+ncta = int((ts[:512, 1] != 0).sum())
+ts = ts[:ncta].astype(np.float64)
+names = ["stage1 (5x fc1/fc11)", "stage2 (5x fc2/fc12)", "tail", "cluster barrier", "dgrad"]
+t0 = ts[:, 1:].min()
+print("CTAs", ncta)
+for i, n in enumerate(names):
+    d = (ts[:, i + 2] - ts[:, i + 1]) if i > 0 else (ts[:, 1] - ts[:, 1] * 0)
+for i, n in enumerate(names):
+    a, b = (ts[:, i + 1], ts[:, i + 2]) if i > 0 else (None, None)
+print("per-CTA durations (us): mean / min / max")
+for i, n in enumerate(names[1:], start=1):
+    d = (ts[:, i + 1] - ts[:, i]) / 1e3
+    print(f"  {n:24s} {d.mean():8.1f} {d.min():8.1f} {d.max():8.1f}")
+t2 = dev.buffer("debug_ts").view(torch.int64).cpu().numpy()[512:512 + ncta].astype(np.float64)
+print("inside stage 2: tiles | barrier1 | finalize | barrier2 (us, mean/min/max)")
+prev = ts[:, 1]
+for i, n in enumerate(["gemm tiles", "cluster barrier 1", "LN finalize", "cluster barrier 2"]):
+    d = (t2[:, i] - prev) / 1e3
+    print(f"  {n:24s} {d.mean():8.1f} {d.min():8.1f} {d.max():8.1f}")
+    prev = t2[:, i]
+pr = dev.buffer("debug_ts").view(torch.int64).cpu().numpy()[1024:1024 + ncta].astype(np.float64) / 1.965e3
+print("thread-0 cycle accumulators over stages 1+2 (us @1.965 GHz, mean over CTAs):")
+for i, n in enumerate(["wait full barrier", "mma (FFMA loop)", "park+combine (2 syncs)", "tile epilogue (stats, stores)", "LN combine", "LN combine+normalise"]):
+    print(f"  {n:32s} {pr[:, i].mean():8.1f}")
+print("  (stage1 starts at the actor-phase stamp of slot 0, so it is derived from the kernel time minus the rest)")
