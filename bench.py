@@ -186,14 +186,51 @@ def run_ours(args):
                "h2d_bytes_per_step": (2 * S + 2 * A + 2) * 4 + B * 8 + 2 * B * A * 4, "d2h_bytes_per_step": 48,
                "mode": "store_transition(host obs) + learn() + loss readback, rng='reference' (host numpy/torch draws)"}
 
+    # config 5 topology (world > 1): rank 0 = learner, ranks >= 1 = actors; per episode ONE NCCL broadcast of the actor
+    # block + ONE gather of 100-transition blocks, then the learner ingests them (store + learn per transition)
+    al = None
+    if world > 1:
+        from smartcal_b200.elasticnet import distributed_per_sac as D
+        ex = D.Exchange(torch.device("cuda", local))
+        T = 2 * S + 2 * A + 2
+        flat = agent.actor.flat()
+        blk = torch.randn(D.TRANSITIONS_PER_EPISODE, T, device="cuda")
+        blk[:, -1] = 0
+        episodes = 3
+        for ep in range(episodes + 1):          # first episode is warm-up
+            if ep == 1:
+                barrier()
+                t_ex, t_all = 0.0, time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ex.broadcast_actor(flat)
+            parts = ex.gather_blocks(blk)
+            e1.record()
+            if rank == 0:
+                for b in parts:
+                    for i in range(b.shape[0]):
+                        dev.store_dev(b, i, 1, 0.0)
+                        dev.learn()
+            torch.cuda.synchronize()
+            if ep >= 1:
+                t_ex += e0.elapsed_time(e1)
+        barrier()
+        dt = time.perf_counter() - t_all
+        al = {"episodes": episodes, "actors": world - 1, "learner_steps_per_s": episodes * (world - 1) * 100 / dt,
+              "exchange_ms_per_episode": t_ex / episodes,
+              "bytes_per_episode": {"broadcast_actor": int(flat.numel() * 4), "gather_transitions_per_actor": int(blk.numel() * 4)}}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peak, peak_src = peaks()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("critic_rowphase_dram_bytes")
     crit_s = kern["critic_rowphase"]["avg_us"] * 1e-6
     roof = {"bound": "hbm", "kernel": "k_rowphase<PROG_CRITIC>", "achieved": CRITIC_PHASE_BYTES / crit_s / 1e9, "peak": peak,
-            "unit": "GB/s", "frac": CRITIC_PHASE_BYTES / crit_s / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+            "unit": "GB/s", "frac": CRITIC_PHASE_BYTES / crit_s / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": CRITIC_PHASE_BYTES,
             "fp32_ffma": {"achieved_tflops": CRITIC_PHASE_FLOP / crit_s / 1e12, "peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12,
                           "note": "the kernel is FP32-FFMA-bound, not HBM-bound (DESIGN.md)"},
@@ -207,13 +244,16 @@ def run_ours(args):
                       "rng": "device Philox", "parallelism": "replicas" if world > 1 else "single agent"},
            "l2_warm": {"value": world * args.steps / (ms_warm * 1e-3), "ms_per_step": ms_warm / args.steps},
            "e2e": e2e, "gpu_launches": int(launches), "kernels": kern, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+    if al is not None:
+        out["actor_learner"] = al
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
 def cpu_baseline(sample_seconds=12.0, steps=None, warmup=5):
-    """oracle port of the reference learn() on the host cores (all threads torch will use)"""
+    """oracle port of the reference learn() on the host cores.  torch's default thread count (all cores) is not the
+    fastest setting for these small layers, so a few thread counts are tried briefly and the best one is timed."""
     from oracle.sac_ref import SacRef
     from smartcal_b200.synth import make_transitions
     torch.manual_seed(0)
@@ -222,8 +262,18 @@ def cpu_baseline(sample_seconds=12.0, steps=None, warmup=5):
     tr = make_transitions(100, C, S, A, "normal", 0.0)
     for i in range(C):
         orc.store_flat(tr["state"][i], tr["action"][i], float(tr["reward"][i]), tr["new_state"][i], False, tr["hint"][i])
-    for _ in range(warmup):
-        orc.learn()
+    default_threads = torch.get_num_threads()
+    tried = {}
+    for nt in sorted({default_threads, min(default_threads, 32), min(default_threads, 16), min(default_threads, 8)}, reverse=True):
+        torch.set_num_threads(nt)
+        for _ in range(warmup):
+            orc.learn()
+        t0 = time.perf_counter()
+        for _ in range(8):
+            orc.learn()
+        tried[nt] = 8 / (time.perf_counter() - t0)
+    best = max(tried, key=tried.get)
+    torch.set_num_threads(best)
     n, t0 = 0, time.perf_counter()
     while True:
         orc.learn()
@@ -231,9 +281,11 @@ def cpu_baseline(sample_seconds=12.0, steps=None, warmup=5):
         el = time.perf_counter() - t0
         if (steps is not None and n >= steps) or (steps is None and el >= sample_seconds):
             break
-    return {"value": n / el, "unit": "learn steps/s", "cores": torch.get_num_threads(), "kind": "port",
+    torch.set_num_threads(default_threads)
+    return {"value": n / el, "unit": "learn steps/s", "cores": best, "kind": "port",
             "sample": f"{n} learn() steps of the same workload in {el:.1f} s (oracle/sac_ref.py, torch {torch.__version__} CPU, "
-                      f"{torch.get_num_threads()} threads of {os.cpu_count()} logical cores)", "ms_per_step": el / n * 1e3}
+                      f"{best} threads = best of {{{', '.join(f'{k}: {v:.1f}/s' for k, v in sorted(tried.items()))}}}, "
+                      f"{os.cpu_count()} logical cores)", "ms_per_step": el / n * 1e3}
 
 
 def run_reference(args):
