@@ -263,8 +263,12 @@ def cpu_baseline(sample_seconds=12.0, steps=None, warmup=5):
     for i in range(C):
         orc.store_flat(tr["state"][i], tr["action"][i], float(tr["reward"][i]), tr["new_state"][i], False, tr["hint"][i])
     default_threads = torch.get_num_threads()
+    ncpu = os.cpu_count() or 1
     tried = {}
-    for nt in sorted({default_threads, min(default_threads, 32), min(default_threads, 16), min(default_threads, 8)}, reverse=True):
+    # (torchrun exports OMP_NUM_THREADS=1, a bare python run defaults to every core: neither is the best for these small
+    #  layers, so sweep.  The widest settings are only probed when they are the process default.)
+    cands = {1, 2, 4, 8, 16, default_threads} | ({32} if ncpu >= 32 else set())
+    for nt in sorted(c for c in cands if c <= ncpu):
         torch.set_num_threads(nt)
         for _ in range(warmup):
             orc.learn()
@@ -303,6 +307,17 @@ def run_reference(args):
 
 
 if __name__ == "__main__":
+    # libraries (NCCL) print banners on fd 1; the contract is ONE JSON line on stdout, so fd 1 is pointed at stderr
+    # while the benchmark runs and the JSON line is written to the saved original stdout
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*a, **k):          # noqa: A001
+        k.setdefault("file", _real_stdout)
+        _print(*a, **k)
+        _real_stdout.flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
