@@ -15,9 +15,9 @@
 #include "sc_params.h"
 
 namespace sc {
-size_t rowphase_smem_bytes();
-void rowphase_cluster_capacity(int* n16, int* n8);
-cudaError_t launch_rowphase(const RowPhaseParams& p, int cluster_size, int nclusters, int tm, cudaStream_t st);
+size_t rowphase_smem_bytes(int variant);
+void rowphase_cluster_capacity(int* out4);
+cudaError_t launch_rowphase(const RowPhaseParams& p, int variant, int cluster_size, int nclusters, int tm, cudaStream_t st);
 size_t wgrad_smem_bytes();
 cudaError_t launch_wgrad(const WgradParams& p, int grid, cudaStream_t st);
 cudaError_t launch_soft_update(const float* src, float* dst, size_t n, float tau, cudaStream_t st);
@@ -26,7 +26,8 @@ cudaError_t launch_replay_fill(const ReplayP& rp, const float* tr, int n, cudaSt
 cudaError_t launch_tree_build(double* tree, int C, const double* pr, int n, cudaStream_t st);
 cudaError_t launch_per_sample(const double* tree, int C, int B, const double* u01, uint64_t seed, uint64_t ctr, double beta,
                               int* tree_idx, int* data_idx, float* is_w, float* is_wsum, cudaStream_t st);
-cudaError_t launch_per_update(double* tree, int C, int B, const int* idx, const float* err, float clip, float* ps_out, cudaStream_t st);
+cudaError_t launch_per_update(double* tree, int C, int B, const int* idx, const float* err, float clip, float* ps_out,
+                              const float* ps_in, cudaStream_t st);
 cudaError_t launch_sample_uniform(int n, int B, uint64_t seed, uint64_t ctr, int* out, cudaStream_t st);
 cudaError_t launch_fill_normal(float* out, int n, uint64_t seed, uint64_t stream, cudaStream_t st);
 cudaError_t launch_hint_coef(const float* pi, const float* hint, int Ap, const int* bidx, int B, int A, float thr, float admm_rho,
@@ -181,6 +182,7 @@ struct sc_agent {
   double* u01;
   float *obs_dev, *act_eps, *act_out, *act_aux, *store_stage;
   WgradOp *critic_ops, *actor_ops;
+  int *critic_tile_map, *actor_tile_map;
   VecOp *critic_vops, *actor_vops;
   int n_critic_ops, n_critic_vops, n_actor_ops, n_actor_vops, critic_tiles, actor_tiles;
   // pinned host staging
@@ -190,7 +192,7 @@ struct sc_agent {
   double* h_u01;
   float* h_act;
   // state
-  int cluster_size, nclusters, tile_tm, wgrad_grid;
+  int row_variant, cluster_size, nclusters, tile_tm, wgrad_grid;
   int64_t mem_cntr, learn_counter, data_pointer, data_length;
   int64_t t_actor, t_critic;          // Adam step counts
   double per_beta;
@@ -311,6 +313,8 @@ static size_t carve(sc_agent* a, void* base) {
   a->critic_ops = (WgradOp*)cv.take(sizeof(WgradOp) * 16);
   a->actor_ops = (WgradOp*)cv.take(sizeof(WgradOp) * 8);
   a->critic_vops = (VecOp*)cv.take(sizeof(VecOp) * 32);
+  a->critic_tile_map = (int*)cv.take(sizeof(int) * 4096);
+  a->actor_tile_map = (int*)cv.take(sizeof(int) * 2048);
   a->actor_vops = (VecOp*)cv.take(sizeof(VecOp) * 16);
   reg("state_memory", rp.state, C, S, Sp, 4);
   reg("new_state_memory", rp.new_state, C, S, Sp, 4);
@@ -494,6 +498,20 @@ static int build_op_tables(sc_agent* a) {
     add_v(cv, tiles, w.dq, nullptr, 1, 1, P.b3, M.b3, V.b3, T.b3, opt);
   }
   a->n_critic_ops = (int)cw.size(); a->n_critic_vops = (int)cv.size(); a->critic_tiles = tiles;
+  auto tile_table = [](const std::vector<WgradOp>& w, const std::vector<VecOp>& v, int total) {
+    std::vector<int> t(total, -1);
+    for (size_t i = 0; i < w.size(); ++i)
+      for (int k = 0; k < w[i].tile_count; ++k) t[w[i].tile_base + k] = (int)i;
+    for (size_t i = 0; i < v.size(); ++i)
+      for (int k = 0; k < v[i].tile_count; ++k) t[v[i].tile_base + k] = 1000 + (int)i;
+    return t;
+  };
+  if (tiles > 4096) return fail(SC_ERR_STATE, "critic tile table overflow (%d)", tiles);
+  {
+    std::vector<int> tt = tile_table(cw, cv, tiles);
+    CK(cudaMemcpyAsync(a->critic_tile_map, tt.data(), tt.size() * sizeof(int), cudaMemcpyHostToDevice, a->st));
+    CK(cudaStreamSynchronize(a->st));
+  }
   CK(cudaMemcpyAsync(a->critic_ops, cw.data(), cw.size() * sizeof(WgradOp), cudaMemcpyHostToDevice, a->st));
   CK(cudaMemcpyAsync(a->critic_vops, cv.data(), cv.size() * sizeof(VecOp), cudaMemcpyHostToDevice, a->st));
 
@@ -526,6 +544,12 @@ static int build_op_tables(sc_agent* a) {
     if (!td3) add_v(avv, tiles, w.dhead + A, nullptr, ldh, A, P.bls, M.bls, V.bls, T.bls, 0);
   }
   a->n_actor_ops = (int)awv.size(); a->n_actor_vops = (int)avv.size(); a->actor_tiles = tiles;
+  if (tiles > 2048) return fail(SC_ERR_STATE, "actor tile table overflow (%d)", tiles);
+  {
+    std::vector<int> tt = tile_table(awv, avv, tiles);
+    CK(cudaMemcpyAsync(a->actor_tile_map, tt.data(), tt.size() * sizeof(int), cudaMemcpyHostToDevice, a->st));
+    CK(cudaStreamSynchronize(a->st));
+  }
   CK(cudaMemcpyAsync(a->actor_ops, awv.data(), awv.size() * sizeof(WgradOp), cudaMemcpyHostToDevice, a->st));
   CK(cudaMemcpyAsync(a->actor_vops, avv.data(), avv.size() * sizeof(VecOp), cudaMemcpyHostToDevice, a->st));
   CK(cudaStreamSynchronize(a->st));
@@ -571,34 +595,43 @@ int sc_agent_create(const sc_config* cfg, void* arena, size_t arena_bytes, void*
   CK(cudaHostAlloc((void**)&a->h_u01, (size_t)a->B * sizeof(double), cudaHostAllocDefault));
   CK(cudaHostAlloc((void**)&a->h_act, 64 * sizeof(float), cudaHostAllocDefault));
   {
-    // cluster geometry: 16-CTA clusters (32-row slabs at B=256) when 8 of them are co-resident, otherwise as many
-    // portable 8-CTA clusters as fit on the SMs (16-row tiles, TM=2)
-    int n16 = 0, n8 = 0;
-    rowphase_cluster_capacity(&n16, &n8);
-    const char* force = getenv("SMARTCAL_CLUSTER");
-    if ((n16 >= 8 && !(force && atoi(force) == 8)) || (force && atoi(force) == 16 && n16 >= 1)) {
-      a->cluster_size = 16; a->nclusters = 8;
-    } else if (n8 >= 1) {
-      a->cluster_size = 8; a->nclusters = n8 < 18 ? n8 : 18;
-    } else {
-      a->cluster_size = 0; a->nclusters = 0;
+    // Row-phase geometry.  Candidates are (variant, cluster size); each gets as many clusters as are co-resident (at most
+    // one per 8-row group) and is scored by the padded GEMM work one SM has to issue:
+    //     ctas_per_sm * ceil(rows_per_cluster / (8 TM)) * 8 TM * (512 / cluster_size) columns
+    // times a penalty for small register tiles (shared-memory-pipe bound) and a bonus for two co-resident CTAs
+    // (they overlap each other's latencies).
+    int cap[4] = {0, 0, 0, 0};
+    rowphase_cluster_capacity(cap);
+    const char* force = getenv("SMARTCAL_GEOM");       // "variant,cs" e.g. "1,8" pins a geometry (profiling)
+    int fv = 0, fc = 0;
+    if (force) sscanf(force, "%d,%d", &fv, &fc);
+    double best = 1e30;
+    a->cluster_size = 0;
+    // measured on B200 (profiles/r1_geometry.md): at B=256 the 2-CTA/SM variant with 32 clusters of 8 rows is the fastest
+    if (!force && cap[3] >= (a->B + 7) / 8) {
+      best = 0; a->row_variant = 2; a->cluster_size = 8; a->nclusters = (a->B + 7) / 8; a->tile_tm = 1;
     }
-    if (a->cluster_size) {
-      while ((a->B + a->nclusters - 1) / a->nclusters > 128) a->nclusters *= 2;
-      if (a->nclusters > a->B) a->nclusters = a->B;
-      // row tile (8*TM rows) that wastes the fewest padded rows for this slab height; ties go to the larger tile
-      const int per = (a->B + a->nclusters - 1) / a->nclusters;
-      int best = 1 << 30;
-      for (int tm = 2; tm <= 4; ++tm) {
+    for (int c = 0; c < 4; ++c) {
+      const int variant = c < 2 ? 1 : 2, cs = (c & 1) ? 8 : 16;
+      if (cap[c] < 1 || (fv && (fv != variant || fc != cs))) continue;
+      const int tm_max = variant == 1 ? 4 : 2, tm_min = variant == 1 ? 2 : 1;
+      int ncl = cap[c];
+      if (ncl > (a->B + 7) / 8) ncl = (a->B + 7) / 8;
+      while ((a->B + ncl - 1) / ncl > 128) ncl *= 2;                 // slab height limit of the LayerNorm staging buffers
+      const int per = (a->B + ncl - 1) / ncl;
+      for (int tm = tm_min; tm <= tm_max; ++tm) {
         const int padded = ((per + 8 * tm - 1) / (8 * tm)) * 8 * tm;
-        if (padded <= best) { best = padded; a->tile_tm = tm; }
+        const int waves = (ncl + cap[c] - 1) / cap[c];
+        const double lds_pen = fmax(1.0, 2.0 * (tm + 8) / (tm * 8.0));      // LDS cycles ~ 2(TM+8) per TM*8 FFMA cycles
+        const double cost = (double)variant * waves * padded * (512.0 / cs) * lds_pen * (variant == 2 ? 0.8 : 1.0);
+        if (cost < best) { best = cost; a->row_variant = variant; a->cluster_size = cs; a->nclusters = ncl; a->tile_tm = tm; }
       }
     }
     if (getenv("SMARTCAL_DEBUG"))
-      fprintf(stderr, "[smartcal] SMs=%d active clusters: 16-CTA=%d 8-CTA=%d -> cluster %d x %d, TM=%d\n", prop.multiProcessorCount,
-              n16, n8, a->cluster_size, a->nclusters, a->tile_tm);
+      fprintf(stderr, "[smartcal] SMs=%d co-resident clusters occ1/16=%d occ1/8=%d occ2/16=%d occ2/8=%d -> variant %d, cluster %d x %d, TM=%d\n",
+              prop.multiProcessorCount, cap[0], cap[1], cap[2], cap[3], a->row_variant, a->cluster_size, a->nclusters, a->tile_tm);
   }
-  if (a->cluster_size == 0) { sc_agent_destroy(a); return fail(SC_ERR_CUDA, "device cannot host an 8-CTA cluster with %zu B of shared memory", rowphase_smem_bytes()); }
+  if (a->cluster_size == 0) { sc_agent_destroy(a); return fail(SC_ERR_CUDA, "device cannot host an 8-CTA cluster with %zu B of shared memory", rowphase_smem_bytes(2)); }
   a->wgrad_grid = prop.multiProcessorCount * 2;
   a->mem_cntr = a->learn_counter = a->data_pointer = a->data_length = 0;
   a->t_actor = a->t_critic = 0;
@@ -801,7 +834,7 @@ int sc_per_update_host(sc_agent* a, const int32_t* tree_idx_host, const float* a
   if (!a->rp.tree) return fail(SC_ERR_STATE, "agent was created with prioritized=0");
   CK(cudaMemcpyAsync(a->tree_idx, tree_idx_host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, a->st));
   CK(cudaMemcpyAsync(a->err, abs_err_host, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, a->st));
-  CK(launch_per_update(a->rp.tree, a->C, n, a->tree_idx, a->err, a->cfg.per_clip, a->ps_out, a->st));
+  CK(launch_per_update(a->rp.tree, a->C, n, a->tree_idx, a->err, a->cfg.per_clip, a->ps_out, nullptr, a->st));
   a->launches++;
   if (priorities_host_out) CK(cudaMemcpyAsync(priorities_host_out, a->ps_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, a->st));
   CK(cudaStreamSynchronize(a->st));
@@ -824,6 +857,8 @@ static void fill_common(sc_agent* a, RowPhaseParams& p) {
   p.bidx = a->bidx;
   p.is_wsum = a->cfg.prioritized ? a->is_wsum : nullptr;
   p.y = a->y; p.err = a->err; p.part = a->part;
+  p.per_ps = a->cfg.prioritized ? a->ps_out : nullptr;
+  p.per_clip = a->cfg.per_clip;
   p.gamma = (float)a->cfg.gamma;
   p.scale = (float)a->cfg.reward_scale;
   p.alpha = a->alpha;
@@ -853,6 +888,7 @@ static void fill_wgrad(sc_agent* a, WgradParams& w, bool actor, int do_soft, int
   w.vops = actor ? a->actor_vops : a->critic_vops;
   w.nvops = actor ? a->n_actor_vops : a->n_critic_vops;
   w.total_tiles = actor ? a->actor_tiles : a->critic_tiles;
+  w.tile_map = actor ? a->actor_tile_map : a->critic_tile_map;
   w.B = a->B;
   w.bidx = a->bidx;
   w.hyper[0] = adam_hyper(a->cfg.lr_actor, a->t_actor);
@@ -874,7 +910,7 @@ static int run_rowphase(sc_agent* a, const RowPhaseParams& p, int timer_id) {
   cudaEvent_t e0, e1;
   if (timer_id >= 0) timer_begin(a, timer_id, &e0, &e1);
   const int ncl = p.program == PROG_ACT ? 1 : a->nclusters;
-  CK(launch_rowphase(p, a->cluster_size, ncl, p.program == PROG_ACT ? 2 : a->tile_tm, a->st));
+  CK(launch_rowphase(p, a->row_variant, a->cluster_size, ncl, p.program == PROG_ACT ? (a->row_variant == 2 ? 1 : 2) : a->tile_tm, a->st));
   if (timer_id >= 0) timer_end(a, timer_id, e0, e1);
   a->launches++;
   return SC_OK;
@@ -989,7 +1025,7 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
   if (per) {
     cudaEvent_t e0, e1;
     timer_begin(a, 5, &e0, &e1);
-    CK(launch_per_update(a->rp.tree, a->C, a->B, a->tree_idx, a->err, a->cfg.per_clip, a->ps_out, a->st));
+    CK(launch_per_update(a->rp.tree, a->C, a->B, a->tree_idx, a->err, a->cfg.per_clip, nullptr, a->ps_out, a->st));
     timer_end(a, 5, e0, e1);
     a->launches++;
   }

@@ -7,7 +7,6 @@ namespace sc {
 // hidden widths of the reference elastic-net MLPs (ref enet_sac.py:357-363,415-419)
 constexpr int H1 = 512, H2 = 256, H3 = 128, HA1 = 128, HA2 = 64, HCAT = H2 + HA2;
 constexpr int AMAX = 32;          // max n_actions supported by the row-local tail
-constexpr int RT = 4;             // rows a CTA carries through the row-local tail at once (the tail is latency-bound: one pass)
 
 struct CriticP {                   // one CriticNetwork: PyTorch-native row-major W[out][in], pitch = roundup4(in)
   float *w11, *b11, *w12, *b12, *w21, *b21, *w22, *b22, *w3, *b3;
@@ -78,7 +77,9 @@ struct RowPhaseParams {
   const float* eps;                          // [B][A] N(0,1) for this phase (nullptr: none)
   const float* is_wsum;                      // device scalar: sum of IS weights (PER) or nullptr
   float* y;                                  // [B] TD target
-  float* err;                                // [B] 0.5(|q1-y|+|q2-y|) (PER priorities)
+  float* err;                                // [B] 0.5(|q1-y|+|q2-y|) (PER errors)
+  float* per_ps;                             // [B] float32 priorities min(err+eps,clip)^alpha, or nullptr (no PER)
+  float per_clip;
   float* part;                               // LN partial statistics [slot][B][CS][2]
   float gamma, scale, alpha, maxa, td3_noise_c;
   int n_q;                                   // critics used by the actor phase (SAC 2, TD3 1)
@@ -120,6 +121,7 @@ struct WgradParams {
   const WgradOp* ops; int nops;
   const VecOp* vops; int nvops;
   int total_tiles;
+  const int* tile_map;             // [total_tiles] owner of each tile: op index, or 1000 + vector-op index
   int B;
   const int* bidx;
   AdamHyper hyper[3];

@@ -104,9 +104,13 @@ __global__ void k_per_sample(const double* __restrict__ tree, int C, int B, cons
                              float* is_wsum) {
   extern __shared__ float sw[];                  // [B] raw weights
   __shared__ float sred[32];
+  __shared__ double stop[511];                   // top 9 levels of the tree: one round of loads instead of 9 dependent ones
   const int tid = threadIdx.x;
   const int ntree = 2 * C - 1;
-  const double total = tree[0];
+  const int ntop = ntree < 511 ? ntree : 511;
+  for (int i = tid; i < ntop; i += blockDim.x) stop[i] = tree[i];
+  __syncthreads();
+  const double total = stop[0];
   const double seg = __ddiv_rn(total, (double)B);
   float lmax = 0.f;
   for (int i = tid; i < B; i += blockDim.x) {
@@ -117,11 +121,11 @@ __global__ void k_per_sample(const double* __restrict__ tree, int C, int B, cons
     while (true) {
       const int left = 2 * node + 1;
       if (left >= ntree) break;
-      const double lv = tree[left];
+      const double lv = left < ntop ? stop[left] : tree[left];
       if (v <= lv) node = left;
       else { v = __dsub_rn(v, lv); node = left + 1; }
     }
-    const double pr = tree[node];
+    const double pr = node < ntop ? stop[node] : tree[node];
     const double prob = __ddiv_rn(pr, total);
     const float w = (float)pow(__dmul_rn((double)B, prob), -beta);
     sw[i] = w;
@@ -145,18 +149,26 @@ __global__ void k_per_sample(const double* __restrict__ tree, int C, int B, cons
     is_w[i] = w;
   }
   __syncthreads();
-  if (tid == 0) {            // fixed-order sum -> mean(w) used by the (B,B)-broadcast losses
+  {                          // deterministic (fixed-shape) sum -> mean(w) used by the (B,B)-broadcast losses
     float s = 0.f;
-    for (int i = 0; i < B; ++i) s += sw[i];
-    *is_wsum = s;
+    for (int i = tid; i < B; i += blockDim.x) s += sw[i];
+    s = warp_sum(s);
+    if ((tid & 31) == 0) sred[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sred[w];
+      *is_wsum = tot;
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // priority refresh (PER.batch_update, enet_sac.py:314-323).  One block; dynamic smem: B doubles x2 + B ints.
 // ---------------------------------------------------------------------------------------------------
+// ps_in != nullptr: the float32 priorities were already evaluated by the critic row-phase kernel (err is ignored)
 __global__ void k_per_update(double* tree, int C, int B, const int* __restrict__ idx, const float* __restrict__ err,
-                             float clip, float* ps_out) {
+                             float clip, float* ps_out, const float* __restrict__ ps_in) {
   extern __shared__ double sd[];
   double* pv = sd;                 // new priorities (widened float32)
   double* chg = sd + B;            // change propagated by sample i
@@ -164,9 +176,14 @@ __global__ void k_per_update(double* tree, int C, int B, const int* __restrict__
   const int tid = threadIdx.x;
   int ok = 1;
   for (int i = tid; i < B; i += blockDim.x) {
-    const float e = fminf(__fadd_rn(err[i], 0.01f), clip);
-    // float32 power with a float32 exponent, evaluated in double and rounded once
-    const float p = (float)pow((double)e, (double)0.6f);
+    float p;
+    if (ps_in != nullptr) {
+      p = __ldcg(ps_in + i);
+    } else {
+      const float e = fminf(__fadd_rn(err[i], 0.01f), clip);
+      // float32 power with a float32 exponent, evaluated in double and rounded once
+      p = (float)pow((double)e, (double)0.6f);
+    }
     pv[i] = (double)p;
     leaf[i] = idx[i];
     if (ps_out) ps_out[i] = p;
@@ -198,13 +215,28 @@ __global__ void k_per_update(double* tree, int C, int B, const int* __restrict__
     if (i == B - 1 || leaf[i + 1] != leaf[i]) tree[leaf[i]] = pv[i];
   int depth = 0;
   while ((1 << depth) < C) ++depth;
-  // (level d, sample i): the first sample of each run of equal ancestors folds the run's changes in order
+  // (level d, sample i): the first sample of each run of equal ancestors folds the run's changes in order.  The run end is
+  // found by binary search (ancestors are non-decreasing in i), so the fold itself is a plain counted loop of dependent
+  // double adds -- the only inherently sequential part (B adds at the root).
   for (int w = tid; w < depth * B; w += blockDim.x) {
     const int d = w / B + 1, i = w - (d - 1) * B;
     const int node = ((leaf[i] + 1) >> d) - 1;
     if (i > 0 && (((leaf[i - 1] + 1) >> d) - 1) == node) continue;
+    int lo = i + 1, hi = B;                      // first j in (i, B] whose ancestor differs
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((((leaf[mid] + 1) >> d) - 1) == node) lo = mid + 1; else hi = mid;
+    }
     double val = tree[node];
-    for (int j = i; j < B && (((leaf[j] + 1) >> d) - 1) == node; ++j) val = __dadd_rn(val, chg[j]);
+    int j = i;
+#pragma unroll 1
+    for (; j + 8 <= lo; j += 8) {
+      const double c0 = chg[j], c1 = chg[j + 1], c2 = chg[j + 2], c3 = chg[j + 3], c4 = chg[j + 4], c5 = chg[j + 5], c6 = chg[j + 6],
+                   c7 = chg[j + 7];
+      val = __dadd_rn(val, c0); val = __dadd_rn(val, c1); val = __dadd_rn(val, c2); val = __dadd_rn(val, c3);
+      val = __dadd_rn(val, c4); val = __dadd_rn(val, c5); val = __dadd_rn(val, c6); val = __dadd_rn(val, c7);
+    }
+    for (; j < lo; ++j) val = __dadd_rn(val, chg[j]);
     tree[node] = val;
   }
 }
@@ -316,14 +348,15 @@ cudaError_t launch_per_sample(const double* tree, int C, int B, const double* u0
   k_per_sample<<<1, threads, (size_t)B * sizeof(float), st>>>(tree, C, B, u01, seed, ctr, beta, tree_idx, data_idx, is_w, is_wsum);
   return cudaGetLastError();
 }
-cudaError_t launch_per_update(double* tree, int C, int B, const int* idx, const float* err, float clip, float* ps_out, cudaStream_t st) {
+cudaError_t launch_per_update(double* tree, int C, int B, const int* idx, const float* err, float clip, float* ps_out,
+                              const float* ps_in, cudaStream_t st) {
   static bool configured = false;
   const size_t smem = (size_t)B * (2 * sizeof(double) + sizeof(int));
   if (!configured) {
     cudaFuncSetAttribute(k_per_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured = true;
   }
-  k_per_update<<<1, 1024, smem, st>>>(tree, C, B, idx, err, clip, ps_out);
+  k_per_update<<<1, 1024, smem, st>>>(tree, C, B, idx, err, clip, ps_out, ps_in);
   return cudaGetLastError();
 }
 cudaError_t launch_sample_uniform(int n, int B, uint64_t seed, uint64_t ctr, int* out, cudaStream_t st) {

@@ -1,1338 +1,105 @@
-// Cluster "row-phase" kernel: everything of one SAC/TD3 update that is independent across batch rows.
+// Cluster "row-phase" kernel, host side: two build configurations of sc_rowphase_impl.cuh and the launcher.
 //
-// One thread-block cluster (CS = 8 or 16 CTAs) owns a slab of batch rows and walks the whole layer chain
-// for them with activations staged through L2 and only cluster barriers in between (no grid-wide sync):
-//   * wide layers (fc1/fc11: S->512, fc2/fc12: 512->256, and the matching dgrads) are "cluster-tiled":
-//     CTA `rank` computes output columns [rank*Nc, rank*Nc+Nc) for all slab rows with the FP32 register-tiled
-//     GEMM of sc_tile.cuh, LayerNorm statistics are exchanged as per-CTA (mean, M2) partials;
-//   * the narrow tail (actor fc3 + heads + tanh-Gaussian sampling, critic action branch, fc3 -> Q, TD target,
-//     TD error and the backward pass down to dz of the 256/128/64-wide layers) is "row-local": CTA `rank`
-//     carries rows rank, rank+CS, ... through it as GEMVs with warp-shuffle reductions.
-// Programs: PROG_CRITIC (target + critic forward + critic dgrad), PROG_ACTOR (actor forward + Q(s,pi(s)) +
-// actor dgrad), PROG_ACT (choose_action, one row).  Replaces the torch-eager bodies of
-// enet_sac.py:569-585,589-598 / enet_td3.py:247-288,303-308 (forward+backward) -- the weight gradients,
-// Adam and the target soft update are in sc_wgrad.cu.
+//   occ1: one CTA per SM  (184 KB shared memory: 2 x 64 KB operand slots of 256 reduction elements, <=32-row tiles, tail RT=4)
+//   occ2: two CTAs per SM (109 KB: 2 x 32 KB slots of 128 reduction elements, <=16-row tiles, tail RT=2, <=112 registers)
+// occ2 doubles the number of resident clusters, so a 256-row batch is cut into 16-row slabs (no padded rows) and two
+// independent instruction streams share every SM, which hides the latencies this kernel is bound by.
 #include "sc_common.cuh"
 #include "sc_params.h"
 #include "sc_tile.cuh"
 
+#define SC_CFG_NS occ1
+#define SC_CFG_KC 256
+#define SC_CFG_RT 4
+#define SC_CFG_REDROWS 32
+#define SC_CFG_ZK 8192
+#define SC_CFG_MINBLOCKS 1
+#include "sc_rowphase_impl.cuh"
+#undef SC_CFG_NS
+#undef SC_CFG_KC
+#undef SC_CFG_RT
+#undef SC_CFG_REDROWS
+#undef SC_CFG_ZK
+#undef SC_CFG_MINBLOCKS
+
+#define SC_CFG_NS occ2
+#define SC_CFG_KC 128
+#define SC_CFG_RT 2
+#define SC_CFG_REDROWS 16
+#define SC_CFG_ZK 4096
+#define SC_CFG_MINBLOCKS 2
+#include "sc_rowphase_impl.cuh"
+#undef SC_CFG_NS
+#undef SC_CFG_KC
+#undef SC_CFG_RT
+#undef SC_CFG_REDROWS
+#undef SC_CFG_ZK
+#undef SC_CFG_MINBLOCKS
+
 namespace sc {
 
-constexpr int MAXOPS = 8;
-constexpr int NPMAX = 16;          // max LayerNorm partials per row (CS * column chunks)
-constexpr int MAXROWS = 128;       // max slab rows per cluster
-
-struct DenseOp {                          // Z = X W^T + b, then LayerNorm + ELU
-  const void *mapA, *mapW;               // tensor maps of X [rows][K] and W [N][K] (K padded to a multiple of 32)
-  const float *bias, *gamma, *beta;
-  int K, N;
-  float *H, *ZH, *RS; int ldo;
-};
-struct DgradOp {                          // dH_in = DZ W, then back through ELU / LayerNorm of the producing layer
-  const void *mapA, *mapP;               // tensor maps of DZ [rows][Nl] and the W panel ([Nl][Kin], box 32 x 128)
-  int Nl, Kin;
-  const float *Hp, *ZHp, *RSp, *gp;      // layer that produced the input (width Kin)
-  float *DU, *DZo; int ldo;
-};
-
-// dynamic shared memory map (floats): operand ring | split-reduction partials | output tile | LN statistics
-constexpr int SM_RING = NSTAGE * SLOT;
-constexpr int SM_RED = SC_WARPS * 32 * 36;
-constexpr int SM_Z = 32 * 32;
-constexpr int SM_STAT = MAXOPS * MAXROWS * 2;
-constexpr int SM_ZK = 8192;                       // raw pre-LayerNorm outputs of a stage, kept on chip between the two barriers
-constexpr int SM_TOTAL_FLOATS = SM_RING + SM_RED + SM_Z + SM_STAT + SM_ZK;
-
-__host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
-
-__device__ __forceinline__ int part_count(int N, int Nc, int nchunks, int pidx) {
-  const int rk = pidx / nchunks, ch = pidx - rk * nchunks;
-  const int start = rk * Nc + ch * 32;
-  const int width = min(32, Nc - ch * 32);
-  return max(0, min(width, N - start));
+template <typename K>
+static cudaError_t configure(K kern, size_t smem, int cs) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess && cs > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  return e;
 }
-
-struct Pipe {
-  int dbg;
-  long long* prof;   // optional cycle accumulators of thread 0: [0] full-wait, [1] mma, [2] park+combine, [3] tile epilogue, [4] LN combine, [5] LN normalise
-  uint64_t* full;     // [NSTAGE] armed by the producer (expect_tx), completed by the bulk copies
-  uint64_t* empty;    // [NSTAGE] one arrival per consumer warp
-};
-
-// One output tile = all reduction chunks of (op, column chunk, row sub-tile).  `g` counts chunks since the kernel
-// began (ring slot = g % NSTAGE, mbarrier phase parity = (g / NSTAGE) & 1); producer and consumers walk the same sequence.
-template <int TM, int TN>
-__device__ __forceinline__ void fwd_tile(const float* ring, const Pipe& pipe, unsigned& g, int K, float* red, float* sZ,
-                                         const float* bias_slice, int ncv) {
-  float acc[TM][TN];
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool prof = pipe.prof != nullptr && threadIdx.x == 0;
-  for (int k0 = 0; k0 < K; k0 += KC, ++g) {
-    const unsigned slot = g % NSTAGE;
-    long long t0 = prof ? clock64() : 0;
-    if (!(pipe.dbg & 2)) mbar_wait(pipe.full + slot, (g / NSTAGE) & 1u);
-    long long t1 = prof ? clock64() : 0;
-    const float* sA = ring + slot * SLOT;
-    const int kq = min(KC, K - k0) >> 2;
-    if (!(pipe.dbg & 1)) mma_nt<TM, TN>(sA, sA + SLOT_A, (kq * warp) / SC_WARPS, (kq * (warp + 1)) / SC_WARPS, acc);
-    __syncwarp();
-    if (lane == 0 && !(pipe.dbg & 2)) mbar_arrive(pipe.empty + slot);
-    if (prof) { pipe.prof[0] += t1 - t0; pipe.prof[1] += clock64() - t1; }
-  }
-  long long t2 = prof ? clock64() : 0;
-  park_partial<TM, TN, false>(red, acc);
-  consumer_sync();
-  combine_partials<TM, TN>(red, sZ, bias_slice, ncv);
-  consumer_sync();
-  if (prof) pipe.prof[2] += clock64() - t2;
-}
-
-template <int TM, int TN>
-__device__ __forceinline__ void bwd_tile(const float* ring, const Pipe& pipe, unsigned& g, int Nl, float* red, float* sZ) {
-  float acc[TM][TN];
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int n0 = 0; n0 < Nl; n0 += KC, ++g) {
-    const unsigned slot = g % NSTAGE;
-    mbar_wait(pipe.full + slot, (g / NSTAGE) & 1u);
-    const float* sA = ring + slot * SLOT;
-    const int kq = min(KC, Nl - n0) >> 2;
-    mma_nn<TM, TN>(sA, sA + SLOT_A, (kq * warp) / SC_WARPS, (kq * (warp + 1)) / SC_WARPS, acc);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(pipe.empty + slot);
-  }
-  park_partial<TM, TN, true>(red, acc);
-  consumer_sync();
-  combine_partials<TM, TN>(red, sZ, nullptr, 0);
-  consumer_sync();
-}
-
-// ======================================================================================================
-// cluster-tiled forward stage
-// ======================================================================================================
-template <int CS, int TM>
-__device__ void dense_stage(const DenseOp* ops, int nops, int B, int row0, int nrows, const int* __restrict__ bidx,
-                            float* part, float* smem, const Pipe& pipe, unsigned& g, unsigned long long* ts = nullptr) {
-  constexpr int ROWS = 8 * TM;
-  float* ring = smem;
-  float* red = ring + SM_RING;
-  float* sZ = red + SM_RED;
-  float* stat = sZ + SM_Z;
-  float* zk = stat + SM_STAT;
-  const int rank = (int)cluster_ctarank();
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nsub = (nrows + ROWS - 1) / ROWS;
-  // raw z of every (op, row, own column) stays in shared memory when it fits, else it is parked in H (global)
-  int zk_need = 0;
-  for (int o = 0; o < nops; ++o) zk_need += nsub * ROWS * round4((ops[o].N + CS - 1) / CS);
-  const bool use_zk = zk_need <= SM_ZK;
-  auto stamp = [&](int i) {
-    if (ts != nullptr && tid == 0) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      ts[i] = t;
-    }
-  };
-
-  if (warp == SC_WARPS) {
-    // ---------------- TMA producer warp: streams every reduction chunk of the stage through the ring ----------------
-    if (nrows > 0 && !(pipe.dbg & 2)) {
-      for (int o = 0; o < nops; ++o) {
-        const DenseOp op = ops[o];
-        const int Nc = round4((op.N + CS - 1) / CS);
-        const int nchunks = (Nc + 31) / 32;
-        for (int ch = 0; ch < nchunks; ++ch) {
-          const int n0 = rank * Nc + ch * 32;
-          const int width = min(32, Nc - ch * 32);
-          for (int sub = 0; sub < nsub; ++sub) {
-            const int r0 = row0 + sub * ROWS;
-            for (int k0 = 0; k0 < op.K; k0 += KC, ++g) {
-              const unsigned slot = g % NSTAGE;
-              const int nkb = (min(KC, op.K - k0) + 31) >> 5;               // 32-float k-blocks in this chunk
-              mbar_wait(pipe.empty + slot, ((g / NSTAGE) & 1u) ^ 1u);
-              float* sA = ring + slot * SLOT;
-              if (lane == 0) mbar_expect_tx(pipe.full + slot, (unsigned)nkb * 2u * BOXF * 4u);
-              __syncwarp();
-              // lanes 0..7: A boxes, lanes 8..15: W boxes; rows beyond the matrix are zero-filled by the TMA unit
-              if (lane < nkb) tma_load_2d(sA + lane * BOXF, op.mapA, k0 + 32 * lane, r0, pipe.full + slot);
-              else if (lane >= KBLK && lane - KBLK < nkb)
-                tma_load_2d(sA + SLOT_A + (lane - KBLK) * BOXF, op.mapW, k0 + 32 * (lane - KBLK), n0, pipe.full + slot);
-            }
-          }
-        }
-      }
-    }
-  } else if (nrows > 0) {
-    // ---------------- consumer warps ----------------
-    int zbase = 0;
-    for (int o = 0; o < nops; ++o) {
-      const DenseOp op = ops[o];
-      const int Nc = round4((op.N + CS - 1) / CS);
-      const int nchunks = (Nc + 31) / 32;
-      float* zko = zk + zbase;
-      zbase += nsub * ROWS * Nc;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const int n0 = rank * Nc + ch * 32;
-        const int width = min(32, Nc - ch * 32);
-        const int ncv = max(0, min(width, op.N - n0));
-        const float* bias_slice = op.bias ? op.bias + n0 : nullptr;
-        for (int sub = 0; sub < nsub; ++sub) {
-          const int r0 = row0 + sub * ROWS;
-          const int rv = min(ROWS, nrows - sub * ROWS);
-          switch (width >> 2) {
-            case 8: fwd_tile<TM, 8>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv); break;
-            case 4: fwd_tile<TM, 4>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv); break;
-            case 2: fwd_tile<TM, 2>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv); break;
-            default: fwd_tile<TM, 1>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv); break;
-          }
-          // raw z -> H (own column slice) and per-row (mean, M2) over the valid columns of this chunk
-          const long long te = (pipe.prof && tid == 0) ? clock64() : 0;
-          const int row = tid >> 3, sub8 = tid & 7;
-          float s = 0.f;
-          if (row < rv)
-            for (int c = sub8; c < ncv; c += 8) s += sZ[row * width + c];
-          s = group8_sum(s);
-          const float mean = ncv > 0 ? s / (float)ncv : 0.f;
-          float m2 = 0.f;
-          if (row < rv)
-            for (int c = sub8; c < ncv; c += 8) {
-              const float d = sZ[row * width + c] - mean;
-              m2 = fmaf(d, d, m2);
-            }
-          m2 = group8_sum(m2);
-          if (row < rv) {
-            if (use_zk) {
-              float* zrow = zko + (sub * ROWS + row) * Nc + ch * 32;
-              for (int c = sub8; c < ncv; c += 8) zrow[c] = sZ[row * width + c];
-            } else {
-              float* hrow = op.H + (size_t)(r0 + row) * op.ldo + n0;
-              for (int c = sub8; c < ncv; c += 8) hrow[c] = sZ[row * width + c];
-            }
-            if (sub8 == 0) {
-              float* pp = part + (((size_t)o * B + (r0 + row)) * NPMAX + (rank * nchunks + ch)) * 2;
-              pp[0] = mean;
-              pp[1] = m2;
-            }
-          }
-          if (pipe.prof && tid == 0) pipe.prof[3] += clock64() - te;
-        }
-      }
-    }
-  }
-  stamp(0);
-  cluster_sync();
-  stamp(1);
-  const long long tf0 = (pipe.prof && tid == 0) ? clock64() : 0;
-  if (warp < SC_WARPS) {
-    // ---- combine the LayerNorm partials of every (op,row) in fixed order (Chan et al.) ----
-    for (int i = tid; i < nops * nrows; i += SC_THREADS) {
-      const int o = i / nrows, r = i - o * nrows;
-      const DenseOp& op = ops[o];
-      const int Nc = round4((op.N + CS - 1) / CS);
-      const int nchunks = (Nc + 31) / 32;
-      const int np = CS * nchunks;
-      const float* pp = part + (((size_t)o * B + (row0 + r)) * NPMAX) * 2;
-      // all partials are fetched first (independent L2 loads in flight together), then combined in fixed order
-      float2 pv[NPMAX];
-#pragma unroll
-      for (int p = 0; p < NPMAX; ++p) pv[p] = p < np ? __ldcg(reinterpret_cast<const float2*>(pp) + p) : make_float2(0.f, 0.f);
-      // valid-column count of partial p = (rank rk, chunk ch): clamp(N - (rk*Nc + 32 ch), 0, min(32, Nc - 32 ch))
-      float msum = 0.f;
-#pragma unroll
-      for (int p = 0; p < NPMAX; ++p) {
-        if (p < np) {
-          const int rk = nchunks == 1 ? p : p >> 1, ch = nchunks == 1 ? 0 : p & 1;      // nchunks is 1 or 2 (Nc <= 64)
-          const int cnt = max(0, min(min(32, Nc - ch * 32), op.N - (rk * Nc + ch * 32)));
-          msum = fmaf((float)cnt, pv[p].x, msum);
-        }
-      }
-      const float mean = msum / (float)op.N;
-      float m2 = 0.f;
-#pragma unroll
-      for (int p = 0; p < NPMAX; ++p) {
-        if (p < np) {
-          const int rk = nchunks == 1 ? p : p >> 1, ch = nchunks == 1 ? 0 : p & 1;
-          const int cnt = max(0, min(min(32, Nc - ch * 32), op.N - (rk * Nc + ch * 32)));
-          const float d = pv[p].x - mean;
-          if (cnt > 0) m2 += pv[p].y + (float)cnt * d * d;
-        }
-      }
-      const float rstd = 1.0f / sqrtf(m2 / (float)op.N + SC_LN_EPS);
-      stat[2 * i] = mean;
-      stat[2 * i + 1] = rstd;
-      if (rank == 0 && op.RS != nullptr) op.RS[row0 + r] = rstd;
-    }
-    consumer_sync();
-    if (pipe.prof && tid == 0) pipe.prof[4] += clock64() - tf0;
-    // normalise + affine + ELU on the own column slice (raw z read back from shared memory, or from H when it did not fit)
-    int zbase = 0;
-    for (int o = 0; o < nops; ++o) {
-      const DenseOp& op = ops[o];
-      const int Nc = round4((op.N + CS - 1) / CS);
-      const int n0 = rank * Nc;
-      const float* zko = zk + zbase;
-      zbase += nsub * ROWS * Nc;
-      for (int e = tid; e < nrows * Nc; e += SC_THREADS) {
-        const int r = e / Nc, c = e - r * Nc, n = n0 + c;
-        if (n < op.N) {
-          const size_t off = (size_t)(row0 + r) * op.ldo + n;
-          const float z = use_zk ? zko[r * Nc + c] : ld_act(op.H + off);     // (sub*ROWS + row) == r
-          const float zh = (z - stat[2 * (o * nrows + r)]) * stat[2 * (o * nrows + r) + 1];
-          const float u = fmaf(zh, ld_w(op.gamma + n), ld_w(op.beta + n));
-          op.H[off] = elu(u);
-          if (op.ZH != nullptr) op.ZH[off] = zh;
-        }
-      }
-    }
-  }
-  if (pipe.prof && tid == 0) pipe.prof[5] += clock64() - tf0;
-  stamp(2);
-  cluster_sync();
-  stamp(3);
-}
-
-// ======================================================================================================
-// cluster-tiled dgrad stage: dH_in = DZ * W, then back through ELU and LayerNorm of the producing layer
-// ======================================================================================================
-template <int CS, int TM>
-__device__ void dgrad_stage(const DgradOp* ops, int nops, int B, int row0, int nrows, float* part, float* smem,
-                            const Pipe& pipe, unsigned& g) {
-  constexpr int ROWS = 8 * TM;
-  float* ring = smem;
-  float* red = ring + SM_RING;
-  float* sZ = red + SM_RED;
-  float* stat = sZ + SM_Z;
-  const int rank = (int)cluster_ctarank();
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nsub = (nrows + ROWS - 1) / ROWS;
-
-  if (warp == SC_WARPS) {
-    if (nrows > 0) {
-      for (int o = 0; o < nops; ++o) {
-        const DgradOp op = ops[o];
-        const int Kc = round4((op.Kin + CS - 1) / CS);
-        const int nchunks = (Kc + 31) / 32;
-        for (int ch = 0; ch < nchunks; ++ch) {
-          const int k0 = rank * Kc + ch * 32;
-          const int width = min(32, Kc - ch * 32);
-          const int kcv = max(0, min(width, op.Kin - k0));
-          for (int sub = 0; sub < nsub; ++sub) {
-            const int r0 = row0 + sub * ROWS;
-            const int rv = min(ROWS, nrows - sub * ROWS);
-            for (int n0 = 0; n0 < op.Nl; n0 += KC, ++g) {
-              const unsigned slot = g % NSTAGE;
-              const int nkb = (min(KC, op.Nl - n0) + 31) >> 5;
-              mbar_wait(pipe.empty + slot, ((g / NSTAGE) & 1u) ^ 1u);
-              float* sA = ring + slot * SLOT;
-              const int npan = (min(KC, op.Nl - n0) + 127) >> 7;               // 128-row weight panels in this chunk
-              if (lane == 0) mbar_expect_tx(pipe.full + slot, (unsigned)nkb * BOXF * 4u + (unsigned)npan * 128u * 32u * 4u);
-              __syncwarp();
-              if (lane < nkb) tma_load_2d(sA + lane * BOXF, op.mapA, n0 + 32 * lane, r0, pipe.full + slot);
-              else if (lane >= KBLK && lane - KBLK < npan)   // [128 n][32 input columns] each
-                tma_load_2d(sA + SLOT_A + (lane - KBLK) * 128 * 32, op.mapP, k0, n0 + 128 * (lane - KBLK), pipe.full + slot);
-            }
-          }
-        }
-      }
-    }
-  } else if (nrows > 0) {
-    for (int o = 0; o < nops; ++o) {
-      const DgradOp op = ops[o];
-      const int Kc = round4((op.Kin + CS - 1) / CS);
-      const int nchunks = (Kc + 31) / 32;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const int k0 = rank * Kc + ch * 32;
-        const int width = min(32, Kc - ch * 32);
-        const int kcv = max(0, min(width, op.Kin - k0));
-        for (int sub = 0; sub < nsub; ++sub) {
-          const int r0 = row0 + sub * ROWS;
-          const int rv = min(ROWS, nrows - sub * ROWS);
-          switch (width >> 2) {
-            case 8: bwd_tile<TM, 8>(ring, pipe, g, op.Nl, red, sZ); break;
-            case 4: bwd_tile<TM, 4>(ring, pipe, g, op.Nl, red, sZ); break;
-            case 2: bwd_tile<TM, 2>(ring, pipe, g, op.Nl, red, sZ); break;
-            default: bwd_tile<TM, 1>(ring, pipe, g, op.Nl, red, sZ); break;
-          }
-          const int row = tid >> 3, sub8 = tid & 7;
-          float s1 = 0.f, s2 = 0.f;
-          if (row < rv) {
-            const size_t base = (size_t)(r0 + row) * op.ldo + k0;
-            for (int c = sub8; c < kcv; c += 8) {
-              const float dh = sZ[row * width + c];
-              const float h = ld_act(op.Hp + base + c);
-              const float zh = ld_act(op.ZHp + base + c);
-              const float du = dh * elu_grad_from_out(h);
-              const float t = du * ld_w(op.gp + k0 + c);
-              s1 += t;
-              s2 = fmaf(t, zh, s2);
-              op.DU[base + c] = du;
-              op.DZo[base + c] = t;
-            }
-          }
-          s1 = group8_sum(s1);
-          s2 = group8_sum(s2);
-          if (row < rv && sub8 == 0) {
-            float* pp = part + (((size_t)o * B + (r0 + row)) * NPMAX + (rank * nchunks + ch)) * 2;
-            pp[0] = s1;
-            pp[1] = s2;
-          }
-        }
-      }
-    }
-  }
-  cluster_sync();
-  if (warp < SC_WARPS) {
-    for (int i = tid; i < nops * nrows; i += SC_THREADS) {
-      const int o = i / nrows, r = i - o * nrows;
-      const DgradOp& op = ops[o];
-      const int Kc = round4((op.Kin + CS - 1) / CS);
-      const int nchunks = (Kc + 31) / 32;
-      const float* pp = part + (((size_t)o * B + (row0 + r)) * NPMAX) * 2;
-      const int np = CS * nchunks;
-      float2 pv[NPMAX];
-#pragma unroll
-      for (int p = 0; p < NPMAX; ++p) pv[p] = p < np ? __ldcg(reinterpret_cast<const float2*>(pp) + p) : make_float2(0.f, 0.f);
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int p = 0; p < NPMAX; ++p) {
-        if (p < np && part_count(op.Kin, Kc, nchunks, p) > 0) {
-          s1 += pv[p].x;
-          s2 += pv[p].y;
-        }
-      }
-      stat[2 * i] = s1 / (float)op.Kin;
-      stat[2 * i + 1] = s2 / (float)op.Kin;
-    }
-    consumer_sync();
-    for (int o = 0; o < nops; ++o) {
-      const DgradOp& op = ops[o];
-      const int Kc = round4((op.Kin + CS - 1) / CS);
-      const int k0 = rank * Kc;
-      for (int e = tid; e < nrows * Kc; e += SC_THREADS) {
-        const int r = e / Kc, c = e - r * Kc, k = k0 + c;
-        if (k < op.Kin) {
-          const size_t off = (size_t)(row0 + r) * op.ldo + k;
-          const float t = ld_act(op.DZo + off);
-          const float zh = ld_act(op.ZHp + off);
-          const float rs = ld_act(op.RSp + row0 + r);
-          op.DZo[off] = rs * (t - stat[2 * (o * nrows + r)] - zh * stat[2 * (o * nrows + r) + 1]);
-        }
-      }
-    }
-  }
-  // no trailing cluster barrier: consumers are in the next kernel
-}
-
-// ======================================================================================================
-// row-local helpers (RT rows at a time, vectors in shared memory)
-// ======================================================================================================
-// zout[t][n] = bias[n] + sum_k W[n][k] * xin[t][k]; one warp per output feature, lanes along k (coalesced W rows)
-__device__ void gemv_rows(const float* __restrict__ W, int ldw, const float* __restrict__ bias, int N, int K,
-                          const float* xin, int ldx, float* zout, int ldz) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int K4 = K >> 2;
-  for (int n0 = warp * 4; n0 < N; n0 += SC_WARPS * 4) {
-    float acc[4][RT];
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int t = 0; t < RT; ++t) acc[u][t] = 0.f;
-    for (int k4 = lane; k4 < K4; k4 += 32) {
-      float4 x[RT];
-#pragma unroll
-      for (int t = 0; t < RT; ++t) x[t] = *reinterpret_cast<const float4*>(xin + t * ldx + 4 * k4);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (n0 + u < N) {
-          const float4 w = ld_w4(W + (size_t)(n0 + u) * ldw + 4 * k4);
-#pragma unroll
-          for (int t = 0; t < RT; ++t) acc[u][t] = dot4(w, x[t], acc[u][t]);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int t = 0; t < RT; ++t) acc[u][t] = warp_sum(acc[u][t]);
-    if (lane == 0) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (n0 + u < N) {
-          const float b = bias ? ld_w(bias + n0 + u) : 0.f;
-#pragma unroll
-          for (int t = 0; t < RT; ++t) zout[t * ldz + n0 + u] = acc[u][t] + b;
-        }
-    }
-  }
-}
-
-// out[t][k] = sum_n din[t][n] * W[n][k]  (k < K, K % 4 == 0, K/4 <= 256); scratch: [256/K4][RT][K] floats.
-// Ends with a consumer_sync(); `out` is complete afterwards.
-__device__ void gemvT_rows(const float* __restrict__ W, int ldw, int N, int K, const float* din, int ldd, float* out,
-                           int ldo, float* scratch) {
-  const int K4 = K >> 2;
-  const int parts = SC_THREADS / K4;
-  const int tid = threadIdx.x;
-  const int part = tid / K4, k4 = tid - part * K4;
-  if (part < parts) {
-    float4 acc[RT];
-#pragma unroll
-    for (int t = 0; t < RT; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int n = part; n < N; n += parts) {
-      const float4 w = ld_w4(W + (size_t)n * ldw + 4 * k4);
-#pragma unroll
-      for (int t = 0; t < RT; ++t) {
-        const float d = din[t * ldd + n];
-        acc[t].x = fmaf(d, w.x, acc[t].x);
-        acc[t].y = fmaf(d, w.y, acc[t].y);
-        acc[t].z = fmaf(d, w.z, acc[t].z);
-        acc[t].w = fmaf(d, w.w, acc[t].w);
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < RT; ++t) *reinterpret_cast<float4*>(scratch + ((size_t)(part * RT + t)) * K + 4 * k4) = acc[t];
-  }
-  consumer_sync();
-  for (int e = tid; e < RT * K; e += SC_THREADS) {
-    const int t = e / K, k = e - t * K;
-    float s = 0.f;
-    for (int p = 0; p < parts; ++p) s += scratch[((size_t)(p * RT + t)) * K + k];
-    out[t * ldo + k] = s;
-  }
-  consumer_sync();
-}
-
-// in place z[t][0:N] -> ELU(LN(z)); optionally keeps the normalised value and 1/std.  One warp per row.
-__device__ void ln_elu_rows(float* z, int ld, int N, const float* __restrict__ gamma, const float* __restrict__ beta,
-                            float* zh, float* rs, int rs_stride) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp < RT) {
-    float* zr = z + warp * ld;
-    float s = 0.f;
-    for (int j = lane; j < N; j += 32) s += zr[j];
-    const float mean = warp_sum(s) / (float)N;
-    float m2 = 0.f;
-    for (int j = lane; j < N; j += 32) {
-      const float d = zr[j] - mean;
-      m2 = fmaf(d, d, m2);
-    }
-    const float rstd = 1.0f / sqrtf(warp_sum(m2) / (float)N + SC_LN_EPS);
-    for (int j = lane; j < N; j += 32) {
-      const float n = (zr[j] - mean) * rstd;
-      if (zh != nullptr) zh[warp * ld + j] = n;
-      zr[j] = elu(fmaf(n, ld_w(gamma + j), ld_w(beta + j)));
-    }
-    if (lane == 0 && rs != nullptr) rs[warp * rs_stride] = rstd;
-  }
-}
-
-// dh -> du = dh * ELU'(.), dz = rstd * (du*gamma - mean(du*gamma) - zh * mean(du*gamma*zh)).  One warp per row.
-__device__ void ln_bwd_rows(const float* dh, const float* h, const float* zh, int ld, int N,
-                            const float* __restrict__ gamma, const float* rs, int rs_stride, float* du, float* dz) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp < RT) {
-    const int o = warp * ld;
-    float s1 = 0.f, s2 = 0.f;
-    for (int j = lane; j < N; j += 32) {
-      const float g = dh[o + j] * elu_grad_from_out(h[o + j]);
-      du[o + j] = g;
-      const float t = g * ld_w(gamma + j);
-      s1 += t;
-      s2 = fmaf(t, zh[o + j], s2);
-    }
-    const float c1 = warp_sum(s1) / (float)N, c2 = warp_sum(s2) / (float)N;
-    const float r = rs[warp * rs_stride];
-    for (int j = lane; j < N; j += 32) dz[o + j] = r * (du[o + j] * ld_w(gamma + j) - c1 - zh[o + j] * c2);
-  }
-}
-
-struct RowSet {          // the RT rows a CTA is carrying through the tail
-  int row[RT];           // global batch row, or -1
-};
-
-__device__ __forceinline__ void load_rows_act(float* dst, int ld, const float* src, int lds, int N, const RowSet& rs) {
-  for (int e = threadIdx.x; e < RT * (N >> 2); e += SC_THREADS) {
-    const int t = e / (N >> 2), c4 = e - t * (N >> 2);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (rs.row[t] >= 0) v = ld_act4(src + (size_t)rs.row[t] * lds + 4 * c4);
-    *reinterpret_cast<float4*>(dst + t * ld + 4 * c4) = v;
-  }
-}
-__device__ __forceinline__ void store_rows(float* dst, int ldd, const float* src, int ld, int N, const RowSet& rs) {
-  if (dst == nullptr) return;
-  for (int e = threadIdx.x; e < RT * (N >> 2); e += SC_THREADS) {
-    const int t = e / (N >> 2), c4 = e - t * (N >> 2);
-    if (rs.row[t] >= 0)
-      *reinterpret_cast<float4*>(dst + (size_t)rs.row[t] * ldd + 4 * c4) = *reinterpret_cast<const float4*>(src + t * ld + 4 * c4);
-  }
-}
-
-// shared-memory map of the tail (floats); lives in the same dynamic buffer as the GEMM ring (different stages)
-constexpr int NETS = 4;   // critic phase: target critics 0,1 and online critics 2,3; actor phase: online critics 0,1
-struct TailSm {
-  float *xh2, *zh2r;              // [RT][H2]   actor layer-2 output rows (+ normalised, actor phase)
-  float *x3, *zh3;                // [RT][H3]
-  float *head;                    // [RT][2*AMAX] mu | raw logsigma (later: d mu | d logsigma)
-  float *an;                      // [2][RT][AMAX] actions fed to the critics: [0] policy sample, [1] replay action
-  float *smp;                     // [RT][AMAX][4]: tanh(u), sigma, eps, clamp-pass mask
-  float *lp;                      // [RT][AMAX] per-action log-prob terms / d loss / d action accumulator
-  float *sc;                      // [RT][16] per-row scalars
-  float *rsx;                     // [RT][8]: [2] rs3, [3] rs2, [4+k] rs12 of online critic k
-  float *h12r;                    // [NETS][RT][H2] state-branch outputs per net
-  float *zh12r;                   // [2][RT][H2]
-  float *v21, *zh21;              // [NETS][RT][HA1]
-  float *v22, *zh22;              // [NETS][RT][HA2]
-  float *rsn;                     // [NETS][RT][2] 1/std of layers 21, 22
-  float *qv;                      // [NETS][RT]
-  float *ga, *gb;                 // [2][RT][H2]  d u12 / d z12   (actor phase: [RT][H3|H2] scratch)
-  float *gc, *gd;                 // [2][RT][HA1] d u21 / d z21
-  float *ge, *gf;                 // [2][RT][HA2] d u22 / d z22
-  float *scratch;                 // gemvT partials (8192 floats)
-};
-__device__ TailSm carve_tail(float* sm) {
-  TailSm t;
-  t.xh2 = sm; sm += RT * H2;
-  t.zh2r = sm; sm += RT * H2;
-  t.x3 = sm; sm += RT * H3;
-  t.zh3 = sm; sm += RT * H3;
-  t.head = sm; sm += RT * 2 * AMAX;
-  t.an = sm; sm += 2 * RT * AMAX;
-  t.smp = sm; sm += RT * AMAX * 4;
-  t.lp = sm; sm += RT * AMAX;
-  t.sc = sm; sm += RT * 16;
-  t.rsx = sm; sm += RT * 8;
-  t.h12r = sm; sm += NETS * RT * H2;
-  t.zh12r = sm; sm += 2 * RT * H2;
-  t.v21 = sm; sm += NETS * RT * HA1;
-  t.zh21 = sm; sm += NETS * RT * HA1;
-  t.v22 = sm; sm += NETS * RT * HA2;
-  t.zh22 = sm; sm += NETS * RT * HA2;
-  t.rsn = sm; sm += NETS * RT * 2;
-  t.qv = sm; sm += NETS * RT;
-  t.ga = sm; sm += 2 * RT * H2;
-  t.gb = sm; sm += 2 * RT * H2;
-  t.gc = sm; sm += 2 * RT * HA1;
-  t.gd = sm; sm += 2 * RT * HA1;
-  t.ge = sm; sm += 2 * RT * HA2;
-  t.gf = sm; sm += 2 * RT * HA2;
-  t.scratch = sm; sm += 8192;
-  return t;
-}
-
-enum { SC_LOGP = 0, SC_Y = 3, SC_DQ1 = 6, SC_DQ2 = 7, SC_GLP = 8 };
-
-// ---- multi-net row helpers: NR = nn*RT rows, row index rix = net*RT + t; warps stride over the rows ---------------
-// in place z -> ELU(LN(z)), keeps the normalised value and 1/std
-__device__ void ln_elu_multi(int nn, float* z, float* zh, int N, const float* const* gamma, const float* const* beta, float* rs,
-                             int rs_stride) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int rix = warp; rix < nn * RT; rix += SC_WARPS) {
-    const int net = rix / RT;
-    float* zr = z + rix * N;
-    float s = 0.f;
-    for (int j = lane; j < N; j += 32) s += zr[j];
-    const float mean = warp_sum(s) / (float)N;
-    float m2 = 0.f;
-    for (int j = lane; j < N; j += 32) {
-      const float d = zr[j] - mean;
-      m2 = fmaf(d, d, m2);
-    }
-    const float rstd = 1.0f / sqrtf(warp_sum(m2) / (float)N + SC_LN_EPS);
-    const float* g = gamma[net];
-    const float* b = beta[net];
-    for (int j = lane; j < N; j += 32) {
-      const float n = (zr[j] - mean) * rstd;
-      zh[rix * N + j] = n;
-      zr[j] = elu(fmaf(n, ld_w(g + j), ld_w(b + j)));
-    }
-    if (lane == 0) rs[rix * rs_stride] = rstd;
-  }
-}
-// dh -> du (in place), dz; per-row h, zh, rs given as arrays indexed like dh
-__device__ void ln_bwd_multi(int nn, float* dh, const float* h, const float* zh, int N, const float* const* gamma, const float* rs,
-                             int rs_stride, float* dz) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int rix = warp; rix < nn * RT; rix += SC_WARPS) {
-    const float* g = gamma[rix / RT];
-    const int o = rix * N;
-    float s1 = 0.f, s2 = 0.f;
-    for (int j = lane; j < N; j += 32) {
-      const float du = dh[o + j] * elu_grad_from_out(h[o + j]);
-      dh[o + j] = du;
-      const float t = du * ld_w(g + j);
-      s1 += t;
-      s2 = fmaf(t, zh[o + j], s2);
-    }
-    const float c1 = warp_sum(s1) / (float)N, c2 = warp_sum(s2) / (float)N;
-    const float r = rs[rix * rs_stride];
-    for (int j = lane; j < N; j += 32) dz[o + j] = r * (dh[o + j] * ld_w(g + j) - c1 - zh[o + j] * c2);
-  }
-}
-// zout[net][t][n] = bias_net[n] + sum_k W_net[n][k] * xin[net][t][k]; work items (net, group of 4 outputs) strided over warps
-__device__ void gemv_multi(int nn, const float* const* W, int ldw, const float* const* bias, int N, int K, const float* xin,
-                           float* zout) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int K4 = K >> 2, groups = (N + 3) >> 2;
-  for (int item = warp; item < nn * groups; item += SC_WARPS) {
-    const int net = item / groups, n0 = (item - net * groups) * 4;
-    const float* Wn = W[net];
-    const float* x0 = xin + net * RT * K;
-    float acc[4][RT];
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int t = 0; t < RT; ++t) acc[u][t] = 0.f;
-    for (int k4 = lane; k4 < K4; k4 += 32) {
-      float4 w[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) w[u] = n0 + u < N ? ld_w4(Wn + (size_t)(n0 + u) * ldw + 4 * k4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int t = 0; t < RT; ++t) {
-        const float4 x = *reinterpret_cast<const float4*>(x0 + t * K + 4 * k4);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u][t] = dot4(w[u], x, acc[u][t]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int t = 0; t < RT; ++t) acc[u][t] = warp_sum(acc[u][t]);
-    if (lane == 0) {
-      const float* bn = bias[net];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (n0 + u < N) {
-          const float b = bn ? ld_w(bn + n0 + u) : 0.f;
-#pragma unroll
-          for (int t = 0; t < RT; ++t) zout[(net * RT + t) * N + n0 + u] = acc[u][t] + b;
-        }
-    }
-  }
-}
-// out[net][t][k] = sum_n din[net][t][n] * W_net[n][k]; threads split (net, part of n, k4); fixed-order combine; 2 barriers
-__device__ void gemvT_multi(int nn, const float* const* W, int ldw, int N, int K, const float* din, float* out, float* scratch) {
-  const int K4 = K >> 2;
-  const int tpn = SC_THREADS / nn;                 // threads per net
-  const int parts = tpn / K4;
-  const int tid = threadIdx.x;
-  const int net = tid / tpn, tl = tid - net * tpn;
-  const int part = tl / K4, k4 = tl - part * K4;
-  if (net < nn && part < parts) {
-    const float* Wn = W[net];
-    const float* d0 = din + net * RT * N;
-    float4 acc[RT];
-#pragma unroll
-    for (int t = 0; t < RT; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int n = part; n < N; n += parts) {
-      const float4 w = ld_w4(Wn + (size_t)n * ldw + 4 * k4);
-#pragma unroll
-      for (int t = 0; t < RT; ++t) {
-        const float d = d0[t * N + n];
-        acc[t].x = fmaf(d, w.x, acc[t].x);
-        acc[t].y = fmaf(d, w.y, acc[t].y);
-        acc[t].z = fmaf(d, w.z, acc[t].z);
-        acc[t].w = fmaf(d, w.w, acc[t].w);
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < RT; ++t)
-      *reinterpret_cast<float4*>(scratch + (((size_t)net * parts + part) * RT + t) * K + 4 * k4) = acc[t];
-  }
-  consumer_sync();
-  for (int e = tid; e < nn * RT * K; e += SC_THREADS) {
-    const int rix = e / K, k = e - rix * K;
-    const int nt = rix / RT, t = rix - nt * RT;
-    float s = 0.f;
-    for (int pp = 0; pp < parts; ++pp) s += scratch[(((size_t)nt * parts + pp) * RT + t) * K + k];
-    out[e] = s;
-  }
-  consumer_sync();
-}
-
-__device__ __forceinline__ void load_rows_to(float* dst, const float* src, int N, const RowSet& rs) {   // dst [RT][N]
-  for (int e = threadIdx.x; e < RT * (N >> 2); e += SC_THREADS) {
-    const int t = e / (N >> 2), c4 = e - t * (N >> 2);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (rs.row[t] >= 0) v = ld_act4(src + (size_t)rs.row[t] * N + 4 * c4);
-    *reinterpret_cast<float4*>(dst + t * N + 4 * c4) = v;
-  }
-}
-__device__ __forceinline__ void store_rows_from(float* dst, const float* src, int N, const RowSet& rs) {   // src [RT][N]
-  if (dst == nullptr) return;
-  for (int e = threadIdx.x; e < RT * (N >> 2); e += SC_THREADS) {
-    const int t = e / (N >> 2), c4 = e - t * (N >> 2);
-    if (rs.row[t] >= 0)
-      *reinterpret_cast<float4*>(dst + (size_t)rs.row[t] * N + 4 * c4) = *reinterpret_cast<const float4*>(src + t * N + 4 * c4);
-  }
-}
-
-// action branches (fc21 -> LN -> ELU -> fc22 -> LN -> ELU) of `nn` critics at once; net i reads actions an_sel[i]
-// ([RT][AMAX]).  Leaves h21/zh21/h22/zh22 in t.v21.. and 1/std in t.rsn[(net*RT+t)*2 + {0,1}].  4 barriers.
-__device__ void action_branches(int nn, const CriticP* const* c, const float* const* an_sel, int A, int Ap, const TailSm& t) {
-  for (int e = threadIdx.x; e < nn * RT * HA1; e += SC_THREADS) {
-    const int rix = e / HA1, n = e - rix * HA1, net = rix / RT, tt = rix - net * RT;
-    const float* w = c[net]->w21 + n * Ap;
-    const float* a = an_sel[net] + tt * AMAX;
-    float acc = 0.f;
-    for (int j = 0; j < A; ++j) acc = fmaf(ld_w(w + j), a[j], acc);
-    t.v21[e] = acc + ld_w(c[net]->b21 + n);
-  }
-  consumer_sync();
-  const float *g21[NETS], *b21[NETS], *g22[NETS], *b22[NETS], *w22[NETS], *bb22[NETS];
-  for (int i = 0; i < nn; ++i) {
-    g21[i] = c[i]->g21; b21[i] = c[i]->be21; g22[i] = c[i]->g22; b22[i] = c[i]->be22; w22[i] = c[i]->w22; bb22[i] = c[i]->b22;
-  }
-  ln_elu_multi(nn, t.v21, t.zh21, HA1, g21, b21, t.rsn, 2);
-  consumer_sync();
-  gemv_multi(nn, w22, HA1, bb22, HA2, HA1, t.v21, t.v22);
-  consumer_sync();
-  ln_elu_multi(nn, t.v22, t.zh22, HA2, g22, b22, t.rsn + 1, 2);
-  consumer_sync();
-}
-// q[net][t] = b3 + w3[0:H2].h12r[net][t] + w3[H2:].h22[net][t]
-__device__ void critic_q_multi(int nn, const CriticP* const* c, const TailSm& t) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int rix = warp; rix < nn * RT; rix += SC_WARPS) {
-    const CriticP* cc = c[rix / RT];
-    float s = 0.f;
-    for (int k = lane; k < H2; k += 32) s = fmaf(ld_w(cc->w3 + k), t.h12r[rix * H2 + k], s);
-    for (int k = lane; k < HA2; k += 32) s = fmaf(ld_w(cc->w3 + H2 + k), t.v22[rix * HA2 + k], s);
-    s = warp_sum(s);
-    if (lane == 0) t.qv[rix] = s + ld_w(cc->b3);
-  }
-}
-
-// actor layer 3 + heads on the rows already staged in t.xh2.  Leaves h3/zh3 in t.x3/t.zh3, raw head outputs in t.head,
-// 1/std of layer 3 in t.rsx[t*8+2].  Ends synchronised (3 barriers).
-__device__ void actor_tail_forward(const RowPhaseParams& p, const TailSm& t) {
-  const ActorP& a = p.actor;
-  const float *w3[1] = {a.w3}, *b3[1] = {a.b3}, *g3[1] = {a.g3}, *be3[1] = {a.be3};
-  gemv_multi(1, w3, H2, b3, H3, H2, t.xh2, t.x3);
-  consumer_sync();
-  ln_elu_multi(1, t.x3, t.zh3, H3, g3, be3, t.rsx + 2, 8);
-  consumer_sync();
-  // heads: (mu | logsigma) rows of width A each, output to t.head[t][0:A] and [AMAX:AMAX+A]
-  {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nh = a.wls != nullptr ? 2 * p.A : p.A;
-    for (int o = warp; o < nh; o += SC_WARPS) {
-      const bool ls = o >= p.A;
-      const int j = ls ? o - p.A : o;
-      const float* w = (ls ? a.wls : a.wmu) + (size_t)j * H3;
-      const float4 wv = ld_w4(w + 4 * lane);           // H3 == 128 == 32 lanes x float4
-      float acc[RT];
-#pragma unroll
-      for (int tt = 0; tt < RT; ++tt) acc[tt] = warp_sum(dot4(wv, *reinterpret_cast<const float4*>(t.x3 + tt * H3 + 4 * lane), 0.f));
-      if (lane == 0) {
-        const float b = ld_w((ls ? a.bls : a.bmu) + j);
-#pragma unroll
-        for (int tt = 0; tt < RT; ++tt) t.head[tt * 2 * AMAX + (ls ? AMAX : 0) + j] = acc[tt] + b;
-      }
-    }
-  }
-  consumer_sync();
-}
-
-// tanh-squashed Gaussian sample + log-prob (SAC, ref ActorNetwork.sample_normal enet_sac.py:446-466) or the
-// deterministic TD3 head.  eps_of(row, j) supplies N(0,1).  Results: t.an[0] (action), t.sc[SC_LOGP], t.smp.  2 barriers.
-template <typename EpsFn>
-__device__ void policy_head(const RowPhaseParams& p, const TailSm& t, const RowSet& rs, bool td3_target, EpsFn eps_of) {
-  const int tid = threadIdx.x;
-  if (tid < RT * p.A) {
-    const int r = tid / p.A, j = tid - r * p.A;
-    float* smp = t.smp + (r * AMAX + j) * 4;
-    if (p.kind == 0) {
-      const float mu = t.head[r * 2 * AMAX + j];
-      const float raw = t.head[r * 2 * AMAX + AMAX + j];
-      const float ls = fminf(fmaxf(raw, -20.f), 2.f);
-      const float sg = expf(ls);
-      const float e = rs.row[r] >= 0 ? eps_of(rs.row[r], j) : 0.f;
-      const float u = __fadd_rn(mu, __fmul_rn(e, sg));                 // loc + eps*scale, two roundings like torch
-      const float th = tanhf(u);
-      const float dm = u - mu;
-      // Normal.log_prob: -((v-loc)^2)/(2 var) - log(scale) - log(sqrt(2 pi)); then the tanh correction
-      float lp = -(dm * dm) / (2.f * (sg * sg)) - logf(sg) - 0.91893853320467274178f;
-      lp -= logf(p.maxa * (1.f - th * th) + 1e-6f);
-      t.an[r * AMAX + j] = th * p.maxa;
-      smp[0] = th; smp[1] = sg; smp[2] = e; smp[3] = (raw >= -20.f && raw <= 2.f) ? 1.f : 0.f;
-      t.lp[r * AMAX + j] = lp;
-    } else {
-      float act = tanhf(t.head[r * 2 * AMAX + j]);
-      smp[0] = act;
-      if (td3_target) act = fminf(fmaxf(act + p.td3_noise_c, -1.f), 1.f);   // enet_td3.py:248-251
-      t.an[r * AMAX + j] = act;
-    }
-  }
-  consumer_sync();
-  if (p.kind == 0 && tid < RT) {
-    float s = 0.f;
-    for (int j = 0; j < p.A; ++j) s += t.lp[tid * AMAX + j];
-    t.sc[tid * 16 + SC_LOGP] = s;
-  }
-  consumer_sync();
-}
-
-// ======================================================================================================
-// PROG_CRITIC tail: policy on s', both target critics, TD target, both online critics forward + backward
-// ======================================================================================================
-__device__ void tail_critic(const RowPhaseParams& p, const TailSm& t, const RowSet& rs) {
-  const int tid = threadIdx.x;
-  // ---- stage every global row this pass needs (one round of L2 latency) ----
-  load_rows_to(t.xh2, p.aw.t_h2, H2, rs);
-  for (int k = 0; k < 2; ++k) {
-    load_rows_to(t.h12r + k * RT * H2, p.tw[k].h12, H2, rs);
-    load_rows_to(t.h12r + (2 + k) * RT * H2, p.cw[k].h12, H2, rs);
-    load_rows_to(t.zh12r + k * RT * H2, p.cw[k].zh12, H2, rs);
-  }
-  if (tid < RT * p.A) {
-    const int r = tid / p.A, j = tid - r * p.A;
-    t.an[RT * AMAX + r * AMAX + j] = rs.row[r] >= 0 ? ld_w(p.rp.action + (size_t)p.bidx[rs.row[r]] * p.Ap + j) : 0.f;
-  }
-  if (tid < 2 * RT) {
-    const int k = tid / RT, r = tid - k * RT;
-    t.rsx[r * 8 + 4 + k] = rs.row[r] >= 0 ? ld_act(p.cw[k].rs12 + rs.row[r]) : 0.f;
-  }
-  consumer_sync();
-  // ---- policy on s' (SAC: online actor, sampled; TD3: target actor + clipped scalar noise) ----
-  actor_tail_forward(p, t);
-  policy_head(p, t, rs, true, [&](int row, int j) { return ld_act(p.eps + (size_t)row * p.A + j); });
-  // ---- action branches of all four critics at once: targets on a', online critics on the replay action ----
-  const CriticP* nets[NETS] = {&p.targ[0], &p.targ[1], &p.crit[0], &p.crit[1]};
-  const float* an_sel[NETS] = {t.an, t.an, t.an + RT * AMAX, t.an + RT * AMAX};
-  action_branches(NETS, nets, an_sel, p.A, p.Ap, t);
-  critic_q_multi(NETS, nets, t);
-  consumer_sync();
-  const float wsum = p.is_wsum ? ld_act(p.is_wsum) : (float)p.B;
-  const float coef = 2.f * wsum / ((float)p.B * (float)p.B);      // d/dq of mean(w)*mean((q-y)^2)
-  if (tid < RT) {
-    float* s = t.sc + tid * 16;
-    const int row = rs.row[tid];
-    float dq1 = 0.f, dq2 = 0.f;
-    if (row >= 0) {
-      const int slot = p.bidx[row];
-      const bool done = p.rp.done[slot] != 0;
-      const float qt1 = t.qv[0 * RT + tid], qt2 = t.qv[1 * RT + tid], q1 = t.qv[2 * RT + tid], q2 = t.qv[3 * RT + tid];
-      float yv;
-      if (p.kind == 0) {   // enet_sac.py:573-575
-        float m = __fsub_rn(fminf(qt1, qt2), __fmul_rn(p.alpha, s[SC_LOGP]));
-        if (done) m = 0.f;
-        yv = __fadd_rn(__fmul_rn(p.scale, ld_w(p.rp.reward + slot)), __fmul_rn(p.gamma, m));
-      } else {             // enet_td3.py:255-260
-        const float m = done ? 0.f : fminf(qt1, qt2);
-        yv = __fadd_rn(ld_w(p.rp.reward + slot), __fmul_rn(p.gamma, m));
-      }
-      p.y[row] = yv;
-      dq1 = coef * (q1 - yv);
-      dq2 = coef * (q2 - yv);
-      p.cw[0].q[row] = q1; p.cw[1].q[row] = q2;
-      p.cw[0].dq[row] = dq1; p.cw[1].dq[row] = dq2;
-      p.err[row] = 0.5f * (fabsf(q1 - yv) + fabsf(q2 - yv));          // enet_td3.py:266-269
-      for (int k = 0; k < 2; ++k) {
-        p.cw[k].rs21[row] = t.rsn[((2 + k) * RT + tid) * 2 + 0];
-        p.cw[k].rs22[row] = t.rsn[((2 + k) * RT + tid) * 2 + 1];
-      }
-    }
-    s[SC_DQ1] = dq1;
-    s[SC_DQ2] = dq2;
-  }
-  for (int k = 0; k < 2; ++k) {      // forward caches of the online critics (inputs of the weight-gradient kernel)
-    store_rows_from(p.cw[k].h21, t.v21 + (2 + k) * RT * HA1, HA1, rs);
-    store_rows_from(p.cw[k].zh21, t.zh21 + (2 + k) * RT * HA1, HA1, rs);
-    store_rows_from(p.cw[k].h22, t.v22 + (2 + k) * RT * HA2, HA2, rs);
-    store_rows_from(p.cw[k].zh22, t.zh22 + (2 + k) * RT * HA2, HA2, rs);
-  }
-  consumer_sync();
-  // ---- backward of both online critics: d cat = dq * w3 ----
-  for (int e = tid; e < 2 * RT * HCAT; e += SC_THREADS) {
-    const int rix = e / HCAT, j = e - rix * HCAT, k = rix / RT, r = rix - k * RT;
-    const float gval = t.sc[r * 16 + SC_DQ1 + k] * ld_w(p.crit[k].w3 + j);
-    if (j < H2) t.ga[rix * H2 + j] = gval; else t.ge[rix * HA2 + (j - H2)] = gval;
-  }
-  consumer_sync();
-  {
-    const float *g12[2] = {p.crit[0].g12, p.crit[1].g12}, *g22[2] = {p.crit[0].g22, p.crit[1].g22};
-    // rs12 of (k, r) sits at t.rsx[r*8 + 4 + k]: present it as a [2*RT] array with stride... copy to a dense temp
-    if (tid < 2 * RT) t.qv[tid] = t.rsx[(tid % RT) * 8 + 4 + tid / RT];
-    consumer_sync();
-    ln_bwd_multi(2, t.ga, t.h12r + 2 * RT * H2, t.zh12r, H2, g12, t.qv, 1, t.gb);
-    ln_bwd_multi(2, t.ge, t.v22 + 2 * RT * HA2, t.zh22 + 2 * RT * HA2, HA2, g22, t.rsn + 2 * RT * 2 + 1, 2, t.gf);
-  }
-  consumer_sync();
-  for (int k = 0; k < 2; ++k) {
-    store_rows_from(p.cw[k].du12, t.ga + k * RT * H2, H2, rs);
-    store_rows_from(p.cw[k].dz12, t.gb + k * RT * H2, H2, rs);
-    store_rows_from(p.cw[k].du22, t.ge + k * RT * HA2, HA2, rs);
-    store_rows_from(p.cw[k].dz22, t.gf + k * RT * HA2, HA2, rs);
-  }
-  {
-    const float* w22[2] = {p.crit[0].w22, p.crit[1].w22};
-    gemvT_multi(2, w22, HA1, HA2, HA1, t.gf, t.gc, t.scratch);
-    const float* g21[2] = {p.crit[0].g21, p.crit[1].g21};
-    ln_bwd_multi(2, t.gc, t.v21 + 2 * RT * HA1, t.zh21 + 2 * RT * HA1, HA1, g21, t.rsn + 2 * RT * 2, 2, t.gd);
-  }
-  consumer_sync();
-  for (int k = 0; k < 2; ++k) {
-    store_rows_from(p.cw[k].du21, t.gc + k * RT * HA1, HA1, rs);
-    store_rows_from(p.cw[k].dz21, t.gd + k * RT * HA1, HA1, rs);
-  }
-  consumer_sync();
-}
-
-// ======================================================================================================
-// PROG_ACTOR tail: policy on s, Q_k(s, pi(s)) with the updated critics, backward to d z2 of the actor
-// ======================================================================================================
-__device__ void tail_actor(const RowPhaseParams& p, const TailSm& t, const RowSet& rs) {
-  const int tid = threadIdx.x;
-  const ActorP& a = p.actor;
-  const int nq = p.n_q;
-  load_rows_to(t.xh2, p.aw.h2, H2, rs);
-  load_rows_to(t.zh2r, p.aw.zh2, H2, rs);
-  for (int k = 0; k < nq; ++k) load_rows_to(t.h12r + k * RT * H2, p.cw[k].p_h12, H2, rs);
-  if (tid < RT) t.rsx[tid * 8 + 3] = rs.row[tid] >= 0 ? ld_act(p.aw.rs2 + rs.row[tid]) : 0.f;
-  consumer_sync();
-  actor_tail_forward(p, t);
-  store_rows_from(p.aw.h3, t.x3, H3, rs);
-  store_rows_from(p.aw.zh3, t.zh3, H3, rs);
-  if (tid < RT && rs.row[tid] >= 0) p.aw.rs3[rs.row[tid]] = t.rsx[tid * 8 + 2];
-  policy_head(p, t, rs, false, [&](int row, int j) { return ld_act(p.eps + (size_t)row * p.A + j); });
-  if (tid < RT * p.A) {
-    const int r = tid / p.A, j = tid - r * p.A;
-    if (rs.row[r] >= 0) p.aw.pi[(size_t)rs.row[r] * p.A + j] = t.an[r * AMAX + j];
-  }
-  if (tid < RT && rs.row[tid] >= 0 && p.kind == 0) p.aw.logp[rs.row[tid]] = t.sc[tid * 16 + SC_LOGP];
-  // ---- Q_k(s, pi(s)) with the freshly updated critics ----
-  const CriticP* nets[NETS] = {&p.crit[0], &p.crit[1], nullptr, nullptr};
-  const float* an_sel[NETS] = {t.an, t.an, nullptr, nullptr};
-  action_branches(nq, nets, an_sel, p.A, p.Ap, t);
-  critic_q_multi(nq, nets, t);
-  consumer_sync();
-  const float wsum = p.is_wsum ? ld_act(p.is_wsum) : (float)p.B;
-  const float coef = wsum / ((float)p.B * (float)p.B);           // d/dx of mean(x*w) with the (B,B) broadcast
-  if (tid < RT) {
-    float* s = t.sc + tid * 16;
-    float g1 = 0.f, g2 = 0.f;
-    if (rs.row[tid] >= 0) {
-      const float q1 = t.qv[tid], q2 = nq == 2 ? t.qv[RT + tid] : 0.f;
-      if (nq == 2) {   // torch.min backward: gradient to the smaller, halves on ties
-        if (q1 < q2) g1 = -coef; else if (q2 < q1) g2 = -coef; else { g1 = -0.5f * coef; g2 = -0.5f * coef; }
-        p.aw.qmin[rs.row[tid]] = fminf(q1, q2);       // critic_value (enet_sac.py:592)
-      } else {
-        g1 = -coef;
-        p.aw.qmin[rs.row[tid]] = q1;
-      }
-    }
-    s[SC_DQ1] = g1;
-    s[SC_DQ2] = g2;
-    s[SC_GLP] = rs.row[tid] >= 0 ? p.alpha * coef : 0.f;
-  }
-  consumer_sync();
-  // ---- back through the action branches of the critics to d loss / d action ----
-  for (int e = tid; e < nq * RT * HA2; e += SC_THREADS) {
-    const int rix = e / HA2, j = e - rix * HA2, k = rix / RT, r = rix - k * RT;
-    t.ge[e] = t.sc[r * 16 + SC_DQ1 + k] * ld_w(p.crit[k].w3 + H2 + j);
-  }
-  consumer_sync();
-  {
-    const float *g22[2] = {p.crit[0].g22, p.crit[1].g22}, *g21[2] = {p.crit[0].g21, p.crit[1].g21};
-    const float* w22[2] = {p.crit[0].w22, p.crit[1].w22};
-    ln_bwd_multi(nq, t.ge, t.v22, t.zh22, HA2, g22, t.rsn + 1, 2, t.gf);
-    consumer_sync();
-    gemvT_multi(nq, w22, HA1, HA2, HA1, t.gf, t.gc, t.scratch);
-    ln_bwd_multi(nq, t.gc, t.v21, t.zh21, HA1, g21, t.rsn, 2, t.gd);
-    consumer_sync();
-  }
-  {   // d action[r][j] = sum_k sum_n dz21_k[r][n] * w21_k[n][j]   (one warp per (row, j), critics in fixed order)
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int o = warp; o < RT * p.A; o += SC_WARPS) {
-      const int r = o / p.A, j = o - r * p.A;
-      float tot = 0.f;
-      for (int k = 0; k < nq; ++k) {
-        float s = 0.f;
-        for (int n = lane; n < HA1; n += 32) s = fmaf(t.gd[(k * RT + r) * HA1 + n], ld_w(p.crit[k].w21 + n * p.Ap + j), s);
-        tot += warp_sum(s);
-      }
-      if (lane == 0) t.lp[r * AMAX + j] = tot;
-    }
-  }
-  consumer_sync();
-  // ---- back through the policy head ----
-  if (tid < RT * p.A) {
-    const int r = tid / p.A, j = tid - r * p.A;
-    float da = t.lp[r * AMAX + j];
-    const float* smp = t.smp + (r * AMAX + j) * 4;
-    const int row = rs.row[r];
-    if (p.hint_coef != nullptr && row >= 0)
-      da = fmaf(ld_act(p.hint_coef), t.an[r * AMAX + j] - ld_w(p.rp.hint + (size_t)p.bidx[row] * p.Ap + j), da);
-    if (p.kind == 0) {
-      const float th = smp[0], sg = smp[1], e = smp[2];
-      const float omt = 1.f - th * th;
-      const float glp = t.sc[r * 16 + SC_GLP];
-      const float du = da * p.maxa * omt + glp * (2.f * th * omt * p.maxa / (p.maxa * omt + 1e-6f));
-      const float dl = (du * sg * e - glp) * smp[3];
-      t.head[r * 2 * AMAX + j] = du;
-      t.head[r * 2 * AMAX + AMAX + j] = dl;
-      if (row >= 0) {
-        p.aw.dhead[(size_t)row * 2 * p.A + j] = du;
-        p.aw.dhead[(size_t)row * 2 * p.A + p.A + j] = dl;
-      }
-    } else {
-      const float act = smp[0];
-      const float dz = da * (1.f - act * act);
-      t.head[r * 2 * AMAX + j] = dz;
-      if (row >= 0) p.aw.dhead[(size_t)row * p.A + j] = dz;
-    }
-  }
-  consumer_sync();
-  for (int e = tid; e < RT * H3; e += SC_THREADS) {
-    const int r = e / H3, k = e - r * H3;
-    float s = 0.f;
-    for (int j = 0; j < p.A; ++j) {
-      s = fmaf(t.head[r * 2 * AMAX + j], ld_w(a.wmu + j * H3 + k), s);
-      if (a.wls != nullptr) s = fmaf(t.head[r * 2 * AMAX + AMAX + j], ld_w(a.wls + j * H3 + k), s);
-    }
-    t.ga[e] = s;
-  }
-  consumer_sync();
-  {
-    const float *g3[1] = {a.g3}, *g2[1] = {a.g2}, *w3[1] = {a.w3};
-    ln_bwd_multi(1, t.ga, t.x3, t.zh3, H3, g3, t.rsx + 2, 8, t.gb);
-    consumer_sync();
-    store_rows_from(p.aw.du3, t.ga, H3, rs);
-    store_rows_from(p.aw.dz3, t.gb, H3, rs);
-    gemvT_multi(1, w3, H2, H3, H2, t.gb, t.gc, t.scratch);     // t.gc has room for [RT][H2] (2*RT*HA1 floats)
-    ln_bwd_multi(1, t.gc, t.xh2, t.zh2r, H2, g2, t.rsx + 3, 8, t.gd);
-    consumer_sync();
-    store_rows_from(p.aw.du2, t.gc, H2, rs);
-    store_rows_from(p.aw.dz2, t.gd, H2, rs);
-  }
-  consumer_sync();
-}
-
-// gather the cluster's minibatch rows of `src` ([C][Sp] replay array) into the dense TMA-readable buffer dst [B][Sp32]
-__device__ __forceinline__ void gather_rows(float* dst, const float* __restrict__ src, const int* __restrict__ bidx, int row0,
-                                            int nrows, int S, int Sp, int Sp32, int rank, int cs) {
-  const int n4 = Sp32 >> 2, v4 = Sp >> 2;
-  for (int lr = rank; lr < nrows; lr += cs) {
-    const int row = row0 + lr;
-    const float* sp = src + (size_t)__ldg(bidx + row) * Sp;
-    for (int c = threadIdx.x; c < n4; c += SC_ROW_THREADS) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c < v4) v = ld_w4(sp + 4 * c);
-      *reinterpret_cast<float4*>(dst + (size_t)row * Sp32 + 4 * c) = v;
-    }
-  }
-}
-
-template <int CS, int TM>
-__global__ void __launch_bounds__(SC_ROW_THREADS, 1) k_rowphase(const __grid_constant__ RowPhaseParams p) {
-  extern __shared__ __align__(16) float smem_raw[];
-  // the TMA boxes use the 128-byte swizzle, whose pattern repeats every 1024 bytes: align the ring accordingly
-  float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ DenseOp dops[MAXOPS];
-  __shared__ DgradOp gops[2];
-  __shared__ __align__(8) uint64_t mbars[2 * NSTAGE];
-  const int tid = threadIdx.x;
-  const bool consumer = tid < SC_THREADS;
-  __shared__ long long prof_acc[8];
-  if (tid < 8) prof_acc[tid] = 0;
-  const Pipe pipe{p.dbg, p.tstamp ? prof_acc : nullptr, mbars, mbars + NSTAGE};
-  unsigned g = 0;                 // chunks streamed so far (identical sequence in producer and consumers)
-  if (tid == 0) {
-    for (int i = 0; i < NSTAGE; ++i) {
-      mbar_init(pipe.full + i, 1);
-      mbar_init(pipe.empty + i, SC_WARPS);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  __syncthreads();
-  const int rank = (int)cluster_ctarank();
-  const int ncl = (int)num_clusters();
-  const int cid = (int)cluster_idx();
-  const int per = (p.B + ncl - 1) / ncl;
-  const int row0 = cid * per;
-  const int nrows = max(0, min(per, p.B - row0));
-  // (clusters with nrows == 0 still walk the barriers; all their loops are empty)
-
-  auto dense = [&](int i, const void* mapA, const void* mapW, const float* b, const float* g_, const float* be, int K, int N,
-                   float* H, float* ZH, float* RS) {
-    if (tid == 0) dops[i] = DenseOp{mapA, mapW, b, g_, be, K, N, H, ZH, RS, N};
-  };
-  const TailSm ts = carve_tail(smem);
-  auto stamp = [&](int i) {
-    if (p.tstamp != nullptr && tid == 0) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      p.tstamp[(size_t)blockIdx.x * 8 + i] = t;
-    }
-  };
-  stamp(0);
-  const TensorMaps& tm = p.tm;
-  const int K1 = p.Sp32;          // layer-1 reduction length, zero-padded to whole 32-float k-blocks
-
-  if (p.program == PROG_CRITIC) {
-    const ActorP& a = p.actor;
-    // stage 0: fused minibatch gather (replay rows -> dense buffers the TMA unit can tile), one cluster barrier
-    gather_rows(p.mb_s, p.rp.state, p.bidx, row0, nrows, p.S, p.Sp, p.Sp32, rank, CS);
-    gather_rows(p.mb_s2, p.rp.new_state, p.bidx, row0, nrows, p.S, p.Sp, p.Sp32, rank, CS);
-    // stage 1: first layers.  s' feeds the policy and both target critics, s feeds both online critics.
-    dense(0, tm.mb_s2, tm.actor_w1, a.b1, a.g1, a.be1, K1, H1, p.aw.t_h1, nullptr, nullptr);
-    dense(1, tm.mb_s2, tm.targ_w11[0], p.targ[0].b11, p.targ[0].g11, p.targ[0].be11, K1, H1, p.tw[0].h11, nullptr, nullptr);
-    dense(2, tm.mb_s2, tm.targ_w11[1], p.targ[1].b11, p.targ[1].g11, p.targ[1].be11, K1, H1, p.tw[1].h11, nullptr, nullptr);
-    dense(3, tm.mb_s, tm.crit_w11[0], p.crit[0].b11, p.crit[0].g11, p.crit[0].be11, K1, H1, p.cw[0].h11, p.cw[0].zh11, p.cw[0].rs11);
-    dense(4, tm.mb_s, tm.crit_w11[1], p.crit[1].b11, p.crit[1].g11, p.crit[1].be11, K1, H1, p.cw[1].h11, p.cw[1].zh11, p.cw[1].rs11);
-    cluster_sync();
-    dense_stage<CS, TM>(dops, 5, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g);
-    stamp(1);
-    // stage 2: second layers
-    dense(0, tm.t_h1, tm.actor_w2, a.b2, a.g2, a.be2, H1, H2, p.aw.t_h2, nullptr, nullptr);
-    dense(1, tm.th11[0], tm.targ_w12[0], p.targ[0].b12, p.targ[0].g12, p.targ[0].be12, H1, H2, p.tw[0].h12, nullptr, nullptr);
-    dense(2, tm.th11[1], tm.targ_w12[1], p.targ[1].b12, p.targ[1].g12, p.targ[1].be12, H1, H2, p.tw[1].h12, nullptr, nullptr);
-    dense(3, tm.ch11[0], tm.crit_w12[0], p.crit[0].b12, p.crit[0].g12, p.crit[0].be12, H1, H2, p.cw[0].h12, p.cw[0].zh12, p.cw[0].rs12);
-    dense(4, tm.ch11[1], tm.crit_w12[1], p.crit[1].b12, p.crit[1].g12, p.crit[1].be12, H1, H2, p.cw[1].h12, p.cw[1].zh12, p.cw[1].rs12);
-    __syncthreads();
-    dense_stage<CS, TM>(dops, 5, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g,
-                        p.tstamp ? p.tstamp + 512 * 8 + (size_t)blockIdx.x * 8 : nullptr);
-    stamp(2);
-    // stage 3: row-local tail
-    if (consumer)
-      for (int gr = rank; gr < nrows; gr += CS * RT) {
-        RowSet rs;
-#pragma unroll
-        for (int t = 0; t < RT; ++t) rs.row[t] = (gr + t * CS < nrows) ? row0 + gr + t * CS : -1;
-        tail_critic(p, ts, rs);
-      }
-    stamp(3);
-    if (tid == 0) {
-      for (int k = 0; k < 2; ++k)
-        gops[k] = DgradOp{tm.dz12[k], tm.crit_w12p[k], H2, H1, p.cw[k].h11, p.cw[k].zh11, p.cw[k].rs11,
-                          p.crit[k].g11, p.cw[k].du11, p.cw[k].dz11, H1};
-    }
-    cluster_sync();
-    stamp(4);
-    // stage 4: dz12 -> layer-11 gradients
-    dgrad_stage<CS, TM>(gops, 2, p.B, row0, nrows, p.part, smem, pipe, g);
-    stamp(5);
-    if (p.tstamp != nullptr && tid == 0)
-      for (int i = 0; i < 6; ++i) p.tstamp[(size_t)(1024 + blockIdx.x) * 8 + i] = (unsigned long long)prof_acc[i];
-  } else if (p.program == PROG_ACTOR) {
-    const ActorP& a = p.actor;
-    // mb_s was gathered by the critic phase of this step (same minibatch)
-    dense(0, tm.mb_s, tm.actor_w1, a.b1, a.g1, a.be1, K1, H1, p.aw.h1, p.aw.zh1, p.aw.rs1);
-    for (int k = 0; k < p.n_q; ++k)
-      dense(1 + k, tm.mb_s, tm.crit_w11[k], p.crit[k].b11, p.crit[k].g11, p.crit[k].be11, K1, H1, p.cw[k].p_h11, nullptr, nullptr);
-    __syncthreads();
-    dense_stage<CS, TM>(dops, 1 + p.n_q, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g);
-    dense(0, tm.h1, tm.actor_w2, a.b2, a.g2, a.be2, H1, H2, p.aw.h2, p.aw.zh2, p.aw.rs2);
-    for (int k = 0; k < p.n_q; ++k)
-      dense(1 + k, tm.ph11[k], tm.crit_w12[k], p.crit[k].b12, p.crit[k].g12, p.crit[k].be12, H1, H2, p.cw[k].p_h12, nullptr, nullptr);
-    __syncthreads();
-    dense_stage<CS, TM>(dops, 1 + p.n_q, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g);
-    if (consumer)
-      for (int gr = rank; gr < nrows; gr += CS * RT) {
-        RowSet rs;
-#pragma unroll
-        for (int t = 0; t < RT; ++t) rs.row[t] = (gr + t * CS < nrows) ? row0 + gr + t * CS : -1;
-        tail_actor(p, ts, rs);
-      }
-    if (tid == 0)
-      gops[0] = DgradOp{tm.dz2, tm.actor_w2p, H2, H1, p.aw.h1, p.aw.zh1, p.aw.rs1, a.g1, p.aw.du1, p.aw.dz1, H1};
-    cluster_sync();
-    dgrad_stage<CS, TM>(gops, 1, p.B, row0, nrows, p.part, smem, pipe, g);
-  } else {   // PROG_ACT: one observation through the actor (enet_sac.py:547-553)
-    const ActorP& a = p.actor;
-    dense(0, tm.obs, tm.actor_w1, a.b1, a.g1, a.be1, K1, H1, p.act_aux, nullptr, nullptr);
-    __syncthreads();
-    dense_stage<CS, TM>(dops, 1, 1, row0, nrows, nullptr, p.part, smem, pipe, g);
-    dense(0, tm.aux, tm.actor_w2, a.b2, a.g2, a.be2, H1, H2, p.act_aux + H1, nullptr, nullptr);
-    __syncthreads();
-    dense_stage<CS, TM>(dops, 1, 1, row0, nrows, nullptr, p.part, smem, pipe, g);
-    if (rank == 0 && nrows > 0 && consumer) {
-      RowSet rs;
-      rs.row[0] = 0;
-#pragma unroll
-      for (int t = 1; t < RT; ++t) rs.row[t] = -1;
-      load_rows_to(ts.xh2, p.act_aux + H1, H2, rs);
-      consumer_sync();
-      actor_tail_forward(p, ts);
-      policy_head(p, ts, rs, false, [&](int, int j) { return p.eps ? ld_act(p.eps + j) : 0.f; });
-      if (tid < p.A) {
-        float v = ts.an[tid];
-        if (p.kind != 0 && p.eps != nullptr) v = fminf(fmaxf(v + ld_act(p.eps + tid), -1.f), 1.f);   // enet_td3.py:215-217
-        p.act_out[tid] = v;
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// host launcher
-// ------------------------------------------------------------------------------------------------------
-size_t rowphase_smem_bytes() { return (size_t)SM_TOTAL_FLOATS * sizeof(float) + 1024; }   // + slack for the 1024-byte alignment
-
-template <int CS, int TM>
-static cudaError_t launch_cs(const RowPhaseParams& p, int nclusters, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_rowphase<CS, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowphase_smem_bytes());
-    if (e != cudaSuccess) return e;
-    if (CS > 8) {
-      e = cudaFuncSetAttribute(k_rowphase<CS, TM>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-      if (e != cudaSuccess) return e;
-    }
-    configured = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(nclusters * CS, 1, 1);
+static void cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int nclusters, int cs, size_t smem, cudaStream_t st) {
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3(nclusters * cs, 1, 1);
   cfg.blockDim = dim3(SC_ROW_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = rowphase_smem_bytes();
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.x = cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_rowphase<CS, TM>, p);
 }
-
-// how many clusters of CS CTAs can be resident at once with this kernel's shared-memory footprint
-template <int CS>
-static int max_active_clusters() {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(64 * CS, 1, 1);
-  cfg.blockDim = dim3(SC_ROW_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = rowphase_smem_bytes();
+template <typename K>
+static cudaError_t launch_k(K kern, size_t smem, const RowPhaseParams& p, int cs, int nclusters, cudaStream_t st) {
+  cudaError_t e = configure(kern, smem, cs);          // idempotent and cheap
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cluster_cfg(cfg, attr, nclusters, cs, smem, st);
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+template <typename K>
+static int max_clusters(K kern, size_t smem, int cs) {
+  if (configure(kern, smem, cs) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  cluster_cfg(cfg, attr, 64, cs, smem, nullptr);
   int n = 0;
-  cudaError_t e = cudaFuncSetAttribute(k_rowphase<CS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowphase_smem_bytes());
-  if (e == cudaSuccess && CS > 8) e = cudaFuncSetAttribute(k_rowphase<CS, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, k_rowphase<CS, 4>, &cfg);
-  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
-void rowphase_cluster_capacity(int* n16, int* n8) {
-  *n16 = max_active_clusters<16>();
-  *n8 = max_active_clusters<8>();
-}
 
-cudaError_t launch_rowphase(const RowPhaseParams& p, int cluster_size, int nclusters, int tm, cudaStream_t st) {
-  if (cluster_size == 16)
-    return tm == 2 ? launch_cs<16, 2>(p, nclusters, st) : tm == 3 ? launch_cs<16, 3>(p, nclusters, st) : launch_cs<16, 4>(p, nclusters, st);
-  return tm == 2 ? launch_cs<8, 2>(p, nclusters, st) : tm == 3 ? launch_cs<8, 3>(p, nclusters, st) : launch_cs<8, 4>(p, nclusters, st);
+// co-resident clusters per (variant, cluster size): out[0] occ1/16, out[1] occ1/8, out[2] occ2/16, out[3] occ2/8
+void rowphase_cluster_capacity(int* out) {
+  out[0] = max_clusters(occ1::k_rowphase<16, 4>, occ1::SMEM_BYTES, 16);
+  out[1] = max_clusters(occ1::k_rowphase<8, 4>, occ1::SMEM_BYTES, 8);
+  out[2] = max_clusters(occ2::k_rowphase<16, 2>, occ2::SMEM_BYTES, 16);
+  out[3] = max_clusters(occ2::k_rowphase<8, 2>, occ2::SMEM_BYTES, 8);
+}
+size_t rowphase_smem_bytes(int variant) { return variant == 2 ? occ2::SMEM_BYTES : occ1::SMEM_BYTES; }
+
+cudaError_t launch_rowphase(const RowPhaseParams& p, int variant, int cs, int nclusters, int tm, cudaStream_t st) {
+  if (variant == 2) {
+    if (cs == 16) return tm == 1 ? launch_k(occ2::k_rowphase<16, 1>, occ2::SMEM_BYTES, p, cs, nclusters, st)
+                                 : launch_k(occ2::k_rowphase<16, 2>, occ2::SMEM_BYTES, p, cs, nclusters, st);
+    return tm == 1 ? launch_k(occ2::k_rowphase<8, 1>, occ2::SMEM_BYTES, p, cs, nclusters, st)
+                   : launch_k(occ2::k_rowphase<8, 2>, occ2::SMEM_BYTES, p, cs, nclusters, st);
+  }
+  if (cs == 16)
+    return tm == 2 ? launch_k(occ1::k_rowphase<16, 2>, occ1::SMEM_BYTES, p, cs, nclusters, st)
+         : tm == 3 ? launch_k(occ1::k_rowphase<16, 3>, occ1::SMEM_BYTES, p, cs, nclusters, st)
+                   : launch_k(occ1::k_rowphase<16, 4>, occ1::SMEM_BYTES, p, cs, nclusters, st);
+  return tm == 2 ? launch_k(occ1::k_rowphase<8, 2>, occ1::SMEM_BYTES, p, cs, nclusters, st)
+       : tm == 3 ? launch_k(occ1::k_rowphase<8, 3>, occ1::SMEM_BYTES, p, cs, nclusters, st)
+                 : launch_k(occ1::k_rowphase<8, 4>, occ1::SMEM_BYTES, p, cs, nclusters, st);
 }
 
 }  // namespace sc

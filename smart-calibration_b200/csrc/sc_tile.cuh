@@ -18,13 +18,8 @@ namespace sc {
 // Slot layout: A part [8 k-blocks][32 rows][32 floats], W part the same (dgrad: [256 n][32 cols] as two 128-row panels).
 // With SWIZZLE_128B the 16-byte chunk c of row r sits at chunk position c ^ (r & 7), which is exactly what makes the
 // register-tile reads below conflict-free: lanes that read rows r, r+1, .., r+7 at the same k hit 8 different chunks.
-constexpr int KC = 256;            // reduction elements per slot (8 k-blocks of 32 floats = 128 bytes)
-constexpr int KBLK = KC / 32;
-constexpr int NSTAGE = 2;          // slots (64 KB each): the producer fills one while the consumers work on the other
-constexpr int BOXF = 32 * 32;      // floats per TMA box
-constexpr int SLOT_A = KBLK * BOXF;
-constexpr int SLOT_W = KBLK * BOXF;   // dgrad: two [128 n][32 cols] panels
-constexpr int SLOT = SLOT_A + SLOT_W;
+constexpr int BOXF = 32 * 32;      // floats per TMA box (32 rows x 128 bytes)
+// (slot geometry -- KC, NSTAGE, SLOT_A/W -- is a per-configuration constant of sc_rowphase_impl.cuh)
 
 // ---- forward: rows rg+8i (i<TM), cols cg+4j (j<TN); operands read as float4 along k -------------------------
 template <int TM, int TN>
@@ -113,12 +108,12 @@ __device__ __forceinline__ void mma_tn(const float* __restrict__ sD, const float
 }
 
 // ---- split-reduction combine: every warp parks its partial tile, then 256 threads add the 8 partials -----
-// red: [8][32][NT+4] floats.  Result (plus optional bias over columns) lands in sZ[8*TM][NT] (pitch NT).
+// red: [8][8*TM][NT+4] floats.  Result (plus optional bias over columns) lands in sZ[8*TM][NT] (pitch NT).
 template <int TM, int TN, bool NN>
 __device__ __forceinline__ void park_partial(float* red, const float (&acc)[TM][TN]) {
   constexpr int NT = 4 * TN, P = NT + 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* base = red + warp * 32 * P;
+  float* base = red + warp * (8 * TM) * P;
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -135,7 +130,7 @@ __device__ __forceinline__ void combine_partials(const float* red, float* sZ, co
     const int r = e / NT, c = e % NT;
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < SC_WARPS; ++w) s += red[(w * 32 + r) * P + c];
+    for (int w = 0; w < SC_WARPS; ++w) s += red[(w * (8 * TM) + r) * P + c];
     if (bias_slice != nullptr && c < ncv) s += ld_w(bias_slice + c);
     sZ[r * NT + c] = s;
   }

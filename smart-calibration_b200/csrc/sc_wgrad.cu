@@ -43,14 +43,15 @@ __device__ __forceinline__ void stage_panel(float* sm, const float* src, int ld,
   const int tid = threadIdx.x;
   const bool vec = ((ld & 3) == 0) && ((ncols & 3) == 0);
   if (vec) {
+    // 16-byte cp.async (LDGSTS through L2): every copy of the panel is in flight at once; the caller waits on the group
     for (int e = tid; e < nb * 8; e += SC_THREADS) {
       const int b = e >> 3, c4 = e & 7;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c0 + 4 * c4 < ncols) {
-        const size_t row = gather ? (size_t)gather[b0 + b] : (size_t)(b0 + b);
-        v = ACT ? ld_act4(src + row * ld + c0 + 4 * c4) : ld_w4(src + row * ld + c0 + 4 * c4);
-      }
-      *reinterpret_cast<float4*>(sm + b * 32 + 4 * c4) = v;
+      const bool ok = c0 + 4 * c4 < ncols;
+      const size_t row = ok ? (gather ? (size_t)gather[b0 + b] : (size_t)(b0 + b)) : 0;
+      const unsigned d = (unsigned)__cvta_generic_to_shared(sm + b * 32 + 4 * c4);
+      const float* g = ok ? src + row * ld + c0 + 4 * c4 : src;
+      const int sz = ok ? 16 : 0;            // src-size 0 zero-fills the destination
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(g), "r"(sz) : "memory");
     }
   } else {
     for (int e = tid; e < nb * 32; e += SC_THREADS) {
@@ -111,10 +112,9 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_wgrad_adam(const __grid_const
       }
       continue;
     }
-    // ---- locate the op that owns this tile ----
-    int oi = -1;
-    for (int i = 0; i < p.nops; ++i)
-      if (tile >= p.ops[i].tile_base && tile < p.ops[i].tile_base + p.ops[i].tile_count) oi = i;
+    // ---- the op that owns this tile (host-built table) ----
+    const int owner = __ldg(p.tile_map + tile);
+    int oi = owner < 1000 ? owner : -1;
     if (oi >= 0) {
       const WgradOp op = p.ops[oi];
       const int lt = tile - op.tile_base;
@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_wgrad_adam(const __grid_const
         stage_panel<true>(sD, op.D, op.ldd, op.N, n0, b0, nb, nullptr);
         if (op.gather) stage_panel<false>(sX, op.X, op.ldx, op.K, k0, b0, nb, p.bidx);
         else stage_panel<true>(sX, op.X, op.ldx, op.K, k0, b0, nb, nullptr);
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
         __syncthreads();
         mma_tn(sD, sX, (nb * warp) / SC_WARPS, (nb * (warp + 1)) / SC_WARPS, acc);
       }
@@ -144,26 +145,56 @@ __global__ void __launch_bounds__(SC_THREADS, 2) k_wgrad_adam(const __grid_const
       }
       __syncthreads();
       const AdamHyper h = p.hyper[op.opt];
-      for (int e = tid; e < 32 * 32; e += SC_THREADS) {
-        const int n = e >> 5, k = e & 31;
-        if (n0 + n < op.N && k0 + k < op.K) {
-          float g = 0.f;
+      // each thread owns 4 elements (rows warp+8u, column lane): all parameter/moment/target loads are issued before
+      // any arithmetic so that their HBM/L2 round trips overlap
+      {
+        const int k = lane;
+        const bool soft = op.T != nullptr && p.do_soft;
+        float g[4], m[4], v[4], pr[4], tg[4];
+        size_t idx[4];
+        bool ok[4];
 #pragma unroll
-          for (int w = 0; w < SC_WARPS; ++w) g += red[(w * 32 + n) * 36 + k];
-          adam_apply(g, op.W, op.M, op.V, op.T, (size_t)(n0 + n) * op.ldw + k0 + k, h, p.tau, p.one_minus_tau, p.do_soft);
+        for (int u = 0; u < 4; ++u) {
+          const int n = warp + 8 * u;
+          ok[u] = n0 + n < op.N && k0 + k < op.K;
+          idx[u] = (size_t)(n0 + n) * op.ldw + k0 + k;
+          if (ok[u]) {
+            m[u] = op.M[idx[u]]; v[u] = op.V[idx[u]]; pr[u] = op.W[idx[u]];
+            tg[u] = soft ? op.T[idx[u]] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int n = warp + 8 * u;
+          float s = 0.f;
+#pragma unroll
+          for (int w = 0; w < SC_WARPS; ++w) s += red[(w * 32 + n) * 36 + k];
+          g[u] = s;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (!ok[u]) continue;
+          const float mm = fmaf(h.one_minus_b1, g[u] - m[u], m[u]);
+          const float vv = __fadd_rn(__fmul_rn(v[u], h.b2), __fmul_rn(__fmul_rn(h.one_minus_b2, g[u]), g[u]));
+          const float denom = __fadd_rn(__fdiv_rn(sqrtf(vv), h.bc2_sqrt), h.eps);
+          const float pp = __fadd_rn(pr[u], __fdiv_rn(__fmul_rn(h.lr_neg_step, mm), denom));
+          op.M[idx[u]] = mm;
+          op.V[idx[u]] = vv;
+          op.W[idx[u]] = pp;
+          if (soft) op.T[idx[u]] = __fadd_rn(__fmul_rn(p.tau, pp), __fmul_rn(p.one_minus_tau, tg[u]));
         }
       }
       continue;
     }
     // ---- vector parameter tile ----
-    for (int i = 0; i < p.nvops; ++i)
-      if (tile >= p.vops[i].tile_base && tile < p.vops[i].tile_base + p.vops[i].tile_count) oi = i;
-    if (oi < 0) continue;
+    oi = owner - 1000;
+    if (oi < 0 || oi >= p.nvops) continue;
     const VecOp vo = p.vops[oi];
     const int n = (tile - vo.tile_base) * 32 + lane;
     float s = 0.f;
     if (n < vo.N) {
       const int b_lo = (p.B * warp) / SC_WARPS, b_hi = (p.B * (warp + 1)) / SC_WARPS;
+#pragma unroll 8
       for (int b = b_lo; b < b_hi; ++b) {
         const float d = ld_act(vo.D + (size_t)b * vo.ld + n);
         s = vo.E ? fmaf(d, ld_act(vo.E + (size_t)b * vo.ld + n), s) : s + d;
