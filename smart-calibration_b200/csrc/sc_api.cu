@@ -30,6 +30,8 @@ cudaError_t launch_per_update(double* tree, int C, int B, const int* idx, const 
                               const float* ps_in, cudaStream_t st);
 cudaError_t launch_sample_uniform(int n, int B, uint64_t seed, uint64_t ctr, int* out, cudaStream_t st);
 cudaError_t launch_fill_normal(float* out, int n, uint64_t seed, uint64_t stream, cudaStream_t st);
+cudaError_t launch_admm_update(int mode, int it, const float* pi, const float* hint, int Ap, const int* bidx, int B, int A,
+                               float* lambda, float* y0, float* a0, float* rho, float rho0, float corr_min, cudaStream_t st);
 cudaError_t launch_hint_coef(const float* pi, const float* hint, int Ap, const int* bidx, int B, int A, float thr, float admm_rho,
                              const float* rho, float* out, float* rho_update, cudaStream_t st);
 }  // namespace sc
@@ -176,7 +178,7 @@ struct sc_agent {
   TargetWs tw[2];
   ActorWs aw;
   std::map<std::string, sc_tensor_info> buffers;
-  float *y, *err, *part, *is_w, *is_wsum, *eps[3], *stats, *hint_out, *rho_dev, *ps_out;
+  float *y, *err, *part, *is_w, *is_wsum, *eps[3], *stats, *hint_out, *rho_dev, *ps_out, *admm_lambda, *admm_y0, *admm_a0;
   int *bidx, *tree_idx;
   unsigned long long* tstamp;
   double* u01;
@@ -290,6 +292,10 @@ static size_t carve(sc_agent* a, void* base) {
   reg("eps_cur", a->eps[1], B, A, A, 4);
   a->stats = cv.f(16);
   a->hint_out = cv.f(8);
+  a->admm_lambda = cv.f((size_t)B * A);
+  a->admm_y0 = cv.f((size_t)B * A);
+  a->admm_a0 = cv.f((size_t)B * A);
+  reg("admm_lambda", a->admm_lambda, B, A, A, 4);
   a->rho_dev = cv.f(4);
   a->bidx = (int*)cv.take(sizeof(int) * B);
   a->tree_idx = (int*)cv.take(sizeof(int) * B);
@@ -1049,10 +1055,29 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
       a->launches++;
       p.hint_coef = a->hint_out;
     }
-    if ((rc = run_rowphase(a, p, 2))) return rc;
-    a->t_actor++;
-    fill_wgrad(a, w, true, 1, 2);
-    if ((rc = run_wgrad(a, w, 3))) return rc;
+    if (!sac && a->cfg.use_hint) {
+      // adaptive-ADMM inner loop (enet_td3.py:310-361): Nadmm = 5 actor steps against the hint constraint; the penalty
+      // lives on the device (rho_dev) and may be re-estimated after the 4th step; targets move once, after the loop
+      CK(launch_admm_update(0, 0, a->aw.pi, a->rp.hint, a->Ap, a->bidx, a->B, a->A, a->admm_lambda, a->admm_y0, a->admm_a0,
+                            a->rho_dev, a->admm_rho, 0.5f, a->st));
+      a->launches++;
+      p.admm_lambda = a->admm_lambda;
+      p.admm_rho = a->rho_dev;
+      for (int it = 0; it < 5; ++it) {
+        if ((rc = run_rowphase(a, p, 2))) return rc;
+        a->t_actor++;
+        fill_wgrad(a, w, true, it == 4 ? 1 : 0, 2);
+        if ((rc = run_wgrad(a, w, 3))) return rc;
+        CK(launch_admm_update(1, it, a->aw.pi, a->rp.hint, a->Ap, a->bidx, a->B, a->A, a->admm_lambda, a->admm_y0, a->admm_a0,
+                              a->rho_dev, a->admm_rho, 0.5f, a->st));
+        a->launches++;
+      }
+    } else {
+      if ((rc = run_rowphase(a, p, 2))) return rc;
+      a->t_actor++;
+      fill_wgrad(a, w, true, 1, 2);
+      if ((rc = run_wgrad(a, w, 3))) return rc;
+    }
     if (sac && a->cfg.use_hint && a->learn_counter % 10 == 0) {
       // dual ascent on the hint multiplier with a fresh no-grad sample from the UPDATED actor (enet_sac.py:608-617)
       if (noise && noise->eps_dual_host) CK(cudaStreamSynchronize(a->st));

@@ -54,7 +54,10 @@ struct TensorMaps {
   const void *t_h1, *th11[2], *ch11[2];      // critic phase, layer-1 outputs
   const void *h1, *ph11[2];                  // actor phase, layer-1 outputs
   const void *dz12[2], *dz2;                 // dgrad inputs
-  const void *obs, *aux;                     // PROG_ACT
+  const void *obs, *aux;                     // TD3 ADMM hint loop (enet_td3.py:310-361): d loss1 / d a = mean(w)/numel * lambda + mean(w)*rho/numel^2 * (a - hint)
+  const float* admm_lambda;                  // [B][A] Lagrange multipliers, or nullptr
+  const float* admm_rho;                     // device scalar: current (adaptive) penalty
+  // PROG_ACT
   const void *actor_w1, *actor_w2;           // actor evaluated in this phase (online or target)
   const void *crit_w11[2], *crit_w12[2], *targ_w11[2], *targ_w12[2];
   const void *actor_w2p, *crit_w12p[2];      // dgrad panels
@@ -85,11 +88,14 @@ struct RowPhaseParams {
   int n_q;                                   // critics used by the actor phase (SAC 2, TD3 1)
   // hint penalty (SAC, enet_sac.py:601-602): coefficient already folded by the host-side pre-pass
   const float* hint_coef;                    // device scalar: (admm_rho*g + rho) * 2*max(0,m-thr) * 2/(B*A), or nullptr
+  // TD3 ADMM hint loop (enet_td3.py:310-361): d loss1 / d a = mean(w)/numel * lambda + mean(w)*rho/numel^2 * (a - hint)
+  const float* admm_lambda;                  // [B][A] Lagrange multipliers, or nullptr
+  const float* admm_rho;                     // device scalar: current (adaptive) penalty
   // PROG_ACT
   const float* obs;                          // [Sp]
   float* act_out;                            // [A]
   float* act_aux;                            // scratch [H1 + H2] activations for the single row
-  int dbg;                                   // profiling experiments: 1 = skip the FFMA work, 2 = skip the operand copies
+  int dbg;                                   // profiling experiment ($SMARTCAL_DBG): 1 = skip the FFMA work of the GEMM stages
   unsigned long long* tstamp;                // optional [CTAs][8] globaltimer stamps at stage boundaries (debug/profiling)
 };
 

@@ -329,6 +329,56 @@ __global__ void k_hint_coef(const float* __restrict__ pi, const float* __restric
   }
 }
 
+// TD3 ADMM bookkeeping after one inner actor step (enet_td3.py:331-359).  One block.
+//   mode 0: start of the loop: lambda <- 0, rho <- rho0
+//   mode 1: lambda += rho*(pi - hint); it == 0 additionally y0 <- pi, a0 <- pi (the reference seeds y0 with the actions);
+//           it == 3 additionally the adaptive-penalty test with the three dot products
+__global__ void k_admm_update(int mode, int it, const float* __restrict__ pi, const float* __restrict__ hint, int Ap,
+                              const int* __restrict__ bidx, int B, int A, float* lambda, float* y0, float* a0, float* rho,
+                              float rho0, float corr_min) {
+  __shared__ float sred[3][32];
+  const int n = B * A, tid = threadIdx.x;
+  if (mode == 0) {
+    for (int e = tid; e < n; e += blockDim.x) lambda[e] = 0.f;
+    if (tid == 0) *rho = rho0;
+    return;
+  }
+  const float r = *rho;
+  float d11 = 0.f, d12 = 0.f, d22 = 0.f;
+  for (int e = tid; e < n; e += blockDim.x) {
+    const int b = e / A, j = e - b * A;
+    const float a = pi[e];
+    const float diff = a - hint[(size_t)bidx[b] * Ap + j];
+    const float lam = lambda[e] + r * diff;
+    lambda[e] = lam;
+    if (it == 0) {
+      y0[e] = a;
+      a0[e] = a;
+    } else if (it == 3) {
+      const float y1 = lam + r * diff;
+      const float dy = y1 - y0[e], du = a - a0[e];
+      d11 = fmaf(dy, dy, d11);
+      d12 = fmaf(dy, du, d12);
+      d22 = fmaf(du, du, d22);
+      y0[e] = y1;
+      a0[e] = a;
+    }
+  }
+  if (it != 3) return;
+  d11 = warp_sum(d11); d12 = warp_sum(d12); d22 = warp_sum(d22);
+  if ((tid & 31) == 0) { sred[0][tid >> 5] = d11; sred[1][tid >> 5] = d12; sred[2][tid >> 5] = d22; }
+  __syncthreads();
+  if (tid == 0) {
+    float s11 = 0.f, s12 = 0.f, s22 = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { s11 += sred[0][w]; s12 += sred[1][w]; s22 += sred[2][w]; }
+    if (s11 > 0.f && s12 > 0.f && s22 > 0.f) {
+      const float alpha = s12 / sqrtf(s11 * s22), a_sd = s11 / s12, a_mg = s12 / s22;
+      const float a_hat = 2.f * a_mg > a_sd ? a_mg : a_sd - 0.5f * a_mg;
+      if (alpha > corr_min && a_hat < 10.f * rho0 && a_hat > 0.1f * rho0) *rho = a_hat;
+    }
+  }
+}
+
 // ---- host launchers ------------------------------------------------------------------------------------
 cudaError_t launch_replay_store(const ReplayP& rp, const float* tr, int slot, int mode, double priority, double clip, cudaStream_t st) {
   k_replay_store<<<1, 256, 0, st>>>(rp, tr, slot, mode, priority, clip);
@@ -379,6 +429,12 @@ cudaError_t launch_fill_normal(float* out, int n, uint64_t seed, uint64_t stream
 cudaError_t launch_hint_coef(const float* pi, const float* hint, int Ap, const int* bidx, int B, int A, float thr, float admm_rho,
                              const float* rho, float* out, float* rho_update, cudaStream_t st) {
   k_hint_coef<<<1, 256, 0, st>>>(pi, hint, Ap, bidx, B, A, thr, admm_rho, rho, out, rho_update);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_admm_update(int mode, int it, const float* pi, const float* hint, int Ap, const int* bidx, int B, int A,
+                               float* lambda, float* y0, float* a0, float* rho, float rho0, float corr_min, cudaStream_t st) {
+  k_admm_update<<<1, 256, 0, st>>>(mode, it, pi, hint, Ap, bidx, B, A, lambda, y0, a0, rho, rho0, corr_min);
   return cudaGetLastError();
 }
 

@@ -81,13 +81,13 @@ __device__ __forceinline__ void fwd_tile(const float* ring, const Pipe& pipe, un
   for (int k0 = 0; k0 < K; k0 += KC, ++g) {
     const unsigned slot = g % NSTAGE;
     long long t0 = prof ? clock64() : 0;
-    if (!(pipe.dbg & 2)) mbar_wait(pipe.full + slot, (g / NSTAGE) & 1u);
+    mbar_wait(pipe.full + slot, (g / NSTAGE) & 1u);
     long long t1 = prof ? clock64() : 0;
     const float* sA = ring + slot * SLOT;
     const int kq = min(KC, K - k0) >> 2;
     if (!(pipe.dbg & 1)) mma_nt<TM, TN>(sA, sA + SLOT_A, (kq * warp) / SC_WARPS, (kq * (warp + 1)) / SC_WARPS, acc);
     __syncwarp();
-    if (lane == 0 && !(pipe.dbg & 2)) mbar_arrive(pipe.empty + slot);
+    if (lane == 0) mbar_arrive(pipe.empty + slot);
     if (prof) { pipe.prof[0] += t1 - t0; pipe.prof[1] += clock64() - t1; }
   }
   long long t2 = prof ? clock64() : 0;
@@ -150,7 +150,7 @@ __device__ void dense_stage(const DenseOp* ops, int nops, int B, int row0, int n
 
   if (warp == SC_WARPS) {
     // ---------------- TMA producer warp: streams every reduction chunk of the stage through the ring ----------------
-    if (nrows > 0 && !(pipe.dbg & 2)) {
+    if (nrows > 0) {
       for (int o = 0; o < nops; ++o) {
         const DenseOp op = ops[o];
         const int Nc = round4((op.N + CS - 1) / CS);
@@ -440,146 +440,9 @@ __device__ void dgrad_stage(const DgradOp* ops, int nops, int B, int row0, int n
 // ======================================================================================================
 // row-local helpers (RT rows at a time, vectors in shared memory)
 // ======================================================================================================
-// zout[t][n] = bias[n] + sum_k W[n][k] * xin[t][k]; one warp per output feature, lanes along k (coalesced W rows)
-__device__ void gemv_rows(const float* __restrict__ W, int ldw, const float* __restrict__ bias, int N, int K,
-                          const float* xin, int ldx, float* zout, int ldz) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int K4 = K >> 2;
-  for (int n0 = warp * 4; n0 < N; n0 += SC_WARPS * 4) {
-    float acc[4][RT];
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int t = 0; t < RT; ++t) acc[u][t] = 0.f;
-    for (int k4 = lane; k4 < K4; k4 += 32) {
-      float4 x[RT];
-#pragma unroll
-      for (int t = 0; t < RT; ++t) x[t] = *reinterpret_cast<const float4*>(xin + t * ldx + 4 * k4);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (n0 + u < N) {
-          const float4 w = ld_w4(W + (size_t)(n0 + u) * ldw + 4 * k4);
-#pragma unroll
-          for (int t = 0; t < RT; ++t) acc[u][t] = dot4(w, x[t], acc[u][t]);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int t = 0; t < RT; ++t) acc[u][t] = warp_sum(acc[u][t]);
-    if (lane == 0) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (n0 + u < N) {
-          const float b = bias ? ld_w(bias + n0 + u) : 0.f;
-#pragma unroll
-          for (int t = 0; t < RT; ++t) zout[t * ldz + n0 + u] = acc[u][t] + b;
-        }
-    }
-  }
-}
-
-// out[t][k] = sum_n din[t][n] * W[n][k]  (k < K, K % 4 == 0, K/4 <= 256); scratch: [256/K4][RT][K] floats.
-// Ends with a consumer_sync(); `out` is complete afterwards.
-__device__ void gemvT_rows(const float* __restrict__ W, int ldw, int N, int K, const float* din, int ldd, float* out,
-                           int ldo, float* scratch) {
-  const int K4 = K >> 2;
-  const int parts = SC_THREADS / K4;
-  const int tid = threadIdx.x;
-  const int part = tid / K4, k4 = tid - part * K4;
-  if (part < parts) {
-    float4 acc[RT];
-#pragma unroll
-    for (int t = 0; t < RT; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int n = part; n < N; n += parts) {
-      const float4 w = ld_w4(W + (size_t)n * ldw + 4 * k4);
-#pragma unroll
-      for (int t = 0; t < RT; ++t) {
-        const float d = din[t * ldd + n];
-        acc[t].x = fmaf(d, w.x, acc[t].x);
-        acc[t].y = fmaf(d, w.y, acc[t].y);
-        acc[t].z = fmaf(d, w.z, acc[t].z);
-        acc[t].w = fmaf(d, w.w, acc[t].w);
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < RT; ++t) *reinterpret_cast<float4*>(scratch + ((size_t)(part * RT + t)) * K + 4 * k4) = acc[t];
-  }
-  consumer_sync();
-  for (int e = tid; e < RT * K; e += SC_THREADS) {
-    const int t = e / K, k = e - t * K;
-    float s = 0.f;
-    for (int p = 0; p < parts; ++p) s += scratch[((size_t)(p * RT + t)) * K + k];
-    out[t * ldo + k] = s;
-  }
-  consumer_sync();
-}
-
-// in place z[t][0:N] -> ELU(LN(z)); optionally keeps the normalised value and 1/std.  One warp per row.
-__device__ void ln_elu_rows(float* z, int ld, int N, const float* __restrict__ gamma, const float* __restrict__ beta,
-                            float* zh, float* rs, int rs_stride) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp < RT) {
-    float* zr = z + warp * ld;
-    float s = 0.f;
-    for (int j = lane; j < N; j += 32) s += zr[j];
-    const float mean = warp_sum(s) / (float)N;
-    float m2 = 0.f;
-    for (int j = lane; j < N; j += 32) {
-      const float d = zr[j] - mean;
-      m2 = fmaf(d, d, m2);
-    }
-    const float rstd = 1.0f / sqrtf(warp_sum(m2) / (float)N + SC_LN_EPS);
-    for (int j = lane; j < N; j += 32) {
-      const float n = (zr[j] - mean) * rstd;
-      if (zh != nullptr) zh[warp * ld + j] = n;
-      zr[j] = elu(fmaf(n, ld_w(gamma + j), ld_w(beta + j)));
-    }
-    if (lane == 0 && rs != nullptr) rs[warp * rs_stride] = rstd;
-  }
-}
-
-// dh -> du = dh * ELU'(.), dz = rstd * (du*gamma - mean(du*gamma) - zh * mean(du*gamma*zh)).  One warp per row.
-__device__ void ln_bwd_rows(const float* dh, const float* h, const float* zh, int ld, int N,
-                            const float* __restrict__ gamma, const float* rs, int rs_stride, float* du, float* dz) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp < RT) {
-    const int o = warp * ld;
-    float s1 = 0.f, s2 = 0.f;
-    for (int j = lane; j < N; j += 32) {
-      const float g = dh[o + j] * elu_grad_from_out(h[o + j]);
-      du[o + j] = g;
-      const float t = g * ld_w(gamma + j);
-      s1 += t;
-      s2 = fmaf(t, zh[o + j], s2);
-    }
-    const float c1 = warp_sum(s1) / (float)N, c2 = warp_sum(s2) / (float)N;
-    const float r = rs[warp * rs_stride];
-    for (int j = lane; j < N; j += 32) dz[o + j] = r * (du[o + j] * ld_w(gamma + j) - c1 - zh[o + j] * c2);
-  }
-}
-
 struct RowSet {          // the RT rows a CTA is carrying through the tail
   int row[RT];           // global batch row, or -1
 };
-
-__device__ __forceinline__ void load_rows_act(float* dst, int ld, const float* src, int lds, int N, const RowSet& rs) {
-  for (int e = threadIdx.x; e < RT * (N >> 2); e += SC_THREADS) {
-    const int t = e / (N >> 2), c4 = e - t * (N >> 2);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (rs.row[t] >= 0) v = ld_act4(src + (size_t)rs.row[t] * lds + 4 * c4);
-    *reinterpret_cast<float4*>(dst + t * ld + 4 * c4) = v;
-  }
-}
-__device__ __forceinline__ void store_rows(float* dst, int ldd, const float* src, int ld, int N, const RowSet& rs) {
-  if (dst == nullptr) return;
-  for (int e = threadIdx.x; e < RT * (N >> 2); e += SC_THREADS) {
-    const int t = e / (N >> 2), c4 = e - t * (N >> 2);
-    if (rs.row[t] >= 0)
-      *reinterpret_cast<float4*>(dst + (size_t)rs.row[t] * ldd + 4 * c4) = *reinterpret_cast<const float4*>(src + t * ld + 4 * c4);
-  }
-}
 
 // shared-memory map of the tail (floats); lives in the same dynamic buffer as the GEMM ring (different stages)
 constexpr int NETS = 4;   // critic phase: target critics 0,1 and online critics 2,3; actor phase: online critics 0,1
@@ -1081,6 +944,11 @@ __device__ void tail_actor(const RowPhaseParams& p, const TailSm& t, const RowSe
     const int row = rs.row[r];
     if (p.hint_coef != nullptr && row >= 0)
       da = fmaf(ld_act(p.hint_coef), t.an[r * AMAX + j] - ld_w(p.rp.hint + (size_t)p.bidx[row] * p.Ap + j), da);
+    if (p.admm_lambda != nullptr && row >= 0) {
+      const float numel = (float)p.B * (float)p.A, wmean = wsum / (float)p.B;
+      const float diff = t.an[r * AMAX + j] - ld_w(p.rp.hint + (size_t)p.bidx[row] * p.Ap + j);
+      da += wmean / numel * ld_act(p.admm_lambda + (size_t)row * p.A + j) + wmean * ld_act(p.admm_rho) / (numel * numel) * diff;
+    }
     if (p.kind == 0) {
       const float th = smp[0], sg = smp[1], e = smp[2];
       const float omt = 1.f - th * th;

@@ -4,8 +4,8 @@ libsmartcal_b200.so.  Same constructor signature, methods, attribute names and c
 
 Kept quirks: one scalar of target-smoothing noise per step, priorities refreshed before the critic step,
 (B,)x(B,1) broadcast in PER.mse and the actor loss, actor + all three targets move only every
-`update_actor_interval`-th learn().  The ADMM hint loop (enet_td3.py:310-361) is not on the CUDA path yet:
-use_hint=True raises (DESIGN.md "next").
+`update_actor_interval`-th learn(); with use_hint the adaptive-ADMM inner loop of enet_td3.py:310-361 (five actor steps,
+penalty re-estimated after the 4th) runs as five actor row-phase + Adam launches with the multipliers kept on the device.
 """
 import numpy as np
 import torch as T
@@ -41,8 +41,6 @@ class Agent():
     def __init__(self, gamma, lr_a, lr_c, input_dims, batch_size, n_actions,
                  max_mem_size=100, tau=0.001, update_actor_interval=2, warmup=1000, noise=0.1, prioritized=False,
                  use_hint=False, rng=None, device=None):
-        if use_hint:
-            raise NotImplementedError("TD3 ADMM hint loop (enet_td3.py:310-361) is not built yet on the CUDA path")
         self.gamma, self.tau, self.batch_size, self.n_actions = gamma, tau, batch_size, n_actions
         self.max_action, self.min_action = 1, -1
         self.time_step, self.warmup = 0, warmup
@@ -53,7 +51,8 @@ class Agent():
         self.rng = rng or H.default_rng_mode()
         S = int(input_dims[0])
         self._dev = dev = H.DeviceAgent(L.SC_KIND_TD3, S, n_actions, batch_size, max_mem_size, gamma, tau, lr_a, lr_c,
-                                        prioritized=prioritized, update_actor_interval=update_actor_interval,
+                                        prioritized=prioritized, use_hint=use_hint, update_actor_interval=update_actor_interval,
+                                        admm_rho=self.admm_rho,
                                         device=device, rng_seed=int(T.initial_seed()) & 0xffffffffffff)
         self.replaymem = (PER(max_mem_size, input_dims, n_actions, _dev=dev) if prioritized
                           else ReplayBuffer(max_mem_size, input_dims, n_actions, _dev=dev))
@@ -72,6 +71,7 @@ class Agent():
         H.critic_initial_state(S, n_actions)
         self.update_network_parameters(tau=1.)
         self.last_stats = None
+        self._admm_rho_sent = self.admm_rho
 
     @property
     def learn_step_cntr(self):
@@ -104,6 +104,9 @@ class Agent():
         dev = self._dev
         if dev.counters()[0] < self.batch_size:
             return
+        if self.use_hint and self.admm_rho != self._admm_rho_sent:     # callers set agent.admm_rho after construction (main_td3.py:22)
+            dev.set_scalars(0.0, 0.0, self.admm_rho)
+            self._admm_rho_sent = self.admm_rho
         if self.rng == 'reference':
             if self.prioritized:
                 dev.per_sample(np.random.random_sample(self.batch_size))

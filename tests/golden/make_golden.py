@@ -140,15 +140,18 @@ def sac_case(name, S, A, B, C, steps, seed, use_hint, done_frac):
     print(f"{name}: {steps} steps, oracle-vs-reference worst rel diff {worst:.3g}")
 
 
-def td3_case(name, S, A, B, C, steps, seed, prioritized, done_frac):
+def td3_case(name, S, A, B, C, steps, seed, prioritized, done_frac, use_hint=False, admm_rho=None):
     hp = dict(gamma=0.99, lr_a=1e-3, lr_c=1e-3, input_dims=[S], batch_size=B, n_actions=A, max_mem_size=C, tau=0.005,
               update_actor_interval=2, warmup=100, noise=0.1)
     tr = make_transitions(seed + 100, C, S, A, "uniform", done_frac)
     np.random.seed(seed)
     torch.manual_seed(seed)
-    agent = ref_td3.Agent(**hp, prioritized=prioritized, use_hint=False)
+    agent = ref_td3.Agent(**hp, prioritized=prioritized, use_hint=use_hint)
     torch.manual_seed(seed)
-    orc = Td3Ref(**hp, prioritized=prioritized, use_hint=False)
+    orc = Td3Ref(**hp, prioritized=prioritized, use_hint=use_hint)
+    if admm_rho is not None:          # main_td3.py:22 sets agent.admm_rho after construction
+        agent.admm_rho = admm_rho
+        orc.admm_rho = admm_rho
     for i in range(C):
         args = (tr["state"][i], tr["action"][i], float(tr["reward"][i]), tr["new_state"][i], bool(tr["done"][i]), tr["hint"][i])
         if prioritized:
@@ -159,7 +162,8 @@ def td3_case(name, S, A, B, C, steps, seed, prioritized, done_frac):
                 getattr(agent.replaymem, arr)[i0] = v
             agent.replaymem.mem_cntr += 1
         orc.store_flat(*args)
-    out = dict(cfg=np.array([S, A, B, C, steps, seed, int(prioritized)], np.int64), done_frac=np.array([done_frac]))
+    out = dict(cfg=np.array([S, A, B, C, steps, seed, int(prioritized)], np.int64), done_frac=np.array([done_frac]),
+               hint=np.array([int(use_hint), 0.0 if admm_rho is None else admm_rho]))
     if prioritized:
         out["tree_after_fill"] = agent.replaymem.tree.tree.copy()
         assert np.array_equal(orc.per.tree.tree, agent.replaymem.tree.tree), "PER fill differs"
@@ -265,3 +269,4 @@ if __name__ == "__main__":
     td3_case("td3_per_s24_b32", 24, 2, 32, 64, 4, 4, True, 0.1)
     td3_case("td3_uniform_s24_b32", 24, 2, 32, 64, 2, 5, False, 0.1)
     td3_case("td3_per_enet_b64", 420, 2, 64, 128, 2, 6, True, 0.05)
+    td3_case("td3_per_hint_s24_b32", 24, 2, 32, 64, 4, 7, True, 0.1, use_hint=True, admm_rho=1.0)

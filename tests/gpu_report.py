@@ -15,6 +15,8 @@ for w in which:
             r = PU.sac_parity_report(S=22, A=2, B=32, C=64, steps=12, seed=5, use_hint=True, verbose=True, trace=False)
         elif w == "td3":
             r = PU.td3_parity_report(S=24, A=2, B=32, C=64, steps=4, seed=9, prioritized=True, verbose=True)
+        elif w == "td3hint":
+            r = PU.td3_parity_report(S=24, A=2, B=32, C=64, steps=4, seed=13, prioritized=True, use_hint=True, admm_rho=1.0, verbose=True)
         elif w == "big":
             r = PU.sac_parity_report(S=420, A=2, B=256, C=1024, steps=2, seed=3, verbose=True)
         elif w == "bigper":

@@ -186,7 +186,7 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
-def compare_nets(rep, tag, agent, orc, grads, kind, lr=1e-3, tau=0.005, actor_stepped=True, targets_moved=True):
+def compare_nets(rep, tag, agent, orc, grads, kind, lr=1e-3, tau=0.005, actor_stepped=True, targets_moved=True, actor_inner_steps=1):
     trip = [("actor", agent.actor, orc.actor, orc.opt_a, grads.get("grad_a")),
             ("critic_1", agent.critic_1, orc.critic_1, orc.opt_1, grads.get("grad_c1")),
             ("critic_2", agent.critic_2, orc.critic_2, orc.opt_2, grads.get("grad_c2"))]
@@ -203,7 +203,7 @@ def compare_nets(rep, tag, agent, orc, grads, kind, lr=1e-3, tau=0.005, actor_st
                 gref = _np(g[k]) if g is not None else _np(st["exp_avg"])
             else:
                 sv = gref = np.ones_like(_np(p))
-            rep.add_params(f"{tag}{nm}.{k}", _np(sd[k]), _np(p), gref, sv, lr)
+            rep.add_params(f"{tag}{nm}.{k}", _np(sd[k]), _np(p), gref, sv, lr * (actor_inner_steps if nm == "actor" else 1))
     tl = [("target_critic_1", agent.target_critic_1, orc.target_critic_1, "critic_1"),
           ("target_critic_2", agent.target_critic_2, orc.target_critic_2, "critic_2")]
     if kind == "td3":
@@ -309,9 +309,14 @@ def sac_parity_report(S=24, A=2, B=32, C=64, steps=2, seed=7, prioritized=False,
     return rep_d
 
 
-def td3_parity_report(S=24, A=2, B=32, C=64, steps=4, seed=9, prioritized=True, verbose=False):
+def td3_parity_report(S=24, A=2, B=32, C=64, steps=4, seed=9, prioritized=True, verbose=False, use_hint=False, admm_rho=None):
     rep = Report(verbose)
-    orc, agent, tr, init_ok = build_pair("td3", S, A, B, C, seed, prioritized, False, reward="uniform")
+    orc, agent, tr, init_ok = build_pair("td3", S, A, B, C, seed, prioritized, use_hint, reward="uniform")
+    if admm_rho is not None:       # main_td3.py:22
+        orc.admm_rho = admm_rho
+        agent.admm_rho = admm_rho
+        agent._dev.set_scalars(0.0, 0.0, admm_rho)       # what Agent.learn() does when the attribute changed
+        agent._admm_rho_sent = admm_rho
     rep.add_exact("init.state_dict (reference draw order)", init_ok, True)
     dev = agent._dev
     np.random.seed(seed + 1)
@@ -337,7 +342,7 @@ def td3_parity_report(S=24, A=2, B=32, C=64, steps=4, seed=9, prioritized=True, 
         rep.add(tag + "critic_1_loss", st["critic_1_loss"], res["critic_1_loss"], 1e-4)
         rep.add(tag + "critic_2_loss", st["critic_2_loss"], res["critic_2_loss"], 1e-4)
         rep.add_exact(tag + "actor_step", bool(st["actor_step"]), bool(res["actor_step"]))
-        if res["actor_step"]:
+        if res["actor_step"] and not use_hint:
             rep.add(tag + "actor_loss", st["actor_loss"], res["actor_loss"], 1e-4)
         if prioritized:
             rep.add(tag + "per.errors", _np(dev.buffer("err")), res["per_errors"], 1e-4)
@@ -345,6 +350,6 @@ def td3_parity_report(S=24, A=2, B=32, C=64, steps=4, seed=9, prioritized=True, 
             rep.add_ulp(tag + "per.priorities", _np(dev.buffer("per_ps")), priorities_from_errors_f32(_np(dev.buffer("err")), 100.0), 2)
             rep.add(tag + "per.tree", _np(dev.buffer("tree")).reshape(-1), orc.per.tree.tree, 1e-6)
             agent.replaymem.tree.tree = orc.per.tree.tree
-        compare_nets(rep, tag, agent, orc, res, "td3", targets_moved=bool(res["actor_step"]))
+        compare_nets(rep, tag, agent, orc, res, "td3", targets_moved=bool(res["actor_step"]), actor_inner_steps=5 if use_hint else 1)
         sync_device_to_oracle(agent, orc, "td3")
     return dict(ok=not rep.failures, failures=rep.failures, rows=rep.rows, max_grad_rel=rep.max_grad_rel, launches=dev.launch_count())

@@ -57,3 +57,9 @@ def test_td3_per_batch_1024():
 def test_batch_64_reference_default():
     # BASELINE.json configs[0] batch size (main_sac.py:34)
     _assert(PU.sac_parity_report(S=420, A=2, B=64, C=1024, steps=2, seed=12))
+
+
+def test_td3_admm_hint_loop():
+    # enet_td3.py:310-361 (five inner actor steps, adaptive penalty), admm_rho set after construction like main_td3.py:22
+    _assert(PU.td3_parity_report(S=24, A=2, B=32, C=64, steps=4, seed=13, prioritized=True, use_hint=True, admm_rho=1.0))
+    _assert(PU.td3_parity_report(S=24, A=2, B=32, C=64, steps=2, seed=14, prioritized=False, use_hint=True))

@@ -92,7 +92,7 @@ def test_sac_oracle_matches_reference(name):
             np.testing.assert_allclose(float(orc.rho), z[f"step{s}/rho"][0], rtol=1e-4, atol=1e-9)
 
 
-@pytest.mark.parametrize("name", ["td3_per_s24_b32", "td3_uniform_s24_b32", "td3_per_enet_b64"])
+@pytest.mark.parametrize("name", ["td3_per_s24_b32", "td3_uniform_s24_b32", "td3_per_enet_b64", "td3_per_hint_s24_b32"])
 def test_td3_oracle_matches_reference(name):
     z = np.load(os.path.join(G, name + ".npz"))
     S, A, B, C, steps, seed, prioritized = [int(x) for x in z["cfg"]]
@@ -100,7 +100,10 @@ def test_td3_oracle_matches_reference(name):
               update_actor_interval=2, warmup=100, noise=0.1)
     tr = make_transitions(seed + 100, C, S, A, "uniform", float(z["done_frac"][0]))
     torch.manual_seed(seed)
-    orc = Td3Ref(**hp, prioritized=bool(prioritized), use_hint=False)
+    use_hint, rho = (int(z["hint"][0]), float(z["hint"][1])) if "hint" in z else (0, 0.0)
+    orc = Td3Ref(**hp, prioritized=bool(prioritized), use_hint=bool(use_hint))
+    if rho:
+        orc.admm_rho = rho
     for i in range(C):
         orc.store_flat(tr["state"][i], tr["action"][i], float(tr["reward"][i]), tr["new_state"][i], bool(tr["done"][i]), tr["hint"][i])
     if prioritized:
