@@ -16,6 +16,8 @@
 
 namespace sc {
 size_t rowphase_smem_bytes(int variant);
+int rowphase_max_rows(int variant);
+int rowphase_panel_rows(int variant);
 void rowphase_cluster_capacity(int* out4);
 cudaError_t launch_rowphase(const RowPhaseParams& p, int variant, int cluster_size, int nclusters, int tm, cudaStream_t st);
 size_t wgrad_smem_bytes();
@@ -314,8 +316,8 @@ static size_t carve(sc_agent* a, void* base) {
   a->act_out = cv.f(round4i(A));
   a->act_aux = cv.f(H1 + H2);
   a->store_stage = cv.f((size_t)a->T * 1);
-  a->tstamp = (unsigned long long*)cv.take(sizeof(unsigned long long) * 8 * 1536);
-  reg("debug_ts", a->tstamp, 1536, 8, 8, 8);
+  a->tstamp = (unsigned long long*)cv.take(sizeof(unsigned long long) * 8 * 2048);
+  reg("debug_ts", a->tstamp, 2048, 8, 8, 8);
   a->critic_ops = (WgradOp*)cv.take(sizeof(WgradOp) * 16);
   a->actor_ops = (WgradOp*)cv.take(sizeof(WgradOp) * 8);
   a->critic_vops = (VecOp*)cv.take(sizeof(VecOp) * 32);
@@ -429,35 +431,41 @@ static int build_tensor_maps(sc_agent* a) {
   const int B = a->B, K1 = a->Sp32;
   TensorMaps t;
   memset(&t, 0, sizeof(t));
-  t.mb_s = add(a->mb_s, K1, B, 32);
-  t.mb_s2 = add(a->mb_s2, K1, B, 32);
-  t.t_h1 = add(a->aw.t_h1, H1, B, 32);
-  t.h1 = add(a->aw.h1, H1, B, 32);
-  t.dz2 = add(a->aw.dz2, H2, B, 32);
-  t.obs = add(a->obs_dev, K1, 1, 32);
-  t.aux = add(a->act_aux, H1, 1, 32);
+  // box heights follow the row-phase geometry: activations are fetched one GEMM tile (8 TM rows) at a time, weights one
+  // CTA column slice (N / cluster size features) at a time, dgrad weight panels PROW reduction rows x 32 input columns
+  const int RB = 8 * a->tile_tm, CSZ = a->cluster_size;
+  const int W1 = ((H1 + CSZ - 1) / CSZ + 3) & ~3, W2 = ((H2 + CSZ - 1) / CSZ + 3) & ~3, PR = rowphase_panel_rows(a->row_variant);
+  if ((W1 != 16 && W1 != 32 && W1 != 64) || (W2 != 16 && W2 != 32 && W2 != 64))
+    return fail(SC_ERR_STATE, "row-phase column slices must be 16, 32 or 64 wide (got %d, %d)", W1, W2);
+  t.mb_s = add(a->mb_s, K1, B, RB);
+  t.mb_s2 = add(a->mb_s2, K1, B, RB);
+  t.t_h1 = add(a->aw.t_h1, H1, B, RB);
+  t.h1 = add(a->aw.h1, H1, B, RB);
+  t.dz2 = add(a->aw.dz2, H2, B, RB);
+  t.obs = add(a->obs_dev, K1, 1, RB);
+  t.aux = add(a->act_aux, H1, 1, RB);
   CriticP C[2] = {critic_ptrs(a->params + a->off_c1, a->Lc), critic_ptrs(a->params + a->off_c2, a->Lc)};
   CriticP T[2] = {critic_ptrs(a->targets + a->toff_c1, a->Lc), critic_ptrs(a->targets + a->toff_c2, a->Lc)};
   for (int k = 0; k < 2; ++k) {
-    t.th11[k] = add(a->tw[k].h11, H1, B, 32);
-    t.ch11[k] = add(a->cw[k].h11, H1, B, 32);
-    t.ph11[k] = add(a->cw[k].p_h11, H1, B, 32);
-    t.dz12[k] = add(a->cw[k].dz12, H2, B, 32);
-    t.crit_w11[k] = add(C[k].w11, K1, H1, 32);
-    t.crit_w12[k] = add(C[k].w12, H1, H2, 32);
-    t.targ_w11[k] = add(T[k].w11, K1, H1, 32);
-    t.targ_w12[k] = add(T[k].w12, H1, H2, 32);
-    t.crit_w12p[k] = add(C[k].w12, H1, H2, 128);
+    t.th11[k] = add(a->tw[k].h11, H1, B, RB);
+    t.ch11[k] = add(a->cw[k].h11, H1, B, RB);
+    t.ph11[k] = add(a->cw[k].p_h11, H1, B, RB);
+    t.dz12[k] = add(a->cw[k].dz12, H2, B, RB);
+    t.crit_w11[k] = add(C[k].w11, K1, H1, W1);
+    t.crit_w12[k] = add(C[k].w12, H1, H2, W2);
+    t.targ_w11[k] = add(T[k].w11, K1, H1, W1);
+    t.targ_w12[k] = add(T[k].w12, H1, H2, W2);
+    t.crit_w12p[k] = add(C[k].w12, H1, H2, PR);
   }
   ActorP on = actor_ptrs(a->params + a->off_actor, a->La, a->cfg.kind);
-  const void* on_w1 = add(on.w1, K1, H1, 32);
-  const void* on_w2 = add(on.w2, H1, H2, 32);
-  t.actor_w2p = add(on.w2, H1, H2, 128);
+  const void* on_w1 = add(on.w1, K1, H1, W1);
+  const void* on_w2 = add(on.w2, H1, H2, W2);
+  t.actor_w2p = add(on.w2, H1, H2, PR);
   const void *tg_w1 = on_w1, *tg_w2 = on_w2;
   if (td3) {
     ActorP tg = actor_ptrs(a->targets + a->toff_actor, a->La, a->cfg.kind);
-    tg_w1 = add(tg.w1, K1, H1, 32);
-    tg_w2 = add(tg.w2, H1, H2, 32);
+    tg_w1 = add(tg.w1, K1, H1, W1);
+    tg_w2 = add(tg.w2, H1, H2, W2);
   }
   if (rc != SC_OK) return rc;
   if (host.size() > 64) return fail(SC_ERR_STATE, "tensor map table overflow");
@@ -623,7 +631,7 @@ int sc_agent_create(const sc_config* cfg, void* arena, size_t arena_bytes, void*
       const int tm_max = variant == 1 ? 4 : 2, tm_min = variant == 1 ? 2 : 1;
       int ncl = cap[c];
       if (ncl > (a->B + 7) / 8) ncl = (a->B + 7) / 8;
-      while ((a->B + ncl - 1) / ncl > 128) ncl *= 2;                 // slab height limit of the LayerNorm staging buffers
+      while ((a->B + ncl - 1) / ncl > rowphase_max_rows(variant)) ncl *= 2;   // slab height limit of the LayerNorm staging buffers
       const int per = (a->B + ncl - 1) / ncl;
       for (int tm = tm_min; tm <= tm_max; ++tm) {
         const int padded = ((per + 8 * tm - 1) / (8 * tm)) * 8 * tm;
@@ -916,7 +924,7 @@ static int run_rowphase(sc_agent* a, const RowPhaseParams& p, int timer_id) {
   cudaEvent_t e0, e1;
   if (timer_id >= 0) timer_begin(a, timer_id, &e0, &e1);
   const int ncl = p.program == PROG_ACT ? 1 : a->nclusters;
-  CK(launch_rowphase(p, a->row_variant, a->cluster_size, ncl, p.program == PROG_ACT ? (a->row_variant == 2 ? 1 : 2) : a->tile_tm, a->st));
+  CK(launch_rowphase(p, a->row_variant, a->cluster_size, ncl, a->tile_tm, a->st));   // (the tensor-map boxes are built for tile_tm)
   if (timer_id >= 0) timer_end(a, timer_id, e0, e1);
   a->launches++;
   return SC_OK;

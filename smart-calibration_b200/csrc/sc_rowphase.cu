@@ -1,7 +1,7 @@
 // Cluster "row-phase" kernel, host side: two build configurations of sc_rowphase_impl.cuh and the launcher.
 //
-//   occ1: one CTA per SM  (184 KB shared memory: 2 x 64 KB operand slots of 256 reduction elements, <=32-row tiles, tail RT=4)
-//   occ2: two CTAs per SM (109 KB: 2 x 32 KB slots of 128 reduction elements, <=16-row tiles, tail RT=2, <=112 registers)
+//   occ1: one CTA per SM  (213 KB shared memory: 3 x 48 KB operand slots of 128 reduction elements, <=32-row tiles, tail RT=4)
+//   occ2: two CTAs per SM (99 KB: 3 x 20 KB slots of 64 reduction elements, <=16-row tiles, tail RT=2, <=112 registers)
 // occ2 doubles the number of resident clusters, so a 256-row batch is cut into 16-row slabs (no padded rows) and two
 // independent instruction streams share every SM, which hides the latencies this kernel is bound by.
 #include "sc_common.cuh"
@@ -9,7 +9,9 @@
 #include "sc_tile.cuh"
 
 #define SC_CFG_NS occ1
-#define SC_CFG_KC 256
+#define SC_CFG_KC 128
+#define SC_CFG_NSTAGE 3
+#define SC_CFG_MAXROWS 128
 #define SC_CFG_RT 4
 #define SC_CFG_REDROWS 32
 #define SC_CFG_ZK 8192
@@ -17,20 +19,26 @@
 #include "sc_rowphase_impl.cuh"
 #undef SC_CFG_NS
 #undef SC_CFG_KC
+#undef SC_CFG_NSTAGE
+#undef SC_CFG_MAXROWS
 #undef SC_CFG_RT
 #undef SC_CFG_REDROWS
 #undef SC_CFG_ZK
 #undef SC_CFG_MINBLOCKS
 
 #define SC_CFG_NS occ2
-#define SC_CFG_KC 128
+#define SC_CFG_KC 64
+#define SC_CFG_NSTAGE 3
+#define SC_CFG_MAXROWS 64
 #define SC_CFG_RT 2
 #define SC_CFG_REDROWS 16
-#define SC_CFG_ZK 4096
+#define SC_CFG_ZK 5120
 #define SC_CFG_MINBLOCKS 2
 #include "sc_rowphase_impl.cuh"
 #undef SC_CFG_NS
 #undef SC_CFG_KC
+#undef SC_CFG_NSTAGE
+#undef SC_CFG_MAXROWS
 #undef SC_CFG_RT
 #undef SC_CFG_REDROWS
 #undef SC_CFG_ZK
@@ -85,6 +93,8 @@ void rowphase_cluster_capacity(int* out) {
   out[3] = max_clusters(occ2::k_rowphase<8, 2>, occ2::SMEM_BYTES, 8);
 }
 size_t rowphase_smem_bytes(int variant) { return variant == 2 ? occ2::SMEM_BYTES : occ1::SMEM_BYTES; }
+int rowphase_max_rows(int variant) { return variant == 2 ? occ2::MAXROWS : occ1::MAXROWS; }       // slab height limit
+int rowphase_panel_rows(int variant) { return variant == 2 ? occ2::PROW : occ1::PROW; }           // dgrad weight panel box rows
 
 cudaError_t launch_rowphase(const RowPhaseParams& p, int variant, int cs, int nclusters, int tm, cudaStream_t st) {
   if (variant == 2) {

@@ -18,25 +18,27 @@ namespace SC_CFG_NS {
 
 constexpr int KC = SC_CFG_KC;            // reduction elements per ring slot
 constexpr int KBLK = KC / 32;            // 32-float (128-byte) k-blocks per slot
-constexpr int NSTAGE = 2;                // slots: the producer fills one while the consumers work on the other
-constexpr int SLOT_A = KBLK * BOXF;
-constexpr int SLOT_W = KBLK * BOXF;      // dgrad: KC/128 panels of [128 n][32 cols]
-constexpr int SLOT = SLOT_A + SLOT_W;
+constexpr int NSTAGE = SC_CFG_NSTAGE;    // ring slots: the producer runs up to NSTAGE-1 slots ahead of the consumers
 constexpr int RT = SC_CFG_RT;            // rows a CTA carries through the row-local tail at once
 constexpr int REDROWS = SC_CFG_REDROWS;  // max rows of a GEMM tile (8*TM)
+constexpr int WCOLS = 64;                // max output features (dgrad: input columns) of a CTA's slice
+constexpr int PROW = KC < 128 ? KC : 128;   // rows of a dgrad weight panel box
+constexpr int SLOT_A = KBLK * REDROWS * 32;  // [k-block][tile rows][32]
+constexpr int SLOT_W = KC * WCOLS;           // forward: [k-block][<=64 features][32]; dgrad: [KC/PROW][<=2][PROW][32]
+constexpr int SLOT = SLOT_A + SLOT_W;
 
 constexpr int MAXOPS = 8;
-constexpr int NPMAX = 16;          // max LayerNorm partials per row (CS * column chunks)
-constexpr int MAXROWS = 128;       // max slab rows per cluster
+constexpr int NPMAX = 16;          // max LayerNorm partials per row (one per CTA of the cluster)
+constexpr int MAXROWS = SC_CFG_MAXROWS;   // max slab rows per cluster
 
 struct DenseOp {                          // Z = X W^T + b, then LayerNorm + ELU
-  const void *mapA, *mapW;               // tensor maps of X [rows][K] and W [N][K] (K padded to a multiple of 32)
+  const void *mapA, *mapW;               // tensor maps of X [rows][K] (box: tile rows) and W [N][K] (box: the CTA's feature slice); K padded to 32
   const float *bias, *gamma, *beta;
   int K, N;
   float *H, *ZH, *RS; int ldo;
 };
 struct DgradOp {                          // dH_in = DZ W, then back through ELU / LayerNorm of the producing layer
-  const void *mapA, *mapP;               // tensor maps of DZ [rows][Nl] and the W panel ([Nl][Kin], box 32 x 128)
+  const void *mapA, *mapP;               // tensor maps of DZ [rows][Nl] and the W panel ([Nl][Kin], box 32 x PROW)
   int Nl, Kin;
   const float *Hp, *ZHp, *RSp, *gp;      // layer that produced the input (width Kin)
   float *DU, *DZo; int ldo;
@@ -44,20 +46,16 @@ struct DgradOp {                          // dH_in = DZ W, then back through ELU
 
 // dynamic shared memory map (floats): operand ring | split-reduction partials | output tile | LN statistics
 constexpr int SM_RING = NSTAGE * SLOT;
-constexpr int SM_RED = SC_WARPS * REDROWS * 36;
-constexpr int SM_Z = REDROWS * 32;
+constexpr int SM_RED = 160 * REDROWS;                  // max over (KS, NC) in {(8,16),(4,32),(2,64)} of KS * REDROWS * (NC + 4)
+constexpr int SM_Z = REDROWS * WCOLS;
 constexpr int SM_STAT = MAXOPS * MAXROWS * 2;
 constexpr int SM_ZK = SC_CFG_ZK;                       // raw pre-LayerNorm outputs of a stage, kept on chip between the two barriers
 constexpr int SM_TOTAL_FLOATS = SM_RING + SM_RED + SM_Z + SM_STAT + SM_ZK;
 
 __host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
 
-__device__ __forceinline__ int part_count(int N, int Nc, int nchunks, int pidx) {
-  const int rk = pidx / nchunks, ch = pidx - rk * nchunks;
-  const int start = rk * Nc + ch * 32;
-  const int width = min(32, Nc - ch * 32);
-  return max(0, min(width, N - start));
-}
+// valid columns of LayerNorm partial `rk` (= the slice of CTA rk): clamp(N - rk*Nc, 0, Nc)
+__device__ __forceinline__ int part_count(int N, int Nc, int rk) { return max(0, min(Nc, N - rk * Nc)); }
 
 struct Pipe {
   int dbg;
@@ -66,17 +64,20 @@ struct Pipe {
   uint64_t* empty;    // [NSTAGE] one arrival per consumer warp
 };
 
-// One output tile = all reduction chunks of (op, column chunk, row sub-tile).  `g` counts chunks since the kernel
-// began (ring slot = g % NSTAGE, mbarrier phase parity = (g / NSTAGE) & 1); producer and consumers walk the same sequence.
-template <int TM, int TN>
+// One output tile = all reduction chunks of (op, row sub-tile) for the CTA's whole column slice (MT feature tiles of 16).
+// The 8 consumer warps are (feature tile mt = warp % MT, reduction part kp = warp / MT).  `g` counts chunks since the
+// kernel began (ring slot = g % NSTAGE, mbarrier phase parity = (g / NSTAGE) & 1); producer and consumers walk the same sequence.
+template <int NT8, int MT>
 __device__ __forceinline__ void fwd_tile(const float* ring, const Pipe& pipe, unsigned& g, int K, float* red, float* sZ,
                                          const float* bias_slice, int ncv) {
-  float acc[TM][TN];
+  constexpr int KS = SC_WARPS / MT, NC = 16 * MT;
+  float acc[NT8][4];
 #pragma unroll
-  for (int i = 0; i < TM; ++i)
+  for (int i = 0; i < NT8; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = warp % MT, kp = warp / MT;
   const bool prof = pipe.prof != nullptr && threadIdx.x == 0;
   for (int k0 = 0; k0 < K; k0 += KC, ++g) {
     const unsigned slot = g % NSTAGE;
@@ -84,40 +85,42 @@ __device__ __forceinline__ void fwd_tile(const float* ring, const Pipe& pipe, un
     mbar_wait(pipe.full + slot, (g / NSTAGE) & 1u);
     long long t1 = prof ? clock64() : 0;
     const float* sA = ring + slot * SLOT;
-    const int kq = min(KC, K - k0) >> 2;
-    if (!(pipe.dbg & 1)) mma_nt<TM, TN>(sA, sA + SLOT_A, (kq * warp) / SC_WARPS, (kq * (warp + 1)) / SC_WARPS, acc);
+    const int nk8 = min(KC, K - k0) >> 3;
+    if (!(pipe.dbg & 1)) mma3_nt<NT8>(sA, 8 * NT8, sA + SLOT_A, NC, mt, (nk8 * kp) / KS, (nk8 * (kp + 1)) / KS, acc);
     __syncwarp();
     if (lane == 0) mbar_arrive(pipe.empty + slot);
     if (prof) { pipe.prof[0] += t1 - t0; pipe.prof[1] += clock64() - t1; }
   }
   long long t2 = prof ? clock64() : 0;
-  park_partial<TM, TN, false>(red, acc);
+  park_partial<NT8>(red, kp, mt, NC, acc);
   consumer_sync();
-  combine_partials<TM, TN>(red, sZ, bias_slice, ncv);
+  combine_partials<NT8>(red, KS, NC, sZ, bias_slice, ncv);
   consumer_sync();
   if (prof) pipe.prof[2] += clock64() - t2;
 }
 
-template <int TM, int TN>
+template <int NT8, int MT>
 __device__ __forceinline__ void bwd_tile(const float* ring, const Pipe& pipe, unsigned& g, int Nl, float* red, float* sZ) {
-  float acc[TM][TN];
+  constexpr int KS = SC_WARPS / MT, NC = 16 * MT, NCH = (NC + 31) / 32;
+  float acc[NT8][4];
 #pragma unroll
-  for (int i = 0; i < TM; ++i)
+  for (int i = 0; i < NT8; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = warp % MT, kp = warp / MT;
   for (int n0 = 0; n0 < Nl; n0 += KC, ++g) {
     const unsigned slot = g % NSTAGE;
     mbar_wait(pipe.full + slot, (g / NSTAGE) & 1u);
     const float* sA = ring + slot * SLOT;
-    const int kq = min(KC, Nl - n0) >> 2;
-    mma_nn<TM, TN>(sA, sA + SLOT_A, (kq * warp) / SC_WARPS, (kq * (warp + 1)) / SC_WARPS, acc);
+    const int nk8 = min(KC, Nl - n0) >> 3;
+    mma3_nn<NT8, PROW>(sA, 8 * NT8, sA + SLOT_A, NCH, mt, (nk8 * kp) / KS, (nk8 * (kp + 1)) / KS, acc);
     __syncwarp();
     if (lane == 0) mbar_arrive(pipe.empty + slot);
   }
-  park_partial<TM, TN, true>(red, acc);
+  park_partial<NT8>(red, kp, mt, NC, acc);
   consumer_sync();
-  combine_partials<TM, TN>(red, sZ, nullptr, 0);
+  combine_partials<NT8>(red, KS, NC, sZ, nullptr, 0);
   consumer_sync();
 }
 
@@ -153,25 +156,21 @@ __device__ void dense_stage(const DenseOp* ops, int nops, int B, int row0, int n
     if (nrows > 0) {
       for (int o = 0; o < nops; ++o) {
         const DenseOp op = ops[o];
-        const int Nc = round4((op.N + CS - 1) / CS);
-        const int nchunks = (Nc + 31) / 32;
-        for (int ch = 0; ch < nchunks; ++ch) {
-          const int n0 = rank * Nc + ch * 32;
-          const int width = min(32, Nc - ch * 32);
-          for (int sub = 0; sub < nsub; ++sub) {
-            const int r0 = row0 + sub * ROWS;
-            for (int k0 = 0; k0 < op.K; k0 += KC, ++g) {
-              const unsigned slot = g % NSTAGE;
-              const int nkb = (min(KC, op.K - k0) + 31) >> 5;               // 32-float k-blocks in this chunk
-              mbar_wait(pipe.empty + slot, ((g / NSTAGE) & 1u) ^ 1u);
-              float* sA = ring + slot * SLOT;
-              if (lane == 0) mbar_expect_tx(pipe.full + slot, (unsigned)nkb * 2u * BOXF * 4u);
-              __syncwarp();
-              // lanes 0..7: A boxes, lanes 8..15: W boxes; rows beyond the matrix are zero-filled by the TMA unit
-              if (lane < nkb) tma_load_2d(sA + lane * BOXF, op.mapA, k0 + 32 * lane, r0, pipe.full + slot);
-              else if (lane >= KBLK && lane - KBLK < nkb)
-                tma_load_2d(sA + SLOT_A + (lane - KBLK) * BOXF, op.mapW, k0 + 32 * (lane - KBLK), n0, pipe.full + slot);
-            }
+        const int Nc = round4((op.N + CS - 1) / CS);      // 16, 32 or 64 (checked at create)
+        const int n0 = rank * Nc;
+        for (int sub = 0; sub < nsub; ++sub) {
+          const int r0 = row0 + sub * ROWS;
+          for (int k0 = 0; k0 < op.K; k0 += KC, ++g) {
+            const unsigned slot = g % NSTAGE;
+            const int nkb = (min(KC, op.K - k0) + 31) >> 5;               // 32-float k-blocks in this chunk
+            mbar_wait(pipe.empty + slot, ((g / NSTAGE) & 1u) ^ 1u);
+            float* sA = ring + slot * SLOT;
+            if (lane == 0) mbar_expect_tx(pipe.full + slot, (unsigned)nkb * (unsigned)(ROWS + Nc) * 128u);
+            __syncwarp();
+            // lanes 0..KBLK-1: X boxes [ROWS][32], lanes KBLK..2KBLK-1: W boxes [Nc][32]; rows beyond the matrix are zero-filled
+            if (lane < nkb) tma_load_2d(sA + lane * ROWS * 32, op.mapA, k0 + 32 * lane, r0, pipe.full + slot);
+            else if (lane >= KBLK && lane - KBLK < nkb)
+              tma_load_2d(sA + SLOT_A + (lane - KBLK) * Nc * 32, op.mapW, k0 + 32 * (lane - KBLK), n0, pipe.full + slot);
           }
         }
       }
@@ -182,54 +181,49 @@ __device__ void dense_stage(const DenseOp* ops, int nops, int B, int row0, int n
     for (int o = 0; o < nops; ++o) {
       const DenseOp op = ops[o];
       const int Nc = round4((op.N + CS - 1) / CS);
-      const int nchunks = (Nc + 31) / 32;
       float* zko = zk + zbase;
       zbase += nsub * ROWS * Nc;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const int n0 = rank * Nc + ch * 32;
-        const int width = min(32, Nc - ch * 32);
-        const int ncv = max(0, min(width, op.N - n0));
-        const float* bias_slice = op.bias ? op.bias + n0 : nullptr;
-        for (int sub = 0; sub < nsub; ++sub) {
-          const int r0 = row0 + sub * ROWS;
-          const int rv = min(ROWS, nrows - sub * ROWS);
-          switch (width >> 2) {
-            case 8: fwd_tile<TM, 8>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv); break;
-            case 4: fwd_tile<TM, 4>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv); break;
-            case 2: fwd_tile<TM, 2>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv); break;
-            default: fwd_tile<TM, 1>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv); break;
-          }
-          // raw z -> H (own column slice) and per-row (mean, M2) over the valid columns of this chunk
-          const long long te = (pipe.prof && tid == 0) ? clock64() : 0;
-          const int row = tid >> 3, sub8 = tid & 7;
-          float s = 0.f;
-          if (row < rv)
-            for (int c = sub8; c < ncv; c += 8) s += sZ[row * width + c];
-          s = group8_sum(s);
-          const float mean = ncv > 0 ? s / (float)ncv : 0.f;
-          float m2 = 0.f;
-          if (row < rv)
-            for (int c = sub8; c < ncv; c += 8) {
-              const float d = sZ[row * width + c] - mean;
-              m2 = fmaf(d, d, m2);
-            }
-          m2 = group8_sum(m2);
-          if (row < rv) {
-            if (use_zk) {
-              float* zrow = zko + (sub * ROWS + row) * Nc + ch * 32;
-              for (int c = sub8; c < ncv; c += 8) zrow[c] = sZ[row * width + c];
-            } else {
-              float* hrow = op.H + (size_t)(r0 + row) * op.ldo + n0;
-              for (int c = sub8; c < ncv; c += 8) hrow[c] = sZ[row * width + c];
-            }
-            if (sub8 == 0) {
-              float* pp = part + (((size_t)o * B + (r0 + row)) * NPMAX + (rank * nchunks + ch)) * 2;
-              pp[0] = mean;
-              pp[1] = m2;
-            }
-          }
-          if (pipe.prof && tid == 0) pipe.prof[3] += clock64() - te;
+      const int n0 = rank * Nc;
+      const int ncv = max(0, min(Nc, op.N - n0));
+      const float* bias_slice = op.bias ? op.bias + n0 : nullptr;
+      for (int sub = 0; sub < nsub; ++sub) {
+        const int r0 = row0 + sub * ROWS;
+        const int rv = min(ROWS, nrows - sub * ROWS);
+        switch (Nc >> 4) {
+          case 4: fwd_tile<TM, 4>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv); break;
+          case 2: fwd_tile<TM, 2>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv); break;
+          default: fwd_tile<TM, 1>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv); break;
         }
+        // raw z -> zk / H (own column slice) and per-row (mean, M2) over the valid columns of the slice
+        const long long te = (pipe.prof && tid == 0) ? clock64() : 0;
+        const int row = tid >> 3, sub8 = tid & 7;
+        float s = 0.f;
+        if (row < rv)
+          for (int c = sub8; c < ncv; c += 8) s += sZ[row * Nc + c];
+        s = group8_sum(s);
+        const float mean = ncv > 0 ? s / (float)ncv : 0.f;
+        float m2 = 0.f;
+        if (row < rv)
+          for (int c = sub8; c < ncv; c += 8) {
+            const float d = sZ[row * Nc + c] - mean;
+            m2 = fmaf(d, d, m2);
+          }
+        m2 = group8_sum(m2);
+        if (row < rv) {
+          if (use_zk) {
+            float* zrow = zko + (sub * ROWS + row) * Nc;
+            for (int c = sub8; c < ncv; c += 8) zrow[c] = sZ[row * Nc + c];
+          } else {
+            float* hrow = op.H + (size_t)(r0 + row) * op.ldo + n0;
+            for (int c = sub8; c < ncv; c += 8) hrow[c] = sZ[row * Nc + c];
+          }
+          if (sub8 == 0) {
+            float* pp = part + (((size_t)o * B + (r0 + row)) * NPMAX + rank) * 2;
+            pp[0] = mean;
+            pp[1] = m2;
+          }
+        }
+        if (pipe.prof && tid == 0) pipe.prof[3] += clock64() - te;
       }
     }
   }
@@ -243,33 +237,21 @@ __device__ void dense_stage(const DenseOp* ops, int nops, int B, int row0, int n
       const int o = i / nrows, r = i - o * nrows;
       const DenseOp& op = ops[o];
       const int Nc = round4((op.N + CS - 1) / CS);
-      const int nchunks = (Nc + 31) / 32;
-      const int np = CS * nchunks;
       const float* pp = part + (((size_t)o * B + (row0 + r)) * NPMAX) * 2;
       // all partials are fetched first (independent L2 loads in flight together), then combined in fixed order
-      float2 pv[NPMAX];
+      float2 pv[CS];
 #pragma unroll
-      for (int p = 0; p < NPMAX; ++p) pv[p] = p < np ? __ldcg(reinterpret_cast<const float2*>(pp) + p) : make_float2(0.f, 0.f);
-      // valid-column count of partial p = (rank rk, chunk ch): clamp(N - (rk*Nc + 32 ch), 0, min(32, Nc - 32 ch))
+      for (int p = 0; p < CS; ++p) pv[p] = __ldcg(reinterpret_cast<const float2*>(pp) + p);
       float msum = 0.f;
 #pragma unroll
-      for (int p = 0; p < NPMAX; ++p) {
-        if (p < np) {
-          const int rk = nchunks == 1 ? p : p >> 1, ch = nchunks == 1 ? 0 : p & 1;      // nchunks is 1 or 2 (Nc <= 64)
-          const int cnt = max(0, min(min(32, Nc - ch * 32), op.N - (rk * Nc + ch * 32)));
-          msum = fmaf((float)cnt, pv[p].x, msum);
-        }
-      }
+      for (int p = 0; p < CS; ++p) msum = fmaf((float)part_count(op.N, Nc, p), pv[p].x, msum);
       const float mean = msum / (float)op.N;
       float m2 = 0.f;
 #pragma unroll
-      for (int p = 0; p < NPMAX; ++p) {
-        if (p < np) {
-          const int rk = nchunks == 1 ? p : p >> 1, ch = nchunks == 1 ? 0 : p & 1;
-          const int cnt = max(0, min(min(32, Nc - ch * 32), op.N - (rk * Nc + ch * 32)));
-          const float d = pv[p].x - mean;
-          if (cnt > 0) m2 += pv[p].y + (float)cnt * d * d;
-        }
+      for (int p = 0; p < CS; ++p) {
+        const int cnt = part_count(op.N, Nc, p);
+        const float d = pv[p].x - mean;
+        if (cnt > 0) m2 += pv[p].y + (float)cnt * d * d;
       }
       const float rstd = 1.0f / sqrtf(m2 / (float)op.N + SC_LN_EPS);
       stat[2 * i] = mean;
@@ -324,26 +306,24 @@ __device__ void dgrad_stage(const DgradOp* ops, int nops, int B, int row0, int n
     if (nrows > 0) {
       for (int o = 0; o < nops; ++o) {
         const DgradOp op = ops[o];
-        const int Kc = round4((op.Kin + CS - 1) / CS);
-        const int nchunks = (Kc + 31) / 32;
-        for (int ch = 0; ch < nchunks; ++ch) {
-          const int k0 = rank * Kc + ch * 32;
-          const int width = min(32, Kc - ch * 32);
-          const int kcv = max(0, min(width, op.Kin - k0));
-          for (int sub = 0; sub < nsub; ++sub) {
-            const int r0 = row0 + sub * ROWS;
-            const int rv = min(ROWS, nrows - sub * ROWS);
-            for (int n0 = 0; n0 < op.Nl; n0 += KC, ++g) {
-              const unsigned slot = g % NSTAGE;
-              const int nkb = (min(KC, op.Nl - n0) + 31) >> 5;
-              mbar_wait(pipe.empty + slot, ((g / NSTAGE) & 1u) ^ 1u);
-              float* sA = ring + slot * SLOT;
-              const int npan = (min(KC, op.Nl - n0) + 127) >> 7;               // 128-row weight panels in this chunk
-              if (lane == 0) mbar_expect_tx(pipe.full + slot, (unsigned)nkb * BOXF * 4u + (unsigned)npan * 128u * 32u * 4u);
-              __syncwarp();
-              if (lane < nkb) tma_load_2d(sA + lane * BOXF, op.mapA, n0 + 32 * lane, r0, pipe.full + slot);
-              else if (lane >= KBLK && lane - KBLK < npan)   // [128 n][32 input columns] each
-                tma_load_2d(sA + SLOT_A + (lane - KBLK) * 128 * 32, op.mapP, k0, n0 + 128 * (lane - KBLK), pipe.full + slot);
+        const int Kc = round4((op.Kin + CS - 1) / CS);     // 16, 32 or 64 input columns per CTA
+        const int nch = (Kc + 31) / 32;
+        const int k0 = rank * Kc;
+        for (int sub = 0; sub < nsub; ++sub) {
+          const int r0 = row0 + sub * ROWS;
+          for (int n0 = 0; n0 < op.Nl; n0 += KC, ++g) {
+            const unsigned slot = g % NSTAGE;
+            const int nn = min(KC, op.Nl - n0);
+            const int nkb = (nn + 31) >> 5;
+            const int npan = (nn + PROW - 1) / PROW;                          // weight panels (PROW reduction rows each)
+            mbar_wait(pipe.empty + slot, ((g / NSTAGE) & 1u) ^ 1u);
+            float* sA = ring + slot * SLOT;
+            if (lane == 0) mbar_expect_tx(pipe.full + slot, (unsigned)nkb * ROWS * 128u + (unsigned)(npan * nch) * PROW * 128u);
+            __syncwarp();
+            if (lane < nkb) tma_load_2d(sA + lane * ROWS * 32, op.mapA, n0 + 32 * lane, r0, pipe.full + slot);
+            else if (lane >= KBLK && lane - KBLK < npan * nch) {             // panel (pn, cc): [PROW n][32 input columns]
+              const int q = lane - KBLK, pn = q / nch, cc = q - pn * nch;
+              tma_load_2d(sA + SLOT_A + q * PROW * 32, op.mapP, k0 + 32 * cc, n0 + PROW * pn, pipe.full + slot);
             }
           }
         }
@@ -353,43 +333,38 @@ __device__ void dgrad_stage(const DgradOp* ops, int nops, int B, int row0, int n
     for (int o = 0; o < nops; ++o) {
       const DgradOp op = ops[o];
       const int Kc = round4((op.Kin + CS - 1) / CS);
-      const int nchunks = (Kc + 31) / 32;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const int k0 = rank * Kc + ch * 32;
-        const int width = min(32, Kc - ch * 32);
-        const int kcv = max(0, min(width, op.Kin - k0));
-        for (int sub = 0; sub < nsub; ++sub) {
-          const int r0 = row0 + sub * ROWS;
-          const int rv = min(ROWS, nrows - sub * ROWS);
-          switch (width >> 2) {
-            case 8: bwd_tile<TM, 8>(ring, pipe, g, op.Nl, red, sZ); break;
-            case 4: bwd_tile<TM, 4>(ring, pipe, g, op.Nl, red, sZ); break;
-            case 2: bwd_tile<TM, 2>(ring, pipe, g, op.Nl, red, sZ); break;
-            default: bwd_tile<TM, 1>(ring, pipe, g, op.Nl, red, sZ); break;
+      const int k0 = rank * Kc;
+      const int kcv = max(0, min(Kc, op.Kin - k0));
+      for (int sub = 0; sub < nsub; ++sub) {
+        const int r0 = row0 + sub * ROWS;
+        const int rv = min(ROWS, nrows - sub * ROWS);
+        switch (Kc >> 4) {
+          case 4: bwd_tile<TM, 4>(ring, pipe, g, op.Nl, red, sZ); break;
+          case 2: bwd_tile<TM, 2>(ring, pipe, g, op.Nl, red, sZ); break;
+          default: bwd_tile<TM, 1>(ring, pipe, g, op.Nl, red, sZ); break;
+        }
+        const int row = tid >> 3, sub8 = tid & 7;
+        float s1 = 0.f, s2 = 0.f;
+        if (row < rv) {
+          const size_t base = (size_t)(r0 + row) * op.ldo + k0;
+          for (int c = sub8; c < kcv; c += 8) {
+            const float dh = sZ[row * Kc + c];
+            const float h = ld_act(op.Hp + base + c);
+            const float zh = ld_act(op.ZHp + base + c);
+            const float du = dh * elu_grad_from_out(h);
+            const float t = du * ld_w(op.gp + k0 + c);
+            s1 += t;
+            s2 = fmaf(t, zh, s2);
+            op.DU[base + c] = du;
+            op.DZo[base + c] = t;
           }
-          const int row = tid >> 3, sub8 = tid & 7;
-          float s1 = 0.f, s2 = 0.f;
-          if (row < rv) {
-            const size_t base = (size_t)(r0 + row) * op.ldo + k0;
-            for (int c = sub8; c < kcv; c += 8) {
-              const float dh = sZ[row * width + c];
-              const float h = ld_act(op.Hp + base + c);
-              const float zh = ld_act(op.ZHp + base + c);
-              const float du = dh * elu_grad_from_out(h);
-              const float t = du * ld_w(op.gp + k0 + c);
-              s1 += t;
-              s2 = fmaf(t, zh, s2);
-              op.DU[base + c] = du;
-              op.DZo[base + c] = t;
-            }
-          }
-          s1 = group8_sum(s1);
-          s2 = group8_sum(s2);
-          if (row < rv && sub8 == 0) {
-            float* pp = part + (((size_t)o * B + (r0 + row)) * NPMAX + (rank * nchunks + ch)) * 2;
-            pp[0] = s1;
-            pp[1] = s2;
-          }
+        }
+        s1 = group8_sum(s1);
+        s2 = group8_sum(s2);
+        if (row < rv && sub8 == 0) {
+          float* pp = part + (((size_t)o * B + (r0 + row)) * NPMAX + rank) * 2;
+          pp[0] = s1;
+          pp[1] = s2;
         }
       }
     }
@@ -400,16 +375,14 @@ __device__ void dgrad_stage(const DgradOp* ops, int nops, int B, int row0, int n
       const int o = i / nrows, r = i - o * nrows;
       const DgradOp& op = ops[o];
       const int Kc = round4((op.Kin + CS - 1) / CS);
-      const int nchunks = (Kc + 31) / 32;
       const float* pp = part + (((size_t)o * B + (row0 + r)) * NPMAX) * 2;
-      const int np = CS * nchunks;
-      float2 pv[NPMAX];
+      float2 pv[CS];
 #pragma unroll
-      for (int p = 0; p < NPMAX; ++p) pv[p] = p < np ? __ldcg(reinterpret_cast<const float2*>(pp) + p) : make_float2(0.f, 0.f);
+      for (int p = 0; p < CS; ++p) pv[p] = __ldcg(reinterpret_cast<const float2*>(pp) + p);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int p = 0; p < NPMAX; ++p) {
-        if (p < np && part_count(op.Kin, Kc, nchunks, p) > 0) {
+      for (int p = 0; p < CS; ++p) {
+        if (part_count(op.Kin, Kc, p) > 0) {
           s1 += pv[p].x;
           s2 += pv[p].y;
         }
@@ -1051,12 +1024,12 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
       p.tstamp[(size_t)blockIdx.x * 8 + i] = t;
     }
   };
-  stamp(0);
   const TensorMaps& tm = p.tm;
   const int K1 = p.Sp32;          // layer-1 reduction length, zero-padded to whole 32-float k-blocks
 
   if (p.program == PROG_CRITIC) {
     const ActorP& a = p.actor;
+    stamp(0);
     // stage 0: fused minibatch gather (replay rows -> dense buffers the TMA unit can tile), one cluster barrier
     gather_rows(p.mb_s, p.rp.state, p.bidx, row0, nrows, p.S, p.Sp, p.Sp32, rank, CS);
     gather_rows(p.mb_s2, p.rp.new_state, p.bidx, row0, nrows, p.S, p.Sp, p.Sp32, rank, CS);
@@ -1067,6 +1040,7 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
     dense(3, tm.mb_s, tm.crit_w11[0], p.crit[0].b11, p.crit[0].g11, p.crit[0].be11, K1, H1, p.cw[0].h11, p.cw[0].zh11, p.cw[0].rs11);
     dense(4, tm.mb_s, tm.crit_w11[1], p.crit[1].b11, p.crit[1].g11, p.crit[1].be11, K1, H1, p.cw[1].h11, p.cw[1].zh11, p.cw[1].rs11);
     cluster_sync();
+    stamp(6);
     dense_stage<CS, TM>(dops, 5, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g);
     stamp(1);
     // stage 2: second layers
@@ -1103,16 +1077,26 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
   } else if (p.program == PROG_ACTOR) {
     const ActorP& a = p.actor;
     // mb_s was gathered by the critic phase of this step (same minibatch)
+    auto astamp = [&](int i) {
+      if (p.tstamp != nullptr && tid == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.tstamp[(size_t)(1536 + blockIdx.x) * 8 + i] = t;
+      }
+    };
+    astamp(0);
     dense(0, tm.mb_s, tm.actor_w1, a.b1, a.g1, a.be1, K1, H1, p.aw.h1, p.aw.zh1, p.aw.rs1);
     for (int k = 0; k < p.n_q; ++k)
       dense(1 + k, tm.mb_s, tm.crit_w11[k], p.crit[k].b11, p.crit[k].g11, p.crit[k].be11, K1, H1, p.cw[k].p_h11, nullptr, nullptr);
     __syncthreads();
     dense_stage<CS, TM>(dops, 1 + p.n_q, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g);
+    astamp(1);
     dense(0, tm.h1, tm.actor_w2, a.b2, a.g2, a.be2, H1, H2, p.aw.h2, p.aw.zh2, p.aw.rs2);
     for (int k = 0; k < p.n_q; ++k)
       dense(1 + k, tm.ph11[k], tm.crit_w12[k], p.crit[k].b12, p.crit[k].g12, p.crit[k].be12, H1, H2, p.cw[k].p_h12, nullptr, nullptr);
     __syncthreads();
     dense_stage<CS, TM>(dops, 1 + p.n_q, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g);
+    astamp(2);
     if (consumer)
       for (int gr = rank; gr < nrows; gr += CS * RT) {
         RowSet rs;
@@ -1120,10 +1104,13 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
         for (int t = 0; t < RT; ++t) rs.row[t] = (gr + t * CS < nrows) ? row0 + gr + t * CS : -1;
         tail_actor(p, ts, rs);
       }
+    astamp(3);
     if (tid == 0)
       gops[0] = DgradOp{tm.dz2, tm.actor_w2p, H2, H1, p.aw.h1, p.aw.zh1, p.aw.rs1, a.g1, p.aw.du1, p.aw.dz1, H1};
     cluster_sync();
+    astamp(4);
     dgrad_stage<CS, TM>(gops, 1, p.B, row0, nrows, p.part, smem, pipe, g);
+    astamp(5);
   } else {   // PROG_ACT: one observation through the actor (enet_sac.py:547-553)
     const ActorP& a = p.actor;
     dense(0, tm.obs, tm.actor_w1, a.b1, a.g1, a.be1, K1, H1, p.act_aux, nullptr, nullptr);

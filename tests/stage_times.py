@@ -20,6 +20,11 @@ for i, n in enumerate(names):
 for i, n in enumerate(names):
     a, b = (ts[:, i + 1], ts[:, i + 2]) if i > 0 else (None, None)
 print("per-CTA durations (us): mean / min / max")
+d = (ts[:, 6] - ts[:, 0]) / 1e3
+print(f"  {'gather + barrier':24s} {d.mean():8.1f} {d.min():8.1f} {d.max():8.1f}")
+d = (ts[:, 1] - ts[:, 6]) / 1e3
+print(f"  {'stage1 (5x fc1/fc11)':24s} {d.mean():8.1f} {d.min():8.1f} {d.max():8.1f}")
+print(f"  first CTA start -> last CTA end: {(ts[:, 5].max() - ts[:, 0].min()) / 1e3:.1f} us; CTA start spread {(ts[:, 0].max() - ts[:, 0].min()) / 1e3:.1f} us")
 for i, n in enumerate(names[1:], start=1):
     d = (ts[:, i + 1] - ts[:, i]) / 1e3
     print(f"  {n:24s} {d.mean():8.1f} {d.min():8.1f} {d.max():8.1f}")
@@ -35,3 +40,11 @@ print("thread-0 cycle accumulators over stages 1+2 (us @1.965 GHz, mean over CTA
 for i, n in enumerate(["wait full barrier", "mma (FFMA loop)", "park+combine (2 syncs)", "tile epilogue (stats, stores)", "LN combine", "LN combine+normalise"]):
     print(f"  {n:32s} {pr[:, i].mean():8.1f}")
 print("  (stage1 starts at the actor-phase stamp of slot 0, so it is derived from the kernel time minus the rest)")
+
+ta = dev.buffer("debug_ts").view(torch.int64).cpu().numpy()[1536:1536 + ncta].astype(np.float64)
+print("actor row-phase per-CTA durations (us): mean / min / max")
+for i, n in enumerate(["stage1 (fc1 + 2x fc11)", "stage2 (fc2 + 2x fc12)", "tail", "cluster barrier", "dgrad"]):
+    d = (ta[:, i + 1] - ta[:, i]) / 1e3
+    print(f"  {n:24s} {d.mean():8.1f} {d.min():8.1f} {d.max():8.1f}")
+print(f"  first CTA start -> last CTA end: {(ta[:, 5].max() - ta[:, 0].min()) / 1e3:.1f} us; CTA start spread {(ta[:, 0].max() - ta[:, 0].min()) / 1e3:.1f} us")
+print(f"  critic kernel end -> actor kernel start (wgrad in between): {(ta[:, 0].min() - ts[:, 5].max()) / 1e3:.1f} us")
