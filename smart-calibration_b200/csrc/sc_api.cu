@@ -316,8 +316,8 @@ static size_t carve(sc_agent* a, void* base) {
   a->act_out = cv.f(round4i(A));
   a->act_aux = cv.f(H1 + H2);
   a->store_stage = cv.f((size_t)a->T * 1);
-  a->tstamp = (unsigned long long*)cv.take(sizeof(unsigned long long) * 8 * 2048);
-  reg("debug_ts", a->tstamp, 2048, 8, 8, 8);
+  a->tstamp = (unsigned long long*)cv.take(sizeof(unsigned long long) * 8 * 3072);
+  reg("debug_ts", a->tstamp, 3072, 8, 8, 8);
   a->critic_ops = (WgradOp*)cv.take(sizeof(WgradOp) * 16);
   a->actor_ops = (WgradOp*)cv.take(sizeof(WgradOp) * 8);
   a->critic_vops = (VecOp*)cv.take(sizeof(VecOp) * 32);

@@ -21,6 +21,7 @@ constexpr int KBLK = KC / 32;            // 32-float (128-byte) k-blocks per slo
 constexpr int NSTAGE = SC_CFG_NSTAGE;    // ring slots: the producer runs up to NSTAGE-1 slots ahead of the consumers
 constexpr int RT = SC_CFG_RT;            // rows a CTA carries through the row-local tail at once
 constexpr int REDROWS = SC_CFG_REDROWS;  // max rows of a GEMM tile (8*TM)
+constexpr int GEMV_U = SC_CFG_MINBLOCKS == 2 ? 1 : 2;   // tail GEMV items in flight per warp (register budget)
 constexpr int WCOLS = 64;                // max output features (dgrad: input columns) of a CTA's slice
 constexpr int PROW = KC < 128 ? KC : 128;   // rows of a dgrad weight panel box
 constexpr int SLOT_A = KBLK * REDROWS * 32;  // [k-block][tile rows][32]
@@ -62,7 +63,16 @@ struct Pipe {
   long long* prof;   // optional cycle accumulators of thread 0: [0] full-wait, [1] mma, [2] park+combine, [3] tile epilogue, [4] LN combine, [5] LN normalise
   uint64_t* full;     // [NSTAGE] armed by the producer (expect_tx), completed by the bulk copies
   uint64_t* empty;    // [NSTAGE] one arrival per consumer warp
+  unsigned long long* tl;   // optional timeline of CTA 0 / thread 0 (globaltimer), tl[0] = next free index
 };
+__device__ __forceinline__ void tl_mark(const Pipe& pipe, int tag) {
+  if (pipe.tl != nullptr && threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long i = pipe.tl[0];
+    if (i < 500) { pipe.tl[1 + i] = (t << 8) | (unsigned long long)tag; pipe.tl[0] = i + 1; }
+  }
+}
 
 // One output tile = all reduction chunks of (op, row sub-tile) for the CTA's whole column slice (MT feature tiles of 16).
 // The 8 consumer warps are (feature tile mt = warp % MT, reduction part kp = warp / MT).  `g` counts chunks since the
@@ -71,14 +81,13 @@ template <int NT8, int MT>
 __device__ __forceinline__ void fwd_tile(const float* ring, const Pipe& pipe, unsigned& g, int K, float* red, float* sZ,
                                          const float* bias_slice, int ncv) {
   constexpr int KS = SC_WARPS / MT, NC = 16 * MT;
-  float acc[NT8][4];
+  Acc3 acc3[NT8];
 #pragma unroll
-  for (int i = 0; i < NT8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int i = 0; i < NT8; ++i) acc3_zero(acc3[i]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = warp % MT, kp = warp / MT;
   const bool prof = pipe.prof != nullptr && threadIdx.x == 0;
+  tl_mark(pipe, 1);
   for (int k0 = 0; k0 < K; k0 += KC, ++g) {
     const unsigned slot = g % NSTAGE;
     long long t0 = prof ? clock64() : 0;
@@ -86,27 +95,30 @@ __device__ __forceinline__ void fwd_tile(const float* ring, const Pipe& pipe, un
     long long t1 = prof ? clock64() : 0;
     const float* sA = ring + slot * SLOT;
     const int nk8 = min(KC, K - k0) >> 3;
-    if (!(pipe.dbg & 1)) mma3_nt<NT8>(sA, 8 * NT8, sA + SLOT_A, NC, mt, (nk8 * kp) / KS, (nk8 * (kp + 1)) / KS, acc);
+    if (!(pipe.dbg & 1)) mma3_nt<NT8>(sA, 8 * NT8, sA + SLOT_A, NC, mt, (nk8 * kp) / KS, (nk8 * (kp + 1)) / KS, acc3);
     __syncwarp();
     if (lane == 0) mbar_arrive(pipe.empty + slot);
     if (prof) { pipe.prof[0] += t1 - t0; pipe.prof[1] += clock64() - t1; }
   }
   long long t2 = prof ? clock64() : 0;
+  tl_mark(pipe, 2);
+  float acc[NT8][4];
+#pragma unroll
+  for (int i = 0; i < NT8; ++i) acc3_fold(acc3[i], acc[i]);
   park_partial<NT8>(red, kp, mt, NC, acc);
   consumer_sync();
   combine_partials<NT8>(red, KS, NC, sZ, bias_slice, ncv);
   consumer_sync();
   if (prof) pipe.prof[2] += clock64() - t2;
+  tl_mark(pipe, 3);
 }
 
 template <int NT8, int MT>
 __device__ __forceinline__ void bwd_tile(const float* ring, const Pipe& pipe, unsigned& g, int Nl, float* red, float* sZ) {
   constexpr int KS = SC_WARPS / MT, NC = 16 * MT, NCH = (NC + 31) / 32;
-  float acc[NT8][4];
+  Acc3 acc3[NT8];
 #pragma unroll
-  for (int i = 0; i < NT8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int i = 0; i < NT8; ++i) acc3_zero(acc3[i]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = warp % MT, kp = warp / MT;
   for (int n0 = 0; n0 < Nl; n0 += KC, ++g) {
@@ -114,10 +126,13 @@ __device__ __forceinline__ void bwd_tile(const float* ring, const Pipe& pipe, un
     mbar_wait(pipe.full + slot, (g / NSTAGE) & 1u);
     const float* sA = ring + slot * SLOT;
     const int nk8 = min(KC, Nl - n0) >> 3;
-    mma3_nn<NT8, PROW>(sA, 8 * NT8, sA + SLOT_A, NCH, mt, (nk8 * kp) / KS, (nk8 * (kp + 1)) / KS, acc);
+    mma3_nn<NT8, PROW>(sA, 8 * NT8, sA + SLOT_A, NCH, mt, (nk8 * kp) / KS, (nk8 * (kp + 1)) / KS, acc3);
     __syncwarp();
     if (lane == 0) mbar_arrive(pipe.empty + slot);
   }
+  float acc[NT8][4];
+#pragma unroll
+  for (int i = 0; i < NT8; ++i) acc3_fold(acc3[i], acc[i]);
   park_partial<NT8>(red, kp, mt, NC, acc);
   consumer_sync();
   combine_partials<NT8>(red, KS, NC, sZ, nullptr, 0);
@@ -224,11 +239,14 @@ __device__ void dense_stage(const DenseOp* ops, int nops, int B, int row0, int n
           }
         }
         if (pipe.prof && tid == 0) pipe.prof[3] += clock64() - te;
+        tl_mark(pipe, 4);
       }
     }
   }
   stamp(0);
+  tl_mark(pipe, 5);
   cluster_sync();
+  tl_mark(pipe, 6);
   stamp(1);
   const long long tf0 = (pipe.prof && tid == 0) ? clock64() : 0;
   if (warp < SC_WARPS) {
@@ -283,7 +301,9 @@ __device__ void dense_stage(const DenseOp* ops, int nops, int B, int row0, int n
   }
   if (pipe.prof && tid == 0) pipe.prof[5] += clock64() - tf0;
   stamp(2);
+  tl_mark(pipe, 7);
   cluster_sync();
+  tl_mark(pipe, 8);
   stamp(3);
 }
 
@@ -518,44 +538,45 @@ __device__ void ln_bwd_multi(int nn, float* dh, const float* h, const float* zh,
     for (int j = lane; j < N; j += 32) dz[o + j] = r * (dh[o + j] * ld_w(g + j) - c1 - zh[o + j] * c2);
   }
 }
-// zout[net][t][n] = bias_net[n] + sum_k W_net[n][k] * xin[net][t][k]; work items (net, group of 4 outputs) strided over warps
-__device__ void gemv_multi(int nn, const float* const* W, int ldw, const float* const* bias, int N, int K, const float* xin,
-                           float* zout) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int K4 = K >> 2, groups = (N + 3) >> 2;
-  for (int item = warp; item < nn * groups; item += SC_WARPS) {
-    const int net = item / groups, n0 = (item - net * groups) * 4;
-    const float* Wn = W[net];
-    const float* x0 = xin + net * RT * K;
-    float acc[4][RT];
+// zout[net][t][n] = bias_net[n] + sum_k W_net[n][k] * xin[net][t][k].  A warp works on 4 output features at a time
+// (lane / 8) with the reduction split over 8 lanes (128 contiguous bytes of a weight row per load instruction), and on
+// U such items at once, so every lane has U*K/32 independent 16-byte weight loads in flight: the tail is bound by the
+// latency of these L2 reads, not by arithmetic.
+template <int K, int U>
+__device__ void gemv_multi(int nn, const float* const* W, int ldw, const float* const* bias, int N, const float* xin, float* zout) {
+  constexpr int KI = K / 32;                       // float4 loads per lane per output feature
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 7, q = lane >> 3;
+  const int groups = (N + 3) >> 2, items = nn * groups;
+  for (int base = warp; base < items; base += SC_WARPS * U) {
+    float4 w[U][KI];
+    int net[U], n[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < U; ++u) {
+      const int item = base + u * SC_WARPS;
+      const bool ok = item < items;
+      net[u] = ok ? item / groups : 0;
+      n[u] = ok ? (item - net[u] * groups) * 4 + q : N;
+      const float* wr = W[net[u]] + (size_t)min(n[u], N - 1) * ldw + 4 * sub;
 #pragma unroll
-      for (int t = 0; t < RT; ++t) acc[u][t] = 0.f;
-    for (int k4 = lane; k4 < K4; k4 += 32) {
-      float4 w[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) w[u] = n0 + u < N ? ld_w4(Wn + (size_t)(n0 + u) * ldw + 4 * k4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int t = 0; t < RT; ++t) {
-        const float4 x = *reinterpret_cast<const float4*>(x0 + t * K + 4 * k4);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u][t] = dot4(w[u], x, acc[u][t]);
-      }
+      for (int i = 0; i < KI; ++i) w[u][i] = n[u] < N ? ld_w4(wr + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < U; ++u) {
+      const float* x0 = xin + net[u] * RT * K + 4 * sub;
+      float acc[RT];
 #pragma unroll
-      for (int t = 0; t < RT; ++t) acc[u][t] = warp_sum(acc[u][t]);
-    if (lane == 0) {
-      const float* bn = bias[net];
+      for (int t = 0; t < RT; ++t) {
+        acc[t] = 0.f;
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (n0 + u < N) {
-          const float b = bn ? ld_w(bn + n0 + u) : 0.f;
+        for (int i = 0; i < KI; ++i) acc[t] = dot4(w[u][i], *reinterpret_cast<const float4*>(x0 + t * K + 32 * i), acc[t]);
+        acc[t] = group8_sum(acc[t]);
+      }
+      if (sub == 0 && n[u] < N) {
+        const float* bn = bias[net[u]];
+        const float b = bn ? ld_w(bn + n[u]) : 0.f;
 #pragma unroll
-          for (int t = 0; t < RT; ++t) zout[(net * RT + t) * N + n0 + u] = acc[u][t] + b;
-        }
+        for (int t = 0; t < RT; ++t) zout[(net[u] * RT + t) * N + n[u]] = acc[t] + b;
+      }
     }
   }
 }
@@ -573,6 +594,7 @@ __device__ void gemvT_multi(int nn, const float* const* W, int ldw, int N, int K
     float4 acc[RT];
 #pragma unroll
     for (int t = 0; t < RT; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
     for (int n = part; n < N; n += parts) {
       const float4 w = ld_w4(Wn + (size_t)n * ldw + 4 * k4);
 #pragma unroll
@@ -634,7 +656,7 @@ __device__ void action_branches(int nn, const CriticP* const* c, const float* co
   }
   ln_elu_multi(nn, t.v21, t.zh21, HA1, g21, b21, t.rsn, 2);
   consumer_sync();
-  gemv_multi(nn, w22, HA1, bb22, HA2, HA1, t.v21, t.v22);
+  gemv_multi<HA1, GEMV_U * 2>(nn, w22, HA1, bb22, HA2, t.v21, t.v22);
   consumer_sync();
   ln_elu_multi(nn, t.v22, t.zh22, HA2, g22, b22, t.rsn + 1, 2);
   consumer_sync();
@@ -657,7 +679,7 @@ __device__ void critic_q_multi(int nn, const CriticP* const* c, const TailSm& t)
 __device__ void actor_tail_forward(const RowPhaseParams& p, const TailSm& t) {
   const ActorP& a = p.actor;
   const float *w3[1] = {a.w3}, *b3[1] = {a.b3}, *g3[1] = {a.g3}, *be3[1] = {a.be3};
-  gemv_multi(1, w3, H2, b3, H3, H2, t.xh2, t.x3);
+  gemv_multi<H2, GEMV_U>(1, w3, H2, b3, H3, t.xh2, t.x3);
   consumer_sync();
   ln_elu_multi(1, t.x3, t.zh3, H3, g3, be3, t.rsx + 2, 8);
   consumer_sync();
@@ -725,8 +747,10 @@ __device__ void policy_head(const RowPhaseParams& p, const TailSm& t, const RowS
 // ======================================================================================================
 // PROG_CRITIC tail: policy on s', both target critics, TD target, both online critics forward + backward
 // ======================================================================================================
-__device__ void tail_critic(const RowPhaseParams& p, const TailSm& t, const RowSet& rs) {
+__device__ void tail_critic(const RowPhaseParams& p, const TailSm& t, const RowSet& rs, long long* prof = nullptr) {
   const int tid = threadIdx.x;
+  long long tprev = (prof && tid == 0) ? clock64() : 0;
+  auto mark = [&](int i) { if (prof && tid == 0) { const long long c = clock64(); prof[i] += c - tprev; tprev = c; } };
   // ---- stage every global row this pass needs (one round of L2 latency) ----
   load_rows_to(t.xh2, p.aw.t_h2, H2, rs);
   for (int k = 0; k < 2; ++k) {
@@ -743,15 +767,20 @@ __device__ void tail_critic(const RowPhaseParams& p, const TailSm& t, const RowS
     t.rsx[r * 8 + 4 + k] = rs.row[r] >= 0 ? ld_act(p.cw[k].rs12 + rs.row[r]) : 0.f;
   }
   consumer_sync();
+  mark(8);
   // ---- policy on s' (SAC: online actor, sampled; TD3: target actor + clipped scalar noise) ----
   actor_tail_forward(p, t);
+  mark(9);
   policy_head(p, t, rs, true, [&](int row, int j) { return ld_act(p.eps + (size_t)row * p.A + j); });
+  mark(10);
   // ---- action branches of all four critics at once: targets on a', online critics on the replay action ----
   const CriticP* nets[NETS] = {&p.targ[0], &p.targ[1], &p.crit[0], &p.crit[1]};
   const float* an_sel[NETS] = {t.an, t.an, t.an + RT * AMAX, t.an + RT * AMAX};
   action_branches(NETS, nets, an_sel, p.A, p.Ap, t);
+  mark(11);
   critic_q_multi(NETS, nets, t);
   consumer_sync();
+  mark(12);
   const float wsum = p.is_wsum ? ld_act(p.is_wsum) : (float)p.B;
   const float coef = 2.f * wsum / ((float)p.B * (float)p.B);      // d/dq of mean(w)*mean((q-y)^2)
   if (tid < RT) {
@@ -796,6 +825,7 @@ __device__ void tail_critic(const RowPhaseParams& p, const TailSm& t, const RowS
     store_rows_from(p.cw[k].zh22, t.zh22 + (2 + k) * RT * HA2, HA2, rs);
   }
   consumer_sync();
+  mark(13);
   // ---- backward of both online critics: d cat = dq * w3 ----
   for (int e = tid; e < 2 * RT * HCAT; e += SC_THREADS) {
     const int rix = e / HCAT, j = e - rix * HCAT, k = rix / RT, r = rix - k * RT;
@@ -812,6 +842,7 @@ __device__ void tail_critic(const RowPhaseParams& p, const TailSm& t, const RowS
     ln_bwd_multi(2, t.ge, t.v22 + 2 * RT * HA2, t.zh22 + 2 * RT * HA2, HA2, g22, t.rsn + 2 * RT * 2 + 1, 2, t.gf);
   }
   consumer_sync();
+  mark(14);
   for (int k = 0; k < 2; ++k) {
     store_rows_from(p.cw[k].du12, t.ga + k * RT * H2, H2, rs);
     store_rows_from(p.cw[k].dz12, t.gb + k * RT * H2, H2, rs);
@@ -830,6 +861,7 @@ __device__ void tail_critic(const RowPhaseParams& p, const TailSm& t, const RowS
     store_rows_from(p.cw[k].dz21, t.gd + k * RT * HA1, HA1, rs);
   }
   consumer_sync();
+  mark(15);
 }
 
 // ======================================================================================================
@@ -992,9 +1024,11 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
   __shared__ __align__(8) uint64_t mbars[2 * NSTAGE];
   const int tid = threadIdx.x;
   const bool consumer = tid < SC_THREADS;
-  __shared__ long long prof_acc[8];
-  if (tid < 8) prof_acc[tid] = 0;
-  const Pipe pipe{p.dbg, p.tstamp ? prof_acc : nullptr, mbars, mbars + NSTAGE};
+  __shared__ long long prof_acc[16];
+  if (tid < 16) prof_acc[tid] = 0;
+  const Pipe pipe{p.dbg, p.tstamp ? prof_acc : nullptr, mbars, mbars + NSTAGE,
+                  (p.tstamp && p.program == PROG_CRITIC) ? p.tstamp + 2048 * 8 : nullptr};
+  if (pipe.tl != nullptr && tid == 0 && blockIdx.x == 0) pipe.tl[0] = 0;
   unsigned g = 0;                 // chunks streamed so far (identical sequence in producer and consumers)
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) {
@@ -1059,7 +1093,7 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
         RowSet rs;
 #pragma unroll
         for (int t = 0; t < RT; ++t) rs.row[t] = (gr + t * CS < nrows) ? row0 + gr + t * CS : -1;
-        tail_critic(p, ts, rs);
+        tail_critic(p, ts, rs, p.tstamp ? prof_acc : nullptr);
       }
     stamp(3);
     if (tid == 0) {
@@ -1073,7 +1107,7 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
     dgrad_stage<CS, TM>(gops, 2, p.B, row0, nrows, p.part, smem, pipe, g);
     stamp(5);
     if (p.tstamp != nullptr && tid == 0)
-      for (int i = 0; i < 6; ++i) p.tstamp[(size_t)(1024 + blockIdx.x) * 8 + i] = (unsigned long long)prof_acc[i];
+      for (int i = 0; i < 16; ++i) p.tstamp[(size_t)(1024 + (i >> 3) * 1536 + blockIdx.x) * 8 + (i & 7)] = (unsigned long long)prof_acc[i];
   } else if (p.program == PROG_ACTOR) {
     const ActorP& a = p.actor;
     // mb_s was gathered by the critic phase of this step (same minibatch)

@@ -3,7 +3,7 @@
 // All three contractions of the MLP step are served from row-major global layouts (PyTorch-native W[N][K]):
 //   forward  Z[m][n]  = sum_k A[m][k]  * W[n][k]     "nt": both operands reduction-contiguous in smem
 //   dgrad    dA[m][k] = sum_n dZ[m][n] * W[n][k]     "nn": B operand is a [n][k-slice] panel
-//   wgrad    dW[n][k] = sum_b dZ[b][n] * A[b][k]     "tn": both operands are [b][slice] panels
+//   wgrad    dW[n][k] = sum_b dZ[b][n] * A[b][k]     "tn": both operands are [b][slice] panels (sc_wgrad.cu)
 // forward and dgrad run on the tensor cores (mma.sync TF32 with error compensation, below); the wgrad kernel keeps a
 // register-tiled FP32 FFMA loop.  The 8 warps of a CTA split the reduction axis and their partial tiles are summed in
 // fixed order through shared memory (deterministic).
@@ -38,11 +38,22 @@ __device__ __forceinline__ void mma_m16n8k8(float (&d)[4], const uint32_t (&a)[4
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ab)[4], const uint32_t (&as)[4], const uint32_t (&bb)[2],
+// three independent accumulator chains (big*big, small*big, big*small): consecutive k-steps do not wait for each other's
+// MMA latency three times over, and the small correction terms are summed among themselves before they meet the big sum
+struct Acc3 { float b[4], s[4], t[4]; };
+__device__ __forceinline__ void acc3_zero(Acc3& a) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a.b[j] = a.s[j] = a.t[j] = 0.f;
+}
+__device__ __forceinline__ void acc3_fold(const Acc3& a, float (&d)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) d[j] = a.b[j] + (a.s[j] + a.t[j]);
+}
+__device__ __forceinline__ void mma3(Acc3& d, const uint32_t (&ab)[4], const uint32_t (&as)[4], const uint32_t (&bb)[2],
                                      const uint32_t (&bs)[2]) {
-  mma_m16n8k8(d, as, bb);
-  mma_m16n8k8(d, ab, bs);
-  mma_m16n8k8(d, ab, bb);
+  mma_m16n8k8(d.s, as, bb);
+  mma_m16n8k8(d.t, ab, bs);
+  mma_m16n8k8(d.b, ab, bb);
 }
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
@@ -59,7 +70,7 @@ __device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], uint32_t addr) {
 // acc[i][0..3] = D(feature g, row 8i+2t), D(g, 8i+2t+1), D(g+8, 8i+2t), D(g+8, 8i+2t+1) with g = lane/4, t = lane%4.
 template <int NT8>
 __device__ __forceinline__ void mma3_nt(const float* __restrict__ sX, int xrows, const float* __restrict__ sW, int wrows, int mt,
-                                        int ks0, int ks1, float (&acc)[NT8][4]) {
+                                        int ks0, int ks1, Acc3 (&acc)[NT8]) {
   const int lane = threadIdx.x & 31, j = lane >> 3, r = lane & 7;
   const uint32_t wrow = smem_u32(sW) + (uint32_t)((mt * 16 + r + 8 * (j & 1)) << 7);
   const uint32_t xrow = smem_u32(sX) + (uint32_t)(r << 7);
@@ -89,7 +100,7 @@ __device__ __forceinline__ void mma3_nt(const float* __restrict__ sX, int xrows,
 // reads (4 different rows -> 4 different chunk pairs) and the dZ reads conflict-free.
 template <int NT8, int prow>
 __device__ __forceinline__ void mma3_nn(const float* __restrict__ sX, int xrows, const float* __restrict__ sW, int nch,
-                                        int mt, int ks0, int ks1, float (&acc)[NT8][4]) {
+                                        int mt, int ks0, int ks1, Acc3 (&acc)[NT8]) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int klo = (t == 0) ? 0 : (t == 1) ? 2 : (t == 2) ? 5 : 7;
   const int khi = (t == 0) ? 1 : (t == 1) ? 3 : (t == 2) ? 4 : 6;
@@ -152,25 +163,6 @@ __device__ __forceinline__ void combine_partials(const float* red, int KS, int N
     for (int w = 0; w < KS; ++w) s += red[((size_t)w * (8 * NT8) + r) * P + c];
     if (bias_slice != nullptr && c < ncv) s += ld_w(bias_slice + c);
     sZ[r * NC + c] = s;
-  }
-}
-
-// ---- wgrad: out rows (n) rg*4+i, out cols (k) cg*8+j; one reduction index b per step -------------------
-// sD: [b][32] dZ panel, sX: [b][32] input panel (pitch 32).
-__device__ __forceinline__ void mma_tn(const float* __restrict__ sD, const float* __restrict__ sX, int b0, int b1,
-                                       float (&acc)[4][8]) {
-  const int lane = threadIdx.x & 31, rg = lane >> 2, cg = lane & 3;
-#pragma unroll 4
-  for (int b = b0; b < b1; ++b) {
-    const float4 d = *reinterpret_cast<const float4*>(sD + b * 32 + rg * 4);
-    const float4 x0 = *reinterpret_cast<const float4*>(sX + b * 32 + cg * 8);
-    const float4 x1 = *reinterpret_cast<const float4*>(sX + b * 32 + cg * 8 + 4);
-    const float dv[4] = {d.x, d.y, d.z, d.w};
-    const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(dv[i], xv[j], acc[i][j]);
   }
 }
 

@@ -13,6 +13,26 @@
 
 namespace sc {
 
+// ---- wgrad: out rows (n) rg*4+i, out cols (k) cg*8+j; one reduction index b per step -------------------
+// sD: [b][32] dZ panel, sX: [b][32] input panel (pitch 32).
+__device__ __forceinline__ void mma_tn(const float* __restrict__ sD, const float* __restrict__ sX, int b0, int b1,
+                                       float (&acc)[4][8]) {
+  const int lane = threadIdx.x & 31, rg = lane >> 2, cg = lane & 3;
+#pragma unroll 4
+  for (int b = b0; b < b1; ++b) {
+    const float4 d = *reinterpret_cast<const float4*>(sD + b * 32 + rg * 4);
+    const float4 x0 = *reinterpret_cast<const float4*>(sX + b * 32 + cg * 8);
+    const float4 x1 = *reinterpret_cast<const float4*>(sX + b * 32 + cg * 8 + 4);
+    const float dv[4] = {d.x, d.y, d.z, d.w};
+    const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(dv[i], xv[j], acc[i][j]);
+  }
+}
+
+
 constexpr int WG_BC = 256;                         // batch rows staged per pass
 constexpr int WG_SM_D = WG_BC * 32;
 constexpr int WG_SM_X = WG_BC * 32;

@@ -48,3 +48,21 @@ for i, n in enumerate(["stage1 (fc1 + 2x fc11)", "stage2 (fc2 + 2x fc12)", "tail
     print(f"  {n:24s} {d.mean():8.1f} {d.min():8.1f} {d.max():8.1f}")
 print(f"  first CTA start -> last CTA end: {(ta[:, 5].max() - ta[:, 0].min()) / 1e3:.1f} us; CTA start spread {(ta[:, 0].max() - ta[:, 0].min()) / 1e3:.1f} us")
 print(f"  critic kernel end -> actor kernel start (wgrad in between): {(ta[:, 0].min() - ts[:, 5].max()) / 1e3:.1f} us")
+
+pt = dev.buffer("debug_ts").view(torch.int64).cpu().numpy()[2560:2560 + ncta].astype(np.float64) / 1.965e3
+print("critic tail phases, thread 0 (us, mean over CTAs):")
+for i, n in enumerate(["stage rows from L2", "actor fc3 + LN + heads", "policy head", "action branches x4 (fc21, LN, fc22, LN)", "q heads",
+                       "TD target, errors, cache stores", "d cat, LN bwd (12, 22)", "fc22^T, LN bwd 21, stores"]):
+    print(f"  {n:40s} {pt[:, i].mean():8.1f}")
+
+tl = dev.buffer("debug_ts").view(torch.int64).cpu().numpy()[2048:2048 + 64].reshape(-1)
+n = int(tl[0]); ev = tl[1:1 + n]
+names = {1: "tile start", 2: "k-loop done", 3: "combined", 4: "epilogue done", 5: "stage tiles done", 6: "barrier 1 passed", 7: "LN done", 8: "barrier 2 passed"}
+print("timeline of CTA 0 / thread 0 through the dense stages (us since first event):")
+t0 = ev[0] >> 8
+prev = t0
+for e in ev:
+    t, tag = e >> 8, int(e & 255)
+    print(f"  {(t - t0) / 1e3:8.2f}  (+{(t - prev) / 1e3:5.2f})  {names.get(tag, tag)}")
+    prev = t
+
