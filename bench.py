@@ -233,10 +233,11 @@ def run_ours(args):
             "unit": "GB/s", "frac": CRITIC_PHASE_BYTES / crit_s / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": CRITIC_PHASE_BYTES,
             "fp32_ffma": {"achieved_tflops": CRITIC_PHASE_FLOP / crit_s / 1e12, "peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12,
-                          "note": "the kernel is FP32-FFMA-bound, not HBM-bound (DESIGN.md)"},
+                          "note": "not HBM-bound: the GEMM stages are bound by the legacy mma.sync TF32 pipe (3 MMAs per product for fp32 parity), the rest by latency (DESIGN.md)"},
             "step": {"algorithmic_bytes": STEP_BYTES, "achieved": STEP_BYTES / (ms_cold / args.steps * 1e-3) / 1e9,
                      "frac": STEP_BYTES / (ms_cold / args.steps * 1e-3) / 1e9 / peak}}
     cpu = cpu_baseline(sample_seconds=12.0)
+    eager = gpu_eager_baseline() if world == 1 else None
     out = {"metric": "SAC learn() steps/sec (batch=256)", "value": world * args.steps / (ms_cold * 1e-3), "unit": "learn steps/s",
            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_cold / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -246,6 +247,8 @@ def run_ours(args):
            "e2e": e2e, "gpu_launches": int(launches), "kernels": kern, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
     if al is not None:
         out["actor_learner"] = al
+    if eager is not None:
+        out["gpu_eager_baseline"] = eager
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -290,6 +293,31 @@ def cpu_baseline(sample_seconds=12.0, steps=None, warmup=5):
             "sample": f"{n} learn() steps of the same workload in {el:.1f} s (oracle/sac_ref.py, torch {torch.__version__} CPU, "
                       f"{best} threads = best of {{{', '.join(f'{k}: {v:.1f}/s' for k, v in sorted(tried.items()))}}}, "
                       f"{os.cpu_count()} logical cores)", "ms_per_step": el / n * 1e3}
+
+
+def gpu_eager_baseline(steps=200, warmup=20):
+    """The same learn() op sequence issued as torch-eager CUDA kernels on this GPU (what the reference does with
+    use_cuda=True, enet_sac.py:12-16): the oracle port with its parameters on cuda:0.  A reported bar, like cpu_baseline;
+    no part of the product path."""
+    from oracle.sac_ref import SacRef
+    from smartcal_b200.synth import make_transitions
+    torch.manual_seed(0)
+    np.random.seed(0)
+    orc = SacRef(**HP, prioritized=True, device="cuda")
+    tr = make_transitions(100, C, S, A, "normal", 0.0)
+    for i in range(C):
+        orc.store_flat(tr["state"][i], tr["action"][i], float(tr["reward"][i]), tr["new_state"][i], False, tr["hint"][i])
+    for _ in range(warmup):
+        orc.learn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.learn()
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t0
+    return {"value": steps / el, "unit": "learn steps/s", "ms_per_step": el / steps * 1e3,
+            "what": f"oracle/sac_ref.py with device='cuda' (torch {torch.__version__} eager kernels, host PER + host sampling like the "
+                    f"reference), {steps} steps, wall clock"}
 
 
 def run_reference(args):

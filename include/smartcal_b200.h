@@ -44,6 +44,10 @@ enum {
 /* which copy of a network's tensors */
 enum { SC_SLOT_PARAM = 0, SC_SLOT_ADAM_M = 1 /* exp_avg */, SC_SLOT_ADAM_V = 2 /* exp_avg_sq */ };
 
+/* DDPG (enet_ddpg.py:192-303) runs on the TD3 program: kind = SC_KIND_TD3, update_actor_interval = 1, target noise 0,
+ * both critic slots loaded with the same network, and this flag for its sum-of-squares critic loss (enet_ddpg.py:281) */
+enum { SC_FLAG_CRITIC_LOSS_SUM = 1 };
+
 /* constructor kwargs of the reference Agent (enet_sac.py:479-480, enet_td3.py:125-126) */
 typedef struct sc_config {
   int32_t abi_version;   /* = SC_ABI_VERSION */
@@ -55,7 +59,7 @@ typedef struct sc_config {
   int32_t prioritized;   /* prioritized (SAC: derived TD3-style wiring) */
   int32_t use_hint;      /* use_hint                                    */
   int32_t update_actor_interval; /* TD3 only (enet_td3.py:137)          */
-  int32_t reserved0;
+  int32_t flags;         /* SC_FLAG_* (0 for SAC / TD3)                  */
   /* Python floats of the reference constructor stay doubles so that every derived scalar
    * (lr/(1-beta1^t), 1-tau, ...) rounds to float32 exactly where torch rounds it */
   double gamma, tau, lr_actor, lr_critic;

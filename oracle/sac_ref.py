@@ -29,8 +29,8 @@ from . import nets_ref as N
 from .per_ref import PerRef
 
 
-def _leafs(params):
-    return OrderedDict((k, v.clone().requires_grad_(True)) for k, v in params.items())
+def _leafs(params, device="cpu"):
+    return OrderedDict((k, v.clone().to(device).requires_grad_(True)) for k, v in params.items())
 
 
 def soft_update_like_reference(online, target, tau):
@@ -78,25 +78,28 @@ class HostReplay:
 
 class SacRef:
     def __init__(self, gamma, lr_a, lr_c, input_dims, batch_size, n_actions, max_mem_size=100,
-                 tau=0.001, reward_scale=2, alpha=0.1, use_hint=False, prioritized=False, per_clip=100.0):
+                 tau=0.001, reward_scale=2, alpha=0.1, use_hint=False, prioritized=False, per_clip=100.0, device="cpu"):
+        # device="cuda" runs the same op sequence as torch-eager CUDA kernels (the reference's own use_cuda=True path,
+        # enet_sac.py:12-16): bench.py's `gpu_eager_baseline`, never a parity oracle
         S, A = int(input_dims[0]), int(n_actions)
+        self.dev = torch.device(device)
         self.S, self.A, self.B = S, A, int(batch_size)
         self.gamma, self.tau, self.scale = gamma, tau, reward_scale
         self.max_action = 1
         # construction order of the reference Agent: actor, critic_1, critic_2, targets 1, 2 (:493-499)
-        self.actor = _leafs(N.init_actor(S, A, "sac"))
-        self.critic_1 = _leafs(N.init_critic(S, A))
-        self.critic_2 = _leafs(N.init_critic(S, A))
-        self.target_critic_1 = _leafs(N.init_critic(S, A))
-        self.target_critic_2 = _leafs(N.init_critic(S, A))
+        self.actor = _leafs(N.init_actor(S, A, "sac"), self.dev)
+        self.critic_1 = _leafs(N.init_critic(S, A), self.dev)
+        self.critic_2 = _leafs(N.init_critic(S, A), self.dev)
+        self.target_critic_1 = _leafs(N.init_critic(S, A), self.dev)
+        self.target_critic_2 = _leafs(N.init_critic(S, A), self.dev)
         self.opt_a = torch.optim.Adam(list(self.actor.values()), lr=lr_a)
         self.opt_1 = torch.optim.Adam(list(self.critic_1.values()), lr=lr_c)
         self.opt_2 = torch.optim.Adam(list(self.critic_2.values()), lr=lr_c)
-        self.alpha = torch.tensor(alpha)
-        self.zero = torch.tensor(0.)
+        self.alpha = torch.tensor(alpha, device=self.dev)
+        self.zero = torch.tensor(0., device=self.dev)
         self.use_hint = use_hint
         self.hint_threshold, self.admm_rho = 0.1, 0.01
-        self.rho = torch.tensor(0.0)
+        self.rho = torch.tensor(0.0, device=self.dev)
         self.replay = HostReplay(max_mem_size, S, A)
         self.per = PerRef(max_mem_size, per_clip) if prioritized else None
         soft_update_like_reference(self.critic_1, self.target_critic_1, 1.0)
@@ -117,8 +120,8 @@ class SacRef:
     def choose_action(self, state_vec, eps):
         """ref choose_action :547-553 on an already concatenated (S,) state, eps (A,)."""
         with torch.no_grad():
-            a, _ = N.sac_sample(self.actor, torch.as_tensor(state_vec), torch.as_tensor(eps), self.max_action)
-        return a.numpy()[0]
+            a, _ = N.sac_sample(self.actor, torch.as_tensor(state_vec).to(self.dev), torch.as_tensor(eps).to(self.dev), self.max_action)
+        return a.cpu().numpy()[0]
 
     # ---- update -------------------------------------------------------------------------
     def _gfun(self, actions, hint):
@@ -127,10 +130,11 @@ class SacRef:
     def learn_on_batch(self, batch, eps_next, eps_cur, eps_dual=None, is_weights=None, tree_idx=None):
         """One reference learn() (:555-628) on an explicit minibatch and explicit noise."""
         s, a, r, s2, done, hint = batch
-        s, s2, a, hint = (torch.as_tensor(x) for x in (s, s2, a, hint))
-        r = self.scale * torch.as_tensor(r).unsqueeze(1)
-        done = torch.as_tensor(done).unsqueeze(1)
-        eps_next, eps_cur = torch.as_tensor(eps_next), torch.as_tensor(eps_cur)
+        T = lambda x: torch.as_tensor(x).to(self.dev)
+        s, s2, a, hint = (T(x) for x in (s, s2, a, hint))
+        r = self.scale * T(r).unsqueeze(1)
+        done = T(done).unsqueeze(1)
+        eps_next, eps_cur = T(eps_next), T(eps_cur)
         out = {}
 
         with torch.no_grad():
@@ -142,8 +146,8 @@ class SacRef:
         q1 = N.critic_forward(self.critic_1, s, a)
         q2 = N.critic_forward(self.critic_2, s, a)
         if is_weights is not None:                       # derived SAC+PER (TD3 wiring)
-            w = torch.as_tensor(is_weights)
-            err = 0.5 * (torch.abs(q1 - y).detach().numpy() + torch.abs(q2 - y).detach().numpy())
+            w = T(is_weights)
+            err = 0.5 * (torch.abs(q1 - y).detach().cpu().numpy() + torch.abs(q2 - y).detach().cpu().numpy())
             out["per_errors"] = err
             if self.per is not None:
                 out["per_ps"] = self.per.update(tree_idx, err)
@@ -177,7 +181,7 @@ class SacRef:
 
         if self.learn_counter % 10 == 0 and self.use_hint:
             with torch.no_grad():
-                act, _ = N.sac_sample(self.actor, s, torch.as_tensor(eps_dual), self.max_action)
+                act, _ = N.sac_sample(self.actor, s, T(eps_dual), self.max_action)
                 self.rho = self.rho + self.admm_rho * self._gfun(act, hint)
         self.learn_counter += 1
         soft_update_like_reference(self.critic_1, self.target_critic_1, self.tau)

@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsmartcal_b200.so")
 
 SC_ABI_VERSION = 1
+SC_FLAG_CRITIC_LOSS_SUM = 1   # include/smartcal_b200.h
 SC_KIND_SAC, SC_KIND_TD3 = 0, 1
 NET_ACTOR, NET_CRITIC_1, NET_CRITIC_2, NET_TARGET_CRITIC_1, NET_TARGET_CRITIC_2, NET_TARGET_ACTOR = range(6)
 SLOT_PARAM, SLOT_ADAM_M, SLOT_ADAM_V = 0, 1, 2
@@ -20,7 +21,7 @@ class ScConfig(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("kind", C.c_int32), ("state_dim", C.c_int32), ("n_actions", C.c_int32),
         ("batch_size", C.c_int32), ("mem_size", C.c_int32), ("prioritized", C.c_int32), ("use_hint", C.c_int32),
-        ("update_actor_interval", C.c_int32), ("reserved0", C.c_int32),
+        ("update_actor_interval", C.c_int32), ("flags", C.c_int32),
         ("gamma", C.c_double), ("tau", C.c_double), ("lr_actor", C.c_double), ("lr_critic", C.c_double),
         ("reward_scale", C.c_double), ("alpha", C.c_double),
         ("max_action", C.c_float), ("per_clip", C.c_float), ("hint_threshold", C.c_float), ("admm_rho", C.c_float),

@@ -14,7 +14,7 @@ _TORCH_DT = {4: torch.float32, 8: torch.float64, 1: torch.uint8}
 class DeviceAgent:
     def __init__(self, kind, state_dim, n_actions, batch_size, mem_size, gamma, tau, lr_actor, lr_critic,
                  reward_scale=1.0, alpha=0.0, prioritized=False, use_hint=False, update_actor_interval=2,
-                 per_clip=100.0, hint_threshold=0.1, admm_rho=0.01, max_action=1.0, rng_seed=0, device=None):
+                 per_clip=100.0, hint_threshold=0.1, admm_rho=0.01, max_action=1.0, rng_seed=0, device=None, flags=0):
         self.lib = L.load()
         if not torch.cuda.is_available():
             raise L.SmartcalError("no CUDA device visible: smart-calibration_b200 has no CPU fallback")
@@ -24,7 +24,7 @@ class DeviceAgent:
         self.prioritized = bool(prioritized)
         cfg = L.ScConfig(abi_version=L.SC_ABI_VERSION, kind=kind, state_dim=self.S, n_actions=self.A,
                          batch_size=self.B, mem_size=self.C, prioritized=int(bool(prioritized)),
-                         use_hint=int(bool(use_hint)), update_actor_interval=int(update_actor_interval),
+                         use_hint=int(bool(use_hint)), update_actor_interval=int(update_actor_interval), flags=int(flags),
                          gamma=float(gamma), tau=float(tau), lr_actor=float(lr_actor), lr_critic=float(lr_critic),
                          reward_scale=float(reward_scale), alpha=float(alpha), max_action=float(max_action),
                          per_clip=float(per_clip), hint_threshold=float(hint_threshold), admm_rho=float(admm_rho),

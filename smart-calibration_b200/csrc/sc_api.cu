@@ -859,6 +859,7 @@ int sc_per_update_host(sc_agent* a, const int32_t* tree_idx_host, const float* a
 static void fill_common(sc_agent* a, RowPhaseParams& p) {
   memset(&p, 0, sizeof(p));
   p.kind = a->cfg.kind;
+  p.closs_scale = (a->cfg.flags & SC_FLAG_CRITIC_LOSS_SUM) ? (float)a->B : 1.f;
   p.B = a->B; p.S = a->S; p.Sp = a->Sp; p.A = a->A; p.Ap = a->Ap;
   p.crit[0] = critic_ptrs(a->params + a->off_c1, a->Lc);
   p.crit[1] = critic_ptrs(a->params + a->off_c2, a->Lc);

@@ -782,7 +782,7 @@ __device__ void tail_critic(const RowPhaseParams& p, const TailSm& t, const RowS
   consumer_sync();
   mark(12);
   const float wsum = p.is_wsum ? ld_act(p.is_wsum) : (float)p.B;
-  const float coef = 2.f * wsum / ((float)p.B * (float)p.B);      // d/dq of mean(w)*mean((q-y)^2)
+  const float coef = 2.f * wsum / ((float)p.B * (float)p.B) * p.closs_scale;   // d/dq of mean(w)*mean((q-y)^2) [DDPG: sum]
   if (tid < RT) {
     float* s = t.sc + tid * 16;
     const int row = rs.row[tid];

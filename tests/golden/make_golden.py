@@ -27,9 +27,11 @@ from smartcal_b200.synth import make_transitions  # noqa: E402
 from oracle.per_ref import PerRef  # noqa: E402
 from oracle.sac_ref import SacRef  # noqa: E402
 from oracle.td3_ref import Td3Ref  # noqa: E402
+from oracle.ddpg_ref import DdpgRef  # noqa: E402
 
 import enet_sac as ref_sac  # noqa: E402  (the reference)
 import enet_td3 as ref_td3  # noqa: E402
+import enet_ddpg as ref_ddpg  # noqa: E402
 
 NSAMP = 32
 
@@ -213,6 +215,54 @@ def td3_case(name, S, A, B, C, steps, seed, prioritized, done_frac, use_hint=Fal
     print(f"{name}: {steps} steps, oracle-vs-reference worst rel diff {worst:.3g}")
 
 
+def ddpg_case(name, S, A, B, C, steps, seed, done_frac):
+    hp = dict(gamma=0.99, lr_a=1e-4, lr_c=1e-3, input_dims=[S], batch_size=B, n_actions=A, max_mem_size=C, tau=0.001)   # main_ddpg.py:18-19
+    tr = make_transitions(seed + 100, C, S, A, "normal", done_frac)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    agent = ref_ddpg.Agent(**hp)
+    torch.manual_seed(seed)
+    orc = DdpgRef(**hp)
+    mem = agent.replaymem
+    mem.state_memory[:C], mem.new_state_memory[:C], mem.action_memory[:C] = tr["state"], tr["new_state"], tr["action"]
+    mem.reward_memory[:C], mem.terminal_memory[:C] = tr["reward"], tr["done"]
+    mem.mem_cntr = C
+    for i in range(C):
+        orc.store_flat(tr["state"][i], tr["action"][i], float(tr["reward"][i]), tr["new_state"][i], bool(tr["done"][i]))
+    out = dict(cfg=np.array([S, A, B, C, steps, seed], np.int64), done_frac=np.array([done_frac]))
+    net_digests(out, "init/actor", agent.actor, False)
+    net_digests(out, "init/critic", agent.critic, False)
+    o0 = {}
+    oracle_digests(o0, "init/actor", orc.actor, None)
+    oracle_digests(o0, "init/critic", orc.critic, None)
+    compare({k: out[k] for k in o0}, o0, name + " init")
+    np.random.seed(seed + 1)
+    torch.manual_seed(seed + 1)
+    worst = 0.0
+    for s in range(steps):
+        nst = np.random.get_state()
+        agent.learn()
+        nend = np.random.get_state()
+        np.random.set_state(nst)
+        idx = np.random.choice(C, B, replace=False)
+        assert np.array_equal(np.random.get_state()[1], nend[1]), "draw order mismatch"
+        out[f"step{s}/idx"] = idx.astype(np.int32)
+        ref_d = {}
+        for nm, mod, adam in (("actor", agent.actor, True), ("critic", agent.critic, True), ("target_actor", agent.target_actor, False),
+                              ("target_critic", agent.target_critic, False)):
+            net_digests(ref_d, f"step{s}/{nm}", mod, adam)
+        res = orc.learn_on_batch(orc.replay.gather(idx))
+        orc_d = {}
+        for nm, prm, opt in (("actor", orc.actor, orc.opt_a), ("critic", orc.critic, orc.opt_c), ("target_actor", orc.target_actor, None),
+                             ("target_critic", orc.target_critic, None)):
+            oracle_digests(orc_d, f"step{s}/{nm}", prm, opt)
+        worst = max(worst, compare(ref_d, orc_d, f"{name} step {s}", tol=1e-12))
+        out.update(ref_d)
+        out[f"step{s}/losses"] = np.array([res["critic_loss"], res["actor_loss"]])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: {steps} steps, oracle-vs-reference worst rel diff {worst:.3g}")
+
+
 def per_case(name, C, B, rounds, seed):
     """Drive the reference PER class directly: stores (with and without errors), stratified samples, updates."""
     rs = np.random.RandomState(seed)
@@ -270,3 +320,4 @@ if __name__ == "__main__":
     td3_case("td3_uniform_s24_b32", 24, 2, 32, 64, 2, 5, False, 0.1)
     td3_case("td3_per_enet_b64", 420, 2, 64, 128, 2, 6, True, 0.05)
     td3_case("td3_per_hint_s24_b32", 24, 2, 32, 64, 4, 7, True, 0.1, use_hint=True, admm_rho=1.0)
+    ddpg_case("ddpg_s24_b32", 24, 2, 32, 64, 3, 8, 0.1)

@@ -86,3 +86,45 @@ def test_sac_learn_against_reference_golden(name):
             assert abs(got[0] - ref[0]) <= 2e-4 * ref[1] + 1e-12, f"{nm}.{k} sum(m)"
             assert abs(got[1] - ref[1]) <= 2e-4 * ref[1] + 1e-12, f"{nm}.{k} sum|m|"
             assert np.max(np.abs(got[2:] - ref[2:])) <= 2e-4 * max(np.max(np.abs(ref[2:])), ref[1] / adam[k][0].numel()) + 1e-12, f"{nm}.{k} samples"
+
+
+def test_ddpg_learn_against_reference_golden():
+    """enet_ddpg.Agent on the TD3 program (mirrored twin critic, sum-of-squares critic loss) vs the unmodified reference."""
+    from smartcal_b200.elasticnet import enet_ddpg
+    z = np.load(os.path.join(G, "ddpg_s24_b32.npz"))
+    S, A, B, C, steps, seed = [int(x) for x in z["cfg"]]
+    tr = make_transitions(seed + 100, C, S, A, "normal", float(z["done_frac"][0]))
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    agent = enet_ddpg.Agent(gamma=0.99, lr_a=1e-4, lr_c=1e-3, input_dims=[S], batch_size=B, n_actions=A, max_mem_size=C, tau=0.001,
+                            rng="reference")
+    for nm, view in (("actor", agent.actor), ("critic", agent.critic)):
+        for k, v in view.state_dict().items():
+            assert np.array_equal(digest(v), z[f"init/{nm}/{k}/p"]), f"init {nm}.{k} differs from the reference"
+    tr = dict(tr)
+    tr["hint"] = np.zeros_like(tr["hint"])
+    agent._dev.fill(pack(tr))
+    np.random.seed(seed + 1)
+    torch.manual_seed(seed + 1)
+    st = agent.learn(want_stats=True)
+    assert np.array_equal(agent._dev.buffer("batch_idx")[:, 0].cpu().numpy(), z["step0/idx"])
+    np.testing.assert_allclose([st["critic_loss"], st["actor_loss"]], z["step0/losses"], rtol=2e-4)
+    for nm, view in (("actor", agent.actor), ("critic", agent.critic)):
+        adam = view.adam_state()
+        for k in adam:
+            ref = z[f"step0/{nm}/{k}/m"]
+            got = digest(adam[k][0])
+            assert abs(got[0] - ref[0]) <= 2e-4 * ref[1] + 1e-12, f"{nm}.{k} sum(m)"
+            assert abs(got[1] - ref[1]) <= 2e-4 * ref[1] + 1e-12, f"{nm}.{k} sum|m|"
+            assert np.max(np.abs(got[2:] - ref[2:])) <= 2e-4 * max(np.max(np.abs(ref[2:])), ref[1] / adam[k][0].numel()) + 1e-12, f"{nm}.{k} samples"
+    # the mirrored critic slot stays bit-identical to the critic, the targets moved with tau
+    for k, v in agent.critic.state_dict().items():
+        assert torch.equal(v, agent._mirror.state_dict()[k]), f"mirror critic diverged at {k}"
+    for nm, view in (("target_actor", agent.target_actor), ("target_critic", agent.target_critic)):
+        for k, v in view.state_dict().items():
+            ref = z[f"step0/{nm}/{k}/p"]
+            got = digest(v)
+            assert np.max(np.abs(got[2:] - ref[2:])) <= 1e-6 * max(1.0, np.max(np.abs(ref[2:]))), f"{nm}.{k}"
+    for s in range(1, steps):
+        agent.learn()
+    assert agent._dev.counters()[1] == steps

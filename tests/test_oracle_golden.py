@@ -121,3 +121,21 @@ def test_td3_oracle_matches_reference(name):
         check_nets(z, f"step{s}", [("actor", orc.actor, orc.opt_a), ("critic_1", orc.critic_1, orc.opt_1), ("critic_2", orc.critic_2, orc.opt_2),
                                    ("target_actor", orc.target_actor, None), ("target_critic_1", orc.target_critic_1, None),
                                    ("target_critic_2", orc.target_critic_2, None)], TOL * (s + 1))
+
+
+def test_ddpg_oracle_matches_reference():
+    from oracle.ddpg_ref import DdpgRef
+    z = np.load(os.path.join(G, "ddpg_s24_b32.npz"))
+    S, A, B, C, steps, seed = [int(x) for x in z["cfg"]]
+    hp = dict(gamma=0.99, lr_a=1e-4, lr_c=1e-3, input_dims=[S], batch_size=B, n_actions=A, max_mem_size=C, tau=0.001)
+    tr = make_transitions(seed + 100, C, S, A, "normal", float(z["done_frac"][0]))
+    torch.manual_seed(seed)
+    orc = DdpgRef(**hp)
+    check_nets(z, "init", [("actor", orc.actor, None), ("critic", orc.critic, None)], 0.0)
+    for i in range(C):
+        orc.store_flat(tr["state"][i], tr["action"][i], float(tr["reward"][i]), tr["new_state"][i], bool(tr["done"][i]))
+    for s in range(steps):
+        res = orc.learn_on_batch(orc.replay.gather(z[f"step{s}/idx"]))
+        check_nets(z, f"step{s}", [("actor", orc.actor, orc.opt_a), ("critic", orc.critic, orc.opt_c),
+                                   ("target_actor", orc.target_actor, None), ("target_critic", orc.target_critic, None)], TOL * (s + 1))
+        np.testing.assert_allclose([res["critic_loss"], res["actor_loss"]], z[f"step{s}/losses"], rtol=1e-4)
