@@ -22,3 +22,13 @@ def pack(tr):
     """(n, 2S+2A+2) float32 rows [s | s2 | a | hint | r | done] -- the C ABI's packed transition"""
     return np.concatenate([tr["state"], tr["new_state"], tr["action"], tr["hint"], tr["reward"][:, None],
                            tr["done"].astype(np.float32)[:, None]], axis=1).astype(np.float32)
+
+
+def make_calib_transitions(seed, n, M, A, img=128, done_frac=0.0):
+    """synthetic calibration transitions (calib_sac.ReplayBuffer layout :26-42): influence-map image (1, img, img), sky
+    table (M+1, 7), action / hint in [-1, 1]^A"""
+    rs = np.random.RandomState(seed)
+    return dict(img=rs.standard_normal((n, 1, img, img)).astype(np.float32), sky=rs.standard_normal((n, M + 1, 7)).astype(np.float32),
+                img2=rs.standard_normal((n, 1, img, img)).astype(np.float32), sky2=rs.standard_normal((n, M + 1, 7)).astype(np.float32),
+                action=rs.uniform(-1, 1, (n, A)).astype(np.float32), hint=rs.uniform(-1, 1, (n, A)).astype(np.float32),
+                reward=rs.standard_normal(n).astype(np.float32), done=rs.uniform(0, 1, n) < done_frac)

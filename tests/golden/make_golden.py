@@ -23,11 +23,12 @@ os.environ["CUDA_VISIBLE_DEVICES"] = ""
 warnings.filterwarnings("ignore")
 
 import smartcal_b200  # noqa: E402
-from smartcal_b200.synth import make_transitions  # noqa: E402
+from smartcal_b200.synth import make_transitions, make_calib_transitions  # noqa: E402
 from oracle.per_ref import PerRef  # noqa: E402
 from oracle.sac_ref import SacRef  # noqa: E402
 from oracle.td3_ref import Td3Ref  # noqa: E402
 from oracle.ddpg_ref import DdpgRef  # noqa: E402
+from oracle.calib_ref import CalibSacRef  # noqa: E402
 
 import enet_sac as ref_sac  # noqa: E402  (the reference)
 import enet_td3 as ref_td3  # noqa: E402
@@ -263,6 +264,100 @@ def ddpg_case(name, S, A, B, C, steps, seed, done_frac):
     print(f"{name}: {steps} steps, oracle-vs-reference worst rel diff {worst:.3g}")
 
 
+def calib_case(name, M, B, C, steps, seed, use_hint, done_frac):
+    """calibration/calib_sac.py (conv SAC).  The module is imported under its own directory (it has its own lbfgsnew.py)."""
+    import contextlib
+    import importlib.util
+    import io
+    cdir = "/root/reference/calibration"
+    sys.path.insert(0, cdir)
+    spec = importlib.util.spec_from_file_location("ref_calib_sac", os.path.join(cdir, "calib_sac.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    sys.path.remove(cdir)
+    A = 2 * M
+    hp = dict(gamma=0.99, batch_size=B, n_actions=A, tau=0.005, max_mem_size=C, input_dims=[1, 128, 128], M=M, lr_a=1e-3, lr_c=1e-3,
+              reward_scale=M, alpha=0.03, hint_threshold=0.01, admm_rho=1.0, use_hint=use_hint)       # calibration/main_sac.py:16-19
+    tr = make_calib_transitions(seed + 100, C, M, A, 128, done_frac)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    agent = ref.Agent(**hp)
+    torch.manual_seed(seed)
+    orc = CalibSacRef(**hp)
+    for i in range(C):
+        agent.replaymem.store_transition({"img": tr["img"][i], "sky": tr["sky"][i]}, tr["action"][i], float(tr["reward"][i]),
+                                         {"img": tr["img2"][i], "sky": tr["sky2"][i]}, bool(tr["done"][i]), tr["hint"][i])
+        orc.replay.store(tr["img"][i], tr["sky"][i], tr["action"][i], float(tr["reward"][i]), tr["img2"][i], tr["sky2"][i],
+                         bool(tr["done"][i]), tr["hint"][i])
+    nets = (("actor", "actor"), ("critic_1", "critic_1"), ("critic_2", "critic_2"), ("target_critic_1", "target_critic_1"),
+            ("target_critic_2", "target_critic_2"))
+
+    def ref_digests(prefix):
+        d = {}
+        for nm, attr in nets:
+            mod = getattr(agent, attr)
+            for k, v in mod.state_dict().items():
+                d[f"{prefix}/{nm}/{k}/p"] = digest(v.float())
+            if hasattr(mod, "optimizer") and not nm.startswith("target"):
+                for k, p in mod.named_parameters():
+                    st = mod.optimizer.state.get(p, None)
+                    if st:
+                        d[f"{prefix}/{nm}/{k}/m"], d[f"{prefix}/{nm}/{k}/v"] = digest(st["exp_avg"]), digest(st["exp_avg_sq"])
+        return d
+
+    def orc_digests(prefix):
+        d = {}
+        for nm, attr in nets:
+            p, b = getattr(orc, attr), getattr(orc, attr + "_b")
+            for k, v in {**p, **b}.items():
+                d[f"{prefix}/{nm}/{k}/p"] = digest(v.float())
+            opt = {"actor": orc.opt_a, "critic_1": orc.opt_1, "critic_2": orc.opt_2}.get(nm)
+            if opt is not None:
+                for k, v in p.items():
+                    st = opt.state.get(v, None)
+                    if st:
+                        d[f"{prefix}/{nm}/{k}/m"], d[f"{prefix}/{nm}/{k}/v"] = digest(st["exp_avg"]), digest(st["exp_avg_sq"])
+        return d
+
+    out = dict(cfg=np.array([M, A, B, C, steps, seed, int(use_hint)], np.int64), done_frac=np.array([done_frac]))
+    out.update(ref_digests("init"))
+    compare(ref_digests("init"), orc_digests("init"), name + " init")
+    np.random.seed(seed + 1)
+    torch.manual_seed(seed + 1)
+    worst = 0.0
+    for s in range(steps):
+        nst, tst = np.random.get_state(), torch.get_rng_state()
+        with contextlib.redirect_stdout(io.StringIO()):
+            agent.learn()
+        nend, tend = np.random.get_state(), torch.get_rng_state()
+        np.random.set_state(nst)
+        torch.set_rng_state(tst)
+        idx = np.random.choice(C, B, replace=False)
+        e1, e2 = torch.randn(B, A), torch.randn(B, A)
+        assert np.array_equal(np.random.get_state()[1], nend[1]) and torch.equal(torch.get_rng_state(), tend), "draw order mismatch"
+        out[f"step{s}/idx"] = idx.astype(np.int32)
+        out[f"step{s}/eps1"], out[f"step{s}/eps2"] = e1.numpy(), e2.numpy()
+        res = orc.learn_on_batch(orc.replay.gather(idx), e1, e2)
+        rd, od = ref_digests(f"step{s}"), orc_digests(f"step{s}")
+        if use_hint:
+            rd[f"step{s}/rho"], od[f"step{s}/rho"] = np.array([float(agent.rho)]), np.array([float(orc.rho)])
+        worst = max(worst, compare(rd, od, f"{name} step {s}", tol=1e-12))
+        out.update(rd)
+        out[f"step{s}/losses"] = np.array([res["critic_1_loss"], res["critic_2_loss"], res["actor_loss"]])
+        out[f"step{s}/y"], out[f"step{s}/q1"], out[f"step{s}/pi"] = digest(res["y"]), digest(res["q1"]), digest(res["pi"])
+    # choose_action in eval mode (running statistics)
+    obs = make_calib_transitions(seed + 200, 1, M, A, 128, 0.0)
+    tst = torch.get_rng_state()
+    a_ref = agent.choose_action({"img": obs["img"][0], "sky": obs["sky"][0]})
+    torch.set_rng_state(tst)
+    eps = torch.randn(1, A)
+    a_orc = orc.choose_action(obs["img"][0], obs["sky"][0], eps)
+    assert np.array_equal(a_ref, a_orc), "choose_action differs"
+    out["act/eps"], out["act/action"] = eps.numpy(), a_ref
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"{name}: {steps} steps, oracle-vs-reference worst rel diff {worst:.3g}")
+
+
 def per_case(name, C, B, rounds, seed):
     """Drive the reference PER class directly: stores (with and without errors), stratified samples, updates."""
     rs = np.random.RandomState(seed)
@@ -321,3 +416,5 @@ if __name__ == "__main__":
     td3_case("td3_per_enet_b64", 420, 2, 64, 128, 2, 6, True, 0.05)
     td3_case("td3_per_hint_s24_b32", 24, 2, 32, 64, 4, 7, True, 0.1, use_hint=True, admm_rho=1.0)
     ddpg_case("ddpg_s24_b32", 24, 2, 32, 64, 3, 8, 0.1)
+    calib_case("calib_m3_b8", 3, 8, 16, 3, 9, False, 0.2)
+    calib_case("calib_m3_hint_b8", 3, 8, 16, 11, 10, True, 0.2)

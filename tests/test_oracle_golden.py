@@ -139,3 +139,37 @@ def test_ddpg_oracle_matches_reference():
         check_nets(z, f"step{s}", [("actor", orc.actor, orc.opt_a), ("critic", orc.critic, orc.opt_c),
                                    ("target_actor", orc.target_actor, None), ("target_critic", orc.target_critic, None)], TOL * (s + 1))
         np.testing.assert_allclose([res["critic_loss"], res["actor_loss"]], z[f"step{s}/losses"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["calib_m3_b8", "calib_m3_hint_b8"])
+def test_calib_oracle_matches_reference(name):
+    """conv SAC of calibration/calib_sac.py: the oracle restatement replays the reference's recorded draws"""
+    from oracle.calib_ref import CalibSacRef
+    from smartcal_b200.synth import make_calib_transitions
+    z = np.load(os.path.join(G, name + ".npz"))
+    M, A, B, C, steps, seed, use_hint = [int(x) for x in z["cfg"]]
+    steps = min(steps, 2)                       # each CPU step costs ~1 s
+    hp = dict(gamma=0.99, batch_size=B, n_actions=A, tau=0.005, max_mem_size=C, input_dims=[1, 128, 128], M=M, lr_a=1e-3, lr_c=1e-3,
+              reward_scale=M, alpha=0.03, hint_threshold=0.01, admm_rho=1.0, use_hint=bool(use_hint))
+    tr = make_calib_transitions(seed + 100, C, M, A, 128, float(z["done_frac"][0]))
+    torch.manual_seed(seed)
+    orc = CalibSacRef(**hp)
+    for i in range(C):
+        orc.replay.store(tr["img"][i], tr["sky"][i], tr["action"][i], float(tr["reward"][i]), tr["img2"][i], tr["sky2"][i],
+                         bool(tr["done"][i]), tr["hint"][i])
+
+    def check(prefix, tol):
+        for nm in ("actor", "critic_1", "critic_2", "target_critic_1", "target_critic_2"):
+            sd = {**getattr(orc, nm), **getattr(orc, nm + "_b")}
+            for k, v in sd.items():
+                ref = z[f"{prefix}/{nm}/{k}/p"]
+                a = v.detach().float().numpy().astype(np.float64).reshape(-1)
+                idx = np.linspace(0, a.size - 1, min(32, a.size)).astype(np.int64)
+                got = np.concatenate([[a.sum(), np.abs(a).sum()], a[idx]])
+                assert np.max(np.abs(got - ref) / (1.0 + np.abs(ref))) <= tol, f"{prefix}/{nm}/{k}"
+
+    check("init", 0.0)
+    for s in range(steps):
+        res = orc.learn_on_batch(orc.replay.gather(z[f"step{s}/idx"]), z[f"step{s}/eps1"], z[f"step{s}/eps2"])
+        check(f"step{s}", TOL * (s + 1))
+        np.testing.assert_allclose([res["critic_1_loss"], res["critic_2_loss"], res["actor_loss"]], z[f"step{s}/losses"], rtol=1e-4)
