@@ -168,6 +168,49 @@ int64_t sc_agent_launch_count(sc_agent* a);
 int sc_agent_kernel_time(sc_agent* a, int which, int reset, double* ms_total, int64_t* launches);
 int sc_agent_enable_kernel_timing(sc_agent* a, int on);
 
+/* =====================================================================================================================
+ * Calibration conv-SAC agent: replaces calibration/calib_sac.py:234-423 (Agent with conv Actor/Critic networks,
+ * BatchNorm2d in training mode inside learn(), KLD hint penalty).  Same conventions as the sc_agent_* group.
+ * ================================================================================================================== */
+/* constructor kwargs of calib_sac.Agent (:235-236); input_dims is fixed to [1, img, img] with img = 128 */
+typedef struct sc_calib_config {
+  int32_t abi_version;   /* = SC_ABI_VERSION */
+  int32_t batch_size, mem_size, n_actions;
+  int32_t M;             /* sky rows - 1: the sky tensor is (M+1) x 7 (calib_sac.py:30-36) */
+  int32_t img;           /* 128 */
+  int32_t use_hint, reserved;
+  double gamma, tau, lr_actor, lr_critic, alpha;
+  float hint_threshold, admm_rho;
+  uint64_t rng_seed;
+} sc_calib_config;
+typedef struct sc_calib sc_calib;
+
+size_t sc_calib_arena_bytes(const sc_calib_config* cfg);
+int sc_calib_create(const sc_calib_config* cfg, void* arena, size_t arena_bytes, void* cuda_stream, sc_calib** out);
+int sc_calib_destroy(sc_calib* a);
+int sc_calib_sync(sc_calib* a);
+/* `net` = SC_NET_ACTOR / SC_NET_CRITIC_{1,2} / SC_NET_TARGET_CRITIC_{1,2}; `name` = a calib_sac state_dict key
+ * ("conv2.weight" as [Cout][Cin*25], "bn1.running_var", "bn3.num_batches_tracked" (int64), "fc21.weight", ...).
+ * slot 3 = gradient of the last backward pass (tests). */
+int sc_calib_tensor(sc_calib* a, int net, int slot, const char* name, sc_tensor_info* out);
+/* replay arrays "state_memory_img", "state_memory_sky", "new_state_memory_img", "new_state_memory_sky",
+ * "action_memory", "hint_memory", "reward_memory", "terminal_memory" (float 0/1) and a few workspace buffers */
+int sc_calib_buffer(sc_calib* a, const char* name, sc_tensor_info* out);
+int sc_calib_get_counters(sc_calib* a, int64_t* mem_cntr, int64_t* learn_counter);
+int sc_calib_set_counters(sc_calib* a, int64_t mem_cntr, int64_t learn_counter);
+int sc_calib_set_scalars(sc_calib* a, float rho, float admm_rho);
+/* ReplayBuffer.store_transition (calib_sac.py:44-56): img (img*img), sky ((M+1)*7), action / hint (n_actions), host */
+int sc_calib_store_host(sc_calib* a, const float* img, const float* sky, const float* img2, const float* sky2, const float* action,
+                        const float* hint, float reward, int done);
+/* indices of np.random.choice(max_mem, B, replace=False) (calib_sac.py:60) */
+int sc_calib_set_batch_host(sc_calib* a, const int32_t* idx_host, int n);
+/* Agent.choose_action (calib_sac.py:285-295): actor in eval() mode; eps (n_actions) N(0,1) or NULL for device Philox */
+int sc_calib_act(sc_calib* a, const float* img_host, const float* sky_host, const float* eps_host, float* action_host_out);
+/* Agent.learn (calib_sac.py:300-378); noise->eps_next_host / eps_cur_host (B, n_actions) or NULL for device Philox */
+int sc_calib_learn(sc_calib* a, const sc_noise* noise_or_null, sc_learn_stats* stats_host_or_null);
+int sc_calib_soft_update(sc_calib* a, float tau);   /* update_network_parameters (calib_sac.py:271-276) */
+int64_t sc_calib_launch_count(sc_calib* a);
+
 #ifdef __cplusplus
 }
 #endif

@@ -130,9 +130,11 @@ def actor_forward(p, b, img, sky, train=True):
     return mu, sigma
 
 
-def sample_normal(p, b, img, sky, eps, max_action=1, train=True):
+def sample_normal(p, b, img, sky, eps, max_action=1, train=True, keep=None):
     """ref sample_normal :212-231 with the N(0,1) draw injected"""
     mu, sigma = actor_forward(p, b, img, sky, train)
+    if keep is not None:
+        keep["sigma"] = sigma.detach().clone()
     u = mu + eps * sigma
     action = torch.tanh(u) * torch.tensor(max_action)
     logp = -((u - mu) ** 2) / (2 * sigma ** 2) - torch.log(sigma) - LOG_SQRT_2PI
@@ -232,17 +234,20 @@ class CalibSacRef:
         self.opt_1.step()
         self.opt_2.step()
 
-        act, logp = sample_normal(self.actor, self.actor_b, img, sky, eps_cur, self.max_action)
-        cv = torch.min(critic_forward(self.critic_1, self.critic_1_b, img, act, sky),
-                       critic_forward(self.critic_2, self.critic_2_b, img, act, sky))
+        act, logp = sample_normal(self.actor, self.actor_b, img, sky, eps_cur, self.max_action, keep=out)
+        qp1 = critic_forward(self.critic_1, self.critic_1_b, img, act, sky)
+        qp2 = critic_forward(self.critic_2, self.critic_2_b, img, act, sky)
+        out.update(q1_pi=qp1.detach().clone(), q2_pi=qp2.detach().clone())
+        cv = torch.min(qp1, qp2)
         actor_loss = (self.alpha * logp - cv).mean()
         if self.use_hint:
             g = self._gfun(act, hint)
             actor_loss = actor_loss + 0.5 * self.admm_rho * g * g + self.rho * g
             out["gfun"] = g.item()
         self.opt_a.zero_grad()
+        act.retain_grad()
         actor_loss.backward()
-        out.update(actor_loss=actor_loss.item(), pi=act.detach().clone(), logp=logp.detach().clone())
+        out.update(actor_loss=actor_loss.item(), pi=act.detach().clone(), logp=logp.detach().clone(), d_pi=act.grad.clone())
         out["grad_a"] = OrderedDict((k, v.grad.clone()) for k, v in self.actor.items())
         self.opt_a.step()
         if self.learn_counter % 10 == 0 and self.use_hint:

@@ -46,6 +46,13 @@ class ScNoise(C.Structure):
                 ("td3_target_noise", C.c_double), ("has_td3_target_noise", C.c_int32), ("reserved", C.c_int32)]
 
 
+class ScCalibConfig(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("batch_size", C.c_int32), ("mem_size", C.c_int32), ("n_actions", C.c_int32),
+                ("M", C.c_int32), ("img", C.c_int32), ("use_hint", C.c_int32), ("reserved", C.c_int32),
+                ("gamma", C.c_double), ("tau", C.c_double), ("lr_actor", C.c_double), ("lr_critic", C.c_double), ("alpha", C.c_double),
+                ("hint_threshold", C.c_float), ("admm_rho", C.c_float), ("rng_seed", C.c_uint64)]
+
+
 # name -> (restype, argtypes); every symbol of include/smartcal_b200.h
 SIGNATURES = {
     "sc_last_error": (C.c_char_p, []),
@@ -72,6 +79,22 @@ SIGNATURES = {
     "sc_agent_launch_count": (C.c_int64, [C.c_void_p]),
     "sc_agent_kernel_time": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "sc_agent_enable_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    # calibration conv-SAC group
+    "sc_calib_arena_bytes": (C.c_size_t, [C.POINTER(ScCalibConfig)]),
+    "sc_calib_create": (C.c_int, [C.POINTER(ScCalibConfig), C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "sc_calib_destroy": (C.c_int, [C.c_void_p]),
+    "sc_calib_sync": (C.c_int, [C.c_void_p]),
+    "sc_calib_tensor": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(ScTensorInfo)]),
+    "sc_calib_buffer": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(ScTensorInfo)]),
+    "sc_calib_get_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "sc_calib_set_counters": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
+    "sc_calib_set_scalars": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
+    "sc_calib_store_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int]),
+    "sc_calib_set_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "sc_calib_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sc_calib_learn": (C.c_int, [C.c_void_p, C.POINTER(ScNoise), C.POINTER(ScLearnStats)]),
+    "sc_calib_soft_update": (C.c_int, [C.c_void_p, C.c_float]),
+    "sc_calib_launch_count": (C.c_int64, [C.c_void_p]),
 }
 
 _lib = None

@@ -357,6 +357,7 @@ static void init_dims(sc_agent* a, const sc_config* cfg) {
 extern "C" {
 
 const char* sc_last_error(void) { return g_err; }
+void sc_set_last_error_(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }   // shared with sc_calib.cu (not part of the ABI)
 int sc_abi_version(void) { return SC_ABI_VERSION; }
 
 size_t sc_agent_arena_bytes(const sc_config* cfg) {

@@ -1,0 +1,1033 @@
+// Calibration conv-SAC agent (calibration/calib_sac.py) on the GPU: C ABI `sc_calib_*` of include/smartcal_b200.h.
+// One learn() = eight trunk forward passes and three trunk backward passes, sequenced
+// here out of the kernels of sc_calib_kernels.cuh plus the small per-row kernels below.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/smartcal_b200.h"
+#include "sc_calib_kernels.cuh"
+
+namespace sc {
+cudaError_t launch_soft_update(const float* src, float* dst, size_t n, float tau, cudaStream_t st);
+cudaError_t launch_fill_normal(float* out, int n, uint64_t seed, uint64_t stream, cudaStream_t st);
+}  // namespace sc
+
+using namespace sc;
+using namespace sc::calib;
+
+extern "C" const char* sc_last_error(void);
+extern "C" void sc_set_last_error_(const char* msg);     // sc_api.cu
+
+static int failc(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  sc_set_last_error_(buf);
+  return code;
+}
+#define CKC(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return failc(SC_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+// ---- geometry of the reference networks (calib_sac.py:100-117,163-183 with input_dims = [1,128,128]) -----------------
+constexpr int IMG = 128, H1C = 62, H2C = 29, H3C = 13;
+constexpr int C1 = 16, C2 = 32, C3 = 32;
+constexpr int FLAT = C3 * H3C * H3C;      // 5408
+constexpr int FEAT = FLAT + 16;           // 5424
+constexpr int HID = 128, SIDE = 16;
+constexpr int AMAXC = 64;                 // max n_actions
+
+// =====================================================================================================================
+// small per-row kernels (one block per batch row unless noted)
+// =====================================================================================================================
+namespace {
+
+// dst[b][:] = src[idx[b]][:]
+__global__ void k_gather(const float* __restrict__ src, const int* __restrict__ idx, size_t W, float* __restrict__ dst) {
+  const size_t b = blockIdx.y;
+  const float* s = src + (size_t)idx[b] * W;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < W; i += (size_t)gridDim.x * blockDim.x) dst[b * W + i] = s[i];
+}
+
+// side network: x1 = [sky | action?] -> relu(fc_a) (128) -> relu(fc_b) (16) -> feat[b][5408:5424]; keeps x1, h1, o16
+__global__ void __launch_bounds__(128) k_side_fwd(const float* __restrict__ sky, int SKY, const float* __restrict__ act, int A,
+                                                  const float* __restrict__ wa, const float* __restrict__ ba, const float* __restrict__ wb,
+                                                  const float* __restrict__ bb, float* __restrict__ x1, float* __restrict__ h1,
+                                                  float* __restrict__ o16, float* __restrict__ feat) {
+  __shared__ float sx[192];
+  __shared__ float sh[HID];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int K1 = SKY + (act ? A : 0);
+  for (int i = tid; i < K1; i += 128) {
+    const float v = i < SKY ? sky[(size_t)b * SKY + i] : act[(size_t)b * A + (i - SKY)];
+    sx[i] = v;
+    x1[(size_t)b * K1 + i] = v;
+  }
+  __syncthreads();
+  {
+    const float* w = wa + (size_t)tid * K1;
+    float s = ba[tid];
+    for (int i = 0; i < K1; ++i) s = fmaf(w[i], sx[i], s);
+    s = fmaxf(s, 0.f);
+    sh[tid] = s;
+    h1[(size_t)b * HID + tid] = s;
+  }
+  __syncthreads();
+  if (tid < SIDE) {
+    const float* w = wb + (size_t)tid * HID;
+    float s = bb[tid];
+    for (int i = 0; i < HID; ++i) s = fmaf(w[i], sh[i], s);
+    s = fmaxf(s, 0.f);
+    o16[(size_t)b * SIDE + tid] = s;
+    feat[(size_t)b * FEAT + FLAT + tid] = s;
+  }
+}
+
+// q[b] = head_w . feat[b] + head_b
+__global__ void __launch_bounds__(256) k_critic_head(const float* __restrict__ feat, const float* __restrict__ hw, const float* __restrict__ hb,
+                                                     float* __restrict__ q) {
+  __shared__ float sh[8];
+  const int b = blockIdx.x;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < FEAT; i += 256) s = fmaf(feat[(size_t)b * FEAT + i], hw[i], s);
+  s = block_sum_float(s, sh);
+  if (threadIdx.x == 0) q[b] = s + hb[0];
+}
+
+// policy head (calib_sac.py:207-231): mu, sigma = clamp(raw, 1e-6, 1), u = mu + eps*sigma, a = tanh(u),
+// logp = sum_j [ -(u-mu)^2/(2 sigma^2) - log sigma - log sqrt(2 pi) - log(1 - a^2 + 1e-6) ]
+__global__ void __launch_bounds__(128) k_actor_head(const float* __restrict__ x21, const float* __restrict__ wmu, const float* __restrict__ bmu,
+                                                    const float* __restrict__ wsg, const float* __restrict__ bsg, const float* __restrict__ eps,
+                                                    int A, float* __restrict__ act, float* __restrict__ sig, float* __restrict__ raw,
+                                                    float* __restrict__ logp, float* __restrict__ mu_out, float* __restrict__ u_out) {
+  __shared__ float sx[HID];
+  __shared__ float slp[AMAXC];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  sx[tid] = x21[(size_t)b * HID + tid];
+  __syncthreads();
+  if (tid < A) {
+    float m = bmu[tid], r = bsg[tid];
+    const float *w1 = wmu + (size_t)tid * HID, *w2 = wsg + (size_t)tid * HID;
+    for (int i = 0; i < HID; ++i) {
+      m = fmaf(w1[i], sx[i], m);
+      r = fmaf(w2[i], sx[i], r);
+    }
+    const float s = fminf(fmaxf(r, 1e-6f), 1.f);
+    const float e = eps[(size_t)b * A + tid];
+    const float u = __fadd_rn(m, __fmul_rn(e, s));
+    const float a = tanhf(u);
+    const float d = u - m;
+    float lp = -(d * d) / (2.f * (s * s)) - logf(s) - 0.91893853320467274178f;
+    lp -= logf(1.f - a * a + 1e-6f);
+    act[(size_t)b * A + tid] = a;
+    sig[(size_t)b * A + tid] = s;
+    raw[(size_t)b * A + tid] = r;
+    if (mu_out != nullptr) {
+      mu_out[(size_t)b * A + tid] = m;
+      u_out[(size_t)b * A + tid] = u;
+    }
+    slp[tid] = lp;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int j = 0; j < A; ++j) s += slp[j];
+    logp[b] = s;
+  }
+}
+
+// y = r + gamma * (done ? 0 : min(qt1, qt2) - alpha * logp')   (calib_sac.py:320-323; no reward scale)
+__global__ void k_target(const float* qt1, const float* qt2, const float* logp2, const float* r, const float* done, float gamma, float alpha,
+                         int B, float* y) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float m = __fsub_rn(fminf(qt1[b], qt2[b]), __fmul_rn(alpha, logp2[b]));
+  if (done[b] != 0.f) m = 0.f;
+  y[b] = __fadd_rn(r[b], __fmul_rn(gamma, m));
+}
+
+// critic loss seed: dq = 2 (q - y) / B; dfeat[b][i] = dq[b] * head_w[i]; stats[slot] = mean (q - y)^2  (one block)
+__global__ void __launch_bounds__(256) k_critic_seed(const float* __restrict__ q, const float* __restrict__ y, int B, float* __restrict__ dq,
+                                                     float* __restrict__ stat) {
+  __shared__ float sh[8];
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += 256) {
+    const float d = q[b] - y[b];
+    dq[b] = 2.f * d / (float)B;
+    s = fmaf(d, d, s);
+  }
+  s = block_sum_float(s, sh);
+  if (threadIdx.x == 0) stat[0] = s / (float)B;
+}
+__global__ void k_outer(const float* __restrict__ dq, const float* __restrict__ hw, int B, int N, float* __restrict__ out) {
+  const size_t total = (size_t)B * N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / N;
+    out[i] = dq[b] * hw[i - b * N];
+  }
+}
+
+// side network backward for one row: d16 = dfeat[b][5408:] * (o16 > 0); dh1 = (W_b^T d16) * (h1 > 0);
+// optionally dact[b][j] (+)= sum_n dh1[n] * W_a[n][SKY + j]
+__global__ void __launch_bounds__(128) k_side_bwd(const float* __restrict__ dfeat_side, long ld_dfeat, const float* __restrict__ o16,
+                                                  const float* __restrict__ h1, const float* __restrict__ wb, const float* __restrict__ wa, int K1,
+                                                  int SKY, int A, float* __restrict__ d16, float* __restrict__ dh1, float* __restrict__ dact,
+                                                  int accumulate) {
+  __shared__ float sd[SIDE];
+  __shared__ float sdh[HID];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid < SIDE) {
+    const float v = o16[(size_t)b * SIDE + tid] > 0.f ? dfeat_side[(size_t)b * ld_dfeat + tid] : 0.f;
+    sd[tid] = v;
+    d16[(size_t)b * SIDE + tid] = v;
+  }
+  __syncthreads();
+  {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < SIDE; ++k) s = fmaf(sd[k], wb[(size_t)k * HID + tid], s);
+    s = h1[(size_t)b * HID + tid] > 0.f ? s : 0.f;
+    sdh[tid] = s;
+    dh1[(size_t)b * HID + tid] = s;
+  }
+  __syncthreads();
+  if (dact != nullptr && tid < A) {
+    float s = 0.f;
+    for (int n = 0; n < HID; ++n) s = fmaf(sdh[n], wa[(size_t)n * K1 + SKY + tid], s);
+    dact[(size_t)b * A + tid] = (accumulate ? dact[(size_t)b * A + tid] : 0.f) + s;
+  }
+}
+
+// actor loss seeds (calib_sac.py:344,355): L = mean(alpha*logp - min(q1,q2)); dq_k = -(1/B) [k attains the min] (halves on ties);
+// dfeat_side_k[b][j] = dq_k[b] * head_w_k[5408 + j]; qmin for the loss readout
+__global__ void k_actor_seed(const float* q1, const float* q2, const float* hw1, const float* hw2, int B, float* ds1, float* ds2, float* qmin) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float a = q1[b], c = q2[b];
+  const float w = 1.f / (float)B;
+  float g1 = 0.f, g2 = 0.f;
+  if (a < c) g1 = -w; else if (c < a) g2 = -w; else { g1 = -0.5f * w; g2 = -0.5f * w; }
+  qmin[b] = fminf(a, c);
+  for (int j = 0; j < SIDE; ++j) {
+    ds1[(size_t)b * SIDE + j] = g1 * hw1[FLAT + j];
+    ds2[(size_t)b * SIDE + j] = g2 * hw2[FLAT + j];
+  }
+}
+
+// hint penalty (calib_sac.py:345-365): kld = h_m (log h_m - log a_m), a_m = clamp(0.5 a + 0.5 + EPS, EPS, 1) (same for h);
+// g = max(0, mean(kld) - thr)^2.  out[0] = d(0.5 admm_rho g^2 + rho g)/d mean(kld) / (B A), out[1] = g, out[2] = penalty value;
+// rho_update (every 10th learn): rho += admm_rho * g.   One block.
+__global__ void __launch_bounds__(256) k_kld_coef(const float* __restrict__ act, const float* __restrict__ hint, int n, float thr, float admm_rho,
+                                                  float* rho, float* out, int do_rho_update) {
+  __shared__ float sh[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float am = fminf(fmaxf(0.5f * act[i] + 0.5f + 1e-6f, 1e-6f), 1.f);
+    const float hm = fminf(fmaxf(0.5f * hint[i] + 0.5f + 1e-6f, 1e-6f), 1.f);
+    s += hm * (logf(hm) - logf(am));
+  }
+  s = block_sum_float(s, sh);
+  if (threadIdx.x == 0) {
+    const float mk = s / (float)n - thr;
+    const float pos = fmaxf(mk, 0.f);
+    const float g = pos * pos;
+    const float r = rho[0];
+    out[0] = (admm_rho * g + r) * 2.f * pos / (float)n;
+    out[1] = g;
+    out[2] = 0.5f * admm_rho * g * g + r * g;
+    if (do_rho_update) rho[0] = r + admm_rho * g;
+  }
+}
+
+// policy head backward for one row.  With ga = dL/da (critics + hint + the tanh correction of logp) and gt = ga (1 - a^2):
+//   dL/dsigma = gt * eps - glp / sigma analytically (see below for the float32 order),   d raw = d sigma * [1e-6 <= raw <= 1]
+//   dL/dmu    = gt analytically -- but the reference reaches it as (gv + gt) - gv, where gv = -glp (u - mu) / sigma^2 is
+//   the derivative of the Gaussian term w.r.t. the sample, which autograd adds to the sample's gradient and subtracts
+//   again through `loc` (Normal.log_prob + rsample, calib_sac.py:213-228).  For actions whose sigma sits at the 1e-6
+//   clamp |gv| ~ 4e3 |eps| while |gt| ~ 1e-3, so the reference's float32 result is gt plus rounding noise of that order.
+//   The same float32 operations are issued here in the same order so that the update matches the reference's.
+//   dx21 = Wmu^T dmu + Wsg^T draw, then through the ELU of fc21.
+__global__ void __launch_bounds__(128) k_actor_head_bwd(const float* __restrict__ da, const float* __restrict__ act, const float* __restrict__ sig,
+                                                        const float* __restrict__ raw, const float* __restrict__ eps, const float* __restrict__ mu,
+                                                        const float* __restrict__ uu, const float* __restrict__ hint,
+                                                        const float* __restrict__ hint_coef, float glp, int A, const float* __restrict__ wmu,
+                                                        const float* __restrict__ wsg, const float* __restrict__ x21, float* __restrict__ dmu,
+                                                        float* __restrict__ draw, float* __restrict__ dpre) {
+  __shared__ float sm[AMAXC], sr[AMAXC];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid < A) {
+    const size_t o = (size_t)b * A + tid;
+    const float a = act[o], s = sig[o], r = raw[o], e = eps[o];
+    float g = da[o];
+    if (hint_coef != nullptr) {
+      const float arg = 0.5f * a + 0.5f + 1e-6f;
+      const float am = fminf(fmaxf(arg, 1e-6f), 1.f);
+      const float hm = fminf(fmaxf(0.5f * hint[o] + 0.5f + 1e-6f, 1e-6f), 1.f);
+      if (arg >= 1e-6f && arg <= 1.f) g += hint_coef[0] * (-hm / am) * 0.5f;
+    }
+    const float omt = __fsub_rn(1.f, __fmul_rn(a, a));
+    g += glp * (2.f * a / (omt + 1e-6f));                      // d(-glp log(1 - a^2 + 1e-6))/da
+    const float gt = __fmul_rn(g, omt);                        // tanh backward
+    const float z = __fsub_rn(uu[o], mu[o]);
+    const float d2 = __fmul_rn(2.f, __fmul_rn(s, s));
+    const float gv = -__fmul_rn(__fdiv_rn(glp, d2), __fmul_rn(2.f, z));
+    const float gu = __fadd_rn(gv, gt);
+    const float du = __fsub_rn(gu, gv);                        // = gt up to the reference's cancellation noise
+    // sigma collects three contributions in autograd's arrival order (log, var = sigma^2, then the sample mu + eps*sigma):
+    //   g3 = -glp / sigma,  g2 = d(-(z^2)/(2 var))/d var * 2 sigma  (ATen: grad_other = -grad * ((self/other)/other)),  g1 = gu * eps.
+    // Analytically g1 + g2 = gt * eps; in float32 z = fl(u - mu) differs from eps*sigma by ~ulp(mu), which for sigma near the
+    // 1e-6 clamp is a 1e-4 relative effect on the dominant -glp/sigma term, so the reference's order is kept.
+    const float nq = __fdiv_rn(-__fmul_rn(z, z), d2);
+    const float gd2 = __fmul_rn(-glp, __fdiv_rn(nq, d2));
+    const float g2 = __fmul_rn(__fmul_rn(gd2, 2.f), __fmul_rn(2.f, s));
+    const float g3 = __fdiv_rn(-glp, s);
+    const float g1 = __fmul_rn(gu, e);
+    const float ds = __fadd_rn(__fadd_rn(g3, g2), g1);
+    const float dr = (r >= 1e-6f && r <= 1.f) ? ds : 0.f;
+    sm[tid] = du;
+    sr[tid] = dr;
+    dmu[o] = du;
+    draw[o] = dr;
+  }
+  __syncthreads();
+  float s = 0.f;
+  for (int j = 0; j < A; ++j) s = fmaf(sm[j], wmu[(size_t)j * HID + tid], fmaf(sr[j], wsg[(size_t)j * HID + tid], s));
+  dpre[(size_t)b * HID + tid] = s * elu_grad_from_out(x21[(size_t)b * HID + tid]);
+}
+
+// actor loss readout: mean(alpha*logp - qmin) (+ penalty)   (one block)
+__global__ void __launch_bounds__(256) k_actor_loss(const float* __restrict__ logp, const float* __restrict__ qmin, int B, float alpha,
+                                                    const float* __restrict__ pen, float* __restrict__ stat) {
+  __shared__ float sh[8];
+  float s = 0.f, l = 0.f;
+  for (int b = threadIdx.x; b < B; b += 256) {
+    s += alpha * logp[b] - qmin[b];
+    l += logp[b];
+  }
+  s = block_sum_float(s, sh);
+  l = block_sum_float(l, sh);
+  if (threadIdx.x == 0) {
+    stat[0] = s / (float)B + (pen ? pen[2] : 0.f);
+    stat[1] = l / (float)B;
+  }
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// host side
+// =====================================================================================================================
+struct CTensor { std::string name; int rows, cols; size_t off; };
+struct CLayout {
+  std::vector<CTensor> t;
+  size_t size = 0;
+  void add(const char* n, int r, int c) { t.push_back(CTensor{n, r, c, size}); size += ((size_t)r * c + 3) & ~(size_t)3; }
+  size_t off(const char* n) const {
+    for (auto& d : t) if (d.name == n) return d.off;
+    return (size_t)-1;
+  }
+};
+struct NetP {
+  float *cw[3], *cb[3], *g[3], *be[3];
+  float *fa_w, *fa_b, *fb_w, *fb_b, *h_w, *h_b, *mu_w, *mu_b, *sg_w, *sg_b;
+};
+struct TrunkWs {
+  float *z[3], *a[3];                 // a[2] aliases feat (image stride FEAT)
+  float* feat;                        // [B][5424]
+  float *mean[3], *rstd[3], *scale[3], *shift[3];
+  float *x1, *h1, *o16;               // side network activations
+};
+struct PiSide { float *x1, *h1, *o16; };
+
+struct sc_calib {
+  sc_calib_config cfg;
+  int B, C, A, M, SKY, K1C;           // K1C: critic side input width (sky + action)
+  cudaStream_t st;
+  bool own_arena;
+  char* arena;
+  size_t arena_bytes;
+  CLayout La, Lc;
+  // parameter-like blocks: [actor | critic_1 | critic_2]
+  float *params, *grads, *adam_m, *adam_v, *targets;     // targets: [t1 | t2] in critic layout
+  size_t off_net[3], n_params;
+  float* bnbuf[5];                    // per net: rm1 rv1 rm2 rv2 rm3 rv3 (16,16,32,32,32,32 floats)
+  long long* nbt[5];                  // per net: 3 counters
+  // replay
+  float *r_img, *r_img2, *r_sky, *r_sky2, *r_act, *r_hint, *r_rew, *r_done;
+  int* bidx;
+  // minibatch
+  float *mb_img, *mb_img2, *mb_sky, *mb_sky2, *mb_act, *mb_hint, *mb_rew, *mb_done;
+  float *eps_next, *eps_cur;
+  TrunkWs ws[4];
+  PiSide pside[2];
+  // heads / scalars
+  float *x21, *pre21;                 // actor fc21 output (post-ELU) [B][128]; scratch
+  float *a2, *sig2, *raw2, *logp2;    // policy on s'
+  float *pi, *sig, *raw, *logp, *mu, *u;   // policy on s
+  float *qt[2], *q[2], *qpi[2], *y, *dq, *qmin;
+  float *dfeat, *dz3, *dA2, *dA1;     // gradient workspace (dz2, dz1 written in place over dA2, dA1)
+  float *d16, *dh1, *ds[2], *dact, *dmu, *draw, *dpre;
+  float *bn_c1, *bn_c2;               // BN backward per-channel means
+  double* red_partial;                // [32][NCH][2]
+  float* wg_partial;
+  float *stats, *rho, *hint_out;
+  float* h_stage;                     // pinned host staging
+  float* h_stats;
+  int* h_idx;
+  int64_t mem_cntr, learn_counter, t_actor, t_critic, launches, noise_ctr;
+  bool batch_ready;
+  float admm_rho;
+  int wg_blocks, nch;
+  std::map<std::string, sc_tensor_info> reg;
+};
+
+static CLayout critic_layout_c(int K1) {
+  CLayout L;
+  L.add("conv1.weight", C1, 1 * TAPS); L.add("conv1.bias", 1, C1); L.add("bn1.weight", 1, C1); L.add("bn1.bias", 1, C1);
+  L.add("conv2.weight", C2, C1 * TAPS); L.add("conv2.bias", 1, C2); L.add("bn2.weight", 1, C2); L.add("bn2.bias", 1, C2);
+  L.add("conv3.weight", C3, C2 * TAPS); L.add("conv3.bias", 1, C3); L.add("bn3.weight", 1, C3); L.add("bn3.bias", 1, C3);
+  L.add("fc1.weight", HID, K1); L.add("fc1.bias", 1, HID);
+  L.add("fc2.weight", SIDE, HID); L.add("fc2.bias", 1, SIDE);
+  L.add("head.weight", 1, FEAT); L.add("head.bias", 1, 1);
+  return L;
+}
+static CLayout actor_layout_c(int SKY, int A) {
+  CLayout L;
+  L.add("conv1.weight", C1, 1 * TAPS); L.add("conv1.bias", 1, C1); L.add("bn1.weight", 1, C1); L.add("bn1.bias", 1, C1);
+  L.add("conv2.weight", C2, C1 * TAPS); L.add("conv2.bias", 1, C2); L.add("bn2.weight", 1, C2); L.add("bn2.bias", 1, C2);
+  L.add("conv3.weight", C3, C2 * TAPS); L.add("conv3.bias", 1, C3); L.add("bn3.weight", 1, C3); L.add("bn3.bias", 1, C3);
+  L.add("fc11.weight", HID, SKY); L.add("fc11.bias", 1, HID);
+  L.add("fc12.weight", SIDE, HID); L.add("fc12.bias", 1, SIDE);
+  L.add("fc21.weight", HID, FEAT); L.add("fc21.bias", 1, HID);
+  L.add("fc22mu.weight", A, HID); L.add("fc22mu.bias", 1, A);
+  L.add("fc22sigma.weight", A, HID); L.add("fc22sigma.bias", 1, A);
+  return L;
+}
+static NetP net_ptrs(float* b, const CLayout& L, bool actor) {
+  NetP p;
+  memset(&p, 0, sizeof(p));
+  const char* cw[3] = {"conv1.weight", "conv2.weight", "conv3.weight"};
+  const char* cb[3] = {"conv1.bias", "conv2.bias", "conv3.bias"};
+  const char* g[3] = {"bn1.weight", "bn2.weight", "bn3.weight"};
+  const char* be[3] = {"bn1.bias", "bn2.bias", "bn3.bias"};
+  for (int l = 0; l < 3; ++l) { p.cw[l] = b + L.off(cw[l]); p.cb[l] = b + L.off(cb[l]); p.g[l] = b + L.off(g[l]); p.be[l] = b + L.off(be[l]); }
+  if (actor) {
+    p.fa_w = b + L.off("fc11.weight"); p.fa_b = b + L.off("fc11.bias");
+    p.fb_w = b + L.off("fc12.weight"); p.fb_b = b + L.off("fc12.bias");
+    p.h_w = b + L.off("fc21.weight"); p.h_b = b + L.off("fc21.bias");
+    p.mu_w = b + L.off("fc22mu.weight"); p.mu_b = b + L.off("fc22mu.bias");
+    p.sg_w = b + L.off("fc22sigma.weight"); p.sg_b = b + L.off("fc22sigma.bias");
+  } else {
+    p.fa_w = b + L.off("fc1.weight"); p.fa_b = b + L.off("fc1.bias");
+    p.fb_w = b + L.off("fc2.weight"); p.fb_b = b + L.off("fc2.bias");
+    p.h_w = b + L.off("head.weight"); p.h_b = b + L.off("head.bias");
+  }
+  return p;
+}
+
+struct CarverC {
+  char* base; size_t off = 0;
+  void* take(size_t bytes) { off = (off + 255) & ~(size_t)255; void* p = base ? base + off : nullptr; off += bytes; return p; }
+  float* f(size_t n) { return (float*)take(n * sizeof(float)); }
+};
+
+static size_t carve_c(sc_calib* a, char* base) {
+  CarverC cv{base};
+  const size_t B = a->B, C = a->C, A = a->A, SKY = a->SKY;
+  auto reg = [&](const char* name, void* p, int64_t rows, int64_t cols, int elem = 4, int is_int = 0) {
+    if (base) a->reg[name] = sc_tensor_info{p, rows, cols, cols, elem, is_int};
+  };
+  a->off_net[0] = 0; a->off_net[1] = a->La.size; a->off_net[2] = a->La.size + a->Lc.size;
+  a->n_params = a->La.size + 2 * a->Lc.size;
+  a->params = cv.f(a->n_params); a->grads = cv.f(a->n_params); a->adam_m = cv.f(a->n_params); a->adam_v = cv.f(a->n_params);
+  a->targets = cv.f(2 * a->Lc.size);
+  for (int n = 0; n < 5; ++n) { a->bnbuf[n] = cv.f(160); a->nbt[n] = (long long*)cv.take(4 * sizeof(long long)); }
+  a->r_img = cv.f(C * IMG * IMG); a->r_img2 = cv.f(C * IMG * IMG);
+  a->r_sky = cv.f(C * SKY); a->r_sky2 = cv.f(C * SKY); a->r_act = cv.f(C * A); a->r_hint = cv.f(C * A); a->r_rew = cv.f(C); a->r_done = cv.f(C);
+  reg("state_memory_img", a->r_img, C, IMG * IMG); reg("new_state_memory_img", a->r_img2, C, IMG * IMG);
+  reg("state_memory_sky", a->r_sky, C, SKY); reg("new_state_memory_sky", a->r_sky2, C, SKY);
+  reg("action_memory", a->r_act, C, A); reg("hint_memory", a->r_hint, C, A); reg("reward_memory", a->r_rew, C, 1); reg("terminal_memory", a->r_done, C, 1);
+  a->bidx = (int*)cv.take(B * sizeof(int)); reg("batch_idx", a->bidx, B, 1, 4, 1);
+  a->mb_img = cv.f(B * IMG * IMG); a->mb_img2 = cv.f(B * IMG * IMG); a->mb_sky = cv.f(B * SKY); a->mb_sky2 = cv.f(B * SKY);
+  a->mb_act = cv.f(B * A); a->mb_hint = cv.f(B * A); a->mb_rew = cv.f(B); a->mb_done = cv.f(B);
+  a->eps_next = cv.f(B * A); a->eps_cur = cv.f(B * A); reg("eps_next", a->eps_next, B, A); reg("eps_cur", a->eps_cur, B, A);
+  for (int w = 0; w < 4; ++w) {
+    TrunkWs& t = a->ws[w];
+    t.z[0] = cv.f(B * C1 * H1C * H1C); t.a[0] = cv.f(B * C1 * H1C * H1C);
+    t.z[1] = cv.f(B * C2 * H2C * H2C); t.a[1] = cv.f(B * C2 * H2C * H2C);
+    t.z[2] = cv.f(B * C3 * H3C * H3C);
+    t.feat = cv.f(B * FEAT); t.a[2] = t.feat;
+    for (int l = 0; l < 3; ++l) { t.mean[l] = cv.f(32); t.rstd[l] = cv.f(32); t.scale[l] = cv.f(32); t.shift[l] = cv.f(32); }
+    t.x1 = cv.f(B * (SKY + A)); t.h1 = cv.f(B * HID); t.o16 = cv.f(B * SIDE);
+  }
+  for (int k = 0; k < 2; ++k) { a->pside[k].x1 = cv.f(B * (SKY + A)); a->pside[k].h1 = cv.f(B * HID); a->pside[k].o16 = cv.f(B * SIDE); }
+  a->x21 = cv.f(B * HID); a->pre21 = cv.f(B * HID);
+  a->a2 = cv.f(B * A); a->sig2 = cv.f(B * A); a->raw2 = cv.f(B * A); a->logp2 = cv.f(B);
+  a->pi = cv.f(B * A); a->sig = cv.f(B * A); a->raw = cv.f(B * A); a->logp = cv.f(B); a->mu = cv.f(B * A); a->u = cv.f(B * A);
+  reg("pi", a->pi, B, A); reg("logp", a->logp, B, 1); reg("sigma", a->sig, B, A);
+  for (int k = 0; k < 2; ++k) { a->qt[k] = cv.f(B); a->q[k] = cv.f(B); a->qpi[k] = cv.f(B); a->ds[k] = cv.f(B * SIDE); }
+  a->y = cv.f(B); a->dq = cv.f(B); a->qmin = cv.f(B);
+  reg("y", a->y, B, 1); reg("q1", a->q[0], B, 1); reg("q2", a->q[1], B, 1); reg("q1_pi", a->qpi[0], B, 1); reg("q2_pi", a->qpi[1], B, 1);
+  a->dfeat = cv.f(B * FEAT); a->dz3 = cv.f(B * C3 * H3C * H3C); a->dA2 = cv.f(B * C2 * H2C * H2C); a->dA1 = cv.f(B * C1 * H1C * H1C);
+  a->d16 = cv.f(B * SIDE); a->dh1 = cv.f(B * HID); a->dact = cv.f(B * A); reg("d_pi", a->dact, B, A); a->dmu = cv.f(B * A); a->draw = cv.f(B * A); reg("d_mu", a->dmu, B, A); reg("d_sigma_raw", a->draw, B, A); a->dpre = cv.f(B * HID);
+  a->bn_c1 = cv.f(32); a->bn_c2 = cv.f(32);
+  a->red_partial = (double*)cv.take(sizeof(double) * 32 * 64 * 2);
+  a->wg_partial = cv.f((size_t)a->wg_blocks * C3 * C2 * TAPS);
+  a->stats = cv.f(16); a->rho = cv.f(4); a->hint_out = cv.f(4);
+  return cv.off;
+}
+
+static int check_cfg_c(const sc_calib_config* c) {
+  if (!c) return failc(SC_ERR_ARG, "null config");
+  if (c->abi_version != SC_ABI_VERSION) return failc(SC_ERR_ARG, "ABI version mismatch");
+  if (c->img != IMG) return failc(SC_ERR_ARG, "only input_dims = [1,128,128] is built (calibration/main_sac.py:17)");
+  if (c->batch_size < 2 || c->mem_size < c->batch_size) return failc(SC_ERR_ARG, "need 2 <= batch_size <= mem_size");
+  if (c->n_actions < 1 || c->n_actions > AMAXC || c->M < 1 || 7 * (c->M + 1) + c->n_actions > 192)
+    return failc(SC_ERR_ARG, "n_actions must be in [1,%d] and 7(M+1)+n_actions <= 192", AMAXC);
+  return SC_OK;
+}
+static void init_dims_c(sc_calib* a, const sc_calib_config* c) {
+  a->cfg = *c;
+  a->B = c->batch_size; a->C = c->mem_size; a->A = c->n_actions; a->M = c->M;
+  a->SKY = 7 * (c->M + 1);
+  a->K1C = a->SKY + a->A;
+  a->La = actor_layout_c(a->SKY, a->A);
+  a->Lc = critic_layout_c(a->K1C);
+  a->wg_blocks = 296;
+  a->nch = a->B < 32 ? a->B : 32;
+}
+
+// ---- launch helpers -------------------------------------------------------------------------------------------------
+#define LAUNCH_OK(a) do { CKC(cudaGetLastError()); (a)->launches++; } while (0)
+static inline int grid_for(size_t n, int block = 256, int cap = 148 * 16) {
+  size_t g = (n + block - 1) / block;
+  return (int)(g > (size_t)cap ? cap : (g ? g : 1));
+}
+
+static int bn_forward(sc_calib* a, TrunkWs& t, const NetP& P, int net, int l, int C, int HW, int act, int train, int Bn) {
+  float* rb = a->bnbuf[net];
+  float* rm = rb + (l == 0 ? 0 : l == 1 ? 32 : 96);
+  float* rv = rm + (l == 0 ? 16 : 32);
+  if (train) {
+    ChanReduceP r;
+    memset(&r, 0, sizeof(r));
+    r.z = t.z[l]; r.B = Bn; r.C = C; r.HW = HW; r.mode = 0; r.partial = a->red_partial;
+    const int nch = Bn < a->nch ? Bn : a->nch;
+    k_chan_reduce<<<dim3(C, nch), 256, 0, a->st>>>(r);
+    LAUNCH_OK(a);
+    BnFinalizeP f{a->red_partial, nch, P.g[l], P.be[l], rm, rv, a->nbt[net] + l, t.mean[l], t.rstd[l], t.scale[l], t.shift[l], (double)Bn * HW, 1};
+    k_bn_finalize<<<1, 32, 0, a->st>>>(f, C);
+    LAUNCH_OK(a);
+  } else {
+    BnFinalizeP f{nullptr, 0, P.g[l], P.be[l], rm, rv, a->nbt[net] + l, t.mean[l], t.rstd[l], t.scale[l], t.shift[l], 1.0, 0};
+    k_bn_finalize<<<1, 32, 0, a->st>>>(f, C);
+    LAUNCH_OK(a);
+  }
+  const size_t total = (size_t)Bn * C * HW;
+  const size_t astride = l == 2 ? (size_t)FEAT : (size_t)C * HW;
+  k_bn_act<<<grid_for(total), 256, 0, a->st>>>(t.z[l], t.scale[l], t.shift[l], C, HW, total, act, t.a[l], astride);
+  LAUNCH_OK(a);
+  return SC_OK;
+}
+
+// conv trunk forward of network `net` (parameters P) on images x [Bn][16384] into workspace t
+static int trunk_forward(sc_calib* a, TrunkWs& t, const NetP& P, int net, const float* x, int act, int train, int Bn) {
+  using G1 = ConvGeom<1, C1, IMG, H1C>;
+  using G2 = ConvGeom<C1, C2, H1C, H2C>;
+  using G3 = ConvGeom<C2, C3, H2C, H3C>;
+  k_conv_fwd<1, C1, IMG, H1C><<<dim3(G1::BLOCKS_PER_IMG, Bn), 256, 0, a->st>>>(x, (size_t)IMG * IMG, P.cw[0], P.cb[0], t.z[0]);
+  LAUNCH_OK(a);
+  int rc = bn_forward(a, t, P, net, 0, C1, H1C * H1C, act, train, Bn);
+  if (rc) return rc;
+  k_conv_fwd<C1, C2, H1C, H2C><<<dim3(G2::BLOCKS_PER_IMG, Bn), 256, 0, a->st>>>(t.a[0], (size_t)C1 * H1C * H1C, P.cw[1], P.cb[1], t.z[1]);
+  LAUNCH_OK(a);
+  if ((rc = bn_forward(a, t, P, net, 1, C2, H2C * H2C, act, train, Bn))) return rc;
+  k_conv_fwd<C2, C3, H2C, H3C><<<dim3(G3::BLOCKS_PER_IMG, Bn), 256, 0, a->st>>>(t.a[1], (size_t)C2 * H2C * H2C, P.cw[2], P.cb[2], t.z[2]);
+  LAUNCH_OK(a);
+  return bn_forward(a, t, P, net, 2, C3, H3C * H3C, act, train, Bn);
+}
+
+static int sgemm(sc_calib* a, const float* A_, long sam, long sak, const float* B_, long sbk, long sbn, float* C_, long ldc, int M, int N, int K,
+                 const float* bias, int act) {
+  k_sgemm<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, a->st>>>(A_, sam, sak, B_, sbk, sbn, C_, ldc, M, N, K, bias, act);
+  LAUNCH_OK(a);
+  return SC_OK;
+}
+static int colsum(sc_calib* a, const float* X, long ldx, const float* w, int Bn, int N, float* out) {
+  k_colsum<<<(N + 127) / 128, 128, 0, a->st>>>(X, ldx, w, Bn, N, out);
+  LAUNCH_OK(a);
+  return SC_OK;
+}
+
+// BatchNorm + conv backward of layer l: dA (image stride dA_stride) is the gradient w.r.t. the layer's activation output.
+// Leaves dz in `dz_out`, writes d gamma / d beta / d conv weight / d conv bias into G, and (l > 0) the input gradient into dA_prev.
+static int layer_backward(sc_calib* a, TrunkWs& t, const NetP& P, const NetP& G, int l, const float* dA, size_t dA_stride, float* dz_out,
+                          const float* x_in, size_t x_stride, float* dA_prev, int act) {
+  const int Cn = l == 0 ? C1 : (l == 1 ? C2 : C3);
+  const int Ho = l == 0 ? H1C : (l == 1 ? H2C : H3C);
+  const int HW = Ho * Ho;
+  const int Bn = a->B;
+  const size_t astride = l == 2 ? (size_t)FEAT : (size_t)Cn * HW;
+  ChanReduceP r;
+  memset(&r, 0, sizeof(r));
+  r.z = t.z[l]; r.a = t.a[l]; r.dA = dA; r.a_img_stride = astride; r.dA_img_stride = dA_stride; r.mean = t.mean[l]; r.rstd = t.rstd[l];
+  r.B = Bn; r.C = Cn; r.HW = HW; r.act = act; r.mode = 1; r.partial = a->red_partial;
+  const int nch = Bn < a->nch ? Bn : a->nch;
+  k_chan_reduce<<<dim3(Cn, nch), 256, 0, a->st>>>(r);
+  LAUNCH_OK(a);
+  BnBwdFinalizeP f{a->red_partial, nch, G.g[l], G.be[l], a->bn_c1, a->bn_c2, (double)Bn * HW};
+  k_bn_bwd_finalize<<<1, 32, 0, a->st>>>(f, Cn);
+  LAUNCH_OK(a);
+  const size_t total = (size_t)Bn * Cn * HW;
+  k_bn_bwd_apply<<<grid_for(total), 256, 0, a->st>>>(dA, dA_stride, t.a[l], astride, t.z[l], t.scale[l], t.mean[l], t.rstd[l], a->bn_c1, a->bn_c2, Cn,
+                                                      HW, total, act, dz_out);
+  LAUNCH_OK(a);
+  // conv bias gradient = sum dz
+  memset(&r, 0, sizeof(r));
+  r.z = dz_out; r.dA = dz_out; r.dA_img_stride = (size_t)Cn * HW; r.B = Bn; r.C = Cn; r.HW = HW; r.mode = 2; r.partial = a->red_partial;
+  k_chan_reduce<<<dim3(Cn, nch), 256, 0, a->st>>>(r);
+  LAUNCH_OK(a);
+  k_bias_grad_finalize<<<1, 32, 0, a->st>>>(a->red_partial, nch, Cn, G.cb[l]);
+  LAUNCH_OK(a);
+  // conv weight gradient: partials per block, then a fixed-order sum
+  const int nb = a->wg_blocks;
+  if (l == 0) {
+    k_conv_wgrad_l1<<<nb, 256, 0, a->st>>>(x_in, x_stride, dz_out, Bn, a->wg_partial);
+    LAUNCH_OK(a);
+    k_sum_partials<<<(C1 * TAPS + 255) / 256, 256, 0, a->st>>>(a->wg_partial, nb, C1 * TAPS, G.cw[0]);
+  } else if (l == 1) {
+    k_conv_wgrad<C1, C2, H1C, H2C><<<nb, 256, 52 * 1024, a->st>>>(x_in, x_stride, dz_out, Bn, a->wg_partial);
+    LAUNCH_OK(a);
+    k_sum_partials<<<(C2 * C1 * TAPS + 255) / 256, 256, 0, a->st>>>(a->wg_partial, nb, C2 * C1 * TAPS, G.cw[1]);
+  } else {
+    k_conv_wgrad<C2, C3, H2C, H3C><<<nb, 256, 101 * 1024, a->st>>>(x_in, x_stride, dz_out, Bn, a->wg_partial);
+    LAUNCH_OK(a);
+    k_sum_partials<<<(C3 * C2 * TAPS + 255) / 256, 256, 0, a->st>>>(a->wg_partial, nb, C3 * C2 * TAPS, G.cw[2]);
+  }
+  LAUNCH_OK(a);
+  if (l == 2) {
+    using G3 = DgradGeom<C2, C3, H2C, H3C>;
+    k_conv_dgrad<C2, C3, H2C, H3C><<<dim3(G3::BLOCKS_PER_IMG, Bn), 256, 0, a->st>>>(dz_out, P.cw[2], dA_prev);
+    LAUNCH_OK(a);
+  } else if (l == 1) {
+    using G2 = DgradGeom<C1, C2, H1C, H2C>;
+    k_conv_dgrad<C1, C2, H1C, H2C><<<dim3(G2::BLOCKS_PER_IMG, Bn), 256, 0, a->st>>>(dz_out, P.cw[1], dA_prev);
+    LAUNCH_OK(a);
+  }
+  return SC_OK;
+}
+
+// whole trunk backward from dfeat[:, 0:5408]
+static int trunk_backward(sc_calib* a, TrunkWs& t, const NetP& P, const NetP& G, const float* img, int act) {
+  int rc;
+  if ((rc = layer_backward(a, t, P, G, 2, a->dfeat, FEAT, a->dz3, t.a[1], (size_t)C2 * H2C * H2C, a->dA2, act))) return rc;
+  if ((rc = layer_backward(a, t, P, G, 1, a->dA2, (size_t)C2 * H2C * H2C, a->dA2, t.a[0], (size_t)C1 * H1C * H1C, a->dA1, act))) return rc;
+  return layer_backward(a, t, P, G, 0, a->dA1, (size_t)C1 * H1C * H1C, a->dA1, img, (size_t)IMG * IMG, nullptr, act);
+}
+
+// side network weight gradients from d16 [B][16], dh1 [B][128], activations h1 and x1 [B][K1]
+static int side_wgrads(sc_calib* a, const float* x1, const float* h1, int K1, const NetP& G) {
+  int rc;
+  if ((rc = sgemm(a, a->d16, 1, SIDE, h1, HID, 1, G.fb_w, HID, SIDE, HID, a->B, nullptr, -1))) return rc;
+  if ((rc = colsum(a, a->d16, SIDE, nullptr, a->B, SIDE, G.fb_b))) return rc;
+  if ((rc = sgemm(a, a->dh1, 1, HID, x1, K1, 1, G.fa_w, K1, HID, K1, a->B, nullptr, -1))) return rc;
+  return colsum(a, a->dh1, HID, nullptr, a->B, HID, G.fa_b);
+}
+
+static AdamP adam_hyper_c(double lr, int64_t t) {
+  const double b1 = 0.9, b2 = 0.999;
+  AdamP h;
+  const double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
+  h.lr_neg_step = (float)(-(lr / bc1));
+  h.bc2_sqrt = (float)sqrt(bc2);
+  h.one_minus_b1 = (float)(1.0 - b1);
+  h.b2 = (float)b2;
+  h.one_minus_b2 = (float)(1.0 - b2);
+  h.eps = 1e-8f;
+  return h;
+}
+static int adam_step(sc_calib* a, int net, double lr, int64_t t) {
+  const size_t n = net == 0 ? a->La.size : a->Lc.size, off = a->off_net[net];
+  k_adam<<<grid_for(n), 256, 0, a->st>>>(a->params + off, a->grads + off, a->adam_m + off, a->adam_v + off, n, adam_hyper_c(lr, t));
+  LAUNCH_OK(a);
+  return SC_OK;
+}
+
+extern "C" {
+
+size_t sc_calib_arena_bytes(const sc_calib_config* cfg) {
+  if (check_cfg_c(cfg) != SC_OK) return 0;
+  sc_calib tmp;
+  init_dims_c(&tmp, cfg);
+  return carve_c(&tmp, nullptr);
+}
+
+int sc_calib_create(const sc_calib_config* cfg, void* arena, size_t arena_bytes, void* cuda_stream, sc_calib** out) {
+  if (!out) return failc(SC_ERR_ARG, "null out");
+  *out = nullptr;
+  int rc = check_cfg_c(cfg);
+  if (rc) return rc;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return failc(SC_ERR_CUDA, "no CUDA device: libsmartcal_b200 has no CPU fallback");
+  }
+  sc_calib* a = new sc_calib();
+  init_dims_c(a, cfg);
+  a->st = (cudaStream_t)cuda_stream;
+  const size_t need = carve_c(a, nullptr);
+  if (arena) {
+    if (arena_bytes < need) { delete a; return failc(SC_ERR_ARG, "arena too small: %zu < %zu", arena_bytes, need); }
+    a->arena = (char*)arena; a->own_arena = false;
+  } else {
+    if (cudaMalloc((void**)&a->arena, need) != cudaSuccess) { delete a; return failc(SC_ERR_CUDA, "cudaMalloc(%zu) failed", need); }
+    a->own_arena = true;
+  }
+  a->arena_bytes = need;
+  carve_c(a, a->arena);
+  CKC(cudaMemsetAsync(a->arena, 0, need, a->st));
+  // BatchNorm buffers start at running_mean = 0, running_var = 1 (nn.BatchNorm2d defaults)
+  {
+    std::vector<float> init(160, 0.f);
+    for (int i = 16; i < 32; ++i) init[i] = 1.f;
+    for (int i = 64; i < 96; ++i) init[i] = 1.f;
+    for (int i = 128; i < 160; ++i) init[i] = 1.f;
+    for (int n = 0; n < 5; ++n) CKC(cudaMemcpyAsync(a->bnbuf[n], init.data(), 160 * sizeof(float), cudaMemcpyHostToDevice, a->st));
+    CKC(cudaStreamSynchronize(a->st));
+  }
+  const size_t stage = (size_t)2 * IMG * IMG + 2 * a->SKY + 2 * a->A + 8 + (size_t)2 * a->B * a->A;
+  CKC(cudaHostAlloc((void**)&a->h_stage, stage * sizeof(float), cudaHostAllocDefault));
+  CKC(cudaHostAlloc((void**)&a->h_stats, 16 * sizeof(float), cudaHostAllocDefault));
+  CKC(cudaHostAlloc((void**)&a->h_idx, (size_t)a->B * sizeof(int), cudaHostAllocDefault));
+  CKC(cudaFuncSetAttribute(k_conv_wgrad<C1, C2, H1C, H2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024));
+  CKC(cudaFuncSetAttribute(k_conv_wgrad<C2, C3, H2C, H3C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 101 * 1024));
+  a->mem_cntr = a->learn_counter = a->t_actor = a->t_critic = a->launches = a->noise_ctr = 0;
+  a->batch_ready = false;
+  a->admm_rho = cfg->admm_rho;
+  *out = a;
+  return SC_OK;
+}
+
+int sc_calib_destroy(sc_calib* a) {
+  if (!a) return SC_OK;
+  cudaStreamSynchronize(a->st);
+  if (a->h_stage) cudaFreeHost(a->h_stage);
+  if (a->h_stats) cudaFreeHost(a->h_stats);
+  if (a->h_idx) cudaFreeHost(a->h_idx);
+  if (a->own_arena && a->arena) cudaFree(a->arena);
+  delete a;
+  return SC_OK;
+}
+int sc_calib_sync(sc_calib* a) {
+  if (!a) return failc(SC_ERR_ARG, "null handle");
+  CKC(cudaStreamSynchronize(a->st));
+  return SC_OK;
+}
+int64_t sc_calib_launch_count(sc_calib* a) { return a ? a->launches : 0; }
+
+int sc_calib_tensor(sc_calib* a, int net, int slot, const char* name, sc_tensor_info* out) {
+  if (!a || !name || !out) return failc(SC_ERR_ARG, "null argument");
+  if (net < 0 || net > 4) return failc(SC_ERR_ARG, "bad net id %d", net);
+  const bool actor = net == SC_NET_ACTOR;
+  const CLayout& L = actor ? a->La : a->Lc;
+  // BatchNorm buffers
+  const char* dot = strrchr(name, '.');
+  if (dot && (!strcmp(dot, ".running_mean") || !strcmp(dot, ".running_var") || !strcmp(dot, ".num_batches_tracked"))) {
+    if (strncmp(name, "bn", 2) != 0 || name[2] < '1' || name[2] > '3') return failc(SC_ERR_ARG, "unknown buffer %s", name);
+    const int l = name[2] - '1';
+    if (!strcmp(dot, ".num_batches_tracked")) { *out = sc_tensor_info{a->nbt[net] + l, 1, 1, 1, 8, 1}; return SC_OK; }
+    float* rm = a->bnbuf[net] + (l == 0 ? 0 : l == 1 ? 32 : 96);
+    const int C = l == 0 ? 16 : 32;
+    *out = sc_tensor_info{!strcmp(dot, ".running_mean") ? rm : rm + C, 1, C, C, 4, 0};
+    return SC_OK;
+  }
+  float* base;
+  if (net <= 2) {
+    float* blocks[3] = {a->params, a->adam_m, a->adam_v};
+    if (slot < 0 || slot > 3) return failc(SC_ERR_ARG, "bad slot %d", slot);
+    base = (slot == 3 ? a->grads : blocks[slot]) + a->off_net[net];
+  } else {
+    if (slot != SC_SLOT_PARAM) return failc(SC_ERR_ARG, "targets have no optimizer state");
+    base = a->targets + (size_t)(net - 3) * a->Lc.size;
+  }
+  if (!strcmp(name, "*")) { *out = sc_tensor_info{base, 1, (int64_t)L.size, (int64_t)L.size, 4, 0}; return SC_OK; }
+  for (auto& d : L.t)
+    if (d.name == name) { *out = sc_tensor_info{base + d.off, d.rows, d.cols, d.cols, 4, 0}; return SC_OK; }
+  return failc(SC_ERR_ARG, "no tensor named %s", name);
+}
+int sc_calib_buffer(sc_calib* a, const char* name, sc_tensor_info* out) {
+  if (!a || !name || !out) return failc(SC_ERR_ARG, "null argument");
+  auto it = a->reg.find(name);
+  if (it == a->reg.end()) return failc(SC_ERR_ARG, "no buffer named %s", name);
+  *out = it->second;
+  return SC_OK;
+}
+int sc_calib_get_counters(sc_calib* a, int64_t* mem_cntr, int64_t* learn_counter) {
+  if (!a) return failc(SC_ERR_ARG, "null handle");
+  if (mem_cntr) *mem_cntr = a->mem_cntr;
+  if (learn_counter) *learn_counter = a->learn_counter;
+  return SC_OK;
+}
+int sc_calib_set_counters(sc_calib* a, int64_t mem_cntr, int64_t learn_counter) {
+  if (!a) return failc(SC_ERR_ARG, "null handle");
+  a->mem_cntr = mem_cntr; a->learn_counter = learn_counter;
+  return SC_OK;
+}
+int sc_calib_set_scalars(sc_calib* a, float rho, float admm_rho) {
+  if (!a) return failc(SC_ERR_ARG, "null handle");
+  a->admm_rho = admm_rho;
+  CKC(cudaMemcpyAsync(a->rho, &rho, sizeof(float), cudaMemcpyHostToDevice, a->st));
+  CKC(cudaStreamSynchronize(a->st));
+  return SC_OK;
+}
+
+int sc_calib_store_host(sc_calib* a, const float* img, const float* sky, const float* img2, const float* sky2, const float* action,
+                        const float* hint, float reward, int done) {
+  if (!a || !img || !sky || !img2 || !sky2 || !action || !hint) return failc(SC_ERR_ARG, "null argument");
+  const size_t slot = (size_t)(a->mem_cntr % a->C), NI = (size_t)IMG * IMG;
+  CKC(cudaStreamSynchronize(a->st));                      // the staging buffer may still be in flight
+  float* h = a->h_stage;
+  memcpy(h, img, NI * 4); memcpy(h + NI, img2, NI * 4);
+  float* s = h + 2 * NI;
+  memcpy(s, sky, a->SKY * 4); memcpy(s + a->SKY, sky2, a->SKY * 4);
+  float* t = s + 2 * a->SKY;
+  memcpy(t, action, a->A * 4); memcpy(t + a->A, hint, a->A * 4);
+  t[2 * a->A] = reward; t[2 * a->A + 1] = done ? 1.f : 0.f;
+  CKC(cudaMemcpyAsync(a->r_img + slot * NI, h, NI * 4, cudaMemcpyHostToDevice, a->st));
+  CKC(cudaMemcpyAsync(a->r_img2 + slot * NI, h + NI, NI * 4, cudaMemcpyHostToDevice, a->st));
+  CKC(cudaMemcpyAsync(a->r_sky + slot * a->SKY, s, a->SKY * 4, cudaMemcpyHostToDevice, a->st));
+  CKC(cudaMemcpyAsync(a->r_sky2 + slot * a->SKY, s + a->SKY, a->SKY * 4, cudaMemcpyHostToDevice, a->st));
+  CKC(cudaMemcpyAsync(a->r_act + slot * a->A, t, a->A * 4, cudaMemcpyHostToDevice, a->st));
+  CKC(cudaMemcpyAsync(a->r_hint + slot * a->A, t + a->A, a->A * 4, cudaMemcpyHostToDevice, a->st));
+  CKC(cudaMemcpyAsync(a->r_rew + slot, t + 2 * a->A, 4, cudaMemcpyHostToDevice, a->st));
+  CKC(cudaMemcpyAsync(a->r_done + slot, t + 2 * a->A + 1, 4, cudaMemcpyHostToDevice, a->st));
+  a->mem_cntr++;
+  return SC_OK;
+}
+
+int sc_calib_set_batch_host(sc_calib* a, const int32_t* idx, int n) {
+  if (!a || !idx) return failc(SC_ERR_ARG, "null argument");
+  if (n != a->B) return failc(SC_ERR_ARG, "need %d indices", a->B);
+  const int64_t lim = a->mem_cntr < a->C ? a->mem_cntr : a->C;
+  for (int i = 0; i < n; ++i)
+    if (idx[i] < 0 || idx[i] >= lim) return failc(SC_ERR_ARG, "batch index %d out of range", idx[i]);
+  CKC(cudaStreamSynchronize(a->st));
+  memcpy(a->h_idx, idx, (size_t)n * sizeof(int));
+  CKC(cudaMemcpyAsync(a->bidx, a->h_idx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, a->st));
+  a->batch_ready = true;
+  return SC_OK;
+}
+
+int sc_calib_soft_update(sc_calib* a, float tau) {
+  if (!a) return failc(SC_ERR_ARG, "null handle");
+  // calib_sac.py:271-276: parameters() only; the targets' BatchNorm buffers are never copied
+  CKC(launch_soft_update(a->params + a->off_net[1], a->targets, 2 * a->Lc.size, tau, a->st));
+  a->launches++;
+  return SC_OK;
+}
+
+// choose_action (calib_sac.py:285-295): actor in eval mode (running statistics), one observation
+int sc_calib_act(sc_calib* a, const float* img, const float* sky, const float* eps, float* action_out) {
+  if (!a || !img || !sky || !action_out) return failc(SC_ERR_ARG, "null argument");
+  const size_t NI = (size_t)IMG * IMG;
+  CKC(cudaStreamSynchronize(a->st));
+  memcpy(a->h_stage, img, NI * 4);
+  memcpy(a->h_stage + NI, sky, a->SKY * 4);
+  if (eps) memcpy(a->h_stage + NI + a->SKY, eps, a->A * 4);
+  CKC(cudaMemcpyAsync(a->mb_img2, a->h_stage, NI * 4, cudaMemcpyHostToDevice, a->st));
+  CKC(cudaMemcpyAsync(a->mb_sky2, a->h_stage + NI, a->SKY * 4, cudaMemcpyHostToDevice, a->st));
+  if (eps) CKC(cudaMemcpyAsync(a->eps_next, a->h_stage + NI + a->SKY, a->A * 4, cudaMemcpyHostToDevice, a->st));
+  else { CKC(launch_fill_normal(a->eps_next, a->A, a->cfg.rng_seed, 0x9000u + (uint64_t)(a->noise_ctr++), a->st)); a->launches++; }
+  const NetP P = net_ptrs(a->params + a->off_net[0], a->La, true);
+  TrunkWs& t = a->ws[0];
+  int rc = trunk_forward(a, t, P, 0, a->mb_img2, ACT_ELU, 0, 1);
+  if (rc) return rc;
+  k_side_fwd<<<1, 128, 0, a->st>>>(a->mb_sky2, a->SKY, nullptr, 0, P.fa_w, P.fa_b, P.fb_w, P.fb_b, t.x1, t.h1, t.o16, t.feat);
+  LAUNCH_OK(a);
+  if ((rc = sgemm(a, t.feat, FEAT, 1, P.h_w, 1, FEAT, a->x21, HID, 1, HID, FEAT, P.h_b, ACT_ELU))) return rc;
+  k_actor_head<<<1, 128, 0, a->st>>>(a->x21, P.mu_w, P.mu_b, P.sg_w, P.sg_b, a->eps_next, a->A, a->a2, a->sig2, a->raw2, a->logp2, nullptr, nullptr);
+  LAUNCH_OK(a);
+  CKC(cudaMemcpyAsync(a->h_stage, a->a2, a->A * 4, cudaMemcpyDeviceToHost, a->st));
+  CKC(cudaStreamSynchronize(a->st));
+  memcpy(action_out, a->h_stage, a->A * 4);
+  a->batch_ready = false;       // the minibatch staging buffers were used as scratch
+  return SC_OK;
+}
+
+int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
+  if (!a) return failc(SC_ERR_ARG, "null handle");
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (a->mem_cntr < a->B) return SC_OK;                                     // calib_sac.py:301-302
+  if (!a->batch_ready) return failc(SC_ERR_STATE, "no minibatch selected: call sc_calib_set_batch_host first");
+  const int B = a->B, A = a->A, SKY = a->SKY;
+  const size_t NI = (size_t)IMG * IMG;
+  int rc;
+  // ---- noise ----
+  if (noise && noise->eps_next_host && noise->eps_cur_host) {
+    CKC(cudaStreamSynchronize(a->st));
+    float* h = a->h_stage;
+    memcpy(h, noise->eps_next_host, (size_t)B * A * 4);
+    memcpy(h + (size_t)B * A, noise->eps_cur_host, (size_t)B * A * 4);
+    CKC(cudaMemcpyAsync(a->eps_next, h, (size_t)B * A * 4, cudaMemcpyHostToDevice, a->st));
+    CKC(cudaMemcpyAsync(a->eps_cur, h + (size_t)B * A, (size_t)B * A * 4, cudaMemcpyHostToDevice, a->st));
+  } else {
+    CKC(launch_fill_normal(a->eps_next, B * A, a->cfg.rng_seed, 2 * (uint64_t)a->noise_ctr, a->st));
+    CKC(launch_fill_normal(a->eps_cur, B * A, a->cfg.rng_seed, 2 * (uint64_t)a->noise_ctr + 1, a->st));
+    a->noise_ctr++;
+    a->launches += 2;
+  }
+  // ---- minibatch gather (replaces the host fancy-indexing + H2D copies of calib_sac.py:304-315) ----
+  k_gather<<<dim3(16, B), 256, 0, a->st>>>(a->r_img, a->bidx, NI, a->mb_img);  LAUNCH_OK(a);
+  k_gather<<<dim3(16, B), 256, 0, a->st>>>(a->r_img2, a->bidx, NI, a->mb_img2);  LAUNCH_OK(a);
+  k_gather<<<dim3(1, B), 128, 0, a->st>>>(a->r_sky, a->bidx, SKY, a->mb_sky);  LAUNCH_OK(a);
+  k_gather<<<dim3(1, B), 128, 0, a->st>>>(a->r_sky2, a->bidx, SKY, a->mb_sky2);  LAUNCH_OK(a);
+  k_gather<<<dim3(1, B), 64, 0, a->st>>>(a->r_act, a->bidx, A, a->mb_act);  LAUNCH_OK(a);
+  k_gather<<<dim3(1, B), 64, 0, a->st>>>(a->r_hint, a->bidx, A, a->mb_hint);  LAUNCH_OK(a);
+  k_gather<<<dim3(1, B), 32, 0, a->st>>>(a->r_rew, a->bidx, 1, a->mb_rew);  LAUNCH_OK(a);
+  k_gather<<<dim3(1, B), 32, 0, a->st>>>(a->r_done, a->bidx, 1, a->mb_done);  LAUNCH_OK(a);
+
+  const NetP PA = net_ptrs(a->params + a->off_net[0], a->La, true), GA = net_ptrs(a->grads + a->off_net[0], a->La, true);
+  NetP PC[2], GC[2], PT[2];
+  for (int k = 0; k < 2; ++k) {
+    PC[k] = net_ptrs(a->params + a->off_net[1 + k], a->Lc, false);
+    GC[k] = net_ptrs(a->grads + a->off_net[1 + k], a->Lc, false);
+    PT[k] = net_ptrs(a->targets + (size_t)k * a->Lc.size, a->Lc, false);
+  }
+  const float alpha = (float)a->cfg.alpha, gamma = (float)a->cfg.gamma;
+
+  // ---- 1. policy on s' (no grad; BatchNorm in train mode like the reference) ----
+  {
+    TrunkWs& t = a->ws[0];
+    if ((rc = trunk_forward(a, t, PA, 0, a->mb_img2, ACT_ELU, 1, B))) return rc;
+    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky2, SKY, nullptr, 0, PA.fa_w, PA.fa_b, PA.fb_w, PA.fb_b, t.x1, t.h1, t.o16, t.feat);
+    LAUNCH_OK(a);
+    if ((rc = sgemm(a, t.feat, FEAT, 1, PA.h_w, 1, FEAT, a->x21, HID, B, HID, FEAT, PA.h_b, ACT_ELU))) return rc;
+    k_actor_head<<<B, 128, 0, a->st>>>(a->x21, PA.mu_w, PA.mu_b, PA.sg_w, PA.sg_b, a->eps_next, A, a->a2, a->sig2, a->raw2, a->logp2, nullptr, nullptr);
+    LAUNCH_OK(a);
+  }
+  // ---- 2. target critics on (s', sky', a') ----
+  for (int k = 0; k < 2; ++k) {
+    TrunkWs& t = a->ws[0];
+    if ((rc = trunk_forward(a, t, PT[k], 3 + k, a->mb_img2, ACT_RELU, 1, B))) return rc;
+    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky2, SKY, a->a2, A, PT[k].fa_w, PT[k].fa_b, PT[k].fb_w, PT[k].fb_b, t.x1, t.h1, t.o16, t.feat);
+    LAUNCH_OK(a);
+    k_critic_head<<<B, 256, 0, a->st>>>(t.feat, PT[k].h_w, PT[k].h_b, a->qt[k]);
+    LAUNCH_OK(a);
+  }
+  k_target<<<(B + 127) / 128, 128, 0, a->st>>>(a->qt[0], a->qt[1], a->logp2, a->mb_rew, a->mb_done, gamma, alpha, B, a->y);
+  LAUNCH_OK(a);
+  // ---- 3. critics: forward on (s, sky, a), MSE loss, backward, Adam ----
+  a->t_critic++;
+  for (int k = 0; k < 2; ++k) {
+    TrunkWs& t = a->ws[1 + k];
+    if ((rc = trunk_forward(a, t, PC[k], 1 + k, a->mb_img, ACT_RELU, 1, B))) return rc;
+    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky, SKY, a->mb_act, A, PC[k].fa_w, PC[k].fa_b, PC[k].fb_w, PC[k].fb_b, t.x1, t.h1, t.o16, t.feat);
+    LAUNCH_OK(a);
+    k_critic_head<<<B, 256, 0, a->st>>>(t.feat, PC[k].h_w, PC[k].h_b, a->q[k]);
+    LAUNCH_OK(a);
+  }
+  for (int k = 0; k < 2; ++k) {
+    TrunkWs& t = a->ws[1 + k];
+    k_critic_seed<<<1, 256, 0, a->st>>>(a->q[k], a->y, B, a->dq, a->stats + k);
+    LAUNCH_OK(a);
+    k_outer<<<grid_for((size_t)B * FEAT), 256, 0, a->st>>>(a->dq, PC[k].h_w, B, FEAT, a->dfeat);
+    LAUNCH_OK(a);
+    if ((rc = colsum(a, t.feat, FEAT, a->dq, B, FEAT, GC[k].h_w))) return rc;       // d head.weight
+    if ((rc = colsum(a, a->dq, 1, nullptr, B, 1, GC[k].h_b))) return rc;             // d head.bias
+    k_side_bwd<<<B, 128, 0, a->st>>>(a->dfeat + FLAT, FEAT, t.o16, t.h1, PC[k].fb_w, PC[k].fa_w, a->K1C, SKY, A, a->d16, a->dh1, nullptr, 0);
+    LAUNCH_OK(a);
+    if ((rc = side_wgrads(a, t.x1, t.h1, a->K1C, GC[k]))) return rc;
+    if ((rc = trunk_backward(a, t, PC[k], GC[k], a->mb_img, ACT_RELU))) return rc;
+  }
+  for (int k = 0; k < 2; ++k)
+    if ((rc = adam_step(a, 1 + k, a->cfg.lr_critic, a->t_critic))) return rc;
+  // ---- 4. actor: policy on s (reparameterised), Q_k(s, pi) with the updated critics, backward, Adam ----
+  {
+    TrunkWs& t = a->ws[3];
+    if ((rc = trunk_forward(a, t, PA, 0, a->mb_img, ACT_ELU, 1, B))) return rc;
+    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky, SKY, nullptr, 0, PA.fa_w, PA.fa_b, PA.fb_w, PA.fb_b, t.x1, t.h1, t.o16, t.feat);
+    LAUNCH_OK(a);
+    if ((rc = sgemm(a, t.feat, FEAT, 1, PA.h_w, 1, FEAT, a->x21, HID, B, HID, FEAT, PA.h_b, ACT_ELU))) return rc;
+    k_actor_head<<<B, 128, 0, a->st>>>(a->x21, PA.mu_w, PA.mu_b, PA.sg_w, PA.sg_b, a->eps_cur, A, a->pi, a->sig, a->raw, a->logp, a->mu, a->u);
+    LAUNCH_OK(a);
+  }
+  for (int k = 0; k < 2; ++k) {
+    TrunkWs& t = a->ws[0];
+    if ((rc = trunk_forward(a, t, PC[k], 1 + k, a->mb_img, ACT_RELU, 1, B))) return rc;
+    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky, SKY, a->pi, A, PC[k].fa_w, PC[k].fa_b, PC[k].fb_w, PC[k].fb_b, a->pside[k].x1, a->pside[k].h1,
+                                     a->pside[k].o16, t.feat);
+    LAUNCH_OK(a);
+    k_critic_head<<<B, 256, 0, a->st>>>(t.feat, PC[k].h_w, PC[k].h_b, a->qpi[k]);
+    LAUNCH_OK(a);
+  }
+  k_actor_seed<<<(B + 127) / 128, 128, 0, a->st>>>(a->qpi[0], a->qpi[1], PC[0].h_w, PC[1].h_w, B, a->ds[0], a->ds[1], a->qmin);
+  LAUNCH_OK(a);
+  for (int k = 0; k < 2; ++k) {
+    k_side_bwd<<<B, 128, 0, a->st>>>(a->ds[k], SIDE, a->pside[k].o16, a->pside[k].h1, PC[k].fb_w, PC[k].fa_w, a->K1C, SKY, A, a->d16, a->dh1, a->dact, k);
+    LAUNCH_OK(a);
+  }
+  const bool hint = a->cfg.use_hint != 0;
+  const int dual = hint && (a->learn_counter % 10 == 0);
+  if (hint) {
+    k_kld_coef<<<1, 256, 0, a->st>>>(a->pi, a->mb_hint, B * A, a->cfg.hint_threshold, a->admm_rho, a->rho, a->hint_out, 0);
+    LAUNCH_OK(a);
+  }
+  k_actor_loss<<<1, 256, 0, a->st>>>(a->logp, a->qmin, B, alpha, hint ? a->hint_out : nullptr, a->stats + 2);
+  LAUNCH_OK(a);
+  {
+    TrunkWs& t = a->ws[3];
+    k_actor_head_bwd<<<B, 128, 0, a->st>>>(a->dact, a->pi, a->sig, a->raw, a->eps_cur, a->mu, a->u, a->mb_hint, hint ? a->hint_out : nullptr, alpha / (float)B, A,
+                                           PA.mu_w, PA.sg_w, a->x21, a->dmu, a->draw, a->dpre);
+    LAUNCH_OK(a);
+    // heads
+    if ((rc = sgemm(a, a->dmu, 1, A, a->x21, HID, 1, GA.mu_w, HID, A, HID, B, nullptr, -1))) return rc;
+    if ((rc = colsum(a, a->dmu, A, nullptr, B, A, GA.mu_b))) return rc;
+    if ((rc = sgemm(a, a->draw, 1, A, a->x21, HID, 1, GA.sg_w, HID, A, HID, B, nullptr, -1))) return rc;
+    if ((rc = colsum(a, a->draw, A, nullptr, B, A, GA.sg_b))) return rc;
+    // fc21: dW = dpre^T feat, db = colsum(dpre), dfeat = dpre W
+    if ((rc = sgemm(a, a->dpre, 1, HID, t.feat, FEAT, 1, GA.h_w, FEAT, HID, FEAT, B, nullptr, -1))) return rc;
+    if ((rc = colsum(a, a->dpre, HID, nullptr, B, HID, GA.h_b))) return rc;
+    if ((rc = sgemm(a, a->dpre, HID, 1, PA.h_w, FEAT, 1, a->dfeat, FEAT, B, FEAT, HID, nullptr, -1))) return rc;
+    k_side_bwd<<<B, 128, 0, a->st>>>(a->dfeat + FLAT, FEAT, t.o16, t.h1, PA.fb_w, PA.fa_w, SKY, SKY, 0, a->d16, a->dh1, nullptr, 0);
+    LAUNCH_OK(a);
+    if ((rc = side_wgrads(a, t.x1, t.h1, SKY, GA))) return rc;
+    if ((rc = trunk_backward(a, t, PA, GA, a->mb_img, ACT_ELU))) return rc;
+  }
+  a->t_actor++;
+  if ((rc = adam_step(a, 0, a->cfg.lr_actor, a->t_actor))) return rc;
+  if (dual) {       // calib_sac.py:360-364: rho += admm_rho * g, g recomputed from the SAME actions
+    k_kld_coef<<<1, 256, 0, a->st>>>(a->pi, a->mb_hint, B * A, a->cfg.hint_threshold, a->admm_rho, a->rho, a->hint_out, 1);
+    LAUNCH_OK(a);
+  }
+  a->learn_counter++;
+  if ((rc = sc_calib_soft_update(a, (float)a->cfg.tau))) return rc;
+  a->batch_ready = false;
+  if (stats) {
+    CKC(cudaMemcpyAsync(a->h_stats, a->stats, 8 * sizeof(float), cudaMemcpyDeviceToHost, a->st));
+    CKC(cudaMemcpyAsync(a->h_stats + 8, a->hint_out, 4 * sizeof(float), cudaMemcpyDeviceToHost, a->st));
+    CKC(cudaMemcpyAsync(a->h_stats + 12, a->rho, sizeof(float), cudaMemcpyDeviceToHost, a->st));
+    CKC(cudaStreamSynchronize(a->st));
+    stats->critic_1_loss = a->h_stats[0]; stats->critic_2_loss = a->h_stats[1]; stats->actor_loss = a->h_stats[2];
+    stats->logp_mean = a->h_stats[3];
+    stats->gfun = hint ? a->h_stats[9] : 0.f;
+    stats->rho = a->h_stats[12];
+    stats->learn_counter = (int32_t)a->learn_counter;
+    stats->did_learn = 1;
+    stats->actor_step = 1;
+  }
+  return SC_OK;
+}
+
+}  // extern "C"
