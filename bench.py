@@ -320,6 +320,75 @@ def gpu_eager_baseline(steps=200, warmup=20):
                     f"reference), {steps} steps, wall clock"}
 
 
+def run_calib(args):
+    """BASELINE.json configs[2]: calibration conv-SAC (calibration/calib_sac.py), batch 256, M = 10 (n_actions 20), synthetic
+    influence-map images (1,128,128) + sky tables.  One extra JSON line; not the headline metric."""
+    from smartcal_b200.calibration import calib_sac
+    from smartcal_b200.synth import make_calib_transitions
+    M, Bc, Cc = 10, 256, 512
+    A = 2 * M
+    hp = dict(gamma=0.99, batch_size=Bc, n_actions=A, tau=0.005, max_mem_size=Cc, input_dims=[1, 128, 128], M=M, lr_a=1e-3, lr_c=1e-3,
+              reward_scale=M, alpha=0.03, hint_threshold=0.01, admm_rho=1.0, use_hint=False)
+    steps, warmup = min(args.steps, 50), max(3, min(args.warmup, 5))
+    torch.manual_seed(0)
+    np.random.seed(0)
+    agent = calib_sac.Agent(**hp, rng="device")
+    tr = make_calib_transitions(100, Cc, M, A, 128, 0.0)
+    dev = agent._dev
+    for name, key in (("state_memory_img", "img"), ("new_state_memory_img", "img2"), ("state_memory_sky", "sky"), ("new_state_memory_sky", "sky2"),
+                      ("action_memory", "action"), ("hint_memory", "hint")):
+        dev.buffer(name).copy_(torch.as_tensor(tr[key].reshape(Cc, -1)).to(dev.device))
+    dev.buffer("reward_memory").copy_(torch.as_tensor(tr["reward"].reshape(Cc, 1)).to(dev.device))
+    dev.set_counters(Cc, 0)
+    rs = np.random.RandomState(1)
+
+    def step():
+        dev.set_batch(rs.choice(Cc, Bc, replace=False))
+        dev.learn()
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    l0 = dev.launch_count()
+    mon = ClockSampler(torch.cuda.current_device())
+    mon.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    st = torch.cuda.current_stream()
+    for e0, e1 in evs:
+        e0.record(st)
+        step()
+        e1.record(st)
+    torch.cuda.synchronize()
+    clocks = mon.stop()
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    launches = dev.launch_count() - l0
+    # CPU oracle (reference op sequence) on a bounded sample
+    from oracle.calib_ref import CalibSacRef
+    torch.manual_seed(0)
+    orc = CalibSacRef(**hp)
+    for i in range(Cc):
+        orc.replay.store(tr["img"][i], tr["sky"][i], tr["action"][i], float(tr["reward"][i]), tr["img2"][i], tr["sky2"][i], False, tr["hint"][i])
+    best = None
+    for nt in (8, 16, 32):
+        if nt > (os.cpu_count() or 1):
+            continue
+        torch.set_num_threads(nt)
+        orc.learn()
+        t0 = time.perf_counter()
+        orc.learn()
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[1]:
+            best = (nt, dt)
+    flop = 119e9      # SURVEY section 8d: ~14 trunk passes x 33 MFLOP x 256
+    print(json.dumps({"metric": "calibration conv-SAC learn() steps/sec (batch=256)", "value": steps / (ms * 1e-3), "unit": "learn steps/s",
+                      "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "dtype": "f32",
+                      "data": "synthetic", "config": {"workload": "calibration conv-SAC Agent.learn(): img (256,1,128,128), sky (256,11,7), A=20, "
+                                                       "M=10, replay 512 (BASELINE.json configs[2]); inputs (67 MB of images per step) exceed L2 reuse"},
+                      "gpu_launches": int(launches), "achieved_tflops_fp32": flop / (ms / steps * 1e-3) / 1e12,
+                      "cpu_baseline": {"value": 1.0 / best[1], "unit": "learn steps/s", "cores": best[0], "kind": "port",
+                                       "sample": f"1 learn() step of the same workload after 1 warm-up (oracle/calib_ref.py, torch CPU, {best[0]} threads)"},
+                      "clocks": clocks}))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -351,8 +420,12 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="enet", choices=["enet", "calib"],
+                    help="enet: the headline elastic-net SAC workload (BASELINE.json configs[1]); calib: configs[2], conv SAC")
     a = ap.parse_args()
-    if a.impl == "reference":
+    if a.workload == "calib":
+        run_calib(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

@@ -382,6 +382,7 @@ struct sc_calib {
   float *bn_c1, *bn_c2;               // BN backward per-channel means
   double* red_partial;                // [32][NCH][2]
   float* wg_partial;
+  float* splitk;                      // [32][B][128] split-K partials of the fc21 forward GEMM
   float *stats, *rho, *hint_out;
   float* h_stage;                     // pinned host staging
   float* h_stats;
@@ -485,6 +486,7 @@ static size_t carve_c(sc_calib* a, char* base) {
   a->bn_c1 = cv.f(32); a->bn_c2 = cv.f(32);
   a->red_partial = (double*)cv.take(sizeof(double) * 32 * 64 * 2);
   a->wg_partial = cv.f((size_t)a->wg_blocks * C3 * C2 * TAPS);
+  a->splitk = cv.f((size_t)32 * B * HID);
   a->stats = cv.f(16); a->rho = cv.f(4); a->hint_out = cv.f(4);
   return cv.off;
 }
@@ -561,7 +563,17 @@ static int trunk_forward(sc_calib* a, TrunkWs& t, const NetP& P, int net, const 
 
 static int sgemm(sc_calib* a, const float* A_, long sam, long sak, const float* B_, long sbk, long sbn, float* C_, long ldc, int M, int N, int K,
                  const float* bias, int act) {
-  k_sgemm<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, a->st>>>(A_, sam, sak, B_, sbk, sbn, C_, ldc, M, N, K, bias, act);
+  const int tiles = ((N + 63) / 64) * ((M + 63) / 64);
+  if (tiles < 32 && K >= 2048 && (size_t)M * N <= (size_t)a->B * HID) {
+    // skinny output, long reduction (fc21 forward: 256 x 128 x 5424): split K over the grid, then add the slices in order
+    const int nz = 32, kslice = ((K + nz * 16 - 1) / (nz * 16)) * 16;
+    k_sgemm<<<dim3((N + 63) / 64, (M + 63) / 64, nz), 256, 0, a->st>>>(A_, sam, sak, B_, sbk, sbn, a->splitk, N, M, N, K, nullptr, -1, kslice);
+    LAUNCH_OK(a);
+    k_splitk_reduce<<<(M * N + 255) / 256, 256, 0, a->st>>>(a->splitk, nz, M, N, bias, act, C_, ldc);
+    LAUNCH_OK(a);
+    return SC_OK;
+  }
+  k_sgemm<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, a->st>>>(A_, sam, sak, B_, sbk, sbn, C_, ldc, M, N, K, bias, act, K);
   LAUNCH_OK(a);
   return SC_OK;
 }

@@ -481,8 +481,11 @@ __global__ void k_bias_grad_finalize(const double* __restrict__ partial, int nch
 // generic strided FP32 GEMM for the dense layers: C[m][n] (+)= sum_k A(m,k) B(k,n), A(m,k) = A[m*sam + k*sak],
 // B(k,n) = B[k*sbk + n*sbn].  64 x 64 tiles, 16-wide k slabs, 4 x 4 outputs per thread.
 // =====================================================================================================================
+// With gridDim.z > 1 the reduction axis is cut into gridDim.z slices of `kslice` (a multiple of 16) and slice z writes its
+// partial product to Cm + z * M * ldc (no bias / activation); k_splitk_reduce adds the slices in order.
 __global__ void __launch_bounds__(256) k_sgemm(const float* __restrict__ A, long sam, long sak, const float* __restrict__ Bm, long sbk, long sbn,
-                                               float* __restrict__ Cm, long ldc, int M, int N, int K, const float* __restrict__ bias_n, int act) {
+                                               float* __restrict__ Cm, long ldc, int M, int N, int K, const float* __restrict__ bias_n, int act,
+                                               int kslice) {
   __shared__ float sA[16][64 + 4];
   __shared__ float sB[16][64 + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -492,7 +495,10 @@ __global__ void __launch_bounds__(256) k_sgemm(const float* __restrict__ A, long
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  const int kbeg = blockIdx.z * kslice, kend = min(K, kbeg + kslice);
+  Cm += (size_t)blockIdx.z * M * ldc;
+  K = kend;
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
     for (int i = tid; i < 16 * 64; i += 256) {
       int kk, mm;
       if (sak == 1) { kk = i & 15; mm = i >> 4; } else { mm = i & 63; kk = i >> 6; }     // walk the contiguous axis fastest
@@ -531,6 +537,19 @@ __global__ void __launch_bounds__(256) k_sgemm(const float* __restrict__ A, long
       Cm[(long)m * ldc + n] = v;
     }
   }
+}
+
+// C[m][n] = act(bias[n] + sum_z partial[z][m][n])
+__global__ void k_splitk_reduce(const float* __restrict__ partial, int nz, int M, int N, const float* __restrict__ bias_n, int act,
+                                float* __restrict__ Cm, long ldc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  const int m = i / N, n = i - m * N;
+  float s = 0.f;
+  for (int z = 0; z < nz; ++z) s += partial[((size_t)z * M + m) * N + n];
+  s += bias_n ? __ldg(bias_n + n) : 0.f;
+  if (act >= 0) s = act_fwd(s, act);
+  Cm[(long)m * ldc + n] = s;
 }
 
 // out[n] = sum_b w[b] * X[b][n]  (w == nullptr: plain column sum); one thread per column, fixed order
