@@ -162,6 +162,8 @@ struct KernelTimer {
 struct sc_agent {
   sc_config cfg;
   cudaStream_t st;
+  cudaStream_t st_side;              // PER tree update runs here, overlapped with the weight-gradient / actor kernels
+  cudaEvent_t ev_fork, ev_join;
   void* arena;
   bool owns_arena;
   size_t arena_bytes;
@@ -589,6 +591,10 @@ int sc_agent_create(const sc_config* cfg, void* arena, size_t arena_bytes, void*
   sc_agent* a = new sc_agent();
   init_dims(a, cfg);
   a->st = (cudaStream_t)cuda_stream;
+  a->st_side = nullptr; a->ev_fork = a->ev_join = nullptr;
+  CK(cudaStreamCreateWithFlags(&a->st_side, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&a->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&a->ev_join, cudaEventDisableTiming));
   const size_t need = carve(a, nullptr);
   if (arena) {
     if (arena_bytes < need) { delete a; return fail(SC_ERR_ARG, "arena too small: %zu < %zu", arena_bytes, need); }
@@ -673,6 +679,9 @@ int sc_agent_destroy(sc_agent* a) {
     for (auto& p : t.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto& p : t.pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   }
+  if (a->st_side) { cudaStreamSynchronize(a->st_side); cudaStreamDestroy(a->st_side); }
+  if (a->ev_fork) cudaEventDestroy(a->ev_fork);
+  if (a->ev_join) cudaEventDestroy(a->ev_join);
   if (a->h_stage) cudaFreeHost(a->h_stage);
   if (a->h_stats) cudaFreeHost(a->h_stats);
   if (a->h_idx) cudaFreeHost(a->h_idx);
@@ -1038,11 +1047,22 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
     p.td3_noise_c = (float)nz;
   }
   if ((rc = run_rowphase(a, p, 0))) return rc;
+  bool per_forked = false;
   if (per) {
-    cudaEvent_t e0, e1;
-    timer_begin(a, 5, &e0, &e1);
-    CK(launch_per_update(a->rp.tree, a->C, a->B, a->tree_idx, a->err, a->cfg.per_clip, nullptr, a->ps_out, a->st));
-    timer_end(a, 5, e0, e1);
+    // PER.batch_update only depends on the priorities written by the critic row-phase and is only consumed by the NEXT
+    // sample: it runs on a side stream under the weight-gradient / actor kernels and is joined at the end of learn()
+    if (a->timing) {
+      cudaEvent_t e0, e1;
+      timer_begin(a, 5, &e0, &e1);
+      CK(launch_per_update(a->rp.tree, a->C, a->B, a->tree_idx, a->err, a->cfg.per_clip, nullptr, a->ps_out, a->st));
+      timer_end(a, 5, e0, e1);
+    } else {
+      CK(cudaEventRecord(a->ev_fork, a->st));
+      CK(cudaStreamWaitEvent(a->st_side, a->ev_fork, 0));
+      CK(launch_per_update(a->rp.tree, a->C, a->B, a->tree_idx, a->err, a->cfg.per_clip, nullptr, a->ps_out, a->st_side));
+      CK(cudaEventRecord(a->ev_join, a->st_side));
+      per_forked = true;
+    }
     a->launches++;
   }
   bool actor_step = true;
@@ -1099,6 +1119,7 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
       a->launches++;
     }
   }
+  if (per_forked) CK(cudaStreamWaitEvent(a->st, a->ev_join, 0));     // join: later work on the agent's stream sees the updated tree
   a->learn_counter++;
   if (stats_host) {
     CK(cudaMemcpyAsync(a->h_stats, a->stats, 16 * sizeof(float), cudaMemcpyDeviceToHost, a->st));
