@@ -170,3 +170,63 @@ def test_calib_against_reference_golden():
             assert int(sd[f"bn{l}.num_batches_tracked"]) == int(z[f"step0/{nm}/bn{l}.num_batches_tracked/p"][0])
             ref, got = z[f"step0/{nm}/bn{l}.running_var/p"], digest(sd[f"bn{l}.running_var"])
             assert np.max(np.abs(got - ref)) <= 1e-4 * np.max(np.abs(ref)), f"{nm}.bn{l}.running_var"
+
+
+def test_calib_config3_dimensions_one_step():
+    """BASELINE.json configs[2] dimensions (M=10: sky 11x7, 20 actions, fc1 in 97 wide) at a batch the CPU oracle finishes quickly"""
+    M, A, B, C, seed = 10, 20, 32, 64, 33
+    agent, orc, tr = build(M, A, B, C, seed, True, 0.1)
+    dev = agent._dev
+    rs = np.random.RandomState(seed + 1)
+    idx = rs.choice(C, B, replace=False)
+    e1, e2 = rs.standard_normal((B, A)).astype(np.float32), rs.standard_normal((B, A)).astype(np.float32)
+    dev.set_batch(idx)
+    st = dev.learn(e1, e2, want_stats=True)
+    res = orc.learn_on_batch(orc.replay.gather(idx), e1, e2)
+    for name, key in (("y", "y"), ("q1", "q1"), ("q2", "q2"), ("pi", "pi"), ("logp", "logp"), ("q1_pi", "q1_pi"), ("q2_pi", "q2_pi")):
+        assert rel(dev.buffer(name).cpu().numpy(), res[key].numpy()) < 3e-5, name
+    np.testing.assert_allclose([st["critic_1_loss"], st["critic_2_loss"], st["actor_loss"], st["gfun"]],
+                               [res["critic_1_loss"], res["critic_2_loss"], res["actor_loss"], res["gfun"]], rtol=2e-4, atol=1e-7)
+    sg_dev, sg_orc = dev.buffer("sigma").cpu().numpy().astype(np.float64), res["sigma"].numpy().astype(np.float64)
+    sig_amp = float(np.max(np.abs(sg_dev - sg_orc) / sg_orc))
+    for nm, gkey in (("critic_1", "grad_c1"), ("critic_2", "grad_c2"), ("actor", "grad_a")):
+        got = getattr(agent, nm).grads()
+        rtol = 3e-5 if nm != "actor" else max(3e-5, 3.0 * sig_amp)
+        for k, g in res[gkey].items():
+            if k.startswith("conv") and k.endswith(".bias"):
+                continue
+            gd, gr = got[k].cpu().numpy().reshape(-1), g.numpy().reshape(-1)
+            assert np.max(np.abs(gd - gr)) <= rtol * np.max(np.abs(gr)) + 1e-9, f"grad {nm}.{k}"
+
+
+def test_calib_facade_api_roundtrip(tmp_path, monkeypatch):
+    """the calls calibration/main_sac.py makes: choose_action / store_transition / learn / save_models / load_models"""
+    from smartcal_b200.calibration import calib_sac
+    monkeypatch.chdir(tmp_path)
+    M, A, B, C = 3, 6, 4, 8
+    torch.manual_seed(5)
+    np.random.seed(5)
+    agent = calib_sac.Agent(gamma=0.99, batch_size=B, n_actions=A, tau=0.005, max_mem_size=C, input_dims=[1, 128, 128], M=M, lr_a=1e-3,
+                            lr_c=1e-3, reward_scale=M, alpha=0.03, hint_threshold=0.01, admm_rho=1.0, use_hint=True)
+    tr = make_calib_transitions(9, C + 2, M, A, 128, 0.0)
+    for i in range(C + 2):                                # wraps the ring
+        obs, obs_ = {"img": tr["img"][i], "sky": tr["sky"][i]}, {"img": tr["img2"][i], "sky": tr["sky2"][i]}
+        action = agent.choose_action(obs)
+        assert action.shape == (A,) and np.all(np.abs(action) <= 1.0)
+        agent.store_transition(obs, action, float(tr["reward"][i]), obs_, False, tr["hint"][i])
+        agent.learn()
+    assert agent.replaymem.mem_cntr == C + 2 and agent.learn_counter == C + 2 - (B - 1)
+    np.testing.assert_array_equal(agent.replaymem.state_memory_img[1], tr["img"][C + 1])          # slot 1 was overwritten on wrap
+    assert float(agent.rho) >= 0.0
+    before = {k: v.clone() for k, v in agent.actor.state_dict().items()}
+    agent.save_models()
+    assert os.path.exists("a_eval_sac_actor.model") and os.path.exists("q_eval_2_sac_critic.model") and os.path.exists("replaymem_sac.model")
+    sd = torch.load("a_eval_sac_actor.model")
+    assert list(sd.keys()) == list(before.keys()) and tuple(sd["conv2.weight"].shape) == (32, 16, 5, 5)
+    agent.actor.load_state_dict({k: torch.zeros_like(v) for k, v in before.items()})
+    agent.load_models()
+    for k, v in agent.actor.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    for k, v in agent.target_critic_1.state_dict().items():
+        if "running" not in k and "num_batches" not in k:
+            assert torch.equal(v, agent.critic_1.state_dict()[k]), k        # load_models hard-copies the targets (calib_sac.py:398-399)
