@@ -1,0 +1,47 @@
+// Host-side launch helpers shared by the two build configurations of the row-phase kernel (sc_rowphase_occ{1,2}.cu).
+#pragma once
+#include "sc_common.cuh"
+#include "sc_params.h"
+
+namespace sc {
+
+template <typename K>
+static cudaError_t configure(K kern, size_t smem, int cs) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess && cs > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  return e;
+}
+static void cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int nclusters, int cs, size_t smem, cudaStream_t st) {
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3(nclusters * cs, 1, 1);
+  cfg.blockDim = dim3(SC_ROW_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+}
+template <typename K>
+static cudaError_t launch_k(K kern, size_t smem, const RowPhaseParams& p, int cs, int nclusters, cudaStream_t st) {
+  cudaError_t e = configure(kern, smem, cs);          // idempotent and cheap
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  cluster_cfg(cfg, attr, nclusters, cs, smem, st);
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+template <typename K>
+static int max_clusters(K kern, size_t smem, int cs) {
+  if (configure(kern, smem, cs) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  cluster_cfg(cfg, attr, 64, cs, smem, nullptr);
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+}  // namespace sc
