@@ -22,6 +22,7 @@ void rowphase_cluster_capacity(int* out4);
 cudaError_t launch_rowphase(const RowPhaseParams& p, int variant, int cluster_size, int nclusters, int tm, cudaStream_t st);
 size_t wgrad_smem_bytes();
 cudaError_t launch_wgrad(const WgradParams& p, int grid, cudaStream_t st);
+cudaError_t launch_wgrad_tc(const WgradTcParams& p, int grid, cudaStream_t st);
 cudaError_t launch_soft_update(const float* src, float* dst, size_t n, float tau, cudaStream_t st);
 cudaError_t launch_replay_store(const ReplayP& rp, const float* tr, int slot, int mode, double priority, double clip, cudaStream_t st);
 cudaError_t launch_replay_fill(const ReplayP& rp, const float* tr, int n, cudaStream_t st);
@@ -163,7 +164,8 @@ struct sc_agent {
   sc_config cfg;
   cudaStream_t st;
   cudaStream_t st_side;              // PER tree update runs here, overlapped with the weight-gradient / actor kernels
-  cudaEvent_t ev_fork, ev_join;
+  cudaStream_t st_side2;             // narrow-layer weight gradients run here next to the tensor-core kernel
+  cudaEvent_t ev_fork, ev_join, ev_fork2, ev_join2;
   void* arena;
   bool owns_arena;
   size_t arena_bytes;
@@ -189,6 +191,12 @@ struct sc_agent {
   float *obs_dev, *act_eps, *act_out, *act_aux, *store_stage;
   WgradOp *critic_ops, *actor_ops;
   int *critic_tile_map, *actor_tile_map;
+  // wide layers on tcgen05 (sc_wgrad_tc.cu): op tables, tile maps, tensor maps
+  WgradTcOp *critic_tc_ops, *actor_tc_ops;
+  int *critic_tc_map, *actor_tc_map;
+  int n_critic_tc, n_actor_tc, critic_tc_tiles, actor_tc_tiles;
+  unsigned char* tmaps_tc;
+  bool use_tc;
   VecOp *critic_vops, *actor_vops;
   int n_critic_ops, n_critic_vops, n_actor_ops, n_actor_vops, critic_tiles, actor_tiles;
   // pinned host staging
@@ -198,7 +206,7 @@ struct sc_agent {
   double* h_u01;
   float* h_act;
   // state
-  int row_variant, cluster_size, nclusters, tile_tm, wgrad_grid;
+  int row_variant, cluster_size, nclusters, tile_tm, wgrad_grid, sm_count;
   int64_t mem_cntr, learn_counter, data_pointer, data_length;
   int64_t t_actor, t_critic;          // Adam step counts
   double per_beta;
@@ -320,6 +328,11 @@ static size_t carve(sc_agent* a, void* base) {
   a->store_stage = cv.f((size_t)a->T * 1);
   a->tstamp = (unsigned long long*)cv.take(sizeof(unsigned long long) * 8 * 3072);
   reg("debug_ts", a->tstamp, 3072, 8, 8, 8);
+  a->critic_tc_ops = (WgradTcOp*)cv.take(sizeof(WgradTcOp) * 8);
+  a->actor_tc_ops = (WgradTcOp*)cv.take(sizeof(WgradTcOp) * 8);
+  a->critic_tc_map = (int*)cv.take(sizeof(int) * 512);
+  a->actor_tc_map = (int*)cv.take(sizeof(int) * 512);
+  a->tmaps_tc = (unsigned char*)cv.take(128 * 32);
   a->critic_ops = (WgradOp*)cv.take(sizeof(WgradOp) * 16);
   a->actor_ops = (WgradOp*)cv.take(sizeof(WgradOp) * 8);
   a->critic_vops = (VecOp*)cv.take(sizeof(VecOp) * 32);
@@ -369,8 +382,14 @@ size_t sc_agent_arena_bytes(const sc_config* cfg) {
   return carve(&tmp, nullptr);
 }
 
+struct TcCand { const float* D; int ldd; const float* X; int ldx; int N, K; float *W, *M, *V, *T; int ldw, opt; };
+static std::vector<TcCand>* g_tc_sink = nullptr;      // when set, wide ops are routed to the tcgen05 kernel instead of the FFMA tile list
 static void add_w(std::vector<WgradOp>& v, int& tiles, const float* D, int ldd, const float* X, int ldx, int gather, int N, int K,
                   float* W, float* M, float* V, float* T, int ldw, int opt) {
+  if (g_tc_sink != nullptr && !gather && N % 128 == 0 && K >= 64 && (ldd & 3) == 0 && (ldx & 3) == 0 && (ldw & 3) == 0) {
+    g_tc_sink->push_back(TcCand{D, ldd, X, ldx, N, K, W, M, V, T, ldw, opt});
+    return;
+  }
   WgradOp o;
   o.D = D; o.ldd = ldd; o.X = X; o.ldx = ldx; o.gather = gather; o.N = N; o.K = K;
   o.W = W; o.M = M; o.V = V; o.T = T; o.ldw = ldw;
@@ -407,7 +426,7 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 // row-major float matrix [rows][ld] (ld a multiple of 32), box {32 floats = 128 B, box_rows}, 128-byte swizzle
-static int encode_map(CUtensorMap* out, const void* base, int ld, int rows, int box_rows) {
+static int encode_map(CUtensorMap* out, const void* base, int ld, int rows, int box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(SC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
@@ -415,7 +434,7 @@ static int encode_map(CUtensorMap* out, const void* base, int ld, int rows, int 
   cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SC_ERR_CUDA, "cuTensorMapEncodeTiled(ld=%d rows=%d box_rows=%d) failed: %d", ld, rows, box_rows, (int)r);
   return SC_OK;
 }
@@ -482,11 +501,51 @@ static int build_tensor_maps(sc_agent* a) {
   return SC_OK;
 }
 
+// tcgen05 weight-gradient tables: tensor maps (ATOM_32B swizzle, boxes of 32 batch rows x 32 floats), op list, tile map
+static int upload_tc_tables(sc_agent* a, const std::vector<TcCand>& cand, WgradTcOp* dev_ops, int* dev_map, int& nops, int& ntiles,
+                            std::vector<CUtensorMap>& maps) {
+  std::vector<WgradTcOp> ops;
+  std::vector<int> tmap;
+  int tiles = 0;
+  for (const TcCand& c : cand) {
+    WgradTcOp o;
+    alignas(64) CUtensorMap md, mx;
+    int rc = encode_map(&md, c.D, c.ldd, a->B, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc == SC_OK) rc = encode_map(&mx, c.X, c.ldx, a->B, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc != SC_OK) return rc;
+    maps.push_back(md);
+    o.mapD = a->tmaps_tc + (maps.size() - 1) * sizeof(CUtensorMap);
+    maps.push_back(mx);
+    o.mapX = a->tmaps_tc + (maps.size() - 1) * sizeof(CUtensorMap);
+    o.N = c.N; o.K = c.K; o.W = c.W; o.M = c.M; o.V = c.V; o.T = c.T; o.ldw = c.ldw; o.opt = c.opt;
+    o.tiles_k = (c.K + 63) / 64;
+    o.tile_base = tiles;
+    o.tile_count = (c.N / 128) * o.tiles_k;
+    for (int t = 0; t < o.tile_count; ++t) tmap.push_back((int)ops.size());
+    tiles += o.tile_count;
+    ops.push_back(o);
+  }
+  if (ops.size() > 8 || tiles > 512 || maps.size() > 32) return fail(SC_ERR_STATE, "tcgen05 wgrad table overflow");
+  nops = (int)ops.size(); ntiles = tiles;
+  if (!ops.empty()) {
+    CK(cudaMemcpyAsync(dev_ops, ops.data(), ops.size() * sizeof(WgradTcOp), cudaMemcpyHostToDevice, a->st));
+    CK(cudaMemcpyAsync(dev_map, tmap.data(), tmap.size() * sizeof(int), cudaMemcpyHostToDevice, a->st));
+    CK(cudaStreamSynchronize(a->st));
+  }
+  return SC_OK;
+}
+
 static int build_op_tables(sc_agent* a) {
   const bool td3 = a->cfg.kind == SC_KIND_TD3;
   std::vector<WgradOp> cw;
   std::vector<VecOp> cv;
   int tiles = 0;
+  // wide layers go to the tensor-core kernel unless SMARTCAL_WGRAD=ffma pins the FP32 tile kernel (A/B comparisons)
+  const char* wg = getenv("SMARTCAL_WGRAD");
+  a->use_tc = !(wg && !strcmp(wg, "ffma"));
+  std::vector<TcCand> tc_critic, tc_actor;
+  std::vector<CUtensorMap> tc_maps;
+  g_tc_sink = a->use_tc ? &tc_critic : nullptr;
   for (int k = 0; k < 2; ++k) {
     const size_t off = k == 0 ? a->off_c1 : a->off_c2;
     const size_t toff = k == 0 ? a->toff_c1 : a->toff_c2;
@@ -514,6 +573,7 @@ static int build_op_tables(sc_agent* a) {
     add_v(cv, tiles, w.du22, nullptr, HA2, HA2, P.be22, M.be22, V.be22, T.be22, opt);
     add_v(cv, tiles, w.dq, nullptr, 1, 1, P.b3, M.b3, V.b3, T.b3, opt);
   }
+  g_tc_sink = a->use_tc ? &tc_actor : nullptr;
   a->n_critic_ops = (int)cw.size(); a->n_critic_vops = (int)cv.size(); a->critic_tiles = tiles;
   auto tile_table = [](const std::vector<WgradOp>& w, const std::vector<VecOp>& v, int total) {
     std::vector<int> t(total, -1);
@@ -560,7 +620,17 @@ static int build_op_tables(sc_agent* a) {
     add_v(avv, tiles, w.dhead, nullptr, ldh, A, P.bmu, M.bmu, V.bmu, T.bmu, 0);
     if (!td3) add_v(avv, tiles, w.dhead + A, nullptr, ldh, A, P.bls, M.bls, V.bls, T.bls, 0);
   }
+  g_tc_sink = nullptr;
   a->n_actor_ops = (int)awv.size(); a->n_actor_vops = (int)avv.size(); a->actor_tiles = tiles;
+  {
+    int rc = upload_tc_tables(a, tc_critic, a->critic_tc_ops, a->critic_tc_map, a->n_critic_tc, a->critic_tc_tiles, tc_maps);
+    if (rc == SC_OK) rc = upload_tc_tables(a, tc_actor, a->actor_tc_ops, a->actor_tc_map, a->n_actor_tc, a->actor_tc_tiles, tc_maps);
+    if (rc != SC_OK) return rc;
+    if (!tc_maps.empty()) {
+      CK(cudaMemcpyAsync(a->tmaps_tc, tc_maps.data(), tc_maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, a->st));
+      CK(cudaStreamSynchronize(a->st));
+    }
+  }
   if (tiles > 2048) return fail(SC_ERR_STATE, "actor tile table overflow (%d)", tiles);
   {
     std::vector<int> tt = tile_table(awv, avv, tiles);
@@ -591,10 +661,14 @@ int sc_agent_create(const sc_config* cfg, void* arena, size_t arena_bytes, void*
   sc_agent* a = new sc_agent();
   init_dims(a, cfg);
   a->st = (cudaStream_t)cuda_stream;
-  a->st_side = nullptr; a->ev_fork = a->ev_join = nullptr;
+  a->st_side = nullptr; a->ev_fork = a->ev_join = a->ev_fork2 = a->ev_join2 = nullptr;
   CK(cudaStreamCreateWithFlags(&a->st_side, cudaStreamNonBlocking));
+  a->st_side2 = nullptr;
+  CK(cudaStreamCreateWithFlags(&a->st_side2, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&a->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&a->ev_join, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&a->ev_fork2, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&a->ev_join2, cudaEventDisableTiming));
   const size_t need = carve(a, nullptr);
   if (arena) {
     if (arena_bytes < need) { delete a; return fail(SC_ERR_ARG, "arena too small: %zu < %zu", arena_bytes, need); }
@@ -654,6 +728,7 @@ int sc_agent_create(const sc_config* cfg, void* arena, size_t arena_bytes, void*
   }
   if (a->cluster_size == 0) { sc_agent_destroy(a); return fail(SC_ERR_CUDA, "device cannot host an 8-CTA cluster with %zu B of shared memory", rowphase_smem_bytes(2)); }
   a->wgrad_grid = prop.multiProcessorCount * 2;
+  a->sm_count = prop.multiProcessorCount;
   a->mem_cntr = a->learn_counter = a->data_pointer = a->data_length = 0;
   a->t_actor = a->t_critic = 0;
   a->per_beta = 0.4;   // PER.beta, enet_sac.py:210
@@ -680,8 +755,11 @@ int sc_agent_destroy(sc_agent* a) {
     for (auto& p : t.pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   }
   if (a->st_side) { cudaStreamSynchronize(a->st_side); cudaStreamDestroy(a->st_side); }
+  if (a->st_side2) { cudaStreamSynchronize(a->st_side2); cudaStreamDestroy(a->st_side2); }
   if (a->ev_fork) cudaEventDestroy(a->ev_fork);
   if (a->ev_join) cudaEventDestroy(a->ev_join);
+  if (a->ev_fork2) cudaEventDestroy(a->ev_fork2);
+  if (a->ev_join2) cudaEventDestroy(a->ev_join2);
   if (a->h_stage) cudaFreeHost(a->h_stage);
   if (a->h_stats) cudaFreeHost(a->h_stats);
   if (a->h_idx) cudaFreeHost(a->h_idx);
@@ -943,9 +1021,37 @@ static int run_rowphase(sc_agent* a, const RowPhaseParams& p, int timer_id) {
 static int run_wgrad(sc_agent* a, const WgradParams& w, int timer_id) {
   cudaEvent_t e0, e1;
   timer_begin(a, timer_id, &e0, &e1);
+  const bool actor = w.ops == a->actor_ops;
+  const int tc_tiles = actor ? a->actor_tc_tiles : a->critic_tc_tiles;
   int grid = a->wgrad_grid;
   if (grid > w.total_tiles + 1) grid = w.total_tiles + 1;
-  CK(launch_wgrad(w, grid, a->st));
+  if (tc_tiles > 0) {
+    WgradTcParams t;
+    memset(&t, 0, sizeof(t));
+    t.ops = actor ? a->actor_tc_ops : a->critic_tc_ops;
+    t.nops = actor ? a->n_actor_tc : a->n_critic_tc;
+    t.total_tiles = tc_tiles;
+    t.tile_map = actor ? a->actor_tc_map : a->critic_tc_map;
+    t.B = a->B;
+    for (int i = 0; i < 3; ++i) t.hyper[i] = w.hyper[i];
+    t.tau = w.tau; t.one_minus_tau = w.one_minus_tau; t.do_soft = w.do_soft;
+    t.tl = (getenv("SMARTCAL_STAMPS") && !actor) ? a->tstamp + 2304 * 8 : nullptr;
+    // the wide layers (tensor-core kernel, <= 88 CTAs of one SM each) and the narrow layers + vector parameters + loss
+    // readout (FP32 tile kernel) are independent: the second runs on the side stream next to the first
+    const bool fork = !a->timing;
+    if (fork) {
+      CK(cudaEventRecord(a->ev_fork2, a->st));
+      CK(cudaStreamWaitEvent(a->st_side2, a->ev_fork2, 0));
+      CK(launch_wgrad(w, grid, a->st_side2));
+      CK(cudaEventRecord(a->ev_join2, a->st_side2));
+    }
+    CK(launch_wgrad_tc(t, tc_tiles < a->sm_count ? tc_tiles : a->sm_count, a->st));
+    a->launches++;
+    if (fork) CK(cudaStreamWaitEvent(a->st, a->ev_join2, 0));
+    else CK(launch_wgrad(w, grid, a->st));
+  } else {
+    CK(launch_wgrad(w, grid, a->st));
+  }
   timer_end(a, timer_id, e0, e1);
   a->launches++;
   return SC_OK;

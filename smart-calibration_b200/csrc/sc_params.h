@@ -117,6 +117,15 @@ struct WgradOp {
   int tile_base, tile_count;       // position in the flat tile list
   int opt;                         // index into AdamHyper[3] (0 actor, 1 critic_1, 2 critic_2)
 };
+struct WgradTcOp {                 // wide-layer weight gradient on tcgen05 (sc_wgrad_tc.cu): 128 (n) x 64 (k) tiles
+  const void* mapD;                // dZ [B][N], boxes {32 floats, 32 rows}, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+  const void* mapX;                // X  [B][K], same box
+  int N, K;
+  float *W, *M, *V, *T; int ldw;
+  int tiles_k;                     // number of 64-wide k tiles
+  int tile_base, tile_count;
+  int opt;
+};
 struct VecOp {                     // g[n] = sum_b D[b][n] * (E ? E[b][n] : 1): biases and LayerNorm affine
   const float* D; const float* E; int ld;
   int N;
@@ -140,6 +149,17 @@ struct WgradParams {
   const float* is_wsum;
   float* stats;                    // device float[16]
   float alpha;
+};
+
+struct WgradTcParams {
+  const WgradTcOp* ops; int nops;
+  int total_tiles;
+  const int* tile_map;             // [total_tiles] -> op index
+  int B;
+  AdamHyper hyper[3];
+  float tau, one_minus_tau;
+  int do_soft;
+  unsigned long long* tl;          // optional debug timeline of CTA 0 (SMARTCAL_STAMPS)
 };
 
 }  // namespace sc

@@ -74,14 +74,28 @@ __device__ __forceinline__ void stage_panel(float* sm, const float* src, int ld,
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(g), "r"(sz) : "memory");
     }
   } else {
-    for (int e = tid; e < nb * 32; e += SC_THREADS) {
-      const int b = e >> 5, c = e & 31;
-      float v = 0.f;
-      if (c0 + c < ncols) {
-        const size_t row = gather ? (size_t)gather[b0 + b] : (size_t)(b0 + b);
-        v = ACT ? ld_act(src + row * ld + c0 + c) : ld_w(src + row * ld + c0 + c);
+    // scalar path (layouts that rule out 16-byte copies: N = 1, K = 2, gathered replay rows).  Eight elements per thread are
+    // kept in flight: a gathered element costs two dependent L2 round trips, and a panel is 32 elements per thread
+    for (int e0 = tid; e0 < nb * 32; e0 += 8 * SC_THREADS) {
+      size_t row[8];
+      bool ok[8];
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u * SC_THREADS, b = e >> 5, c = e & 31;
+        ok[u] = e < nb * 32 && c0 + c < ncols;
+        row[u] = ok[u] ? (gather ? (size_t)__ldg(gather + b0 + b) : (size_t)(b0 + b)) : 0;
       }
-      sm[b * 32 + c] = v;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = (e0 + u * SC_THREADS) & 31;
+        v[u] = ok[u] ? (ACT ? ld_act(src + row[u] * ld + c0 + c) : ld_w(src + row[u] * ld + c0 + c)) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u * SC_THREADS;
+        if (e < nb * 32) sm[e] = v[u];                    // sm[b * 32 + c] with e = b * 32 + c
+      }
     }
   }
 }

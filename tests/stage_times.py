@@ -66,3 +66,17 @@ for e in ev:
     print(f"  {(t - t0) / 1e3:8.2f}  (+{(t - prev) / 1e3:5.2f})  {names.get(tag, tag)}")
     prev = t
 
+
+tl = dev.buffer("debug_ts").view(torch.int64).cpu().numpy().reshape(-1)[2304 * 8:2304 * 8 + 192]
+names = {1: "producer: issue stage", 2: "mma: stage ready (lo done)", 3: "mma: issued", 4: "split: raw landed", 5: "split: lo written", 6: "epilogue: accumulator done",
+         7: "epilogue: tile in smem", 8: "epilogue: Adam done"}
+evs = []
+for who in range(3):
+    n = int(tl[64 * who])
+    evs += [(int(e) >> 8, int(e) & 255) for e in tl[64 * who + 1:64 * who + 1 + n]]
+evs.sort()
+print("timeline of CTA 0 of the tcgen05 critic wgrad kernel (us since first event):")
+if evs:
+    t0 = evs[0][0]
+    for t, tag in evs:
+        print(f"  {(t - t0) / 1e3:8.2f}  {names.get(tag, tag)}")
