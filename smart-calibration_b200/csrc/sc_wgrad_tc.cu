@@ -10,7 +10,7 @@
 // three products per k-step: A*B + A_lo*B + A*B_lo, where X_lo = X - trunc(X) is written next to the raw tile by four
 // "splitter" warps (the raw tile itself serves as the big part).
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue (one thread), warps 2..11 = lo-split;
+// Warp roles (512 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue (one thread), warps 2..15 = lo-split;
 // epilogue: warps 2..5 move the accumulator TMEM -> registers -> shared tile, then ALL warps apply Adam (its IEEE divisions and
 // square roots make the epilogue latency-bound on few threads).  Three 48 KB stages of 32 batch rows.
 #include "sc_common.cuh"
@@ -24,7 +24,7 @@ constexpr int TC_A_BYTES = (TC_M / 32) * TC_BR * 128;       // 16 KB: 4 boxes of
 constexpr int TC_B_BYTES = (TC_N / 32) * TC_BR * 128;       // 8 KB
 constexpr int TC_STAGE_BYTES = 2 * (TC_A_BYTES + TC_B_BYTES);   // raw + lo
 constexpr int TC_TILE_PITCH = TC_N + 4;
-constexpr int TC_THREADS = 384;
+constexpr int TC_THREADS = 512;
 constexpr int TC_SPLIT_THREADS = TC_THREADS - 64;          // warps 2..11
 
 __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
     } else {
       // the Adam operands of this tile (parameter, both moments, target: 4 x 32 KB) are pulled into L2 while the GEMM runs
       {
-        const int q = tid - 64;                               // 0..319
+        const int q = tid - 64;                               // 0..447
         for (int i = q; i < TC_M * 2 * 4; i += TC_SPLIT_THREADS) {
           const int arr = i >> 8, r = (i >> 1) & 127, half = i & 1;
           const float* base = arr == 0 ? op.W : arr == 1 ? op.M : arr == 2 ? op.V : op.T;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
         }
       }
       // ---------------- splitter warps: X_lo = X - trunc_tf32(X), same swizzled layout ----------------
-      const int wl = tid - 64;                                // 0..319
+      const int wl = tid - 64;                                // 0..447
       for (int s = 0; s < nstages; ++s) {
         const unsigned g = it + s, slot = g % TC_STAGES;
         mbar_wait(full_raw + slot, (g / TC_STAGES) & 1u);
@@ -204,13 +204,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
       const AdamHyper h = p.hyper[op.opt];
       const bool soft = op.T != nullptr && p.do_soft;
       constexpr int NF = TC_M * TC_N / 4;                     // float4 elements of the tile
+      constexpr int EU = NF / TC_THREADS;                     // float4 elements per thread: all their operands are requested at once
+      static_assert(EU * TC_THREADS == NF, "tile / thread mismatch");
 #pragma unroll 1
-      for (int f0 = tid; f0 < NF; f0 += 3 * TC_THREADS) {
-        float4 pm[3], pv[3], pp[3], pt[3];
-        bool ok[3];
-        size_t idx[3];
+      for (int f0 = tid; f0 < NF; f0 += EU * TC_THREADS) {
+        float4 pm[EU], pv[EU], pp[EU], pt[EU];
+        bool ok[EU];
+        size_t idx[EU];
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
+        for (int u = 0; u < EU; ++u) {
           const int f = f0 + u * TC_THREADS, r = f >> 4, c4 = f & 15;
           ok[u] = f < NF && (n0 + r < op.N) && (k0 + 4 * c4 < op.K);
           idx[u] = ok[u] ? (size_t)(n0 + r) * op.ldw + k0 + 4 * c4 : 0;
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
           }
         }
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
+        for (int u = 0; u < EU; ++u) {
           if (!ok[u]) continue;
           const int f = f0 + u * TC_THREADS, r = f >> 4, c4 = f & 15;
           const float4 g4 = *reinterpret_cast<const float4*>(tile_s + r * TC_TILE_PITCH + 4 * c4);
