@@ -65,6 +65,7 @@ struct TensorMaps {
 
 struct RowPhaseParams {
   int program, kind;                         // RowProgram, SC_KIND_*
+  int fwd_tc;                                // 1: forward GEMM stages on tcgen05 (weights in TMEM), 0: mma.sync (SMARTCAL_FWD=mma)
   float closs_scale;                         // critic-loss gradient scale: 1 (mean of squares), B (DDPG's sum of squares)
   int B, S, Sp, A, Ap;
   ActorP actor;                              // actor evaluated in this phase
