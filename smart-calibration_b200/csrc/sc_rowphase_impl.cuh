@@ -51,7 +51,11 @@ constexpr int SM_RED = 160 * REDROWS;                  // max over (KS, NC) in {
 constexpr int SM_Z = REDROWS * WCOLS;
 constexpr int SM_STAT = MAXOPS * MAXROWS * 2;
 constexpr int SM_ZK = SC_CFG_ZK;                       // raw pre-LayerNorm outputs of a stage, kept on chip between the two barriers
+#ifdef SC_ENABLE_FWD_TC
 constexpr int SM_XLO = 2 * REDROWS * 32;                 // tcgen05 forward path: small parts of the X k-blocks (one per warp group)
+#else
+constexpr int SM_XLO = 0;
+#endif
 constexpr int SM_TOTAL_FLOATS = SM_RING + SM_RED + SM_Z + SM_STAT + SM_ZK + SM_XLO;
 static_assert((SM_RING + SM_RED + SM_Z + SM_STAT + SM_ZK) % 256 == 0, "X_lo staging must keep the 1024-byte swizzle alignment");
 
@@ -120,6 +124,7 @@ __device__ __forceinline__ void fwd_tile(const float* ring, const Pipe& pipe, un
   tl_mark(pipe, 3);
 }
 
+#ifdef SC_ENABLE_FWD_TC      // experimental: correct, but 3x slower than mma.sync at 8-row tiles
 // ---- forward tile on the 5th-generation tensor cores (tcgen05, weights through tensor memory) ---------------------------
 // Same contract as fwd_tile.  D^T[feature][row] += W[feature][k] X[row][k] with M = 64 features (the CTA's slice; slices
 // narrower than 64 leave the upper TMEM lanes unused), N = 8 NT8 batch rows, K = 8 per instruction.  The weight tile goes
@@ -283,6 +288,8 @@ __device__ __forceinline__ void fwd_tile_tc(const float* ring, const Pipe& pipe,
   consumer_sync();
 }
 
+#endif  // SC_ENABLE_FWD_TC
+
 template <int NT8, int MT>
 __device__ __forceinline__ void bwd_tile(const float* ring, const Pipe& pipe, unsigned& g, int Nl, float* red, float* sZ) {
   constexpr int KS = SC_WARPS / MT, NC = 16 * MT, NCH = (NC + 31) / 32;
@@ -374,13 +381,16 @@ __device__ void dense_stage(const DenseOp* ops, int nops, int B, int row0, int n
       for (int sub = 0; sub < nsub; ++sub) {
         const int r0 = row0 + sub * ROWS;
         const int rv = min(ROWS, nrows - sub * ROWS);
+#ifdef SC_ENABLE_FWD_TC
         if (pipe.tmem != 0xffffffffu) {
           switch (Nc >> 4) {
             case 4: fwd_tile_tc<TM, 4>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv, tc_uses); break;
             case 2: fwd_tile_tc<TM, 2>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv, tc_uses); break;
             default: fwd_tile_tc<TM, 1>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv, tc_uses); break;
           }
-        } else {
+        } else
+#endif
+        {
           switch (Nc >> 4) {
             case 4: fwd_tile<TM, 4>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv); break;
             case 2: fwd_tile<TM, 2>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv); break;
@@ -1219,6 +1229,7 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
+#ifdef SC_ENABLE_FWD_TC
   if (p.fwd_tc && tid < 32) {
     // 256 of the SM's 512 tensor-memory columns (two CTAs per SM): two accumulators + two (big | small) weight buffers
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256));
@@ -1227,6 +1238,7 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#endif
   const Pipe pipe{p.dbg, p.tstamp ? prof_acc : nullptr, mbars, mbars + NSTAGE,
                   (p.tstamp && p.program == PROG_CRITIC) ? p.tstamp + 2048 * 8 : nullptr,
                   tmem_slot, mma_done, smem + SM_RING + SM_RED + SM_Z + SM_STAT + SM_ZK, nullptr};
@@ -1362,11 +1374,13 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
       }
     }
   }
+#ifdef SC_ENABLE_FWD_TC
   if (p.fwd_tc) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(pipe.tmem), "r"(256));
   }
+#endif
 }
 
 
