@@ -164,6 +164,7 @@ struct sc_agent {
   sc_config cfg;
   cudaStream_t st;
   cudaStream_t st_side;              // PER tree update runs here, overlapped with the weight-gradient / actor kernels
+  int eps_inline[3]; unsigned long long eps_stream[3];
   cudaStream_t st_side2;             // narrow-layer weight gradients run here next to the tensor-core kernel
   cudaEvent_t ev_fork, ev_join, ev_fork2, ev_join2;
   void* arena;
@@ -1113,11 +1114,20 @@ static int upload_noise(sc_agent* a, const float* host, int slot, uint64_t strea
     float* h = a->h_stage + (size_t)slot * n;
     memcpy(h, host, n * sizeof(float));
     CK(cudaMemcpyAsync(a->eps[slot], h, n * sizeof(float), cudaMemcpyHostToDevice, a->st));
+    a->eps_inline[slot] = 0;
   } else {
-    CK(launch_fill_normal(a->eps[slot], (int)n, a->cfg.rng_seed, stream_tag + (a->noise_ctr++), a->st));
-    a->launches++;
+    // device RNG: no fill launch -- the row-phase kernel draws the same Philox values where it consumes them
+    a->eps_inline[slot] = 1;
+    a->eps_stream[slot] = stream_tag + (a->noise_ctr++);
   }
   return SC_OK;
+}
+static void set_eps(sc_agent* a, RowPhaseParams& p, int slot) {
+  p.eps = a->eps[slot];
+  p.eps_inline = a->eps_inline[slot];
+  p.eps_seed = a->cfg.rng_seed;
+  p.eps_stream = a->eps_stream[slot];
+  p.eps_store = a->eps[slot];
 }
 
 int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_host) {
@@ -1148,7 +1158,7 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
   p.tm = a->tm_critic;
   if (sac) {
     p.actor = actor_ptrs(a->params + a->off_actor, a->La, a->cfg.kind);
-    p.eps = a->eps[0];
+    set_eps(a, p, 0);
   } else {
     p.actor = actor_ptrs(a->targets + a->toff_actor, a->La, a->cfg.kind);
     double nz = 0.0;
@@ -1187,7 +1197,7 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
     p.program = PROG_ACTOR;
     p.tm = a->tm_actor;
     p.actor = actor_ptrs(a->params + a->off_actor, a->La, a->cfg.kind);
-    p.eps = sac ? a->eps[1] : nullptr;
+    if (sac) set_eps(a, p, 1); else p.eps = nullptr;
     if (sac && a->cfg.use_hint) {
       // pre-pass: forward only matters (pi), then the batch-wide penalty scalar (enet_sac.py:601-602)
       if ((rc = run_rowphase(a, p, -1))) return rc;
@@ -1222,7 +1232,7 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
       // dual ascent on the hint multiplier with a fresh no-grad sample from the UPDATED actor (enet_sac.py:608-617)
       if (noise && noise->eps_dual_host) CK(cudaStreamSynchronize(a->st));
       if ((rc = upload_noise(a, noise ? noise->eps_dual_host : nullptr, 2, 0x3000000000ull))) return rc;
-      p.eps = a->eps[2];
+      set_eps(a, p, 2);
       p.hint_coef = nullptr;
       if ((rc = run_rowphase(a, p, -1))) return rc;
       CK(launch_hint_coef(a->aw.pi, a->rp.hint, a->Ap, a->bidx, a->B, a->A, a->cfg.hint_threshold, a->admm_rho, a->rho_dev, a->hint_out + 4, a->rho_dev, a->st));

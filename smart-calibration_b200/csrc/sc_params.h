@@ -65,6 +65,9 @@ struct TensorMaps {
 
 struct RowPhaseParams {
   int program, kind;                         // RowProgram, SC_KIND_*
+  // device-RNG mode: the N(0,1) draws of the policy head are generated in the kernel (Philox counter = element index / 2, the
+  // same values k_fill_normal would have written) and stored to eps_store for inspection
+  int eps_inline; unsigned long long eps_seed, eps_stream; float* eps_store;
   int fwd_tc;                                // 1: forward GEMM stages on tcgen05 (weights in TMEM), 0: mma.sync (SMARTCAL_FWD=mma)
   float closs_scale;                         // critic-loss gradient scale: 1 (mean of squares), B (DDPG's sum of squares)
   int B, S, Sp, A, Ap;

@@ -893,6 +893,15 @@ __device__ void actor_tail_forward(const RowPhaseParams& p, const TailSm& t) {
   consumer_sync();
 }
 
+__device__ __forceinline__ float eps_value(const RowPhaseParams& p, int row, int j) {
+  const size_t e = (size_t)row * p.A + j;
+  if (!p.eps_inline) return ld_act(p.eps + e);
+  const float2 z = philox_normal2(p.eps_seed, p.eps_stream, (uint64_t)(e >> 1));
+  const float v = (e & 1) ? z.y : z.x;
+  if (p.eps_store != nullptr) p.eps_store[e] = v;
+  return v;
+}
+
 // tanh-squashed Gaussian sample + log-prob (SAC, ref ActorNetwork.sample_normal enet_sac.py:446-466) or the
 // deterministic TD3 head.  eps_of(row, j) supplies N(0,1).  Results: t.an[0] (action), t.sc[SC_LOGP], t.smp.  2 barriers.
 template <typename EpsFn>
@@ -959,7 +968,7 @@ __device__ void tail_critic(const RowPhaseParams& p, const TailSm& t, const RowS
   // ---- policy on s' (SAC: online actor, sampled; TD3: target actor + clipped scalar noise) ----
   actor_tail_forward(p, t);
   mark(9);
-  policy_head(p, t, rs, true, [&](int row, int j) { return ld_act(p.eps + (size_t)row * p.A + j); });
+  policy_head(p, t, rs, true, [&](int row, int j) { return eps_value(p, row, j); });
   mark(10);
   // ---- action branches of all four critics at once: targets on a', online critics on the replay action ----
   const CriticP* nets[NETS] = {&p.targ[0], &p.targ[1], &p.crit[0], &p.crit[1]};
@@ -1068,7 +1077,7 @@ __device__ void tail_actor(const RowPhaseParams& p, const TailSm& t, const RowSe
   store_rows_from(p.aw.h3, t.x3, H3, rs);
   store_rows_from(p.aw.zh3, t.zh3, H3, rs);
   if (tid < RT && rs.row[tid] >= 0) p.aw.rs3[rs.row[tid]] = t.rsx[tid * 8 + 2];
-  policy_head(p, t, rs, false, [&](int row, int j) { return ld_act(p.eps + (size_t)row * p.A + j); });
+  policy_head(p, t, rs, false, [&](int row, int j) { return eps_value(p, row, j); });
   if (tid < RT * p.A) {
     const int r = tid / p.A, j = tid - r * p.A;
     if (rs.row[r] >= 0) p.aw.pi[(size_t)rs.row[r] * p.A + j] = t.an[r * AMAX + j];
