@@ -23,6 +23,9 @@ cudaError_t launch_rowphase(const RowPhaseParams& p, int variant, int cluster_si
 size_t wgrad_smem_bytes();
 cudaError_t launch_wgrad(const WgradParams& p, int grid, cudaStream_t st);
 cudaError_t launch_wgrad_tc(const WgradTcParams& p, int grid, cudaStream_t st);
+cudaError_t launch_dense_tc(const DenseTcParams& p, cudaStream_t st);
+cudaError_t launch_gather_mb(float* mb_s, float* mb_s2, const float* state, const float* new_state, const int* bidx, int B, int Sp,
+                             int Sp32, cudaStream_t st);
 cudaError_t launch_soft_update(const float* src, float* dst, size_t n, float tau, cudaStream_t st);
 cudaError_t launch_replay_store(const ReplayP& rp, const float* tr, int slot, int mode, double priority, double clip, cudaStream_t st);
 cudaError_t launch_replay_fill(const ReplayP& rp, const float* tr, int n, cudaStream_t st);
@@ -174,6 +177,8 @@ struct sc_agent {
   float *mb_s, *mb_s2;                // [B][Sp32] minibatch gather buffers
   unsigned char* tmaps;               // device table of CUtensorMap (128 B each)
   TensorMaps tm_critic, tm_actor, tm_act;   // per-program map pointer sets
+  TensorMaps tmd_critic, tmd_actor;         // the same matrices with 128-row boxes for the tcgen05 dense stages (sc_dense_tc.cu)
+  bool dense_tc;                            // batched passes run their two wide forward layers as k_dense_tc launches
   NetLayout Lc, La;
   size_t online_floats;               // actor + c1 + c2
   float *params, *adam_m, *adam_v;    // online blocks
@@ -490,8 +495,40 @@ static int build_tensor_maps(sc_agent* a) {
     tg_w1 = add(tg.w1, K1, H1, W1);
     tg_w2 = add(tg.w2, H1, H2, W2);
   }
+  // second set for the tcgen05 dense stages: 128-row boxes of the layer inputs and of the [N][K] weights
+  TensorMaps d;
+  memset(&d, 0, sizeof(d));
+  const void *d_on_w1 = nullptr, *d_on_w2 = nullptr, *d_tg_w1 = nullptr, *d_tg_w2 = nullptr;
+  {
+    const int DB = 128, DW = 64;               // box rows: 128 batch rows, 64 output features (sc_dense_tc.cu tile)
+    d.mb_s = add(a->mb_s, K1, B, DB);
+    d.mb_s2 = add(a->mb_s2, K1, B, DB);
+    d.t_h1 = add(a->aw.t_h1, H1, B, DB);
+    d.h1 = add(a->aw.h1, H1, B, DB);
+    for (int k = 0; k < 2; ++k) {
+      d.th11[k] = add(a->tw[k].h11, H1, B, DB);
+      d.ch11[k] = add(a->cw[k].h11, H1, B, DB);
+      d.ph11[k] = add(a->cw[k].p_h11, H1, B, DB);
+      d.crit_w11[k] = add(C[k].w11, K1, H1, DW);
+      d.crit_w12[k] = add(C[k].w12, H1, H2, DW);
+      d.targ_w11[k] = add(T[k].w11, K1, H1, DW);
+      d.targ_w12[k] = add(T[k].w12, H1, H2, DW);
+    }
+    d_on_w1 = add(on.w1, K1, H1, DW);
+    d_on_w2 = add(on.w2, H1, H2, DW);
+    d_tg_w1 = d_on_w1; d_tg_w2 = d_on_w2;
+    if (td3) {
+      ActorP tg = actor_ptrs(a->targets + a->toff_actor, a->La, a->cfg.kind);
+      d_tg_w1 = add(tg.w1, K1, H1, DW);
+      d_tg_w2 = add(tg.w2, H1, H2, DW);
+    }
+  }
   if (rc != SC_OK) return rc;
   if (host.size() > 64) return fail(SC_ERR_STATE, "tensor map table overflow");
+  a->tmd_critic = d; a->tmd_actor = d;
+  a->tmd_critic.actor_w1 = td3 ? d_tg_w1 : d_on_w1;
+  a->tmd_critic.actor_w2 = td3 ? d_tg_w2 : d_on_w2;
+  a->tmd_actor.actor_w1 = d_on_w1; a->tmd_actor.actor_w2 = d_on_w2;
   a->tm_critic = t; a->tm_actor = t; a->tm_act = t;
   a->tm_critic.actor_w1 = td3 ? tg_w1 : on_w1;      // critic phase evaluates the TD3 target actor / the SAC online actor on s'
   a->tm_critic.actor_w2 = td3 ? tg_w2 : on_w2;
@@ -544,6 +581,9 @@ static int build_op_tables(sc_agent* a) {
   // wide layers go to the tensor-core kernel unless SMARTCAL_WGRAD=ffma pins the FP32 tile kernel (A/B comparisons)
   const char* wg = getenv("SMARTCAL_WGRAD");
   a->use_tc = !(wg && !strcmp(wg, "ffma"));
+  // wide forward layers of the batched passes: tcgen05 launches unless SMARTCAL_DENSE=mma keeps them in the row-phase kernel
+  const char* dn = getenv("SMARTCAL_DENSE");
+  a->dense_tc = !(dn && !strcmp(dn, "mma"));
   std::vector<TcCand> tc_critic, tc_actor;
   std::vector<CUtensorMap> tc_maps;
   g_tc_sink = a->use_tc ? &tc_critic : nullptr;
@@ -1014,9 +1054,65 @@ static void fill_wgrad(sc_agent* a, WgradParams& w, bool actor, int do_soft, int
   w.alpha = a->cfg.kind == SC_KIND_SAC ? a->alpha : 0.f;
 }
 
-static int run_rowphase(sc_agent* a, const RowPhaseParams& p, int timer_id) {
+// The two wide forward layers of a batched phase as tcgen05 launches (sc_dense_tc.cu); the op lists mirror the dense(...)
+// tables of k_rowphase (sc_rowphase_impl.cuh, PROG_CRITIC / PROG_ACTOR).
+static int run_dense_tc(sc_agent* a, const RowPhaseParams& p) {
+  const bool critic = p.program == PROG_CRITIC;
+  const TensorMaps& m = critic ? a->tmd_critic : a->tmd_actor;
+  const ActorP& ac = p.actor;
+  DenseTcParams d1, d2;
+  memset(&d1, 0, sizeof(d1));
+  memset(&d2, 0, sizeof(d2));
+  d1.N = H1; d2.N = H2;
+  d1.B = d2.B = p.B;
+  d1.nrb = d2.nrb = (p.B + 127) / 128;
+  const int K1 = p.Sp32;
+  int n = 0;
+  auto op = [&](const void* mx1, const void* mw1, const float* b1, const float* g1, const float* be1, float* h1, float* zh1, float* rs1,
+                const void* mx2, const void* mw2, const float* b2, const float* g2, const float* be2, float* h2, float* zh2, float* rs2) {
+    d1.ops[n] = DenseTcOp{mx1, mw1, b1, g1, be1, h1, zh1, rs1, K1};
+    d2.ops[n] = DenseTcOp{mx2, mw2, b2, g2, be2, h2, zh2, rs2, H1};
+    ++n;
+  };
+  if (critic) {
+    CK(launch_gather_mb(a->mb_s, a->mb_s2, p.rp.state, p.rp.new_state, p.bidx, p.B, p.Sp, p.Sp32, a->st));
+    a->launches++;
+    op(m.mb_s2, m.actor_w1, ac.b1, ac.g1, ac.be1, p.aw.t_h1, nullptr, nullptr,
+       m.t_h1, m.actor_w2, ac.b2, ac.g2, ac.be2, p.aw.t_h2, nullptr, nullptr);
+    for (int k = 0; k < 2; ++k)
+      op(m.mb_s2, m.targ_w11[k], p.targ[k].b11, p.targ[k].g11, p.targ[k].be11, p.tw[k].h11, nullptr, nullptr,
+         m.th11[k], m.targ_w12[k], p.targ[k].b12, p.targ[k].g12, p.targ[k].be12, p.tw[k].h12, nullptr, nullptr);
+    for (int k = 0; k < 2; ++k)
+      op(m.mb_s, m.crit_w11[k], p.crit[k].b11, p.crit[k].g11, p.crit[k].be11, p.cw[k].h11, p.cw[k].zh11, p.cw[k].rs11,
+         m.ch11[k], m.crit_w12[k], p.crit[k].b12, p.crit[k].g12, p.crit[k].be12, p.cw[k].h12, p.cw[k].zh12, p.cw[k].rs12);
+  } else {
+    op(m.mb_s, m.actor_w1, ac.b1, ac.g1, ac.be1, p.aw.h1, p.aw.zh1, p.aw.rs1,
+       m.h1, m.actor_w2, ac.b2, ac.g2, ac.be2, p.aw.h2, p.aw.zh2, p.aw.rs2);
+    for (int k = 0; k < p.n_q; ++k)
+      op(m.mb_s, m.crit_w11[k], p.crit[k].b11, p.crit[k].g11, p.crit[k].be11, p.cw[k].p_h11, nullptr, nullptr,
+         m.ph11[k], m.crit_w12[k], p.crit[k].b12, p.crit[k].g12, p.crit[k].be12, p.cw[k].p_h12, nullptr, nullptr);
+  }
+  d1.nops = d2.nops = n;
+  if (getenv("SMARTCAL_STAMPS")) {
+    if (critic) d1.tl = a->tstamp + 2880 * 8;
+    d1.ts = a->tstamp + (critic ? 1280 : 1792) * 8;
+    d2.ts = a->tstamp + (critic ? 1408 : 1920) * 8;
+  }
+  CK(launch_dense_tc(d1, a->st));
+  CK(launch_dense_tc(d2, a->st));
+  a->launches += 2;
+  return SC_OK;
+}
+
+static int run_rowphase(sc_agent* a, const RowPhaseParams& p_in, int timer_id) {
   cudaEvent_t e0, e1;
   if (timer_id >= 0) timer_begin(a, timer_id, &e0, &e1);
+  RowPhaseParams p = p_in;
+  if (a->dense_tc && p.program != PROG_ACT) {
+    int rc = run_dense_tc(a, p);
+    if (rc) return rc;
+    p.skip_dense = 1;
+  }
   const int ncl = p.program == PROG_ACT ? 1 : a->nclusters;
   CK(launch_rowphase(p, a->row_variant, a->cluster_size, ncl, a->tile_tm, a->st));   // (the tensor-map boxes are built for tile_tm)
   if (timer_id >= 0) timer_end(a, timer_id, e0, e1);

@@ -1,0 +1,351 @@
+// The two wide forward layers of every network pass (fc1/fc11: S -> 512, fc2/fc12: 512 -> 256; ref enet_sac.py:357-368,
+// 415-424) on the 5th-generation tensor cores: Z = X W^T as a tcgen05.mma kind::tf32 GEMM with the batch rows on M (128 per
+// CTA, one accumulator lane per row) and 64 output features on N, accumulator in tensor memory, followed by the fused
+// bias + LayerNorm + ELU epilogue.  A row's LayerNorm statistics span the N / 64 CTAs of a thread-block cluster, which
+// exchange per-row (mean, M2) partials through distributed shared memory and combine them in fixed order (Chan et al.),
+// exactly like the mma.sync row-phase stage this replaces for batched passes (sc_rowphase_impl.cuh dense_stage).
+//
+// Both operands are K-major (X [rows][K], W [features][K]): TMA boxes of [128 rows][32 floats] with the 128-byte swizzle,
+// described to the MMA as 8-row atoms of 1024 B (SBO), +32 B per 8-deep k-step.  kind::tf32 truncates its fp32 inputs to 10
+// mantissa bits, so fp32 fidelity is restored with three products per k-step, X_lo W + X W_lo + X W: the splitter warps
+// round every raw box to tf32 in place (big part) and write the rounded remainder (small part) next to it.
+//
+// Warp roles (512 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue (one thread), warps 2..15 =
+// big/small split; epilogue on all 16 warps: warp w reads TMEM lanes 32 (w & 3).. (its rows) x columns 16 (w >> 2).. (its features).
+// The operand traffic of three SS-mode products per k-step makes the loop shared-memory-bandwidth bound (per 8-deep k-step
+// the tensor core reads 3 (M + N) 32 B, TMA and the split move another 4 (M + N) 32 B), which is why the tile is only 64 wide:
+// more, smaller CTAs put more SMs' shared memory to work.
+#include "sc_common.cuh"
+#include "sc_params.h"
+
+namespace sc {
+
+constexpr int DT_M = 128, DT_N = 64;                         // batch rows / output features per CTA
+constexpr int DT_STAGES = 4;
+constexpr int DT_CW = DT_N / 4;                              // epilogue: features per thread
+constexpr int DT_X_BYTES = DT_M * 128, DT_W_BYTES = DT_N * 128;   // one k-chunk of 32 floats
+constexpr int DT_STAGE_BYTES = 2 * (DT_X_BYTES + DT_W_BYTES);     // raw + lo: 64 KB
+constexpr int DT_THREADS = 512, DT_SPLIT_THREADS = DT_THREADS - 64;
+constexpr int DT_MAXCS = 8;
+
+__device__ __forceinline__ uint64_t dt_desc(uint32_t saddr) {
+  uint64_t d = 0;                                            // K-major, SWIZZLE_128B, 8-row atoms of 1024 B
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((1024u >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void dt_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// x = big + small with big = x rounded to tf32 (so the tensor core's truncation leaves it unchanged) and small = the
+// remainder rounded to tf32 (round-to-nearest halves the dropped small*small term against a truncating split)
+__device__ __forceinline__ void split_rn(float x, float& big, float& small) {
+  uint32_t b, s;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(x));
+  big = __uint_as_float(b);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(s) : "f"(x - big));
+  small = __uint_as_float(s);
+}
+__device__ __forceinline__ void dt_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constant__ DenseTcParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_raw[DT_STAGES], full_lo[DT_STAGES], empty[DT_STAGES], acc_done;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float psum[4][DT_M], pm2[4][DT_M];
+  __shared__ __align__(16) float svec[3][DT_N];             // bias, gamma, beta of this CTA's features
+  __shared__ __align__(8) float2 xstat[DT_MAXCS][DT_M];     // (mean, M2) of every cluster CTA's 128-feature slice, per row
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cs = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
+  const int tile = (int)cluster_idx();
+  const int op_i = tile / p.nrb, rb = tile - op_i * p.nrb;
+  const DenseTcOp& op = p.ops[op_i];
+  const int n0 = rank * DT_N, r0 = rb * DT_M;
+  // debug timeline of CTA 0: each of three threads appends (globaltimer << 8 | tag) to its own shared-memory list (flushed at
+  // the end, so that taking a mark costs no memory round trip)
+  __shared__ unsigned long long tlbuf[3][62];
+  __shared__ int tln[3];
+  auto mark = [&](int slot, int tag) {
+    if (p.tl != nullptr && blockIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      const int n = tln[slot];
+      if (n < 62) { tlbuf[slot][n] = (t << 8) | (unsigned long long)tag; tln[slot] = n + 1; }
+    }
+  };
+  auto stamp = [&](int i) {
+    if (p.ts != nullptr && tid == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.ts[(size_t)blockIdx.x * 8 + i] = t;
+    }
+  };
+  stamp(0);
+  if (tid < 3) tln[tid] = 0;
+  if (tid == 0) {
+    for (int i = 0; i < DT_STAGES; ++i) {
+      mbar_init(full_raw + i, 1);
+      mbar_init(full_lo + i, DT_SPLIT_THREADS / 32);
+      mbar_init(empty + i, 1);
+    }
+    mbar_init(&acc_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(DT_N));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // first cluster barrier phase: its wait (before the statistics exchange) proves every peer CTA is resident
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  pdl_launch();
+  pdl_wait();                                                 // everything above overlapped the previous kernel's tail
+  stamp(1);
+  const uint32_t tmem = tmem_slot;
+  const int nk = (op.K + 31) >> 5;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    for (int s = 0; s < nk; ++s) {
+      const int slot = s % DT_STAGES;
+      if (s >= DT_STAGES) mbar_wait(empty + slot, ((s / DT_STAGES) - 1) & 1u);
+      uint8_t* st = smem + (size_t)slot * DT_STAGE_BYTES;
+      if (lane == 0) {
+        mark(0, 1);
+        mbar_expect_tx(full_raw + slot, DT_X_BYTES + DT_W_BYTES);
+        tma_load_2d(reinterpret_cast<float*>(st), op.mapX, 32 * s, r0, full_raw + slot);
+        tma_load_2d(reinterpret_cast<float*>(st + DT_X_BYTES), op.mapW, 32 * s, n0, full_raw + slot);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issue (one thread) ----------------
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(DT_N >> 3) << 17) | ((uint32_t)(DT_M >> 4) << 24);
+    // one elected lane issues; elect.sync (rather than a lane test) lets the compiler keep the descriptors in uniform
+    // registers and emit the MMAs back to back -- a divergent branch costs ~70 cycles of uniform-datapath fix-up per MMA
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(leader));
+    const uint64_t d_x0 = dt_desc(smem_u32(smem)), d_w0 = d_x0 + (uint64_t)(DT_X_BYTES >> 4);
+    const uint64_t d_xl0 = d_w0 + (uint64_t)(DT_W_BYTES >> 4), d_wl0 = d_xl0 + (uint64_t)(DT_X_BYTES >> 4);
+    for (int s = 0; s < nk; ++s) {
+      const int slot = s % DT_STAGES;
+      mbar_wait(full_lo + slot, (s / DT_STAGES) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (leader) {
+        mark(1, 2);
+        const uint64_t so = (uint64_t)((slot * DT_STAGE_BYTES) >> 4);        // (descriptor addresses count 16-byte units)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t o = so + (uint64_t)(2 * j);                           // + 32 B per 8-deep k-step
+          dt_mma(tmem, d_xl0 + o, d_w0 + o, idesc, (s | j) != 0 ? 1u : 0u);
+          dt_mma(tmem, d_x0 + o, d_wl0 + o, idesc, 1u);
+          dt_mma(tmem, d_x0 + o, d_w0 + o, idesc, 1u);
+        }
+        mark(1, 3);
+        dt_commit(empty + slot);                              // frees the stage when these MMAs have read it
+        if (s == nk - 1) dt_commit(&acc_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------- splitter warps: lo = x - trunc_tf32(x), same swizzled layout ----------------
+    const int wl = tid - 64;
+    if (wl < 3 * DT_N) {
+      const int a = wl / DT_N, j = wl - a * DT_N;
+      const float* src = a == 0 ? op.bias : a == 1 ? op.gamma : op.beta;
+      svec[a][j] = src ? ld_w(src + n0 + j) : 0.f;            // (made visible to the epilogue by its first __syncthreads)
+    }
+    for (int s = 0; s < nk; ++s) {
+      const int slot = s % DT_STAGES;
+      mbar_wait(full_raw + slot, (s / DT_STAGES) & 1u);
+      if (wl == 0) mark(2, 4);
+      float4* raw = reinterpret_cast<float4*>(smem + (size_t)slot * DT_STAGE_BYTES);
+      float4* lo = reinterpret_cast<float4*>(smem + (size_t)slot * DT_STAGE_BYTES + DT_X_BYTES + DT_W_BYTES);
+#pragma unroll 5
+      for (int i = wl; i < (DT_X_BYTES + DT_W_BYTES) / 16; i += DT_SPLIT_THREADS) {
+        const float4 x = raw[i];
+        float4 h, y;
+        split_rn(x.x, h.x, y.x);
+        split_rn(x.y, h.y, y.y);
+        split_rn(x.z, h.z, y.z);
+        split_rn(x.w, h.w, y.w);
+        raw[i] = h;
+        lo[i] = y;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic stores -> visible to the tensor core's reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_lo + slot);
+      if (wl == 0) mark(2, 5);
+    }
+  }
+  // ---------------- epilogue (all warps): bias, LayerNorm across the cluster, ELU, stores ----------------
+  mbar_wait(&acc_done, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (tid == 64) mark(2, 6);
+  stamp(2);
+  const int q = warp & 3, c = warp >> 2;
+  const int row = q * 32 + lane;                              // TMEM lane = batch row of the tile
+  const int cb = c * DT_CW;                                   // first of this thread's DT_CW features within the CTA slice
+  float z[DT_CW];
+  {
+    uint32_t v[DT_CW];
+    const uint32_t addr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(addr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < DT_CW; ++j) z[j] = __uint_as_float(v[j]);
+  }
+  __syncthreads();                                            // svec is complete
+  if (tid == 64) mark(2, 8);
+#pragma unroll
+  for (int j = 0; j < DT_CW; ++j) z[j] += svec[0][cb + j];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < DT_CW; ++j) s += z[j];
+  psum[c][row] = s;
+  __syncthreads();
+  const float mean_c = (((psum[0][row] + psum[1][row]) + psum[2][row]) + psum[3][row]) * (1.0f / (float)DT_N);
+  float m2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < DT_CW; ++j) {
+    const float d = z[j] - mean_c;
+    m2 = fmaf(d, d, m2);
+  }
+  pm2[c][row] = m2;
+  __syncthreads();
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+  if (tid == 64) mark(2, 9);
+  if (tid < DT_M * 2) {
+    // (row, peer-half) pairs: thread t sends row t & 127 to the peers of parity t >> 7
+    const int r_ = tid & (DT_M - 1);
+    const float mc = (((psum[0][r_] + psum[1][r_]) + psum[2][r_]) + psum[3][r_]) * (1.0f / (float)DT_N);
+    const float m2c = ((pm2[0][r_] + pm2[1][r_]) + pm2[2][r_]) + pm2[3][r_];
+    const uint32_t local = smem_u32(&xstat[rank][r_]);
+    for (int r = tid >> 7; r < cs; r += 2) {
+      uint32_t remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+      asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(mc), "f"(m2c) : "memory");
+    }
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+  if (tid == 64) mark(2, 10);
+  // combine the slices in rank order (same arithmetic as the mma.sync stage: count-weighted mean, Chan's M2 update)
+  const float fN = (float)p.N;
+  float msum = 0.f;
+  for (int r = 0; r < cs; ++r) msum = fmaf((float)DT_N, xstat[r][row].x, msum);
+  const float mean = msum / fN;
+  float m2t = 0.f;
+  for (int r = 0; r < cs; ++r) {
+    const float2 pv = xstat[r][row];
+    const float d = pv.x - mean;
+    m2t += pv.y + (float)DT_N * d * d;
+  }
+  const float rstd = 1.0f / sqrtf(m2t / fN + SC_LN_EPS);
+  const int gr = r0 + row;
+  if (gr < p.B) {
+    float* hrow = op.H + (size_t)gr * p.N + n0 + cb;
+    float* zrow = op.ZH ? op.ZH + (size_t)gr * p.N + n0 + cb : nullptr;
+#pragma unroll
+    for (int j = 0; j < DT_CW; j += 4) {
+      const float4 g4 = *reinterpret_cast<const float4*>(&svec[1][cb + j]), b4 = *reinterpret_cast<const float4*>(&svec[2][cb + j]);
+      float4 zh, h;
+      zh.x = (z[j] - mean) * rstd;
+      zh.y = (z[j + 1] - mean) * rstd;
+      zh.z = (z[j + 2] - mean) * rstd;
+      zh.w = (z[j + 3] - mean) * rstd;
+      h.x = elu(fmaf(zh.x, g4.x, b4.x));
+      h.y = elu(fmaf(zh.y, g4.y, b4.y));
+      h.z = elu(fmaf(zh.z, g4.z, b4.z));
+      h.w = elu(fmaf(zh.w, g4.w, b4.w));
+      *reinterpret_cast<float4*>(hrow + j) = h;
+      if (zrow != nullptr) *reinterpret_cast<float4*>(zrow + j) = zh;
+    }
+    if (rank == 0 && c == 0 && op.RS != nullptr) op.RS[gr] = rstd;
+  }
+  if (tid == 64) mark(2, 7);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  stamp(3);
+  if (p.tl != nullptr && blockIdx.x == 0 && tid < 3) {
+    p.tl[64 * tid] = (unsigned long long)tln[tid];
+    for (int i = 0; i < tln[tid]; ++i) p.tl[64 * tid + 1 + i] = tlbuf[tid][i];
+  }
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(DT_N));
+}
+
+// minibatch gather: replay rows [C][Sp] -> dense TMA-readable buffers [B][Sp32] (zero padded), states and next states
+__global__ void __launch_bounds__(128) k_gather_mb(float* mb_s, float* mb_s2, const float* __restrict__ state,
+                                                   const float* __restrict__ new_state, const int* __restrict__ bidx, int Sp, int Sp32) {
+  const int r = blockIdx.x >> 1, which = blockIdx.x & 1;
+  pdl_launch();
+  pdl_wait();
+  const float* src = (which ? new_state : state) + (size_t)__ldg(bidx + r) * Sp;
+  float* dst = (which ? mb_s2 : mb_s) + (size_t)r * Sp32;
+  const int n4 = Sp32 >> 2, v4 = Sp >> 2;
+  for (int c4 = threadIdx.x; c4 < n4; c4 += 128) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < v4) v = ld_w4(src + 4 * c4);
+    *reinterpret_cast<float4*>(dst + 4 * c4) = v;
+  }
+}
+
+size_t dense_tc_smem_bytes() { return (size_t)DT_STAGES * DT_STAGE_BYTES + 1024; }
+
+cudaError_t launch_dense_tc(const DenseTcParams& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_tc_smem_bytes());
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int cs = p.N / DT_N;
+  if (cs < 1 || cs > DT_MAXCS || cs * DT_N != p.N) return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
+  cudaLaunchAttribute attr[2];
+  cfg.gridDim = dim3(p.nops * p.nrb * cs, 1, 1);
+  cfg.blockDim = dim3(DT_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = dense_tc_smem_bytes();
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, k_dense_tc, p);
+}
+
+cudaError_t launch_gather_mb(float* mb_s, float* mb_s2, const float* state, const float* new_state, const int* bidx, int B, int Sp,
+                             int Sp32, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3(2 * B, 1, 1);
+  cfg.blockDim = dim3(128, 1, 1);
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_gather_mb, mb_s, mb_s2, state, new_state, bidx, Sp, Sp32);
+}
+
+}  // namespace sc

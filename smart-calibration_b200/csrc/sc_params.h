@@ -68,6 +68,7 @@ struct RowPhaseParams {
   // device-RNG mode: the N(0,1) draws of the policy head are generated in the kernel (Philox counter = element index / 2, the
   // same values k_fill_normal would have written) and stored to eps_store for inspection
   int eps_inline; unsigned long long eps_seed, eps_stream; float* eps_store;
+  int skip_dense;                            // 1: gather + both dense stages already ran as k_dense_tc launches (sc_dense_tc.cu)
   int fwd_tc;                                // 1: forward GEMM stages on tcgen05 (weights in TMEM), 0: mma.sync (SMARTCAL_FWD=mma)
   float closs_scale;                         // critic-loss gradient scale: 1 (mean of squares), B (DDPG's sum of squares)
   int B, S, Sp, A, Ap;
@@ -153,6 +154,21 @@ struct WgradParams {
   const float* is_wsum;
   float* stats;                    // device float[16]
   float alpha;
+};
+
+// ---- dense forward stages on tcgen05 (sc_dense_tc.cu): H = ELU(LN(X W^T + b)) for up to 5 layers of equal width ----
+struct DenseTcOp {
+  const void* mapX;                // X [B][K], boxes {32 floats, 128 rows}, CU_TENSOR_MAP_SWIZZLE_128B
+  const void* mapW;                // W [N][K] (PyTorch layout), boxes {32 floats, 64 rows}
+  const float *bias, *gamma, *beta;
+  float *H, *ZH, *RS;              // outputs [B][N] (ZH, RS nullable) as the row-phase tail reads them
+  int K;                           // reduction length, multiple of 32 (zero padded / TMA zero filled)
+};
+struct DenseTcParams {
+  DenseTcOp ops[5];
+  int nops, N, B, nrb;             // layer width (cluster size = N / 64), batch rows, 128-row blocks
+  unsigned long long* tl;          // optional debug timeline of CTA 0
+  unsigned long long* ts;          // optional [CTA][8] globaltimer stamps: entry, dependency met, accumulator done, end
 };
 
 struct WgradTcParams {

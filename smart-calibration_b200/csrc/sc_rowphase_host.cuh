@@ -21,6 +21,8 @@ static void cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int 
   attr[0].val.clusterDim.x = cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  // (no programmatic dependent launch here: clusters of the 256-CTA grid that become resident early next to the dense
+  //  kernels' CTAs were measured to leave the grid running in two waves)
   cfg.attrs = attr;
   cfg.numAttrs = 1;
 }
@@ -29,7 +31,7 @@ static cudaError_t launch_k(K kern, size_t smem, const RowPhaseParams& p, int cs
   cudaError_t e = configure(kern, smem, cs);          // idempotent and cheap
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   cluster_cfg(cfg, attr, nclusters, cs, smem, st);
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
@@ -37,7 +39,7 @@ template <typename K>
 static int max_clusters(K kern, size_t smem, int cs) {
   if (configure(kern, smem, cs) != cudaSuccess) { cudaGetLastError(); return 0; }
   cudaLaunchConfig_t cfg;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   cluster_cfg(cfg, attr, 64, cs, smem, nullptr);
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }

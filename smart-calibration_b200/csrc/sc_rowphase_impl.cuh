@@ -1248,6 +1248,8 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #endif
+  pdl_launch();
+  pdl_wait();                     // (programmatic dependent launch: the barrier setup above overlapped the previous kernel)
   const Pipe pipe{p.dbg, p.tstamp ? prof_acc : nullptr, mbars, mbars + NSTAGE,
                   (p.tstamp && p.program == PROG_CRITIC) ? p.tstamp + 2048 * 8 : nullptr,
                   tmem_slot, mma_done, smem + SM_RING + SM_RED + SM_Z + SM_STAT + SM_ZK, nullptr};
@@ -1278,6 +1280,7 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
   if (p.program == PROG_CRITIC) {
     const ActorP& a = p.actor;
     stamp(0);
+    if (!p.skip_dense) {
     // stage 0: fused minibatch gather (replay rows -> dense buffers the TMA unit can tile), one cluster barrier
     gather_rows(p.mb_s, p.rp.state, p.bidx, row0, nrows, p.S, p.Sp, p.Sp32, rank, CS);
     gather_rows(p.mb_s2, p.rp.new_state, p.bidx, row0, nrows, p.S, p.Sp, p.Sp32, rank, CS);
@@ -1300,6 +1303,7 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
     __syncthreads();
     dense_stage<CS, TM>(dops, 5, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g, tc_uses,
                         p.tstamp ? p.tstamp + 512 * 8 + (size_t)blockIdx.x * 8 : nullptr);
+    }
     stamp(2);
     // stage 3: row-local tail
     if (consumer)
@@ -1333,6 +1337,7 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
       }
     };
     astamp(0);
+    if (!p.skip_dense) {
     dense(0, tm.mb_s, tm.actor_w1, a.b1, a.g1, a.be1, K1, H1, p.aw.h1, p.aw.zh1, p.aw.rs1);
     for (int k = 0; k < p.n_q; ++k)
       dense(1 + k, tm.mb_s, tm.crit_w11[k], p.crit[k].b11, p.crit[k].g11, p.crit[k].be11, K1, H1, p.cw[k].p_h11, nullptr, nullptr);
@@ -1344,6 +1349,7 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
       dense(1 + k, tm.ph11[k], tm.crit_w12[k], p.crit[k].b12, p.crit[k].g12, p.crit[k].be12, H1, H2, p.cw[k].p_h12, nullptr, nullptr);
     __syncthreads();
     dense_stage<CS, TM>(dops, 1 + p.n_q, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g, tc_uses);
+    }
     astamp(2);
     if (consumer)
       for (int gr = rank; gr < nrows; gr += CS * RT) {
