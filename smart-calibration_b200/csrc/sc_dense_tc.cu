@@ -27,6 +27,8 @@ constexpr int DT_X_BYTES = DT_M * 128, DT_W_BYTES = DT_N * 128;   // one k-chunk
 constexpr int DT_STAGE_BYTES = 2 * (DT_X_BYTES + DT_W_BYTES);     // raw + lo: 64 KB
 constexpr int DT_THREADS = 512, DT_SPLIT_THREADS = DT_THREADS - 64;
 constexpr int DT_MAXCS = 8;
+constexpr int DT_TP = DT_N + 4;                              // output tile pitch (floats)
+static_assert(2 * DT_M * DT_TP * 4 <= DT_STAGE_BYTES * DT_STAGES, "output tiles must fit in the operand ring");
 
 __device__ __forceinline__ uint64_t dt_desc(uint32_t saddr) {
   uint64_t d = 0;                                            // K-major, SWIZZLE_128B, 8-row atoms of 1024 B
@@ -109,7 +111,6 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   // first cluster barrier phase: its wait (before the statistics exchange) proves every peer CTA is resident
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-  pdl_launch();
   pdl_wait();                                                 // everything above overlapped the previous kernel's tail
   stamp(1);
   const uint32_t tmem = tmem_slot;
@@ -192,6 +193,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
   }
   // ---------------- epilogue (all warps): bias, LayerNorm across the cluster, ELU, stores ----------------
   mbar_wait(&acc_done, 0);
+  pdl_launch();                                               // the next kernel may set itself up under this epilogue
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (tid == 64) mark(2, 6);
   stamp(2);
@@ -258,26 +260,35 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
     m2t += pv.y + (float)DT_N * d * d;
   }
   const float rstd = 1.0f / sqrtf(m2t / fN + SC_LN_EPS);
-  const int gr = r0 + row;
-  if (gr < p.B) {
-    float* hrow = op.H + (size_t)gr * p.N + n0 + cb;
-    float* zrow = op.ZH ? op.ZH + (size_t)gr * p.N + n0 + cb : nullptr;
+  // outputs go through a shared-memory tile (the operand ring is idle now) so that every 256-byte row segment is written
+  // by 16 consecutive lanes
+  float* tile_h = reinterpret_cast<float*>(smem);
+  float* tile_z = tile_h + DT_M * DT_TP;
 #pragma unroll
-    for (int j = 0; j < DT_CW; j += 4) {
-      const float4 g4 = *reinterpret_cast<const float4*>(&svec[1][cb + j]), b4 = *reinterpret_cast<const float4*>(&svec[2][cb + j]);
-      float4 zh, h;
-      zh.x = (z[j] - mean) * rstd;
-      zh.y = (z[j + 1] - mean) * rstd;
-      zh.z = (z[j + 2] - mean) * rstd;
-      zh.w = (z[j + 3] - mean) * rstd;
-      h.x = elu(fmaf(zh.x, g4.x, b4.x));
-      h.y = elu(fmaf(zh.y, g4.y, b4.y));
-      h.z = elu(fmaf(zh.z, g4.z, b4.z));
-      h.w = elu(fmaf(zh.w, g4.w, b4.w));
-      *reinterpret_cast<float4*>(hrow + j) = h;
-      if (zrow != nullptr) *reinterpret_cast<float4*>(zrow + j) = zh;
+  for (int j = 0; j < DT_CW; j += 4) {
+    const float4 g4 = *reinterpret_cast<const float4*>(&svec[1][cb + j]), b4 = *reinterpret_cast<const float4*>(&svec[2][cb + j]);
+    float4 zh, h;
+    zh.x = (z[j] - mean) * rstd;
+    zh.y = (z[j + 1] - mean) * rstd;
+    zh.z = (z[j + 2] - mean) * rstd;
+    zh.w = (z[j + 3] - mean) * rstd;
+    h.x = elu(fmaf(zh.x, g4.x, b4.x));
+    h.y = elu(fmaf(zh.y, g4.y, b4.y));
+    h.z = elu(fmaf(zh.z, g4.z, b4.z));
+    h.w = elu(fmaf(zh.w, g4.w, b4.w));
+    *reinterpret_cast<float4*>(tile_h + row * DT_TP + cb + j) = h;
+    if (op.ZH != nullptr) *reinterpret_cast<float4*>(tile_z + row * DT_TP + cb + j) = zh;
+  }
+  if (rank == 0 && c == 0 && op.RS != nullptr && r0 + row < p.B) op.RS[r0 + row] = rstd;
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < DT_M * DT_N / 4 / DT_THREADS; ++u) {
+    const int f = tid + u * DT_THREADS, r = f / (DT_N / 4), c4 = f % (DT_N / 4);
+    if (r0 + r < p.B) {
+      const size_t off = (size_t)(r0 + r) * p.N + n0 + 4 * c4;
+      *reinterpret_cast<float4*>(op.H + off) = *reinterpret_cast<const float4*>(tile_h + r * DT_TP + 4 * c4);
+      if (op.ZH != nullptr) *reinterpret_cast<float4*>(op.ZH + off) = *reinterpret_cast<const float4*>(tile_z + r * DT_TP + 4 * c4);
     }
-    if (rank == 0 && c == 0 && op.RS != nullptr) op.RS[gr] = rstd;
   }
   if (tid == 64) mark(2, 7);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

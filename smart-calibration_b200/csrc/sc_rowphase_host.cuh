@@ -1,5 +1,6 @@
 // Host-side launch helpers shared by the two build configurations of the row-phase kernel (sc_rowphase_occ{1,2}.cu).
 #pragma once
+#include <stdlib.h>
 #include "sc_common.cuh"
 #include "sc_params.h"
 
@@ -21,10 +22,14 @@ static void cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int 
   attr[0].val.clusterDim.x = cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  // (no programmatic dependent launch here: clusters of the 256-CTA grid that become resident early next to the dense
-  //  kernels' CTAs were measured to leave the grid running in two waves)
+  // programmatic dependent launch of this 256-CTA grid is opt-in (SMARTCAL_PDL_ROW=1): with an early trigger in the preceding
+  // kernel its clusters became resident piecemeal and the grid ran in two waves
+  static int pdl_row = -1;
+  if (pdl_row < 0) { const char* e = getenv("SMARTCAL_PDL_ROW"); pdl_row = (e && e[0] == '1') ? 1 : 0; }
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_row ? 2 : 1;
 }
 template <typename K>
 static cudaError_t launch_k(K kern, size_t smem, const RowPhaseParams& p, int cs, int nclusters, cudaStream_t st) {
