@@ -1093,6 +1093,15 @@ static int run_dense_tc(sc_agent* a, const RowPhaseParams& p) {
          m.ph11[k], m.crit_w12[k], p.crit[k].b12, p.crit[k].g12, p.crit[k].be12, p.cw[k].p_h12, nullptr, nullptr);
   }
   d1.nops = d2.nops = n;
+  // reduction split: the K loop of one CTA is the latency of the launch, so K is halved across CTA pairs wherever the grid
+  // still fits the machine in one wave (SMARTCAL_DENSE_KS=a,b pins the two stages' splits)
+  d1.ks = 1; d2.ks = 2;
+  if (n * d1.nrb * (H1 / 64) * 2 <= a->sm_count && (K1 / 32) % 2 == 0) d1.ks = 2;
+  if (n * d2.nrb * (H2 / 64) * 2 > a->sm_count) d2.ks = 1;
+  if (const char* e = getenv("SMARTCAL_DENSE_KS")) {
+    int k1 = 0, k2 = 0;
+    if (sscanf(e, "%d,%d", &k1, &k2) == 2 && k1 >= 1 && k1 <= 2 && k2 >= 1 && k2 <= 2 && (K1 / 32) % k1 == 0) { d1.ks = k1; d2.ks = k2; }
+  }
   if (getenv("SMARTCAL_STAMPS")) {
     if (critic) d1.tl = a->tstamp + 2880 * 8;
     d1.ts = a->tstamp + (critic ? 1280 : 1792) * 8;

@@ -21,7 +21,7 @@
 namespace sc {
 
 constexpr int DT_M = 128, DT_N = 64;                         // batch rows / output features per CTA
-constexpr int DT_STAGES = 4;
+constexpr int DT_STAGES = 3;
 constexpr int DT_CW = DT_N / 4;                              // epilogue: features per thread
 constexpr int DT_X_BYTES = DT_M * 128, DT_W_BYTES = DT_N * 128;   // one k-chunk of 32 floats
 constexpr int DT_STAGE_BYTES = 2 * (DT_X_BYTES + DT_W_BYTES);     // raw + lo: 64 KB
@@ -29,6 +29,7 @@ constexpr int DT_THREADS = 512, DT_SPLIT_THREADS = DT_THREADS - 64;
 constexpr int DT_MAXCS = 8;
 constexpr int DT_TP = DT_N + 4;                              // output tile pitch (floats)
 static_assert(2 * DT_M * DT_TP * 4 <= DT_STAGE_BYTES * DT_STAGES, "output tiles must fit in the operand ring");
+constexpr int DT_PART_BYTES = DT_M * DT_TP * 4;             // split-K: the partner CTA's partial accumulators land here
 
 __device__ __forceinline__ uint64_t dt_desc(uint32_t saddr) {
   uint64_t d = 0;                                            // K-major, SWIZZLE_128B, 8-row atoms of 1024 B
@@ -71,7 +72,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
   const int tile = (int)cluster_idx();
   const int op_i = tile / p.nrb, rb = tile - op_i * p.nrb;
   const DenseTcOp& op = p.ops[op_i];
-  const int n0 = rank * DT_N, r0 = rb * DT_M;
+  // cluster = (N / 64 feature blocks) x (ks reduction halves): rank = kh * nfb + fb.  With ks = 2 the kh = 1 CTA reduces the
+  // second half of K and hands its raw accumulators to CTA fb (kh = 0) through distributed shared memory.
+  const int nfb = cs / p.ks, fb = rank % nfb, kh = rank / nfb;
+  const int n0 = fb * DT_N, r0 = rb * DT_M;
+  float* part = reinterpret_cast<float*>(smem + (size_t)DT_STAGES * DT_STAGE_BYTES);
   // debug timeline of CTA 0: each of three threads appends (globaltimer << 8 | tag) to its own shared-memory list (flushed at
   // the end, so that taking a mark costs no memory round trip)
   __shared__ unsigned long long tlbuf[3][62];
@@ -114,7 +119,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
   pdl_wait();                                                 // everything above overlapped the previous kernel's tail
   stamp(1);
   const uint32_t tmem = tmem_slot;
-  const int nk = (op.K + 31) >> 5;
+  const int nk_all = (op.K + 31) >> 5;
+  const int nk = nk_all / p.ks, kc0 = kh * nk;                // (launch_dense_tc checks divisibility)
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -125,8 +131,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
       if (lane == 0) {
         mark(0, 1);
         mbar_expect_tx(full_raw + slot, DT_X_BYTES + DT_W_BYTES);
-        tma_load_2d(reinterpret_cast<float*>(st), op.mapX, 32 * s, r0, full_raw + slot);
-        tma_load_2d(reinterpret_cast<float*>(st + DT_X_BYTES), op.mapW, 32 * s, n0, full_raw + slot);
+        tma_load_2d(reinterpret_cast<float*>(st), op.mapX, 32 * (kc0 + s), r0, full_raw + slot);
+        tma_load_2d(reinterpret_cast<float*>(st + DT_X_BYTES), op.mapW, 32 * (kc0 + s), n0, full_raw + slot);
       }
       __syncwarp();
     }
@@ -215,6 +221,35 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
   }
   __syncthreads();                                            // svec is complete
   if (tid == 64) mark(2, 8);
+  if (p.ks > 1) {
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");      // phase 1: every peer is resident
+    if (kh > 0) {
+      const uint32_t local = smem_u32(part + row * DT_TP + cb);
+      uint32_t remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(fb));
+#pragma unroll
+      for (int j = 0; j < DT_CW; j += 4)
+        asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote + 4u * j), "f"(z[j]), "f"(z[j + 1]), "f"(z[j + 2]), "f"(z[j + 3])
+                     : "memory");
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");    // phase 2: partials delivered
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    if (kh > 0) {
+      // nothing else to compute here: keep the cluster barriers of the statistics exchange balanced, then leave
+      asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      stamp(3);
+      if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(DT_N));
+      return;
+    }
+#pragma unroll
+    for (int j = 0; j < DT_CW; j += 4) {
+      const float4 q4 = *reinterpret_cast<const float4*>(part + row * DT_TP + cb + j);
+      z[j] += q4.x; z[j + 1] += q4.y; z[j + 2] += q4.z; z[j + 3] += q4.w;
+    }
+  }
 #pragma unroll
   for (int j = 0; j < DT_CW; ++j) z[j] += svec[0][cb + j];
   float s = 0.f;
@@ -231,15 +266,15 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
   }
   pm2[c][row] = m2;
   __syncthreads();
-  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+  if (p.ks == 1) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
   if (tid == 64) mark(2, 9);
   if (tid < DT_M * 2) {
     // (row, peer-half) pairs: thread t sends row t & 127 to the peers of parity t >> 7
     const int r_ = tid & (DT_M - 1);
     const float mc = (((psum[0][r_] + psum[1][r_]) + psum[2][r_]) + psum[3][r_]) * (1.0f / (float)DT_N);
     const float m2c = ((pm2[0][r_] + pm2[1][r_]) + pm2[2][r_]) + pm2[3][r_];
-    const uint32_t local = smem_u32(&xstat[rank][r_]);
-    for (int r = tid >> 7; r < cs; r += 2) {
+    const uint32_t local = smem_u32(&xstat[fb][r_]);
+    for (int r = tid >> 7; r < nfb; r += 2) {
       uint32_t remote;
       asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
       asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(mc), "f"(m2c) : "memory");
@@ -251,10 +286,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
   // combine the slices in rank order (same arithmetic as the mma.sync stage: count-weighted mean, Chan's M2 update)
   const float fN = (float)p.N;
   float msum = 0.f;
-  for (int r = 0; r < cs; ++r) msum = fmaf((float)DT_N, xstat[r][row].x, msum);
+  for (int r = 0; r < nfb; ++r) msum = fmaf((float)DT_N, xstat[r][row].x, msum);
   const float mean = msum / fN;
   float m2t = 0.f;
-  for (int r = 0; r < cs; ++r) {
+  for (int r = 0; r < nfb; ++r) {
     const float2 pv = xstat[r][row];
     const float d = pv.x - mean;
     m2t += pv.y + (float)DT_N * d * d;
@@ -279,7 +314,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
     *reinterpret_cast<float4*>(tile_h + row * DT_TP + cb + j) = h;
     if (op.ZH != nullptr) *reinterpret_cast<float4*>(tile_z + row * DT_TP + cb + j) = zh;
   }
-  if (rank == 0 && c == 0 && op.RS != nullptr && r0 + row < p.B) op.RS[r0 + row] = rstd;
+  if (fb == 0 && c == 0 && op.RS != nullptr && r0 + row < p.B) op.RS[r0 + row] = rstd;
   __syncthreads();
 #pragma unroll
   for (int u = 0; u < DT_M * DT_N / 4 / DT_THREADS; ++u) {
@@ -317,7 +352,7 @@ __global__ void __launch_bounds__(128) k_gather_mb(float* mb_s, float* mb_s2, co
   }
 }
 
-size_t dense_tc_smem_bytes() { return (size_t)DT_STAGES * DT_STAGE_BYTES + 1024; }
+size_t dense_tc_smem_bytes() { return (size_t)DT_STAGES * DT_STAGE_BYTES + DT_PART_BYTES + 1024; }
 
 cudaError_t launch_dense_tc(const DenseTcParams& p, cudaStream_t st) {
   static bool configured = false;
@@ -326,8 +361,18 @@ cudaError_t launch_dense_tc(const DenseTcParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int cs = p.N / DT_N;
-  if (cs < 1 || cs > DT_MAXCS || cs * DT_N != p.N) return cudaErrorInvalidValue;
+  const int nfb = p.N / DT_N, cs = nfb * p.ks;
+  if (nfb < 1 || nfb > DT_MAXCS || nfb * DT_N != p.N || p.ks < 1 || p.ks > 2 || cs > 16) return cudaErrorInvalidValue;
+  for (int i = 0; i < p.nops; ++i)
+    if (((p.ops[i].K + 31) / 32) % p.ks != 0) return cudaErrorInvalidValue;
+  if (cs > 8) {
+    static bool big = false;
+    if (!big) {
+      cudaError_t e = cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e != cudaSuccess) return e;
+      big = true;
+    }
+  }
   cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
   cudaLaunchAttribute attr[2];
   cfg.gridDim = dim3(p.nops * p.nrb * cs, 1, 1);

@@ -166,7 +166,8 @@ struct DenseTcOp {
 };
 struct DenseTcParams {
   DenseTcOp ops[5];
-  int nops, N, B, nrb;             // layer width (cluster size = N / 64), batch rows, 128-row blocks
+  int nops, N, B, nrb;             // layer width, batch rows, 128-row blocks
+  int ks;                          // reduction split (1 or 2); cluster size = (N / 64) * ks
   unsigned long long* tl;          // optional debug timeline of CTA 0
   unsigned long long* ts;          // optional [CTA][8] globaltimer stamps: entry, dependency met, accumulator done, end
 };
