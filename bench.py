@@ -42,6 +42,16 @@ CRITIC_PHASE_BYTES = B * ((2 * S + A + 1) * 4 + 1) + (PA + 4 * PC) * 4
 CRITIC_PHASE_FLOP = 2 * B * (379392 + 4 * 354880 + 2 * (131072 + 8192 + 320))   # fwd actor + 4 critic fwd + 2 critic dgrad (fc12, fc22, fc3)
 
 
+DENSE_FLOP = 2 * B * 5 * (S * 512 + 512 * 256)       # the two wide layers of the five passes of the critic phase
+
+
+def peaks_tf32():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return 0.5 * float(json.load(open(p))["bf16_tflops"])
+    return 0.5 * 2250.0
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -151,12 +161,15 @@ def run_ours(args):
 
     # per-kernel CUDA-event timing (second pass so that the event records do not perturb the headline)
     dev.enable_timing(True)
-    for w in range(6):
+    for w in range(8):
         dev.kernel_time(w, reset=True)
     timed_steps(dev, min(args.steps, 100), flush)
-    kt = [dev.kernel_time(w, reset=True) for w in range(6)]
+    kt = [dev.kernel_time(w, reset=True) for w in range(8)]
     dev.enable_timing(False)
-    names = ["critic_rowphase", "critic_wgrad_adam", "actor_rowphase", "actor_wgrad_adam", "per_sample", "per_update"]
+    # *_rowphase are the phase groups (minibatch gather + the two tcgen05 dense launches + the row-phase tail/dgrad kernel);
+    # *_dense_tc is the part of the group spent in k_gather_mb + 2 x k_dense_tc
+    names = ["critic_rowphase", "critic_wgrad_adam", "actor_rowphase", "actor_wgrad_adam", "per_sample", "per_update",
+             "critic_dense_tc", "actor_dense_tc"]
     kern = {n: {"avg_us": (ms / max(cnt, 1)) * 1e3, "launches": cnt} for n, (ms, cnt) in zip(names, kt)}
 
     # end-to-end through the public API with host buffers (reference-RNG mode: host draws + H2D every step)
@@ -225,15 +238,28 @@ def run_ours(args):
         return
     peak, peak_src = peaks()
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r1q_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("critic_rowphase_dram_bytes")
+        traffic = json.load(open(tp)).get("critic_phase_dram_bytes")
     crit_s = kern["critic_rowphase"]["avg_us"] * 1e-6
-    roof = {"bound": "hbm", "kernel": "k_rowphase<PROG_CRITIC>", "achieved": CRITIC_PHASE_BYTES / crit_s / 1e9, "peak": peak,
+    dense_s = kern["critic_dense_tc"]["avg_us"] * 1e-6
+    tf32_peak = peaks_tf32()
+    roof = {"bound": "hbm", "kernel": "critic phase = k_gather_mb + 2 x k_dense_tc + k_rowphase<PROG_CRITIC> (one dependent chain, timed as a group)",
+            "achieved": CRITIC_PHASE_BYTES / crit_s / 1e9, "peak": peak,
             "unit": "GB/s", "frac": CRITIC_PHASE_BYTES / crit_s / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": CRITIC_PHASE_BYTES,
-            "fp32_ffma": {"achieved_tflops": CRITIC_PHASE_FLOP / crit_s / 1e12, "peak_tflops": 148 * 128 * 2 * 1.965e9 / 1e12,
-                          "note": "not HBM-bound: the GEMM stages are bound by the legacy mma.sync TF32 pipe (3 MMAs per product for fp32 parity), the rest by latency (DESIGN.md)"},
+            "note": "not HBM-bound: a chain of latency-bound stages on 256 rows (DESIGN.md 5); the wide layers run on tcgen05 (next object), "
+                    "the row-local tail and the dgrad stage on FP32 / mma.sync",
+            "tensor": {"kernel": "k_dense_tc (critic phase: 5 x fc1/fc11 then 5 x fc2/fc12, with the gather launch)",
+                       "algorithmic_tflop_per_phase": DENSE_FLOP / 1e12,
+                       "achieved": DENSE_FLOP / dense_s / 1e12 if dense_s > 0 else None,
+                       "issued": 3 * DENSE_FLOP / dense_s / 1e12 if dense_s > 0 else None,
+                       "peak": tf32_peak, "unit": "TFLOP/s",
+                       "frac": DENSE_FLOP / dense_s / 1e12 / tf32_peak if dense_s > 0 else None,
+                       "peak_source": "0.5 x MEASURED_PEAKS.json bf16_tflops (kind::tf32 runs at half the bf16 rate; tools/probe/mma_rate.cu: "
+                                      "2015 vs 4030 MAC/clk/SM)",
+                       "note": "fp32 parity costs 3 TF32 products per MAC ('issued'); at 20-80 CTAs of one 128x64 tile each the launches are "
+                               "latency- and shared-memory-bandwidth-bound, not tensor-bound (DESIGN.md 5)"},
             "step": {"algorithmic_bytes": STEP_BYTES, "achieved": STEP_BYTES / (ms_cold / args.steps * 1e-3) / 1e9,
                      "frac": STEP_BYTES / (ms_cold / args.steps * 1e-3) / 1e9 / peak}}
     cpu = cpu_baseline(sample_seconds=12.0)

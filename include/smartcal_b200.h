@@ -164,7 +164,9 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise_or_null, sc_learn_stats* s
 int sc_agent_soft_update(sc_agent* a, float tau);
 /* kernels launched by this library since the handle was created (bench.py "gpu_launches") */
 int64_t sc_agent_launch_count(sc_agent* a);
-/* CUDA-event time (ms) of the dominant kernel accumulated since the last call with reset!=0 */
+/* CUDA-event time (ms) accumulated since the last call with reset!=0 (after sc_agent_enable_kernel_timing): which = 0 critic
+ * row-phase group, 1 critic wgrad+Adam, 2 actor row-phase group, 3 actor wgrad+Adam, 4 PER sample, 5 PER update,
+ * 6 / 7 the tensor-core dense launches inside groups 0 / 2 */
 int sc_agent_kernel_time(sc_agent* a, int which, int reset, double* ms_total, int64_t* launches);
 int sc_agent_enable_kernel_timing(sc_agent* a, int on);
 

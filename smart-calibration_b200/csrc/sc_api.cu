@@ -221,7 +221,7 @@ struct sc_agent {
   uint64_t noise_ctr;
   int64_t launches;
   bool timing;
-  KernelTimer timers[6];
+  KernelTimer timers[8];              // 0..5 phase groups (bench.py), 6/7 the tcgen05 dense launches of the critic / actor phase
 };
 
 static void timer_begin(sc_agent* a, int which, cudaEvent_t* ev0, cudaEvent_t* ev1) {
@@ -1118,8 +1118,12 @@ static int run_rowphase(sc_agent* a, const RowPhaseParams& p_in, int timer_id) {
   if (timer_id >= 0) timer_begin(a, timer_id, &e0, &e1);
   RowPhaseParams p = p_in;
   if (a->dense_tc && p.program != PROG_ACT) {
+    cudaEvent_t d0, d1;
+    const int dense_timer = timer_id == 0 ? 6 : timer_id == 2 ? 7 : -1;
+    if (dense_timer >= 0) timer_begin(a, dense_timer, &d0, &d1);
     int rc = run_dense_tc(a, p);
     if (rc) return rc;
+    if (dense_timer >= 0) timer_end(a, dense_timer, d0, d1);
     p.skip_dense = 1;
   }
   const int ncl = p.program == PROG_ACT ? 1 : a->nclusters;
@@ -1380,7 +1384,7 @@ int sc_agent_enable_kernel_timing(sc_agent* a, int on) {
   return SC_OK;
 }
 int sc_agent_kernel_time(sc_agent* a, int which, int reset, double* ms_total, int64_t* launches) {
-  if (!a || which < 0 || which >= 6) return fail(SC_ERR_ARG, "bad argument");
+  if (!a || which < 0 || which >= 8) return fail(SC_ERR_ARG, "bad argument");
   CK(cudaStreamSynchronize(a->st));
   KernelTimer& t = a->timers[which];
   for (auto& pr : t.pending) {
