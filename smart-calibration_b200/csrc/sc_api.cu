@@ -192,6 +192,13 @@ struct sc_agent {
   std::map<std::string, sc_tensor_info> buffers;
   float *y, *err, *part, *is_w, *is_wsum, *eps[3], *stats, *hint_out, *rho_dev, *ps_out, *admm_lambda, *admm_y0, *admm_a0;
   int *bidx, *tree_idx;
+  // PER presampling (device RNG): while the rest of learn() runs, the side stream already draws the NEXT minibatch from the
+  // updated tree into the alternate buffers; learn() swaps them in if nothing touched the replay state in between
+  int *bidx_alt, *tree_idx_alt;
+  float *is_w_alt, *is_wsum_alt;
+  uint64_t sample_ctr;                // draws of the minibatch samplers (separate from the noise counter)
+  bool presampled, quiet;             // quiet: no store / tree write / buffer access since the end of the previous learn()
+  double presample_beta;
   unsigned long long* tstamp;
   double* u01;
   float *obs_dev, *act_eps, *act_out, *act_aux, *store_stage;
@@ -224,6 +231,13 @@ struct sc_agent {
   KernelTimer timers[8];              // 0..5 phase groups (bench.py), 6/7 the tcgen05 dense launches of the critic / actor phase
 };
 
+// Anything that may change what the next minibatch draw would see (stores, tree writes, raw buffer access, an explicit
+// sample) drops a pending presample and gives its draw counter back, so results do not depend on whether presampling ran.
+static void touch_replay(sc_agent* a) {
+  if (!a) return;
+  if (a->presampled) { a->presampled = false; a->sample_ctr--; }
+  a->quiet = false;
+}
 static void timer_begin(sc_agent* a, int which, cudaEvent_t* ev0, cudaEvent_t* ev1) {
   if (!a->timing) return;
   KernelTimer& t = a->timers[which];
@@ -317,6 +331,10 @@ static size_t carve(sc_agent* a, void* base) {
   a->rho_dev = cv.f(4);
   a->bidx = (int*)cv.take(sizeof(int) * B);
   a->tree_idx = (int*)cv.take(sizeof(int) * B);
+  a->bidx_alt = (int*)cv.take(sizeof(int) * B);
+  a->tree_idx_alt = (int*)cv.take(sizeof(int) * B);
+  a->is_w_alt = cv.f(B);
+  a->is_wsum_alt = cv.f(4);
   reg("batch_idx", a->bidx, B, 1, 1, 4);
   reg("tree_idx", a->tree_idx, B, 1, 1, 4);
   a->buffers["batch_idx"].is_int = 1;   // int32
@@ -774,6 +792,7 @@ int sc_agent_create(const sc_config* cfg, void* arena, size_t arena_bytes, void*
   a->t_actor = a->t_critic = 0;
   a->per_beta = 0.4;   // PER.beta, enet_sac.py:210
   a->batch_ready = false;
+  a->presampled = false; a->quiet = false; a->presample_beta = 0.0; a->sample_ctr = 0;
   a->alpha = (float)cfg->alpha;
   a->rho = 0.f;
   a->admm_rho = cfg->admm_rho;
@@ -849,6 +868,7 @@ int sc_agent_tensor(sc_agent* a, int net, int slot, const char* name, sc_tensor_
 
 int sc_agent_buffer(sc_agent* a, const char* name, sc_tensor_info* out) {
   if (!a || !name || !out) return fail(SC_ERR_ARG, "null argument");
+  touch_replay(a);                            // the caller may write the tree / replay arrays through the returned pointer
   auto it = a->buffers.find(name);
   if (it == a->buffers.end()) return fail(SC_ERR_ARG, "unknown buffer '%s'", name);
   *out = it->second;
@@ -864,6 +884,7 @@ int sc_agent_get_counters(sc_agent* a, int64_t* mem_cntr, int64_t* learn_counter
   return SC_OK;
 }
 int sc_agent_set_counters(sc_agent* a, int64_t mem_cntr, int64_t learn_counter, int64_t data_pointer, double per_beta) {
+  touch_replay(a);
   if (!a) return fail(SC_ERR_ARG, "null agent");
   a->mem_cntr = mem_cntr; a->learn_counter = learn_counter; a->data_pointer = data_pointer; a->per_beta = per_beta;
   a->data_length = mem_cntr < a->C ? mem_cntr : a->C;
@@ -895,6 +916,7 @@ static int store_common(sc_agent* a, const float* tr_dev, int priority_mode, dou
   return SC_OK;
 }
 int sc_replay_store_host(sc_agent* a, const float* transition_host, int priority_mode, double priority) {
+  touch_replay(a);
   if (!a || !transition_host) return fail(SC_ERR_ARG, "null argument");
   // the staging slot is reused by the next call: wait for the previous copy-out kernel (one tiny sync per env step)
   CK(cudaStreamSynchronize(a->st));
@@ -903,10 +925,12 @@ int sc_replay_store_host(sc_agent* a, const float* transition_host, int priority
   return store_common(a, a->store_stage, priority_mode, priority);
 }
 int sc_replay_store_dev(sc_agent* a, const float* transitions_dev, int index, int priority_mode, double priority) {
+  touch_replay(a);
   if (!a || !transitions_dev || index < 0) return fail(SC_ERR_ARG, "bad argument");
   return store_common(a, transitions_dev + (size_t)index * a->T, priority_mode, priority);
 }
 int sc_replay_fill_host(sc_agent* a, const float* transitions_host, int n, const double* priorities_host) {
+  touch_replay(a);
   if (!a || !transitions_host || n < 0 || n > a->C) return fail(SC_ERR_ARG, "bad argument");
   float* tmp = nullptr;
   CK(cudaMalloc(&tmp, (size_t)n * a->T * sizeof(float)));
@@ -933,6 +957,7 @@ int sc_replay_fill_host(sc_agent* a, const float* transitions_host, int n, const
 }
 
 int sc_replay_set_batch_host(sc_agent* a, const int32_t* idx_host, int n) {
+  touch_replay(a);
   if (!a || !idx_host || n != a->B) return fail(SC_ERR_ARG, "expected %d indices", a ? a->B : 0);
   CK(cudaStreamSynchronize(a->st));   // h_idx may still be in flight from the previous step
   memcpy(a->h_idx, idx_host, (size_t)n * sizeof(int32_t));
@@ -941,15 +966,17 @@ int sc_replay_set_batch_host(sc_agent* a, const int32_t* idx_host, int n) {
   return SC_OK;
 }
 int sc_replay_sample_uniform_dev(sc_agent* a) {
+  touch_replay(a);
   if (!a) return fail(SC_ERR_ARG, "null agent");
   const int n = (int)(a->mem_cntr < a->C ? a->mem_cntr : a->C);
   if (n < a->B) return fail(SC_ERR_STATE, "only %d transitions stored, batch is %d", n, a->B);
-  CK(launch_sample_uniform(n, a->B, a->cfg.rng_seed, 0x5000000000ull + (a->noise_ctr++), a->bidx, a->st));
+  CK(launch_sample_uniform(n, a->B, a->cfg.rng_seed, 0x5000000000ull + (a->sample_ctr++), a->bidx, a->st));
   a->launches++;
   a->batch_ready = true;
   return SC_OK;
 }
 int sc_per_sample(sc_agent* a, const double* u01_host, int32_t* tree_idx_host_out, float* is_weights_host_out) {
+  touch_replay(a);
   if (!a) return fail(SC_ERR_ARG, "null agent");
   if (!a->rp.tree) return fail(SC_ERR_STATE, "agent was created with prioritized=0");
   const double* u = nullptr;
@@ -962,7 +989,7 @@ int sc_per_sample(sc_agent* a, const double* u01_host, int32_t* tree_idx_host_ou
   a->per_beta = fmin(1.0, a->per_beta + 1e-4);   // enet_sac.py:288
   cudaEvent_t e0, e1;
   timer_begin(a, 4, &e0, &e1);
-  CK(launch_per_sample(a->rp.tree, a->C, a->B, u, a->cfg.rng_seed, 0x6000000000ull + (a->noise_ctr++), a->per_beta, a->tree_idx,
+  CK(launch_per_sample(a->rp.tree, a->C, a->B, u, a->cfg.rng_seed, 0x6000000000ull + (a->sample_ctr++), a->per_beta, a->tree_idx,
                        a->bidx, a->is_w, a->is_wsum, a->st));
   timer_end(a, 4, e0, e1);
   a->launches++;
@@ -973,6 +1000,7 @@ int sc_per_sample(sc_agent* a, const double* u01_host, int32_t* tree_idx_host_ou
   return SC_OK;
 }
 int sc_per_update_host(sc_agent* a, const int32_t* tree_idx_host, const float* abs_err_host, int n, float* priorities_host_out) {
+  touch_replay(a);
   if (!a || !tree_idx_host || !abs_err_host || n != a->B) return fail(SC_ERR_ARG, "bad argument");
   if (!a->rp.tree) return fail(SC_ERR_STATE, "agent was created with prioritized=0");
   CK(cudaMemcpyAsync(a->tree_idx, tree_idx_host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, a->st));
@@ -1249,10 +1277,23 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
   const bool sac = a->cfg.kind == SC_KIND_SAC;
   const bool per = a->cfg.prioritized != 0;
   int rc;
+  const bool was_quiet = a->quiet;          // nothing touched the replay state since the previous learn() returned
+  bool internal_sample = false;
   if (!a->batch_ready) {
-    rc = per ? sc_per_sample(a, nullptr, nullptr, nullptr) : sc_replay_sample_uniform_dev(a);
-    if (rc) return rc;
+    internal_sample = true;
+    if (per && a->presampled) {
+      // the minibatch was drawn on the side stream during the previous step (after its priority update): swap it in
+      std::swap(a->bidx, a->bidx_alt); std::swap(a->tree_idx, a->tree_idx_alt);
+      std::swap(a->is_w, a->is_w_alt); std::swap(a->is_wsum, a->is_wsum_alt);
+      a->buffers["batch_idx"].dev_ptr = a->bidx; a->buffers["tree_idx"].dev_ptr = a->tree_idx; a->buffers["is_weights"].dev_ptr = a->is_w;
+      a->per_beta = a->presample_beta;
+      a->presampled = false;
+    } else {
+      rc = per ? sc_per_sample(a, nullptr, nullptr, nullptr) : sc_replay_sample_uniform_dev(a);
+      if (rc) return rc;
+    }
   }
+  if (a->presampled) { a->presampled = false; a->sample_ctr--; }   // (a batch supplied from outside supersedes it)
   a->batch_ready = false;
   const bool host_noise = noise && (noise->eps_next_host || noise->eps_cur_host || noise->eps_dual_host);
   if (host_noise) CK(cudaStreamSynchronize(a->st));   // staging buffers may be in flight
@@ -1289,6 +1330,15 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
       CK(cudaEventRecord(a->ev_fork, a->st));
       CK(cudaStreamWaitEvent(a->st_side, a->ev_fork, 0));
       CK(launch_per_update(a->rp.tree, a->C, a->B, a->tree_idx, a->err, a->cfg.per_clip, nullptr, a->ps_out, a->st_side));
+      if (internal_sample && was_quiet && !getenv("SMARTCAL_NO_PRESAMPLE")) {
+        // learn() is being called back to back with the library's own sampling: draw the next minibatch now, from the tree
+        // this update just produced (PER.sample_buffer of the next step, enet_sac.py:270-312), under the remaining kernels
+        a->presample_beta = fmin(1.0, a->per_beta + 1e-4);
+        CK(launch_per_sample(a->rp.tree, a->C, a->B, nullptr, a->cfg.rng_seed, 0x6000000000ull + (a->sample_ctr++), a->presample_beta,
+                             a->tree_idx_alt, a->bidx_alt, a->is_w_alt, a->is_wsum_alt, a->st_side));
+        a->launches++;
+        a->presampled = true;
+      }
       CK(cudaEventRecord(a->ev_join, a->st_side));
       per_forked = true;
     }
@@ -1349,6 +1399,7 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
     }
   }
   if (per_forked) CK(cudaStreamWaitEvent(a->st, a->ev_join, 0));     // join: later work on the agent's stream sees the updated tree
+  a->quiet = internal_sample;               // cleared by anything that may change what the next sample would see
   a->learn_counter++;
   if (stats_host) {
     CK(cudaMemcpyAsync(a->h_stats, a->stats, 16 * sizeof(float), cudaMemcpyDeviceToHost, a->st));

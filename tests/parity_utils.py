@@ -77,16 +77,17 @@ class Report:
             print(f"  {'FAIL' if bad else 'ok  '} {name:34s} max ulp diff={u}")
 
     def add_params(self, name, got, ref, grad_ref, vhat_sqrt, lr):
-        """Adam-aware parameter check for ONE step from identical state: the update is lr_t*mhat/(sqrt(vhat)+eps), so an
-        error dg in this step's gradient moves it by at most lr*min(1, |dg|/sqrt(vhat)).  With |dg| <= GRAD_RTOL*max|g|
+        """Adam-aware parameter check for ONE step from identical state: the update is lr_t*mhat/(sqrt(vhat)+eps), which
+        lies in [-lr, lr], so an error dg in this step's gradient moves it by at most lr*min(2, |dg|/sqrt(vhat)) (the cap 2 is
+        a sign flip of a near-zero gradient on the first step, where the update is lr*sign(g)).  With |dg| <= GRAD_RTOL*max|g|
         (checked separately) the admissible deviation of element i is
-            PARAM_ATOL*(1+max|p|) + lr*min(1, 2*GRAD_RTOL*max|g| / sqrt(vhat_i))."""
+            PARAM_ATOL*(1+max|p|) + lr*min(2, 2*GRAD_RTOL*max|g| / sqrt(vhat_i))."""
         got = np.asarray(got, np.float64).reshape(-1)
         ref = np.asarray(ref, np.float64).reshape(-1)
         g = np.abs(np.asarray(grad_ref, np.float64).reshape(-1))
         sv = np.maximum(np.asarray(vhat_sqrt, np.float64).reshape(-1), 1e-30)
         gmax = max(g.max(), 1e-30)
-        allowed = PARAM_ATOL * (1 + np.abs(ref).max()) + lr * np.minimum(1.0, 2 * GRAD_RTOL * gmax / sv)
+        allowed = PARAM_ATOL * (1 + np.abs(ref).max()) + lr * np.minimum(2.0, 2 * GRAD_RTOL * gmax / sv)
         self.allowed[name] = allowed
         d = np.abs(got - ref)
         ratio = float((d / allowed).max())

@@ -177,3 +177,48 @@ def test_main_sac_shaped_loop_with_stub_env():
         scores.append(score.cpu().data.item() / loop)
     assert agent.replaymem.mem_cntr == 80 and agent.learn_counter == 80 - 63
     assert np.isfinite(scores).all()
+
+
+def test_per_presample_is_transparent(monkeypatch):
+    """rng='device', prioritized: back-to-back learn() calls draw the next minibatch on the side stream during the current
+    step.  That must be invisible: same parameters bit for bit as with SMARTCAL_NO_PRESAMPLE=1, including across a store
+    between two steps (which discards the pending draw) and a raw tree access."""
+    from smartcal_b200.elasticnet import enet_sac
+    from smartcal_b200.synth import make_transitions, pack
+
+    def run(no_presample):
+        if no_presample:
+            monkeypatch.setenv("SMARTCAL_NO_PRESAMPLE", "1")
+        else:
+            monkeypatch.delenv("SMARTCAL_NO_PRESAMPLE", raising=False)
+        torch.manual_seed(5)
+        agent = enet_sac.Agent(gamma=0.99, lr_a=1e-3, lr_c=1e-3, input_dims=[24], batch_size=32, n_actions=2, max_mem_size=128,
+                               tau=0.005, reward_scale=1, alpha=0.03, rng="device", prioritized=True)
+        dev = agent._dev
+        tr = pack(make_transitions(1, 129, 24, 2))
+        dev.fill(tr[:128])
+        batches = []
+        for _ in range(5):
+            dev.learn()
+        batches.append(dev.buffer("batch_idx")[:, 0].cpu().numpy().copy())        # (raw buffer access: drops the pending draw)
+        for _ in range(3):
+            dev.learn()
+        dev.store(tr[128])                                                          # a store between two steps
+        for _ in range(4):
+            dev.learn()
+        batches.append(dev.buffer("batch_idx")[:, 0].cpu().numpy().copy())
+        beta = dev.counters()[3]
+        params = {k: v.detach().cpu().clone() for net in (agent.actor, agent.critic_1, agent.critic_2, agent.target_critic_1)
+                  for k, v in net.state_dict().items()}
+        tree = dev.buffer("tree")[:, 0].cpu().numpy().copy()
+        return batches, beta, params, tree, dev.launch_count()
+
+    b0, beta0, p0, t0, n0 = run(False)
+    b1, beta1, p1, t1, n1 = run(True)
+    assert n0 > n1, "the presampling path did not run"
+    assert beta0 == beta1 == pytest.approx(0.4 + 12e-4)
+    for x, y in zip(b0, b1):
+        assert np.array_equal(x, y)
+    assert np.array_equal(t0, t1)
+    for (k, v), (k2, v2) in zip(p0.items(), p1.items()):
+        assert k == k2 and torch.equal(v, v2), k

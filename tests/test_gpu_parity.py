@@ -63,3 +63,18 @@ def test_td3_admm_hint_loop():
     # enet_td3.py:310-361 (five inner actor steps, adaptive penalty), admm_rho set after construction like main_td3.py:22
     _assert(PU.td3_parity_report(S=24, A=2, B=32, C=64, steps=4, seed=13, prioritized=True, use_hint=True, admm_rho=1.0))
     _assert(PU.td3_parity_report(S=24, A=2, B=32, C=64, steps=2, seed=14, prioritized=False, use_hint=True))
+
+
+def test_dense_stage_variants(monkeypatch):
+    # the wide forward layers have two implementations: k_dense_tc launches (default; reduction optionally split across
+    # CTA pairs) and the mma.sync stages inside k_rowphase (SMARTCAL_DENSE=mma, also what choose_action uses).  Same parity
+    # bar for all of them.
+    monkeypatch.setenv("SMARTCAL_DENSE", "mma")
+    _assert(PU.sac_parity_report(S=24, A=2, B=32, C=64, steps=2, seed=21))
+    _assert(PU.sac_parity_report(S=420, A=2, B=64, C=256, steps=2, seed=22, prioritized=True))
+    monkeypatch.delenv("SMARTCAL_DENSE")
+    for ks in ("1,1", "2,2"):
+        monkeypatch.setenv("SMARTCAL_DENSE_KS", ks)
+        _assert(PU.sac_parity_report(S=420, A=2, B=64, C=256, steps=2, seed=23, prioritized=True))
+        _assert(PU.sac_parity_report(S=56, A=3, B=200, C=256, steps=2, seed=24))     # two row blocks, the second ragged
+    monkeypatch.delenv("SMARTCAL_DENSE_KS")
