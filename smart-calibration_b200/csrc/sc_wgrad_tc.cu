@@ -13,6 +13,7 @@
 // Warp roles (512 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue (one thread), warps 2..15 = lo-split;
 // epilogue: warps 2..5 move the accumulator TMEM -> registers -> shared tile, then ALL warps apply Adam (its IEEE divisions and
 // square roots make the epilogue latency-bound on few threads).  Three 48 KB stages of 32 batch rows.
+#include <stdlib.h>
 #include "sc_common.cuh"
 #include "sc_params.h"
 
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  pdl_wait();                                                 // (programmatic dependent launch: the set-up above ran under the previous kernel)
   const uint32_t tmem = tmem_slot;
   const int nstages = (p.B + TC_BR - 1) / TC_BR;
   unsigned it = 0;                                            // stages streamed so far by this CTA (all roles count alike)
@@ -266,8 +268,19 @@ cudaError_t launch_wgrad_tc(const WgradTcParams& p, int grid, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  k_wgrad_tc<<<grid, TC_THREADS, wgrad_tc_smem_bytes(), st>>>(p);
-  return cudaGetLastError();
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("SMARTCAL_PDL_WGRAD"); pdl = (e && e[0] == '0') ? 0 : 1; }
+  cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = wgrad_tc_smem_bytes();
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k_wgrad_tc, p);
 }
 
 }  // namespace sc
