@@ -1124,6 +1124,7 @@ static int run_dense_tc(sc_agent* a, const RowPhaseParams& p) {
   // reduction split: the K loop of one CTA is the latency of the launch, so K is halved across CTA pairs wherever the grid
   // still fits the machine in one wave (SMARTCAL_DENSE_KS=a,b pins the two stages' splits)
   d1.ks = 1; d2.ks = 2;
+  d2.late_trigger = 1;
   if (n * d1.nrb * (H1 / 64) * 2 <= a->sm_count && (K1 / 32) % 2 == 0) d1.ks = 2;
   if (n * d2.nrb * (H2 / 64) * 2 > a->sm_count) d2.ks = 1;
   if (const char* e = getenv("SMARTCAL_DENSE_KS")) {

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
   }
   // ---------------- epilogue (all warps): bias, LayerNorm across the cluster, ELU, stores ----------------
   mbar_wait(&acc_done, 0);
-  pdl_launch();                                               // the next kernel may set itself up under this epilogue
+  if (!p.late_trigger) pdl_launch();                          // the next kernel may set itself up under this epilogue
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (tid == 64) mark(2, 6);
   stamp(2);
@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
       // nothing else to compute here: keep the cluster barriers of the statistics exchange balanced, then leave
       asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
       asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+      if (p.late_trigger) pdl_launch();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
       stamp(3);
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
     }
   }
   if (tid == 64) mark(2, 7);
+  if (p.late_trigger) pdl_launch();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   stamp(3);

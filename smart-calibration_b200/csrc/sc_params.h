@@ -168,6 +168,7 @@ struct DenseTcParams {
   DenseTcOp ops[5];
   int nops, N, B, nrb;             // layer width, batch rows, 128-row blocks
   int ks;                          // reduction split (1 or 2); cluster size = (N / 64) * ks
+  int late_trigger;                // 1: release the dependent launch only after the outputs are stored (next kernel is a big cluster grid)
   unsigned long long* tl;          // optional debug timeline of CTA 0
   unsigned long long* ts;          // optional [CTA][8] globaltimer stamps: entry, dependency met, accumulator done, end
 };

@@ -22,10 +22,11 @@ static void cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int 
   attr[0].val.clusterDim.x = cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  // programmatic dependent launch of this 256-CTA grid is opt-in (SMARTCAL_PDL_ROW=1): with an early trigger in the preceding
-  // kernel its clusters became resident piecemeal and the grid ran in two waves
+  // programmatic dependent launch (SMARTCAL_PDL_ROW=0 turns it off).  The kernel in front must release it LATE (k_dense_tc
+  // stage 2 does, after its stores): released early, the clusters of this 256-CTA grid became resident piecemeal next to
+  // the dense CTAs and the grid ran in two waves (+40 us, measured)
   static int pdl_row = -1;
-  if (pdl_row < 0) { const char* e = getenv("SMARTCAL_PDL_ROW"); pdl_row = (e && e[0] == '1') ? 1 : 0; }
+  if (pdl_row < 0) { const char* e = getenv("SMARTCAL_PDL_ROW"); pdl_row = (e && e[0] == '0') ? 0 : 1; }
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
