@@ -1017,10 +1017,6 @@ static void fill_common(sc_agent* a, RowPhaseParams& p) {
   memset(&p, 0, sizeof(p));
   p.kind = a->cfg.kind;
   p.closs_scale = (a->cfg.flags & SC_FLAG_CRITIC_LOSS_SUM) ? (float)a->B : 1.f;
-  {
-    const char* f = getenv("SMARTCAL_FWD");
-    p.fwd_tc = (f && !strcmp(f, "tc")) ? 1 : 0;          // experimental tcgen05 forward stages: only in builds with -DSC_ENABLE_FWD_TC
-  }
   p.B = a->B; p.S = a->S; p.Sp = a->Sp; p.A = a->A; p.Ap = a->Ap;
   p.crit[0] = critic_ptrs(a->params + a->off_c1, a->Lc);
   p.crit[1] = critic_ptrs(a->params + a->off_c2, a->Lc);

@@ -69,7 +69,6 @@ struct RowPhaseParams {
   // same values k_fill_normal would have written) and stored to eps_store for inspection
   int eps_inline; unsigned long long eps_seed, eps_stream; float* eps_store;
   int skip_dense;                            // 1: gather + both dense stages already ran as k_dense_tc launches (sc_dense_tc.cu)
-  int fwd_tc;                                // 1: forward GEMM stages on tcgen05 (weights in TMEM), 0: mma.sync (SMARTCAL_FWD=mma)
   float closs_scale;                         // critic-loss gradient scale: 1 (mean of squares), B (DDPG's sum of squares)
   int B, S, Sp, A, Ap;
   ActorP actor;                              // actor evaluated in this phase

@@ -51,13 +51,7 @@ constexpr int SM_RED = 160 * REDROWS;                  // max over (KS, NC) in {
 constexpr int SM_Z = REDROWS * WCOLS;
 constexpr int SM_STAT = MAXOPS * MAXROWS * 2;
 constexpr int SM_ZK = SC_CFG_ZK;                       // raw pre-LayerNorm outputs of a stage, kept on chip between the two barriers
-#ifdef SC_ENABLE_FWD_TC
-constexpr int SM_XLO = 2 * REDROWS * 32;                 // tcgen05 forward path: small parts of the X k-blocks (one per warp group)
-#else
-constexpr int SM_XLO = 0;
-#endif
-constexpr int SM_TOTAL_FLOATS = SM_RING + SM_RED + SM_Z + SM_STAT + SM_ZK + SM_XLO;
-static_assert((SM_RING + SM_RED + SM_Z + SM_STAT + SM_ZK) % 256 == 0, "X_lo staging must keep the 1024-byte swizzle alignment");
+constexpr int SM_TOTAL_FLOATS = SM_RING + SM_RED + SM_Z + SM_STAT + SM_ZK;
 
 __host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
 
@@ -70,11 +64,6 @@ struct Pipe {
   uint64_t* full;     // [NSTAGE] armed by the producer (expect_tx), completed by the bulk copies
   uint64_t* empty;    // [NSTAGE] one arrival per consumer warp
   unsigned long long* tl;   // optional timeline of CTA 0 / thread 0 (globaltimer), tl[0] = next free index
-  // tcgen05 forward path: TMEM base (0 columns: unused), per-group "MMAs done" barriers and their use counts, X_lo staging
-  uint32_t tmem;
-  uint64_t* mma_done;       // [2]
-  float* xlo;               // [2][REDROWS][32] floats, swizzled like the X boxes
-  unsigned* mma_uses;       // [2] completed phases of mma_done (per-thread copies live in registers; see fwd_tile_tc)
 };
 __device__ __forceinline__ void tl_mark(const Pipe& pipe, int tag) {
   if (pipe.tl != nullptr && threadIdx.x == 0 && blockIdx.x == 0) {
@@ -124,171 +113,6 @@ __device__ __forceinline__ void fwd_tile(const float* ring, const Pipe& pipe, un
   tl_mark(pipe, 3);
 }
 
-#ifdef SC_ENABLE_FWD_TC      // experimental: correct, but 3x slower than mma.sync at 8-row tiles
-// ---- forward tile on the 5th-generation tensor cores (tcgen05, weights through tensor memory) ---------------------------
-// Same contract as fwd_tile.  D^T[feature][row] += W[feature][k] X[row][k] with M = 64 features (the CTA's slice; slices
-// narrower than 64 leave the upper TMEM lanes unused), N = 8 NT8 batch rows, K = 8 per instruction.  The weight tile goes
-// shared memory -> registers (split into tf32 big + small parts) -> tensor memory (tcgen05.st) ONCE per 32-deep k-block and
-// is then the A operand of 12 MMAs from TMEM, so the shared-memory read path -- the limit of both an SS-mode tcgen05 and,
-// at 8 rows, of the FP32 version -- carries each weight once.  B = the X box as TMA wrote it (K-major, 128-byte swizzle)
-// and its small part X_lo, written next to it by the same warps.  Per k-step: D += W_lo X + W X_lo + W X (3xTF32).
-// The 8 consumer warps form two independent pipelines (group g = warp / 4 takes k-block g of every slot, its own TMEM
-// weight buffer, accumulator and "MMAs done" mbarrier); warp q of a group owns features 16 q + t (t = lane < 16), which is
-// the M = 64 TMEM layout (feature 16 q + t <-> lane 32 q + t).  The two accumulators are added in the usual combine step.
-constexpr uint32_t TC_COL_D = 0, TC_COL_A = 64;      // TMEM columns: D of group g at 32 g, A of group g at 64 + 64 g (big | small)
-__device__ __forceinline__ uint64_t tc_desc_k128(uint32_t saddr) {
-  uint64_t d = 0;                                    // K-major, SWIZZLE_128B, 8-row atoms of 1024 B
-  d |= (uint64_t)((saddr >> 4) & 0x3fff);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)((1024u >> 4) & 0x3fff) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-template <int NT8, int MT>
-__device__ __forceinline__ void fwd_tile_tc(const float* ring, const Pipe& pipe, unsigned& g, int K, float* red, float* sZ,
-                                            const float* bias_slice, int ncv, unsigned& uses) {
-  constexpr int NC = 16 * MT, ROWS = 8 * NT8;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = warp >> 2, q = warp & 3;
-  const bool has_rows = q < MT;                      // this warp's 16 features exist in the CTA's slice
-  uint64_t* done = pipe.mma_done + grp;
-  const uint32_t tD = pipe.tmem + TC_COL_D + 32u * grp, tA = pipe.tmem + TC_COL_A + 64u * grp + ((uint32_t)(q * 32) << 16);
-  float* xlo = pipe.xlo + grp * (REDROWS * 32);
-  // D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M = 64 (>> 4) at bit 24
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ROWS >> 3) << 17) | (4u << 24);
-  bool first = true, pending = false;
-  unsigned pending_slot = 0;
-  for (int k0 = 0; k0 < K; k0 += KC, ++g) {
-    const unsigned slot = g % NSTAGE;
-    mbar_wait(pipe.full + slot, (g / NSTAGE) & 1u);
-    const float* sX = ring + slot * SLOT;
-    const float* sW = sX + SLOT_A;
-    const int nkb = (min(KC, K - k0) + 31) >> 5;     // 32-deep k-blocks present in this slot
-    // k-blocks of the slot are dealt to the groups round-robin (KBLK is 2 or 4)
-    for (int kb = grp; kb < nkb; kb += 2) {
-      if (pending) {                                 // the group's previous MMAs must be done before its TMEM buffer is rewritten;
-        mbar_wait(done, uses & 1u);                  // that also means the slot they read from can go back to the producer
-        ++uses;
-        pending = false;
-        if (pending_slot != slot) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(pipe.empty + pending_slot);
-        }
-      }
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (has_rows) {
-        // weight rows 16 q + t of k-block kb: 32 floats per row, chunk c of row r sits at chunk c ^ (r & 7)
-        const int r = q * 16 + (lane & 15);
-        const float4* wrow = reinterpret_cast<const float4*>(sW + (kb * NC + r) * 32);
-        uint32_t hi[32], lo[32];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 v = wrow[c ^ (r & 7)];
-          const float x[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const uint32_t b = __float_as_uint(x[e]) & 0xffffe000u;
-            hi[4 * c + e] = b;
-            lo[4 * c + e] = __float_as_uint(x[e] - __uint_as_float(b));
-          }
-        }
-        asm volatile(
-            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
-            "%26,%27,%28,%29,%30,%31,%32};" ::"r"(tA),
-            "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]), "r"(hi[8]), "r"(hi[9]), "r"(hi[10]),
-            "r"(hi[11]), "r"(hi[12]), "r"(hi[13]), "r"(hi[14]), "r"(hi[15]), "r"(hi[16]), "r"(hi[17]), "r"(hi[18]), "r"(hi[19]), "r"(hi[20]),
-            "r"(hi[21]), "r"(hi[22]), "r"(hi[23]), "r"(hi[24]), "r"(hi[25]), "r"(hi[26]), "r"(hi[27]), "r"(hi[28]), "r"(hi[29]), "r"(hi[30]),
-            "r"(hi[31]) : "memory");
-        asm volatile(
-            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
-            "%26,%27,%28,%29,%30,%31,%32};" ::"r"(tA + 32u),
-            "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]), "r"(lo[8]), "r"(lo[9]), "r"(lo[10]),
-            "r"(lo[11]), "r"(lo[12]), "r"(lo[13]), "r"(lo[14]), "r"(lo[15]), "r"(lo[16]), "r"(lo[17]), "r"(lo[18]), "r"(lo[19]), "r"(lo[20]),
-            "r"(lo[21]), "r"(lo[22]), "r"(lo[23]), "r"(lo[24]), "r"(lo[25]), "r"(lo[26]), "r"(lo[27]), "r"(lo[28]), "r"(lo[29]), "r"(lo[30]),
-            "r"(lo[31]) : "memory");
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      }
-      // small part of the X k-block (ROWS x 32 floats, same swizzled positions)
-      {
-        const float4* xs = reinterpret_cast<const float4*>(sX + kb * ROWS * 32);
-        float4* xd = reinterpret_cast<float4*>(xlo);
-        for (int i = (threadIdx.x & 127); i < ROWS * 8; i += 128) {
-          const float4 v = xs[i];
-          float4 y;
-          y.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-          y.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-          y.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-          y.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-          xd[i] = y;
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");          // the group's four warps
-      if (q == 0 && lane == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t xb = smem_u32(sX + kb * ROWS * 32), xl = smem_u32(xlo);
-        const uint32_t aH = pipe.tmem + TC_COL_A + 64u * grp, aL = aH + 32u;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          tc_mma_ts(tD, aL + 8u * j, tc_desc_k128(xb + 32u * j), idesc, (first && j == 0) ? 0u : 1u);
-          tc_mma_ts(tD, aH + 8u * j, tc_desc_k128(xl + 32u * j), idesc, 1u);
-          tc_mma_ts(tD, aH + 8u * j, tc_desc_k128(xb + 32u * j), idesc, 1u);
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(done)) : "memory");
-      }
-      first = false;
-      pending = true;
-      pending_slot = slot;
-    }
-    // a group that had no k-block in this slot (partial last slot) still owes the producer its four arrivals
-    if (grp >= nkb) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(pipe.empty + slot);
-    }
-  }
-  if (pending) {
-    mbar_wait(done, uses & 1u);
-    ++uses;
-    __syncwarp();
-    if (lane == 0) mbar_arrive(pipe.empty + pending_slot);
-  }
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  // accumulator of this group: feature 16 q + t in TMEM lane 32 q + t, ROWS columns -> red[grp][row][feature]
-  {
-    uint32_t v[ROWS];
-    const uint32_t addr = tD + ((uint32_t)(q * 32) << 16);
-    if constexpr (ROWS == 8) {
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(addr));
-    } else {
-#pragma unroll
-      for (int c = 0; c < ROWS; c += 8)
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(v[c]), "=r"(v[c + 1]), "=r"(v[c + 2]), "=r"(v[c + 3]), "=r"(v[c + 4]), "=r"(v[c + 5]), "=r"(v[c + 6]), "=r"(v[c + 7])
-                     : "r"(addr + (uint32_t)c));
-    }
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (has_rows && lane < 16) {
-      const int P = NC + 4, f = q * 16 + lane;
-#pragma unroll
-      for (int r = 0; r < ROWS; ++r) red[((size_t)grp * ROWS + r) * P + f] = first ? 0.f : __uint_as_float(v[r]);
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  consumer_sync();
-  combine_partials<NT8>(red, 2, NC, sZ, bias_slice, ncv);
-  consumer_sync();
-}
-
-#endif  // SC_ENABLE_FWD_TC
 
 template <int NT8, int MT>
 __device__ __forceinline__ void bwd_tile(const float* ring, const Pipe& pipe, unsigned& g, int Nl, float* red, float* sZ) {
@@ -321,7 +145,7 @@ __device__ __forceinline__ void bwd_tile(const float* ring, const Pipe& pipe, un
 // ======================================================================================================
 template <int CS, int TM>
 __device__ void dense_stage(const DenseOp* ops, int nops, int B, int row0, int nrows, const int* __restrict__ bidx,
-                            float* part, float* smem, const Pipe& pipe, unsigned& g, unsigned& tc_uses, unsigned long long* ts = nullptr) {
+                            float* part, float* smem, const Pipe& pipe, unsigned& g, unsigned long long* ts = nullptr) {
   constexpr int ROWS = 8 * TM;
   float* ring = smem;
   float* red = ring + SM_RING;
@@ -381,15 +205,6 @@ __device__ void dense_stage(const DenseOp* ops, int nops, int B, int row0, int n
       for (int sub = 0; sub < nsub; ++sub) {
         const int r0 = row0 + sub * ROWS;
         const int rv = min(ROWS, nrows - sub * ROWS);
-#ifdef SC_ENABLE_FWD_TC
-        if (pipe.tmem != 0xffffffffu) {
-          switch (Nc >> 4) {
-            case 4: fwd_tile_tc<TM, 4>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv, tc_uses); break;
-            case 2: fwd_tile_tc<TM, 2>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv, tc_uses); break;
-            default: fwd_tile_tc<TM, 1>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv, tc_uses); break;
-          }
-        } else
-#endif
         {
           switch (Nc >> 4) {
             case 4: fwd_tile<TM, 4>(ring, pipe, g, op.K, red, sZ, bias_slice, ncv); break;
@@ -1222,37 +1037,20 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
   const int tid = threadIdx.x;
   const bool consumer = tid < SC_THREADS;
   __shared__ long long prof_acc[16];
-  __shared__ __align__(8) uint64_t mma_done[2];
-  __shared__ uint32_t tmem_slot;
   if (tid < 16) prof_acc[tid] = 0;
   unsigned g = 0;                 // chunks streamed so far (identical sequence in producer and consumers)
-  unsigned tc_uses = 0;           // completed phases of this thread's group "MMAs done" barrier (tcgen05 forward path)
   if (tid == 0) {
     for (int i = 0; i < NSTAGE; ++i) {
       mbar_init(mbars + i, 1);
       mbar_init(mbars + NSTAGE + i, SC_WARPS);
     }
-    mbar_init(mma_done, 1);
-    mbar_init(mma_done + 1, 1);
-    tmem_slot = 0xffffffffu;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-#ifdef SC_ENABLE_FWD_TC
-  if (p.fwd_tc && tid < 32) {
-    // 256 of the SM's 512 tensor-memory columns (two CTAs per SM): two accumulators + two (big | small) weight buffers
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#endif
   pdl_launch();
   pdl_wait();                     // (programmatic dependent launch: the barrier setup above overlapped the previous kernel)
   const Pipe pipe{p.dbg, p.tstamp ? prof_acc : nullptr, mbars, mbars + NSTAGE,
-                  (p.tstamp && p.program == PROG_CRITIC) ? p.tstamp + 2048 * 8 : nullptr,
-                  tmem_slot, mma_done, smem + SM_RING + SM_RED + SM_Z + SM_STAT + SM_ZK, nullptr};
+                  (p.tstamp && p.program == PROG_CRITIC) ? p.tstamp + 2048 * 8 : nullptr};
   if (pipe.tl != nullptr && tid == 0 && blockIdx.x == 0) pipe.tl[0] = 0;
   const int rank = (int)cluster_ctarank();
   const int ncl = (int)num_clusters();
@@ -1292,7 +1090,7 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
     dense(4, tm.mb_s, tm.crit_w11[1], p.crit[1].b11, p.crit[1].g11, p.crit[1].be11, K1, H1, p.cw[1].h11, p.cw[1].zh11, p.cw[1].rs11);
     cluster_sync();
     stamp(6);
-    dense_stage<CS, TM>(dops, 5, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g, tc_uses);
+    dense_stage<CS, TM>(dops, 5, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g);
     stamp(1);
     // stage 2: second layers
     dense(0, tm.t_h1, tm.actor_w2, a.b2, a.g2, a.be2, H1, H2, p.aw.t_h2, nullptr, nullptr);
@@ -1301,7 +1099,7 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
     dense(3, tm.ch11[0], tm.crit_w12[0], p.crit[0].b12, p.crit[0].g12, p.crit[0].be12, H1, H2, p.cw[0].h12, p.cw[0].zh12, p.cw[0].rs12);
     dense(4, tm.ch11[1], tm.crit_w12[1], p.crit[1].b12, p.crit[1].g12, p.crit[1].be12, H1, H2, p.cw[1].h12, p.cw[1].zh12, p.cw[1].rs12);
     __syncthreads();
-    dense_stage<CS, TM>(dops, 5, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g, tc_uses,
+    dense_stage<CS, TM>(dops, 5, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g,
                         p.tstamp ? p.tstamp + 512 * 8 + (size_t)blockIdx.x * 8 : nullptr);
     }
     stamp(2);
@@ -1342,13 +1140,13 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
     for (int k = 0; k < p.n_q; ++k)
       dense(1 + k, tm.mb_s, tm.crit_w11[k], p.crit[k].b11, p.crit[k].g11, p.crit[k].be11, K1, H1, p.cw[k].p_h11, nullptr, nullptr);
     __syncthreads();
-    dense_stage<CS, TM>(dops, 1 + p.n_q, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g, tc_uses);
+    dense_stage<CS, TM>(dops, 1 + p.n_q, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g);
     astamp(1);
     dense(0, tm.h1, tm.actor_w2, a.b2, a.g2, a.be2, H1, H2, p.aw.h2, p.aw.zh2, p.aw.rs2);
     for (int k = 0; k < p.n_q; ++k)
       dense(1 + k, tm.ph11[k], tm.crit_w12[k], p.crit[k].b12, p.crit[k].g12, p.crit[k].be12, H1, H2, p.cw[k].p_h12, nullptr, nullptr);
     __syncthreads();
-    dense_stage<CS, TM>(dops, 1 + p.n_q, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g, tc_uses);
+    dense_stage<CS, TM>(dops, 1 + p.n_q, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g);
     }
     astamp(2);
     if (consumer)
@@ -1369,10 +1167,10 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
     const ActorP& a = p.actor;
     dense(0, tm.obs, tm.actor_w1, a.b1, a.g1, a.be1, K1, H1, p.act_aux, nullptr, nullptr);
     __syncthreads();
-    dense_stage<CS, TM>(dops, 1, 1, row0, nrows, nullptr, p.part, smem, pipe, g, tc_uses);
+    dense_stage<CS, TM>(dops, 1, 1, row0, nrows, nullptr, p.part, smem, pipe, g);
     dense(0, tm.aux, tm.actor_w2, a.b2, a.g2, a.be2, H1, H2, p.act_aux + H1, nullptr, nullptr);
     __syncthreads();
-    dense_stage<CS, TM>(dops, 1, 1, row0, nrows, nullptr, p.part, smem, pipe, g, tc_uses);
+    dense_stage<CS, TM>(dops, 1, 1, row0, nrows, nullptr, p.part, smem, pipe, g);
     if (rank == 0 && nrows > 0 && consumer) {
       RowSet rs;
       rs.row[0] = 0;
@@ -1389,13 +1187,6 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
       }
     }
   }
-#ifdef SC_ENABLE_FWD_TC
-  if (p.fwd_tc) {
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(pipe.tmem), "r"(256));
-  }
-#endif
 }
 
 
