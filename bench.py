@@ -196,7 +196,7 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * args.steps / float(tt[0]), "unit": "learn steps/s",
-               "h2d_bytes_per_step": (2 * S + 2 * A + 2) * 4 + B * 8 + 2 * B * A * 4, "d2h_bytes_per_step": 48,
+               "h2d_bytes_per_step": (2 * S + 2 * A + 2) * 4 + B * 8 + 2 * B * A * 4, "d2h_bytes_per_step": 16 * 4 + 4,     # the 16-float loss / diagnostics block + the hint multiplier, one copy each
                "mode": "store_transition(host obs) + learn() + loss readback, rng='reference' (host numpy/torch draws)"}
 
     # config 5 topology (world > 1): rank 0 = learner, ranks >= 1 = actors; per episode ONE NCCL broadcast of the actor

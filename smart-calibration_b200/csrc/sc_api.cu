@@ -170,6 +170,9 @@ struct sc_agent {
   int eps_inline[3]; unsigned long long eps_stream[3];
   cudaStream_t st_side2;             // narrow-layer weight gradients run here next to the tensor-core kernel
   cudaEvent_t ev_fork, ev_join, ev_fork2, ev_join2;
+  // pinned staging regions are guarded by one event each (recorded after the copy that reads the region, waited on before
+  // the host rewrites it) instead of stream-wide synchronisation: 0..2 noise slots, 3 transition, 4 PER uniforms, 5 batch indices
+  cudaEvent_t ev_stage[6];
   void* arena;
   bool owns_arena;
   size_t arena_bytes;
@@ -213,7 +216,7 @@ struct sc_agent {
   VecOp *critic_vops, *actor_vops;
   int n_critic_ops, n_critic_vops, n_actor_ops, n_actor_vops, critic_tiles, actor_tiles;
   // pinned host staging
-  float* h_stage;                     // max(3*B*A, T, Sp) floats
+  float* h_stage;                     // [3][B*A] noise slots | [T] transition | [Sp32] observation
   float* h_stats;
   int32_t* h_idx;
   double* h_u01;
@@ -721,6 +724,7 @@ int sc_agent_create(const sc_config* cfg, void* arena, size_t arena_bytes, void*
   init_dims(a, cfg);
   a->st = (cudaStream_t)cuda_stream;
   a->st_side = nullptr; a->ev_fork = a->ev_join = a->ev_fork2 = a->ev_join2 = nullptr;
+  for (auto& e : a->ev_stage) e = nullptr;
   CK(cudaStreamCreateWithFlags(&a->st_side, cudaStreamNonBlocking));
   a->st_side2 = nullptr;
   CK(cudaStreamCreateWithFlags(&a->st_side2, cudaStreamNonBlocking));
@@ -728,6 +732,7 @@ int sc_agent_create(const sc_config* cfg, void* arena, size_t arena_bytes, void*
   CK(cudaEventCreateWithFlags(&a->ev_join, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&a->ev_fork2, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&a->ev_join2, cudaEventDisableTiming));
+  for (auto& e : a->ev_stage) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   const size_t need = carve(a, nullptr);
   if (arena) {
     if (arena_bytes < need) { delete a; return fail(SC_ERR_ARG, "arena too small: %zu < %zu", arena_bytes, need); }
@@ -744,7 +749,7 @@ int sc_agent_create(const sc_config* cfg, void* arena, size_t arena_bytes, void*
   CK(cudaMemsetAsync(a->arena, 0, need, a->st));
   const size_t stage_floats = (size_t)3 * a->B * a->A + a->T + a->Sp32 + 64;
   CK(cudaHostAlloc((void**)&a->h_stage, stage_floats * sizeof(float), cudaHostAllocDefault));
-  CK(cudaHostAlloc((void**)&a->h_stats, 16 * sizeof(float), cudaHostAllocDefault));
+  CK(cudaHostAlloc((void**)&a->h_stats, 32 * sizeof(float), cudaHostAllocDefault));
   CK(cudaHostAlloc((void**)&a->h_idx, (size_t)a->B * sizeof(int32_t), cudaHostAllocDefault));
   CK(cudaHostAlloc((void**)&a->h_u01, (size_t)a->B * sizeof(double), cudaHostAllocDefault));
   CK(cudaHostAlloc((void**)&a->h_act, 64 * sizeof(float), cudaHostAllocDefault));
@@ -816,6 +821,7 @@ int sc_agent_destroy(sc_agent* a) {
   }
   if (a->st_side) { cudaStreamSynchronize(a->st_side); cudaStreamDestroy(a->st_side); }
   if (a->st_side2) { cudaStreamSynchronize(a->st_side2); cudaStreamDestroy(a->st_side2); }
+  for (auto& e : a->ev_stage) if (e) cudaEventDestroy(e);
   if (a->ev_fork) cudaEventDestroy(a->ev_fork);
   if (a->ev_join) cudaEventDestroy(a->ev_join);
   if (a->ev_fork2) cudaEventDestroy(a->ev_fork2);
@@ -918,10 +924,12 @@ static int store_common(sc_agent* a, const float* tr_dev, int priority_mode, dou
 int sc_replay_store_host(sc_agent* a, const float* transition_host, int priority_mode, double priority) {
   touch_replay(a);
   if (!a || !transition_host) return fail(SC_ERR_ARG, "null argument");
-  // the staging slot is reused by the next call: wait for the previous copy-out kernel (one tiny sync per env step)
-  CK(cudaStreamSynchronize(a->st));
-  memcpy(a->h_stage, transition_host, (size_t)a->T * sizeof(float));
-  CK(cudaMemcpyAsync(a->store_stage, a->h_stage, (size_t)a->T * sizeof(float), cudaMemcpyHostToDevice, a->st));
+  // the pinned slot is reused by the next call: wait for the copy that read it last (normally long complete)
+  float* h = a->h_stage + (size_t)3 * a->B * a->A;
+  CK(cudaEventSynchronize(a->ev_stage[3]));
+  memcpy(h, transition_host, (size_t)a->T * sizeof(float));
+  CK(cudaMemcpyAsync(a->store_stage, h, (size_t)a->T * sizeof(float), cudaMemcpyHostToDevice, a->st));
+  CK(cudaEventRecord(a->ev_stage[3], a->st));
   return store_common(a, a->store_stage, priority_mode, priority);
 }
 int sc_replay_store_dev(sc_agent* a, const float* transitions_dev, int index, int priority_mode, double priority) {
@@ -959,9 +967,10 @@ int sc_replay_fill_host(sc_agent* a, const float* transitions_host, int n, const
 int sc_replay_set_batch_host(sc_agent* a, const int32_t* idx_host, int n) {
   touch_replay(a);
   if (!a || !idx_host || n != a->B) return fail(SC_ERR_ARG, "expected %d indices", a ? a->B : 0);
-  CK(cudaStreamSynchronize(a->st));   // h_idx may still be in flight from the previous step
+  CK(cudaEventSynchronize(a->ev_stage[5]));   // h_idx may still be in flight from the previous step
   memcpy(a->h_idx, idx_host, (size_t)n * sizeof(int32_t));
   CK(cudaMemcpyAsync(a->bidx, a->h_idx, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, a->st));
+  CK(cudaEventRecord(a->ev_stage[5], a->st));
   a->batch_ready = true;
   return SC_OK;
 }
@@ -981,9 +990,10 @@ int sc_per_sample(sc_agent* a, const double* u01_host, int32_t* tree_idx_host_ou
   if (!a->rp.tree) return fail(SC_ERR_STATE, "agent was created with prioritized=0");
   const double* u = nullptr;
   if (u01_host) {
-    CK(cudaStreamSynchronize(a->st));
+    CK(cudaEventSynchronize(a->ev_stage[4]));
     memcpy(a->h_u01, u01_host, (size_t)a->B * sizeof(double));
     CK(cudaMemcpyAsync(a->u01, a->h_u01, (size_t)a->B * sizeof(double), cudaMemcpyHostToDevice, a->st));
+    CK(cudaEventRecord(a->ev_stage[4], a->st));
     u = a->u01;
   }
   a->per_beta = fmin(1.0, a->per_beta + 1e-4);   // enet_sac.py:288
@@ -1199,7 +1209,7 @@ static int run_wgrad(sc_agent* a, const WgradParams& w, int timer_id) {
 int sc_agent_act(sc_agent* a, const float* obs_host, const float* eps_host, float* action_host_out) {
   if (!a || !obs_host || !action_host_out) return fail(SC_ERR_ARG, "null argument");
   CK(cudaStreamSynchronize(a->st));
-  float* h = a->h_stage;
+  float* h = a->h_stage + (size_t)3 * a->B * a->A + a->T;
   memset(h, 0, (size_t)a->Sp32 * sizeof(float));
   memcpy(h, obs_host, (size_t)a->S * sizeof(float));
   CK(cudaMemcpyAsync(a->obs_dev, h, (size_t)a->Sp32 * sizeof(float), cudaMemcpyHostToDevice, a->st));
@@ -1246,8 +1256,10 @@ static int upload_noise(sc_agent* a, const float* host, int slot, uint64_t strea
   const size_t n = (size_t)a->B * a->A;
   if (host) {
     float* h = a->h_stage + (size_t)slot * n;
+    CK(cudaEventSynchronize(a->ev_stage[slot]));
     memcpy(h, host, n * sizeof(float));
     CK(cudaMemcpyAsync(a->eps[slot], h, n * sizeof(float), cudaMemcpyHostToDevice, a->st));
+    CK(cudaEventRecord(a->ev_stage[slot], a->st));
     a->eps_inline[slot] = 0;
   } else {
     // device RNG: no fill launch -- the row-phase kernel draws the same Philox values where it consumes them
@@ -1292,8 +1304,6 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
   }
   if (a->presampled) { a->presampled = false; a->sample_ctr--; }   // (a batch supplied from outside supersedes it)
   a->batch_ready = false;
-  const bool host_noise = noise && (noise->eps_next_host || noise->eps_cur_host || noise->eps_dual_host);
-  if (host_noise) CK(cudaStreamSynchronize(a->st));   // staging buffers may be in flight
   if (sac) {
     if ((rc = upload_noise(a, noise ? noise->eps_next_host : nullptr, 0, 0x1000000000ull))) return rc;
     if ((rc = upload_noise(a, noise ? noise->eps_cur_host : nullptr, 1, 0x2000000000ull))) return rc;
@@ -1386,7 +1396,6 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
     }
     if (sac && a->cfg.use_hint && a->learn_counter % 10 == 0) {
       // dual ascent on the hint multiplier with a fresh no-grad sample from the UPDATED actor (enet_sac.py:608-617)
-      if (noise && noise->eps_dual_host) CK(cudaStreamSynchronize(a->st));
       if ((rc = upload_noise(a, noise ? noise->eps_dual_host : nullptr, 2, 0x3000000000ull))) return rc;
       set_eps(a, p, 2);
       p.hint_coef = nullptr;
@@ -1400,7 +1409,9 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
   a->learn_counter++;
   if (stats_host) {
     CK(cudaMemcpyAsync(a->h_stats, a->stats, 16 * sizeof(float), cudaMemcpyDeviceToHost, a->st));
-    CK(cudaStreamSynchronize(a->st));
+    CK(cudaMemcpyAsync(a->h_stats + 16, a->rho_dev, sizeof(float), cudaMemcpyDeviceToHost, a->st));
+    if (sac && a->cfg.use_hint) CK(cudaMemcpyAsync(a->h_stats + 20, a->hint_out + 1, 2 * sizeof(float), cudaMemcpyDeviceToHost, a->st));
+    CK(cudaStreamSynchronize(a->st));         // the one synchronisation of a step that reads its losses back
     stats_host->critic_1_loss = a->h_stats[0];
     stats_host->critic_2_loss = a->h_stats[1];
     stats_host->actor_loss = a->h_stats[2];
@@ -1408,14 +1419,12 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
     stats_host->q2_mean = a->h_stats[4];
     stats_host->target_mean = a->h_stats[5];
     stats_host->logp_mean = a->h_stats[6];
-    CK(cudaMemcpy(&a->rho, a->rho_dev, sizeof(float), cudaMemcpyDeviceToHost));
+    a->rho = a->h_stats[16];
     stats_host->rho = a->rho;
     stats_host->gfun = 0.f;
     if (sac && a->cfg.use_hint) {
-      float pen[2] = {0.f, 0.f};
-      CK(cudaMemcpy(pen, a->hint_out + 1, 2 * sizeof(float), cudaMemcpyDeviceToHost));
-      stats_host->gfun = pen[0];
-      stats_host->actor_loss += pen[1];
+      stats_host->gfun = a->h_stats[20];
+      stats_host->actor_loss += a->h_stats[21];
     }
     stats_host->learn_counter = (int32_t)a->learn_counter;
     stats_host->did_learn = 1;
