@@ -24,6 +24,7 @@ size_t wgrad_smem_bytes();
 cudaError_t launch_wgrad(const WgradParams& p, int grid, cudaStream_t st);
 cudaError_t launch_wgrad_tc(const WgradTcParams& p, int grid, cudaStream_t st);
 cudaError_t launch_dense_tc(const DenseTcParams& p, cudaStream_t st);
+int dense_tc_max_clusters(int cs);
 cudaError_t launch_gather_mb(float* mb_s, float* mb_s2, const float* state, const float* new_state, const int* bidx, int B, int Sp,
                              int Sp32, cudaStream_t st);
 cudaError_t launch_soft_update(const float* src, float* dst, size_t n, float tau, cudaStream_t st);
@@ -182,6 +183,7 @@ struct sc_agent {
   TensorMaps tm_critic, tm_actor, tm_act;   // per-program map pointer sets
   TensorMaps tmd_critic, tmd_actor;         // the same matrices with 128-row boxes for the tcgen05 dense stages (sc_dense_tc.cu)
   bool dense_tc;                            // batched passes run their two wide forward layers as k_dense_tc launches
+  int dense_cap[3];                         // co-resident k_dense_tc clusters of 4 / 8 / 16 CTAs on this device
   NetLayout Lc, La;
   size_t online_floats;               // actor + c1 + c2
   float *params, *adam_m, *adam_v;    // online blocks
@@ -605,6 +607,10 @@ static int build_op_tables(sc_agent* a) {
   // wide forward layers of the batched passes: tcgen05 launches unless SMARTCAL_DENSE=mma keeps them in the row-phase kernel
   const char* dn = getenv("SMARTCAL_DENSE");
   a->dense_tc = !(dn && !strcmp(dn, "mma"));
+  if (a->dense_tc) {
+    a->dense_cap[0] = dense_tc_max_clusters(4); a->dense_cap[1] = dense_tc_max_clusters(8); a->dense_cap[2] = dense_tc_max_clusters(16);
+    if (a->dense_cap[0] < 1 || a->dense_cap[1] < 1) a->dense_tc = false;     // cannot host the clusters: keep the wide layers in k_rowphase
+  }
   std::vector<TcCand> tc_critic, tc_actor;
   std::vector<CUtensorMap> tc_maps;
   g_tc_sink = a->use_tc ? &tc_critic : nullptr;
@@ -1131,11 +1137,13 @@ static int run_dense_tc(sc_agent* a, const RowPhaseParams& p) {
   // still fits the machine in one wave (SMARTCAL_DENSE_KS=a,b pins the two stages' splits)
   d1.ks = 1; d2.ks = 2;
   d2.late_trigger = 1;
-  if (n * d1.nrb * (H1 / 64) * 2 <= a->sm_count && (K1 / 32) % 2 == 0) d1.ks = 2;
+  if (n * d1.nrb * (H1 / 64) * 2 <= a->sm_count && (K1 / 32) % 2 == 0 && n * d1.nrb <= a->dense_cap[2]) d1.ks = 2;   // 16-CTA clusters
   if (n * d2.nrb * (H2 / 64) * 2 > a->sm_count) d2.ks = 1;
   if (const char* e = getenv("SMARTCAL_DENSE_KS")) {
     int k1 = 0, k2 = 0;
-    if (sscanf(e, "%d,%d", &k1, &k2) == 2 && k1 >= 1 && k1 <= 2 && k2 >= 1 && k2 <= 2 && (K1 / 32) % k1 == 0) { d1.ks = k1; d2.ks = k2; }
+    if (sscanf(e, "%d,%d", &k1, &k2) == 2 && k1 >= 1 && k1 <= 2 && k2 >= 1 && k2 <= 2 && (K1 / 32) % k1 == 0 && (k1 == 1 || a->dense_cap[2] >= 1)) {
+      d1.ks = k1; d2.ks = k2;
+    }
   }
   if (getenv("SMARTCAL_STAMPS")) {
     if (critic) d1.tl = a->tstamp + 2880 * 8;

@@ -356,6 +356,26 @@ __global__ void __launch_bounds__(128) k_gather_mb(float* mb_s, float* mb_s2, co
 
 size_t dense_tc_smem_bytes() { return (size_t)DT_STAGES * DT_STAGE_BYTES + DT_PART_BYTES + 1024; }
 
+// co-resident clusters of `cs` CTAs this device can host for k_dense_tc (0: such clusters cannot be launched at all)
+int dense_tc_max_clusters(int cs) {
+  if (cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_tc_smem_bytes()) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cs > 8 && cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3(cs * 8, 1, 1);
+  cfg.blockDim = dim3(DT_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = dense_tc_smem_bytes();
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, k_dense_tc, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
 cudaError_t launch_dense_tc(const DenseTcParams& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
