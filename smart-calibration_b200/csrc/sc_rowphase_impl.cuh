@@ -324,6 +324,9 @@ __device__ void dgrad_stage(const DgradOp* ops, int nops, int B, int row0, int n
   const int rank = (int)cluster_ctarank();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nsub = (nrows + ROWS - 1) / ROWS;
+  // per (op, sub-tile): [h | zh] slices of the producing layer, ROWS x WCOLS floats each, in the (idle) raw-z area
+  float* stash = stat + SM_STAT;
+  const bool use_stash = 2 * nops * nsub * ROWS * WCOLS <= SM_ZK;
 
   if (warp == SC_WARPS) {
     if (nrows > 0) {
@@ -361,10 +364,29 @@ __device__ void dgrad_stage(const DgradOp* ops, int nops, int B, int row0, int n
       for (int sub = 0; sub < nsub; ++sub) {
         const int r0 = row0 + sub * ROWS;
         const int rv = min(ROWS, nrows - sub * ROWS);
+        // the producing layer's h and zh slices of this tile do not depend on the GEMM: fetch them into shared memory now
+        // (cp.async, no registers held) so that their L2 latency runs under the k-loop; they stay there for the second pass
+        float* st_h = stash + (size_t)((o * nsub + sub) * 2) * ROWS * WCOLS;
+        float* st_z = st_h + ROWS * WCOLS;
+        if (use_stash) {
+          const int q4 = Kc >> 2;
+          for (int e = tid; e < 2 * rv * q4; e += SC_THREADS) {
+            const int arr = e / (rv * q4), f = e - arr * rv * q4, row = f / q4, c = (f - row * q4) * 4;
+            if (c < kcv) {
+              const float* src = (arr ? op.ZHp : op.Hp) + (size_t)(r0 + row) * op.ldo + k0 + c;
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32((arr ? st_z : st_h) + row * Kc + c)), "l"(src) : "memory");
+            }
+          }
+          asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
         switch (Kc >> 4) {
           case 4: bwd_tile<TM, 4>(ring, pipe, g, op.Nl, red, sZ); break;
           case 2: bwd_tile<TM, 2>(ring, pipe, g, op.Nl, red, sZ); break;
           default: bwd_tile<TM, 1>(ring, pipe, g, op.Nl, red, sZ); break;
+        }
+        if (use_stash) {
+          asm volatile("cp.async.wait_all;\n" ::: "memory");
+          consumer_sync();
         }
         const int row = tid >> 3, sub8 = tid & 7;
         float s1 = 0.f, s2 = 0.f;
@@ -372,14 +394,15 @@ __device__ void dgrad_stage(const DgradOp* ops, int nops, int B, int row0, int n
           const size_t base = (size_t)(r0 + row) * op.ldo + k0;
           for (int c = sub8; c < kcv; c += 8) {
             const float dh = sZ[row * Kc + c];
-            const float h = ld_act(op.Hp + base + c);
-            const float zh = ld_act(op.ZHp + base + c);
+            const float h = use_stash ? st_h[row * Kc + c] : ld_act(op.Hp + base + c);
+            const float zh = use_stash ? st_z[row * Kc + c] : ld_act(op.ZHp + base + c);
             const float du = dh * elu_grad_from_out(h);
             const float t = du * ld_w(op.gp + k0 + c);
             s1 += t;
             s2 = fmaf(t, zh, s2);
             op.DU[base + c] = du;
-            op.DZo[base + c] = t;
+            if (use_stash) st_h[row * Kc + c] = t;          // (h is not needed again: its slot carries t to the second pass)
+            else op.DZo[base + c] = t;
           }
         }
         s1 = group8_sum(s1);
@@ -394,6 +417,7 @@ __device__ void dgrad_stage(const DgradOp* ops, int nops, int B, int row0, int n
   }
   cluster_sync();
   if (warp < SC_WARPS) {
+    float* rsv = red;                                       // 1/std of the producing LayerNorm per (op, row); `red` is idle now
     for (int i = tid; i < nops * nrows; i += SC_THREADS) {
       const int o = i / nrows, r = i - o * nrows;
       const DgradOp& op = ops[o];
@@ -402,6 +426,7 @@ __device__ void dgrad_stage(const DgradOp* ops, int nops, int B, int row0, int n
       float2 pv[CS];
 #pragma unroll
       for (int p = 0; p < CS; ++p) pv[p] = __ldcg(reinterpret_cast<const float2*>(pp) + p);
+      const float rs = ld_act(op.RSp + row0 + r);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int p = 0; p < CS; ++p) {
@@ -412,6 +437,7 @@ __device__ void dgrad_stage(const DgradOp* ops, int nops, int B, int row0, int n
       }
       stat[2 * i] = s1 / (float)op.Kin;
       stat[2 * i + 1] = s2 / (float)op.Kin;
+      rsv[i] = rs;
     }
     consumer_sync();
     for (int o = 0; o < nops; ++o) {
@@ -422,10 +448,17 @@ __device__ void dgrad_stage(const DgradOp* ops, int nops, int B, int row0, int n
         const int r = e / Kc, c = e - r * Kc, k = k0 + c;
         if (k < op.Kin) {
           const size_t off = (size_t)(row0 + r) * op.ldo + k;
-          const float t = ld_act(op.DZo + off);
-          const float zh = ld_act(op.ZHp + off);
-          const float rs = ld_act(op.RSp + row0 + r);
-          op.DZo[off] = rs * (t - stat[2 * (o * nrows + r)] - zh * stat[2 * (o * nrows + r) + 1]);
+          float t, zh;
+          if (use_stash) {
+            const int sub = r / ROWS, row = r - sub * ROWS;
+            const float* st_h = stash + (size_t)((o * nsub + sub) * 2) * ROWS * WCOLS;
+            t = st_h[row * Kc + c];
+            zh = st_h[ROWS * WCOLS + row * Kc + c];
+          } else {
+            t = ld_act(op.DZo + off);
+            zh = ld_act(op.ZHp + off);
+          }
+          op.DZo[off] = rsv[o * nrows + r] * (t - stat[2 * (o * nrows + r)] - zh * stat[2 * (o * nrows + r) + 1]);
         }
       }
     }
