@@ -14,7 +14,9 @@
 // big/small split; epilogue on all 16 warps: warp w reads TMEM lanes 32 (w & 3).. (its rows) x columns 16 (w >> 2).. (its features).
 // The operand traffic of three SS-mode products per k-step makes the loop shared-memory-bandwidth bound (per 8-deep k-step
 // the tensor core reads 3 (M + N) 32 B, TMA and the split move another 4 (M + N) 32 B), which is why the tile is only 64 wide:
-// more, smaller CTAs put more SMs' shared memory to work.
+// more, smaller CTAs put more SMs' shared memory to work.  For the same reason the reduction can be split over a CTA pair
+// (DenseTcParams.ks = 2: cluster = feature blocks x 2, the second CTA's accumulators travel through distributed shared memory).
+// Launched with programmatic dependent launch: everything up to pdl_wait() overlaps the previous kernel.
 #include "sc_common.cuh"
 #include "sc_params.h"
 
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
       __syncwarp();
     }
   } else {
-    // ---------------- splitter warps: lo = x - trunc_tf32(x), same swizzled layout ----------------
+    // ---------------- splitter warps: big = rna_tf32(x) in place, small = rna_tf32(x - big) next to it (same swizzled layout) ----------------
     const int wl = tid - 64;
     if (wl < 3 * DT_N) {
       const int a = wl / DT_N, j = wl - a * DT_N;
