@@ -25,8 +25,8 @@ cudaError_t launch_wgrad(const WgradParams& p, int grid, cudaStream_t st);
 cudaError_t launch_wgrad_tc(const WgradTcParams& p, int grid, cudaStream_t st);
 cudaError_t launch_dense_tc(const DenseTcParams& p, cudaStream_t st);
 int dense_tc_max_clusters(int cs);
-cudaError_t launch_gather_mb(float* mb_s, float* mb_s2, const float* state, const float* new_state, const int* bidx, int B, int Sp,
-                             int Sp32, cudaStream_t st);
+cudaError_t launch_gather_mb(float* mb_s, float* mb_s2, float* hl, const float* state, const float* new_state, const int* bidx, int B,
+                             int Sp, int Sp32, cudaStream_t st);
 cudaError_t launch_soft_update(const float* src, float* dst, size_t n, float tau, cudaStream_t st);
 cudaError_t launch_replay_store(const ReplayP& rp, const float* tr, int slot, int mode, double priority, double clip, cudaStream_t st);
 cudaError_t launch_replay_fill(const ReplayP& rp, const float* tr, int n, cudaStream_t st);
@@ -179,6 +179,8 @@ struct sc_agent {
   size_t arena_bytes;
   int S, Sp, Sp32, A, Ap, B, C, T;    // T = packed transition length; Sp32 = S padded to whole 32-float k-blocks
   float *mb_s, *mb_s2;                // [B][Sp32] minibatch gather buffers
+  float* mb_hl;                       // [4][B][Sp32]: tf32 big / small parts of mb_s, then of mb_s2 (X operands of k_dense_tc)
+  const void *tmd_s_hi, *tmd_s_lo, *tmd_s2_hi, *tmd_s2_lo;
   unsigned char* tmaps;               // device table of CUtensorMap (128 B each)
   TensorMaps tm_critic, tm_actor, tm_act;   // per-program map pointer sets
   TensorMaps tmd_critic, tmd_actor;         // the same matrices with 128-row boxes for the tcgen05 dense stages (sc_dense_tc.cu)
@@ -347,6 +349,7 @@ static size_t carve(sc_agent* a, void* base) {
   a->u01 = (double*)cv.take(sizeof(double) * B);
   a->mb_s = cv.f((size_t)B * a->Sp32);
   a->mb_s2 = cv.f((size_t)B * a->Sp32);
+  a->mb_hl = cv.f((size_t)4 * B * a->Sp32);
   reg("mb_state", a->mb_s, B, S, a->Sp32, 4);
   reg("mb_new_state", a->mb_s2, B, S, a->Sp32, 4);
   a->tmaps = (unsigned char*)cv.take(128 * 64);
@@ -526,6 +529,11 @@ static int build_tensor_maps(sc_agent* a) {
     const int DB = 128, DW = 64;               // box rows: 128 batch rows, 64 output features (sc_dense_tc.cu tile)
     d.mb_s = add(a->mb_s, K1, B, DB);
     d.mb_s2 = add(a->mb_s2, K1, B, DB);
+    const size_t plane = (size_t)B * K1;
+    a->tmd_s_hi = add(a->mb_hl, K1, B, DB);
+    a->tmd_s_lo = add(a->mb_hl + plane, K1, B, DB);
+    a->tmd_s2_hi = add(a->mb_hl + 2 * plane, K1, B, DB);
+    a->tmd_s2_lo = add(a->mb_hl + 3 * plane, K1, B, DB);
     d.t_h1 = add(a->aw.t_h1, H1, B, DB);
     d.h1 = add(a->aw.h1, H1, B, DB);
     for (int k = 0; k < 2; ++k) {
@@ -1108,14 +1116,16 @@ static int run_dense_tc(sc_agent* a, const RowPhaseParams& p) {
   d1.nrb = d2.nrb = (p.B + 127) / 128;
   const int K1 = p.Sp32;
   int n = 0;
+  // (the layer-1 input is the gathered minibatch, which k_gather_mb also wrote as tf32 big / small parts)
   auto op = [&](const void* mx1, const void* mw1, const float* b1, const float* g1, const float* be1, float* h1, float* zh1, float* rs1,
                 const void* mx2, const void* mw2, const float* b2, const float* g2, const float* be2, float* h2, float* zh2, float* rs2) {
-    d1.ops[n] = DenseTcOp{mx1, mw1, b1, g1, be1, h1, zh1, rs1, K1};
-    d2.ops[n] = DenseTcOp{mx2, mw2, b2, g2, be2, h2, zh2, rs2, H1};
+    const bool next = mx1 == m.mb_s2;
+    d1.ops[n] = DenseTcOp{next ? a->tmd_s2_hi : a->tmd_s_hi, next ? a->tmd_s2_lo : a->tmd_s_lo, mw1, b1, g1, be1, h1, zh1, rs1, K1};
+    d2.ops[n] = DenseTcOp{mx2, nullptr, mw2, b2, g2, be2, h2, zh2, rs2, H1};
     ++n;
   };
   if (critic) {
-    CK(launch_gather_mb(a->mb_s, a->mb_s2, p.rp.state, p.rp.new_state, p.bidx, p.B, p.Sp, p.Sp32, a->st));
+    CK(launch_gather_mb(a->mb_s, a->mb_s2, a->mb_hl, p.rp.state, p.rp.new_state, p.bidx, p.B, p.Sp, p.Sp32, a->st));
     a->launches++;
     op(m.mb_s2, m.actor_w1, ac.b1, ac.g1, ac.be1, p.aw.t_h1, nullptr, nullptr,
        m.t_h1, m.actor_w2, ac.b2, ac.g2, ac.be2, p.aw.t_h2, nullptr, nullptr);

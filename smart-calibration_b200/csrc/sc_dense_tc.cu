@@ -132,9 +132,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
       uint8_t* st = smem + (size_t)slot * DT_STAGE_BYTES;
       if (lane == 0) {
         mark(0, 1);
-        mbar_expect_tx(full_raw + slot, DT_X_BYTES + DT_W_BYTES);
+        mbar_expect_tx(full_raw + slot, DT_X_BYTES + DT_W_BYTES + (op.mapXlo ? DT_X_BYTES : 0));
         tma_load_2d(reinterpret_cast<float*>(st), op.mapX, 32 * (kc0 + s), r0, full_raw + slot);
         tma_load_2d(reinterpret_cast<float*>(st + DT_X_BYTES), op.mapW, 32 * (kc0 + s), n0, full_raw + slot);
+        if (op.mapXlo)        // pre-split X: the small part goes straight to where the splitter would have written it
+          tma_load_2d(reinterpret_cast<float*>(st + DT_X_BYTES + DT_W_BYTES), op.mapXlo, 32 * (kc0 + s), r0, full_raw + slot);
       }
       __syncwarp();
     }
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
       float4* raw = reinterpret_cast<float4*>(smem + (size_t)slot * DT_STAGE_BYTES);
       float4* lo = reinterpret_cast<float4*>(smem + (size_t)slot * DT_STAGE_BYTES + DT_X_BYTES + DT_W_BYTES);
 #pragma unroll 5
-      for (int i = wl; i < (DT_X_BYTES + DT_W_BYTES) / 16; i += DT_SPLIT_THREADS) {
+      for (int i = (op.mapXlo ? DT_X_BYTES / 16 : 0) + wl; i < (DT_X_BYTES + DT_W_BYTES) / 16; i += DT_SPLIT_THREADS) {
         const float4 x = raw[i];
         float4 h, y;
         split_rn(x.x, h.x, y.x);
@@ -340,19 +342,32 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(DT_N));
 }
 
-// minibatch gather: replay rows [C][Sp] -> dense TMA-readable buffers [B][Sp32] (zero padded), states and next states
-__global__ void __launch_bounds__(128) k_gather_mb(float* mb_s, float* mb_s2, const float* __restrict__ state,
-                                                   const float* __restrict__ new_state, const int* __restrict__ bidx, int Sp, int Sp32) {
+// minibatch gather: replay rows [C][Sp] -> dense TMA-readable buffers [B][Sp32] (zero padded), states and next states:
+// the fp32 rows (X operand of the layer-1 weight gradients) and their tf32 big / small parts (X operand of k_dense_tc,
+// which then skips the split of the X boxes in every one of its CTAs)
+__global__ void __launch_bounds__(128) k_gather_mb(float* mb_s, float* mb_s2, float* hl, const float* __restrict__ state,
+                                                   const float* __restrict__ new_state, const int* __restrict__ bidx, int B, int Sp, int Sp32) {
   const int r = blockIdx.x >> 1, which = blockIdx.x & 1;
   pdl_launch();
   pdl_wait();
   const float* src = (which ? new_state : state) + (size_t)__ldg(bidx + r) * Sp;
   float* dst = (which ? mb_s2 : mb_s) + (size_t)r * Sp32;
+  float* dhi = hl + ((size_t)(2 * which) * B + r) * Sp32;    // hl = [s_hi | s_lo | s2_hi | s2_lo], each [B][Sp32]
+  float* dlo = dhi + (size_t)B * Sp32;
   const int n4 = Sp32 >> 2, v4 = Sp >> 2;
   for (int c4 = threadIdx.x; c4 < n4; c4 += 128) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c4 < v4) v = ld_w4(src + 4 * c4);
     *reinterpret_cast<float4*>(dst + 4 * c4) = v;
+    if (hl != nullptr) {
+      float4 h, y;
+      split_rn(v.x, h.x, y.x);
+      split_rn(v.y, h.y, y.y);
+      split_rn(v.z, h.z, y.z);
+      split_rn(v.w, h.w, y.w);
+      *reinterpret_cast<float4*>(dhi + 4 * c4) = h;
+      *reinterpret_cast<float4*>(dlo + 4 * c4) = y;
+    }
   }
 }
 
@@ -414,8 +429,8 @@ cudaError_t launch_dense_tc(const DenseTcParams& p, cudaStream_t st) {
   return cudaLaunchKernelEx(&cfg, k_dense_tc, p);
 }
 
-cudaError_t launch_gather_mb(float* mb_s, float* mb_s2, const float* state, const float* new_state, const int* bidx, int B, int Sp,
-                             int Sp32, cudaStream_t st) {
+cudaError_t launch_gather_mb(float* mb_s, float* mb_s2, float* hl, const float* state, const float* new_state, const int* bidx, int B,
+                             int Sp, int Sp32, cudaStream_t st) {
   cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
   cudaLaunchAttribute attr[1];
   cfg.gridDim = dim3(2 * B, 1, 1);
@@ -425,7 +440,7 @@ cudaError_t launch_gather_mb(float* mb_s, float* mb_s2, const float* state, cons
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_gather_mb, mb_s, mb_s2, state, new_state, bidx, Sp, Sp32);
+  return cudaLaunchKernelEx(&cfg, k_gather_mb, mb_s, mb_s2, hl, state, new_state, bidx, B, Sp, Sp32);
 }
 
 }  // namespace sc

@@ -158,6 +158,7 @@ struct WgradParams {
 // ---- dense forward stages on tcgen05 (sc_dense_tc.cu): H = ELU(LN(X W^T + b)) for up to 5 layers of equal width ----
 struct DenseTcOp {
   const void* mapX;                // X [B][K], boxes {32 floats, 128 rows}, CU_TENSOR_MAP_SWIZZLE_128B
+  const void* mapXlo;              // nullptr, or: X arrives already split (mapX = tf32-rounded big part, mapXlo = small part)
   const void* mapW;                // W [N][K] (PyTorch layout), boxes {32 floats, 64 rows}
   const float *bias, *gamma, *beta;
   float *H, *ZH, *RS;              // outputs [B][N] (ZH, RS nullable) as the row-phase tail reads them
