@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SC_ABI_VERSION 1
+#define SC_ABI_VERSION 2
 
 enum { SC_OK = 0, SC_ERR_ARG = 1, SC_ERR_CUDA = 2, SC_ERR_STATE = 3, SC_ERR_UNSUPPORTED = 4 };
 
@@ -101,6 +101,10 @@ typedef struct sc_noise {
   double td3_target_noise;       /* np.random.normal(scale=0.2) scalar   (enet_td3.py:249)      */
   int32_t has_td3_target_noise;
   int32_t reserved;
+  /* the minibatch draw of this learn(), when the caller owns the numpy stream and has not already sampled through
+   * sc_per_sample / sc_replay_set_batch_host (they travel in the same host->device copy as the noise): */
+  const double* per_u01_host;    /* (B) float64 uniforms of PER.sample_buffer (enet_sac.py:294), prioritized agents   */
+  const int32_t* batch_idx_host; /* (B) np.random.choice(max_mem, B, replace=False) (enet_sac.py:48), uniform buffer */
 } sc_noise;
 
 const char* sc_last_error(void);
@@ -162,6 +166,25 @@ int sc_agent_act(sc_agent* a, const float* obs_host, const float* eps_host, floa
  *      Agent.update_network_parameters (enet_sac.py:523-542) ------------------------------------------ */
 int sc_agent_learn(sc_agent* a, const sc_noise* noise_or_null, sc_learn_stats* stats_host_or_null);
 int sc_agent_soft_update(sc_agent* a, float tau);
+/* Agent.store_transition (enet_sac.py:544-545) followed by Agent.learn() as ONE call: the packed transition, the noise and
+ * the sampling randomness travel in a single pinned block / host->device copy, the kernels replay from a CUDA graph.
+ * Arguments as for sc_replay_store_host + sc_agent_learn. */
+int sc_agent_store_learn(sc_agent* a, const float* transition_host, int priority_mode, double priority,
+                         const sc_noise* noise_or_null, sc_learn_stats* stats_host_or_null);
+
+/* ---- ensembles: E independent agents (the reference's seed-ensemble axis, elasticnet/do.sh:1-6: one python process per
+ *      seed) stepped in lock-step by ONE launch sequence -- every kernel of learn() runs once with blockIdx.y = agent.
+ *      Agents must share the configuration (except rng_seed), device and stream; weights, replay contents and randomness
+ *      are per agent, and each agent's results are bit-identical to the same agent stepped alone. ------------------------ */
+typedef struct sc_ensemble sc_ensemble;
+int sc_ensemble_create(sc_agent** agents, int n, sc_ensemble** out);   /* agents stay owned by the caller and individually usable */
+int sc_ensemble_destroy(sc_ensemble* e);
+/* noise / stats: arrays of n entries (or NULL) */
+int sc_ensemble_learn(sc_ensemble* e, const sc_noise* noise_array_or_null, sc_learn_stats* stats_host_array_or_null);
+/* transitions_host: n packed transitions, one per agent; priorities_or_null: n doubles (priority_mode 2 / 3) */
+int sc_ensemble_store_learn(sc_ensemble* e, const float* transitions_host, int priority_mode, const double* priorities_or_null,
+                            const sc_noise* noise_array_or_null, sc_learn_stats* stats_host_array_or_null);
+int64_t sc_ensemble_launch_count(sc_ensemble* e);
 /* kernels launched by this library since the handle was created (bench.py "gpu_launches") */
 int64_t sc_agent_launch_count(sc_agent* a);
 /* CUDA-event time (ms) accumulated since the last call with reset!=0 (after sc_agent_enable_kernel_timing): which = 0 critic

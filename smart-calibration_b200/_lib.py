@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsmartcal_b200.so")
 
-SC_ABI_VERSION = 1
+SC_ABI_VERSION = 2
 SC_FLAG_CRITIC_LOSS_SUM = 1   # include/smartcal_b200.h
 SC_KIND_SAC, SC_KIND_TD3 = 0, 1
 NET_ACTOR, NET_CRITIC_1, NET_CRITIC_2, NET_TARGET_CRITIC_1, NET_TARGET_CRITIC_2, NET_TARGET_ACTOR = range(6)
@@ -43,7 +43,8 @@ class ScLearnStats(C.Structure):
 
 class ScNoise(C.Structure):
     _fields_ = [("eps_next_host", C.c_void_p), ("eps_cur_host", C.c_void_p), ("eps_dual_host", C.c_void_p),
-                ("td3_target_noise", C.c_double), ("has_td3_target_noise", C.c_int32), ("reserved", C.c_int32)]
+                ("td3_target_noise", C.c_double), ("has_td3_target_noise", C.c_int32), ("reserved", C.c_int32),
+                ("per_u01_host", C.c_void_p), ("batch_idx_host", C.c_void_p)]
 
 
 class ScCalibConfig(C.Structure):
@@ -76,6 +77,12 @@ SIGNATURES = {
     "sc_agent_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sc_agent_learn": (C.c_int, [C.c_void_p, C.POINTER(ScNoise), C.POINTER(ScLearnStats)]),
     "sc_agent_soft_update": (C.c_int, [C.c_void_p, C.c_float]),
+    "sc_agent_store_learn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.POINTER(ScNoise), C.POINTER(ScLearnStats)]),
+    "sc_ensemble_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]),
+    "sc_ensemble_destroy": (C.c_int, [C.c_void_p]),
+    "sc_ensemble_learn": (C.c_int, [C.c_void_p, C.POINTER(ScNoise), C.POINTER(ScLearnStats)]),
+    "sc_ensemble_store_learn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(ScNoise), C.POINTER(ScLearnStats)]),
+    "sc_ensemble_launch_count": (C.c_int64, [C.c_void_p]),
     "sc_agent_launch_count": (C.c_int64, [C.c_void_p]),
     "sc_agent_kernel_time": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "sc_agent_enable_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),

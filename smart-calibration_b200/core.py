@@ -43,6 +43,16 @@ class DeviceAgent:
         self.h = h
         self._noise = L.ScNoise()
         self._stats = L.ScLearnStats()
+        self._pending = None          # a packed transition whose store is fused into the next learn() (sc_agent_store_learn)
+        self.n_stored = 0             # host mirror of mem_cntr (the facade's "buffer filled yet?" test costs no ABI call)
+        self.n_learned = 0            # host mirror of learn_counter
+
+    def flush(self):
+        """issue a deferred store_transition now (anything that looks at the replay state calls this first)"""
+        if self._pending is not None:
+            packed, mode, prio = self._pending
+            self._pending = None
+            L.check(self.lib.sc_replay_store_host(self.h, L.ptr(packed), int(mode), float(prio)))
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:
@@ -69,23 +79,33 @@ class DeviceAgent:
         return self._view(info)
 
     def buffer(self, name):
+        self.flush()
         info = L.ScTensorInfo()
         L.check(self.lib.sc_agent_buffer(self.h, name.encode(), C.byref(info)))
         return self._view(info)
 
     # ---- counters ---------------------------------------------------------------------------------------
     def counters(self):
+        self.flush()
         m, l, d, b = C.c_int64(), C.c_int64(), C.c_int64(), C.c_double()
         L.check(self.lib.sc_agent_get_counters(self.h, C.byref(m), C.byref(l), C.byref(d), C.byref(b)))
         return m.value, l.value, d.value, b.value
 
     def set_counters(self, mem_cntr, learn_counter, data_pointer, per_beta):
+        self.flush()
+        self.n_stored, self.n_learned = int(mem_cntr), int(learn_counter)
         L.check(self.lib.sc_agent_set_counters(self.h, int(mem_cntr), int(learn_counter), int(data_pointer), float(per_beta)))
 
     def set_scalars(self, alpha, rho, admm_rho):
         L.check(self.lib.sc_agent_set_scalars(self.h, float(alpha), float(rho), float(admm_rho)))
 
+    def rho(self):
+        """current hint multiplier / adaptive ADMM penalty (device scalar)"""
+        self.flush()
+        return float(self.buffer("rho")[0, 0].item())
+
     def sync(self):
+        self.flush()
         L.check(self.lib.sc_agent_sync(self.h))
 
     # ---- replay -----------------------------------------------------------------------------------------
@@ -100,23 +120,36 @@ class DeviceAgent:
         t[2 * S + 2 * A + 1] = 1.0 if done else 0.0
         return t
 
-    def store(self, packed, priority_mode=0, priority=0.0):
+    def store(self, packed, priority_mode=0, priority=0.0, defer=False):
+        """store one packed transition.  defer=True (the facades' store_transition): the store is held back and fused
+        into the next learn() -- one pinned block, one host->device copy, one graph launch for store + update"""
+        self.flush()
         packed = np.ascontiguousarray(packed, np.float32)
+        self.n_stored += 1
+        if defer:
+            self._pending = (packed, int(priority_mode), float(priority))
+            return
         L.check(self.lib.sc_replay_store_host(self.h, L.ptr(packed), int(priority_mode), float(priority)))
 
     def store_dev(self, block, index, priority_mode=0, priority=0.0):
+        self.flush()
+        self.n_stored += 1
         L.check(self.lib.sc_replay_store_dev(self.h, C.c_void_p(block.data_ptr()), int(index), int(priority_mode), float(priority)))
 
     def fill(self, packed, priorities=None):
         packed = np.ascontiguousarray(packed, np.float32)
         pr = None if priorities is None else np.ascontiguousarray(priorities, np.float64)
+        self.flush()
+        self.n_stored = int(packed.shape[0])
         L.check(self.lib.sc_replay_fill_host(self.h, L.ptr(packed), packed.shape[0], L.ptr(pr)))
 
     def set_batch(self, idx):
+        self.flush()
         idx = np.ascontiguousarray(idx, np.int32)
         L.check(self.lib.sc_replay_set_batch_host(self.h, L.ptr(idx), idx.shape[0]))
 
     def per_sample(self, u01=None, want_outputs=False):
+        self.flush()
         u = None if u01 is None else np.ascontiguousarray(u01, np.float64)
         if want_outputs:
             ti, w = np.empty(self.B, np.int32), np.empty(self.B, np.float32)
@@ -126,6 +159,7 @@ class DeviceAgent:
         return None
 
     def per_update(self, tree_idx, abs_err):
+        self.flush()
         ti = np.ascontiguousarray(tree_idx, np.int32)
         er = np.ascontiguousarray(np.asarray(abs_err, np.float32).reshape(-1))
         ps = np.empty(self.B, np.float32)
@@ -140,25 +174,37 @@ class DeviceAgent:
         L.check(self.lib.sc_agent_act(self.h, L.ptr(obs), L.ptr(e), L.ptr(out)))
         return out
 
-    def learn(self, eps_next=None, eps_cur=None, eps_dual=None, td3_noise=None, want_stats=False):
-        keep = []
-        n = self._noise
-
-        def hp(x):
+    def _fill_noise(self, n, keep, eps_next, eps_cur, eps_dual, td3_noise, per_u01, batch_idx):
+        def hp(x, dt):
             if x is None:
                 return None
-            arr = np.ascontiguousarray(x, np.float32)
+            arr = np.ascontiguousarray(x, dt)
             keep.append(arr)
             return arr.ctypes.data
 
-        n.eps_next_host, n.eps_cur_host, n.eps_dual_host = hp(eps_next), hp(eps_cur), hp(eps_dual)
+        n.eps_next_host, n.eps_cur_host, n.eps_dual_host = hp(eps_next, np.float32), hp(eps_cur, np.float32), hp(eps_dual, np.float32)
         n.has_td3_target_noise = 0 if td3_noise is None else 1
         n.td3_target_noise = 0.0 if td3_noise is None else float(td3_noise)
+        n.per_u01_host, n.batch_idx_host = hp(per_u01, np.float64), hp(batch_idx, np.int32)
+
+    def learn(self, eps_next=None, eps_cur=None, eps_dual=None, td3_noise=None, want_stats=False, per_u01=None, batch_idx=None):
+        """one Agent.learn().  Host arrays (noise, PER uniforms / batch indices of the caller's numpy stream) and a deferred
+        store_transition all ride in the step's single host->device copy."""
+        keep = []
+        n = self._noise
+        self._fill_noise(n, keep, eps_next, eps_cur, eps_dual, td3_noise, per_u01, batch_idx)
+        st = C.byref(self._stats) if want_stats else None
+        if self._pending is not None:
+            packed, mode, prio = self._pending
+            self._pending = None
+            L.check(self.lib.sc_agent_store_learn(self.h, L.ptr(packed), mode, prio, C.byref(n), st))
+        else:
+            L.check(self.lib.sc_agent_learn(self.h, C.byref(n), st))
+        if self.n_stored >= self.B:
+            self.n_learned += 1
         if want_stats:
-            L.check(self.lib.sc_agent_learn(self.h, C.byref(n), C.byref(self._stats)))
             s = self._stats
             return {f: getattr(s, f) for f, _ in s._fields_}
-        L.check(self.lib.sc_agent_learn(self.h, C.byref(n), None))
         return None
 
     def soft_update(self, tau):
@@ -174,3 +220,54 @@ class DeviceAgent:
         ms, n = C.c_double(), C.c_int64()
         L.check(self.lib.sc_agent_kernel_time(self.h, which, int(reset), C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+
+class DeviceEnsemble:
+    """E agents of identical configuration stepped in lock-step by ONE launch sequence (sc_ensemble_*): every kernel of
+    learn() runs once with blockIdx.y = agent.  The reference's counterpart is one python process per seed
+    (elasticnet/do.sh:1-6).  Each agent's results are bit-identical to the same agent stepped alone."""
+
+    def __init__(self, devs):
+        self.devs = list(devs)
+        self.lib = self.devs[0].lib
+        E = len(self.devs)
+        arr = (C.c_void_p * E)(*[d.h.value for d in self.devs])
+        h = C.c_void_p()
+        L.check(self.lib.sc_ensemble_create(arr, E, C.byref(h)))
+        self.h = h
+        self._noise = (L.ScNoise * E)()
+        self._stats = (L.ScLearnStats * E)()
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.sc_ensemble_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def learn(self, noise=None, want_stats=False):
+        """noise: None (device Philox for every agent) or a list of E dicts with the keyword arguments of DeviceAgent.learn"""
+        keep = []
+        for d in self.devs:
+            d.flush()
+        na = None
+        if noise is not None:
+            for i, kw in enumerate(noise):
+                kw = kw or {}
+                self.devs[i]._fill_noise(self._noise[i], keep, kw.get("eps_next"), kw.get("eps_cur"), kw.get("eps_dual"),
+                                         kw.get("td3_noise"), kw.get("per_u01"), kw.get("batch_idx"))
+            na = self._noise
+        L.check(self.lib.sc_ensemble_learn(self.h, na, self._stats if want_stats else None))
+        for d in self.devs:
+            if d.n_stored >= d.B:
+                d.n_learned += 1
+        if want_stats:
+            return [{f: getattr(s, f) for f, _ in s._fields_} for s in self._stats]
+        return None
+
+    def launch_count(self):
+        return self.lib.sc_ensemble_launch_count(self.h)

@@ -19,28 +19,25 @@ size_t rowphase_smem_bytes(int variant);
 int rowphase_max_rows(int variant);
 int rowphase_panel_rows(int variant);
 void rowphase_cluster_capacity(int* out4);
-cudaError_t launch_rowphase(const RowPhaseParams& p, int variant, int cluster_size, int nclusters, int tm, cudaStream_t st);
+// every kernel of a learn() step takes a device array of E parameter blocks (blockIdx.y = agent of the ensemble)
+cudaError_t launch_rowphase(const RowPhaseParams* pp, int E, int variant, int cluster_size, int nclusters, int tm, cudaStream_t st);
 size_t wgrad_smem_bytes();
-cudaError_t launch_wgrad(const WgradParams& p, int grid, cudaStream_t st);
-cudaError_t launch_wgrad_tc(const WgradTcParams& p, int grid, cudaStream_t st);
-cudaError_t launch_dense_tc(const DenseTcParams& p, cudaStream_t st);
+cudaError_t launch_wgrad(const WgradParams* pp, int E, int grid, cudaStream_t st);
+cudaError_t launch_wgrad_tc(const WgradTcParams* pp, int E, int grid, cudaStream_t st);
+cudaError_t launch_dense_tc(const DenseTcParams* pp, int E, int nops, int nrb, int N, int ks, cudaStream_t st);
 int dense_tc_max_clusters(int cs);
-cudaError_t launch_gather_mb(float* mb_s, float* mb_s2, float* hl, const float* state, const float* new_state, const int* bidx, int B,
-                             int Sp, int Sp32, cudaStream_t st);
+cudaError_t launch_gather_mb(const GatherP* pp, int E, int B, cudaStream_t st);
 cudaError_t launch_soft_update(const float* src, float* dst, size_t n, float tau, cudaStream_t st);
 cudaError_t launch_replay_store(const ReplayP& rp, const float* tr, int slot, int mode, double priority, double clip, cudaStream_t st);
+cudaError_t launch_replay_store_t(const StoreP* pp, int E, cudaStream_t st);
 cudaError_t launch_replay_fill(const ReplayP& rp, const float* tr, int n, cudaStream_t st);
 cudaError_t launch_tree_build(double* tree, int C, const double* pr, int n, cudaStream_t st);
-cudaError_t launch_per_sample(const double* tree, int C, int B, const double* u01, uint64_t seed, uint64_t ctr, double beta,
-                              int* tree_idx, int* data_idx, float* is_w, float* is_wsum, cudaStream_t st);
-cudaError_t launch_per_update(double* tree, int C, int B, const int* idx, const float* err, float clip, float* ps_out,
-                              const float* ps_in, cudaStream_t st);
-cudaError_t launch_sample_uniform(int n, int B, uint64_t seed, uint64_t ctr, int* out, cudaStream_t st);
+cudaError_t launch_per_sample(const PerSampleP* pp, int E, int B, cudaStream_t st);
+cudaError_t launch_per_update(const PerUpdateP* pp, int E, int B, cudaStream_t st);
+cudaError_t launch_sample_uniform(const UniformP* pp, int E, int n, cudaStream_t st);
 cudaError_t launch_fill_normal(float* out, int n, uint64_t seed, uint64_t stream, cudaStream_t st);
-cudaError_t launch_admm_update(int mode, int it, const float* pi, const float* hint, int Ap, const int* bidx, int B, int A,
-                               float* lambda, float* y0, float* a0, float* rho, float rho0, float corr_min, cudaStream_t st);
-cudaError_t launch_hint_coef(const float* pi, const float* hint, int Ap, const int* bidx, int B, int A, float thr, float admm_rho,
-                             const float* rho, float* out, float* rho_update, cudaStream_t st);
+cudaError_t launch_admm_update(const AdmmP* pp, int E, cudaStream_t st);
+cudaError_t launch_hint_coef(const HintCoefP* pp, int E, cudaStream_t st);
 }  // namespace sc
 
 using namespace sc;
@@ -58,6 +55,20 @@ static int fail(int code, const char* fmt, ...) {
     cudaError_t e_ = (call);                                                                     \
     if (e_ != cudaSuccess) return fail(SC_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
   } while (0)
+
+// every ABI entry selects the agent's device for its duration (and restores the caller's): handles are usable from any
+// current-device context, e.g. one agent per GPU inside one process
+struct DevGuard {
+  int prev = -1, dev;
+  explicit DevGuard(int d) : dev(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DevGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
+#define DEV(a) DevGuard dev_guard_((a)->device)
 
 static inline int round4i(int x) { return (x + 3) & ~3; }
 static inline int round32i(int x) { return (x + 31) & ~31; }
@@ -164,15 +175,62 @@ struct KernelTimer {
   int64_t launches = 0;
 };
 
+// ---- step tape + launch plan -----------------------------------------------------------------------------------------------
+// One learn() step (of one agent, or of all E agents of an ensemble in lock-step) is planned on the host as a list of
+// records -- kernel launches, stream forks / joins, host data blocks -- while every parameter block and every host-supplied
+// array (noise, PER uniforms, batch indices, a transition to store) is written into ONE pinned "tape".  The step then costs
+// one host->device copy of the tape plus the launches, each kernel reading its parameters from the device copy
+// (blockIdx.y = agent).  Identical plans (same records, same tape offsets) are replayed as a CUDA graph.
+enum { KID_STORE = 0, KID_PER_SAMPLE, KID_UNIFORM, KID_GATHER, KID_DENSE, KID_ROW, KID_PER_UPDATE, KID_WGRAD, KID_WGRAD_TC, KID_HINT,
+       KID_ADMM };
+enum { REC_KERNEL = 0, REC_DATA, REC_FORK, REC_JOIN_RECORD, REC_JOIN_WAIT, REC_TBEGIN, REC_TEND };
+struct Rec {
+  int type, kid, stream;           // stream: 0 main, 1 side (PER), 2 side2 (narrow weight gradients)
+  int g[5];                        // kernel geometry (grid / cluster / variant ...), or fork/join pair, or timer id
+  size_t off, bytes;               // tape offset of the E parameter blocks / data blocks, bytes per agent
+};
+struct GraphEntry { int seen = 0; cudaGraphExec_t exec = nullptr; };
+struct sc_group {
+  std::vector<sc_agent*> ag;
+  int E = 0, device = 0;
+  cudaStream_t st = nullptr;                  // agent 0's stream: eager launches, tape copies and graph launches go here
+  cudaStream_t st_side = nullptr, st_side2 = nullptr, st_cap = nullptr;   // library-owned (st may be the legacy default stream, which cannot be captured)
+  cudaEvent_t ev_fork[3] = {nullptr, nullptr, nullptr}, ev_join[3] = {nullptr, nullptr, nullptr};
+  char* tape_dev = nullptr;
+  char* tape_host[2] = {nullptr, nullptr};
+  cudaEvent_t ev_up[2] = {nullptr, nullptr};
+  int tk = 0;
+  size_t tape_cap = 0, used = 0;
+  float *stats_dev = nullptr, *h_stats = nullptr;          // [E][32]
+  std::vector<Rec> recs;
+  std::map<uint64_t, GraphEntry> graphs;
+  int use_graph = 1;
+  int plan_error = 0;
+  int64_t launches = 0, graph_launches = 0;
+};
+struct sc_ensemble { sc_group g; };
+extern "C" {
+static int group_init(sc_group* g, sc_agent** agents, int n);
+static void group_free(sc_group* g);
+}
+constexpr size_t IMM_SLOT = 8192;
+
 struct sc_agent {
   sc_config cfg;
+  int device;
+  sc_group* own;                     // the agent's private group of one (stand-alone learn())
+  sc_group* grp;                     // group the agent is being planned in (own, or an ensemble's)
+  int gidx;                          // index within grp
+  size_t cursor;                     // next plan record (agents after the first re-walk the records of agent 0)
+  // immediate parameter slots for the stand-alone entry points (act, sample, update): pinned ring + device ring
+  char *imm_host, *imm_dev;
+  cudaEvent_t ev_imm[4];
+  int imm_k;
   cudaStream_t st;
-  cudaStream_t st_side;              // PER tree update runs here, overlapped with the weight-gradient / actor kernels
   int eps_inline[3]; unsigned long long eps_stream[3];
-  cudaStream_t st_side2;             // narrow-layer weight gradients run here next to the tensor-core kernel
-  cudaEvent_t ev_fork, ev_join, ev_fork2, ev_join2;
+  const float* eps_dev[3];           // where this step's noise arrays live (tape data block, or the arena buffer for in-kernel draws)
   // pinned staging regions are guarded by one event each (recorded after the copy that reads the region, waited on before
-  // the host rewrites it) instead of stream-wide synchronisation: 0..2 noise slots, 3 transition, 4 PER uniforms, 5 batch indices
+  // the host rewrites it) instead of stream-wide synchronisation: 3 transition, 4 PER uniforms, 5 batch indices
   cudaEvent_t ev_stage[6];
   void* arena;
   bool owns_arena;
@@ -199,6 +257,7 @@ struct sc_agent {
   std::map<std::string, sc_tensor_info> buffers;
   float *y, *err, *part, *is_w, *is_wsum, *eps[3], *stats, *hint_out, *rho_dev, *ps_out, *admm_lambda, *admm_y0, *admm_a0;
   int *bidx, *tree_idx;
+  const int* bidx_step;               // minibatch slots of the step being planned: bidx, or a host-supplied list in the step tape
   // PER presampling (device RNG): while the rest of learn() runs, the side stream already draws the NEXT minibatch from the
   // updated tree into the alternate buffers; learn() swaps them in if nothing touched the replay state in between
   int *bidx_alt, *tree_idx_alt;
@@ -336,6 +395,7 @@ static size_t carve(sc_agent* a, void* base) {
   a->admm_a0 = cv.f((size_t)B * A);
   reg("admm_lambda", a->admm_lambda, B, A, A, 4);
   a->rho_dev = cv.f(4);
+  reg("rho", a->rho_dev, 1, 1, 1, 4);
   a->bidx = (int*)cv.take(sizeof(int) * B);
   a->tree_idx = (int*)cv.take(sizeof(int) * B);
   a->bidx_alt = (int*)cv.take(sizeof(int) * B);
@@ -737,16 +797,15 @@ int sc_agent_create(const sc_config* cfg, void* arena, size_t arena_bytes, void*
   sc_agent* a = new sc_agent();
   init_dims(a, cfg);
   a->st = (cudaStream_t)cuda_stream;
-  a->st_side = nullptr; a->ev_fork = a->ev_join = a->ev_fork2 = a->ev_join2 = nullptr;
+  a->device = dev;
+  a->own = nullptr; a->grp = nullptr; a->gidx = 0; a->cursor = 0;
+  a->imm_host = a->imm_dev = nullptr; a->imm_k = 0;
+  for (auto& e : a->ev_imm) e = nullptr;
   for (auto& e : a->ev_stage) e = nullptr;
-  CK(cudaStreamCreateWithFlags(&a->st_side, cudaStreamNonBlocking));
-  a->st_side2 = nullptr;
-  CK(cudaStreamCreateWithFlags(&a->st_side2, cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&a->ev_fork, cudaEventDisableTiming));
-  CK(cudaEventCreateWithFlags(&a->ev_join, cudaEventDisableTiming));
-  CK(cudaEventCreateWithFlags(&a->ev_fork2, cudaEventDisableTiming));
-  CK(cudaEventCreateWithFlags(&a->ev_join2, cudaEventDisableTiming));
   for (auto& e : a->ev_stage) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : a->ev_imm) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CK(cudaHostAlloc((void**)&a->imm_host, 4 * IMM_SLOT, cudaHostAllocDefault));
+  CK(cudaMalloc((void**)&a->imm_dev, 4 * IMM_SLOT));
   const size_t need = carve(a, nullptr);
   if (arena) {
     if (arena_bytes < need) { delete a; return fail(SC_ERR_ARG, "arena too small: %zu < %zu", arena_bytes, need); }
@@ -822,24 +881,27 @@ int sc_agent_create(const sc_config* cfg, void* arena, size_t arena_bytes, void*
   if (rc) { sc_agent_destroy(a); return rc; }
   rc = build_tensor_maps(a);
   if (rc) { sc_agent_destroy(a); return rc; }
+  a->own = new sc_group();
+  sc_agent* one[1] = {a};
+  rc = group_init(a->own, one, 1);
+  if (rc) { sc_agent_destroy(a); return rc; }
   *out = a;
   return SC_OK;
 }
 
 int sc_agent_destroy(sc_agent* a) {
   if (!a) return SC_OK;
+  DEV(a);
   cudaStreamSynchronize(a->st);
   for (auto& t : a->timers) {
     for (auto& p : t.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto& p : t.pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   }
-  if (a->st_side) { cudaStreamSynchronize(a->st_side); cudaStreamDestroy(a->st_side); }
-  if (a->st_side2) { cudaStreamSynchronize(a->st_side2); cudaStreamDestroy(a->st_side2); }
+  if (a->own) { group_free(a->own); delete a->own; a->own = nullptr; }
   for (auto& e : a->ev_stage) if (e) cudaEventDestroy(e);
-  if (a->ev_fork) cudaEventDestroy(a->ev_fork);
-  if (a->ev_join) cudaEventDestroy(a->ev_join);
-  if (a->ev_fork2) cudaEventDestroy(a->ev_fork2);
-  if (a->ev_join2) cudaEventDestroy(a->ev_join2);
+  for (auto& e : a->ev_imm) if (e) cudaEventDestroy(e);
+  if (a->imm_host) cudaFreeHost(a->imm_host);
+  if (a->imm_dev) cudaFree(a->imm_dev);
   if (a->h_stage) cudaFreeHost(a->h_stage);
   if (a->h_stats) cudaFreeHost(a->h_stats);
   if (a->h_idx) cudaFreeHost(a->h_idx);
@@ -852,6 +914,7 @@ int sc_agent_destroy(sc_agent* a) {
 
 int sc_agent_sync(sc_agent* a) {
   if (!a) return fail(SC_ERR_ARG, "null agent");
+  DEV(a);
   CK(cudaStreamSynchronize(a->st));
   return SC_OK;
 }
@@ -888,7 +951,7 @@ int sc_agent_tensor(sc_agent* a, int net, int slot, const char* name, sc_tensor_
 
 int sc_agent_buffer(sc_agent* a, const char* name, sc_tensor_info* out) {
   if (!a || !name || !out) return fail(SC_ERR_ARG, "null argument");
-  touch_replay(a);                            // the caller may write the tree / replay arrays through the returned pointer
+  if (strcmp(name, "rho") != 0) touch_replay(a);   // the caller may write the tree / replay arrays through the returned pointer
   auto it = a->buffers.find(name);
   if (it == a->buffers.end()) return fail(SC_ERR_ARG, "unknown buffer '%s'", name);
   *out = it->second;
@@ -904,22 +967,40 @@ int sc_agent_get_counters(sc_agent* a, int64_t* mem_cntr, int64_t* learn_counter
   return SC_OK;
 }
 int sc_agent_set_counters(sc_agent* a, int64_t mem_cntr, int64_t learn_counter, int64_t data_pointer, double per_beta) {
-  touch_replay(a);
   if (!a) return fail(SC_ERR_ARG, "null agent");
+  touch_replay(a);
   a->mem_cntr = mem_cntr; a->learn_counter = learn_counter; a->data_pointer = data_pointer; a->per_beta = per_beta;
   a->data_length = mem_cntr < a->C ? mem_cntr : a->C;
   return SC_OK;
 }
 int sc_agent_set_scalars(sc_agent* a, float alpha, float rho, float admm_rho) {
   if (!a) return fail(SC_ERR_ARG, "null agent");
+  DEV(a);
   a->alpha = alpha; a->rho = rho; a->admm_rho = admm_rho;
   CK(cudaStreamSynchronize(a->st));
   CK(cudaMemcpy(a->rho_dev, &rho, sizeof(float), cudaMemcpyHostToDevice));   // rho evolves on the device
   return SC_OK;
 }
 
+// ---- immediate parameter slots (stand-alone entry points outside learn()) ------------------------------------------------
+struct ImmSlot { char* host; char* dev; int k; };
+static int imm_begin(sc_agent* a, ImmSlot& s) {
+  s.k = a->imm_k;
+  a->imm_k = (a->imm_k + 1) & 3;
+  CK(cudaEventSynchronize(a->ev_imm[s.k]));                  // the copy that read this pinned slot last (normally long complete)
+  s.host = a->imm_host + (size_t)s.k * IMM_SLOT;
+  s.dev = a->imm_dev + (size_t)s.k * IMM_SLOT;
+  return SC_OK;
+}
+static int imm_commit(sc_agent* a, const ImmSlot& s, size_t bytes) {
+  CK(cudaMemcpyAsync(s.dev, s.host, bytes, cudaMemcpyHostToDevice, a->st));
+  CK(cudaEventRecord(a->ev_imm[s.k], a->st));
+  return SC_OK;
+}
+
 // ---- replay ----------------------------------------------------------------------------------------------
-static int store_common(sc_agent* a, const float* tr_dev, int priority_mode, double priority) {
+// slot bookkeeping of ReplayBuffer.store_transition (enet_sac.py:35-44) / PER.store_transition (:237-268)
+static int next_slot(sc_agent* a, int& priority_mode) {
   int slot;
   if (a->cfg.prioritized) {
     if (priority_mode == 0) priority_mode = 1;
@@ -930,16 +1011,21 @@ static int store_common(sc_agent* a, const float* tr_dev, int priority_mode, dou
     priority_mode = 0;
     slot = (int)(a->mem_cntr % a->C);
   }
+  a->mem_cntr++;
+  return slot;
+}
+static int store_common(sc_agent* a, const float* tr_dev, int priority_mode, double priority) {
+  const int slot = next_slot(a, priority_mode);
   CK(launch_replay_store(a->rp, tr_dev, slot, priority_mode, priority, (double)a->cfg.per_clip, a->st));
   a->launches++;
-  a->mem_cntr++;
   return SC_OK;
 }
 int sc_replay_store_host(sc_agent* a, const float* transition_host, int priority_mode, double priority) {
-  touch_replay(a);
   if (!a || !transition_host) return fail(SC_ERR_ARG, "null argument");
+  DEV(a);
+  touch_replay(a);
   // the pinned slot is reused by the next call: wait for the copy that read it last (normally long complete)
-  float* h = a->h_stage + (size_t)3 * a->B * a->A;
+  float* h = a->h_stage;
   CK(cudaEventSynchronize(a->ev_stage[3]));
   memcpy(h, transition_host, (size_t)a->T * sizeof(float));
   CK(cudaMemcpyAsync(a->store_stage, h, (size_t)a->T * sizeof(float), cudaMemcpyHostToDevice, a->st));
@@ -947,13 +1033,15 @@ int sc_replay_store_host(sc_agent* a, const float* transition_host, int priority
   return store_common(a, a->store_stage, priority_mode, priority);
 }
 int sc_replay_store_dev(sc_agent* a, const float* transitions_dev, int index, int priority_mode, double priority) {
-  touch_replay(a);
   if (!a || !transitions_dev || index < 0) return fail(SC_ERR_ARG, "bad argument");
+  DEV(a);
+  touch_replay(a);
   return store_common(a, transitions_dev + (size_t)index * a->T, priority_mode, priority);
 }
 int sc_replay_fill_host(sc_agent* a, const float* transitions_host, int n, const double* priorities_host) {
-  touch_replay(a);
   if (!a || !transitions_host || n < 0 || n > a->C) return fail(SC_ERR_ARG, "bad argument");
+  DEV(a);
+  touch_replay(a);
   float* tmp = nullptr;
   CK(cudaMalloc(&tmp, (size_t)n * a->T * sizeof(float)));
   CK(cudaMemcpyAsync(tmp, transitions_host, (size_t)n * a->T * sizeof(float), cudaMemcpyHostToDevice, a->st));
@@ -979,8 +1067,9 @@ int sc_replay_fill_host(sc_agent* a, const float* transitions_host, int n, const
 }
 
 int sc_replay_set_batch_host(sc_agent* a, const int32_t* idx_host, int n) {
-  touch_replay(a);
   if (!a || !idx_host || n != a->B) return fail(SC_ERR_ARG, "expected %d indices", a ? a->B : 0);
+  DEV(a);
+  touch_replay(a);
   CK(cudaEventSynchronize(a->ev_stage[5]));   // h_idx may still be in flight from the previous step
   memcpy(a->h_idx, idx_host, (size_t)n * sizeof(int32_t));
   CK(cudaMemcpyAsync(a->bidx, a->h_idx, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, a->st));
@@ -988,33 +1077,61 @@ int sc_replay_set_batch_host(sc_agent* a, const int32_t* idx_host, int n) {
   a->batch_ready = true;
   return SC_OK;
 }
+static UniformP uniform_params(sc_agent* a, int n) {
+  UniformP u;
+  u.n = n; u.B = a->B; u.seed = a->cfg.rng_seed; u.ctr = 0x5000000000ull + (a->sample_ctr++); u.out = a->bidx;
+  return u;
+}
 int sc_replay_sample_uniform_dev(sc_agent* a) {
-  touch_replay(a);
   if (!a) return fail(SC_ERR_ARG, "null agent");
+  DEV(a);
+  touch_replay(a);
   const int n = (int)(a->mem_cntr < a->C ? a->mem_cntr : a->C);
   if (n < a->B) return fail(SC_ERR_STATE, "only %d transitions stored, batch is %d", n, a->B);
-  CK(launch_sample_uniform(n, a->B, a->cfg.rng_seed, 0x5000000000ull + (a->sample_ctr++), a->bidx, a->st));
+  ImmSlot s;
+  int rc = imm_begin(a, s);
+  if (rc) return rc;
+  *reinterpret_cast<UniformP*>(s.host) = uniform_params(a, n);
+  if ((rc = imm_commit(a, s, sizeof(UniformP)))) return rc;
+  CK(launch_sample_uniform(reinterpret_cast<const UniformP*>(s.dev), 1, n, a->st));
   a->launches++;
   a->batch_ready = true;
   return SC_OK;
 }
+static PerSampleP per_sample_params(sc_agent* a, const double* u01_dev, double beta, bool alt) {
+  PerSampleP p;
+  p.tree = a->rp.tree; p.C = a->C; p.B = a->B; p.u01 = u01_dev;
+  p.seed = a->cfg.rng_seed; p.ctr = 0x6000000000ull + (a->sample_ctr++);
+  p.beta = beta;
+  p.tree_idx = alt ? a->tree_idx_alt : a->tree_idx;
+  p.data_idx = alt ? a->bidx_alt : a->bidx;
+  p.is_w = alt ? a->is_w_alt : a->is_w;
+  p.is_wsum = alt ? a->is_wsum_alt : a->is_wsum;
+  return p;
+}
 int sc_per_sample(sc_agent* a, const double* u01_host, int32_t* tree_idx_host_out, float* is_weights_host_out) {
-  touch_replay(a);
   if (!a) return fail(SC_ERR_ARG, "null agent");
   if (!a->rp.tree) return fail(SC_ERR_STATE, "agent was created with prioritized=0");
+  DEV(a);
+  touch_replay(a);
+  if (sizeof(PerSampleP) + 16 + (size_t)a->B * sizeof(double) > IMM_SLOT) return fail(SC_ERR_UNSUPPORTED, "batch too large for the immediate slot");
+  ImmSlot s;
+  int rc = imm_begin(a, s);
+  if (rc) return rc;
+  const size_t uoff = (sizeof(PerSampleP) + 15) & ~(size_t)15;
+  size_t bytes = sizeof(PerSampleP);
   const double* u = nullptr;
   if (u01_host) {
-    CK(cudaEventSynchronize(a->ev_stage[4]));
-    memcpy(a->h_u01, u01_host, (size_t)a->B * sizeof(double));
-    CK(cudaMemcpyAsync(a->u01, a->h_u01, (size_t)a->B * sizeof(double), cudaMemcpyHostToDevice, a->st));
-    CK(cudaEventRecord(a->ev_stage[4], a->st));
-    u = a->u01;
+    memcpy(s.host + uoff, u01_host, (size_t)a->B * sizeof(double));
+    u = reinterpret_cast<const double*>(s.dev + uoff);
+    bytes = uoff + (size_t)a->B * sizeof(double);
   }
   a->per_beta = fmin(1.0, a->per_beta + 1e-4);   // enet_sac.py:288
+  *reinterpret_cast<PerSampleP*>(s.host) = per_sample_params(a, u, a->per_beta, false);
+  if ((rc = imm_commit(a, s, bytes))) return rc;
   cudaEvent_t e0, e1;
   timer_begin(a, 4, &e0, &e1);
-  CK(launch_per_sample(a->rp.tree, a->C, a->B, u, a->cfg.rng_seed, 0x6000000000ull + (a->sample_ctr++), a->per_beta, a->tree_idx,
-                       a->bidx, a->is_w, a->is_wsum, a->st));
+  CK(launch_per_sample(reinterpret_cast<const PerSampleP*>(s.dev), 1, a->B, a->st));
   timer_end(a, 4, e0, e1);
   a->launches++;
   a->batch_ready = true;
@@ -1023,13 +1140,25 @@ int sc_per_sample(sc_agent* a, const double* u01_host, int32_t* tree_idx_host_ou
   if (tree_idx_host_out || is_weights_host_out) CK(cudaStreamSynchronize(a->st));
   return SC_OK;
 }
+static PerUpdateP per_update_params(sc_agent* a, float* ps_out, const float* ps_in) {
+  PerUpdateP p;
+  p.tree = a->rp.tree; p.C = a->C; p.B = a->B; p.idx = a->tree_idx; p.err = a->err; p.clip = a->cfg.per_clip;
+  p.ps_out = ps_out; p.ps_in = ps_in;
+  return p;
+}
 int sc_per_update_host(sc_agent* a, const int32_t* tree_idx_host, const float* abs_err_host, int n, float* priorities_host_out) {
-  touch_replay(a);
   if (!a || !tree_idx_host || !abs_err_host || n != a->B) return fail(SC_ERR_ARG, "bad argument");
   if (!a->rp.tree) return fail(SC_ERR_STATE, "agent was created with prioritized=0");
+  DEV(a);
+  touch_replay(a);
   CK(cudaMemcpyAsync(a->tree_idx, tree_idx_host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, a->st));
   CK(cudaMemcpyAsync(a->err, abs_err_host, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, a->st));
-  CK(launch_per_update(a->rp.tree, a->C, n, a->tree_idx, a->err, a->cfg.per_clip, a->ps_out, nullptr, a->st));
+  ImmSlot s;
+  int rc = imm_begin(a, s);
+  if (rc) return rc;
+  *reinterpret_cast<PerUpdateP*>(s.host) = per_update_params(a, a->ps_out, nullptr);
+  if ((rc = imm_commit(a, s, sizeof(PerUpdateP)))) return rc;
+  CK(launch_per_update(reinterpret_cast<const PerUpdateP*>(s.dev), 1, a->B, a->st));
   a->launches++;
   if (priorities_host_out) CK(cudaMemcpyAsync(priorities_host_out, a->ps_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, a->st));
   CK(cudaStreamSynchronize(a->st));
@@ -1037,7 +1166,13 @@ int sc_per_update_host(sc_agent* a, const int32_t* tree_idx_host, const float* a
 }
 
 // ---- kernel parameter assembly -----------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 static void fill_common(sc_agent* a, RowPhaseParams& p) {
+  static const bool stamps = getenv("SMARTCAL_STAMPS") != nullptr;
+  static const int dbg = env_int("SMARTCAL_DBG", 0);
   memset(&p, 0, sizeof(p));
   p.kind = a->cfg.kind;
   p.closs_scale = (a->cfg.flags & SC_FLAG_CRITIC_LOSS_SUM) ? (float)a->B : 1.f;
@@ -1050,7 +1185,7 @@ static void fill_common(sc_agent* a, RowPhaseParams& p) {
   p.tw[0] = a->tw[0]; p.tw[1] = a->tw[1];
   p.aw = a->aw;
   p.rp = a->rp;
-  p.bidx = a->bidx;
+  p.bidx = a->bidx_step;
   p.is_wsum = a->cfg.prioritized ? a->is_wsum : nullptr;
   p.y = a->y; p.err = a->err; p.part = a->part;
   p.per_ps = a->cfg.prioritized ? a->ps_out : nullptr;
@@ -1061,8 +1196,8 @@ static void fill_common(sc_agent* a, RowPhaseParams& p) {
   p.maxa = a->cfg.max_action;
   p.n_q = a->cfg.kind == SC_KIND_SAC ? 2 : 1;
   p.mb_s = a->mb_s; p.mb_s2 = a->mb_s2; p.Sp32 = a->Sp32;
-  p.tstamp = getenv("SMARTCAL_STAMPS") ? a->tstamp : nullptr;
-  p.dbg = getenv("SMARTCAL_DBG") ? atoi(getenv("SMARTCAL_DBG")) : 0;
+  p.tstamp = stamps ? a->tstamp : nullptr;
+  p.dbg = dbg;
 }
 static AdamHyper adam_hyper(double lr, int64_t t) {
   // torch/optim/adam.py::_single_tensor_adam scalar math, in double like Python floats
@@ -1086,7 +1221,7 @@ static void fill_wgrad(sc_agent* a, WgradParams& w, bool actor, int do_soft, int
   w.total_tiles = actor ? a->actor_tiles : a->critic_tiles;
   w.tile_map = actor ? a->actor_tile_map : a->critic_tile_map;
   w.B = a->B;
-  w.bidx = a->bidx;
+  w.bidx = a->bidx_step;
   w.hyper[0] = adam_hyper(a->cfg.lr_actor, a->t_actor);
   w.hyper[1] = adam_hyper(a->cfg.lr_critic, a->t_critic);
   w.hyper[2] = w.hyper[1];
@@ -1098,13 +1233,72 @@ static void fill_wgrad(sc_agent* a, WgradParams& w, bool actor, int do_soft, int
   w.logp = a->cfg.kind == SC_KIND_SAC ? a->aw.logp : nullptr;
   w.pi_q = a->aw.qmin;
   w.is_wsum = a->cfg.prioritized ? a->is_wsum : nullptr;
-  w.stats = a->stats;
+  w.stats = a->grp->stats_dev + (size_t)a->gidx * 32;
   w.alpha = a->cfg.kind == SC_KIND_SAC ? a->alpha : 0.f;
 }
 
+// ---- plan records ------------------------------------------------------------------------------------------------
+static int plan_fail(sc_group* g, const char* what) {
+  g->plan_error = 1;
+  return fail(SC_ERR_STATE, "ensemble agents diverged while planning a step (%s): all agents of an ensemble must be in lock-step "
+                            "(same configuration, counters and call sequence)", what);
+}
+// appends (agent 0) or re-walks (agents 1..E-1) one record; returns its index or -1
+static int plan_rec(sc_agent* a, int type, int kid, int stream, const int (&geo)[5], size_t bytes) {
+  sc_group* g = a->grp;
+  if (g->plan_error) return -1;
+  if (a->gidx == 0) {
+    Rec r;
+    r.type = type; r.kid = kid; r.stream = stream;
+    for (int i = 0; i < 5; ++i) r.g[i] = geo[i];
+    r.bytes = bytes;
+    g->used = (g->used + 255) & ~(size_t)255;
+    r.off = g->used;
+    g->used += bytes * (size_t)g->E;
+    if (g->used > g->tape_cap) { g->plan_error = 1; fail(SC_ERR_STATE, "step tape overflow (%zu > %zu bytes)", g->used, g->tape_cap); return -1; }
+    g->recs.push_back(r);
+    if (type == REC_KERNEL) { a->launches++; g->launches++; }
+  } else {
+    if (a->cursor >= g->recs.size()) { plan_fail(g, "extra record"); return -1; }
+    const Rec& r = g->recs[a->cursor];
+    bool same = r.type == type && r.kid == kid && r.stream == stream && r.bytes == bytes;
+    for (int i = 0; i < 5; ++i) same = same && r.g[i] == geo[i];
+    if (!same) { plan_fail(g, "different record"); return -1; }
+  }
+  return (int)(a->cursor++);
+}
+extern "C++" {
+template <class P>
+static P* emit_kernel(sc_agent* a, int kid, int stream, int g0 = 0, int g1 = 0, int g2 = 0, int g3 = 0, int g4 = 0) {
+  static_assert(sizeof(P) % 8 == 0, "parameter blocks are arrays in the tape");
+  const int geo[5] = {g0, g1, g2, g3, g4};
+  const int i = plan_rec(a, REC_KERNEL, kid, stream, geo, sizeof(P));
+  if (i < 0) return nullptr;
+  sc_group* g = a->grp;
+  return reinterpret_cast<P*>(g->tape_host[g->tk] + g->recs[i].off + (size_t)a->gidx * sizeof(P));
+}
+}  // extern "C++"
+// host-supplied array of this step (noise, uniforms, indices, a transition): lands in the tape, *dev is where kernels read it
+static void* emit_data(sc_agent* a, size_t bytes, const void** dev) {
+  const int geo[5] = {0, 0, 0, 0, 0};
+  const size_t b = (bytes + 15) & ~(size_t)15;
+  const int i = plan_rec(a, REC_DATA, 0, 0, geo, b);
+  if (i < 0) return nullptr;
+  sc_group* g = a->grp;
+  const size_t off = g->recs[i].off + (size_t)a->gidx * b;
+  *dev = g->tape_dev + off;
+  return g->tape_host[g->tk] + off;
+}
+static int emit_ctl(sc_agent* a, int type, int which) {
+  const int geo[5] = {which, 0, 0, 0, 0};
+  return plan_rec(a, type, 0, 0, geo, 0) < 0 ? SC_ERR_STATE : SC_OK;
+}
+#define PL(ptr) do { if ((ptr) == nullptr) return SC_ERR_STATE; } while (0)
+
 // The two wide forward layers of a batched phase as tcgen05 launches (sc_dense_tc.cu); the op lists mirror the dense(...)
 // tables of k_rowphase (sc_rowphase_impl.cuh, PROG_CRITIC / PROG_ACTOR).
-static int run_dense_tc(sc_agent* a, const RowPhaseParams& p) {
+static int plan_dense_tc(sc_agent* a, const RowPhaseParams& p) {
+  static const bool stamps = getenv("SMARTCAL_STAMPS") != nullptr;
   const bool critic = p.program == PROG_CRITIC;
   const TensorMaps& m = critic ? a->tmd_critic : a->tmd_actor;
   const ActorP& ac = p.actor;
@@ -1125,8 +1319,11 @@ static int run_dense_tc(sc_agent* a, const RowPhaseParams& p) {
     ++n;
   };
   if (critic) {
-    CK(launch_gather_mb(a->mb_s, a->mb_s2, a->mb_hl, p.rp.state, p.rp.new_state, p.bidx, p.B, p.Sp, p.Sp32, a->st));
-    a->launches++;
+    GatherP* gp = emit_kernel<GatherP>(a, KID_GATHER, 0, a->B);
+    PL(gp);
+    gp->mb_s = a->mb_s; gp->mb_s2 = a->mb_s2; gp->hl = a->mb_hl; gp->state = p.rp.state; gp->new_state = p.rp.new_state;
+    gp->bidx = p.bidx; gp->bidx_mirror = (p.bidx != a->bidx) ? a->bidx : nullptr;
+    gp->B = p.B; gp->Sp = p.Sp; gp->Sp32 = p.Sp32;
     op(m.mb_s2, m.actor_w1, ac.b1, ac.g1, ac.be1, p.aw.t_h1, nullptr, nullptr,
        m.t_h1, m.actor_w2, ac.b2, ac.g2, ac.be2, p.aw.t_h2, nullptr, nullptr);
     for (int k = 0; k < 2; ++k)
@@ -1144,7 +1341,8 @@ static int run_dense_tc(sc_agent* a, const RowPhaseParams& p) {
   }
   d1.nops = d2.nops = n;
   // reduction split: the K loop of one CTA is the latency of the launch, so K is halved across CTA pairs wherever the grid
-  // still fits the machine in one wave (SMARTCAL_DENSE_KS=a,b pins the two stages' splits)
+  // of ONE agent still fits the machine in one wave (SMARTCAL_DENSE_KS=a,b pins the two stages' splits).  The split changes
+  // the summation order, so it is decided per agent, never by the ensemble size: an agent's bits do not depend on E.
   d1.ks = 1; d2.ks = 2;
   d2.late_trigger = 1;
   if (n * d1.nrb * (H1 / 64) * 2 <= a->sm_count && (K1 / 32) % 2 == 0 && n * d1.nrb <= a->dense_cap[2]) d1.ks = 2;   // 16-CTA clusters
@@ -1155,43 +1353,52 @@ static int run_dense_tc(sc_agent* a, const RowPhaseParams& p) {
       d1.ks = k1; d2.ks = k2;
     }
   }
-  if (getenv("SMARTCAL_STAMPS")) {
+  if (stamps) {
     if (critic) d1.tl = a->tstamp + 2880 * 8;
     d1.ts = a->tstamp + (critic ? 1280 : 1792) * 8;
     d2.ts = a->tstamp + (critic ? 1408 : 1920) * 8;
   }
-  CK(launch_dense_tc(d1, a->st));
-  CK(launch_dense_tc(d2, a->st));
-  a->launches += 2;
+  DenseTcParams* t1 = emit_kernel<DenseTcParams>(a, KID_DENSE, 0, d1.nops, d1.nrb, d1.N, d1.ks);
+  PL(t1);
+  *t1 = d1;
+  DenseTcParams* t2 = emit_kernel<DenseTcParams>(a, KID_DENSE, 0, d2.nops, d2.nrb, d2.N, d2.ks);
+  PL(t2);
+  *t2 = d2;
   return SC_OK;
 }
 
-static int run_rowphase(sc_agent* a, const RowPhaseParams& p_in, int timer_id) {
-  cudaEvent_t e0, e1;
-  if (timer_id >= 0) timer_begin(a, timer_id, &e0, &e1);
+static int plan_rowphase(sc_agent* a, const RowPhaseParams& p_in, int timer_id) {
+  int rc;
+  if (timer_id >= 0 && a->timing && (rc = emit_ctl(a, REC_TBEGIN, timer_id))) return rc;
   RowPhaseParams p = p_in;
-  if (a->dense_tc && p.program != PROG_ACT) {
-    cudaEvent_t d0, d1;
+  if (a->dense_tc) {
     const int dense_timer = timer_id == 0 ? 6 : timer_id == 2 ? 7 : -1;
-    if (dense_timer >= 0) timer_begin(a, dense_timer, &d0, &d1);
-    int rc = run_dense_tc(a, p);
-    if (rc) return rc;
-    if (dense_timer >= 0) timer_end(a, dense_timer, d0, d1);
+    if (dense_timer >= 0 && a->timing && (rc = emit_ctl(a, REC_TBEGIN, dense_timer))) return rc;
+    if ((rc = plan_dense_tc(a, p))) return rc;
+    if (dense_timer >= 0 && a->timing && (rc = emit_ctl(a, REC_TEND, dense_timer))) return rc;
     p.skip_dense = 1;
   }
-  const int ncl = p.program == PROG_ACT ? 1 : a->nclusters;
-  CK(launch_rowphase(p, a->row_variant, a->cluster_size, ncl, a->tile_tm, a->st));   // (the tensor-map boxes are built for tile_tm)
-  if (timer_id >= 0) timer_end(a, timer_id, e0, e1);
-  a->launches++;
+  RowPhaseParams* t = emit_kernel<RowPhaseParams>(a, KID_ROW, 0, a->row_variant, a->cluster_size, a->nclusters, a->tile_tm);
+  PL(t);
+  *t = p;
+  if (timer_id >= 0 && a->timing && (rc = emit_ctl(a, REC_TEND, timer_id))) return rc;
   return SC_OK;
 }
-static int run_wgrad(sc_agent* a, const WgradParams& w, int timer_id) {
-  cudaEvent_t e0, e1;
-  timer_begin(a, timer_id, &e0, &e1);
+// per-agent grid width of the grid-stride tile kernels: a stand-alone agent gets the whole machine, an ensemble shares it
+static int shared_grid(const sc_agent* a, int full, int tiles) {
+  const int E = a->grp->E;
+  int gx = (full + E - 1) / E;
+  if (gx < 8) gx = 8;
+  if (gx > tiles) gx = tiles;
+  return gx < 1 ? 1 : gx;
+}
+static int plan_wgrad(sc_agent* a, const WgradParams& w, int timer_id) {
+  static const bool stamps = getenv("SMARTCAL_STAMPS") != nullptr;
+  int rc;
+  if (a->timing && (rc = emit_ctl(a, REC_TBEGIN, timer_id))) return rc;
   const bool actor = w.ops == a->actor_ops;
   const int tc_tiles = actor ? a->actor_tc_tiles : a->critic_tc_tiles;
-  int grid = a->wgrad_grid;
-  if (grid > w.total_tiles + 1) grid = w.total_tiles + 1;
+  const int grid = shared_grid(a, a->wgrad_grid, w.total_tiles + 1);
   if (tc_tiles > 0) {
     WgradTcParams t;
     memset(&t, 0, sizeof(t));
@@ -1202,36 +1409,51 @@ static int run_wgrad(sc_agent* a, const WgradParams& w, int timer_id) {
     t.B = a->B;
     for (int i = 0; i < 3; ++i) t.hyper[i] = w.hyper[i];
     t.tau = w.tau; t.one_minus_tau = w.one_minus_tau; t.do_soft = w.do_soft;
-    t.tl = (getenv("SMARTCAL_STAMPS") && !actor) ? a->tstamp + 2304 * 8 : nullptr;
+    t.tl = (stamps && !actor) ? a->tstamp + 2304 * 8 : nullptr;
     // the wide layers (tensor-core kernel, <= 88 CTAs of one SM each) and the narrow layers + vector parameters + loss
     // readout (FP32 tile kernel) are independent: the second runs on the side stream next to the first
     const bool fork = !a->timing;
+    if (fork && (rc = emit_ctl(a, REC_FORK, 2))) return rc;
     if (fork) {
-      CK(cudaEventRecord(a->ev_fork2, a->st));
-      CK(cudaStreamWaitEvent(a->st_side2, a->ev_fork2, 0));
-      CK(launch_wgrad(w, grid, a->st_side2));
-      CK(cudaEventRecord(a->ev_join2, a->st_side2));
+      WgradParams* wp = emit_kernel<WgradParams>(a, KID_WGRAD, 2, grid);
+      PL(wp);
+      *wp = w;
+      if ((rc = emit_ctl(a, REC_JOIN_RECORD, 2))) return rc;
     }
-    CK(launch_wgrad_tc(t, tc_tiles < a->sm_count ? tc_tiles : a->sm_count, a->st));
-    a->launches++;
-    if (fork) CK(cudaStreamWaitEvent(a->st, a->ev_join2, 0));
-    else CK(launch_wgrad(w, grid, a->st));
+    WgradTcParams* tp = emit_kernel<WgradTcParams>(a, KID_WGRAD_TC, 0, shared_grid(a, a->sm_count, tc_tiles));
+    PL(tp);
+    *tp = t;
+    if (fork) {
+      if ((rc = emit_ctl(a, REC_JOIN_WAIT, 2))) return rc;
+    } else {
+      WgradParams* wp = emit_kernel<WgradParams>(a, KID_WGRAD, 0, grid);
+      PL(wp);
+      *wp = w;
+    }
   } else {
-    CK(launch_wgrad(w, grid, a->st));
+    WgradParams* wp = emit_kernel<WgradParams>(a, KID_WGRAD, 0, grid);
+    PL(wp);
+    *wp = w;
   }
-  timer_end(a, timer_id, e0, e1);
-  a->launches++;
+  if (a->timing && (rc = emit_ctl(a, REC_TEND, timer_id))) return rc;
   return SC_OK;
 }
 
 int sc_agent_act(sc_agent* a, const float* obs_host, const float* eps_host, float* action_host_out) {
   if (!a || !obs_host || !action_host_out) return fail(SC_ERR_ARG, "null argument");
-  CK(cudaStreamSynchronize(a->st));
-  float* h = a->h_stage + (size_t)3 * a->B * a->A + a->T;
-  memset(h, 0, (size_t)a->Sp32 * sizeof(float));
-  memcpy(h, obs_host, (size_t)a->S * sizeof(float));
-  CK(cudaMemcpyAsync(a->obs_dev, h, (size_t)a->Sp32 * sizeof(float), cudaMemcpyHostToDevice, a->st));
-  RowPhaseParams p;
+  DEV(a);
+  // parameters, observation and noise travel in ONE pinned block and one host->device copy
+  const size_t obs_off = (sizeof(RowPhaseParams) + 255) & ~(size_t)255, eps_off = obs_off + (size_t)a->Sp32 * sizeof(float);
+  const size_t bytes = eps_off + (size_t)round4i(a->A) * sizeof(float);
+  if (bytes > IMM_SLOT) return fail(SC_ERR_UNSUPPORTED, "observation too large for the immediate slot");
+  ImmSlot s;
+  int rc = imm_begin(a, s);
+  if (rc) return rc;
+  float* h_obs = reinterpret_cast<float*>(s.host + obs_off);
+  memset(h_obs, 0, (size_t)a->Sp32 * sizeof(float));
+  memcpy(h_obs, obs_host, (size_t)a->S * sizeof(float));
+  RowPhaseParams& p = *reinterpret_cast<RowPhaseParams*>(s.host);
+  a->bidx_step = a->bidx;
   fill_common(a, p);
   p.program = PROG_ACT;
   p.tm = a->tm_act;
@@ -1241,16 +1463,17 @@ int sc_agent_act(sc_agent* a, const float* obs_host, const float* eps_host, floa
   p.act_out = a->act_out;
   p.act_aux = a->act_aux;
   if (eps_host) {
-    memcpy(a->h_act, eps_host, (size_t)a->A * sizeof(float));
-    CK(cudaMemcpyAsync(a->act_eps, a->h_act, (size_t)a->A * sizeof(float), cudaMemcpyHostToDevice, a->st));
-    p.eps = a->act_eps;
+    memcpy(s.host + eps_off, eps_host, (size_t)a->A * sizeof(float));
+    p.eps = reinterpret_cast<const float*>(s.dev + eps_off);
   } else if (a->cfg.kind == SC_KIND_SAC) {
     CK(launch_fill_normal(a->act_eps, a->A, a->cfg.rng_seed, 0x7000000000ull + (a->noise_ctr++), a->st));
     a->launches++;
     p.eps = a->act_eps;
   }
-  int rc = run_rowphase(a, p, -1);
-  if (rc) return rc;
+  if ((rc = imm_commit(a, s, bytes))) return rc;
+  CK(cudaMemcpyAsync(a->obs_dev, s.dev + obs_off, (size_t)a->Sp32 * sizeof(float), cudaMemcpyDeviceToDevice, a->st));
+  CK(launch_rowphase(reinterpret_cast<const RowPhaseParams*>(s.dev), 1, a->row_variant, a->cluster_size, 1, a->tile_tm, a->st));
+  a->launches++;
   CK(cudaMemcpyAsync(a->h_act + 32, a->act_out, (size_t)a->A * sizeof(float), cudaMemcpyDeviceToHost, a->st));
   CK(cudaStreamSynchronize(a->st));
   memcpy(action_host_out, a->h_act + 32, (size_t)a->A * sizeof(float));
@@ -1259,6 +1482,7 @@ int sc_agent_act(sc_agent* a, const float* obs_host, const float* eps_host, floa
 
 int sc_agent_soft_update(sc_agent* a, float tau) {
   if (!a) return fail(SC_ERR_ARG, "null agent");
+  DEV(a);
   const bool td3 = a->cfg.kind == SC_KIND_TD3;
   CK(launch_soft_update(a->params + a->off_c1, a->targets + a->toff_c1, a->Lc.size, tau, a->st));
   CK(launch_soft_update(a->params + a->off_c2, a->targets + a->toff_c2, a->Lc.size, tau, a->st));
@@ -1270,61 +1494,128 @@ int sc_agent_soft_update(sc_agent* a, float tau) {
   return SC_OK;
 }
 
-static int upload_noise(sc_agent* a, const float* host, int slot, uint64_t stream_tag) {
+// noise of slot `slot` for this step: host array -> tape data block; NULL -> drawn in the kernel that consumes it (Philox)
+static int plan_noise(sc_agent* a, const float* host, int slot, uint64_t stream_tag) {
   const size_t n = (size_t)a->B * a->A;
   if (host) {
-    float* h = a->h_stage + (size_t)slot * n;
-    CK(cudaEventSynchronize(a->ev_stage[slot]));
+    const void* dev = nullptr;
+    void* h = emit_data(a, n * sizeof(float), &dev);
+    PL(h);
     memcpy(h, host, n * sizeof(float));
-    CK(cudaMemcpyAsync(a->eps[slot], h, n * sizeof(float), cudaMemcpyHostToDevice, a->st));
-    CK(cudaEventRecord(a->ev_stage[slot], a->st));
+    a->eps_dev[slot] = reinterpret_cast<const float*>(dev);
     a->eps_inline[slot] = 0;
   } else {
-    // device RNG: no fill launch -- the row-phase kernel draws the same Philox values where it consumes them
+    a->eps_dev[slot] = a->eps[slot];
     a->eps_inline[slot] = 1;
     a->eps_stream[slot] = stream_tag + (a->noise_ctr++);
   }
   return SC_OK;
 }
 static void set_eps(sc_agent* a, RowPhaseParams& p, int slot) {
-  p.eps = a->eps[slot];
+  p.eps = a->eps_dev[slot];
   p.eps_inline = a->eps_inline[slot];
   p.eps_seed = a->cfg.rng_seed;
   p.eps_stream = a->eps_stream[slot];
-  p.eps_store = a->eps[slot];
+  p.eps_store = a->eps[slot];                 // the values used are left in the arena ("eps_next" / "eps_cur") for inspection
+}
+static HintCoefP hint_params(sc_agent* a, float* out, float* rho_update, float* stats_rho, float* stats_g) {
+  HintCoefP h;
+  h.pi = a->aw.pi; h.hint = a->rp.hint; h.Ap = a->Ap; h.bidx = a->bidx_step; h.B = a->B; h.A = a->A;
+  h.thr = a->cfg.hint_threshold; h.admm_rho = a->admm_rho; h.rho = a->rho_dev; h.out = out; h.rho_update = rho_update;
+  h.stats_rho = stats_rho; h.stats_g = stats_g;
+  return h;
+}
+static AdmmP admm_params(sc_agent* a, int mode, int it, float* stats_rho) {
+  AdmmP m;
+  m.mode = mode; m.it = it; m.pi = a->aw.pi; m.hint = a->rp.hint; m.Ap = a->Ap; m.bidx = a->bidx_step; m.B = a->B; m.A = a->A;
+  m.lambda = a->admm_lambda; m.y0 = a->admm_y0; m.a0 = a->admm_a0; m.rho = a->rho_dev; m.rho0 = a->admm_rho; m.corr_min = 0.5f;
+  m.stats_rho = stats_rho;
+  return m;
 }
 
-int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_host) {
-  if (!a) return fail(SC_ERR_ARG, "null agent");
-  if (stats_host) memset(stats_host, 0, sizeof(*stats_host));
-  if (a->mem_cntr < a->B) {   // enet_sac.py:556-557
-    if (stats_host) stats_host->learn_counter = (int32_t)a->learn_counter;
-    return SC_OK;
+struct StepArgs {
+  const sc_noise* noise = nullptr;
+  const float* store_tr = nullptr;            // fused store: one packed transition (host) stored before the update
+  int store_mode = 0;
+  double store_priority = 0.0;
+};
+struct StepOut { bool did_learn = false, actor_step = false, hint_stats = false; };
+
+// Plans one agent's step into its group's tape (Agent.store_transition + Agent.learn, enet_sac.py:544-628 / enet_td3.py:222-364)
+static int plan_step(sc_agent* a, const StepArgs& sa, StepOut& so) {
+  const sc_noise* noise = sa.noise;
+  int rc;
+  a->bidx_step = a->bidx;
+  float* stats = a->grp->stats_dev + (size_t)a->gidx * 32;
+  if (sa.store_tr) {
+    touch_replay(a);
+    int mode = sa.store_mode;
+    const int slot = next_slot(a, mode);
+    const void* dev = nullptr;
+    void* h = emit_data(a, (size_t)a->T * sizeof(float), &dev);
+    PL(h);
+    memcpy(h, sa.store_tr, (size_t)a->T * sizeof(float));
+    StoreP* sp = emit_kernel<StoreP>(a, KID_STORE, 0);
+    PL(sp);
+    sp->rp = a->rp; sp->tr = reinterpret_cast<const float*>(dev); sp->slot = slot; sp->priority_mode = mode;
+    sp->priority = sa.store_priority; sp->clip = (double)a->cfg.per_clip;
   }
+  if (a->mem_cntr < a->B) return SC_OK;   // enet_sac.py:556-557
+  so.did_learn = true;
   const bool sac = a->cfg.kind == SC_KIND_SAC;
   const bool per = a->cfg.prioritized != 0;
-  int rc;
   const bool was_quiet = a->quiet;          // nothing touched the replay state since the previous learn() returned
   bool internal_sample = false;
   if (!a->batch_ready) {
     internal_sample = true;
-    if (per && a->presampled) {
+    const double* u01_host = noise ? noise->per_u01_host : nullptr;
+    const int32_t* idx_host = noise ? noise->batch_idx_host : nullptr;
+    if (per && a->presampled && !u01_host) {
       // the minibatch was drawn on the side stream during the previous step (after its priority update): swap it in
       std::swap(a->bidx, a->bidx_alt); std::swap(a->tree_idx, a->tree_idx_alt);
       std::swap(a->is_w, a->is_w_alt); std::swap(a->is_wsum, a->is_wsum_alt);
       a->buffers["batch_idx"].dev_ptr = a->bidx; a->buffers["tree_idx"].dev_ptr = a->tree_idx; a->buffers["is_weights"].dev_ptr = a->is_w;
+      a->bidx_step = a->bidx;
       a->per_beta = a->presample_beta;
       a->presampled = false;
+    } else if (per) {
+      touch_replay(a);
+      const double* u = nullptr;
+      if (u01_host) {
+        const void* dev = nullptr;
+        void* h = emit_data(a, (size_t)a->B * sizeof(double), &dev);
+        PL(h);
+        memcpy(h, u01_host, (size_t)a->B * sizeof(double));
+        u = reinterpret_cast<const double*>(dev);
+      }
+      a->per_beta = fmin(1.0, a->per_beta + 1e-4);   // enet_sac.py:288
+      if (a->timing && (rc = emit_ctl(a, REC_TBEGIN, 4))) return rc;
+      PerSampleP* ps = emit_kernel<PerSampleP>(a, KID_PER_SAMPLE, 0, a->B);
+      PL(ps);
+      *ps = per_sample_params(a, u, a->per_beta, false);
+      if (a->timing && (rc = emit_ctl(a, REC_TEND, 4))) return rc;
+    } else if (idx_host && a->dense_tc) {
+      touch_replay(a);
+      const void* dev = nullptr;
+      void* h = emit_data(a, (size_t)a->B * sizeof(int32_t), &dev);
+      PL(h);
+      memcpy(h, idx_host, (size_t)a->B * sizeof(int32_t));
+      a->bidx_step = reinterpret_cast<const int*>(dev);      // (k_gather_mb mirrors it into the arena's batch_idx buffer)
+    } else if (idx_host) {
+      if ((rc = sc_replay_set_batch_host(a, idx_host, a->B))) return rc;
     } else {
-      rc = per ? sc_per_sample(a, nullptr, nullptr, nullptr) : sc_replay_sample_uniform_dev(a);
-      if (rc) return rc;
+      touch_replay(a);
+      const int n = (int)(a->mem_cntr < a->C ? a->mem_cntr : a->C);
+      UniformP* up = emit_kernel<UniformP>(a, KID_UNIFORM, 0, n);
+      PL(up);
+      *up = uniform_params(a, n);
     }
   }
   if (a->presampled) { a->presampled = false; a->sample_ctr--; }   // (a batch supplied from outside supersedes it)
   a->batch_ready = false;
   if (sac) {
-    if ((rc = upload_noise(a, noise ? noise->eps_next_host : nullptr, 0, 0x1000000000ull))) return rc;
-    if ((rc = upload_noise(a, noise ? noise->eps_cur_host : nullptr, 1, 0x2000000000ull))) return rc;
+    if ((rc = plan_noise(a, noise ? noise->eps_next_host : nullptr, 0, 0x1000000000ull))) return rc;
+    if ((rc = plan_noise(a, noise ? noise->eps_cur_host : nullptr, 1, 0x2000000000ull))) return rc;
   }
   // ---- critic phase ----
   RowPhaseParams p;
@@ -1341,40 +1632,43 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
     nz = nz < -0.5 ? -0.5 : (nz > 0.5 ? 0.5 : nz);          // enet_td3.py:249 clamp in float64, cast with the add
     p.td3_noise_c = (float)nz;
   }
-  if ((rc = run_rowphase(a, p, 0))) return rc;
+  if ((rc = plan_rowphase(a, p, 0))) return rc;
   bool per_forked = false;
   if (per) {
     // PER.batch_update only depends on the priorities written by the critic row-phase and is only consumed by the NEXT
-    // sample: it runs on a side stream under the weight-gradient / actor kernels and is joined at the end of learn()
+    // sample: it runs on a side stream under the weight-gradient / actor kernels and is joined at the end of the step
     if (a->timing) {
-      cudaEvent_t e0, e1;
-      timer_begin(a, 5, &e0, &e1);
-      CK(launch_per_update(a->rp.tree, a->C, a->B, a->tree_idx, a->err, a->cfg.per_clip, nullptr, a->ps_out, a->st));
-      timer_end(a, 5, e0, e1);
+      if ((rc = emit_ctl(a, REC_TBEGIN, 5))) return rc;
+      PerUpdateP* pu = emit_kernel<PerUpdateP>(a, KID_PER_UPDATE, 0, a->B);
+      PL(pu);
+      *pu = per_update_params(a, nullptr, a->ps_out);
+      if ((rc = emit_ctl(a, REC_TEND, 5))) return rc;
     } else {
-      CK(cudaEventRecord(a->ev_fork, a->st));
-      CK(cudaStreamWaitEvent(a->st_side, a->ev_fork, 0));
-      CK(launch_per_update(a->rp.tree, a->C, a->B, a->tree_idx, a->err, a->cfg.per_clip, nullptr, a->ps_out, a->st_side));
-      if (internal_sample && was_quiet && !getenv("SMARTCAL_NO_PRESAMPLE")) {
+      static const bool no_presample = getenv("SMARTCAL_NO_PRESAMPLE") != nullptr;
+      if ((rc = emit_ctl(a, REC_FORK, 1))) return rc;
+      PerUpdateP* pu = emit_kernel<PerUpdateP>(a, KID_PER_UPDATE, 1, a->B);
+      PL(pu);
+      *pu = per_update_params(a, nullptr, a->ps_out);
+      if (internal_sample && was_quiet && !no_presample && !(noise && noise->per_u01_host)) {
         // learn() is being called back to back with the library's own sampling: draw the next minibatch now, from the tree
         // this update just produced (PER.sample_buffer of the next step, enet_sac.py:270-312), under the remaining kernels
         a->presample_beta = fmin(1.0, a->per_beta + 1e-4);
-        CK(launch_per_sample(a->rp.tree, a->C, a->B, nullptr, a->cfg.rng_seed, 0x6000000000ull + (a->sample_ctr++), a->presample_beta,
-                             a->tree_idx_alt, a->bidx_alt, a->is_w_alt, a->is_wsum_alt, a->st_side));
-        a->launches++;
+        PerSampleP* ps = emit_kernel<PerSampleP>(a, KID_PER_SAMPLE, 1, a->B);
+        PL(ps);
+        *ps = per_sample_params(a, nullptr, a->presample_beta, true);
         a->presampled = true;
       }
-      CK(cudaEventRecord(a->ev_join, a->st_side));
+      if ((rc = emit_ctl(a, REC_JOIN_RECORD, 1))) return rc;
       per_forked = true;
     }
-    a->launches++;
   }
   bool actor_step = true;
   if (!sac) actor_step = ((a->learn_counter + 1) % (a->cfg.update_actor_interval > 0 ? a->cfg.update_actor_interval : 1)) == 0;
+  so.actor_step = actor_step;
   a->t_critic++;
   WgradParams w;
   fill_wgrad(a, w, false, actor_step ? 1 : 0, 1);
-  if ((rc = run_wgrad(a, w, 1))) return rc;
+  if ((rc = plan_wgrad(a, w, 1))) return rc;
   // ---- actor phase ----
   if (actor_step) {
     fill_common(a, p);
@@ -1384,72 +1678,306 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
     if (sac) set_eps(a, p, 1); else p.eps = nullptr;
     if (sac && a->cfg.use_hint) {
       // pre-pass: forward only matters (pi), then the batch-wide penalty scalar (enet_sac.py:601-602)
-      if ((rc = run_rowphase(a, p, -1))) return rc;
-      CK(launch_hint_coef(a->aw.pi, a->rp.hint, a->Ap, a->bidx, a->B, a->A, a->cfg.hint_threshold, a->admm_rho, a->rho_dev, a->hint_out, nullptr, a->st));
-      a->launches++;
+      if ((rc = plan_rowphase(a, p, -1))) return rc;
+      HintCoefP* hp = emit_kernel<HintCoefP>(a, KID_HINT, 0);
+      PL(hp);
+      *hp = hint_params(a, a->hint_out, nullptr, stats + 16, stats + 20);
       p.hint_coef = a->hint_out;
+      so.hint_stats = true;
     }
     if (!sac && a->cfg.use_hint) {
       // adaptive-ADMM inner loop (enet_td3.py:310-361): Nadmm = 5 actor steps against the hint constraint; the penalty
       // lives on the device (rho_dev) and may be re-estimated after the 4th step; targets move once, after the loop
-      CK(launch_admm_update(0, 0, a->aw.pi, a->rp.hint, a->Ap, a->bidx, a->B, a->A, a->admm_lambda, a->admm_y0, a->admm_a0,
-                            a->rho_dev, a->admm_rho, 0.5f, a->st));
-      a->launches++;
+      AdmmP* m0 = emit_kernel<AdmmP>(a, KID_ADMM, 0);
+      PL(m0);
+      *m0 = admm_params(a, 0, 0, nullptr);
       p.admm_lambda = a->admm_lambda;
       p.admm_rho = a->rho_dev;
       for (int it = 0; it < 5; ++it) {
-        if ((rc = run_rowphase(a, p, 2))) return rc;
+        if ((rc = plan_rowphase(a, p, 2))) return rc;
         a->t_actor++;
         fill_wgrad(a, w, true, it == 4 ? 1 : 0, 2);
-        if ((rc = run_wgrad(a, w, 3))) return rc;
-        CK(launch_admm_update(1, it, a->aw.pi, a->rp.hint, a->Ap, a->bidx, a->B, a->A, a->admm_lambda, a->admm_y0, a->admm_a0,
-                              a->rho_dev, a->admm_rho, 0.5f, a->st));
-        a->launches++;
+        if ((rc = plan_wgrad(a, w, 3))) return rc;
+        AdmmP* mi = emit_kernel<AdmmP>(a, KID_ADMM, 0);
+        PL(mi);
+        *mi = admm_params(a, 1, it, stats + 16);
       }
+      so.hint_stats = true;
     } else {
-      if ((rc = run_rowphase(a, p, 2))) return rc;
+      if ((rc = plan_rowphase(a, p, 2))) return rc;
       a->t_actor++;
       fill_wgrad(a, w, true, 1, 2);
-      if ((rc = run_wgrad(a, w, 3))) return rc;
+      if ((rc = plan_wgrad(a, w, 3))) return rc;
     }
     if (sac && a->cfg.use_hint && a->learn_counter % 10 == 0) {
       // dual ascent on the hint multiplier with a fresh no-grad sample from the UPDATED actor (enet_sac.py:608-617)
-      if ((rc = upload_noise(a, noise ? noise->eps_dual_host : nullptr, 2, 0x3000000000ull))) return rc;
+      if ((rc = plan_noise(a, noise ? noise->eps_dual_host : nullptr, 2, 0x3000000000ull))) return rc;
       set_eps(a, p, 2);
       p.hint_coef = nullptr;
-      if ((rc = run_rowphase(a, p, -1))) return rc;
-      CK(launch_hint_coef(a->aw.pi, a->rp.hint, a->Ap, a->bidx, a->B, a->A, a->cfg.hint_threshold, a->admm_rho, a->rho_dev, a->hint_out + 4, a->rho_dev, a->st));
-      a->launches++;
+      if ((rc = plan_rowphase(a, p, -1))) return rc;
+      HintCoefP* hp = emit_kernel<HintCoefP>(a, KID_HINT, 0);
+      PL(hp);
+      *hp = hint_params(a, a->hint_out + 4, a->rho_dev, stats + 16, nullptr);
     }
   }
-  if (per_forked) CK(cudaStreamWaitEvent(a->st, a->ev_join, 0));     // join: later work on the agent's stream sees the updated tree
+  if (per_forked && (rc = emit_ctl(a, REC_JOIN_WAIT, 1))) return rc;     // join: later work on the stream sees the updated tree
   a->quiet = internal_sample;               // cleared by anything that may change what the next sample would see
   a->learn_counter++;
-  if (stats_host) {
-    CK(cudaMemcpyAsync(a->h_stats, a->stats, 16 * sizeof(float), cudaMemcpyDeviceToHost, a->st));
-    CK(cudaMemcpyAsync(a->h_stats + 16, a->rho_dev, sizeof(float), cudaMemcpyDeviceToHost, a->st));
-    if (sac && a->cfg.use_hint) CK(cudaMemcpyAsync(a->h_stats + 20, a->hint_out + 1, 2 * sizeof(float), cudaMemcpyDeviceToHost, a->st));
-    CK(cudaStreamSynchronize(a->st));         // the one synchronisation of a step that reads its losses back
-    stats_host->critic_1_loss = a->h_stats[0];
-    stats_host->critic_2_loss = a->h_stats[1];
-    stats_host->actor_loss = a->h_stats[2];
-    stats_host->q1_mean = a->h_stats[3];
-    stats_host->q2_mean = a->h_stats[4];
-    stats_host->target_mean = a->h_stats[5];
-    stats_host->logp_mean = a->h_stats[6];
-    a->rho = a->h_stats[16];
-    stats_host->rho = a->rho;
-    stats_host->gfun = 0.f;
-    if (sac && a->cfg.use_hint) {
-      stats_host->gfun = a->h_stats[20];
-      stats_host->actor_loss += a->h_stats[21];
+  return SC_OK;
+}
+
+// ---- group execution ---------------------------------------------------------------------------------------------
+static void group_free(sc_group* g) {
+  DevGuard dev_guard_(g->device);
+  if (g->st) cudaStreamSynchronize(g->st);
+  for (auto& kv : g->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  g->graphs.clear();
+  for (cudaStream_t* s : {&g->st_side, &g->st_side2, &g->st_cap})
+    if (*s) { cudaStreamSynchronize(*s); cudaStreamDestroy(*s); *s = nullptr; }
+  for (auto& e : g->ev_fork) if (e) { cudaEventDestroy(e); e = nullptr; }
+  for (auto& e : g->ev_join) if (e) { cudaEventDestroy(e); e = nullptr; }
+  for (auto& e : g->ev_up) if (e) { cudaEventDestroy(e); e = nullptr; }
+  for (auto& h : g->tape_host) if (h) { cudaFreeHost(h); h = nullptr; }
+  if (g->tape_dev) { cudaFree(g->tape_dev); g->tape_dev = nullptr; }
+  if (g->stats_dev) { cudaFree(g->stats_dev); g->stats_dev = nullptr; }
+  if (g->h_stats) { cudaFreeHost(g->h_stats); g->h_stats = nullptr; }
+}
+static int group_init(sc_group* g, sc_agent** agents, int n) {
+  g->ag.assign(agents, agents + n);
+  g->E = n;
+  g->device = agents[0]->device;
+  g->st = agents[0]->st;
+  DevGuard dev_guard_(g->device);
+  CK(cudaStreamCreateWithFlags(&g->st_side, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&g->st_side2, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&g->st_cap, cudaStreamNonBlocking));
+  for (auto& e : g->ev_fork) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : g->ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : g->ev_up) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  // per agent and step: <= 2 + 7 row-phase blocks, 4 + 14 dense blocks, 12 weight-gradient blocks, the small kernels, and
+  // the host arrays (3 noise tensors, B uniforms or indices, one transition)
+  const sc_agent* a = agents[0];
+  const size_t per_agent = 9 * sizeof(RowPhaseParams) + 18 * sizeof(DenseTcParams) + 12 * (sizeof(WgradParams) + sizeof(WgradTcParams)) + 8192 +
+                           (size_t)3 * a->B * a->A * sizeof(float) + (size_t)a->B * sizeof(double) + (size_t)a->T * sizeof(float) + 64 * 256;
+  g->tape_cap = ((per_agent * (size_t)n) + 4095) & ~(size_t)4095;
+  CK(cudaMalloc((void**)&g->tape_dev, g->tape_cap));
+  for (auto& h : g->tape_host) CK(cudaHostAlloc((void**)&h, g->tape_cap, cudaHostAllocDefault));
+  CK(cudaMalloc((void**)&g->stats_dev, (size_t)n * 32 * sizeof(float)));
+  CK(cudaMemset(g->stats_dev, 0, (size_t)n * 32 * sizeof(float)));
+  CK(cudaHostAlloc((void**)&g->h_stats, (size_t)n * 32 * sizeof(float), cudaHostAllocDefault));
+  const char* e = getenv("SMARTCAL_GRAPH");
+  g->use_graph = (e && e[0] == '0') ? 0 : 1;
+  return SC_OK;
+}
+static int group_begin(sc_group* g) {
+  CK(cudaEventSynchronize(g->ev_up[g->tk]));     // the tape copy that read this pinned buffer two steps ago
+  g->recs.clear();
+  g->used = 0;
+  g->plan_error = 0;
+  for (int i = 0; i < g->E; ++i) { g->ag[i]->grp = g; g->ag[i]->gidx = i; g->ag[i]->cursor = 0; }
+  return SC_OK;
+}
+static cudaError_t issue_recs(sc_group* g, cudaStream_t st0) {
+  cudaStream_t sts[3] = {st0, g->st_side, g->st_side2};
+  sc_agent* a0 = g->ag[0];
+  cudaEvent_t tev[8][2];
+  cudaError_t e = cudaSuccess;
+  for (const Rec& r : g->recs) {
+    cudaStream_t st = sts[r.stream];
+    const char* pp = g->tape_dev + r.off;
+    switch (r.type) {
+      case REC_DATA: break;
+      case REC_FORK:
+        e = cudaEventRecord(g->ev_fork[r.g[0]], st0);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(sts[r.g[0]], g->ev_fork[r.g[0]], 0);
+        break;
+      case REC_JOIN_RECORD: e = cudaEventRecord(g->ev_join[r.g[0]], sts[r.g[0]]); break;
+      case REC_JOIN_WAIT: e = cudaStreamWaitEvent(st0, g->ev_join[r.g[0]], 0); break;
+      case REC_TBEGIN: timer_begin(a0, r.g[0], &tev[r.g[0]][0], &tev[r.g[0]][1]); break;
+      case REC_TEND: timer_end(a0, r.g[0], tev[r.g[0]][0], tev[r.g[0]][1]); break;
+      case REC_KERNEL:
+        switch (r.kid) {
+          case KID_STORE: e = launch_replay_store_t(reinterpret_cast<const StoreP*>(pp), g->E, st); break;
+          case KID_PER_SAMPLE: e = launch_per_sample(reinterpret_cast<const PerSampleP*>(pp), g->E, r.g[0], st); break;
+          case KID_UNIFORM: e = launch_sample_uniform(reinterpret_cast<const UniformP*>(pp), g->E, r.g[0], st); break;
+          case KID_GATHER: e = launch_gather_mb(reinterpret_cast<const GatherP*>(pp), g->E, r.g[0], st); break;
+          case KID_DENSE: e = launch_dense_tc(reinterpret_cast<const DenseTcParams*>(pp), g->E, r.g[0], r.g[1], r.g[2], r.g[3], st); break;
+          case KID_ROW: e = launch_rowphase(reinterpret_cast<const RowPhaseParams*>(pp), g->E, r.g[0], r.g[1], r.g[2], r.g[3], st); break;
+          case KID_PER_UPDATE: e = launch_per_update(reinterpret_cast<const PerUpdateP*>(pp), g->E, r.g[0], st); break;
+          case KID_WGRAD: e = launch_wgrad(reinterpret_cast<const WgradParams*>(pp), g->E, r.g[0], st); break;
+          case KID_WGRAD_TC: e = launch_wgrad_tc(reinterpret_cast<const WgradTcParams*>(pp), g->E, r.g[0], st); break;
+          case KID_HINT: e = launch_hint_coef(reinterpret_cast<const HintCoefP*>(pp), g->E, st); break;
+          case KID_ADMM: e = launch_admm_update(reinterpret_cast<const AdmmP*>(pp), g->E, st); break;
+          default: e = cudaErrorInvalidValue;
+        }
+        break;
     }
-    stats_host->learn_counter = (int32_t)a->learn_counter;
-    stats_host->did_learn = 1;
-    stats_host->actor_step = actor_step ? 1 : 0;
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+static uint64_t plan_key(const sc_group* g) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
+  mix((uint64_t)g->E);
+  for (const Rec& r : g->recs) {
+    mix((uint64_t)r.type | ((uint64_t)r.kid << 8) | ((uint64_t)r.stream << 16));
+    for (int i = 0; i < 5; ++i) mix((uint64_t)(uint32_t)r.g[i]);
+    mix((uint64_t)r.off);
+    mix((uint64_t)r.bytes);
+  }
+  return h;
+}
+// uploads the tape and runs the planned records: eagerly the first time a plan shape is seen, from its CUDA graph afterwards
+static int group_run(sc_group* g) {
+  if (g->plan_error) return SC_ERR_STATE;
+  for (int i = 0; i < g->E; ++i)
+    if (g->ag[i]->cursor != g->recs.size()) return plan_fail(g, "missing records");
+  if (g->recs.empty()) return SC_OK;
+  CK(cudaMemcpyAsync(g->tape_dev, g->tape_host[g->tk], g->used, cudaMemcpyHostToDevice, g->st));
+  CK(cudaEventRecord(g->ev_up[g->tk], g->st));
+  g->tk ^= 1;
+  bool timing = false;
+  for (const Rec& r : g->recs) timing = timing || r.type == REC_TBEGIN;
+  if (g->use_graph && !timing) {
+    GraphEntry& ge = g->graphs[plan_key(g)];
+    if (ge.exec == nullptr && ge.seen >= 1) {
+      // second occurrence of this plan shape: capture it (on a library-owned stream: the caller's may be the legacy default
+      // stream) -- programmatic dependent launches become programmatic graph edges
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamBeginCapture(g->st_cap, cudaStreamCaptureModeRelaxed);
+      if (e == cudaSuccess) {
+        e = issue_recs(g, g->st_cap);
+        cudaError_t e2 = cudaStreamEndCapture(g->st_cap, &graph);
+        if (e == cudaSuccess) e = e2;
+      }
+      if (e == cudaSuccess) e = cudaGraphInstantiate(&ge.exec, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        ge.exec = nullptr;
+        g->use_graph = 0;                                     // this driver cannot graph the step: stay eager
+        if (getenv("SMARTCAL_DEBUG")) fprintf(stderr, "[smartcal] CUDA graph capture failed (%s): eager launches\n", cudaGetErrorString(e));
+      }
+    }
+    ge.seen++;
+    if (ge.exec != nullptr) {
+      CK(cudaGraphLaunch(ge.exec, g->st));
+      g->graph_launches++;
+      return SC_OK;
+    }
+  }
+  CK(issue_recs(g, g->st));
+  return SC_OK;
+}
+static void fill_stats(sc_agent* a, const float* hs, const StepOut& so, sc_learn_stats* out) {
+  const bool sac = a->cfg.kind == SC_KIND_SAC;
+  out->critic_1_loss = hs[0];
+  out->critic_2_loss = hs[1];
+  out->actor_loss = hs[2];
+  out->q1_mean = hs[3];
+  out->q2_mean = hs[4];
+  out->target_mean = hs[5];
+  out->logp_mean = hs[6];
+  if (so.hint_stats) a->rho = hs[16];
+  out->rho = a->rho;
+  out->gfun = 0.f;
+  if (sac && a->cfg.use_hint && so.actor_step) {
+    out->gfun = hs[20];
+    out->actor_loss += hs[21];
+  }
+  out->learn_counter = (int32_t)a->learn_counter;
+  out->did_learn = 1;
+  out->actor_step = so.actor_step ? 1 : 0;
+}
+// one step of every agent of the group; args / stats arrays have E entries (stats nullable)
+static int group_step(sc_group* g, const StepArgs* args, sc_learn_stats* stats_host) {
+  DevGuard dev_guard_(g->device);
+  int rc = group_begin(g);
+  if (rc) return rc;
+  std::vector<StepOut> so(g->E);
+  for (int i = 0; i < g->E; ++i) {
+    if (stats_host) memset(&stats_host[i], 0, sizeof(sc_learn_stats));
+    if ((rc = plan_step(g->ag[i], args[i], so[i]))) break;
+    if (so[i].did_learn != so[0].did_learn) { rc = plan_fail(g, "replay fill level"); break; }
+  }
+  for (int i = 0; i < g->E; ++i) g->ag[i]->grp = g->ag[i]->own;
+  if (rc) return rc;
+  if ((rc = group_run(g))) return rc;
+  if (stats_host) {
+    if (so[0].did_learn) {
+      CK(cudaMemcpyAsync(g->h_stats, g->stats_dev, (size_t)g->E * 32 * sizeof(float), cudaMemcpyDeviceToHost, g->st));
+      CK(cudaStreamSynchronize(g->st));         // the one synchronisation of a step that reads its losses back
+      for (int i = 0; i < g->E; ++i) fill_stats(g->ag[i], g->h_stats + (size_t)i * 32, so[i], &stats_host[i]);
+    } else {
+      for (int i = 0; i < g->E; ++i) stats_host[i].learn_counter = (int32_t)g->ag[i]->learn_counter;
+    }
   }
   return SC_OK;
 }
+
+int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_host) {
+  if (!a) return fail(SC_ERR_ARG, "null agent");
+  StepArgs sa;
+  sa.noise = noise;
+  return group_step(a->own, &sa, stats_host);
+}
+int sc_agent_store_learn(sc_agent* a, const float* transition_host, int priority_mode, double priority, const sc_noise* noise,
+                         sc_learn_stats* stats_host) {
+  if (!a || !transition_host) return fail(SC_ERR_ARG, "null argument");
+  StepArgs sa;
+  sa.noise = noise; sa.store_tr = transition_host; sa.store_mode = priority_mode; sa.store_priority = priority;
+  return group_step(a->own, &sa, stats_host);
+}
+
+// ---- ensembles: E independent agents (the reference's seed-ensemble axis, elasticnet/do.sh:1-6) stepped by ONE launch sequence ----
+int sc_ensemble_create(sc_agent** agents, int n, sc_ensemble** out) {
+  if (!agents || !out || n < 1 || n > 1024) return fail(SC_ERR_ARG, "bad argument");
+  *out = nullptr;
+  const sc_agent* a0 = agents[0];
+  for (int i = 0; i < n; ++i) {
+    const sc_agent* a = agents[i];
+    if (!a) return fail(SC_ERR_ARG, "null agent %d", i);
+    sc_config c = a->cfg, c0 = a0->cfg;
+    c.rng_seed = c0.rng_seed = 0;                             // agents may differ in their seed (and their weights / replay contents) only
+    if (memcmp(&c, &c0, sizeof(c)) != 0 || a->device != a0->device || a->st != a0->st)
+      return fail(SC_ERR_ARG, "agent %d differs from agent 0 in configuration, device or stream", i);
+    if (a->row_variant != a0->row_variant || a->cluster_size != a0->cluster_size || a->nclusters != a0->nclusters || a->tile_tm != a0->tile_tm)
+      return fail(SC_ERR_STATE, "agent %d has a different kernel geometry", i);
+    for (int j = 0; j < i; ++j)
+      if (agents[j] == a) return fail(SC_ERR_ARG, "agent %d listed twice", i);
+  }
+  sc_ensemble* e = new sc_ensemble();
+  int rc = group_init(&e->g, agents, n);
+  if (rc) { group_free(&e->g); delete e; return rc; }
+  *out = e;
+  return SC_OK;
+}
+int sc_ensemble_destroy(sc_ensemble* e) {
+  if (!e) return SC_OK;
+  group_free(&e->g);
+  delete e;
+  return SC_OK;
+}
+int sc_ensemble_learn(sc_ensemble* e, const sc_noise* noise_array, sc_learn_stats* stats_host_array) {
+  if (!e) return fail(SC_ERR_ARG, "null ensemble");
+  std::vector<StepArgs> sa(e->g.E);
+  for (int i = 0; i < e->g.E; ++i) sa[i].noise = noise_array ? &noise_array[i] : nullptr;
+  return group_step(&e->g, sa.data(), stats_host_array);
+}
+int sc_ensemble_store_learn(sc_ensemble* e, const float* transitions_host, int priority_mode, const double* priorities,
+                            const sc_noise* noise_array, sc_learn_stats* stats_host_array) {
+  if (!e || !transitions_host) return fail(SC_ERR_ARG, "null argument");
+  std::vector<StepArgs> sa(e->g.E);
+  for (int i = 0; i < e->g.E; ++i) {
+    sa[i].noise = noise_array ? &noise_array[i] : nullptr;
+    sa[i].store_tr = transitions_host + (size_t)i * e->g.ag[i]->T;
+    sa[i].store_mode = priority_mode;
+    sa[i].store_priority = priorities ? priorities[i] : 0.0;
+  }
+  return group_step(&e->g, sa.data(), stats_host_array);
+}
+int64_t sc_ensemble_launch_count(sc_ensemble* e) { return e ? e->g.launches : -1; }
 
 int64_t sc_agent_launch_count(sc_agent* a) { return a ? a->launches : -1; }
 
@@ -1460,6 +1988,7 @@ int sc_agent_enable_kernel_timing(sc_agent* a, int on) {
 }
 int sc_agent_kernel_time(sc_agent* a, int which, int reset, double* ms_total, int64_t* launches) {
   if (!a || which < 0 || which >= 8) return fail(SC_ERR_ARG, "bad argument");
+  DEV(a);
   CK(cudaStreamSynchronize(a->st));
   KernelTimer& t = a->timers[which];
   for (auto& pr : t.pending) {

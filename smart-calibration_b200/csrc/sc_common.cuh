@@ -48,6 +48,20 @@ __device__ __forceinline__ void cluster_sync() {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 
+// Every kernel of a learn() step takes its parameter block from a device-resident array with one entry per agent of the
+// launch (blockIdx.y = agent; a stand-alone agent is an ensemble of one).  The block is written by the single host->device
+// copy at the head of the step (sc_api.cu "step tape"), long before any kernel of the step starts, so fetching it here --
+// ahead of griddepcontrol.wait -- is safe under programmatic dependent launch.  All threads of the CTA must call this.
+template <typename P>
+__device__ __forceinline__ const P& load_params(const P* __restrict__ pp, P* smem_copy) {
+  static_assert(sizeof(P) % 4 == 0, "parameter blocks are copied word by word");
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(pp + blockIdx.y);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(smem_copy);
+  for (int i = threadIdx.x; i < (int)(sizeof(P) / 4); i += blockDim.x) dst[i] = __ldg(src + i);
+  __syncthreads();
+  return *smem_copy;
+}
+
 // barrier over the 256 consumer threads only (the producer warp never joins it)
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 

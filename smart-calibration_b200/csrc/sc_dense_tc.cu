@@ -61,7 +61,9 @@ __device__ __forceinline__ void dt_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constant__ DenseTcParams p) {
+__global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const DenseTcParams* __restrict__ pp) {
+  __shared__ DenseTcParams p_sm;
+  const DenseTcParams& p = load_params(pp, &p_sm);             // blockIdx.y = agent of the ensemble
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_raw[DT_STAGES], full_lo[DT_STAGES], empty[DT_STAGES], acc_done;
@@ -345,11 +347,17 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const __grid_constan
 // minibatch gather: replay rows [C][Sp] -> dense TMA-readable buffers [B][Sp32] (zero padded), states and next states:
 // the fp32 rows (X operand of the layer-1 weight gradients) and their tf32 big / small parts (X operand of k_dense_tc,
 // which then skips the split of the X boxes in every one of its CTAs)
-__global__ void __launch_bounds__(128) k_gather_mb(float* mb_s, float* mb_s2, float* hl, const float* __restrict__ state,
-                                                   const float* __restrict__ new_state, const int* __restrict__ bidx, int B, int Sp, int Sp32) {
+__global__ void __launch_bounds__(128) k_gather_mb(const GatherP* __restrict__ pp) {
+  const GatherP P = pp[blockIdx.y];
+  float *mb_s = P.mb_s, *mb_s2 = P.mb_s2, *hl = P.hl;
+  const float* __restrict__ state = P.state;
+  const float* __restrict__ new_state = P.new_state;
+  const int* __restrict__ bidx = P.bidx;
+  const int B = P.B, Sp = P.Sp, Sp32 = P.Sp32;
   const int r = blockIdx.x >> 1, which = blockIdx.x & 1;
   pdl_launch();
   pdl_wait();
+  if (P.bidx_mirror != nullptr && which == 0 && threadIdx.x == 0) P.bidx_mirror[r] = __ldg(bidx + r);
   const float* src = (which ? new_state : state) + (size_t)__ldg(bidx + r) * Sp;
   float* dst = (which ? mb_s2 : mb_s) + (size_t)r * Sp32;
   float* dhi = hl + ((size_t)(2 * which) * B + r) * Sp32;    // hl = [s_hi | s_lo | s2_hi | s2_lo], each [B][Sp32]
@@ -393,28 +401,31 @@ int dense_tc_max_clusters(int cs) {
   return n;
 }
 
-cudaError_t launch_dense_tc(const DenseTcParams& p, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+static bool dt_first_use(bool (&done)[64]) {
+  int d = 0;
+  cudaGetDevice(&d);
+  d &= 63;
+  if (done[d]) return false;
+  done[d] = true;
+  return true;
+}
+
+// pp: device array of E parameter blocks (one per agent, identical geometry nops, nrb, N, ks; every op's K / 32 divisible by ks)
+cudaError_t launch_dense_tc(const DenseTcParams* pp, int E, int nops, int nrb, int N, int ks, cudaStream_t st) {
+  static bool configured[64], big[64];
+  if (dt_first_use(configured)) {
     cudaError_t e = cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_tc_smem_bytes());
     if (e != cudaSuccess) return e;
-    configured = true;
   }
-  const int nfb = p.N / DT_N, cs = nfb * p.ks;
-  if (nfb < 1 || nfb > DT_MAXCS || nfb * DT_N != p.N || p.ks < 1 || p.ks > 2 || cs > 16) return cudaErrorInvalidValue;
-  for (int i = 0; i < p.nops; ++i)
-    if (((p.ops[i].K + 31) / 32) % p.ks != 0) return cudaErrorInvalidValue;
-  if (cs > 8) {
-    static bool big = false;
-    if (!big) {
-      cudaError_t e = cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-      if (e != cudaSuccess) return e;
-      big = true;
-    }
+  const int nfb = N / DT_N, cs = nfb * ks;
+  if (nfb < 1 || nfb > DT_MAXCS || nfb * DT_N != N || ks < 1 || ks > 2 || cs > 16) return cudaErrorInvalidValue;
+  if (cs > 8 && dt_first_use(big)) {
+    cudaError_t e = cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
   }
   cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
   cudaLaunchAttribute attr[2];
-  cfg.gridDim = dim3(p.nops * p.nrb * cs, 1, 1);
+  cfg.gridDim = dim3(nops * nrb * cs, E, 1);
   cfg.blockDim = dim3(DT_THREADS, 1, 1);
   cfg.dynamicSmemBytes = dense_tc_smem_bytes();
   cfg.stream = st;
@@ -426,21 +437,20 @@ cudaError_t launch_dense_tc(const DenseTcParams& p, cudaStream_t st) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  return cudaLaunchKernelEx(&cfg, k_dense_tc, p);
+  return cudaLaunchKernelEx(&cfg, k_dense_tc, pp);
 }
 
-cudaError_t launch_gather_mb(float* mb_s, float* mb_s2, float* hl, const float* state, const float* new_state, const int* bidx, int B,
-                             int Sp, int Sp32, cudaStream_t st) {
+cudaError_t launch_gather_mb(const GatherP* pp, int E, int B, cudaStream_t st) {
   cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
   cudaLaunchAttribute attr[1];
-  cfg.gridDim = dim3(2 * B, 1, 1);
+  cfg.gridDim = dim3(2 * B, E, 1);
   cfg.blockDim = dim3(128, 1, 1);
   cfg.stream = st;
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_gather_mb, mb_s, mb_s2, hl, state, new_state, bidx, B, Sp, Sp32);
+  return cudaLaunchKernelEx(&cfg, k_gather_mb, pp);
 }
 
 }  // namespace sc

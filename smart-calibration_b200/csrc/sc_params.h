@@ -173,6 +173,50 @@ struct DenseTcParams {
   unsigned long long* ts;          // optional [CTA][8] globaltimer stamps: entry, dependency met, accumulator done, end
 };
 
+// ---- small kernels of the step, parameter blocks (sc_per.cu, k_gather_mb) ----------------------------------------
+struct GatherP {                   // k_gather_mb
+  float *mb_s, *mb_s2, *hl;
+  const float *state, *new_state;
+  const int* bidx;
+  int* bidx_mirror;                // nullable: host-supplied indices are copied here (the arena's "batch_idx" buffer)
+  int B, Sp, Sp32;
+};
+struct PerSampleP {                // k_per_sample
+  const double* tree; int C, B;
+  const double* u01;               // B host-drawn uniforms, or nullptr: Philox(seed, ctr)
+  unsigned long long seed, ctr;
+  double beta;
+  int *tree_idx, *data_idx;
+  float *is_w, *is_wsum;
+};
+struct PerUpdateP {                // k_per_update
+  double* tree; int C, B;
+  const int* idx; const float* err;
+  float clip;
+  float* ps_out; const float* ps_in;
+};
+struct UniformP { int n, B; unsigned long long seed, ctr; int* out; };   // k_sample_uniform
+struct HintCoefP {                 // k_hint_coef
+  const float *pi, *hint; int Ap; const int* bidx; int B, A;
+  float thr, admm_rho;
+  const float* rho; float* out; float* rho_update;
+  float* stats_rho;                // nullable: *stats_rho = rho after the (optional) dual update
+  float* stats_g;                  // nullable: stats_g[0] = g, stats_g[1] = penalty added to the actor loss
+};
+struct AdmmP {                     // k_admm_update
+  int mode, it;
+  const float *pi, *hint; int Ap; const int* bidx; int B, A;
+  float *lambda, *y0, *a0, *rho;
+  float rho0, corr_min;
+  float* stats_rho;                // nullable: current penalty for the host-side diagnostics block
+};
+struct StoreP {                    // k_replay_store
+  ReplayP rp;
+  const float* tr;
+  int slot, priority_mode;
+  double priority, clip;
+};
+
 struct WgradTcParams {
   const WgradTcOp* ops; int nops;
   int total_tiles;

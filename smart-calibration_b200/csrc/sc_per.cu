@@ -18,8 +18,8 @@ namespace sc {
 // store one packed transition [s(S) | s2(S) | a(A) | hint(A) | r | done] into slot `slot`
 // priority_mode: 0 none, 1 max-leaf (or clip when the tree is empty), 2 given (f64 change), 3 given (f32 change)
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_replay_store(ReplayP rp, const float* __restrict__ tr, int slot, int priority_mode, double priority,
-                               double clip) {
+__device__ __forceinline__ void replay_store_body(const ReplayP& rp, const float* __restrict__ tr, int slot, int priority_mode,
+                                                  double priority, double clip) {
   const int tid = threadIdx.x;
   const int S = rp.S, A = rp.A;
   for (int i = tid; i < S; i += blockDim.x) {
@@ -61,6 +61,14 @@ __global__ void k_replay_store(ReplayP rp, const float* __restrict__ tr, int slo
     }
   }
 }
+__global__ void k_replay_store(ReplayP rp, const float* __restrict__ tr, int slot, int priority_mode, double priority, double clip) {
+  replay_store_body(rp, tr, slot, priority_mode, priority, clip);
+}
+// the same store as the first launch of a fused store + learn step: parameters (and the packed transition) come from the step tape
+__global__ void k_replay_store_t(const StoreP* __restrict__ pp) {
+  const StoreP p = pp[blockIdx.y];
+  replay_store_body(p.rp, p.tr, p.slot, p.priority_mode, p.priority, p.clip);
+}
 
 // bulk fill of slots [0,n) from packed transitions already in HBM
 __global__ void k_replay_fill(ReplayP rp, const float* __restrict__ tr, int n) {
@@ -99,9 +107,15 @@ __global__ void k_tree_build(double* tree, int C, const double* __restrict__ pr,
 // ---------------------------------------------------------------------------------------------------
 // stratified proportional sampling (PER.sample_buffer, enet_sac.py:270-312).  One block.
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_per_sample(const double* __restrict__ tree, int C, int B, const double* __restrict__ u01,
-                             uint64_t seed, uint64_t ctr, double beta, int* tree_idx, int* data_idx, float* is_w,
-                             float* is_wsum) {
+__global__ void k_per_sample(const PerSampleP* __restrict__ pp) {
+  const PerSampleP P = pp[blockIdx.y];
+  const double* __restrict__ tree = P.tree;
+  const int C = P.C, B = P.B;
+  const double* __restrict__ u01 = P.u01;
+  const uint64_t seed = P.seed, ctr = P.ctr;
+  const double beta = P.beta;
+  int *tree_idx = P.tree_idx, *data_idx = P.data_idx;
+  float *is_w = P.is_w, *is_wsum = P.is_wsum;
   extern __shared__ float sw[];                  // [B] raw weights
   __shared__ float sred[32];
   __shared__ double stop[511];                   // top 9 levels of the tree: one round of loads instead of 9 dependent ones
@@ -167,8 +181,15 @@ __global__ void k_per_sample(const double* __restrict__ tree, int C, int B, cons
 // priority refresh (PER.batch_update, enet_sac.py:314-323).  One block; dynamic smem: B doubles x2 + B ints.
 // ---------------------------------------------------------------------------------------------------
 // ps_in != nullptr: the float32 priorities were already evaluated by the critic row-phase kernel (err is ignored)
-__global__ void k_per_update(double* tree, int C, int B, const int* __restrict__ idx, const float* __restrict__ err,
-                             float clip, float* ps_out, const float* __restrict__ ps_in) {
+__global__ void k_per_update(const PerUpdateP* __restrict__ pp) {
+  const PerUpdateP P = pp[blockIdx.y];
+  double* tree = P.tree;
+  const int C = P.C, B = P.B;
+  const int* __restrict__ idx = P.idx;
+  const float* __restrict__ err = P.err;
+  const float clip = P.clip;
+  float* ps_out = P.ps_out;
+  const float* __restrict__ ps_in = P.ps_in;
   extern __shared__ double sd[];
   double* pv = sd;                 // new priorities (widened float32)
   double* chg = sd + B;            // change propagated by sample i
@@ -246,7 +267,11 @@ __global__ void k_per_update(double* tree, int C, int B, const int* __restrict__
 // (n <= 8192: bitonic sort in shared memory; larger: Floyd's algorithm by one thread).  Replaces
 // np.random.choice(max_mem, B, replace=False) (enet_sac.py:48) when the caller does not inject indices.
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_sample_uniform(int n, int B, uint64_t seed, uint64_t ctr, int* out) {
+__global__ void k_sample_uniform(const UniformP* __restrict__ pp) {
+  const UniformP P = pp[blockIdx.y];
+  const int n = P.n, B = P.B;
+  const uint64_t seed = P.seed, ctr = P.ctr;
+  int* out = P.out;
   extern __shared__ unsigned long long keys[];
   const int tid = threadIdx.x;
   if (n <= 8192) {
@@ -304,8 +329,15 @@ __global__ void k_fill_normal(float* out, int n, uint64_t seed, uint64_t stream)
 // hint penalty coefficient (SAC, enet_sac.py:601-602,616-617): m = mean((pi-hint)^2) over B*A,
 // g = max(0, m-thr)^2, d(0.5*admm_rho*g^2 + rho*g)/d pi = (admm_rho*g + rho) * 2*max(0,m-thr) * 2(pi-hint)/(B*A).
 // Writes out[0] = that scalar coefficient (without the (pi-hint) factor), out[1] = g.  One block.
-__global__ void k_hint_coef(const float* __restrict__ pi, const float* __restrict__ hint, int Ap, const int* __restrict__ bidx,
-                            int B, int A, float thr, float admm_rho, const float* rho, float* out, float* rho_update) {
+__global__ void k_hint_coef(const HintCoefP* __restrict__ pp) {
+  const HintCoefP P = pp[blockIdx.y];
+  const float* __restrict__ pi = P.pi;
+  const float* __restrict__ hint = P.hint;
+  const int Ap = P.Ap, B = P.B, A = P.A;
+  const int* __restrict__ bidx = P.bidx;
+  const float thr = P.thr, admm_rho = P.admm_rho;
+  const float* rho = P.rho;
+  float *out = P.out, *rho_update = P.rho_update;
   __shared__ float sred[32];
   float s = 0.f;
   for (int e = threadIdx.x; e < B * A; e += blockDim.x) {
@@ -326,6 +358,8 @@ __global__ void k_hint_coef(const float* __restrict__ pi, const float* __restric
     out[1] = g;
     out[2] = 0.5f * admm_rho * g * g + *rho * g;                               // penalty added to actor_loss (enet_sac.py:602)
     if (rho_update != nullptr) *rho_update = *rho_update + admm_rho * g;       // rho += admm_rho*gfun (enet_sac.py:617)
+    if (P.stats_g != nullptr) { P.stats_g[0] = g; P.stats_g[1] = out[2]; }
+    if (P.stats_rho != nullptr) *P.stats_rho = *rho;                           // (rho_update aliases rho: the value after the update)
   }
 }
 
@@ -333,9 +367,14 @@ __global__ void k_hint_coef(const float* __restrict__ pi, const float* __restric
 //   mode 0: start of the loop: lambda <- 0, rho <- rho0
 //   mode 1: lambda += rho*(pi - hint); it == 0 additionally y0 <- pi, a0 <- pi (the reference seeds y0 with the actions);
 //           it == 3 additionally the adaptive-penalty test with the three dot products
-__global__ void k_admm_update(int mode, int it, const float* __restrict__ pi, const float* __restrict__ hint, int Ap,
-                              const int* __restrict__ bidx, int B, int A, float* lambda, float* y0, float* a0, float* rho,
-                              float rho0, float corr_min) {
+__global__ void k_admm_update(const AdmmP* __restrict__ pp) {
+  const AdmmP P = pp[blockIdx.y];
+  const int mode = P.mode, it = P.it, Ap = P.Ap, B = P.B, A = P.A;
+  const float* __restrict__ pi = P.pi;
+  const float* __restrict__ hint = P.hint;
+  const int* __restrict__ bidx = P.bidx;
+  float *lambda = P.lambda, *y0 = P.y0, *a0 = P.a0, *rho = P.rho;
+  const float rho0 = P.rho0, corr_min = P.corr_min;
   __shared__ float sred[3][32];
   const int n = B * A, tid = threadIdx.x;
   if (mode == 0) {
@@ -364,7 +403,10 @@ __global__ void k_admm_update(int mode, int it, const float* __restrict__ pi, co
       a0[e] = a;
     }
   }
-  if (it != 3) return;
+  if (it != 3) {
+    if (tid == 0 && P.stats_rho != nullptr) *P.stats_rho = r;
+    return;
+  }
   d11 = warp_sum(d11); d12 = warp_sum(d12); d22 = warp_sum(d22);
   if ((tid & 31) == 0) { sred[0][tid >> 5] = d11; sred[1][tid >> 5] = d12; sred[2][tid >> 5] = d22; }
   __syncthreads();
@@ -376,6 +418,7 @@ __global__ void k_admm_update(int mode, int it, const float* __restrict__ pi, co
       const float a_hat = 2.f * a_mg > a_sd ? a_mg : a_sd - 0.5f * a_mg;
       if (alpha > corr_min && a_hat < 10.f * rho0 && a_hat > 0.1f * rho0) *rho = a_hat;
     }
+    if (P.stats_rho != nullptr) *P.stats_rho = *rho;
   }
 }
 
@@ -392,33 +435,38 @@ cudaError_t launch_tree_build(double* tree, int C, const double* pr, int n, cuda
   k_tree_build<<<1, 1024, 0, st>>>(tree, C, pr, n);
   return cudaGetLastError();
 }
-cudaError_t launch_per_sample(const double* tree, int C, int B, const double* u01, uint64_t seed, uint64_t ctr, double beta,
-                              int* tree_idx, int* data_idx, float* is_w, float* is_wsum, cudaStream_t st) {
+// per-device one-time kernel attribute set-up (an agent per GPU of one process each needs its own opt-in)
+static bool first_use(bool (&done)[64]) {
+  int d = 0;
+  cudaGetDevice(&d);
+  d &= 63;
+  if (done[d]) return false;
+  done[d] = true;
+  return true;
+}
+cudaError_t launch_replay_store_t(const StoreP* pp, int E, cudaStream_t st) {
+  k_replay_store_t<<<dim3(1, E), 256, 0, st>>>(pp);
+  return cudaGetLastError();
+}
+cudaError_t launch_per_sample(const PerSampleP* pp, int E, int B, cudaStream_t st) {
   const int threads = B >= 1024 ? 1024 : ((B + 31) / 32) * 32;
-  k_per_sample<<<1, threads, (size_t)B * sizeof(float), st>>>(tree, C, B, u01, seed, ctr, beta, tree_idx, data_idx, is_w, is_wsum);
+  k_per_sample<<<dim3(1, E), threads, (size_t)B * sizeof(float), st>>>(pp);
   return cudaGetLastError();
 }
-cudaError_t launch_per_update(double* tree, int C, int B, const int* idx, const float* err, float clip, float* ps_out,
-                              const float* ps_in, cudaStream_t st) {
-  static bool configured = false;
+cudaError_t launch_per_update(const PerUpdateP* pp, int E, int B, cudaStream_t st) {
+  static bool configured[64];
   const size_t smem = (size_t)B * (2 * sizeof(double) + sizeof(int));
-  if (!configured) {
-    cudaFuncSetAttribute(k_per_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
-  }
-  k_per_update<<<1, 1024, smem, st>>>(tree, C, B, idx, err, clip, ps_out, ps_in);
+  if (first_use(configured)) cudaFuncSetAttribute(k_per_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  k_per_update<<<dim3(1, E), 1024, smem, st>>>(pp);
   return cudaGetLastError();
 }
-cudaError_t launch_sample_uniform(int n, int B, uint64_t seed, uint64_t ctr, int* out, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(k_sample_uniform, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
-    configured = true;
-  }
+cudaError_t launch_sample_uniform(const UniformP* pp, int E, int n, cudaStream_t st) {
+  static bool configured[64];
+  if (first_use(configured)) cudaFuncSetAttribute(k_sample_uniform, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8);
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   const size_t smem = n <= 8192 ? (size_t)np2 * 8 : 0;
-  k_sample_uniform<<<1, 1024, smem, st>>>(n, B, seed, ctr, out);
+  k_sample_uniform<<<dim3(1, E), 1024, smem, st>>>(pp);
   return cudaGetLastError();
 }
 cudaError_t launch_fill_normal(float* out, int n, uint64_t seed, uint64_t stream, cudaStream_t st) {
@@ -426,15 +474,12 @@ cudaError_t launch_fill_normal(float* out, int n, uint64_t seed, uint64_t stream
   k_fill_normal<<<(pairs + 255) / 256, 256, 0, st>>>(out, n, seed, stream);
   return cudaGetLastError();
 }
-cudaError_t launch_hint_coef(const float* pi, const float* hint, int Ap, const int* bidx, int B, int A, float thr, float admm_rho,
-                             const float* rho, float* out, float* rho_update, cudaStream_t st) {
-  k_hint_coef<<<1, 256, 0, st>>>(pi, hint, Ap, bidx, B, A, thr, admm_rho, rho, out, rho_update);
+cudaError_t launch_hint_coef(const HintCoefP* pp, int E, cudaStream_t st) {
+  k_hint_coef<<<dim3(1, E), 256, 0, st>>>(pp);
   return cudaGetLastError();
 }
-
-cudaError_t launch_admm_update(int mode, int it, const float* pi, const float* hint, int Ap, const int* bidx, int B, int A,
-                               float* lambda, float* y0, float* a0, float* rho, float rho0, float corr_min, cudaStream_t st) {
-  k_admm_update<<<1, 256, 0, st>>>(mode, it, pi, hint, Ap, bidx, B, A, lambda, y0, a0, rho, rho0, corr_min);
+cudaError_t launch_admm_update(const AdmmP* pp, int E, cudaStream_t st) {
+  k_admm_update<<<dim3(1, E), 256, 0, st>>>(pp);
   return cudaGetLastError();
 }
 

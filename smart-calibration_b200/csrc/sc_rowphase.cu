@@ -18,8 +18,8 @@ int rowphase_max_rows_occ1();
 int rowphase_max_rows_occ2();
 int rowphase_panel_rows_occ1();
 int rowphase_panel_rows_occ2();
-cudaError_t launch_rowphase_occ1(const RowPhaseParams& p, int cs, int nclusters, int tm, cudaStream_t st);
-cudaError_t launch_rowphase_occ2(const RowPhaseParams& p, int cs, int nclusters, int tm, cudaStream_t st);
+cudaError_t launch_rowphase_occ1(const RowPhaseParams* p, int E, int cs, int nclusters, int tm, cudaStream_t st);
+cudaError_t launch_rowphase_occ2(const RowPhaseParams* p, int E, int cs, int nclusters, int tm, cudaStream_t st);
 
 // co-resident clusters per (variant, cluster size): out[0] occ1/16, out[1] occ1/8, out[2] occ2/16, out[3] occ2/8
 void rowphase_cluster_capacity(int* out) {
@@ -32,8 +32,8 @@ size_t rowphase_smem_bytes(int variant) { return variant == 2 ? rowphase_smem_oc
 int rowphase_max_rows(int variant) { return variant == 2 ? rowphase_max_rows_occ2() : rowphase_max_rows_occ1(); }       // slab height limit
 int rowphase_panel_rows(int variant) { return variant == 2 ? rowphase_panel_rows_occ2() : rowphase_panel_rows_occ1(); } // dgrad weight panel box rows
 
-cudaError_t launch_rowphase(const RowPhaseParams& p, int variant, int cs, int nclusters, int tm, cudaStream_t st) {
-  return variant == 2 ? launch_rowphase_occ2(p, cs, nclusters, tm, st) : launch_rowphase_occ1(p, cs, nclusters, tm, st);
+cudaError_t launch_rowphase(const RowPhaseParams* p, int E, int variant, int cs, int nclusters, int tm, cudaStream_t st) {
+  return variant == 2 ? launch_rowphase_occ2(p, E, cs, nclusters, tm, st) : launch_rowphase_occ1(p, E, cs, nclusters, tm, st);
 }
 
 }  // namespace sc

@@ -12,9 +12,9 @@ static cudaError_t configure(K kern, size_t smem, int cs) {
   if (e == cudaSuccess && cs > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   return e;
 }
-static void cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int nclusters, int cs, size_t smem, cudaStream_t st) {
+static void cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int nclusters, int cs, size_t smem, cudaStream_t st, int E = 1) {
   cfg = cudaLaunchConfig_t{};
-  cfg.gridDim = dim3(nclusters * cs, 1, 1);
+  cfg.gridDim = dim3(nclusters * cs, E, 1);
   cfg.blockDim = dim3(SC_ROW_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -33,13 +33,13 @@ static void cluster_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int 
   cfg.numAttrs = pdl_row ? 2 : 1;
 }
 template <typename K>
-static cudaError_t launch_k(K kern, size_t smem, const RowPhaseParams& p, int cs, int nclusters, cudaStream_t st) {
+static cudaError_t launch_k(K kern, size_t smem, const RowPhaseParams* pp, int E, int cs, int nclusters, cudaStream_t st) {
   cudaError_t e = configure(kern, smem, cs);          // idempotent and cheap
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[2];
-  cluster_cfg(cfg, attr, nclusters, cs, smem, st);
-  return cudaLaunchKernelEx(&cfg, kern, p);
+  cluster_cfg(cfg, attr, nclusters, cs, smem, st, E);
+  return cudaLaunchKernelEx(&cfg, kern, pp);
 }
 template <typename K>
 static int max_clusters(K kern, size_t smem, int cs) {

@@ -743,7 +743,11 @@ __device__ void actor_tail_forward(const RowPhaseParams& p, const TailSm& t) {
 
 __device__ __forceinline__ float eps_value(const RowPhaseParams& p, int row, int j) {
   const size_t e = (size_t)row * p.A + j;
-  if (!p.eps_inline) return ld_act(p.eps + e);
+  if (!p.eps_inline) {
+    const float v = ld_act(p.eps + e);
+    if (p.eps_store != nullptr && p.eps_store != p.eps) p.eps_store[e] = v;
+    return v;
+  }
   const float2 z = philox_normal2(p.eps_seed, p.eps_stream, (uint64_t)(e >> 1));
   const float v = (e & 1) ? z.y : z.x;
   if (p.eps_store != nullptr) p.eps_store[e] = v;
@@ -1060,7 +1064,9 @@ __device__ __forceinline__ void gather_rows(float* dst, const float* __restrict_
 }
 
 template <int CS, int TM>
-__global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(const __grid_constant__ RowPhaseParams p) {
+__global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(const RowPhaseParams* __restrict__ pp) {
+  __shared__ RowPhaseParams p_sm;
+  const RowPhaseParams& p = load_params(pp, &p_sm);           // blockIdx.y = agent of the ensemble
   extern __shared__ __align__(16) float smem_raw[];
   // the TMA boxes use the 128-byte swizzle, whose pattern repeats every 1024 bytes: align the ring accordingly
   float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);

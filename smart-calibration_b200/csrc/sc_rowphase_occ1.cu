@@ -29,13 +29,13 @@ int rowphase_capacity_occ1(int cs) {
 size_t rowphase_smem_occ1() { return occ1::SMEM_BYTES; }
 int rowphase_max_rows_occ1() { return occ1::MAXROWS; }
 int rowphase_panel_rows_occ1() { return occ1::PROW; }
-cudaError_t launch_rowphase_occ1(const RowPhaseParams& p, int cs, int nclusters, int tm, cudaStream_t st) {
+cudaError_t launch_rowphase_occ1(const RowPhaseParams* p, int E, int cs, int nclusters, int tm, cudaStream_t st) {
   if (cs == 16)
-    return tm == 2 ? launch_k(occ1::k_rowphase<16, 2>, occ1::SMEM_BYTES, p, cs, nclusters, st)
-         : tm == 3 ? launch_k(occ1::k_rowphase<16, 3>, occ1::SMEM_BYTES, p, cs, nclusters, st)
-                   : launch_k(occ1::k_rowphase<16, 4>, occ1::SMEM_BYTES, p, cs, nclusters, st);
-  return tm == 2 ? launch_k(occ1::k_rowphase<8, 2>, occ1::SMEM_BYTES, p, cs, nclusters, st)
-       : tm == 3 ? launch_k(occ1::k_rowphase<8, 3>, occ1::SMEM_BYTES, p, cs, nclusters, st)
-                 : launch_k(occ1::k_rowphase<8, 4>, occ1::SMEM_BYTES, p, cs, nclusters, st);
+    return tm == 2 ? launch_k(occ1::k_rowphase<16, 2>, occ1::SMEM_BYTES, p, E, cs, nclusters, st)
+         : tm == 3 ? launch_k(occ1::k_rowphase<16, 3>, occ1::SMEM_BYTES, p, E, cs, nclusters, st)
+                   : launch_k(occ1::k_rowphase<16, 4>, occ1::SMEM_BYTES, p, E, cs, nclusters, st);
+  return tm == 2 ? launch_k(occ1::k_rowphase<8, 2>, occ1::SMEM_BYTES, p, E, cs, nclusters, st)
+       : tm == 3 ? launch_k(occ1::k_rowphase<8, 3>, occ1::SMEM_BYTES, p, E, cs, nclusters, st)
+                 : launch_k(occ1::k_rowphase<8, 4>, occ1::SMEM_BYTES, p, E, cs, nclusters, st);
 }
 }  // namespace sc

@@ -29,10 +29,10 @@ int rowphase_capacity_occ2(int cs) {
 size_t rowphase_smem_occ2() { return occ2::SMEM_BYTES; }
 int rowphase_max_rows_occ2() { return occ2::MAXROWS; }
 int rowphase_panel_rows_occ2() { return occ2::PROW; }
-cudaError_t launch_rowphase_occ2(const RowPhaseParams& p, int cs, int nclusters, int tm, cudaStream_t st) {
-  if (cs == 16) return tm == 1 ? launch_k(occ2::k_rowphase<16, 1>, occ2::SMEM_BYTES, p, cs, nclusters, st)
-                               : launch_k(occ2::k_rowphase<16, 2>, occ2::SMEM_BYTES, p, cs, nclusters, st);
-  return tm == 1 ? launch_k(occ2::k_rowphase<8, 1>, occ2::SMEM_BYTES, p, cs, nclusters, st)
-                 : launch_k(occ2::k_rowphase<8, 2>, occ2::SMEM_BYTES, p, cs, nclusters, st);
+cudaError_t launch_rowphase_occ2(const RowPhaseParams* p, int E, int cs, int nclusters, int tm, cudaStream_t st) {
+  if (cs == 16) return tm == 1 ? launch_k(occ2::k_rowphase<16, 1>, occ2::SMEM_BYTES, p, E, cs, nclusters, st)
+                               : launch_k(occ2::k_rowphase<16, 2>, occ2::SMEM_BYTES, p, E, cs, nclusters, st);
+  return tm == 1 ? launch_k(occ2::k_rowphase<8, 1>, occ2::SMEM_BYTES, p, E, cs, nclusters, st)
+                 : launch_k(occ2::k_rowphase<8, 2>, occ2::SMEM_BYTES, p, E, cs, nclusters, st);
 }
 }  // namespace sc

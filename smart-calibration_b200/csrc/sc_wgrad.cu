@@ -100,7 +100,9 @@ __device__ __forceinline__ void stage_panel(float* sm, const float* src, int ld,
   }
 }
 
-__global__ void __launch_bounds__(SC_THREADS, 2) k_wgrad_adam(const __grid_constant__ WgradParams p) {
+__global__ void __launch_bounds__(SC_THREADS, 2) k_wgrad_adam(const WgradParams* __restrict__ pp) {
+  __shared__ WgradParams p_sm;
+  const WgradParams& p = load_params(pp, &p_sm);              // blockIdx.y = agent of the ensemble
   extern __shared__ __align__(16) float smem[];
   float* sD = smem;
   float* sX = sD + WG_SM_D;
@@ -254,14 +256,17 @@ __global__ void k_soft_update(const float* __restrict__ src, float* __restrict__
 
 size_t wgrad_smem_bytes() { return (size_t)WG_SM_FLOATS * sizeof(float); }
 
-cudaError_t launch_wgrad(const WgradParams& p, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+cudaError_t launch_wgrad(const WgradParams* pp, int E, int grid, cudaStream_t st) {
+  static bool configured[64];
+  int d = 0;
+  cudaGetDevice(&d);
+  d &= 63;
+  if (!configured[d]) {
     cudaError_t e = cudaFuncSetAttribute(k_wgrad_adam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem_bytes());
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[d] = true;
   }
-  k_wgrad_adam<<<grid, SC_THREADS, wgrad_smem_bytes(), st>>>(p);
+  k_wgrad_adam<<<dim3(grid, E), SC_THREADS, wgrad_smem_bytes(), st>>>(pp);
   return cudaGetLastError();
 }
 

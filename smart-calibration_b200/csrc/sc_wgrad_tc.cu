@@ -55,7 +55,9 @@ __device__ __forceinline__ void adam_math_tc(float g, float& m, float& v, float&
   p = __fadd_rn(p, __fdiv_rn(__fmul_rn(h.lr_neg_step, m), denom));
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constant__ WgradTcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const WgradTcParams* __restrict__ pp) {
+  __shared__ WgradTcParams p_sm;
+  const WgradTcParams& p = load_params(pp, &p_sm);            // blockIdx.y = agent of the ensemble
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_raw[TC_STAGES], full_lo[TC_STAGES], empty[TC_STAGES], acc_done;
@@ -261,18 +263,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const __grid_constan
 
 size_t wgrad_tc_smem_bytes() { return (size_t)TC_STAGES * TC_STAGE_BYTES + 1024; }
 
-cudaError_t launch_wgrad_tc(const WgradTcParams& p, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+cudaError_t launch_wgrad_tc(const WgradTcParams* pp, int E, int grid, cudaStream_t st) {
+  static bool configured[64];
+  int d = 0;
+  cudaGetDevice(&d);
+  d &= 63;
+  if (!configured[d]) {
     cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_tc_smem_bytes());
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[d] = true;
   }
   static int pdl = -1;
   if (pdl < 0) { const char* e = getenv("SMARTCAL_PDL_WGRAD"); pdl = (e && e[0] == '0') ? 0 : 1; }
   cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
   cudaLaunchAttribute attr[1];
-  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.gridDim = dim3(grid, E, 1);
   cfg.blockDim = dim3(TC_THREADS, 1, 1);
   cfg.dynamicSmemBytes = wgrad_tc_smem_bytes();
   cfg.stream = st;
@@ -280,7 +285,7 @@ cudaError_t launch_wgrad_tc(const WgradTcParams& p, int grid, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, k_wgrad_tc, p);
+  return cudaLaunchKernelEx(&cfg, k_wgrad_tc, pp);
 }
 
 }  // namespace sc

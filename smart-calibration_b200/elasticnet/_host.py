@@ -169,6 +169,14 @@ class NetView:
         return f"{type(self).__name__}(sm_100a HBM-resident, keys={len(self._keys)})"
 
 
+def plain_state(obj):
+    """attribute dict of an unpickled replay object (ours, the reference's, or already a dict) WITHOUT going through class
+    properties: a PER rebuilt by pickle has no device behind the DeviceReplayMixin properties"""
+    if isinstance(obj, dict):
+        return obj
+    return dict(getattr(obj, "__dict__", {}))
+
+
 # ---- replay facades ---------------------------------------------------------------------------------------
 _ARRAYS = ("state_memory", "new_state_memory", "action_memory", "reward_memory", "terminal_memory", "hint_memory")
 
@@ -179,7 +187,9 @@ class DeviceReplayMixin:
 
     @property
     def mem_cntr(self):
-        return self._dev.counters()[0]
+        if self.__dict__.get("_dev") is None:          # an instance rebuilt by pickle: plain attributes
+            return self.__dict__.get("mem_cntr", 0)
+        return self._dev.n_stored
 
     @mem_cntr.setter
     def mem_cntr(self, v):
@@ -187,6 +197,8 @@ class DeviceReplayMixin:
         self._dev.set_counters(int(v), l, d, b)
 
     def _arr(self, name):
+        if self.__dict__.get("_dev") is None:
+            return self.__dict__.get(name)
         v = self._dev.buffer(name)
         a = v.cpu().numpy()
         if name in ("reward_memory",):
@@ -203,8 +215,9 @@ class DeviceReplayMixin:
     terminal_memory = property(lambda self: self._arr("terminal_memory"))
 
     def _upload_arrays(self, src):
+        src = plain_state(src)
         for name in _ARRAYS:
-            a = np.asarray(getattr(src, name) if not isinstance(src, dict) else src[name])
+            a = np.asarray(src[name])
             v = self._dev.buffer(name)
             t = T.as_tensor(a.astype(np.uint8) if name == "terminal_memory" else a.astype(np.float32))
             v.copy_(t.reshape(v.shape[0], -1).to(v.device))

@@ -20,7 +20,6 @@ except ImportError:
     from enet_sac import ReplayBuffer as _SacReplayBuffer
 
 L = H.L
-mydevice = T.device('cuda') if T.cuda.is_available() else T.device('cpu')
 
 
 class OUActionNoise(object):
@@ -59,6 +58,8 @@ class ReplayBuffer(object):
         return s, a, r, s2, d.astype(np.float32)
 
     def __getattr__(self, name):        # mem_cntr, mem_size, *_memory, save/load_checkpoint, filename
+        if name == '_inner':            # (an object rebuilt by pickle has no _inner yet: do not recurse)
+            raise AttributeError(name)
         return getattr(self._inner, name)
 
 
@@ -126,11 +127,13 @@ class Agent():
 
     def learn(self, want_stats=False):
         dev = self._dev
-        if dev.counters()[0] < self.batch_size:
+        if dev.n_stored < self.batch_size:
+            dev.flush()
             return
+        kw = {}
         if self.rng == 'reference':
-            dev.set_batch(np.random.choice(min(dev.counters()[0], dev.C), self.batch_size, replace=False))
-        st = dev.learn(td3_noise=0.0, want_stats=want_stats)
+            kw = dict(batch_idx=np.random.choice(min(dev.n_stored, dev.C), self.batch_size, replace=False))
+        st = dev.learn(td3_noise=0.0, want_stats=want_stats, **kw)
         if st is not None:
             st = dict(st)
             st["critic_loss"] = st["critic_1_loss"] * self.batch_size       # sum of squares (enet_ddpg.py:281)

@@ -12,6 +12,7 @@ Deviations from the reference, all deliberate and documented in DESIGN.md:
   * extra keyword `rng=` ('reference' | 'device'), default from $SMARTCAL_RNG or 'reference' (host draws from
     numpy's / torch's global generators in the reference's order).
 """
+import copyreg
 import pickle
 
 import numpy as np
@@ -23,7 +24,6 @@ except ImportError:          # imported as a top-level module (directory placed 
     import _host as H
 
 L = H.L
-mydevice = T.device('cuda') if T.cuda.is_available() else T.device('cpu')
 
 
 def is_power_of_2(n):
@@ -81,33 +81,38 @@ class _DeviceReplayBuffer(H.DeviceReplayMixin, ReplayBuffer):
         self.filename = 'replaymem_sac.model'
 
     def store_transition(self, state, action, reward, state_, done, hint):
-        self._dev.store(self._dev.pack(H.flat_state(state), action, H._scalar(reward), H.flat_state(state_), bool(done), hint))
+        # deferred: fused into the next learn() (sc_agent_store_learn); anything that looks at the replay flushes it first
+        self._dev.store(self._dev.pack(H.flat_state(state), action, H._scalar(reward), H.flat_state(state_), bool(done), hint), defer=True)
 
     def store_transition_from_buffer(self, state, action, reward, state_, done, hint):
-        self._dev.store(self._dev.pack(state, action, H._scalar(reward), state_, bool(done), hint))
+        self._dev.store(self._dev.pack(state, action, H._scalar(reward), state_, bool(done), hint), defer=True)
 
     def sample_buffer(self, batch_size):
         pick = np.random.choice(min(self.mem_cntr, self.mem_size), batch_size, replace=False)
         return tuple(getattr(self, n)[pick] for n in ("state_memory", "action_memory", "reward_memory",
                                                       "new_state_memory", "terminal_memory", "hint_memory"))
 
-    def __reduce__(self):      # pickles as a plain host ReplayBuffer the reference can read
-        host = ReplayBuffer.__new__(ReplayBuffer)
-        host.__dict__.update(self._host_state())
-        return (_rebuild, (ReplayBuffer, host.__dict__))
+    def __reduce__(self):
+        # pickles as a plain host ReplayBuffer through the standard protocol (class name + __dict__ only), so the
+        # reference's enet_sac.ReplayBuffer.load_checkpoint reads the file as well
+        return (copyreg.__newobj__, (ReplayBuffer,), self._host_state())
 
     def load_checkpoint(self):
         with open(self.filename, 'rb') as f:
             other = pickle.load(f)
-        self._upload_arrays(other)
+        st = H.plain_state(other)
+        self._upload_arrays(st)
         m, l, d, b = self._dev.counters()
-        self._dev.set_counters(other.mem_cntr, l, other.mem_cntr % self.mem_size, b)
+        self._dev.set_counters(st["mem_cntr"], l, st["mem_cntr"] % self.mem_size, b)
 
 
-def _rebuild(cls, state):
-    obj = cls.__new__(cls)
-    obj.__dict__.update(state)
-    return obj
+class _HostSumTree(object):
+    """what a device SumTree pickles as: class SumTree with the reference's attribute set (tree, capacity, data_pointer,
+    data_length) in its __dict__ -- readable by the reference's enet_sac.SumTree and by SumTree below (plain attributes win
+    over the device properties when no device is attached)"""
+
+    def __reduce__(self):
+        return (copyreg.__newobj__, (SumTree,), dict(self.__dict__))
 
 
 class SumTree():
@@ -119,9 +124,16 @@ class SumTree():
         self._dev = _dev
         self._host = None if _dev is not None else np.zeros(2 * self.capacity - 1)
 
+    def _plain(self, name):
+        """attribute of an instance rebuilt by pickle (no device behind it)"""
+        d = self.__dict__
+        return d.get(name) if d.get("_dev") is None and name in d else None
+
     @property
     def tree(self):
-        return self._host if self._dev is None else self._dev.buffer("tree")[:, 0].cpu().numpy()
+        if self.__dict__.get("_dev") is None:
+            return self.__dict__.get("_host") if self.__dict__.get("_host") is not None else self.__dict__.get("tree")
+        return self._dev.buffer("tree")[:, 0].cpu().numpy()
 
     @tree.setter
     def tree(self, values):
@@ -133,11 +145,11 @@ class SumTree():
 
     @property
     def data_pointer(self):
-        return self._dev.counters()[2]
+        return self._plain("data_pointer") if self.__dict__.get("_dev") is None else self._dev.counters()[2]
 
     @property
     def data_length(self):
-        return min(self._dev.counters()[0], self.capacity)
+        return self._plain("data_length") if self.__dict__.get("_dev") is None else min(self._dev.counters()[0], self.capacity)
 
     def __len__(self):
         return self.data_length
@@ -176,7 +188,9 @@ class PER(H.DeviceReplayMixin):
 
     @property
     def beta(self):
-        return self._dev.counters()[3] if self._dev is not None else 0.4
+        if self.__dict__.get("_dev") is None:
+            return self.__dict__.get("beta", 0.4)
+        return self._dev.counters()[3]
 
     def __len__(self):
         return len(self.tree)
@@ -191,10 +205,10 @@ class PER(H.DeviceReplayMixin):
             return
         packed = dev.pack(s, a, H._scalar(r), s2, bool(done), hint)
         if error is None:
-            dev.store(packed, 1, 0.0)
+            dev.store(packed, 1, 0.0, defer=True)
         else:
             p = min((abs(error) + self.epsilon) ** self.alpha, self.absolute_error_upper)   # enet_sac.py:242, same objects
-            dev.store(packed, 3 if isinstance(error, T.Tensor) else 2, H._scalar(p))
+            dev.store(packed, 3 if isinstance(error, T.Tensor) else 2, H._scalar(p), defer=True)
 
     def store_transition(self, state, action, reward, state_, done, hint, error=None):
         self._store(H.flat_state(state), action, reward, H.flat_state(state_), done, hint, error)
@@ -222,24 +236,32 @@ class PER(H.DeviceReplayMixin):
         return T.sum(weighted_squared_error) / T.numel(weighted_squared_error)
 
     def __reduce__(self):
+        # class PER / SumTree with the reference's attribute names in their __dict__ (arrays, counters, tree / capacity /
+        # data_pointer / data_length): the reference's PER.load_checkpoint reads the file, and so does ours -- the loaders
+        # below only look at __dict__, never at the device-backed properties
         st = self._host_state()
-        tree = SumTree.__new__(SumTree)
-        tree.__dict__.update(capacity=self.tree.capacity, _dev=None, _host=self.tree.tree.copy())
+        tree = _HostSumTree()
+        tree.__dict__.update(capacity=self.tree.capacity, tree=self.tree.tree.copy(), data_pointer=int(self.tree.data_pointer),
+                             data_length=int(self.tree.data_length))
         st["tree"] = tree
-        st["_dev"] = None
-        return (_rebuild, (PER, st))
+        st["beta"] = float(self.beta)
+        return (copyreg.__newobj__, (PER,), st)
 
     def save_checkpoint(self):
         with open(self.filename, 'wb') as f:
             pickle.dump(self, f)
 
     def load_checkpoint(self):
+        """reads files written by this class AND by the reference's PER.save_checkpoint (a pickled reference PER whose
+        SumTree carries a raw `tree` ndarray)"""
         with open(self.filename, 'rb') as f:
             other = pickle.load(f)
-        self._upload_arrays(other if not isinstance(other, dict) else other)
-        self.tree.tree = other.tree.tree
+        st = H.plain_state(other)
+        self._upload_arrays(st)
+        tree = H.plain_state(st["tree"])
+        self.tree.tree = np.asarray(tree["tree"] if "tree" in tree else tree["_host"], np.float64)
         m, l, d, b = self._dev.counters()
-        self._dev.set_counters(other.mem_cntr, l, getattr(other.tree, "data_pointer", other.mem_cntr % self.mem_size), b)
+        self._dev.set_counters(st["mem_cntr"], l, int(tree.get("data_pointer", st["mem_cntr"] % self.mem_size)), float(st.get("beta", b)))
 
 
 class CriticNetwork(H.NetView):
@@ -298,25 +320,41 @@ class Agent():
         H.critic_initial_state(S, n_actions)      # the reference draws (then overwrites) the target inits too
         self.target_critic_2 = CriticNetwork(lr_c, input_dims, n_actions, name_prefix + 'q_target_2', _dev=dev, _net=L.NET_TARGET_CRITIC_2)
         H.critic_initial_state(S, n_actions)
-        self.alpha = T.tensor(alpha, requires_grad=False, device=dev.device)
+        self._alpha, self._admm_rho = float(alpha), 0.01
         self.scale = reward_scale
         self.learn_alpha = False
         if self.use_hint:
-            self.hint_threshold, self.admm_rho = 0.1, 0.01
+            self.hint_threshold = 0.1
         self.update_network_parameters(tau=1.)
         self.last_stats = None
 
-    # hint multiplier lives on the device; expose it like the reference's tensor attribute
+    # scalars the kernels read live in the library: assignments (agent.alpha = ..., agent.admm_rho = ...) reach the device
+    @property
+    def alpha(self):
+        return T.tensor(self._alpha, device=self._dev.device)
+
+    @alpha.setter
+    def alpha(self, v):
+        self._alpha = float(v)
+        self._dev.set_scalars(self._alpha, float(self.rho), self._admm_rho)
+
+    @property
+    def admm_rho(self):
+        return self._admm_rho
+
+    @admm_rho.setter
+    def admm_rho(self, v):
+        self._admm_rho = float(v)
+        self._dev.set_scalars(self._alpha, float(self.rho), self._admm_rho)
+
     @property
     def rho(self):
-        return T.tensor(self._dev.learn(want_stats=True)["rho"]) if False else T.tensor(self._rho_host())
-
-    def _rho_host(self):
-        return float(self.last_stats["rho"]) if self.last_stats else 0.0
+        """hint multiplier (enet_sac.py:515); it evolves on the device -- read from there"""
+        return T.tensor(self._dev.rho())
 
     @property
     def learn_counter(self):
-        return self._dev.counters()[1]
+        return self._dev.n_learned
 
     def update_network_parameters(self, tau=None):
         self._dev.soft_update(self.tau if tau is None else tau)
@@ -332,23 +370,28 @@ class Agent():
 
     def learn(self, want_stats=False):
         dev = self._dev
-        if dev.counters()[0] < self.batch_size:
+        if dev.n_stored < self.batch_size:
+            dev.flush()
             return
         B, A = self.batch_size, self.n_actions
+        # the reference prints `learn_counter rho` every 100th call when hints are on (enet_sac.py:619-620): only then is a
+        # read-back (and its synchronisation) needed
+        report = self.use_hint and dev.n_learned % 100 == 0
         if self.rng == 'reference':
-            # draws in the reference's order: numpy batch first, then torch noise (enet_sac.py:48/294, :570, :589, :611)
+            # draws in the reference's order: numpy batch first, then torch noise (enet_sac.py:48/294, :570, :589, :611); the
+            # arrays (and a deferred store_transition) travel to the device in the step's one host->device copy
             if self.prioritized:
-                dev.per_sample(np.random.random_sample(B))
+                kw = dict(per_u01=np.random.random_sample(B))
             else:
-                dev.set_batch(np.random.choice(min(dev.counters()[0], dev.C), B, replace=False))
+                kw = dict(batch_idx=np.random.choice(min(dev.n_stored, dev.C), B, replace=False))
             e1, e2 = T.randn(B, A).numpy(), T.randn(B, A).numpy()
-            e3 = T.randn(B, A).numpy() if (self.use_hint and self.learn_counter % 10 == 0) else None
-            st = dev.learn(e1, e2, e3, want_stats=want_stats or self.use_hint)
+            e3 = T.randn(B, A).numpy() if (self.use_hint and dev.n_learned % 10 == 0) else None
+            st = dev.learn(e1, e2, e3, want_stats=want_stats or report, **kw)
         else:
-            st = dev.learn(want_stats=want_stats)
+            st = dev.learn(want_stats=want_stats or report)
         if st is not None:
             self.last_stats = st
-            if self.use_hint and (st["learn_counter"] - 1) % 100 == 0:
+            if report:
                 print(f'{st["learn_counter"] - 1} {st["rho"]}')
         return st if want_stats else None
 

@@ -18,7 +18,6 @@ except ImportError:
     from enet_sac import ReplayBuffer, PER
 
 L = H.L
-mydevice = T.device('cuda') if T.cuda.is_available() else T.device('cpu')
 
 
 class CriticNetwork(H.NetView):
@@ -72,10 +71,11 @@ class Agent():
         self.update_network_parameters(tau=1.)
         self.last_stats = None
         self._admm_rho_sent = self.admm_rho
+        self._dev_rng = np.random.default_rng(int(T.initial_seed()) & 0xffffffff)
 
     @property
     def learn_step_cntr(self):
-        return self._dev.counters()[1]
+        return self._dev.n_learned
 
     def update_network_parameters(self, tau=None):
         self._dev.soft_update(self.tau if tau is None else tau)
@@ -102,19 +102,23 @@ class Agent():
 
     def learn(self, want_stats=False):
         dev = self._dev
-        if dev.counters()[0] < self.batch_size:
+        if dev.n_stored < self.batch_size:
+            dev.flush()
             return
         if self.use_hint and self.admm_rho != self._admm_rho_sent:     # callers set agent.admm_rho after construction (main_td3.py:22)
             dev.set_scalars(0.0, 0.0, self.admm_rho)
             self._admm_rho_sent = self.admm_rho
         if self.rng == 'reference':
+            # reference draw order (enet_td3.py:232/294 then :249); the arrays ride in the step's one host->device copy
             if self.prioritized:
-                dev.per_sample(np.random.random_sample(self.batch_size))
+                kw = dict(per_u01=np.random.random_sample(self.batch_size))
             else:
-                dev.set_batch(np.random.choice(min(dev.counters()[0], dev.C), self.batch_size, replace=False))
-            st = dev.learn(td3_noise=np.random.normal(scale=0.2), want_stats=want_stats)
+                kw = dict(batch_idx=np.random.choice(min(dev.n_stored, dev.C), self.batch_size, replace=False))
+            st = dev.learn(td3_noise=np.random.normal(scale=0.2), want_stats=want_stats, **kw)
         else:
-            st = dev.learn(td3_noise=float(np.random.normal(scale=0.2)), want_stats=want_stats)
+            # rng='device': minibatch on the device (Philox); the ONE scalar of target-smoothing noise per step
+            # (enet_td3.py:248-249) comes from the agent's own seeded generator, not from numpy's global stream
+            st = dev.learn(td3_noise=float(self._dev_rng.normal(scale=0.2)), want_stats=want_stats)
         if st is not None:
             self.last_stats = st
         return st if want_stats else None

@@ -28,12 +28,12 @@ def test_library_exports_every_declared_symbol():
 
 def test_config_struct_layout_and_arena_size():
     lib = L.load()
-    cfg = L.ScConfig(abi_version=1, kind=0, state_dim=420, n_actions=2, batch_size=256, mem_size=4096, prioritized=1,
+    cfg = L.ScConfig(abi_version=L.SC_ABI_VERSION, kind=0, state_dim=420, n_actions=2, batch_size=256, mem_size=4096, prioritized=1,
                      gamma=0.99, tau=0.005, lr_actor=1e-3, lr_critic=1e-3, reward_scale=20, alpha=0.03, max_action=1, per_clip=100)
     n = lib.sc_agent_arena_bytes(C.byref(cfg))
     # nets+Adam+targets 16.0 MB, replay 14.0 MB, workspace ~15 MB
     assert 30e6 < n < 80e6
-    bad = L.ScConfig(abi_version=1, kind=0, state_dim=420, n_actions=2, batch_size=256, mem_size=1000, prioritized=1)
+    bad = L.ScConfig(abi_version=L.SC_ABI_VERSION, kind=0, state_dim=420, n_actions=2, batch_size=256, mem_size=1000, prioritized=1)
     assert lib.sc_agent_arena_bytes(C.byref(bad)) == 0
     assert b"power of 2" in lib.sc_last_error()       # same message as the reference assert (enet_sac.py:99)
 
@@ -44,7 +44,7 @@ def test_no_cpu_fallback():
     with pytest.raises(L.SmartcalError, match="no CPU fallback"):
         enet_sac.Agent(gamma=0.99, lr_a=1e-3, lr_c=1e-3, input_dims=[24], batch_size=8, n_actions=2)
     lib = L.load()
-    cfg = L.ScConfig(abi_version=1, kind=0, state_dim=24, n_actions=2, batch_size=8, mem_size=16)
+    cfg = L.ScConfig(abi_version=L.SC_ABI_VERSION, kind=0, state_dim=24, n_actions=2, batch_size=8, mem_size=16)
     h = C.c_void_p()
     assert lib.sc_agent_create(C.byref(cfg), None, 0, None, C.byref(h)) == 2      # SC_ERR_CUDA
     assert b"no CPU fallback" in lib.sc_last_error()
