@@ -196,9 +196,13 @@ struct sc_group {
   cudaStream_t st = nullptr;                  // agent 0's stream: eager launches, tape copies and graph launches go here
   cudaStream_t st_side = nullptr, st_side2 = nullptr, st_cap = nullptr;   // library-owned (st may be the legacy default stream, which cannot be captured)
   cudaEvent_t ev_fork[3] = {nullptr, nullptr, nullptr}, ev_join[3] = {nullptr, nullptr, nullptr};
-  char* tape_dev = nullptr;
+  // the tape is double-buffered on both sides and uploaded on its own copy stream: the copy for step n+1 runs while the kernels
+  // of step n execute (no copy bubble between steps); buffer k is reused once the step that read it two steps ago is done
+  char* tape_dev[2] = {nullptr, nullptr};
   char* tape_host[2] = {nullptr, nullptr};
-  cudaEvent_t ev_up[2] = {nullptr, nullptr};
+  cudaEvent_t ev_up[2] = {nullptr, nullptr};    // upload of buffer k complete
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};  // kernels of the step that read buffer k complete
+  cudaStream_t st_copy = nullptr;
   int tk = 0;
   size_t tape_cap = 0, used = 0;
   float *stats_dev = nullptr, *h_stats = nullptr;          // [E][32]
@@ -213,7 +217,7 @@ extern "C" {
 static int group_init(sc_group* g, sc_agent** agents, int n);
 static void group_free(sc_group* g);
 }
-constexpr size_t IMM_SLOT = 8192;
+constexpr size_t IMM_SLOT = 80 * 1024;   // parameters + B float64 uniforms (B <= 8192)
 
 struct sc_agent {
   sc_config cfg;
@@ -1286,7 +1290,7 @@ static void* emit_data(sc_agent* a, size_t bytes, const void** dev) {
   if (i < 0) return nullptr;
   sc_group* g = a->grp;
   const size_t off = g->recs[i].off + (size_t)a->gidx * b;
-  *dev = g->tape_dev + off;
+  *dev = g->tape_dev[g->tk] + off;
   return g->tape_host[g->tk] + off;
 }
 static int emit_ctl(sc_agent* a, int type, int which) {
@@ -1644,7 +1648,7 @@ static int plan_step(sc_agent* a, const StepArgs& sa, StepOut& so) {
       *pu = per_update_params(a, nullptr, a->ps_out);
       if ((rc = emit_ctl(a, REC_TEND, 5))) return rc;
     } else {
-      static const bool no_presample = getenv("SMARTCAL_NO_PRESAMPLE") != nullptr;
+      const bool no_presample = getenv("SMARTCAL_NO_PRESAMPLE") != nullptr;    // (read per step: tests toggle it)
       if ((rc = emit_ctl(a, REC_FORK, 1))) return rc;
       PerUpdateP* pu = emit_kernel<PerUpdateP>(a, KID_PER_UPDATE, 1, a->B);
       PL(pu);
@@ -1732,13 +1736,14 @@ static void group_free(sc_group* g) {
   if (g->st) cudaStreamSynchronize(g->st);
   for (auto& kv : g->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   g->graphs.clear();
-  for (cudaStream_t* s : {&g->st_side, &g->st_side2, &g->st_cap})
+  for (cudaStream_t* s : {&g->st_side, &g->st_side2, &g->st_cap, &g->st_copy})
     if (*s) { cudaStreamSynchronize(*s); cudaStreamDestroy(*s); *s = nullptr; }
   for (auto& e : g->ev_fork) if (e) { cudaEventDestroy(e); e = nullptr; }
   for (auto& e : g->ev_join) if (e) { cudaEventDestroy(e); e = nullptr; }
   for (auto& e : g->ev_up) if (e) { cudaEventDestroy(e); e = nullptr; }
+  for (auto& e : g->ev_done) if (e) { cudaEventDestroy(e); e = nullptr; }
   for (auto& h : g->tape_host) if (h) { cudaFreeHost(h); h = nullptr; }
-  if (g->tape_dev) { cudaFree(g->tape_dev); g->tape_dev = nullptr; }
+  for (auto& d : g->tape_dev) if (d) { cudaFree(d); d = nullptr; }
   if (g->stats_dev) { cudaFree(g->stats_dev); g->stats_dev = nullptr; }
   if (g->h_stats) { cudaFreeHost(g->h_stats); g->h_stats = nullptr; }
 }
@@ -1751,16 +1756,18 @@ static int group_init(sc_group* g, sc_agent** agents, int n) {
   CK(cudaStreamCreateWithFlags(&g->st_side, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&g->st_side2, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&g->st_cap, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&g->st_copy, cudaStreamNonBlocking));
   for (auto& e : g->ev_fork) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : g->ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : g->ev_up) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : g->ev_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   // per agent and step: <= 2 + 7 row-phase blocks, 4 + 14 dense blocks, 12 weight-gradient blocks, the small kernels, and
   // the host arrays (3 noise tensors, B uniforms or indices, one transition)
   const sc_agent* a = agents[0];
   const size_t per_agent = 9 * sizeof(RowPhaseParams) + 18 * sizeof(DenseTcParams) + 12 * (sizeof(WgradParams) + sizeof(WgradTcParams)) + 8192 +
                            (size_t)3 * a->B * a->A * sizeof(float) + (size_t)a->B * sizeof(double) + (size_t)a->T * sizeof(float) + 64 * 256;
   g->tape_cap = ((per_agent * (size_t)n) + 4095) & ~(size_t)4095;
-  CK(cudaMalloc((void**)&g->tape_dev, g->tape_cap));
+  for (auto& d : g->tape_dev) CK(cudaMalloc((void**)&d, g->tape_cap));
   for (auto& h : g->tape_host) CK(cudaHostAlloc((void**)&h, g->tape_cap, cudaHostAllocDefault));
   CK(cudaMalloc((void**)&g->stats_dev, (size_t)n * 32 * sizeof(float)));
   CK(cudaMemset(g->stats_dev, 0, (size_t)n * 32 * sizeof(float)));
@@ -1784,7 +1791,7 @@ static cudaError_t issue_recs(sc_group* g, cudaStream_t st0) {
   cudaError_t e = cudaSuccess;
   for (const Rec& r : g->recs) {
     cudaStream_t st = sts[r.stream];
-    const char* pp = g->tape_dev + r.off;
+    const char* pp = g->tape_dev[g->tk] + r.off;
     switch (r.type) {
       case REC_DATA: break;
       case REC_FORK:
@@ -1816,10 +1823,11 @@ static cudaError_t issue_recs(sc_group* g, cudaStream_t st0) {
   }
   return cudaSuccess;
 }
+static int group_issue(sc_group* g);
 static uint64_t plan_key(const sc_group* g) {
   uint64_t h = 1469598103934665603ull;
   auto mix = [&](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
-  mix((uint64_t)g->E);
+  mix((uint64_t)g->E | ((uint64_t)g->tk << 32));               // (the kernels of a graph read one particular device tape buffer)
   for (const Rec& r : g->recs) {
     mix((uint64_t)r.type | ((uint64_t)r.kid << 8) | ((uint64_t)r.stream << 16));
     for (int i = 0; i < 5; ++i) mix((uint64_t)(uint32_t)r.g[i]);
@@ -1834,9 +1842,19 @@ static int group_run(sc_group* g) {
   for (int i = 0; i < g->E; ++i)
     if (g->ag[i]->cursor != g->recs.size()) return plan_fail(g, "missing records");
   if (g->recs.empty()) return SC_OK;
-  CK(cudaMemcpyAsync(g->tape_dev, g->tape_host[g->tk], g->used, cudaMemcpyHostToDevice, g->st));
-  CK(cudaEventRecord(g->ev_up[g->tk], g->st));
+  // upload on the copy stream as soon as the step that read this device buffer last (two steps ago) has finished; the
+  // agents' stream only waits for the copy, which normally completed while the previous step was still running
+  const int k = g->tk;
+  CK(cudaStreamWaitEvent(g->st_copy, g->ev_done[k], 0));
+  CK(cudaMemcpyAsync(g->tape_dev[k], g->tape_host[k], g->used, cudaMemcpyHostToDevice, g->st_copy));
+  CK(cudaEventRecord(g->ev_up[k], g->st_copy));
+  CK(cudaStreamWaitEvent(g->st, g->ev_up[k], 0));
+  int rc = group_issue(g);
+  CK(cudaEventRecord(g->ev_done[k], g->st));
   g->tk ^= 1;
+  return rc;
+}
+static int group_issue(sc_group* g) {
   bool timing = false;
   for (const Rec& r : g->recs) timing = timing || r.type == REC_TBEGIN;
   if (g->use_graph && !timing) {

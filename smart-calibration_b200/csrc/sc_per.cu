@@ -357,9 +357,13 @@ __global__ void k_hint_coef(const HintCoefP* __restrict__ pp) {
     out[0] = (admm_rho * g + *rho) * 2.f * ex * 2.f / (float)(B * A);
     out[1] = g;
     out[2] = 0.5f * admm_rho * g * g + *rho * g;                               // penalty added to actor_loss (enet_sac.py:602)
-    if (rho_update != nullptr) *rho_update = *rho_update + admm_rho * g;       // rho += admm_rho*gfun (enet_sac.py:617)
+    float rho_now = *rho;
+    if (rho_update != nullptr) {                                               // rho += admm_rho*gfun (enet_sac.py:617)
+      rho_now = *rho_update + admm_rho * g;
+      *rho_update = rho_now;
+    }
     if (P.stats_g != nullptr) { P.stats_g[0] = g; P.stats_g[1] = out[2]; }
-    if (P.stats_rho != nullptr) *P.stats_rho = *rho;                           // (rho_update aliases rho: the value after the update)
+    if (P.stats_rho != nullptr) *P.stats_rho = rho_now;                        // the multiplier after the (optional) dual update
   }
 }
 
@@ -413,12 +417,16 @@ __global__ void k_admm_update(const AdmmP* __restrict__ pp) {
   if (tid == 0) {
     float s11 = 0.f, s12 = 0.f, s22 = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { s11 += sred[0][w]; s12 += sred[1][w]; s22 += sred[2][w]; }
+    float rho_now = r;
     if (s11 > 0.f && s12 > 0.f && s22 > 0.f) {
       const float alpha = s12 / sqrtf(s11 * s22), a_sd = s11 / s12, a_mg = s12 / s22;
       const float a_hat = 2.f * a_mg > a_sd ? a_mg : a_sd - 0.5f * a_mg;
-      if (alpha > corr_min && a_hat < 10.f * rho0 && a_hat > 0.1f * rho0) *rho = a_hat;
+      if (alpha > corr_min && a_hat < 10.f * rho0 && a_hat > 0.1f * rho0) {
+        rho_now = a_hat;
+        *rho = a_hat;
+      }
     }
-    if (P.stats_rho != nullptr) *P.stats_rho = *rho;
+    if (P.stats_rho != nullptr) *P.stats_rho = rho_now;
   }
 }
 

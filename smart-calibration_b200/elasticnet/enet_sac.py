@@ -95,7 +95,7 @@ class _DeviceReplayBuffer(H.DeviceReplayMixin, ReplayBuffer):
     def __reduce__(self):
         # pickles as a plain host ReplayBuffer through the standard protocol (class name + __dict__ only), so the
         # reference's enet_sac.ReplayBuffer.load_checkpoint reads the file as well
-        return (copyreg.__newobj__, (ReplayBuffer,), self._host_state())
+        return (copyreg._reconstructor, (ReplayBuffer, object, None), self._host_state())
 
     def load_checkpoint(self):
         with open(self.filename, 'rb') as f:
@@ -112,7 +112,7 @@ class _HostSumTree(object):
     over the device properties when no device is attached)"""
 
     def __reduce__(self):
-        return (copyreg.__newobj__, (SumTree,), dict(self.__dict__))
+        return (copyreg._reconstructor, (SumTree, object, None), dict(self.__dict__))
 
 
 class SumTree():
@@ -245,7 +245,7 @@ class PER(H.DeviceReplayMixin):
                              data_length=int(self.tree.data_length))
         st["tree"] = tree
         st["beta"] = float(self.beta)
-        return (copyreg.__newobj__, (PER,), st)
+        return (copyreg._reconstructor, (PER, object, None), st)
 
     def save_checkpoint(self):
         with open(self.filename, 'wb') as f:
