@@ -21,6 +21,7 @@ int rowphase_panel_rows(int variant);
 void rowphase_cluster_capacity(int* out4);
 // every kernel of a learn() step takes a device array of E parameter blocks (blockIdx.y = agent of the ensemble)
 cudaError_t launch_rowphase(const RowPhaseParams* pp, int E, int variant, int cluster_size, int nclusters, int tm, cudaStream_t st);
+cudaError_t launch_tail(const RowPhaseParams* pp, int E, int B, cudaStream_t st);
 size_t wgrad_smem_bytes();
 cudaError_t launch_wgrad(const WgradParams* pp, int E, int grid, cudaStream_t st);
 cudaError_t launch_wgrad_tc(const WgradTcParams* pp, int E, int grid, cudaStream_t st);
@@ -182,7 +183,7 @@ struct KernelTimer {
 // one host->device copy of the tape plus the launches, each kernel reading its parameters from the device copy
 // (blockIdx.y = agent).  Identical plans (same records, same tape offsets) are replayed as a CUDA graph.
 enum { KID_STORE = 0, KID_PER_SAMPLE, KID_UNIFORM, KID_GATHER, KID_DENSE, KID_ROW, KID_PER_UPDATE, KID_WGRAD, KID_WGRAD_TC, KID_HINT,
-       KID_ADMM };
+       KID_ADMM, KID_TAIL };
 enum { REC_KERNEL = 0, REC_DATA, REC_FORK, REC_JOIN_RECORD, REC_JOIN_WAIT, REC_TBEGIN, REC_TEND };
 struct Rec {
   int type, kid, stream;           // stream: 0 main, 1 side (PER), 2 side2 (narrow weight gradients)
@@ -1381,6 +1382,14 @@ static int plan_rowphase(sc_agent* a, const RowPhaseParams& p_in, int timer_id) 
     if ((rc = plan_dense_tc(a, p))) return rc;
     if (dense_timer >= 0 && a->timing && (rc = emit_ctl(a, REC_TEND, dense_timer))) return rc;
     p.skip_dense = 1;
+    // the row-local tail as its own launch (sc_tail.cu; SMARTCAL_TAIL=row keeps it inside k_rowphase for A/B runs)
+    static const bool tail_row = getenv("SMARTCAL_TAIL") != nullptr && !strcmp(getenv("SMARTCAL_TAIL"), "row");
+    if (!tail_row) {
+      RowPhaseParams* tt = emit_kernel<RowPhaseParams>(a, KID_TAIL, 0, a->B);
+      PL(tt);
+      *tt = p;
+      p.skip_tail = 1;
+    }
   }
   RowPhaseParams* t = emit_kernel<RowPhaseParams>(a, KID_ROW, 0, a->row_variant, a->cluster_size, a->nclusters, a->tile_tm);
   PL(t);
@@ -1764,7 +1773,7 @@ static int group_init(sc_group* g, sc_agent** agents, int n) {
   // per agent and step: <= 2 + 7 row-phase blocks, 4 + 14 dense blocks, 12 weight-gradient blocks, the small kernels, and
   // the host arrays (3 noise tensors, B uniforms or indices, one transition)
   const sc_agent* a = agents[0];
-  const size_t per_agent = 9 * sizeof(RowPhaseParams) + 18 * sizeof(DenseTcParams) + 12 * (sizeof(WgradParams) + sizeof(WgradTcParams)) + 8192 +
+  const size_t per_agent = 18 * sizeof(RowPhaseParams) + 18 * sizeof(DenseTcParams) + 12 * (sizeof(WgradParams) + sizeof(WgradTcParams)) + 8192 +
                            (size_t)3 * a->B * a->A * sizeof(float) + (size_t)a->B * sizeof(double) + (size_t)a->T * sizeof(float) + 64 * 256;
   g->tape_cap = ((per_agent * (size_t)n) + 4095) & ~(size_t)4095;
   for (auto& d : g->tape_dev) CK(cudaMalloc((void**)&d, g->tape_cap));
@@ -1815,6 +1824,7 @@ static cudaError_t issue_recs(sc_group* g, cudaStream_t st0) {
           case KID_WGRAD_TC: e = launch_wgrad_tc(reinterpret_cast<const WgradTcParams*>(pp), g->E, r.g[0], st); break;
           case KID_HINT: e = launch_hint_coef(reinterpret_cast<const HintCoefP*>(pp), g->E, st); break;
           case KID_ADMM: e = launch_admm_update(reinterpret_cast<const AdmmP*>(pp), g->E, st); break;
+          case KID_TAIL: e = launch_tail(reinterpret_cast<const RowPhaseParams*>(pp), g->E, r.g[0], st); break;
           default: e = cudaErrorInvalidValue;
         }
         break;

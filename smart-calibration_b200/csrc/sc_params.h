@@ -69,6 +69,7 @@ struct RowPhaseParams {
   // same values k_fill_normal would have written) and stored to eps_store for inspection
   int eps_inline; unsigned long long eps_seed, eps_stream; float* eps_store;
   int skip_dense;                            // 1: gather + both dense stages already ran as k_dense_tc launches (sc_dense_tc.cu)
+  int skip_tail;                             // 1: the row-local tail already ran as a k_tail launch (sc_tail.cu): only the wide dgrad stage is left
   float closs_scale;                         // critic-loss gradient scale: 1 (mean of squares), B (DDPG's sum of squares)
   int B, S, Sp, A, Ap;
   ActorP actor;                              // actor evaluated in this phase

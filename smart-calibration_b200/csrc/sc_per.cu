@@ -107,7 +107,7 @@ __global__ void k_tree_build(double* tree, int C, const double* __restrict__ pr,
 // ---------------------------------------------------------------------------------------------------
 // stratified proportional sampling (PER.sample_buffer, enet_sac.py:270-312).  One block.
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_per_sample(const PerSampleP* __restrict__ pp) {
+__global__ void __launch_bounds__(1024) k_per_sample(const PerSampleP* __restrict__ pp) {
   const PerSampleP P = pp[blockIdx.y];
   const double* __restrict__ tree = P.tree;
   const int C = P.C, B = P.B;
@@ -181,7 +181,7 @@ __global__ void k_per_sample(const PerSampleP* __restrict__ pp) {
 // priority refresh (PER.batch_update, enet_sac.py:314-323).  One block; dynamic smem: B doubles x2 + B ints.
 // ---------------------------------------------------------------------------------------------------
 // ps_in != nullptr: the float32 priorities were already evaluated by the critic row-phase kernel (err is ignored)
-__global__ void k_per_update(const PerUpdateP* __restrict__ pp) {
+__global__ void __launch_bounds__(1024) k_per_update(const PerUpdateP* __restrict__ pp) {
   const PerUpdateP P = pp[blockIdx.y];
   double* tree = P.tree;
   const int C = P.C, B = P.B;
@@ -267,7 +267,7 @@ __global__ void k_per_update(const PerUpdateP* __restrict__ pp) {
 // (n <= 8192: bitonic sort in shared memory; larger: Floyd's algorithm by one thread).  Replaces
 // np.random.choice(max_mem, B, replace=False) (enet_sac.py:48) when the caller does not inject indices.
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_sample_uniform(const UniformP* __restrict__ pp) {
+__global__ void __launch_bounds__(1024) k_sample_uniform(const UniformP* __restrict__ pp) {
   const UniformP P = pp[blockIdx.y];
   const int n = P.n, B = P.B;
   const uint64_t seed = P.seed, ctr = P.ctr;

@@ -1143,7 +1143,7 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
     }
     stamp(2);
     // stage 3: row-local tail
-    if (consumer)
+    if (consumer && !p.skip_tail)
       for (int gr = rank; gr < nrows; gr += CS * RT) {
         RowSet rs;
 #pragma unroll
@@ -1188,7 +1188,7 @@ __global__ void __launch_bounds__(SC_ROW_THREADS, SC_CFG_MINBLOCKS) k_rowphase(c
     dense_stage<CS, TM>(dops, 1 + p.n_q, p.B, row0, nrows, p.bidx, p.part, smem, pipe, g);
     }
     astamp(2);
-    if (consumer)
+    if (consumer && !p.skip_tail)
       for (int gr = rank; gr < nrows; gr += CS * RT) {
         RowSet rs;
 #pragma unroll
