@@ -27,6 +27,8 @@ cudaError_t launch_wgrad(const WgradParams* pp, int E, int grid, cudaStream_t st
 cudaError_t launch_wgrad_tc(const WgradTcParams* pp, int E, int grid, cudaStream_t st);
 cudaError_t launch_dense_tc(const DenseTcParams* pp, int E, int nops, int nrb, int N, int ks, cudaStream_t st);
 int dense_tc_max_clusters(int cs);
+int dgrad_tc_max_clusters(int cs);
+cudaError_t launch_dgrad_tc(const DenseTcParams* pp, int E, int nops, int nrb, int N, int ks, cudaStream_t st);
 cudaError_t launch_gather_mb(const GatherP* pp, int E, int B, cudaStream_t st);
 cudaError_t launch_soft_update(const float* src, float* dst, size_t n, float tau, cudaStream_t st);
 cudaError_t launch_replay_store(const ReplayP& rp, const float* tr, int slot, int mode, double priority, double clip, cudaStream_t st);
@@ -183,7 +185,7 @@ struct KernelTimer {
 // one host->device copy of the tape plus the launches, each kernel reading its parameters from the device copy
 // (blockIdx.y = agent).  Identical plans (same records, same tape offsets) are replayed as a CUDA graph.
 enum { KID_STORE = 0, KID_PER_SAMPLE, KID_UNIFORM, KID_GATHER, KID_DENSE, KID_ROW, KID_PER_UPDATE, KID_WGRAD, KID_WGRAD_TC, KID_HINT,
-       KID_ADMM, KID_TAIL };
+       KID_ADMM, KID_TAIL, KID_DGRAD };
 enum { REC_KERNEL = 0, REC_DATA, REC_FORK, REC_JOIN_RECORD, REC_JOIN_WAIT, REC_TBEGIN, REC_TEND };
 struct Rec {
   int type, kid, stream;           // stream: 0 main, 1 side (PER), 2 side2 (narrow weight gradients)
@@ -247,6 +249,9 @@ struct sc_agent {
   unsigned char* tmaps;               // device table of CUtensorMap (128 B each)
   TensorMaps tm_critic, tm_actor, tm_act;   // per-program map pointer sets
   TensorMaps tmd_critic, tmd_actor;         // the same matrices with 128-row boxes for the tcgen05 dense stages (sc_dense_tc.cu)
+  const void *tmg_dz12[2], *tmg_dz2;        // k_dgrad_tc: dZ of the layer above, 128-row boxes
+  const void *tmg_w12p[2], *tmg_w2p;        //             W12 / W2 as MN-major panels (boxes {32 floats, 32 rows}, ATOM_32B swizzle)
+  bool dgrad_tc;
   bool dense_tc;                            // batched passes run their two wide forward layers as k_dense_tc launches
   int dense_cap[3];                         // co-resident k_dense_tc clusters of 4 / 8 / 16 CTAs on this device
   NetLayout Lc, La;
@@ -417,7 +422,7 @@ static size_t carve(sc_agent* a, void* base) {
   a->mb_hl = cv.f((size_t)4 * B * a->Sp32);
   reg("mb_state", a->mb_s, B, S, a->Sp32, 4);
   reg("mb_new_state", a->mb_s2, B, S, a->Sp32, 4);
-  a->tmaps = (unsigned char*)cv.take(128 * 64);
+  a->tmaps = (unsigned char*)cv.take(128 * 96);
   a->obs_dev = cv.f(a->Sp32);
   a->act_eps = cv.f(round4i(A));
   a->act_out = cv.f(round4i(A));
@@ -538,11 +543,11 @@ static int encode_map(CUtensorMap* out, const void* base, int ld, int rows, int 
 
 static int build_tensor_maps(sc_agent* a) {
   std::vector<CUtensorMap> host;
-  host.reserve(64);
+  host.reserve(96);
   int rc = SC_OK;
-  auto add = [&](const void* base, int ld, int rows, int box_rows) -> const void* {
+  auto add = [&](const void* base, int ld, int rows, int box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) -> const void* {
     alignas(64) CUtensorMap m;
-    if (rc == SC_OK) rc = encode_map(&m, base, ld, rows, box_rows);
+    if (rc == SC_OK) rc = encode_map(&m, base, ld, rows, box_rows, swz);
     host.push_back(m);
     return a->tmaps + (host.size() - 1) * sizeof(CUtensorMap);
   };
@@ -612,6 +617,12 @@ static int build_tensor_maps(sc_agent* a) {
     }
     d_on_w1 = add(on.w1, K1, H1, DW);
     d_on_w2 = add(on.w2, H1, H2, DW);
+    for (int k = 0; k < 2; ++k) {
+      a->tmg_dz12[k] = add(a->cw[k].dz12, H2, B, DB);
+      a->tmg_w12p[k] = add(C[k].w12, H1, H2, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    }
+    a->tmg_dz2 = add(a->aw.dz2, H2, B, DB);
+    a->tmg_w2p = add(on.w2, H1, H2, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     d_tg_w1 = d_on_w1; d_tg_w2 = d_on_w2;
     if (td3) {
       ActorP tg = actor_ptrs(a->targets + a->toff_actor, a->La, a->cfg.kind);
@@ -620,7 +631,7 @@ static int build_tensor_maps(sc_agent* a) {
     }
   }
   if (rc != SC_OK) return rc;
-  if (host.size() > 64) return fail(SC_ERR_STATE, "tensor map table overflow");
+  if (host.size() > 96) return fail(SC_ERR_STATE, "tensor map table overflow");
   a->tmd_critic = d; a->tmd_actor = d;
   a->tmd_critic.actor_w1 = td3 ? d_tg_w1 : d_on_w1;
   a->tmd_critic.actor_w2 = td3 ? d_tg_w2 : d_on_w2;
@@ -684,6 +695,9 @@ static int build_op_tables(sc_agent* a) {
     a->dense_cap[0] = dense_tc_max_clusters(4); a->dense_cap[1] = dense_tc_max_clusters(8); a->dense_cap[2] = dense_tc_max_clusters(16);
     if (a->dense_cap[0] < 1 || a->dense_cap[1] < 1) a->dense_tc = false;     // cannot host the clusters: keep the wide layers in k_rowphase
   }
+  // wide input gradients on tcgen05 as well (SMARTCAL_DGRAD=mma keeps the mma.sync stage of k_rowphase)
+  const char* dg = getenv("SMARTCAL_DGRAD");
+  a->dgrad_tc = a->dense_tc && !(dg && !strcmp(dg, "mma")) && dgrad_tc_max_clusters(8) >= 1;
   std::vector<TcCand> tc_critic, tc_actor;
   std::vector<CUtensorMap> tc_maps;
   g_tc_sink = a->use_tc ? &tc_critic : nullptr;
@@ -1389,6 +1403,27 @@ static int plan_rowphase(sc_agent* a, const RowPhaseParams& p_in, int timer_id) 
       PL(tt);
       *tt = p;
       p.skip_tail = 1;
+      if (a->dgrad_tc) {
+        // the wide input gradient (dz12 -> du11 / dz11 of both critics, or dz2 -> du1 / dz1 of the actor) on tcgen05
+        DenseTcParams g;
+        memset(&g, 0, sizeof(g));
+        g.N = H1; g.B = p.B; g.nrb = (p.B + 127) / 128; g.ks = 1; g.late_trigger = 0;
+        if (p.program == PROG_CRITIC) {
+          for (int k = 0; k < 2; ++k) {
+            g.ops[k] = DenseTcOp{a->tmg_dz12[k], nullptr, a->tmg_w12p[k], nullptr, p.crit[k].g11, nullptr, p.cw[k].h11, p.cw[k].zh11, p.cw[k].rs11, H2,
+                                 p.cw[k].du11, p.cw[k].dz11};
+          }
+          g.nops = 2;
+        } else {
+          g.ops[0] = DenseTcOp{a->tmg_dz2, nullptr, a->tmg_w2p, nullptr, p.actor.g1, nullptr, p.aw.h1, p.aw.zh1, p.aw.rs1, H2, p.aw.du1, p.aw.dz1};
+          g.nops = 1;
+        }
+        DenseTcParams* gp = emit_kernel<DenseTcParams>(a, KID_DGRAD, 0, g.nops, g.nrb, g.N, g.ks);
+        PL(gp);
+        *gp = g;
+        if (timer_id >= 0 && a->timing && (rc = emit_ctl(a, REC_TEND, timer_id))) return rc;
+        return SC_OK;
+      }
     }
   }
   RowPhaseParams* t = emit_kernel<RowPhaseParams>(a, KID_ROW, 0, a->row_variant, a->cluster_size, a->nclusters, a->tile_tm);
@@ -1825,6 +1860,7 @@ static cudaError_t issue_recs(sc_group* g, cudaStream_t st0) {
           case KID_HINT: e = launch_hint_coef(reinterpret_cast<const HintCoefP*>(pp), g->E, st); break;
           case KID_ADMM: e = launch_admm_update(reinterpret_cast<const AdmmP*>(pp), g->E, st); break;
           case KID_TAIL: e = launch_tail(reinterpret_cast<const RowPhaseParams*>(pp), g->E, r.g[0], st); break;
+          case KID_DGRAD: e = launch_dgrad_tc(reinterpret_cast<const DenseTcParams*>(pp), g->E, r.g[0], r.g[1], r.g[2], r.g[3], st); break;
           default: e = cudaErrorInvalidValue;
         }
         break;

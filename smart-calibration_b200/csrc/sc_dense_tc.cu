@@ -42,6 +42,17 @@ __device__ __forceinline__ uint64_t dt_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+__device__ __forceinline__ uint64_t dt_desc_mn(uint32_t saddr) {
+  // MN-major, SWIZZLE_128B_BASE32B (boxes of [32 reduction rows][32 floats] written with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):
+  // LBO = 4096 B (next box of 32 MN elements), SBO = 512 B, version 1 -- the layout sc_wgrad_tc.cu established with tools/probe/tc_probe.cu
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((4096u >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((512u >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
 __device__ __forceinline__ void dt_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -61,7 +72,12 @@ __device__ __forceinline__ void dt_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const DenseTcParams* __restrict__ pp) {
+// MODE 0: forward layer  H = ELU(LN(X W^T + b))            (X [B][K] K-major, W [N][K] K-major)
+// MODE 1: input gradient dU = (dZ W) * ELU'(h), dZ_in = LayerNorm backward of the producing layer
+//         (dZ [B][K] K-major with K = width of the layer above, W [K][N] MN-major panels, N = width of the producing layer).
+//         Replaces the mma.sync dgrad stage of k_rowphase (sc_rowphase_impl.cuh dgrad_stage) for batched passes.
+template <int MODE>
+__global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc_t(const DenseTcParams* __restrict__ pp) {
   __shared__ DenseTcParams p_sm;
   const DenseTcParams& p = load_params(pp, &p_sm);             // blockIdx.y = agent of the ensemble
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -136,7 +152,12 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const DenseTcParams*
         mark(0, 1);
         mbar_expect_tx(full_raw + slot, DT_X_BYTES + DT_W_BYTES + (op.mapXlo ? DT_X_BYTES : 0));
         tma_load_2d(reinterpret_cast<float*>(st), op.mapX, 32 * (kc0 + s), r0, full_raw + slot);
-        tma_load_2d(reinterpret_cast<float*>(st + DT_X_BYTES), op.mapW, 32 * (kc0 + s), n0, full_raw + slot);
+        if constexpr (MODE == 0) {
+          tma_load_2d(reinterpret_cast<float*>(st + DT_X_BYTES), op.mapW, 32 * (kc0 + s), n0, full_raw + slot);
+        } else {          // two panels [32 reduction rows][32 output columns]
+          tma_load_2d(reinterpret_cast<float*>(st + DT_X_BYTES), op.mapW, n0, 32 * (kc0 + s), full_raw + slot);
+          tma_load_2d(reinterpret_cast<float*>(st + DT_X_BYTES + 4096), op.mapW, n0 + 32, 32 * (kc0 + s), full_raw + slot);
+        }
         if (op.mapXlo)        // pre-split X: the small part goes straight to where the splitter would have written it
           tma_load_2d(reinterpret_cast<float*>(st + DT_X_BYTES + DT_W_BYTES), op.mapXlo, 32 * (kc0 + s), r0, full_raw + slot);
       }
@@ -145,13 +166,15 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const DenseTcParams*
   } else if (warp == 1) {
     // ---------------- MMA issue (one thread) ----------------
     // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(DT_N >> 3) << 17) | ((uint32_t)(DT_M >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (MODE == 1 ? (1u << 16) : 0u) | ((uint32_t)(DT_N >> 3) << 17) | ((uint32_t)(DT_M >> 4) << 24);
     // one elected lane issues; elect.sync (rather than a lane test) lets the compiler keep the descriptors in uniform
     // registers and emit the MMAs back to back -- a divergent branch costs ~70 cycles of uniform-datapath fix-up per MMA
     uint32_t leader;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(leader));
-    const uint64_t d_x0 = dt_desc(smem_u32(smem)), d_w0 = d_x0 + (uint64_t)(DT_X_BYTES >> 4);
-    const uint64_t d_xl0 = d_w0 + (uint64_t)(DT_W_BYTES >> 4), d_wl0 = d_xl0 + (uint64_t)(DT_X_BYTES >> 4);
+    const uint64_t d_x0 = dt_desc(smem_u32(smem));
+    const uint64_t d_w0 = MODE == 0 ? d_x0 + (uint64_t)(DT_X_BYTES >> 4) : dt_desc_mn(smem_u32(smem) + DT_X_BYTES);
+    const uint64_t d_xl0 = d_x0 + (uint64_t)((DT_X_BYTES + DT_W_BYTES) >> 4), d_wl0 = d_w0 + (uint64_t)((DT_X_BYTES + DT_W_BYTES) >> 4);
+    constexpr uint64_t WSTEP = MODE == 0 ? 2 : 64;             // B operand advance per 8-deep k-step: +32 B (K-major) / +1024 B (MN-major)
     for (int s = 0; s < nk; ++s) {
       const int slot = s % DT_STAGES;
       mbar_wait(full_lo + slot, (s / DT_STAGES) & 1u);
@@ -161,10 +184,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const DenseTcParams*
         const uint64_t so = (uint64_t)((slot * DT_STAGE_BYTES) >> 4);        // (descriptor addresses count 16-byte units)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint64_t o = so + (uint64_t)(2 * j);                           // + 32 B per 8-deep k-step
-          dt_mma(tmem, d_xl0 + o, d_w0 + o, idesc, (s | j) != 0 ? 1u : 0u);
-          dt_mma(tmem, d_x0 + o, d_wl0 + o, idesc, 1u);
-          dt_mma(tmem, d_x0 + o, d_w0 + o, idesc, 1u);
+          const uint64_t o = so + (uint64_t)(2 * j), ow = so + WSTEP * (uint64_t)j;   // A: + 32 B per 8-deep k-step
+          dt_mma(tmem, d_xl0 + o, d_w0 + ow, idesc, (s | j) != 0 ? 1u : 0u);
+          dt_mma(tmem, d_x0 + o, d_wl0 + ow, idesc, 1u);
+          dt_mma(tmem, d_x0 + o, d_w0 + ow, idesc, 1u);
         }
         mark(1, 3);
         dt_commit(empty + slot);                              // frees the stage when these MMAs have read it
@@ -204,6 +227,18 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const DenseTcParams*
     }
   }
   // ---------------- epilogue (all warps): bias, LayerNorm across the cluster, ELU, stores ----------------
+  // dgrad mode: this thread's 16 columns of the producing layer's h / zh are requested now, ahead of the accumulator
+  float4 hq[MODE == 1 ? DT_CW / 4 : 1], zq[MODE == 1 ? DT_CW / 4 : 1];
+  if constexpr (MODE == 1) {
+    const int row_ = (warp & 3) * 32 + lane, cb_ = (warp >> 2) * DT_CW;
+    const bool ok = kh == 0 && r0 + row_ < p.B;
+    const size_t off = (size_t)(ok ? r0 + row_ : 0) * p.N + n0 + cb_;
+#pragma unroll
+    for (int j = 0; j < DT_CW / 4; ++j) {
+      hq[j] = ok ? ld_act4(op.H + off + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      zq[j] = ok ? ld_act4(op.ZH + off + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   mbar_wait(&acc_done, 0);
   if (!p.late_trigger) pdl_launch();                          // the next kernel may set itself up under this epilogue
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -257,6 +292,71 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const DenseTcParams*
       z[j] += q4.x; z[j + 1] += q4.y; z[j + 2] += q4.z; z[j + 3] += q4.w;
     }
   }
+  if constexpr (MODE == 1) {
+    // ---- dgrad epilogue: dU = dH * ELU'(h);  t = dU * gamma;  dZ = rs * (t - mean(t) - zh * mean(t * zh))  (row means over all N columns) ----
+    float tv[DT_CW], zhv[DT_CW];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < DT_CW; ++j) {
+      const float4 h4 = hq[j >> 2], z4 = zq[j >> 2];
+      const float h = (j & 3) == 0 ? h4.x : (j & 3) == 1 ? h4.y : (j & 3) == 2 ? h4.z : h4.w;
+      zhv[j] = (j & 3) == 0 ? z4.x : (j & 3) == 1 ? z4.y : (j & 3) == 2 ? z4.z : z4.w;
+      const float du = z[j] * elu_grad_from_out(h);
+      z[j] = du;
+      tv[j] = du * svec[1][cb + j];
+      s1 += tv[j];
+      s2 = fmaf(tv[j], zhv[j], s2);
+    }
+    psum[c][row] = s1;
+    pm2[c][row] = s2;
+    __syncthreads();
+    if (p.ks == 1) asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    if (tid < DT_M * 2) {
+      const int r_ = tid & (DT_M - 1);
+      const float a1 = ((psum[0][r_] + psum[1][r_]) + psum[2][r_]) + psum[3][r_];
+      const float a2 = ((pm2[0][r_] + pm2[1][r_]) + pm2[2][r_]) + pm2[3][r_];
+      const uint32_t local = smem_u32(&xstat[fb][r_]);
+      for (int r = tid >> 7; r < nfb; r += 2) {
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+        asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(a1), "f"(a2) : "memory");
+      }
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    float c1 = 0.f, c2 = 0.f;
+    for (int r = 0; r < nfb; ++r) {                           // slices in rank order
+      const float2 pv = xstat[r][row];
+      c1 += pv.x;
+      c2 += pv.y;
+    }
+    const float fN = (float)p.N;
+    c1 /= fN;
+    c2 /= fN;
+    const float rsr = (r0 + row < p.B) ? ld_act(op.RS + r0 + row) : 0.f;
+    float* tile_u = reinterpret_cast<float*>(smem);
+    float* tile_d = tile_u + DT_M * DT_TP;
+#pragma unroll
+    for (int j = 0; j < DT_CW; j += 4) {
+      float4 u4 = make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]), d4;
+      d4.x = rsr * (tv[j] - c1 - zhv[j] * c2);
+      d4.y = rsr * (tv[j + 1] - c1 - zhv[j + 1] * c2);
+      d4.z = rsr * (tv[j + 2] - c1 - zhv[j + 2] * c2);
+      d4.w = rsr * (tv[j + 3] - c1 - zhv[j + 3] * c2);
+      *reinterpret_cast<float4*>(tile_u + row * DT_TP + cb + j) = u4;
+      *reinterpret_cast<float4*>(tile_d + row * DT_TP + cb + j) = d4;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < DT_M * DT_N / 4 / DT_THREADS; ++u) {
+      const int f = tid + u * DT_THREADS, r = f / (DT_N / 4), c4 = f % (DT_N / 4);
+      if (r0 + r < p.B) {
+        const size_t off = (size_t)(r0 + r) * p.N + n0 + 4 * c4;
+        *reinterpret_cast<float4*>(op.DU + off) = *reinterpret_cast<const float4*>(tile_u + r * DT_TP + 4 * c4);
+        *reinterpret_cast<float4*>(op.DZ + off) = *reinterpret_cast<const float4*>(tile_d + r * DT_TP + 4 * c4);
+      }
+    }
+  } else {
 #pragma unroll
   for (int j = 0; j < DT_CW; ++j) z[j] += svec[0][cb + j];
   float s = 0.f;
@@ -332,6 +432,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc(const DenseTcParams*
       if (op.ZH != nullptr) *reinterpret_cast<float4*>(op.ZH + off) = *reinterpret_cast<const float4*>(tile_z + r * DT_TP + 4 * c4);
     }
   }
+  }
   if (tid == 64) mark(2, 7);
   if (p.late_trigger) pdl_launch();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -380,11 +481,12 @@ __global__ void __launch_bounds__(128) k_gather_mb(const GatherP* __restrict__ p
 }
 
 size_t dense_tc_smem_bytes() { return (size_t)DT_STAGES * DT_STAGE_BYTES + DT_PART_BYTES + 1024; }
+size_t dgrad_tc_smem_bytes() { return dense_tc_smem_bytes(); }
 
 // co-resident clusters of `cs` CTAs this device can host for k_dense_tc (0: such clusters cannot be launched at all)
 int dense_tc_max_clusters(int cs) {
-  if (cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_tc_smem_bytes()) != cudaSuccess) { cudaGetLastError(); return 0; }
-  if (cs > 8 && cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cudaFuncSetAttribute(k_dense_tc_t<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_tc_smem_bytes()) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cs > 8 && cudaFuncSetAttribute(k_dense_tc_t<0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 0; }
   cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
   cudaLaunchAttribute attr[1];
   cfg.gridDim = dim3(cs * 8, 1, 1);
@@ -397,7 +499,7 @@ int dense_tc_max_clusters(int cs) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, k_dense_tc, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cudaOccupancyMaxActiveClusters(&n, k_dense_tc_t<0>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
 
@@ -414,13 +516,13 @@ static bool dt_first_use(bool (&done)[64]) {
 cudaError_t launch_dense_tc(const DenseTcParams* pp, int E, int nops, int nrb, int N, int ks, cudaStream_t st) {
   static bool configured[64], big[64];
   if (dt_first_use(configured)) {
-    cudaError_t e = cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_tc_smem_bytes());
+    cudaError_t e = cudaFuncSetAttribute(k_dense_tc_t<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_tc_smem_bytes());
     if (e != cudaSuccess) return e;
   }
   const int nfb = N / DT_N, cs = nfb * ks;
   if (nfb < 1 || nfb > DT_MAXCS || nfb * DT_N != N || ks < 1 || ks > 2 || cs > 16) return cudaErrorInvalidValue;
   if (cs > 8 && dt_first_use(big)) {
-    cudaError_t e = cudaFuncSetAttribute(k_dense_tc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaError_t e = cudaFuncSetAttribute(k_dense_tc_t<0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return e;
   }
   cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
@@ -437,7 +539,54 @@ cudaError_t launch_dense_tc(const DenseTcParams* pp, int E, int nops, int nrb, i
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  return cudaLaunchKernelEx(&cfg, k_dense_tc, pp);
+  return cudaLaunchKernelEx(&cfg, k_dense_tc_t<0>, pp);
+}
+
+// the wide input-gradient GEMM (MODE 1): same geometry rules as launch_dense_tc
+cudaError_t launch_dgrad_tc(const DenseTcParams* pp, int E, int nops, int nrb, int N, int ks, cudaStream_t st) {
+  static bool configured[64], big[64];
+  if (dt_first_use(configured)) {
+    cudaError_t e = cudaFuncSetAttribute(k_dense_tc_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgrad_tc_smem_bytes());
+    if (e != cudaSuccess) return e;
+  }
+  const int nfb = N / DT_N, cs = nfb * ks;
+  if (nfb < 1 || nfb > DT_MAXCS || nfb * DT_N != N || ks < 1 || ks > 2 || cs > 16) return cudaErrorInvalidValue;
+  if (cs > 8 && dt_first_use(big)) {
+    cudaError_t e = cudaFuncSetAttribute(k_dense_tc_t<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+  }
+  cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
+  cudaLaunchAttribute attr[2];
+  cfg.gridDim = dim3(nops * nrb * cs, E, 1);
+  cfg.blockDim = dim3(DT_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = dgrad_tc_smem_bytes();
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, k_dense_tc_t<1>, pp);
+}
+int dgrad_tc_max_clusters(int cs) {
+  if (cudaFuncSetAttribute(k_dense_tc_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dgrad_tc_smem_bytes()) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3(cs * 8, 1, 1);
+  cfg.blockDim = dim3(DT_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = dgrad_tc_smem_bytes();
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, k_dense_tc_t<1>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
 }
 
 cudaError_t launch_gather_mb(const GatherP* pp, int E, int B, cudaStream_t st) {

@@ -162,8 +162,11 @@ struct DenseTcOp {
   const void* mapXlo;              // nullptr, or: X arrives already split (mapX = tf32-rounded big part, mapXlo = small part)
   const void* mapW;                // W [N][K] (PyTorch layout), boxes {32 floats, 64 rows}
   const float *bias, *gamma, *beta;
-  float *H, *ZH, *RS;              // outputs [B][N] (ZH, RS nullable) as the row-phase tail reads them
+  float *H, *ZH, *RS;              // forward: outputs [B][N] (ZH, RS nullable) as the tail reads them; dgrad: the PRODUCING layer's h / zh / 1/std (inputs)
   int K;                           // reduction length, multiple of 32 (zero padded / TMA zero filled)
+  // dgrad mode (k_dgrad_tc): X = dZ [B][K] of the layer above, W = that layer's weight [K][N] as MN-major panels (boxes {32 floats, 32 rows},
+  // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), gamma = LayerNorm weight of the producing layer; outputs dU = dH * ELU'(h) and dZ (LayerNorm backward)
+  float *DU, *DZ;
 };
 struct DenseTcParams {
   DenseTcOp ops[5];
