@@ -117,6 +117,132 @@ def timed_steps(dev, steps, flush, timing=False):
     return sum(a.elapsed_time(b) for a, b in evs)      # ms
 
 
+def time_agent(learn, steps, warmup, flush=None):
+    """device time of `steps` calls of learn(): each call bracketed by its own CUDA-event pair on the launching stream; with
+    `flush` (a buffer larger than L2) the L2 is overwritten between calls, outside the pairs"""
+    for _ in range(warmup):
+        learn()
+    torch.cuda.synchronize()
+    st = torch.cuda.current_stream()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        if flush is not None:
+            flush.zero_()
+        a.record(st)
+        learn()
+        b.record(st)
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) / steps        # ms per step
+
+
+def td3_bytes(Bt):
+    """algorithmic bytes of one elastic-net TD3 step, actor / target updates every 2nd step"""
+    pa = 381826
+    return Bt * ((2 * S + A + 1) * 4 + 1) + (pa + 4 * PC) * 4 + 2 * PC * 20 + 0.5 * (pa * 4 + pa * 20 + (2 * PC + pa) * 4)
+
+
+def other_configs(args, peak):
+    """BASELINE.json configs measured in the same run as the headline: uniform-replay SAC (the reference's real learn(),
+    enet_sac.py:555-628), TD3 batch 1024 prioritized (configs[3]), calibration conv-SAC batch 256 (configs[2]) and
+    choose_action latency.  Each: device-timed steps/s (warm L2, CUDA events per step), roofline on algorithmic bytes, and the
+    CPU oracle port on a bounded sample."""
+    from smartcal_b200.elasticnet import enet_sac, enet_td3
+    from smartcal_b200.synth import make_transitions, pack
+    out = {}
+    n = min(args.steps, 100)
+
+    def port_rate(orc, k, threads=8):
+        t = torch.get_num_threads()
+        torch.set_num_threads(min(threads, os.cpu_count() or 1))
+        orc.learn()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            orc.learn()
+        dt = (time.perf_counter() - t0) / k
+        torch.set_num_threads(t)
+        return {"value": 1.0 / dt, "unit": "learn steps/s", "cores": min(threads, os.cpu_count() or 1), "kind": "port",
+                "sample": f"{k} learn() steps after 1 warm-up"}
+
+    # --- uniform-replay SAC, batch 256 (the reference's own code path) ---
+    torch.manual_seed(1)
+    np.random.seed(1)
+    ag = enet_sac.Agent(**HP, prioritized=False, use_hint=False, rng="device")
+    tr = make_transitions(101, C, S, A, "normal", 0.0)
+    ag._dev.fill(pack(tr), None)
+    ms = time_agent(ag._dev.learn, n, 10)
+    from oracle.sac_ref import SacRef
+    torch.manual_seed(1)
+    orc = SacRef(**HP, prioritized=False)
+    for i in range(C):
+        orc.store_flat(tr["state"][i], tr["action"][i], float(tr["reward"][i]), tr["new_state"][i], False, tr["hint"][i])
+    out["sac_uniform_b256"] = {"value": 1e3 / ms, "unit": "learn steps/s", "ms_per_step": ms,
+                               "roofline": {"bound": "hbm", "achieved": STEP_BYTES / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                            "frac": STEP_BYTES / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": STEP_BYTES},
+                               "cpu_baseline": port_rate(orc, 20)}
+    # choose_action latency (enet_sac.py:547-553): host obs -> device -> host action, one call
+    ob = {"eig": torch.from_numpy(tr["state"][0, :20].copy()), "A": torch.from_numpy(tr["state"][0, 20:].copy())}
+    for _ in range(20):
+        ag.choose_action(ob)
+    t0 = time.perf_counter()
+    for _ in range(200):
+        ag.choose_action(ob)
+    out["choose_action_us"] = {"value": (time.perf_counter() - t0) / 200 * 1e6, "unit": "us per call (host obs in, host action out, one sync)",
+                               "reference_cpu_us": 1700.0, "reference_source": "SURVEY section 6 probe (8 vCPU)"}
+    ag._dev.close()
+    # --- TD3 batch 1024 prioritized ---
+    Bt = 1024
+    torch.manual_seed(2)
+    np.random.seed(2)
+    hp3 = dict(gamma=0.99, lr_a=1e-3, lr_c=1e-3, input_dims=[S], batch_size=Bt, n_actions=A, max_mem_size=C, tau=0.005)
+    ag = enet_td3.Agent(**hp3, update_actor_interval=2, warmup=100, noise=0.1, prioritized=True, rng="device")
+    tr = make_transitions(102, C, S, A, "uniform", 0.0)
+    ag._dev.fill(pack(tr), None)
+    ms = time_agent(ag.learn, n, 10)
+    from oracle.td3_ref import Td3Ref
+    torch.manual_seed(2)
+    orc = Td3Ref(**hp3, update_actor_interval=2, warmup=0, noise=0.1, prioritized=True)
+    for i in range(C):
+        orc.store_flat(tr["state"][i], tr["action"][i], float(tr["reward"][i]), tr["new_state"][i], False, tr["hint"][i])
+    by = td3_bytes(Bt)
+    out["td3_b1024_per"] = {"value": 1e3 / ms, "unit": "learn steps/s", "ms_per_step": ms,
+                            "roofline": {"bound": "hbm", "achieved": by / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                         "frac": by / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": by},
+                            "cpu_baseline": port_rate(orc, 4)}
+    ag._dev.close()
+    # --- calibration conv-SAC batch 256 ---
+    try:
+        out["calib_b256"] = calib_numbers(min(args.steps, 30), 3)
+    except Exception as e:      # (never lose the headline line to a secondary config)
+        out["calib_b256"] = {"error": repr(e)}
+    return out
+
+
+def ensemble_numbers(args, single_ms, peak):
+    """E independent agents (different seeds / weights / replay contents) stepped by ONE launch sequence (sc_ensemble_learn,
+    blockIdx.y = agent): aggregate agent-steps/s.  The reference's counterpart is one process per seed (elasticnet/do.sh).
+    The ensembles' working sets (46 MB per agent) exceed the 126 MB L2 from E = 4 on, so no flush is needed there."""
+    from smartcal_b200.core import DeviceEnsemble
+    res = {}
+    for E in (2, 4, 8, 16):
+        agents = [make_agent(300 + i, "device")[0] for i in range(E)]
+        ens = DeviceEnsemble([a._dev for a in agents])
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if E < 4 else None
+        ms = time_agent(ens.learn, min(args.steps, 100), 10, flush)
+        res[str(E)] = {"agent_steps_per_s": E * 1e3 / ms, "us_per_agent_step": ms / E * 1e3, "ms_per_ensemble_step": ms,
+                       "vs_single_agent": (E * 1e3 / ms) / (1e3 / single_ms),
+                       "roofline_step": {"achieved": E * STEP_BYTES / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                         "frac": E * STEP_BYTES / (ms * 1e-3) / 1e9 / peak}}
+        ens.close()
+        for a in agents:
+            a._dev.close()
+        del agents, ens
+        torch.cuda.empty_cache()
+    best = max(res, key=lambda k: res[k]["agent_steps_per_s"])
+    return {"what": "E agents per launch sequence on ONE GPU (every kernel of learn() runs once with blockIdx.y = agent); each agent bit-identical "
+                    "to the same agent stepped alone (tests/test_gpu_round2.py)", "per_E": res, "best_E": int(best),
+            "best_agent_steps_per_s": res[best]["agent_steps_per_s"]}
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -159,48 +285,49 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_cold, ms_warm = float(t[0]), float(t[1])
 
-    # per-kernel CUDA-event timing (second pass so that the event records do not perturb the headline)
+    # per-kernel-group CUDA-event timing (second pass, eager launches, so that the event records do not perturb the headline)
     dev.enable_timing(True)
     for w in range(8):
         dev.kernel_time(w, reset=True)
     timed_steps(dev, min(args.steps, 100), flush)
     kt = [dev.kernel_time(w, reset=True) for w in range(8)]
     dev.enable_timing(False)
-    # *_rowphase are the phase groups (minibatch gather + the two tcgen05 dense launches + the row-phase tail/dgrad kernel);
+    # *_phase are the phase groups (minibatch gather + the two tcgen05 dense launches + k_tail + the tcgen05 dgrad launch);
     # *_dense_tc is the part of the group spent in k_gather_mb + 2 x k_dense_tc
-    names = ["critic_rowphase", "critic_wgrad_adam", "actor_rowphase", "actor_wgrad_adam", "per_sample", "per_update",
+    names = ["critic_phase", "critic_wgrad_adam", "actor_phase", "actor_wgrad_adam", "per_sample", "per_update",
              "critic_dense_tc", "actor_dense_tc"]
     kern = {n: {"avg_us": (ms / max(cnt, 1)) * 1e3, "launches": cnt} for n, (ms, cnt) in zip(names, kt)}
 
-    # end-to-end through the public API with host buffers (reference-RNG mode: host draws + H2D every step)
-    e2e = None
-    if True:
-        agent2, tr2 = make_agent(200 + rank, "reference")
-        obs = [{"eig": torch.from_numpy(tr2["state"][i, :20].copy()), "A": torch.from_numpy(tr2["state"][i, 20:].copy())} for i in range(64)]
-        obs2 = [{"eig": torch.from_numpy(tr2["new_state"][i, :20].copy()), "A": torch.from_numpy(tr2["new_state"][i, 20:].copy())} for i in range(64)]
+    # end-to-end through the public API with host buffers (reference-RNG mode: host draws, ONE pinned block + H2D per step)
+    agent2, tr2 = make_agent(200 + rank, "reference")
+    obs = [{"eig": torch.from_numpy(tr2["state"][i, :20].copy()), "A": torch.from_numpy(tr2["state"][i, 20:].copy())} for i in range(64)]
+    obs2 = [{"eig": torch.from_numpy(tr2["new_state"][i, :20].copy()), "A": torch.from_numpy(tr2["new_state"][i, 20:].copy())} for i in range(64)]
 
-        def one(i):
-            j = i % 64
-            agent2.store_transition(obs[j], tr2["action"][j], float(tr2["reward"][j]), obs2[j], False, tr2["hint"][j])
-            return agent2.learn(want_stats=True)
+    def one(i):
+        j = i % 64
+        agent2.store_transition(obs[j], tr2["action"][j], float(tr2["reward"][j]), obs2[j], False, tr2["hint"][j])
+        return agent2.learn(want_stats=True)
 
-        for i in range(max(args.warmup, 3)):
-            one(i)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            one(i)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * args.steps / float(tt[0]), "unit": "learn steps/s",
-               "h2d_bytes_per_step": (2 * S + 2 * A + 2) * 4 + B * 8 + 2 * B * A * 4, "d2h_bytes_per_step": 16 * 4 + 4,     # the 16-float loss / diagnostics block + the hint multiplier, one copy each
-               "mode": "store_transition(host obs) + learn() + loss readback, rng='reference' (host numpy/torch draws)"}
+    for i in range(max(args.warmup, 3)):
+        one(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        one(i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * args.steps / float(tt[0]), "unit": "learn steps/s",
+           "h2d_bytes_per_step": (2 * S + 2 * A + 2) * 4 + B * 8 + 2 * B * A * 4, "d2h_bytes_per_step": 32 * 4,     # the 32-float loss / diagnostics block
+           "mode": "store_transition(host obs) + learn() + loss readback through the facade, rng='reference' (host numpy/torch draws); the "
+                   "transition, the PER uniforms and both noise tensors travel in ONE pinned block / host->device copy, the kernels replay "
+                   "from a CUDA graph (sc_agent_store_learn)"}
+    agent2._dev.close()
 
     # config 5 topology (world > 1): rank 0 = learner, ranks >= 1 = actors; per episode ONE NCCL broadcast of the actor
-    # block + ONE gather of 100-transition blocks, then the learner ingests them (store + learn per transition)
+    # block + ONE all_gather of 100-transition blocks, then the learner ingests them (store + learn per transition)
     al = None
     if world > 1:
         from smartcal_b200.elasticnet import distributed_per_sac as D
@@ -209,16 +336,20 @@ def run_ours(args):
         flat = agent.actor.flat()
         blk = torch.randn(D.TRANSITIONS_PER_EPISODE, T, device="cuda")
         blk[:, -1] = 0
+        ex.warm(flat.numel(), D.TRANSITIONS_PER_EPISODE, T)
         episodes = 3
+        t_bc = t_ag = 0.0
         for ep in range(episodes + 1):          # first episode is warm-up
             if ep == 1:
                 barrier()
-                t_ex, t_all = 0.0, time.perf_counter()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t_bc = t_ag = 0.0
+                t_all = time.perf_counter()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record()
             ex.broadcast_actor(flat)
-            parts = ex.gather_blocks(blk)
             e1.record()
+            parts = ex.gather_blocks(blk)
+            e2.record()
             if rank == 0:
                 for b in parts:
                     for i in range(b.shape[0]):
@@ -226,30 +357,35 @@ def run_ours(args):
                         dev.learn()
             torch.cuda.synchronize()
             if ep >= 1:
-                t_ex += e0.elapsed_time(e1)
+                t_bc += e0.elapsed_time(e1)
+                t_ag += e1.elapsed_time(e2)
         barrier()
         dt = time.perf_counter() - t_all
         al = {"episodes": episodes, "actors": world - 1, "learner_steps_per_s": episodes * (world - 1) * 100 / dt,
-              "exchange_ms_per_episode": t_ex / episodes,
+              "exchange_ms_per_episode": (t_bc + t_ag) / episodes, "broadcast_ms_per_episode": t_bc / episodes,
+              "all_gather_ms_per_episode": t_ag / episodes,
               "bytes_per_episode": {"broadcast_actor": int(flat.numel() * 4), "gather_transitions_per_actor": int(blk.numel() * 4)}}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peak, peak_src = peaks()
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1q_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("critic_phase_dram_bytes")
-    crit_s = kern["critic_rowphase"]["avg_us"] * 1e-6
+    traffic, traffic_src = None, None
+    for cand in ("r2_traffic.json",):
+        tp = os.path.join(ROOT, "profiles", cand)
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj.get("critic_phase_dram_bytes"), f"profiles/{cand}: {tj.get('how', '')}"
+    crit_s = kern["critic_phase"]["avg_us"] * 1e-6
     dense_s = kern["critic_dense_tc"]["avg_us"] * 1e-6
     tf32_peak = peaks_tf32()
-    roof = {"bound": "hbm", "kernel": "critic phase = k_gather_mb + 2 x k_dense_tc + k_rowphase<PROG_CRITIC> (one dependent chain, timed as a group)",
+    step_s = ms_cold / args.steps * 1e-3
+    roof = {"bound": "hbm", "kernel": "critic phase = k_gather_mb + 2 x k_dense_tc + k_tail + k_dense_tc_t<1> (dgrad) (one dependent chain, timed as a group)",
             "achieved": CRITIC_PHASE_BYTES / crit_s / 1e9, "peak": peak,
-            "unit": "GB/s", "frac": CRITIC_PHASE_BYTES / crit_s / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+            "unit": "GB/s", "frac": CRITIC_PHASE_BYTES / crit_s / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": CRITIC_PHASE_BYTES,
-            "note": "not HBM-bound: a chain of latency-bound stages on 256 rows (DESIGN.md 5); the wide layers run on tcgen05 (next object), "
-                    "the row-local tail and the dgrad stage on FP32 / mma.sync",
+            "note": "a single agent's step is a dependent chain of latency-bound stages on 256 rows (DESIGN.md 5), not an HBM stream; the "
+                    "ensemble object below is the same path with the machine filled",
             "tensor": {"kernel": "k_dense_tc (critic phase: 5 x fc1/fc11 then 5 x fc2/fc12, with the gather launch)",
                        "algorithmic_tflop_per_phase": DENSE_FLOP / 1e12,
                        "achieved": DENSE_FLOP / dense_s / 1e12 if dense_s > 0 else None,
@@ -258,11 +394,18 @@ def run_ours(args):
                        "frac": DENSE_FLOP / dense_s / 1e12 / tf32_peak if dense_s > 0 else None,
                        "peak_source": "0.5 x MEASURED_PEAKS.json bf16_tflops (kind::tf32 runs at half the bf16 rate; tools/probe/mma_rate.cu: "
                                       "2015 vs 4030 MAC/clk/SM)",
-                       "note": "fp32 parity costs 3 TF32 products per MAC ('issued'); at 20-80 CTAs of one 128x64 tile each the launches are "
-                               "latency- and shared-memory-bandwidth-bound, not tensor-bound (DESIGN.md 5)"},
-            "step": {"algorithmic_bytes": STEP_BYTES, "achieved": STEP_BYTES / (ms_cold / args.steps * 1e-3) / 1e9,
-                     "frac": STEP_BYTES / (ms_cold / args.steps * 1e-3) / 1e9 / peak}}
+                       "note": "fp32 parity costs 3 TF32 products per MAC ('issued')"},
+            "step": {"algorithmic_bytes": STEP_BYTES, "achieved": STEP_BYTES / step_s / 1e9, "frac": STEP_BYTES / step_s / 1e9 / peak}}
+    ens = ensemble_numbers(args, ms_cold / args.steps, peak) if world == 1 else None
+    if ens is not None:
+        b = ens["per_E"][str(ens["best_E"])]
+        roof["ensemble_step"] = {"E": ens["best_E"], "algorithmic_bytes": ens["best_E"] * STEP_BYTES, "achieved": b["roofline_step"]["achieved"],
+                                 "peak": peak, "unit": "GB/s", "frac": b["roofline_step"]["frac"]}
+    configs = other_configs(args, peak) if world == 1 else None
     cpu = cpu_baseline(sample_seconds=12.0)
+    pvr = os.path.join(ROOT, "profiles", "r2_port_vs_reference.json")
+    if os.path.exists(pvr):
+        cpu["port_vs_reference"] = json.load(open(pvr))
     eager = gpu_eager_baseline() if world == 1 else None
     out = {"metric": "SAC learn() steps/sec (batch=256)", "value": world * args.steps / (ms_cold * 1e-3), "unit": "learn steps/s",
            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_cold / args.steps,
@@ -271,6 +414,10 @@ def run_ours(args):
                       "rng": "device Philox", "parallelism": "replicas" if world > 1 else "single agent"},
            "l2_warm": {"value": world * args.steps / (ms_warm * 1e-3), "ms_per_step": ms_warm / args.steps},
            "e2e": e2e, "gpu_launches": int(launches), "kernels": kern, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+    if ens is not None:
+        out["ensemble"] = ens
+    if configs is not None:
+        out["configs"] = configs
     if al is not None:
         out["actor_learner"] = al
     if eager is not None:
@@ -344,6 +491,52 @@ def gpu_eager_baseline(steps=200, warmup=20):
     return {"value": steps / el, "unit": "learn steps/s", "ms_per_step": el / steps * 1e3,
             "what": f"oracle/sac_ref.py with device='cuda' (torch {torch.__version__} eager kernels, host PER + host sampling like the "
                     f"reference), {steps} steps, wall clock"}
+
+
+def calib_numbers(steps, warmup):
+    """calibration conv-SAC (BASELINE.json configs[2]) device-timed steps/s + CPU port on one step; used inside the headline line"""
+    from smartcal_b200.calibration import calib_sac
+    from smartcal_b200.synth import make_calib_transitions
+    M, Bc, Cc = 10, 256, 512
+    A_ = 2 * M
+    hp = dict(gamma=0.99, batch_size=Bc, n_actions=A_, tau=0.005, max_mem_size=Cc, input_dims=[1, 128, 128], M=M, lr_a=1e-3, lr_c=1e-3,
+              reward_scale=M, alpha=0.03, hint_threshold=0.01, admm_rho=1.0, use_hint=False)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    agent = calib_sac.Agent(**hp, rng="device")
+    tr = make_calib_transitions(100, Cc, M, A_, 128, 0.0)
+    dev = agent._dev
+    for name, key in (("state_memory_img", "img"), ("new_state_memory_img", "img2"), ("state_memory_sky", "sky"), ("new_state_memory_sky", "sky2"),
+                      ("action_memory", "action"), ("hint_memory", "hint")):
+        dev.buffer(name).copy_(torch.as_tensor(tr[key].reshape(Cc, -1)).to(dev.device))
+    dev.buffer("reward_memory").copy_(torch.as_tensor(tr["reward"].reshape(Cc, 1)).to(dev.device))
+    dev.set_counters(Cc, 0)
+    rs = np.random.RandomState(1)
+
+    def step():
+        dev.set_batch(rs.choice(Cc, Bc, replace=False))
+        dev.learn()
+    ms = time_agent(step, steps, warmup)
+    flop = 119e9
+    from oracle.calib_ref import CalibSacRef
+    torch.manual_seed(0)
+    orc = CalibSacRef(**hp)
+    for i in range(Cc):
+        orc.replay.store(tr["img"][i], tr["sky"][i], tr["action"][i], float(tr["reward"][i]), tr["img2"][i], tr["sky2"][i], False, tr["hint"][i])
+    t = torch.get_num_threads()
+    nt = min(32, os.cpu_count() or 1)
+    torch.set_num_threads(nt)
+    orc.learn()
+    t0 = time.perf_counter()
+    orc.learn()
+    dt = time.perf_counter() - t0
+    torch.set_num_threads(t)
+    tf32_peak = peaks_tf32()
+    return {"value": 1e3 / ms, "unit": "learn steps/s", "ms_per_step": ms,
+            "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                         "frac": flop / (ms * 1e-3) / 1e12 / tf32_peak, "algorithmic_flop": flop,
+                         "note": "conv trunk still on FP32 FFMA kernels (DESIGN.md): fraction of the TF32 tensor peak it would be bound by"},
+            "cpu_baseline": {"value": 1.0 / dt, "unit": "learn steps/s", "cores": nt, "kind": "port", "sample": "1 learn() step after 1 warm-up"}}
 
 
 def run_calib(args):

@@ -25,9 +25,10 @@
 namespace sc {
 
 constexpr int TR = 4;                       // batch rows per CTA
-constexpr int TL_THREADS = 256;             // consumer threads
+constexpr int TL_THREADS = 512;             // consumer threads: the chain is latency-bound, 16 warps hide twice what 8 did
 constexpr int TL_ALL = TL_THREADS + 32;     // + the producer warp
-constexpr int TL_WARPS = 8;
+constexpr int TL_WARPS = 16;
+constexpr int RED_SLOTS = 8;                // cross-warp partial slots of the transposed product (warps w and w + 8 share slot w)
 constexpr int CH_FLOATS = 4096;             // floats per weight chunk (16 KB): 16 rows of 256 or 32 rows of 128
 constexpr int NSLOT = 3;                    // ring depth
 constexpr int PSTAGE_FLOATS = 9600;         // staged small parameters (biases, LayerNorm affine, fc21, fc3, heads) of the actor + 4 critics
@@ -52,13 +53,13 @@ struct TailS {
   float *ga, *gb;                // [2][TR][H2]
   float *gc, *gd;                // [2][TR][HA1]  (actor phase: [TR][H2])
   float *ge, *gf;                // [2][TR][HA2]
-  float *red;                    // [TL_WARPS][TR][H2] cross-warp partials
+  float *red;                    // [RED_SLOTS][TR][H2] cross-warp partials
   float *wbuf;                   // [NSLOT][CH_FLOATS] weight chunk ring
   float *pstage;                 // [PSTAGE_FLOATS] small parameters
 };
 constexpr int TAIL_SMEM_FLOATS = 2 * TR * H2 + 2 * TR * H3 + TR * 2 * AMAX + 2 * TR * AMAX + TR * AMAX * 4 + TR * AMAX + TR * 16 + TR * 8 +
                                  NETS4 * TR * H2 + 2 * TR * H2 + 2 * NETS4 * TR * HA1 + 2 * NETS4 * TR * HA2 + NETS4 * TR * 2 + NETS4 * TR +
-                                 4 * TR * H2 + 4 * TR * HA1 + 4 * TR * HA2 + TL_WARPS * TR * H2 + NSLOT * CH_FLOATS + PSTAGE_FLOATS;
+                                 4 * TR * H2 + 4 * TR * HA1 + 4 * TR * HA2 + RED_SLOTS * TR * H2 + NSLOT * CH_FLOATS + PSTAGE_FLOATS;
 __device__ TailS tail_carve(float* sm) {
   TailS t;
   t.xh2 = sm; sm += TR * H2;
@@ -85,7 +86,7 @@ __device__ TailS tail_carve(float* sm) {
   t.gd = sm; sm += 2 * TR * HA1;
   t.ge = sm; sm += 2 * TR * HA2;
   t.gf = sm; sm += 2 * TR * HA2;
-  t.red = sm; sm += TL_WARPS * TR * H2;
+  t.red = sm; sm += RED_SLOTS * TR * H2;
   t.wbuf = sm; sm += NSLOT * CH_FLOATS;
   t.pstage = sm; sm += PSTAGE_FLOATS;
   return t;
@@ -96,6 +97,18 @@ enum { TSC_LOGP = 0, TSC_DQ1 = 6, TSC_DQ2 = 7, TSC_GLP = 8, TSC_REWARD = 9, TSC_
 // network parameters are read through generic loads: the small tensors are staged in shared memory at kernel start (below)
 __device__ __forceinline__ float ldp(const float* p) { return *p; }
 __device__ __forceinline__ float4 ldp4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+__device__ unsigned long long* g_tail_ts = nullptr;     // debug timeline target of t_mark_g (set per kernel by thread 0)
+__device__ __forceinline__ void t_mark_g(int i) {
+  if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 64 && g_tail_ts != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_tail_ts[(size_t)(2400 + 2 * blockIdx.x) * 8 + i] = t;
+  }
+}
+// barrier over the consumer threads only (the producer warp never joins it)
+__device__ __forceinline__ void tsync() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
+static_assert(TL_THREADS == 512, "tsync() is written for 512 consumer threads");
 
 // ---- weight chunk stream ---------------------------------------------------------------------------------------------------
 // A phase's weight traffic is a flat list of chunks (whole rows of one matrix, <= 16 KB, contiguous in global memory because
@@ -177,7 +190,7 @@ __device__ void linear_fwd(const LinJob* jobs, int njobs, const Stream& st, int&
       chunk_release(st, cur);
     }
   }
-  consumer_sync();
+  tsync();
 }
 
 // transposed: out[r][k] = sum_n d[r][n] W[n][k] for ONE job (N rows, K columns); result left in out ([TR][K], shared memory)
@@ -212,18 +225,33 @@ __device__ void linear_bwd(const LinJob& jb, float* out, const Stream& st, int& 
     }
     chunk_release(st, cur);
   }
+  // cross-warp combination in fixed order: slot w <- warp w, then += warp w + 8, then slots 0..7 are summed
+  if (warp < RED_SLOTS) {
 #pragma unroll
-  for (int r = 0; r < TR; ++r)
+    for (int r = 0; r < TR; ++r)
 #pragma unroll
-    for (int v = 0; v < KV; ++v) *reinterpret_cast<float4*>(s.red + (warp * TR + r) * K + 4 * lane + 128 * v) = acc[r][v];
-  consumer_sync();
+      for (int v = 0; v < KV; ++v) *reinterpret_cast<float4*>(s.red + (warp * TR + r) * K + 4 * lane + 128 * v) = acc[r][v];
+  }
+  tsync();
+  if (warp >= RED_SLOTS) {
+#pragma unroll
+    for (int r = 0; r < TR; ++r)
+#pragma unroll
+      for (int v = 0; v < KV; ++v) {
+        float4* q = reinterpret_cast<float4*>(s.red + ((warp - RED_SLOTS) * TR + r) * K + 4 * lane + 128 * v);
+        float4 t = *q;
+        t.x += acc[r][v].x; t.y += acc[r][v].y; t.z += acc[r][v].z; t.w += acc[r][v].w;
+        *q = t;
+      }
+  }
+  tsync();
   for (int e = tid; e < TR * K; e += TL_THREADS) {
     float v = 0.f;
 #pragma unroll
-    for (int w = 0; w < TL_WARPS; ++w) v += s.red[w * TR * K + e];
+    for (int w = 0; w < RED_SLOTS; ++w) v += s.red[w * TR * K + e];
     out[e] = v;
   }
-  consumer_sync();
+  tsync();
 }
 
 // ---- row helpers (rows indexed rix = net*TR + t; warps stride over them) -----------------------------------------------------
@@ -301,7 +329,8 @@ __device__ void t_action_branches(int nn, const CriticP* const* c, const float* 
     for (int j = 0; j < A; ++j) acc = fmaf(ldp(w + j), a[j], acc);
     s.v21[e] = acc + ldp(c[net]->b21 + n);
   }
-  consumer_sync();
+  tsync();
+  if (nn == NETS4) t_mark_g(10);
   const float *g21[NETS4], *b21[NETS4], *g22[NETS4], *b22[NETS4];
   LinJob jobs[NETS4];
   for (int i = 0; i < nn; ++i) {
@@ -309,10 +338,12 @@ __device__ void t_action_branches(int nn, const CriticP* const* c, const float* 
     jobs[i] = LinJob{HA2, c[i]->b22, s.v21 + i * TR * HA1, s.v22 + i * TR * HA2};
   }
   t_ln_elu(nn, s.v21, s.zh21, HA1, g21, b21, s.rsn, 2);
-  consumer_sync();
+  tsync();
+  if (nn == NETS4) t_mark_g(11);
   linear_fwd<HA1>(jobs, nn, st, cur);
+  if (nn == NETS4) t_mark_g(12);
   t_ln_elu(nn, s.v22, s.zh22, HA2, g22, b22, s.rsn + 1, 2);
-  consumer_sync();
+  tsync();
 }
 // q[net][t] = b3 + w3[0:H2].h12[net][t] + w3[H2:].h22[net][t]
 __device__ void t_critic_q(int nn, const CriticP* const* c, const TailS& s) {
@@ -333,7 +364,7 @@ __device__ void t_actor_forward(const RowPhaseParams& p, const TailS& s, const S
   LinJob j3{H3, a.b3, s.xh2, s.x3};
   linear_fwd<H2>(&j3, 1, st, cur);
   t_ln_elu(1, s.x3, s.zh3, H3, g3, be3, s.rsx + 2, 8);
-  consumer_sync();
+  tsync();
   // heads: (mu | logsigma) rows of width A each -> s.head[t][0:A] and [AMAX:AMAX+A]; one warp per output, weights from L2 (<= 2A rows)
   {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -352,7 +383,7 @@ __device__ void t_actor_forward(const RowPhaseParams& p, const TailS& s, const S
       }
     }
   }
-  consumer_sync();
+  tsync();
 }
 __device__ __forceinline__ float t_eps_value(const RowPhaseParams& p, int row, int j) {
   const size_t e = (size_t)row * p.A + j;
@@ -394,13 +425,22 @@ __device__ void t_policy_head(const RowPhaseParams& p, const TailS& s, const TRo
       s.an[r * AMAX + j] = act;
     }
   }
-  consumer_sync();
+  tsync();
   if (p.kind == 0 && tid < TR) {
     float v = 0.f;
     for (int j = 0; j < p.A; ++j) v += s.lp[tid * AMAX + j];
     s.sc[tid * 16 + TSC_LOGP] = v;
   }
-  consumer_sync();
+  tsync();
+}
+
+// optional stage timeline (SMARTCAL_STAMPS): thread 0 of CTA b stamps globaltimer into debug_ts rows 2400 + 2 b .. (16 marks)
+__device__ __forceinline__ void t_mark(const RowPhaseParams& p, int i) {
+  if (p.tstamp != nullptr && threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.tstamp[(size_t)(2400 + 2 * blockIdx.x) * 8 + i] = t;
+  }
 }
 
 // ======================================================================================================
@@ -409,6 +449,7 @@ __device__ void t_policy_head(const RowPhaseParams& p, const TailS& s, const TRo
 __device__ void t_critic(const RowPhaseParams& p, const TailS& s, const TRows& rs, const Stream& st) {
   int cur = 0;
   const int tid = threadIdx.x;
+  t_mark(p, 0);
   t_load_rows(s.xh2, p.aw.t_h2, H2, rs);
   for (int k = 0; k < 2; ++k) {
     t_load_rows(s.h12 + k * TR * H2, p.tw[k].h12, H2, rs);
@@ -429,16 +470,21 @@ __device__ void t_critic(const RowPhaseParams& p, const TailS& s, const TRows& r
     s.sc[tid * 16 + TSC_DONE] = p.rp.done[slot] != 0 ? 1.f : 0.f;
   }
   mbar_wait(st.pbar, 0);          // staged parameters have landed (the copies ran under the row loads)
-  consumer_sync();
+  tsync();
+  t_mark(p, 1);
   // ---- policy on s' (SAC: online actor, sampled; TD3: target actor + clipped scalar noise) ----
   t_actor_forward(p, s, st, cur);
+  t_mark(p, 2);
   t_policy_head(p, s, rs, true);
+  t_mark(p, 3);
   // ---- action branches of all four critics at once: targets on a', online critics on the replay action ----
   const CriticP* nets[NETS4] = {&p.targ[0], &p.targ[1], &p.crit[0], &p.crit[1]};
   const float* an_sel[NETS4] = {s.an, s.an, s.an + TR * AMAX, s.an + TR * AMAX};
   t_action_branches(NETS4, nets, an_sel, p.A, p.Ap, s, st, cur);
+  t_mark(p, 4);
   t_critic_q(NETS4, nets, s);
-  consumer_sync();
+  tsync();
+  t_mark(p, 5);
   const float wsum = p.is_wsum ? ld_act(p.is_wsum) : (float)p.B;
   const float coef = 2.f * wsum / ((float)p.B * (float)p.B) * p.closs_scale;   // d/dq of mean(w)*mean((q-y)^2) [DDPG: sum]
   if (tid < TR) {
@@ -480,7 +526,8 @@ __device__ void t_critic(const RowPhaseParams& p, const TailS& s, const TRows& r
     t_store_rows(p.cw[k].h22, s.v22 + (2 + k) * TR * HA2, HA2, rs);
     t_store_rows(p.cw[k].zh22, s.zh22 + (2 + k) * TR * HA2, HA2, rs);
   }
-  consumer_sync();
+  tsync();
+  t_mark(p, 6);
   // ---- backward of both online critics: d cat = dq * w3 ----
   for (int e = tid; e < 2 * TR * HCAT; e += TL_THREADS) {
     const int rix = e / HCAT, j = e - rix * HCAT, k = rix / TR, r = rix - k * TR;
@@ -488,13 +535,14 @@ __device__ void t_critic(const RowPhaseParams& p, const TailS& s, const TRows& r
     if (j < H2) s.ga[rix * H2 + j] = gval; else s.ge[rix * HA2 + (j - H2)] = gval;
   }
   if (tid < 2 * TR) s.qv[tid] = s.rsx[(tid % TR) * 8 + 4 + tid / TR];      // rs12 of (k, r) as a dense [2*TR] array
-  consumer_sync();
+  tsync();
   {
     const float *g12[2] = {p.crit[0].g12, p.crit[1].g12}, *g22[2] = {p.crit[0].g22, p.crit[1].g22};
     t_ln_bwd(2, s.ga, s.h12 + 2 * TR * H2, s.zh12, H2, g12, s.qv, 1, s.gb);
     t_ln_bwd(2, s.ge, s.v22 + 2 * TR * HA2, s.zh22 + 2 * TR * HA2, HA2, g22, s.rsn + 2 * TR * 2 + 1, 2, s.gf);
   }
-  consumer_sync();
+  tsync();
+  t_mark(p, 7);
   for (int k = 0; k < 2; ++k) {
     t_store_rows(p.cw[k].du12, s.ga + k * TR * H2, H2, rs);
     t_store_rows(p.cw[k].dz12, s.gb + k * TR * H2, H2, rs);
@@ -505,15 +553,17 @@ __device__ void t_critic(const RowPhaseParams& p, const TailS& s, const TRows& r
     LinJob jb{HA2, nullptr, s.gf + k * TR * HA2, nullptr};
     linear_bwd<HA1>(jb, s.gc + k * TR * HA1, st, cur, s);
   }
+  t_mark(p, 8);
   {
     const float* g21[2] = {p.crit[0].g21, p.crit[1].g21};
     t_ln_bwd(2, s.gc, s.v21 + 2 * TR * HA1, s.zh21 + 2 * TR * HA1, HA1, g21, s.rsn + 2 * TR * 2, 2, s.gd);
   }
-  consumer_sync();
+  tsync();
   for (int k = 0; k < 2; ++k) {
     t_store_rows(p.cw[k].du21, s.gc + k * TR * HA1, HA1, rs);
     t_store_rows(p.cw[k].dz21, s.gd + k * TR * HA1, HA1, rs);
   }
+  t_mark(p, 9);
 }
 
 // ======================================================================================================
@@ -533,7 +583,7 @@ __device__ void t_actor(const RowPhaseParams& p, const TailS& s, const TRows& rs
     s.an[TR * AMAX + r * AMAX + j] = rs.row[r] >= 0 ? ld_w(p.rp.hint + (size_t)p.bidx[rs.row[r]] * p.Ap + j) : 0.f;
   }
   mbar_wait(st.pbar, 0);                              // staged parameters have landed (the copies ran under the row loads)
-  consumer_sync();
+  tsync();
   t_actor_forward(p, s, st, cur);
   t_store_rows(p.aw.h3, s.x3, H3, rs);
   t_store_rows(p.aw.zh3, s.zh3, H3, rs);
@@ -549,7 +599,7 @@ __device__ void t_actor(const RowPhaseParams& p, const TailS& s, const TRows& rs
   const float* an_sel[NETS4] = {s.an, s.an, nullptr, nullptr};
   t_action_branches(nq, nets, an_sel, p.A, p.Ap, s, st, cur);
   t_critic_q(nq, nets, s);
-  consumer_sync();
+  tsync();
   const float wsum = p.is_wsum ? ld_act(p.is_wsum) : (float)p.B;
   const float coef = wsum / ((float)p.B * (float)p.B);           // d/dx of mean(x*w) with the (B,B) broadcast
   if (tid < TR) {
@@ -569,23 +619,23 @@ __device__ void t_actor(const RowPhaseParams& p, const TailS& s, const TRows& rs
     sc[TSC_DQ2] = g2;
     sc[TSC_GLP] = rs.row[tid] >= 0 ? p.alpha * coef : 0.f;
   }
-  consumer_sync();
+  tsync();
   // ---- back through the action branches of the critics to d loss / d action ----
   for (int e = tid; e < nq * TR * HA2; e += TL_THREADS) {
     const int rix = e / HA2, j = e - rix * HA2, k = rix / TR, r = rix - k * TR;
     s.ge[e] = s.sc[r * 16 + TSC_DQ1 + k] * ldp(p.crit[k].w3 + H2 + j);
   }
-  consumer_sync();
+  tsync();
   {
     const float *g22[2] = {p.crit[0].g22, p.crit[1].g22}, *g21[2] = {p.crit[0].g21, p.crit[1].g21};
     t_ln_bwd(nq, s.ge, s.v22, s.zh22, HA2, g22, s.rsn + 1, 2, s.gf);
-    consumer_sync();
+    tsync();
     for (int k = 0; k < nq; ++k) {
       LinJob jb{HA2, nullptr, s.gf + k * TR * HA2, nullptr};
       linear_bwd<HA1>(jb, s.gc + k * TR * HA1, st, cur, s);
     }
     t_ln_bwd(nq, s.gc, s.v21, s.zh21, HA1, g21, s.rsn, 2, s.gd);
-    consumer_sync();
+    tsync();
   }
   {   // d action[r][j] = sum_k sum_n dz21_k[r][n] * w21_k[n][j]   (one warp per (row, j), critics in fixed order)
     const int warp = tid >> 5, lane = tid & 31;
@@ -600,7 +650,7 @@ __device__ void t_actor(const RowPhaseParams& p, const TailS& s, const TRows& rs
       if (lane == 0) s.lp[r * AMAX + j] = tot;
     }
   }
-  consumer_sync();
+  tsync();
   // ---- back through the policy head ----
   if (tid < TR * p.A) {
     const int r = tid / p.A, j = tid - r * p.A;
@@ -633,7 +683,7 @@ __device__ void t_actor(const RowPhaseParams& p, const TailS& s, const TRows& rs
       if (row >= 0) p.aw.dhead[(size_t)row * p.A + j] = dz;
     }
   }
-  consumer_sync();
+  tsync();
   for (int e = tid; e < TR * H3; e += TL_THREADS) {
     const int r = e / H3, k = e - r * H3;
     float v = 0.f;
@@ -643,17 +693,17 @@ __device__ void t_actor(const RowPhaseParams& p, const TailS& s, const TRows& rs
     }
     s.ga[e] = v;
   }
-  consumer_sync();
+  tsync();
   {
     const float *g3[1] = {a.g3}, *g2[1] = {a.g2};
     t_ln_bwd(1, s.ga, s.x3, s.zh3, H3, g3, s.rsx + 2, 8, s.gb);
-    consumer_sync();
+    tsync();
     t_store_rows(p.aw.du3, s.ga, H3, rs);
     t_store_rows(p.aw.dz3, s.gb, H3, rs);
     LinJob jb{H3, nullptr, s.gb, nullptr};
     linear_bwd<H2>(jb, s.gc, st, cur, s);                            // s.gc has room for [TR][H2] (2*TR*HA1 floats)
     t_ln_bwd(1, s.gc, s.xh2, s.zh2, H2, g2, s.rsx + 3, 8, s.gd);
-    consumer_sync();
+    tsync();
     t_store_rows(p.aw.du2, s.gc, H2, rs);
     t_store_rows(p.aw.dz2, s.gd, H2, rs);
   }
@@ -732,6 +782,7 @@ __global__ void __launch_bounds__(TL_ALL, 1) k_tail(const RowPhaseParams* __rest
     n_pcopy = nc;
     pcopy_bytes = total;
   }
+  if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) g_tail_ts = (p.program == PROG_CRITIC) ? p.tstamp : nullptr;
   __syncthreads();
   pdl_wait();                     // (set-up above overlapped the previous kernel; the weights it streams were written long before)
   const Stream st{sched, n_chunks, mbars, mbars + NSLOT, s.wbuf, mbars + 2 * NSLOT};
