@@ -306,20 +306,28 @@ def run_ours(args):
     def one(i):
         j = i % 64
         agent2.store_transition(obs[j], tr2["action"][j], float(tr2["reward"][j]), obs2[j], False, tr2["hint"][j])
-        return agent2.learn(want_stats=True)
+        return agent2.learn(want_stats=mode)
 
-    for i in range(max(args.warmup, 3)):
-        one(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        one(i)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e = {"value": world * args.steps / float(tt[0]), "unit": "learn steps/s",
+    rates = {}
+    for mode in (True, "deferred"):
+        for i in range(max(args.warmup, 3)):
+            one(i)
+        barrier()
+        t0 = time.perf_counter()
+        got = 0
+        for i in range(args.steps):
+            st_ = one(i)
+            got += 1 if (st_ and st_["did_learn"]) else 0
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert got >= args.steps - 1, "every step's losses must have been read back"
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        rates[mode] = world * args.steps / float(tt[0])
+    e2e = {"value": rates["deferred"], "unit": "learn steps/s", "value_synchronous_readback": rates[True],
+           "readback": "value: want_stats='deferred' -- the losses of step n are copied to pinned memory behind its kernels and read by the call for "
+                       "step n+1 (no synchronisation; every step's losses read once); value_synchronous_readback: want_stats=True waits for each step",
            "h2d_bytes_per_step": (2 * S + 2 * A + 2) * 4 + B * 8 + 2 * B * A * 4, "d2h_bytes_per_step": 32 * 4,     # the 32-float loss / diagnostics block
            "mode": "store_transition(host obs) + learn() + loss readback through the facade, rng='reference' (host numpy/torch draws); the "
                    "transition, the PER uniforms and both noise tensors travel in ONE pinned block / host->device copy, the kernels replay "

@@ -172,6 +172,12 @@ int sc_agent_soft_update(sc_agent* a, float tau);
 int sc_agent_store_learn(sc_agent* a, const float* transition_host, int priority_mode, double priority,
                          const sc_noise* noise_or_null, sc_learn_stats* stats_host_or_null);
 
+/* Loss read-back mode of sc_agent_learn / sc_agent_store_learn when `stats_host` != NULL.  0 (default): the call waits for the
+ * step and returns ITS losses.  1: deferred -- the call queues the copy of this step's losses behind its kernels and returns the
+ * losses of the PREVIOUS step (did_learn = 0 on the first call); no synchronisation, so the host prepares step n+1 (random
+ * draws, transition packing) while the device runs step n.  Every step's losses are still read exactly once. */
+int sc_agent_set_stats_mode(sc_agent* a, int deferred);
+
 /* ---- ensembles: E independent agents (the reference's seed-ensemble axis, elasticnet/do.sh:1-6: one python process per
  *      seed) stepped in lock-step by ONE launch sequence -- every kernel of learn() runs once with blockIdx.y = agent.
  *      Agents must share the configuration (except rng_seed), device and stream; weights, replay contents and randomness

@@ -207,6 +207,10 @@ class DeviceAgent:
             return {f: getattr(s, f) for f, _ in s._fields_}
         return None
 
+    def set_stats_mode(self, deferred):
+        """deferred=True: learn(want_stats=True) returns the PREVIOUS step's losses without synchronising (sc_agent_set_stats_mode)"""
+        L.check(self.lib.sc_agent_set_stats_mode(self.h, int(bool(deferred))))
+
     def soft_update(self, tau):
         L.check(self.lib.sc_agent_soft_update(self.h, float(tau)))
 

@@ -208,7 +208,13 @@ struct sc_group {
   cudaStream_t st_copy = nullptr;
   int tk = 0;
   size_t tape_cap = 0, used = 0;
-  float *stats_dev = nullptr, *h_stats = nullptr;          // [E][32]
+  float *stats_dev = nullptr, *h_stats = nullptr;          // [E][32] (h_stats: two pinned slots of E x 32 floats)
+  // deferred read-back (sc_agent_set_stats_mode): the losses of step n are copied to a pinned slot without a synchronisation
+  // and handed out by the call for step n+1, so the host prepares the next step while the device still runs this one
+  int stats_deferred = 0, stats_slot = 0, stats_pending = 0;
+  cudaEvent_t ev_stats[2] = {nullptr, nullptr};
+  std::vector<int> pend_flags;                             // per agent: bit 0 did_learn, 1 actor_step, 2 hint_stats
+  std::vector<int32_t> pend_counter;
   std::vector<Rec> recs;
   std::map<uint64_t, GraphEntry> graphs;
   int use_graph = 1;
@@ -1786,6 +1792,7 @@ static void group_free(sc_group* g) {
   for (auto& e : g->ev_join) if (e) { cudaEventDestroy(e); e = nullptr; }
   for (auto& e : g->ev_up) if (e) { cudaEventDestroy(e); e = nullptr; }
   for (auto& e : g->ev_done) if (e) { cudaEventDestroy(e); e = nullptr; }
+  for (auto& e : g->ev_stats) if (e) { cudaEventDestroy(e); e = nullptr; }
   for (auto& h : g->tape_host) if (h) { cudaFreeHost(h); h = nullptr; }
   for (auto& d : g->tape_dev) if (d) { cudaFree(d); d = nullptr; }
   if (g->stats_dev) { cudaFree(g->stats_dev); g->stats_dev = nullptr; }
@@ -1805,6 +1812,9 @@ static int group_init(sc_group* g, sc_agent** agents, int n) {
   for (auto& e : g->ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : g->ev_up) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : g->ev_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : g->ev_stats) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  g->pend_flags.assign(n, 0);
+  g->pend_counter.assign(n, 0);
   // per agent and step: <= 2 + 7 row-phase blocks, 4 + 14 dense blocks, 12 weight-gradient blocks, the small kernels, and
   // the host arrays (3 noise tensors, B uniforms or indices, one transition)
   const sc_agent* a = agents[0];
@@ -1815,7 +1825,7 @@ static int group_init(sc_group* g, sc_agent** agents, int n) {
   for (auto& h : g->tape_host) CK(cudaHostAlloc((void**)&h, g->tape_cap, cudaHostAllocDefault));
   CK(cudaMalloc((void**)&g->stats_dev, (size_t)n * 32 * sizeof(float)));
   CK(cudaMemset(g->stats_dev, 0, (size_t)n * 32 * sizeof(float)));
-  CK(cudaHostAlloc((void**)&g->h_stats, (size_t)n * 32 * sizeof(float), cudaHostAllocDefault));
+  CK(cudaHostAlloc((void**)&g->h_stats, (size_t)2 * n * 32 * sizeof(float), cudaHostAllocDefault));
   const char* e = getenv("SMARTCAL_GRAPH");
   g->use_graph = (e && e[0] == '0') ? 0 : 1;
   return SC_OK;
@@ -1968,6 +1978,34 @@ static int group_step(sc_group* g, const StepArgs* args, sc_learn_stats* stats_h
   for (int i = 0; i < g->E; ++i) g->ag[i]->grp = g->ag[i]->own;
   if (rc) return rc;
   if ((rc = group_run(g))) return rc;
+  if (stats_host && g->stats_deferred) {
+    // hand out the PREVIOUS step's block (its copy finished long ago), then queue this step's copy behind its kernels
+    if (g->stats_pending) {
+      const int k = g->stats_slot ^ 1;
+      CK(cudaEventSynchronize(g->ev_stats[k]));
+      for (int i = 0; i < g->E; ++i) {
+        StepOut o;
+        o.did_learn = (g->pend_flags[i] & 1) != 0; o.actor_step = (g->pend_flags[i] & 2) != 0; o.hint_stats = (g->pend_flags[i] & 4) != 0;
+        if (o.did_learn) {
+          fill_stats(g->ag[i], g->h_stats + ((size_t)k * g->E + i) * 32, o, &stats_host[i]);
+          stats_host[i].learn_counter = g->pend_counter[i];
+        }
+      }
+    }
+    g->stats_pending = 0;
+    if (so[0].did_learn) {
+      const int k = g->stats_slot;
+      CK(cudaMemcpyAsync(g->h_stats + (size_t)k * g->E * 32, g->stats_dev, (size_t)g->E * 32 * sizeof(float), cudaMemcpyDeviceToHost, g->st));
+      CK(cudaEventRecord(g->ev_stats[k], g->st));
+      for (int i = 0; i < g->E; ++i) {
+        g->pend_flags[i] = (so[i].did_learn ? 1 : 0) | (so[i].actor_step ? 2 : 0) | (so[i].hint_stats ? 4 : 0);
+        g->pend_counter[i] = (int32_t)g->ag[i]->learn_counter;
+      }
+      g->stats_slot ^= 1;
+      g->stats_pending = 1;
+    }
+    return SC_OK;
+  }
   if (stats_host) {
     if (so[0].did_learn) {
       CK(cudaMemcpyAsync(g->h_stats, g->stats_dev, (size_t)g->E * 32 * sizeof(float), cudaMemcpyDeviceToHost, g->st));
@@ -1985,6 +2023,12 @@ int sc_agent_learn(sc_agent* a, const sc_noise* noise, sc_learn_stats* stats_hos
   StepArgs sa;
   sa.noise = noise;
   return group_step(a->own, &sa, stats_host);
+}
+int sc_agent_set_stats_mode(sc_agent* a, int deferred) {
+  if (!a) return fail(SC_ERR_ARG, "null agent");
+  a->own->stats_deferred = deferred != 0;
+  a->own->stats_pending = 0;
+  return SC_OK;
 }
 int sc_agent_store_learn(sc_agent* a, const float* transition_host, int priority_mode, double priority, const sc_noise* noise,
                          sc_learn_stats* stats_host) {

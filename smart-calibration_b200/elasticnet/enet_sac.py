@@ -369,10 +369,16 @@ class Agent():
         return self._dev.act(H.flat_state(observation), eps)
 
     def learn(self, want_stats=False):
+        """Agent.learn() (enet_sac.py:555-628).  want_stats=True returns this step's losses (one synchronisation);
+        want_stats='deferred' returns the PREVIOUS step's losses without synchronising, so host-side preparation of the next
+        step overlaps the device (every step's losses are still read exactly once)."""
         dev = self._dev
         if dev.n_stored < self.batch_size:
             dev.flush()
             return
+        if (want_stats == 'deferred') != getattr(self, '_deferred', False):
+            self._deferred = want_stats == 'deferred'
+            dev.set_stats_mode(self._deferred)
         B, A = self.batch_size, self.n_actions
         # the reference prints `learn_counter rho` every 100th call when hints are on (enet_sac.py:619-620): only then is a
         # read-back (and its synchronisation) needed

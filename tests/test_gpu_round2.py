@@ -320,3 +320,20 @@ def test_agent_on_non_current_device_and_scalar_properties():
         with torch.cuda.device(1):
             agent.learn()               # current device 1, agent lives on device 0
         assert torch.cuda.current_device() == 0
+
+
+def test_deferred_stats_are_the_previous_steps_losses():
+    """want_stats='deferred': no synchronisation inside learn(); the call for step n+1 returns exactly what a synchronous read of step n gives"""
+    def run(mode):
+        a = _make(81, True)
+        out = []
+        for _ in range(8):
+            out.append(a.learn(want_stats=mode))
+        a._dev.sync()
+        return out
+
+    sync, deferred = run(True), run("deferred")
+    assert deferred[0]["did_learn"] == 0
+    for n in range(7):
+        for k in ("critic_1_loss", "critic_2_loss", "actor_loss", "q1_mean", "learn_counter"):
+            assert deferred[n + 1][k] == sync[n][k], (n, k)
