@@ -209,11 +209,21 @@ typedef struct sc_calib_config {
   int32_t batch_size, mem_size, n_actions;
   int32_t M;             /* sky rows - 1: the sky tensor is (M+1) x 7 (calib_sac.py:30-36) */
   int32_t img;           /* 128 */
-  int32_t use_hint, reserved;
+  int32_t use_hint;
+  int32_t variant;       /* 0 = calibration/calib_sac.py; SC_CALIB_* flags select the demixing agents of the same network family */
   double gamma, tau, lr_actor, lr_critic, alpha;
   float hint_threshold, admm_rho;
   uint64_t rng_seed;
 } sc_calib_config;
+/* network-family variants (sc_calib_config.variant).  demixing_rl/demix_sac.py:372-527 = LOGSIGMA | DEMIX_HINT | FLAT_META;
+ * demixing_fuzzy/demix_sac.py:96-276 with use_influence=False = the same + NO_TRUNK | SIDE32. */
+enum {
+  SC_CALIB_LOGSIGMA = 1,    /* second policy head is fc22logsigma: sigma = exp(clamp(., -20, 2)) (demix_sac.py:467,492-494) instead of clamp(fc22sigma, 1e-6, 1) */
+  SC_CALIB_NO_TRUNK = 2,    /* no conv trunk / influence map (use_influence=False): features = metadata network only                                   */
+  SC_CALIB_DEMIX_HINT = 4,  /* KLD hint without clamping and dual update from a fresh no-grad sample of the updated actor (demix_sac.py:636-676)        */
+  SC_CALIB_FLAT_META = 8,   /* metadata is a flat vector of M values (demix) instead of the (M+1) x 7 sky table (calib)                                 */
+  SC_CALIB_SIDE32 = 16      /* INNER_DIM = 32 (demixing_fuzzy/demix_sac.py:13) instead of 16; MLP family only                                          */
+};
 typedef struct sc_calib sc_calib;
 
 size_t sc_calib_arena_bytes(const sc_calib_config* cfg);

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libsmartcal_b200.so")
 SC_ABI_VERSION = 2
 SC_FLAG_CRITIC_LOSS_SUM = 1   # include/smartcal_b200.h
 SC_KIND_SAC, SC_KIND_TD3 = 0, 1
+SC_CALIB_LOGSIGMA, SC_CALIB_NO_TRUNK, SC_CALIB_DEMIX_HINT, SC_CALIB_FLAT_META, SC_CALIB_SIDE32 = 1, 2, 4, 8, 16
 NET_ACTOR, NET_CRITIC_1, NET_CRITIC_2, NET_TARGET_CRITIC_1, NET_TARGET_CRITIC_2, NET_TARGET_ACTOR = range(6)
 SLOT_PARAM, SLOT_ADAM_M, SLOT_ADAM_V = 0, 1, 2
 
@@ -49,7 +50,7 @@ class ScNoise(C.Structure):
 
 class ScCalibConfig(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("batch_size", C.c_int32), ("mem_size", C.c_int32), ("n_actions", C.c_int32),
-                ("M", C.c_int32), ("img", C.c_int32), ("use_hint", C.c_int32), ("reserved", C.c_int32),
+                ("M", C.c_int32), ("img", C.c_int32), ("use_hint", C.c_int32), ("variant", C.c_int32),
                 ("gamma", C.c_double), ("tau", C.c_double), ("lr_actor", C.c_double), ("lr_critic", C.c_double), ("alpha", C.c_double),
                 ("hint_threshold", C.c_float), ("admm_rho", C.c_float), ("rng_seed", C.c_uint64)]
 

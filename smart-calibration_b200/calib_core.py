@@ -12,14 +12,14 @@ _DT = {(4, 0): torch.float32, (4, 1): torch.int32, (8, 1): torch.int64, (8, 0): 
 
 class CalibDevice:
     def __init__(self, batch_size, mem_size, n_actions, M, gamma, tau, lr_actor, lr_critic, alpha, use_hint=False, hint_threshold=0.1,
-                 admm_rho=1.0, img=128, rng_seed=0, device=None):
+                 admm_rho=1.0, img=128, rng_seed=0, device=None, variant=0):
         self.lib = L.load()
         if not torch.cuda.is_available():
             raise L.SmartcalError("no CUDA device visible: smart-calibration_b200 has no CPU fallback")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.B, self.C, self.A, self.M, self.img = int(batch_size), int(mem_size), int(n_actions), int(M), int(img)
         cfg = L.ScCalibConfig(abi_version=L.SC_ABI_VERSION, batch_size=self.B, mem_size=self.C, n_actions=self.A, M=self.M, img=self.img,
-                              use_hint=int(bool(use_hint)), gamma=float(gamma), tau=float(tau), lr_actor=float(lr_actor),
+                              use_hint=int(bool(use_hint)), variant=int(variant), gamma=float(gamma), tau=float(tau), lr_actor=float(lr_actor),
                               lr_critic=float(lr_critic), alpha=float(alpha), hint_threshold=float(hint_threshold),
                               admm_rho=float(admm_rho), rng_seed=int(rng_seed))
         self.cfg = cfg
@@ -80,7 +80,7 @@ class CalibDevice:
         return np.ascontiguousarray(np.asarray(x, dtype=np.float32).reshape(-1))
 
     def store(self, img, sky, action, reward, img2, sky2, done, hint):
-        arrs = [self._f32(v) for v in (img, sky, img2, sky2, action, hint)]
+        arrs = [None if v is None else self._f32(v) for v in (img, sky, img2, sky2, action, hint)]     # (img / img2 None: MLP family)
         L.check(self.lib.sc_calib_store_host(self.h, *[L.ptr(v) for v in arrs], float(reward), int(bool(done))))
 
     def set_batch(self, idx):
@@ -88,23 +88,22 @@ class CalibDevice:
         L.check(self.lib.sc_calib_set_batch_host(self.h, L.ptr(idx), idx.size))
 
     def act(self, img, sky, eps=None):
-        img, sky = self._f32(img), self._f32(sky)
+        img, sky = (None if img is None else self._f32(img)), self._f32(sky)
         e = None if eps is None else self._f32(eps)
         out = np.empty(self.A, np.float32)
         L.check(self.lib.sc_calib_act(self.h, L.ptr(img), L.ptr(sky), L.ptr(e), L.ptr(out)))
         return out
 
-    def learn(self, eps_next=None, eps_cur=None, want_stats=False):
+    def learn(self, eps_next=None, eps_cur=None, want_stats=False, eps_dual=None):
         n = self._noise
         keep = []
-        for f, v in (("eps_next_host", eps_next), ("eps_cur_host", eps_cur)):
+        for f, v in (("eps_next_host", eps_next), ("eps_cur_host", eps_cur), ("eps_dual_host", eps_dual)):
             if v is None:
                 setattr(n, f, None)
             else:
                 arr = self._f32(v)
                 keep.append(arr)
                 setattr(n, f, arr.ctypes.data)
-        n.eps_dual_host = None
         if want_stats:
             L.check(self.lib.sc_calib_learn(self.h, C.byref(n), C.byref(self._stats)))
             s = self._stats

@@ -47,7 +47,8 @@ constexpr int C1 = 16, C2 = 32, C3 = 32;
 constexpr int FLAT = C3 * H3C * H3C;      // 5408
 constexpr int FEAT = FLAT + 16;           // 5424
 constexpr int HID = 128, SIDE = 16;
-constexpr int AMAXC = 64;                 // max n_actions
+constexpr int AMAXC = 128;                // max n_actions (demixing_fuzzy: 24 (K-1) + 8 = 128)
+constexpr int SIDEMAX = 32;               // INNER_DIM of demixing_fuzzy (16 for calibration / demixing_rl)
 
 // =====================================================================================================================
 // small per-row kernels (one block per batch row unless noted)
@@ -65,7 +66,7 @@ __global__ void k_gather(const float* __restrict__ src, const int* __restrict__ 
 __global__ void __launch_bounds__(128) k_side_fwd(const float* __restrict__ sky, int SKY, const float* __restrict__ act, int A,
                                                   const float* __restrict__ wa, const float* __restrict__ ba, const float* __restrict__ wb,
                                                   const float* __restrict__ bb, float* __restrict__ x1, float* __restrict__ h1,
-                                                  float* __restrict__ o16, float* __restrict__ feat) {
+                                                  float* __restrict__ o16, float* __restrict__ feat, int side, int feat_ld, int flat) {
   __shared__ float sx[192];
   __shared__ float sh[HID];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -85,23 +86,23 @@ __global__ void __launch_bounds__(128) k_side_fwd(const float* __restrict__ sky,
     h1[(size_t)b * HID + tid] = s;
   }
   __syncthreads();
-  if (tid < SIDE) {
+  if (tid < side) {
     const float* w = wb + (size_t)tid * HID;
     float s = bb[tid];
     for (int i = 0; i < HID; ++i) s = fmaf(w[i], sh[i], s);
     s = fmaxf(s, 0.f);
-    o16[(size_t)b * SIDE + tid] = s;
-    feat[(size_t)b * FEAT + FLAT + tid] = s;
+    o16[(size_t)b * side + tid] = s;
+    feat[(size_t)b * feat_ld + flat + tid] = s;
   }
 }
 
 // q[b] = head_w . feat[b] + head_b
 __global__ void __launch_bounds__(256) k_critic_head(const float* __restrict__ feat, const float* __restrict__ hw, const float* __restrict__ hb,
-                                                     float* __restrict__ q) {
+                                                     float* __restrict__ q, int feat_ld) {
   __shared__ float sh[8];
   const int b = blockIdx.x;
   float s = 0.f;
-  for (int i = threadIdx.x; i < FEAT; i += 256) s = fmaf(feat[(size_t)b * FEAT + i], hw[i], s);
+  for (int i = threadIdx.x; i < feat_ld; i += 256) s = fmaf(feat[(size_t)b * feat_ld + i], hw[i], s);
   s = block_sum_float(s, sh);
   if (threadIdx.x == 0) q[b] = s + hb[0];
 }
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(256) k_critic_head(const float* __restrict__ f
 __global__ void __launch_bounds__(128) k_actor_head(const float* __restrict__ x21, const float* __restrict__ wmu, const float* __restrict__ bmu,
                                                     const float* __restrict__ wsg, const float* __restrict__ bsg, const float* __restrict__ eps,
                                                     int A, float* __restrict__ act, float* __restrict__ sig, float* __restrict__ raw,
-                                                    float* __restrict__ logp, float* __restrict__ mu_out, float* __restrict__ u_out) {
+                                                    float* __restrict__ logp, float* __restrict__ mu_out, float* __restrict__ u_out, int sigma_mode) {
   __shared__ float sx[HID];
   __shared__ float slp[AMAXC];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -124,7 +125,8 @@ __global__ void __launch_bounds__(128) k_actor_head(const float* __restrict__ x2
       m = fmaf(w1[i], sx[i], m);
       r = fmaf(w2[i], sx[i], r);
     }
-    const float s = fminf(fmaxf(r, 1e-6f), 1.f);
+    // sigma_mode 0: sigma = clamp(raw, 1e-6, 1) (calib_sac.py:201-203); 1: sigma = exp(clamp(raw, -20, 2)) (demix_sac.py fc22logsigma)
+    const float s = sigma_mode == 0 ? fminf(fmaxf(r, 1e-6f), 1.f) : expf(fminf(fmaxf(r, -20.f), 2.f));
     const float e = eps[(size_t)b * A + tid];
     const float u = __fadd_rn(m, __fmul_rn(e, s));
     const float a = tanhf(u);
@@ -184,20 +186,19 @@ __global__ void k_outer(const float* __restrict__ dq, const float* __restrict__ 
 __global__ void __launch_bounds__(128) k_side_bwd(const float* __restrict__ dfeat_side, long ld_dfeat, const float* __restrict__ o16,
                                                   const float* __restrict__ h1, const float* __restrict__ wb, const float* __restrict__ wa, int K1,
                                                   int SKY, int A, float* __restrict__ d16, float* __restrict__ dh1, float* __restrict__ dact,
-                                                  int accumulate) {
-  __shared__ float sd[SIDE];
+                                                  int accumulate, int side) {
+  __shared__ float sd[SIDEMAX];
   __shared__ float sdh[HID];
   const int b = blockIdx.x, tid = threadIdx.x;
-  if (tid < SIDE) {
-    const float v = o16[(size_t)b * SIDE + tid] > 0.f ? dfeat_side[(size_t)b * ld_dfeat + tid] : 0.f;
+  if (tid < side) {
+    const float v = o16[(size_t)b * side + tid] > 0.f ? dfeat_side[(size_t)b * ld_dfeat + tid] : 0.f;
     sd[tid] = v;
-    d16[(size_t)b * SIDE + tid] = v;
+    d16[(size_t)b * side + tid] = v;
   }
   __syncthreads();
   {
     float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < SIDE; ++k) s = fmaf(sd[k], wb[(size_t)k * HID + tid], s);
+    for (int k = 0; k < side; ++k) s = fmaf(sd[k], wb[(size_t)k * HID + tid], s);
     s = h1[(size_t)b * HID + tid] > 0.f ? s : 0.f;
     sdh[tid] = s;
     dh1[(size_t)b * HID + tid] = s;
@@ -212,7 +213,8 @@ __global__ void __launch_bounds__(128) k_side_bwd(const float* __restrict__ dfea
 
 // actor loss seeds (calib_sac.py:344,355): L = mean(alpha*logp - min(q1,q2)); dq_k = -(1/B) [k attains the min] (halves on ties);
 // dfeat_side_k[b][j] = dq_k[b] * head_w_k[5408 + j]; qmin for the loss readout
-__global__ void k_actor_seed(const float* q1, const float* q2, const float* hw1, const float* hw2, int B, float* ds1, float* ds2, float* qmin) {
+__global__ void k_actor_seed(const float* q1, const float* q2, const float* hw1, const float* hw2, int B, float* ds1, float* ds2, float* qmin, int side,
+                             int flat) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float a = q1[b], c = q2[b];
@@ -220,22 +222,23 @@ __global__ void k_actor_seed(const float* q1, const float* q2, const float* hw1,
   float g1 = 0.f, g2 = 0.f;
   if (a < c) g1 = -w; else if (c < a) g2 = -w; else { g1 = -0.5f * w; g2 = -0.5f * w; }
   qmin[b] = fminf(a, c);
-  for (int j = 0; j < SIDE; ++j) {
-    ds1[(size_t)b * SIDE + j] = g1 * hw1[FLAT + j];
-    ds2[(size_t)b * SIDE + j] = g2 * hw2[FLAT + j];
+  for (int j = 0; j < side; ++j) {
+    ds1[(size_t)b * side + j] = g1 * hw1[flat + j];
+    ds2[(size_t)b * side + j] = g2 * hw2[flat + j];
   }
 }
 
 // hint penalty (calib_sac.py:345-365): kld = h_m (log h_m - log a_m), a_m = clamp(0.5 a + 0.5 + EPS, EPS, 1) (same for h);
 // g = max(0, mean(kld) - thr)^2.  out[0] = d(0.5 admm_rho g^2 + rho g)/d mean(kld) / (B A), out[1] = g, out[2] = penalty value;
 // rho_update (every 10th learn): rho += admm_rho * g.   One block.
+// kld_mode 1 (demix_sac.py kld_loss): no clamp of the mapped values
 __global__ void __launch_bounds__(256) k_kld_coef(const float* __restrict__ act, const float* __restrict__ hint, int n, float thr, float admm_rho,
-                                                  float* rho, float* out, int do_rho_update) {
+                                                  float* rho, float* out, int do_rho_update, int kld_mode) {
   __shared__ float sh[8];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += 256) {
-    const float am = fminf(fmaxf(0.5f * act[i] + 0.5f + 1e-6f, 1e-6f), 1.f);
-    const float hm = fminf(fmaxf(0.5f * hint[i] + 0.5f + 1e-6f, 1e-6f), 1.f);
+    float am = 0.5f * act[i] + 0.5f + 1e-6f, hm = 0.5f * hint[i] + 0.5f + 1e-6f;
+    if (kld_mode == 0) { am = fminf(fmaxf(am, 1e-6f), 1.f); hm = fminf(fmaxf(hm, 1e-6f), 1.f); }
     s += hm * (logf(hm) - logf(am));
   }
   s = block_sum_float(s, sh);
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(128) k_actor_head_bwd(const float* __restrict_
                                                         const float* __restrict__ uu, const float* __restrict__ hint,
                                                         const float* __restrict__ hint_coef, float glp, int A, const float* __restrict__ wmu,
                                                         const float* __restrict__ wsg, const float* __restrict__ x21, float* __restrict__ dmu,
-                                                        float* __restrict__ draw, float* __restrict__ dpre) {
+                                                        float* __restrict__ draw, float* __restrict__ dpre, int sigma_mode, int kld_mode) {
   __shared__ float sm[AMAXC], sr[AMAXC];
   const int b = blockIdx.x, tid = threadIdx.x;
   if (tid < A) {
@@ -273,9 +276,13 @@ __global__ void __launch_bounds__(128) k_actor_head_bwd(const float* __restrict_
     float g = da[o];
     if (hint_coef != nullptr) {
       const float arg = 0.5f * a + 0.5f + 1e-6f;
-      const float am = fminf(fmaxf(arg, 1e-6f), 1.f);
-      const float hm = fminf(fmaxf(0.5f * hint[o] + 0.5f + 1e-6f, 1e-6f), 1.f);
-      if (arg >= 1e-6f && arg <= 1.f) g += hint_coef[0] * (-hm / am) * 0.5f;
+      if (kld_mode == 0) {
+        const float am = fminf(fmaxf(arg, 1e-6f), 1.f);
+        const float hm = fminf(fmaxf(0.5f * hint[o] + 0.5f + 1e-6f, 1e-6f), 1.f);
+        if (arg >= 1e-6f && arg <= 1.f) g += hint_coef[0] * (-hm / am) * 0.5f;
+      } else {
+        g += hint_coef[0] * (-(0.5f * hint[o] + 0.5f + 1e-6f) / arg) * 0.5f;
+      }
     }
     const float omt = __fsub_rn(1.f, __fmul_rn(a, a));
     g += glp * (2.f * a / (omt + 1e-6f));                      // d(-glp log(1 - a^2 + 1e-6))/da
@@ -295,7 +302,8 @@ __global__ void __launch_bounds__(128) k_actor_head_bwd(const float* __restrict_
     const float g3 = __fdiv_rn(-glp, s);
     const float g1 = __fmul_rn(gu, e);
     const float ds = __fadd_rn(__fadd_rn(g3, g2), g1);
-    const float dr = (r >= 1e-6f && r <= 1.f) ? ds : 0.f;
+    // sigma_mode 1: sigma = exp(clamp(raw, -20, 2)): exp backward multiplies by its output, the clamp masks
+    const float dr = sigma_mode == 0 ? ((r >= 1e-6f && r <= 1.f) ? ds : 0.f) : ((r >= -20.f && r <= 2.f) ? __fmul_rn(ds, s) : 0.f);
     sm[tid] = du;
     sr[tid] = dr;
     dmu[o] = du;
@@ -354,6 +362,11 @@ struct PiSide { float *x1, *h1, *o16; };
 struct sc_calib {
   sc_calib_config cfg;
   int B, C, A, M, SKY, K1C;           // K1C: critic side input width (sky + action)
+  // network family (sc_calib_config.variant): calibration (calib_sac.py), demixing_rl (demix_sac.py) or demixing_fuzzy MLP
+  bool trunk;                         // conv trunk present (use_influence); false: pure MLP, features = side network only
+  int side, flat, feat;               // side-network width (INNER_DIM), flattened trunk width (0 without trunk), feat = flat + side
+  int sigma_mode, kld_mode;           // 0 calibration, 1 demixing (log-sigma heads; unclamped KLD + resampled dual update)
+  float *eps_dual;
   cudaStream_t st;
   bool own_arena;
   char* arena;
@@ -394,26 +407,29 @@ struct sc_calib {
   std::map<std::string, sc_tensor_info> reg;
 };
 
-static CLayout critic_layout_c(int K1) {
-  CLayout L;
+static void add_trunk(CLayout& L) {
   L.add("conv1.weight", C1, 1 * TAPS); L.add("conv1.bias", 1, C1); L.add("bn1.weight", 1, C1); L.add("bn1.bias", 1, C1);
   L.add("conv2.weight", C2, C1 * TAPS); L.add("conv2.bias", 1, C2); L.add("bn2.weight", 1, C2); L.add("bn2.bias", 1, C2);
   L.add("conv3.weight", C3, C2 * TAPS); L.add("conv3.bias", 1, C3); L.add("bn3.weight", 1, C3); L.add("bn3.bias", 1, C3);
+}
+static CLayout critic_layout_c(int K1, bool trunk, int side, int feat) {
+  CLayout L;
+  if (trunk) add_trunk(L);
   L.add("fc1.weight", HID, K1); L.add("fc1.bias", 1, HID);
-  L.add("fc2.weight", SIDE, HID); L.add("fc2.bias", 1, SIDE);
-  L.add("head.weight", 1, FEAT); L.add("head.bias", 1, 1);
+  L.add("fc2.weight", side, HID); L.add("fc2.bias", 1, side);
+  L.add("head.weight", 1, feat); L.add("head.bias", 1, 1);
   return L;
 }
-static CLayout actor_layout_c(int SKY, int A) {
+static CLayout actor_layout_c(int SKY, int A, bool trunk, int side, int feat, int sigma_mode) {
   CLayout L;
-  L.add("conv1.weight", C1, 1 * TAPS); L.add("conv1.bias", 1, C1); L.add("bn1.weight", 1, C1); L.add("bn1.bias", 1, C1);
-  L.add("conv2.weight", C2, C1 * TAPS); L.add("conv2.bias", 1, C2); L.add("bn2.weight", 1, C2); L.add("bn2.bias", 1, C2);
-  L.add("conv3.weight", C3, C2 * TAPS); L.add("conv3.bias", 1, C3); L.add("bn3.weight", 1, C3); L.add("bn3.bias", 1, C3);
+  if (trunk) add_trunk(L);
   L.add("fc11.weight", HID, SKY); L.add("fc11.bias", 1, HID);
-  L.add("fc12.weight", SIDE, HID); L.add("fc12.bias", 1, SIDE);
-  L.add("fc21.weight", HID, FEAT); L.add("fc21.bias", 1, HID);
+  L.add("fc12.weight", side, HID); L.add("fc12.bias", 1, side);
+  L.add("fc21.weight", HID, feat); L.add("fc21.bias", 1, HID);
   L.add("fc22mu.weight", A, HID); L.add("fc22mu.bias", 1, A);
-  L.add("fc22sigma.weight", A, HID); L.add("fc22sigma.bias", 1, A);
+  // calib_sac.py:185 names the second head fc22sigma, demix_sac.py:467 fc22logsigma
+  if (sigma_mode == 0) { L.add("fc22sigma.weight", A, HID); L.add("fc22sigma.bias", 1, A); }
+  else { L.add("fc22logsigma.weight", A, HID); L.add("fc22logsigma.bias", 1, A); }
   return L;
 }
 static NetP net_ptrs(float* b, const CLayout& L, bool actor) {
@@ -423,13 +439,15 @@ static NetP net_ptrs(float* b, const CLayout& L, bool actor) {
   const char* cb[3] = {"conv1.bias", "conv2.bias", "conv3.bias"};
   const char* g[3] = {"bn1.weight", "bn2.weight", "bn3.weight"};
   const char* be[3] = {"bn1.bias", "bn2.bias", "bn3.bias"};
-  for (int l = 0; l < 3; ++l) { p.cw[l] = b + L.off(cw[l]); p.cb[l] = b + L.off(cb[l]); p.g[l] = b + L.off(g[l]); p.be[l] = b + L.off(be[l]); }
+  if (L.off(cw[0]) != (size_t)-1)
+    for (int l = 0; l < 3; ++l) { p.cw[l] = b + L.off(cw[l]); p.cb[l] = b + L.off(cb[l]); p.g[l] = b + L.off(g[l]); p.be[l] = b + L.off(be[l]); }
   if (actor) {
     p.fa_w = b + L.off("fc11.weight"); p.fa_b = b + L.off("fc11.bias");
     p.fb_w = b + L.off("fc12.weight"); p.fb_b = b + L.off("fc12.bias");
     p.h_w = b + L.off("fc21.weight"); p.h_b = b + L.off("fc21.bias");
     p.mu_w = b + L.off("fc22mu.weight"); p.mu_b = b + L.off("fc22mu.bias");
-    p.sg_w = b + L.off("fc22sigma.weight"); p.sg_b = b + L.off("fc22sigma.bias");
+    const bool logsig = L.off("fc22sigma.weight") == (size_t)-1;
+    p.sg_w = b + L.off(logsig ? "fc22logsigma.weight" : "fc22sigma.weight"); p.sg_b = b + L.off(logsig ? "fc22logsigma.bias" : "fc22sigma.bias");
   } else {
     p.fa_w = b + L.off("fc1.weight"); p.fa_b = b + L.off("fc1.bias");
     p.fb_w = b + L.off("fc2.weight"); p.fb_b = b + L.off("fc2.bias");
@@ -455,58 +473,72 @@ static size_t carve_c(sc_calib* a, char* base) {
   a->params = cv.f(a->n_params); a->grads = cv.f(a->n_params); a->adam_m = cv.f(a->n_params); a->adam_v = cv.f(a->n_params);
   a->targets = cv.f(2 * a->Lc.size);
   for (int n = 0; n < 5; ++n) { a->bnbuf[n] = cv.f(160); a->nbt[n] = (long long*)cv.take(4 * sizeof(long long)); }
-  a->r_img = cv.f(C * IMG * IMG); a->r_img2 = cv.f(C * IMG * IMG);
+  const size_t NIMG = a->trunk ? (size_t)IMG * IMG : 0;       // no influence maps without the conv trunk
+  const size_t FEATR = a->feat, SIDER = a->side;
+  a->r_img = cv.f(C * NIMG); a->r_img2 = cv.f(C * NIMG);
   a->r_sky = cv.f(C * SKY); a->r_sky2 = cv.f(C * SKY); a->r_act = cv.f(C * A); a->r_hint = cv.f(C * A); a->r_rew = cv.f(C); a->r_done = cv.f(C);
-  reg("state_memory_img", a->r_img, C, IMG * IMG); reg("new_state_memory_img", a->r_img2, C, IMG * IMG);
+  if (a->trunk) { reg("state_memory_img", a->r_img, C, IMG * IMG); reg("new_state_memory_img", a->r_img2, C, IMG * IMG); }
   reg("state_memory_sky", a->r_sky, C, SKY); reg("new_state_memory_sky", a->r_sky2, C, SKY);
   reg("action_memory", a->r_act, C, A); reg("hint_memory", a->r_hint, C, A); reg("reward_memory", a->r_rew, C, 1); reg("terminal_memory", a->r_done, C, 1);
   a->bidx = (int*)cv.take(B * sizeof(int)); reg("batch_idx", a->bidx, B, 1, 4, 1);
-  a->mb_img = cv.f(B * IMG * IMG); a->mb_img2 = cv.f(B * IMG * IMG); a->mb_sky = cv.f(B * SKY); a->mb_sky2 = cv.f(B * SKY);
+  a->mb_img = cv.f(B * NIMG); a->mb_img2 = cv.f(B * NIMG); a->mb_sky = cv.f(B * SKY); a->mb_sky2 = cv.f(B * SKY);
   a->mb_act = cv.f(B * A); a->mb_hint = cv.f(B * A); a->mb_rew = cv.f(B); a->mb_done = cv.f(B);
   a->eps_next = cv.f(B * A); a->eps_cur = cv.f(B * A); reg("eps_next", a->eps_next, B, A); reg("eps_cur", a->eps_cur, B, A);
+  a->eps_dual = cv.f(B * A);
   for (int w = 0; w < 4; ++w) {
     TrunkWs& t = a->ws[w];
-    t.z[0] = cv.f(B * C1 * H1C * H1C); t.a[0] = cv.f(B * C1 * H1C * H1C);
-    t.z[1] = cv.f(B * C2 * H2C * H2C); t.a[1] = cv.f(B * C2 * H2C * H2C);
-    t.z[2] = cv.f(B * C3 * H3C * H3C);
-    t.feat = cv.f(B * FEAT); t.a[2] = t.feat;
+    const size_t TB = a->trunk ? B : 0;
+    t.z[0] = cv.f(TB * C1 * H1C * H1C); t.a[0] = cv.f(TB * C1 * H1C * H1C);
+    t.z[1] = cv.f(TB * C2 * H2C * H2C); t.a[1] = cv.f(TB * C2 * H2C * H2C);
+    t.z[2] = cv.f(TB * C3 * H3C * H3C);
+    t.feat = cv.f(B * FEATR); t.a[2] = t.feat;
     for (int l = 0; l < 3; ++l) { t.mean[l] = cv.f(32); t.rstd[l] = cv.f(32); t.scale[l] = cv.f(32); t.shift[l] = cv.f(32); }
-    t.x1 = cv.f(B * (SKY + A)); t.h1 = cv.f(B * HID); t.o16 = cv.f(B * SIDE);
+    t.x1 = cv.f(B * (SKY + A)); t.h1 = cv.f(B * HID); t.o16 = cv.f(B * SIDER);
   }
-  for (int k = 0; k < 2; ++k) { a->pside[k].x1 = cv.f(B * (SKY + A)); a->pside[k].h1 = cv.f(B * HID); a->pside[k].o16 = cv.f(B * SIDE); }
+  for (int k = 0; k < 2; ++k) { a->pside[k].x1 = cv.f(B * (SKY + A)); a->pside[k].h1 = cv.f(B * HID); a->pside[k].o16 = cv.f(B * SIDER); }
   a->x21 = cv.f(B * HID); a->pre21 = cv.f(B * HID);
   a->a2 = cv.f(B * A); a->sig2 = cv.f(B * A); a->raw2 = cv.f(B * A); a->logp2 = cv.f(B);
   a->pi = cv.f(B * A); a->sig = cv.f(B * A); a->raw = cv.f(B * A); a->logp = cv.f(B); a->mu = cv.f(B * A); a->u = cv.f(B * A);
   reg("pi", a->pi, B, A); reg("logp", a->logp, B, 1); reg("sigma", a->sig, B, A);
-  for (int k = 0; k < 2; ++k) { a->qt[k] = cv.f(B); a->q[k] = cv.f(B); a->qpi[k] = cv.f(B); a->ds[k] = cv.f(B * SIDE); }
+  for (int k = 0; k < 2; ++k) { a->qt[k] = cv.f(B); a->q[k] = cv.f(B); a->qpi[k] = cv.f(B); a->ds[k] = cv.f(B * SIDER); }
   a->y = cv.f(B); a->dq = cv.f(B); a->qmin = cv.f(B);
   reg("y", a->y, B, 1); reg("q1", a->q[0], B, 1); reg("q2", a->q[1], B, 1); reg("q1_pi", a->qpi[0], B, 1); reg("q2_pi", a->qpi[1], B, 1);
-  a->dfeat = cv.f(B * FEAT); a->dz3 = cv.f(B * C3 * H3C * H3C); a->dA2 = cv.f(B * C2 * H2C * H2C); a->dA1 = cv.f(B * C1 * H1C * H1C);
-  a->d16 = cv.f(B * SIDE); a->dh1 = cv.f(B * HID); a->dact = cv.f(B * A); reg("d_pi", a->dact, B, A); a->dmu = cv.f(B * A); a->draw = cv.f(B * A); reg("d_mu", a->dmu, B, A); reg("d_sigma_raw", a->draw, B, A); a->dpre = cv.f(B * HID);
+  const size_t TB2 = a->trunk ? B : 0;
+  a->dfeat = cv.f(B * FEATR); a->dz3 = cv.f(TB2 * C3 * H3C * H3C); a->dA2 = cv.f(TB2 * C2 * H2C * H2C); a->dA1 = cv.f(TB2 * C1 * H1C * H1C);
+  a->d16 = cv.f(B * SIDER); a->dh1 = cv.f(B * HID); a->dact = cv.f(B * A); reg("d_pi", a->dact, B, A); a->dmu = cv.f(B * A); a->draw = cv.f(B * A); reg("d_mu", a->dmu, B, A); reg("d_sigma_raw", a->draw, B, A); a->dpre = cv.f(B * HID);
   a->bn_c1 = cv.f(32); a->bn_c2 = cv.f(32);
   a->red_partial = (double*)cv.take(sizeof(double) * 32 * 64 * 2);
-  a->wg_partial = cv.f((size_t)a->wg_blocks * C3 * C2 * TAPS);
+  a->wg_partial = cv.f(a->trunk ? (size_t)a->wg_blocks * C3 * C2 * TAPS : 4);
   a->splitk = cv.f((size_t)32 * B * HID);
-  a->stats = cv.f(16); a->rho = cv.f(4); a->hint_out = cv.f(4);
+  a->stats = cv.f(16); a->rho = cv.f(4); a->hint_out = cv.f(8);
   return cv.off;
 }
 
 static int check_cfg_c(const sc_calib_config* c) {
   if (!c) return failc(SC_ERR_ARG, "null config");
   if (c->abi_version != SC_ABI_VERSION) return failc(SC_ERR_ARG, "ABI version mismatch");
-  if (c->img != IMG) return failc(SC_ERR_ARG, "only input_dims = [1,128,128] is built (calibration/main_sac.py:17)");
+  const bool trunk = !(c->variant & SC_CALIB_NO_TRUNK);
+  if (trunk && c->img != IMG) return failc(SC_ERR_ARG, "only input_dims = [1,128,128] is built (calibration/main_sac.py:17)");
+  if (trunk && (c->variant & SC_CALIB_SIDE32)) return failc(SC_ERR_UNSUPPORTED, "INNER_DIM = 32 is built for the MLP (use_influence=False) family only");
   if (c->batch_size < 2 || c->mem_size < c->batch_size) return failc(SC_ERR_ARG, "need 2 <= batch_size <= mem_size");
-  if (c->n_actions < 1 || c->n_actions > AMAXC || c->M < 1 || 7 * (c->M + 1) + c->n_actions > 192)
-    return failc(SC_ERR_ARG, "n_actions must be in [1,%d] and 7(M+1)+n_actions <= 192", AMAXC);
+  const int sky = (c->variant & SC_CALIB_FLAT_META) ? c->M : 7 * (c->M + 1);
+  if (c->n_actions < 1 || c->n_actions > AMAXC || c->M < 1 || sky + c->n_actions > 192)
+    return failc(SC_ERR_ARG, "n_actions must be in [1,%d] and metadata width + n_actions <= 192", AMAXC);
   return SC_OK;
 }
 static void init_dims_c(sc_calib* a, const sc_calib_config* c) {
   a->cfg = *c;
   a->B = c->batch_size; a->C = c->mem_size; a->A = c->n_actions; a->M = c->M;
-  a->SKY = 7 * (c->M + 1);
+  a->trunk = !(c->variant & SC_CALIB_NO_TRUNK);
+  a->side = (c->variant & SC_CALIB_SIDE32) ? 32 : SIDE;
+  a->flat = a->trunk ? FLAT : 0;
+  a->feat = a->flat + a->side;
+  a->sigma_mode = (c->variant & SC_CALIB_LOGSIGMA) ? 1 : 0;
+  a->kld_mode = (c->variant & SC_CALIB_DEMIX_HINT) ? 1 : 0;
+  a->SKY = (c->variant & SC_CALIB_FLAT_META) ? c->M : 7 * (c->M + 1);
   a->K1C = a->SKY + a->A;
-  a->La = actor_layout_c(a->SKY, a->A);
-  a->Lc = critic_layout_c(a->K1C);
+  a->La = actor_layout_c(a->SKY, a->A, a->trunk, a->side, a->feat, a->sigma_mode);
+  a->Lc = critic_layout_c(a->K1C, a->trunk, a->side, a->feat);
   a->wg_blocks = 296;
   a->nch = a->B < 32 ? a->B : 32;
 }
@@ -652,8 +684,8 @@ static int trunk_backward(sc_calib* a, TrunkWs& t, const NetP& P, const NetP& G,
 // side network weight gradients from d16 [B][16], dh1 [B][128], activations h1 and x1 [B][K1]
 static int side_wgrads(sc_calib* a, const float* x1, const float* h1, int K1, const NetP& G) {
   int rc;
-  if ((rc = sgemm(a, a->d16, 1, SIDE, h1, HID, 1, G.fb_w, HID, SIDE, HID, a->B, nullptr, -1))) return rc;
-  if ((rc = colsum(a, a->d16, SIDE, nullptr, a->B, SIDE, G.fb_b))) return rc;
+  if ((rc = sgemm(a, a->d16, 1, a->side, h1, HID, 1, G.fb_w, HID, a->side, HID, a->B, nullptr, -1))) return rc;
+  if ((rc = colsum(a, a->d16, a->side, nullptr, a->B, a->side, G.fb_b))) return rc;
   if ((rc = sgemm(a, a->dh1, 1, HID, x1, K1, 1, G.fa_w, K1, HID, K1, a->B, nullptr, -1))) return rc;
   return colsum(a, a->dh1, HID, nullptr, a->B, HID, G.fa_b);
 }
@@ -807,18 +839,20 @@ int sc_calib_set_scalars(sc_calib* a, float rho, float admm_rho) {
 
 int sc_calib_store_host(sc_calib* a, const float* img, const float* sky, const float* img2, const float* sky2, const float* action,
                         const float* hint, float reward, int done) {
-  if (!a || !img || !sky || !img2 || !sky2 || !action || !hint) return failc(SC_ERR_ARG, "null argument");
-  const size_t slot = (size_t)(a->mem_cntr % a->C), NI = (size_t)IMG * IMG;
+  if (!a || !sky || !sky2 || !action || !hint || (a->trunk && (!img || !img2))) return failc(SC_ERR_ARG, "null argument");
+  const size_t slot = (size_t)(a->mem_cntr % a->C), NI = a->trunk ? (size_t)IMG * IMG : 0;       // (no influence maps in the MLP family)
   CKC(cudaStreamSynchronize(a->st));                      // the staging buffer may still be in flight
   float* h = a->h_stage;
-  memcpy(h, img, NI * 4); memcpy(h + NI, img2, NI * 4);
+  if (NI) { memcpy(h, img, NI * 4); memcpy(h + NI, img2, NI * 4); }
   float* s = h + 2 * NI;
   memcpy(s, sky, a->SKY * 4); memcpy(s + a->SKY, sky2, a->SKY * 4);
   float* t = s + 2 * a->SKY;
   memcpy(t, action, a->A * 4); memcpy(t + a->A, hint, a->A * 4);
   t[2 * a->A] = reward; t[2 * a->A + 1] = done ? 1.f : 0.f;
-  CKC(cudaMemcpyAsync(a->r_img + slot * NI, h, NI * 4, cudaMemcpyHostToDevice, a->st));
-  CKC(cudaMemcpyAsync(a->r_img2 + slot * NI, h + NI, NI * 4, cudaMemcpyHostToDevice, a->st));
+  if (NI) {
+    CKC(cudaMemcpyAsync(a->r_img + slot * NI, h, NI * 4, cudaMemcpyHostToDevice, a->st));
+    CKC(cudaMemcpyAsync(a->r_img2 + slot * NI, h + NI, NI * 4, cudaMemcpyHostToDevice, a->st));
+  }
   CKC(cudaMemcpyAsync(a->r_sky + slot * a->SKY, s, a->SKY * 4, cudaMemcpyHostToDevice, a->st));
   CKC(cudaMemcpyAsync(a->r_sky2 + slot * a->SKY, s + a->SKY, a->SKY * 4, cudaMemcpyHostToDevice, a->st));
   CKC(cudaMemcpyAsync(a->r_act + slot * a->A, t, a->A * 4, cudaMemcpyHostToDevice, a->st));
@@ -852,24 +886,24 @@ int sc_calib_soft_update(sc_calib* a, float tau) {
 
 // choose_action (calib_sac.py:285-295): actor in eval mode (running statistics), one observation
 int sc_calib_act(sc_calib* a, const float* img, const float* sky, const float* eps, float* action_out) {
-  if (!a || !img || !sky || !action_out) return failc(SC_ERR_ARG, "null argument");
-  const size_t NI = (size_t)IMG * IMG;
+  if (!a || !sky || !action_out || (a->trunk && !img)) return failc(SC_ERR_ARG, "null argument");
+  const size_t NI = a->trunk ? (size_t)IMG * IMG : 0;
   CKC(cudaStreamSynchronize(a->st));
-  memcpy(a->h_stage, img, NI * 4);
+  if (NI) memcpy(a->h_stage, img, NI * 4);
   memcpy(a->h_stage + NI, sky, a->SKY * 4);
   if (eps) memcpy(a->h_stage + NI + a->SKY, eps, a->A * 4);
-  CKC(cudaMemcpyAsync(a->mb_img2, a->h_stage, NI * 4, cudaMemcpyHostToDevice, a->st));
+  if (NI) CKC(cudaMemcpyAsync(a->mb_img2, a->h_stage, NI * 4, cudaMemcpyHostToDevice, a->st));
   CKC(cudaMemcpyAsync(a->mb_sky2, a->h_stage + NI, a->SKY * 4, cudaMemcpyHostToDevice, a->st));
   if (eps) CKC(cudaMemcpyAsync(a->eps_next, a->h_stage + NI + a->SKY, a->A * 4, cudaMemcpyHostToDevice, a->st));
   else { CKC(launch_fill_normal(a->eps_next, a->A, a->cfg.rng_seed, 0x9000u + (uint64_t)(a->noise_ctr++), a->st)); a->launches++; }
   const NetP P = net_ptrs(a->params + a->off_net[0], a->La, true);
   TrunkWs& t = a->ws[0];
-  int rc = trunk_forward(a, t, P, 0, a->mb_img2, ACT_ELU, 0, 1);
+  int rc = a->trunk ? trunk_forward(a, t, P, 0, a->mb_img2, ACT_ELU, 0, 1) : SC_OK;
   if (rc) return rc;
-  k_side_fwd<<<1, 128, 0, a->st>>>(a->mb_sky2, a->SKY, nullptr, 0, P.fa_w, P.fa_b, P.fb_w, P.fb_b, t.x1, t.h1, t.o16, t.feat);
+  k_side_fwd<<<1, 128, 0, a->st>>>(a->mb_sky2, a->SKY, nullptr, 0, P.fa_w, P.fa_b, P.fb_w, P.fb_b, t.x1, t.h1, t.o16, t.feat, a->side, a->feat, a->flat);
   LAUNCH_OK(a);
-  if ((rc = sgemm(a, t.feat, FEAT, 1, P.h_w, 1, FEAT, a->x21, HID, 1, HID, FEAT, P.h_b, ACT_ELU))) return rc;
-  k_actor_head<<<1, 128, 0, a->st>>>(a->x21, P.mu_w, P.mu_b, P.sg_w, P.sg_b, a->eps_next, a->A, a->a2, a->sig2, a->raw2, a->logp2, nullptr, nullptr);
+  if ((rc = sgemm(a, t.feat, a->feat, 1, P.h_w, 1, a->feat, a->x21, HID, 1, HID, a->feat, P.h_b, ACT_ELU))) return rc;
+  k_actor_head<<<1, 128, 0, a->st>>>(a->x21, P.mu_w, P.mu_b, P.sg_w, P.sg_b, a->eps_next, a->A, a->a2, a->sig2, a->raw2, a->logp2, nullptr, nullptr, a->sigma_mode);
   LAUNCH_OK(a);
   CKC(cudaMemcpyAsync(a->h_stage, a->a2, a->A * 4, cudaMemcpyDeviceToHost, a->st));
   CKC(cudaStreamSynchronize(a->st));
@@ -901,12 +935,14 @@ int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
     a->launches += 2;
   }
   // ---- minibatch gather (replaces the host fancy-indexing + H2D copies of calib_sac.py:304-315) ----
-  k_gather<<<dim3(16, B), 256, 0, a->st>>>(a->r_img, a->bidx, NI, a->mb_img);  LAUNCH_OK(a);
-  k_gather<<<dim3(16, B), 256, 0, a->st>>>(a->r_img2, a->bidx, NI, a->mb_img2);  LAUNCH_OK(a);
+  if (a->trunk) {
+    k_gather<<<dim3(16, B), 256, 0, a->st>>>(a->r_img, a->bidx, NI, a->mb_img);  LAUNCH_OK(a);
+    k_gather<<<dim3(16, B), 256, 0, a->st>>>(a->r_img2, a->bidx, NI, a->mb_img2);  LAUNCH_OK(a);
+  }
   k_gather<<<dim3(1, B), 128, 0, a->st>>>(a->r_sky, a->bidx, SKY, a->mb_sky);  LAUNCH_OK(a);
   k_gather<<<dim3(1, B), 128, 0, a->st>>>(a->r_sky2, a->bidx, SKY, a->mb_sky2);  LAUNCH_OK(a);
-  k_gather<<<dim3(1, B), 64, 0, a->st>>>(a->r_act, a->bidx, A, a->mb_act);  LAUNCH_OK(a);
-  k_gather<<<dim3(1, B), 64, 0, a->st>>>(a->r_hint, a->bidx, A, a->mb_hint);  LAUNCH_OK(a);
+  k_gather<<<dim3(1, B), 128, 0, a->st>>>(a->r_act, a->bidx, A, a->mb_act);  LAUNCH_OK(a);
+  k_gather<<<dim3(1, B), 128, 0, a->st>>>(a->r_hint, a->bidx, A, a->mb_hint);  LAUNCH_OK(a);
   k_gather<<<dim3(1, B), 32, 0, a->st>>>(a->r_rew, a->bidx, 1, a->mb_rew);  LAUNCH_OK(a);
   k_gather<<<dim3(1, B), 32, 0, a->st>>>(a->r_done, a->bidx, 1, a->mb_done);  LAUNCH_OK(a);
 
@@ -922,20 +958,20 @@ int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
   // ---- 1. policy on s' (no grad; BatchNorm in train mode like the reference) ----
   {
     TrunkWs& t = a->ws[0];
-    if ((rc = trunk_forward(a, t, PA, 0, a->mb_img2, ACT_ELU, 1, B))) return rc;
-    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky2, SKY, nullptr, 0, PA.fa_w, PA.fa_b, PA.fb_w, PA.fb_b, t.x1, t.h1, t.o16, t.feat);
+    if (a->trunk && (rc = trunk_forward(a, t, PA, 0, a->mb_img2, ACT_ELU, 1, B))) return rc;
+    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky2, SKY, nullptr, 0, PA.fa_w, PA.fa_b, PA.fb_w, PA.fb_b, t.x1, t.h1, t.o16, t.feat, a->side, a->feat, a->flat);
     LAUNCH_OK(a);
-    if ((rc = sgemm(a, t.feat, FEAT, 1, PA.h_w, 1, FEAT, a->x21, HID, B, HID, FEAT, PA.h_b, ACT_ELU))) return rc;
-    k_actor_head<<<B, 128, 0, a->st>>>(a->x21, PA.mu_w, PA.mu_b, PA.sg_w, PA.sg_b, a->eps_next, A, a->a2, a->sig2, a->raw2, a->logp2, nullptr, nullptr);
+    if ((rc = sgemm(a, t.feat, a->feat, 1, PA.h_w, 1, a->feat, a->x21, HID, B, HID, a->feat, PA.h_b, ACT_ELU))) return rc;
+    k_actor_head<<<B, 128, 0, a->st>>>(a->x21, PA.mu_w, PA.mu_b, PA.sg_w, PA.sg_b, a->eps_next, A, a->a2, a->sig2, a->raw2, a->logp2, nullptr, nullptr, a->sigma_mode);
     LAUNCH_OK(a);
   }
   // ---- 2. target critics on (s', sky', a') ----
   for (int k = 0; k < 2; ++k) {
     TrunkWs& t = a->ws[0];
-    if ((rc = trunk_forward(a, t, PT[k], 3 + k, a->mb_img2, ACT_RELU, 1, B))) return rc;
-    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky2, SKY, a->a2, A, PT[k].fa_w, PT[k].fa_b, PT[k].fb_w, PT[k].fb_b, t.x1, t.h1, t.o16, t.feat);
+    if (a->trunk && (rc = trunk_forward(a, t, PT[k], 3 + k, a->mb_img2, ACT_RELU, 1, B))) return rc;
+    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky2, SKY, a->a2, A, PT[k].fa_w, PT[k].fa_b, PT[k].fb_w, PT[k].fb_b, t.x1, t.h1, t.o16, t.feat, a->side, a->feat, a->flat);
     LAUNCH_OK(a);
-    k_critic_head<<<B, 256, 0, a->st>>>(t.feat, PT[k].h_w, PT[k].h_b, a->qt[k]);
+    k_critic_head<<<B, 256, 0, a->st>>>(t.feat, PT[k].h_w, PT[k].h_b, a->qt[k], a->feat);
     LAUNCH_OK(a);
   }
   k_target<<<(B + 127) / 128, 128, 0, a->st>>>(a->qt[0], a->qt[1], a->logp2, a->mb_rew, a->mb_done, gamma, alpha, B, a->y);
@@ -944,56 +980,56 @@ int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
   a->t_critic++;
   for (int k = 0; k < 2; ++k) {
     TrunkWs& t = a->ws[1 + k];
-    if ((rc = trunk_forward(a, t, PC[k], 1 + k, a->mb_img, ACT_RELU, 1, B))) return rc;
-    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky, SKY, a->mb_act, A, PC[k].fa_w, PC[k].fa_b, PC[k].fb_w, PC[k].fb_b, t.x1, t.h1, t.o16, t.feat);
+    if (a->trunk && (rc = trunk_forward(a, t, PC[k], 1 + k, a->mb_img, ACT_RELU, 1, B))) return rc;
+    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky, SKY, a->mb_act, A, PC[k].fa_w, PC[k].fa_b, PC[k].fb_w, PC[k].fb_b, t.x1, t.h1, t.o16, t.feat, a->side, a->feat, a->flat);
     LAUNCH_OK(a);
-    k_critic_head<<<B, 256, 0, a->st>>>(t.feat, PC[k].h_w, PC[k].h_b, a->q[k]);
+    k_critic_head<<<B, 256, 0, a->st>>>(t.feat, PC[k].h_w, PC[k].h_b, a->q[k], a->feat);
     LAUNCH_OK(a);
   }
   for (int k = 0; k < 2; ++k) {
     TrunkWs& t = a->ws[1 + k];
     k_critic_seed<<<1, 256, 0, a->st>>>(a->q[k], a->y, B, a->dq, a->stats + k);
     LAUNCH_OK(a);
-    k_outer<<<grid_for((size_t)B * FEAT), 256, 0, a->st>>>(a->dq, PC[k].h_w, B, FEAT, a->dfeat);
+    k_outer<<<grid_for((size_t)B * a->feat), 256, 0, a->st>>>(a->dq, PC[k].h_w, B, a->feat, a->dfeat);
     LAUNCH_OK(a);
-    if ((rc = colsum(a, t.feat, FEAT, a->dq, B, FEAT, GC[k].h_w))) return rc;       // d head.weight
+    if ((rc = colsum(a, t.feat, a->feat, a->dq, B, a->feat, GC[k].h_w))) return rc;       // d head.weight
     if ((rc = colsum(a, a->dq, 1, nullptr, B, 1, GC[k].h_b))) return rc;             // d head.bias
-    k_side_bwd<<<B, 128, 0, a->st>>>(a->dfeat + FLAT, FEAT, t.o16, t.h1, PC[k].fb_w, PC[k].fa_w, a->K1C, SKY, A, a->d16, a->dh1, nullptr, 0);
+    k_side_bwd<<<B, 128, 0, a->st>>>(a->dfeat + a->flat, a->feat, t.o16, t.h1, PC[k].fb_w, PC[k].fa_w, a->K1C, SKY, A, a->d16, a->dh1, nullptr, 0, a->side);
     LAUNCH_OK(a);
     if ((rc = side_wgrads(a, t.x1, t.h1, a->K1C, GC[k]))) return rc;
-    if ((rc = trunk_backward(a, t, PC[k], GC[k], a->mb_img, ACT_RELU))) return rc;
+    if (a->trunk && (rc = trunk_backward(a, t, PC[k], GC[k], a->mb_img, ACT_RELU))) return rc;
   }
   for (int k = 0; k < 2; ++k)
     if ((rc = adam_step(a, 1 + k, a->cfg.lr_critic, a->t_critic))) return rc;
   // ---- 4. actor: policy on s (reparameterised), Q_k(s, pi) with the updated critics, backward, Adam ----
   {
     TrunkWs& t = a->ws[3];
-    if ((rc = trunk_forward(a, t, PA, 0, a->mb_img, ACT_ELU, 1, B))) return rc;
-    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky, SKY, nullptr, 0, PA.fa_w, PA.fa_b, PA.fb_w, PA.fb_b, t.x1, t.h1, t.o16, t.feat);
+    if (a->trunk && (rc = trunk_forward(a, t, PA, 0, a->mb_img, ACT_ELU, 1, B))) return rc;
+    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky, SKY, nullptr, 0, PA.fa_w, PA.fa_b, PA.fb_w, PA.fb_b, t.x1, t.h1, t.o16, t.feat, a->side, a->feat, a->flat);
     LAUNCH_OK(a);
-    if ((rc = sgemm(a, t.feat, FEAT, 1, PA.h_w, 1, FEAT, a->x21, HID, B, HID, FEAT, PA.h_b, ACT_ELU))) return rc;
-    k_actor_head<<<B, 128, 0, a->st>>>(a->x21, PA.mu_w, PA.mu_b, PA.sg_w, PA.sg_b, a->eps_cur, A, a->pi, a->sig, a->raw, a->logp, a->mu, a->u);
+    if ((rc = sgemm(a, t.feat, a->feat, 1, PA.h_w, 1, a->feat, a->x21, HID, B, HID, a->feat, PA.h_b, ACT_ELU))) return rc;
+    k_actor_head<<<B, 128, 0, a->st>>>(a->x21, PA.mu_w, PA.mu_b, PA.sg_w, PA.sg_b, a->eps_cur, A, a->pi, a->sig, a->raw, a->logp, a->mu, a->u, a->sigma_mode);
     LAUNCH_OK(a);
   }
   for (int k = 0; k < 2; ++k) {
     TrunkWs& t = a->ws[0];
-    if ((rc = trunk_forward(a, t, PC[k], 1 + k, a->mb_img, ACT_RELU, 1, B))) return rc;
+    if (a->trunk && (rc = trunk_forward(a, t, PC[k], 1 + k, a->mb_img, ACT_RELU, 1, B))) return rc;
     k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky, SKY, a->pi, A, PC[k].fa_w, PC[k].fa_b, PC[k].fb_w, PC[k].fb_b, a->pside[k].x1, a->pside[k].h1,
-                                     a->pside[k].o16, t.feat);
+                                     a->pside[k].o16, t.feat, a->side, a->feat, a->flat);
     LAUNCH_OK(a);
-    k_critic_head<<<B, 256, 0, a->st>>>(t.feat, PC[k].h_w, PC[k].h_b, a->qpi[k]);
+    k_critic_head<<<B, 256, 0, a->st>>>(t.feat, PC[k].h_w, PC[k].h_b, a->qpi[k], a->feat);
     LAUNCH_OK(a);
   }
-  k_actor_seed<<<(B + 127) / 128, 128, 0, a->st>>>(a->qpi[0], a->qpi[1], PC[0].h_w, PC[1].h_w, B, a->ds[0], a->ds[1], a->qmin);
+  k_actor_seed<<<(B + 127) / 128, 128, 0, a->st>>>(a->qpi[0], a->qpi[1], PC[0].h_w, PC[1].h_w, B, a->ds[0], a->ds[1], a->qmin, a->side, a->flat);
   LAUNCH_OK(a);
   for (int k = 0; k < 2; ++k) {
-    k_side_bwd<<<B, 128, 0, a->st>>>(a->ds[k], SIDE, a->pside[k].o16, a->pside[k].h1, PC[k].fb_w, PC[k].fa_w, a->K1C, SKY, A, a->d16, a->dh1, a->dact, k);
+    k_side_bwd<<<B, 128, 0, a->st>>>(a->ds[k], a->side, a->pside[k].o16, a->pside[k].h1, PC[k].fb_w, PC[k].fa_w, a->K1C, SKY, A, a->d16, a->dh1, a->dact, k, a->side);
     LAUNCH_OK(a);
   }
   const bool hint = a->cfg.use_hint != 0;
   const int dual = hint && (a->learn_counter % 10 == 0);
   if (hint) {
-    k_kld_coef<<<1, 256, 0, a->st>>>(a->pi, a->mb_hint, B * A, a->cfg.hint_threshold, a->admm_rho, a->rho, a->hint_out, 0);
+    k_kld_coef<<<1, 256, 0, a->st>>>(a->pi, a->mb_hint, B * A, a->cfg.hint_threshold, a->admm_rho, a->rho, a->hint_out, 0, a->kld_mode);
     LAUNCH_OK(a);
   }
   k_actor_loss<<<1, 256, 0, a->st>>>(a->logp, a->qmin, B, alpha, hint ? a->hint_out : nullptr, a->stats + 2);
@@ -1001,7 +1037,7 @@ int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
   {
     TrunkWs& t = a->ws[3];
     k_actor_head_bwd<<<B, 128, 0, a->st>>>(a->dact, a->pi, a->sig, a->raw, a->eps_cur, a->mu, a->u, a->mb_hint, hint ? a->hint_out : nullptr, alpha / (float)B, A,
-                                           PA.mu_w, PA.sg_w, a->x21, a->dmu, a->draw, a->dpre);
+                                           PA.mu_w, PA.sg_w, a->x21, a->dmu, a->draw, a->dpre, a->sigma_mode, a->kld_mode);
     LAUNCH_OK(a);
     // heads
     if ((rc = sgemm(a, a->dmu, 1, A, a->x21, HID, 1, GA.mu_w, HID, A, HID, B, nullptr, -1))) return rc;
@@ -1009,18 +1045,38 @@ int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
     if ((rc = sgemm(a, a->draw, 1, A, a->x21, HID, 1, GA.sg_w, HID, A, HID, B, nullptr, -1))) return rc;
     if ((rc = colsum(a, a->draw, A, nullptr, B, A, GA.sg_b))) return rc;
     // fc21: dW = dpre^T feat, db = colsum(dpre), dfeat = dpre W
-    if ((rc = sgemm(a, a->dpre, 1, HID, t.feat, FEAT, 1, GA.h_w, FEAT, HID, FEAT, B, nullptr, -1))) return rc;
+    if ((rc = sgemm(a, a->dpre, 1, HID, t.feat, a->feat, 1, GA.h_w, a->feat, HID, a->feat, B, nullptr, -1))) return rc;
     if ((rc = colsum(a, a->dpre, HID, nullptr, B, HID, GA.h_b))) return rc;
-    if ((rc = sgemm(a, a->dpre, HID, 1, PA.h_w, FEAT, 1, a->dfeat, FEAT, B, FEAT, HID, nullptr, -1))) return rc;
-    k_side_bwd<<<B, 128, 0, a->st>>>(a->dfeat + FLAT, FEAT, t.o16, t.h1, PA.fb_w, PA.fa_w, SKY, SKY, 0, a->d16, a->dh1, nullptr, 0);
+    if ((rc = sgemm(a, a->dpre, HID, 1, PA.h_w, a->feat, 1, a->dfeat, a->feat, B, a->feat, HID, nullptr, -1))) return rc;
+    k_side_bwd<<<B, 128, 0, a->st>>>(a->dfeat + a->flat, a->feat, t.o16, t.h1, PA.fb_w, PA.fa_w, SKY, SKY, 0, a->d16, a->dh1, nullptr, 0, a->side);
     LAUNCH_OK(a);
     if ((rc = side_wgrads(a, t.x1, t.h1, SKY, GA))) return rc;
-    if ((rc = trunk_backward(a, t, PA, GA, a->mb_img, ACT_ELU))) return rc;
+    if (a->trunk && (rc = trunk_backward(a, t, PA, GA, a->mb_img, ACT_ELU))) return rc;
   }
   a->t_actor++;
   if ((rc = adam_step(a, 0, a->cfg.lr_actor, a->t_actor))) return rc;
-  if (dual) {       // calib_sac.py:360-364: rho += admm_rho * g, g recomputed from the SAME actions
-    k_kld_coef<<<1, 256, 0, a->st>>>(a->pi, a->mb_hint, B * A, a->cfg.hint_threshold, a->admm_rho, a->rho, a->hint_out, 1);
+  if (dual && a->kld_mode == 0) {       // calib_sac.py:360-364: rho += admm_rho * g, g recomputed from the SAME actions
+    k_kld_coef<<<1, 256, 0, a->st>>>(a->pi, a->mb_hint, B * A, a->cfg.hint_threshold, a->admm_rho, a->rho, a->hint_out, 1, 0);
+    LAUNCH_OK(a);
+  }
+  if (dual && a->kld_mode == 1) {
+    // demix_sac.py:660-670: a fresh no-grad sample from the UPDATED actor (training-mode BatchNorm: running statistics move again)
+    if (noise && noise->eps_dual_host) {
+      CKC(cudaStreamSynchronize(a->st));
+      memcpy(a->h_stage, noise->eps_dual_host, (size_t)B * A * 4);
+      CKC(cudaMemcpyAsync(a->eps_dual, a->h_stage, (size_t)B * A * 4, cudaMemcpyHostToDevice, a->st));
+    } else {
+      CKC(launch_fill_normal(a->eps_dual, B * A, a->cfg.rng_seed, 0xD000000000ull + (uint64_t)a->noise_ctr, a->st));
+      a->launches++;
+    }
+    TrunkWs& t = a->ws[3];
+    if (a->trunk && (rc = trunk_forward(a, t, PA, 0, a->mb_img, ACT_ELU, 1, B))) return rc;
+    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky, SKY, nullptr, 0, PA.fa_w, PA.fa_b, PA.fb_w, PA.fb_b, t.x1, t.h1, t.o16, t.feat, a->side, a->feat, a->flat);
+    LAUNCH_OK(a);
+    if ((rc = sgemm(a, t.feat, a->feat, 1, PA.h_w, 1, a->feat, a->x21, HID, B, HID, a->feat, PA.h_b, ACT_ELU))) return rc;
+    k_actor_head<<<B, 128, 0, a->st>>>(a->x21, PA.mu_w, PA.mu_b, PA.sg_w, PA.sg_b, a->eps_dual, A, a->a2, a->sig2, a->raw2, a->logp2, nullptr, nullptr, a->sigma_mode);
+    LAUNCH_OK(a);
+    k_kld_coef<<<1, 256, 0, a->st>>>(a->a2, a->mb_hint, B * A, a->cfg.hint_threshold, a->admm_rho, a->rho, a->hint_out + 4, 1, 1);
     LAUNCH_OK(a);
   }
   a->learn_counter++;

@@ -32,3 +32,14 @@ def make_calib_transitions(seed, n, M, A, img=128, done_frac=0.0):
                 img2=rs.standard_normal((n, 1, img, img)).astype(np.float32), sky2=rs.standard_normal((n, M + 1, 7)).astype(np.float32),
                 action=rs.uniform(-1, 1, (n, A)).astype(np.float32), hint=rs.uniform(-1, 1, (n, A)).astype(np.float32),
                 reward=rs.standard_normal(n).astype(np.float32), done=rs.uniform(0, 1, n) < done_frac)
+
+
+def make_demix_transitions(seed, n, M, A, img=128, done_frac=0.0):
+    """synthetic demixing transitions (demix_sac.ReplayBuffer layout): influence map (1, img, img) (img = 0: none, the MLP
+    family), flat metadata (M,), action / hint in [-1, 1]^A"""
+    rs = np.random.RandomState(seed)
+    shp = (n, 1, img, img) if img else (n, 1, 1, 1)
+    return dict(img=rs.standard_normal(shp).astype(np.float32), meta=rs.standard_normal((n, M)).astype(np.float32),
+                img2=rs.standard_normal(shp).astype(np.float32), meta2=rs.standard_normal((n, M)).astype(np.float32),
+                action=rs.uniform(-1, 1, (n, A)).astype(np.float32), hint=rs.uniform(-1, 1, (n, A)).astype(np.float32),
+                reward=rs.standard_normal(n).astype(np.float32), done=rs.uniform(0, 1, n) < done_frac)

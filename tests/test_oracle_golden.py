@@ -173,3 +173,41 @@ def test_calib_oracle_matches_reference(name):
         res = orc.learn_on_batch(orc.replay.gather(z[f"step{s}/idx"]), z[f"step{s}/eps1"], z[f"step{s}/eps2"])
         check(f"step{s}", TOL * (s + 1))
         np.testing.assert_allclose([res["critic_1_loss"], res["critic_2_loss"], res["actor_loss"]], z[f"step{s}/losses"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["demix_fuzzy_mlp_b16", "demix_fuzzy_mlp_hint_b16", "demix_rl_b8", "demix_rl_hint_b8"])
+def test_demix_oracle_matches_reference(name):
+    """the two demixing SAC agents (demixing_rl/demix_sac.py, demixing_fuzzy/demix_sac.py): the oracle restatement replays the
+    draws recorded from the unmodified reference modules (tests/golden/make_golden_demix.py)"""
+    from oracle.demix_ref import DemixSacRef
+    from smartcal_b200.synth import make_demix_transitions
+    z = np.load(os.path.join(G, name + ".npz"))
+    M, A, B, C, steps, seed, use_hint, ui, inner = [int(x) for x in z["cfg"]]
+    steps = min(steps, 2 if ui else 11)         # each conv CPU step costs ~1 s
+    hp = dict(gamma=0.99, batch_size=B, n_actions=A, tau=0.005, max_mem_size=C, input_dims=[1, 128, 128], lr_a=3e-4, lr_c=1e-3,
+              alpha=0.03, hint_threshold=0.01, admm_rho=1.0, use_hint=bool(use_hint))
+    tr = make_demix_transitions(seed + 100, C, M, A, 128 if ui else 0, float(z["done_frac"][0]))
+    torch.manual_seed(seed)
+    orc = DemixSacRef(**hp, M=M, use_influence=bool(ui), inner=inner)
+    for i in range(C):
+        orc.replay.store(tr["img"][i] if ui else None, tr["meta"][i], tr["action"][i], float(tr["reward"][i]), tr["img2"][i] if ui else None,
+                         tr["meta2"][i], bool(tr["done"][i]), tr["hint"][i])
+
+    def check(prefix, tol):
+        for nm in ("actor", "critic_1", "critic_2", "target_critic_1", "target_critic_2"):
+            sd = {**getattr(orc, nm), **getattr(orc, nm + "_b")}
+            for k, v in sd.items():
+                ref = z[f"{prefix}/{nm}/{k}/p"]
+                a = v.detach().float().numpy().astype(np.float64).reshape(-1)
+                idx = np.linspace(0, a.size - 1, min(32, a.size)).astype(np.int64)
+                got = np.concatenate([[a.sum(), np.abs(a).sum()], a[idx]])
+                assert np.max(np.abs(got - ref) / (1.0 + np.abs(ref))) <= tol, f"{prefix}/{nm}/{k}"
+
+    check("init", 0.0)
+    for s in range(steps):
+        e3 = z[f"step{s}/eps3"] if f"step{s}/eps3" in z else None
+        res = orc.learn_on_batch(orc.replay.gather(z[f"step{s}/idx"]), z[f"step{s}/eps1"], z[f"step{s}/eps2"], e3)
+        check(f"step{s}", TOL * (s + 1))
+        np.testing.assert_allclose([res["critic_1_loss"], res["critic_2_loss"], res["actor_loss"]], z[f"step{s}/losses"], rtol=1e-4)
+        if use_hint:
+            assert abs(float(orc.rho) - float(z[f"step{s}/rho"][0])) <= 1e-6 * (1 + abs(float(orc.rho)))
