@@ -214,7 +214,68 @@ def other_configs(args, peak):
         out["calib_b256"] = calib_numbers(min(args.steps, 30), 3)
     except Exception as e:      # (never lose the headline line to a secondary config)
         out["calib_b256"] = {"error": repr(e)}
+    # --- the two demixing SAC agents at the shapes of their main_sac.py ---
+    for key, family in (("demix_fuzzy_mlp_b256", "demixing_fuzzy"), ("demix_rl_conv_b256", "demixing_rl")):
+        try:
+            out[key] = demix_numbers(family, min(args.steps, 100 if family == "demixing_fuzzy" else 30), 5)
+        except Exception as e:
+            out[key] = {"error": repr(e)}
     return out
+
+
+def demix_numbers(family, steps, warmup):
+    """demixing_fuzzy/main_sac.py shape (MLP SAC: n_meta 32, n_actions 128, batch 256) or demixing_rl/main_sac.py shape (conv SAC:
+    M 20, n_actions 6, batch 256): device-timed steps/s (uniform replay, device noise) + the CPU oracle port on a bounded sample"""
+    from smartcal_b200.synth import make_demix_transitions
+    from oracle.demix_ref import DemixSacRef
+    ui = family == "demixing_rl"
+    M, A_, Bd, Cd = (20, 6, 256, 512) if ui else (32, 128, 256, 1024)
+    hp = dict(gamma=0.99, batch_size=Bd, n_actions=A_, tau=0.005, max_mem_size=Cd, input_dims=[1, 128, 128], lr_a=3e-4, lr_c=1e-3 if ui else 3e-4,
+              alpha=0.03, hint_threshold=0.01, admm_rho=1.0, use_hint=False)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    if ui:
+        from smartcal_b200.demixing_rl import demix_sac
+        agent = demix_sac.DemixingAgent(**hp, M=M, rng="device")
+    else:
+        from smartcal_b200.demixing_fuzzy import demix_sac
+        agent = demix_sac.DemixingAgent(**hp, n_meta=M, use_influence=False, rng="device")
+    tr = make_demix_transitions(100, Cd, M, A_, 128 if ui else 0, 0.0)
+    dev = agent._dev
+    names = [("state_memory_sky", "meta"), ("new_state_memory_sky", "meta2"), ("action_memory", "action"), ("hint_memory", "hint")]
+    if ui:
+        names += [("state_memory_img", "img"), ("new_state_memory_img", "img2")]
+    for name, key in names:
+        dev.buffer(name).copy_(torch.as_tensor(tr[key].reshape(Cd, -1)).to(dev.device))
+    dev.buffer("reward_memory").copy_(torch.as_tensor(tr["reward"].reshape(Cd, 1)).to(dev.device))
+    dev.set_counters(Cd, 0)
+    rs = np.random.RandomState(1)
+
+    def step():
+        dev.set_batch(rs.choice(Cd, Bd, replace=False))
+        dev.learn()
+    ms = time_agent(step, steps, warmup)
+    torch.manual_seed(0)
+    orc = DemixSacRef(**hp, M=M, use_influence=ui, inner=16 if ui else 32)
+    for i in range(Cd):
+        orc.replay.store(tr["img"][i] if ui else None, tr["meta"][i], tr["action"][i], float(tr["reward"][i]), tr["img2"][i] if ui else None,
+                         tr["meta2"][i], False, tr["hint"][i])
+    t = torch.get_num_threads()
+    nt = min(32 if ui else 8, os.cpu_count() or 1)
+    torch.set_num_threads(nt)
+    orc.learn()
+    k = 1 if ui else 20
+    t0 = time.perf_counter()
+    for _ in range(k):
+        orc.learn()
+    dt = (time.perf_counter() - t0) / k
+    torch.set_num_threads(t)
+    launches = dev.launch_count()
+    return {"value": 1e3 / ms, "unit": "learn steps/s", "ms_per_step": ms,
+            "workload": ("demixing_rl conv SAC: img (256,1,128,128), metadata 20, 6 actions" if ui else
+                         "demixing_fuzzy MLP SAC: metadata 32, 128 actions, batch 256 (use_influence=False)"),
+            "cpu_baseline": {"value": 1.0 / dt, "unit": "learn steps/s", "cores": nt, "kind": "port", "sample": f"{k} learn() step(s) after 1 warm-up"},
+            "gpu_launches_total": int(launches)}
 
 
 def ensemble_numbers(args, single_ms, peak):
