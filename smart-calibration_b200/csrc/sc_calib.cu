@@ -18,6 +18,7 @@
 namespace sc {
 cudaError_t launch_soft_update(const float* src, float* dst, size_t n, float tau, cudaStream_t st);
 cudaError_t launch_fill_normal(float* out, int n, uint64_t seed, uint64_t stream, cudaStream_t st);
+cudaError_t launch_fill_normal_p(float* out, int n, uint64_t seed, const unsigned long long* stream_dev, cudaStream_t st);
 }  // namespace sc
 
 using namespace sc;
@@ -404,6 +405,18 @@ struct sc_calib {
   bool batch_ready;
   float admm_rho;
   int wg_blocks, nch;
+  // per-step scalars in device memory (Adam bias corrections of the three optimizers, Philox stream ids of the noise draws): one
+  // small copy per step; with them the launch sequence of learn() is identical from step to step and replays from a CUDA graph
+  struct StepScalars { AdamP adam[3]; unsigned long long noise[4]; };
+  StepScalars* step_dev;
+  StepScalars* step_host;          // pinned, two slots
+  cudaEvent_t ev_step[2];
+  int step_k;
+  cudaStream_t st_cap;             // library-owned capture stream (the caller's may be the legacy default stream)
+  cudaGraphExec_t graph[2];        // [dual update step?]
+  int graph_seen[2];
+  int use_graph;
+  int64_t graph_launches[2];
   std::map<std::string, sc_tensor_info> reg;
 };
 
@@ -605,12 +618,22 @@ static int sgemm(sc_calib* a, const float* A_, long sam, long sak, const float* 
     LAUNCH_OK(a);
     return SC_OK;
   }
+  if (tiles <= 16 && K >= 128 && (size_t)M * N <= (size_t)a->B * HID) {
+    // few output tiles (the small GEMMs of the metadata / head networks and their weight gradients, reduction = batch): a handful of
+    // CTAs would walk the whole reduction 16 elements at a time, two barriers per step -- cut it into 16-element-multiple slices instead
+    const int nz = K >= 512 ? 16 : 8, kslice = ((K + nz * 16 - 1) / (nz * 16)) * 16;
+    k_sgemm<<<dim3((N + 63) / 64, (M + 63) / 64, nz), 256, 0, a->st>>>(A_, sam, sak, B_, sbk, sbn, a->splitk, N, M, N, K, nullptr, -1, kslice);
+    LAUNCH_OK(a);
+    k_splitk_reduce<<<(M * N + 255) / 256, 256, 0, a->st>>>(a->splitk, nz, M, N, bias, act, C_, ldc);
+    LAUNCH_OK(a);
+    return SC_OK;
+  }
   k_sgemm<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, a->st>>>(A_, sam, sak, B_, sbk, sbn, C_, ldc, M, N, K, bias, act, K);
   LAUNCH_OK(a);
   return SC_OK;
 }
 static int colsum(sc_calib* a, const float* X, long ldx, const float* w, int Bn, int N, float* out) {
-  k_colsum<<<(N + 127) / 128, 128, 0, a->st>>>(X, ldx, w, Bn, N, out);
+  k_colsum<<<(N + 31) / 32, 256, 0, a->st>>>(X, ldx, w, Bn, N, out);
   LAUNCH_OK(a);
   return SC_OK;
 }
@@ -702,9 +725,9 @@ static AdamP adam_hyper_c(double lr, int64_t t) {
   h.eps = 1e-8f;
   return h;
 }
-static int adam_step(sc_calib* a, int net, double lr, int64_t t) {
+static int adam_step(sc_calib* a, int net) {       // hyper-parameters of optimizer `net`: step_dev->adam[net] (written by learn())
   const size_t n = net == 0 ? a->La.size : a->Lc.size, off = a->off_net[net];
-  k_adam<<<grid_for(n), 256, 0, a->st>>>(a->params + off, a->grads + off, a->adam_m + off, a->adam_v + off, n, adam_hyper_c(lr, t));
+  k_adam<<<grid_for(n), 256, 0, a->st>>>(a->params + off, a->grads + off, a->adam_m + off, a->adam_v + off, n, &a->step_dev->adam[net]);
   LAUNCH_OK(a);
   return SC_OK;
 }
@@ -757,6 +780,18 @@ int sc_calib_create(const sc_calib_config* cfg, void* arena, size_t arena_bytes,
   CKC(cudaHostAlloc((void**)&a->h_idx, (size_t)a->B * sizeof(int), cudaHostAllocDefault));
   CKC(cudaFuncSetAttribute(k_conv_wgrad<C1, C2, H1C, H2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024));
   CKC(cudaFuncSetAttribute(k_conv_wgrad<C2, C3, H2C, H3C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 101 * 1024));
+  CKC(cudaMalloc((void**)&a->step_dev, sizeof(sc_calib::StepScalars)));
+  CKC(cudaHostAlloc((void**)&a->step_host, 2 * sizeof(sc_calib::StepScalars), cudaHostAllocDefault));
+  for (auto& e : a->ev_step) CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CKC(cudaStreamCreateWithFlags(&a->st_cap, cudaStreamNonBlocking));
+  a->step_k = 0;
+  a->graph[0] = a->graph[1] = nullptr;
+  a->graph_seen[0] = a->graph_seen[1] = 0;
+  a->graph_launches[0] = a->graph_launches[1] = 0;
+  {
+    const char* e = getenv("SMARTCAL_GRAPH");
+    a->use_graph = (e && e[0] == '0') ? 0 : 1;
+  }
   a->mem_cntr = a->learn_counter = a->t_actor = a->t_critic = a->launches = a->noise_ctr = 0;
   a->batch_ready = false;
   a->admm_rho = cfg->admm_rho;
@@ -767,6 +802,11 @@ int sc_calib_create(const sc_calib_config* cfg, void* arena, size_t arena_bytes,
 int sc_calib_destroy(sc_calib* a) {
   if (!a) return SC_OK;
   cudaStreamSynchronize(a->st);
+  for (auto& g : a->graph) if (g) cudaGraphExecDestroy(g);
+  if (a->st_cap) { cudaStreamSynchronize(a->st_cap); cudaStreamDestroy(a->st_cap); }
+  for (auto& e : a->ev_step) if (e) cudaEventDestroy(e);
+  if (a->step_dev) cudaFree(a->step_dev);
+  if (a->step_host) cudaFreeHost(a->step_host);
   if (a->h_stage) cudaFreeHost(a->h_stage);
   if (a->h_stats) cudaFreeHost(a->h_stats);
   if (a->h_idx) cudaFreeHost(a->h_idx);
@@ -912,26 +952,15 @@ int sc_calib_act(sc_calib* a, const float* img, const float* sky, const float* e
   return SC_OK;
 }
 
-int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
-  if (!a) return failc(SC_ERR_ARG, "null handle");
-  if (stats) memset(stats, 0, sizeof(*stats));
-  if (a->mem_cntr < a->B) return SC_OK;                                     // calib_sac.py:301-302
-  if (!a->batch_ready) return failc(SC_ERR_STATE, "no minibatch selected: call sc_calib_set_batch_host first");
+// every launch of one learn() (calib_sac.py:317-378 / demix_sac.py:594-682) on a->st; with device-generated noise the sequence
+// is identical from step to step (step-dependent scalars live in step_dev) and is replayed from a CUDA graph
+static int calib_body(sc_calib* a, bool host_noise, bool hint, int dual) {
   const int B = a->B, A = a->A, SKY = a->SKY;
   const size_t NI = (size_t)IMG * IMG;
   int rc;
-  // ---- noise ----
-  if (noise && noise->eps_next_host && noise->eps_cur_host) {
-    CKC(cudaStreamSynchronize(a->st));
-    float* h = a->h_stage;
-    memcpy(h, noise->eps_next_host, (size_t)B * A * 4);
-    memcpy(h + (size_t)B * A, noise->eps_cur_host, (size_t)B * A * 4);
-    CKC(cudaMemcpyAsync(a->eps_next, h, (size_t)B * A * 4, cudaMemcpyHostToDevice, a->st));
-    CKC(cudaMemcpyAsync(a->eps_cur, h + (size_t)B * A, (size_t)B * A * 4, cudaMemcpyHostToDevice, a->st));
-  } else {
-    CKC(launch_fill_normal(a->eps_next, B * A, a->cfg.rng_seed, 2 * (uint64_t)a->noise_ctr, a->st));
-    CKC(launch_fill_normal(a->eps_cur, B * A, a->cfg.rng_seed, 2 * (uint64_t)a->noise_ctr + 1, a->st));
-    a->noise_ctr++;
+  if (!host_noise) {
+    CKC(launch_fill_normal_p(a->eps_next, B * A, a->cfg.rng_seed, &a->step_dev->noise[0], a->st));
+    CKC(launch_fill_normal_p(a->eps_cur, B * A, a->cfg.rng_seed, &a->step_dev->noise[1], a->st));
     a->launches += 2;
   }
   // ---- minibatch gather (replaces the host fancy-indexing + H2D copies of calib_sac.py:304-315) ----
@@ -977,7 +1006,6 @@ int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
   k_target<<<(B + 127) / 128, 128, 0, a->st>>>(a->qt[0], a->qt[1], a->logp2, a->mb_rew, a->mb_done, gamma, alpha, B, a->y);
   LAUNCH_OK(a);
   // ---- 3. critics: forward on (s, sky, a), MSE loss, backward, Adam ----
-  a->t_critic++;
   for (int k = 0; k < 2; ++k) {
     TrunkWs& t = a->ws[1 + k];
     if (a->trunk && (rc = trunk_forward(a, t, PC[k], 1 + k, a->mb_img, ACT_RELU, 1, B))) return rc;
@@ -1000,7 +1028,7 @@ int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
     if (a->trunk && (rc = trunk_backward(a, t, PC[k], GC[k], a->mb_img, ACT_RELU))) return rc;
   }
   for (int k = 0; k < 2; ++k)
-    if ((rc = adam_step(a, 1 + k, a->cfg.lr_critic, a->t_critic))) return rc;
+    if ((rc = adam_step(a, 1 + k))) return rc;
   // ---- 4. actor: policy on s (reparameterised), Q_k(s, pi) with the updated critics, backward, Adam ----
   {
     TrunkWs& t = a->ws[3];
@@ -1026,8 +1054,6 @@ int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
     k_side_bwd<<<B, 128, 0, a->st>>>(a->ds[k], a->side, a->pside[k].o16, a->pside[k].h1, PC[k].fb_w, PC[k].fa_w, a->K1C, SKY, A, a->d16, a->dh1, a->dact, k, a->side);
     LAUNCH_OK(a);
   }
-  const bool hint = a->cfg.use_hint != 0;
-  const int dual = hint && (a->learn_counter % 10 == 0);
   if (hint) {
     k_kld_coef<<<1, 256, 0, a->st>>>(a->pi, a->mb_hint, B * A, a->cfg.hint_threshold, a->admm_rho, a->rho, a->hint_out, 0, a->kld_mode);
     LAUNCH_OK(a);
@@ -1053,20 +1079,15 @@ int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
     if ((rc = side_wgrads(a, t.x1, t.h1, SKY, GA))) return rc;
     if (a->trunk && (rc = trunk_backward(a, t, PA, GA, a->mb_img, ACT_ELU))) return rc;
   }
-  a->t_actor++;
-  if ((rc = adam_step(a, 0, a->cfg.lr_actor, a->t_actor))) return rc;
+  if ((rc = adam_step(a, 0))) return rc;
   if (dual && a->kld_mode == 0) {       // calib_sac.py:360-364: rho += admm_rho * g, g recomputed from the SAME actions
     k_kld_coef<<<1, 256, 0, a->st>>>(a->pi, a->mb_hint, B * A, a->cfg.hint_threshold, a->admm_rho, a->rho, a->hint_out, 1, 0);
     LAUNCH_OK(a);
   }
   if (dual && a->kld_mode == 1) {
     // demix_sac.py:660-670: a fresh no-grad sample from the UPDATED actor (training-mode BatchNorm: running statistics move again)
-    if (noise && noise->eps_dual_host) {
-      CKC(cudaStreamSynchronize(a->st));
-      memcpy(a->h_stage, noise->eps_dual_host, (size_t)B * A * 4);
-      CKC(cudaMemcpyAsync(a->eps_dual, a->h_stage, (size_t)B * A * 4, cudaMemcpyHostToDevice, a->st));
-    } else {
-      CKC(launch_fill_normal(a->eps_dual, B * A, a->cfg.rng_seed, 0xD000000000ull + (uint64_t)a->noise_ctr, a->st));
+    if (!host_noise) {
+      CKC(launch_fill_normal_p(a->eps_dual, B * A, a->cfg.rng_seed, &a->step_dev->noise[2], a->st));
       a->launches++;
     }
     TrunkWs& t = a->ws[3];
@@ -1079,8 +1100,86 @@ int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
     k_kld_coef<<<1, 256, 0, a->st>>>(a->a2, a->mb_hint, B * A, a->cfg.hint_threshold, a->admm_rho, a->rho, a->hint_out + 4, 1, 1);
     LAUNCH_OK(a);
   }
-  a->learn_counter++;
   if ((rc = sc_calib_soft_update(a, (float)a->cfg.tau))) return rc;
+  return SC_OK;
+}
+
+int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
+  if (!a) return failc(SC_ERR_ARG, "null handle");
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (a->mem_cntr < a->B) return SC_OK;                                     // calib_sac.py:301-302
+  if (!a->batch_ready) return failc(SC_ERR_STATE, "no minibatch selected: call sc_calib_set_batch_host first");
+  const int B = a->B, A = a->A;
+  int rc;
+  const bool hint = a->cfg.use_hint != 0;
+  const int dual = hint && (a->learn_counter % 10 == 0);
+  const bool host_noise = noise && noise->eps_next_host && noise->eps_cur_host;
+  // ---- step scalars: Adam bias corrections (t counts steps per optimizer) and the Philox streams of this step's draws ----
+  {
+    const int k = a->step_k;
+    a->step_k ^= 1;
+    CKC(cudaEventSynchronize(a->ev_step[k]));
+    sc_calib::StepScalars& h = a->step_host[k];
+    a->t_critic++;
+    a->t_actor++;
+    h.adam[0] = adam_hyper_c(a->cfg.lr_actor, a->t_actor);
+    h.adam[1] = h.adam[2] = adam_hyper_c(a->cfg.lr_critic, a->t_critic);
+    h.noise[0] = 2 * (unsigned long long)a->noise_ctr;
+    h.noise[1] = 2 * (unsigned long long)a->noise_ctr + 1;
+    h.noise[2] = 0xD000000000ull + (unsigned long long)a->noise_ctr;
+    h.noise[3] = 0;
+    if (!host_noise) a->noise_ctr++;
+    CKC(cudaMemcpyAsync(a->step_dev, &h, sizeof(h), cudaMemcpyHostToDevice, a->st));
+    CKC(cudaEventRecord(a->ev_step[k], a->st));
+  }
+  if (host_noise) {
+    CKC(cudaStreamSynchronize(a->st));
+    float* h = a->h_stage;
+    memcpy(h, noise->eps_next_host, (size_t)B * A * 4);
+    memcpy(h + (size_t)B * A, noise->eps_cur_host, (size_t)B * A * 4);
+    CKC(cudaMemcpyAsync(a->eps_next, h, (size_t)B * A * 4, cudaMemcpyHostToDevice, a->st));
+    CKC(cudaMemcpyAsync(a->eps_cur, h + (size_t)B * A, (size_t)B * A * 4, cudaMemcpyHostToDevice, a->st));
+    if (dual && a->kld_mode == 1) {
+      if (!noise->eps_dual_host) return failc(SC_ERR_ARG, "host noise given but eps_dual_host missing on a dual-update step");
+      CKC(cudaStreamSynchronize(a->st));
+      memcpy(h, noise->eps_dual_host, (size_t)B * A * 4);
+      CKC(cudaMemcpyAsync(a->eps_dual, h, (size_t)B * A * 4, cudaMemcpyHostToDevice, a->st));
+    }
+  }
+  // ---- the launches: eager the first time a shape is seen, captured the second time, replayed afterwards ----
+  bool done = false;
+  if (a->use_graph && !host_noise) {
+    if (a->graph[dual] == nullptr && a->graph_seen[dual] >= 1) {
+      cudaStream_t user = a->st;
+      const int64_t launches0 = a->launches;
+      a->st = a->st_cap;
+      cudaGraph_t g = nullptr;
+      cudaError_t e = cudaStreamBeginCapture(a->st_cap, cudaStreamCaptureModeRelaxed);
+      int brc = SC_OK;
+      if (e == cudaSuccess) {
+        brc = calib_body(a, host_noise, hint, dual);
+        cudaError_t e2 = cudaStreamEndCapture(a->st_cap, &g);
+        if (e == cudaSuccess) e = e2;
+      }
+      a->st = user;
+      a->launches = launches0;
+      if (e == cudaSuccess && brc == SC_OK) e = cudaGraphInstantiate(&a->graph[dual], g, 0);
+      if (g) cudaGraphDestroy(g);
+      if (e != cudaSuccess || brc != SC_OK) { cudaGetLastError(); a->graph[dual] = nullptr; a->use_graph = 0; }
+    }
+    a->graph_seen[dual]++;
+    if (a->graph[dual] != nullptr) {
+      CKC(cudaGraphLaunch(a->graph[dual], a->st));
+      a->launches += a->graph_launches[dual];
+      done = true;
+    }
+  }
+  if (!done) {
+    const int64_t l0 = a->launches;
+    if ((rc = calib_body(a, host_noise, hint, dual))) return rc;
+    a->graph_launches[dual] = a->launches - l0;
+  }
+  a->learn_counter++;
   a->batch_ready = false;
   if (stats) {
     CKC(cudaMemcpyAsync(a->h_stats, a->stats, 8 * sizeof(float), cudaMemcpyDeviceToHost, a->st));

@@ -553,19 +553,32 @@ __global__ void k_splitk_reduce(const float* __restrict__ partial, int nz, int M
 }
 
 // out[n] = sum_b w[b] * X[b][n]  (w == nullptr: plain column sum); one thread per column, fixed order
-__global__ void k_colsum(const float* __restrict__ X, long ldx, const float* __restrict__ wrow, int B, int N, float* __restrict__ out) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// out[n] = sum_b wrow[b] * X[b][n]: 32 columns per block, 8 row groups (rows rg, rg + 8, ...) combined in fixed order
+__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ X, long ldx, const float* __restrict__ wrow, int B, int N, float* __restrict__ out) {
+  __shared__ float part[8][33];
+  const int c = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + c;
   float s = 0.f;
-  for (int b = 0; b < B; ++b) s = fmaf(wrow ? wrow[b] : 1.f, X[(long)b * ldx + n], s);
-  out[n] = s;
+  if (n < N)
+    for (int b = rg; b < B; b += 8) s = fmaf(wrow ? wrow[b] : 1.f, X[(long)b * ldx + n], s);
+  part[rg][c] = s;
+  __syncthreads();
+  if (rg == 0 && n < N) {
+    float t = part[0][c];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) t += part[r][c];
+    out[n] = t;
+  }
 }
 
 // =====================================================================================================================
 // Adam over a flat parameter block (torch.optim.Adam defaults; same roundings as sc_wgrad.cu)
 // =====================================================================================================================
 struct AdamP { float lr_neg_step, bc2_sqrt, one_minus_b1, b2, one_minus_b2, eps; };
-__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n, const AdamP h) {
+// (the step-dependent scalars come from device memory, written by the one small host->device copy at the head of a step, so
+//  that the launch itself is identical every step and a learn() can be replayed from a CUDA graph)
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n, const AdamP* __restrict__ hp) {
+  const AdamP h = *hp;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float gi = g[i];
     float mi = m[i], vi = v[i];

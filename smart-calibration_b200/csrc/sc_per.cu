@@ -326,6 +326,16 @@ __global__ void k_fill_normal(float* out, int n, uint64_t seed, uint64_t stream)
   }
 }
 
+// the same fill with the Philox stream id read from device memory (graph-replayed steps: the launch arguments stay constant)
+__global__ void k_fill_normal_p(float* out, int n, uint64_t seed, const unsigned long long* __restrict__ stream) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (2 * i < n) {
+    const float2 z = philox_normal2(seed, (uint64_t)*stream, (uint64_t)i);
+    out[2 * i] = z.x;
+    if (2 * i + 1 < n) out[2 * i + 1] = z.y;
+  }
+}
+
 // hint penalty coefficient (SAC, enet_sac.py:601-602,616-617): m = mean((pi-hint)^2) over B*A,
 // g = max(0, m-thr)^2, d(0.5*admm_rho*g^2 + rho*g)/d pi = (admm_rho*g + rho) * 2*max(0,m-thr) * 2(pi-hint)/(B*A).
 // Writes out[0] = that scalar coefficient (without the (pi-hint) factor), out[1] = g.  One block.
@@ -480,6 +490,11 @@ cudaError_t launch_sample_uniform(const UniformP* pp, int E, int n, cudaStream_t
 cudaError_t launch_fill_normal(float* out, int n, uint64_t seed, uint64_t stream, cudaStream_t st) {
   const int pairs = (n + 1) / 2;
   k_fill_normal<<<(pairs + 255) / 256, 256, 0, st>>>(out, n, seed, stream);
+  return cudaGetLastError();
+}
+cudaError_t launch_fill_normal_p(float* out, int n, uint64_t seed, const unsigned long long* stream_dev, cudaStream_t st) {
+  const int pairs = (n + 1) / 2;
+  k_fill_normal_p<<<(pairs + 255) / 256, 256, 0, st>>>(out, n, seed, stream_dev);
   return cudaGetLastError();
 }
 cudaError_t launch_hint_coef(const HintCoefP* pp, int E, cudaStream_t st) {

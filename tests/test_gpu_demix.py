@@ -224,3 +224,43 @@ def test_demixing_rl_per_clips_errors_at_one():
     if ps_ref is not None:
         assert np.abs(np.asarray(ps, np.float32).view(np.int32).astype(np.int64) - np.asarray(ps_ref, np.float32).view(np.int32).astype(np.int64)).max() <= 2
     np.testing.assert_allclose(per.tree.tree, orc.tree.tree, rtol=1e-6)
+
+
+@pytest.mark.parametrize("family", ["demixing_fuzzy", "demixing_rl"])
+def test_calib_family_graph_replay_equals_eager(family, monkeypatch):
+    """rng='device': learn() of the sc_calib_* family replays from a CUDA graph from the third step on (step-dependent scalars --
+    Adam bias corrections, Philox stream ids -- live in device memory); SMARTCAL_GRAPH=0 keeps eager launches.  Same bits."""
+    M, A = (32, 128) if family == "demixing_fuzzy" else (20, 6)
+    ui = family == "demixing_rl"
+    B, C = 16, 32
+
+    def run(graph):
+        monkeypatch.setenv("SMARTCAL_GRAPH", "1" if graph else "0")
+        hp = dict(gamma=0.99, batch_size=B, n_actions=A, tau=0.005, max_mem_size=C, input_dims=[1, 128, 128], lr_a=3e-4, lr_c=1e-3,
+                  alpha=0.03, hint_threshold=0.01, admm_rho=1.0, use_hint=True)
+        torch.manual_seed(3)
+        np.random.seed(3)
+        if ui:
+            from smartcal_b200.demixing_rl import demix_sac
+            agent = demix_sac.DemixingAgent(**hp, M=M, rng="device")
+        else:
+            from smartcal_b200.demixing_fuzzy import demix_sac
+            agent = demix_sac.DemixingAgent(**hp, n_meta=M, use_influence=False, rng="device")
+        tr = make_demix_transitions(4, C, M, A, 128 if ui else 0, 0.1)
+        for i in range(C):
+            s = {"infmap": tr["img"][i] if ui else 0, "metadata": tr["meta"][i]}
+            s2 = {"infmap": tr["img2"][i] if ui else 0, "metadata": tr["meta2"][i]}
+            agent.store_transition(s, tr["action"][i], float(tr["reward"][i]), s2, bool(tr["done"][i]), tr["hint"][i])
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            for _ in range(13):                   # covers plain steps (graph) and two dual-update steps (their own graph)
+                st = agent.learn(want_stats=True)
+        out = {f"{nm}.{k}": v.detach().cpu().clone() for nm in NETS for k, v in getattr(agent, nm).state_dict().items()}
+        out["rho"] = torch.tensor(st["rho"])
+        agent._dev.close()
+        return out
+
+    g, e = run(True), run(False)
+    for k in e:
+        assert torch.equal(g[k], e[k]), k
