@@ -140,10 +140,11 @@ def test_fused_store_learn_equals_store_then_learn(prioritized):
 
 
 # ---- free-running trajectories ------------------------------------------------------------------------------------------------
-# Stated band (measured drift is reported in the assertion message): over 50 un-forced learn() calls at S=420, B=256 from identical
-# initial state and identical minibatches / noise, the CUDA path's critic losses stay within 2 % (+1e-3 abs) and the batch
-# mean of Q1 within 2 % (+2e-2 abs) of the CPU oracle's; with PER each side samples from ITS OWN tree with the same uniforms,
-# so float32-ulp priority differences may flip an occasional index (at most 2 % of the draws) and the band is 10 %.
+# Stated band: over 50 un-forced learn() calls at S=420, B=256 from identical initial state and identical minibatches / noise, the
+# CUDA path's critic losses and the batch mean of Q1 stay within 5e-4 relative (+1e-5 / +2e-4 abs) of the CPU oracle's; with PER
+# each side samples from ITS OWN tree with the same uniforms (float32-ulp priority differences may flip an occasional index: at
+# most 0.2 % of the draws) and the band is 2e-3.  Measured on B200 (round 2): worst relative deviation 4e-6 (uniform) / 7e-5 (PER),
+# no index flips in 12 800 draws -- Adam's amplification of rounding-level gradient noise does not compound visibly.
 @pytest.mark.parametrize("prioritized", [False, True])
 def test_free_running_50_steps_stay_within_band_of_oracle(prioritized):
     S, A, B, C, steps = 420, 2, 256, 512, 50
@@ -154,7 +155,7 @@ def test_free_running_50_steps_stay_within_band_of_oracle(prioritized):
     torch.manual_seed(42)
     worst = dict(c1=0.0, c2=0.0, q1=0.0)
     flips = 0
-    band_l, band_q = (0.10, 0.10) if prioritized else (0.02, 0.02)
+    band_l, band_q = (2e-3, 2e-3) if prioritized else (5e-4, 5e-4)
     for s in range(steps):
         e1, e2 = torch.randn(B, A), torch.randn(B, A)
         if prioritized:
@@ -168,16 +169,16 @@ def test_free_running_50_steps_stay_within_band_of_oracle(prioritized):
             res = orc.learn_on_batch(orc.replay.gather(idx), e1, e2, None)
             st = dev.learn(e1.numpy(), e2.numpy(), want_stats=True, batch_idx=idx)
             assert np.array_equal(dev.buffer("batch_idx")[:, 0].cpu().numpy(), idx)
-        for key, ref, got, band, ab in (("c1", res["critic_1_loss"], st["critic_1_loss"], band_l, 1e-3),
-                                        ("c2", res["critic_2_loss"], st["critic_2_loss"], band_l, 1e-3),
-                                        ("q1", float(res["q1"].mean()) if "q1" in res else None, st["q1_mean"], band_q, 2e-2)):
+        for key, ref, got, band, ab in (("c1", res["critic_1_loss"], st["critic_1_loss"], band_l, 1e-5),
+                                        ("c2", res["critic_2_loss"], st["critic_2_loss"], band_l, 1e-5),
+                                        ("q1", float(res["q1"].mean()) if "q1" in res else None, st["q1_mean"], band_q, 2e-4)):
             if ref is None:
                 continue
             dev_rel = abs(got - float(ref)) / (band * abs(float(ref)) + ab)
             worst[key] = max(worst[key], dev_rel)
     print(f"free-running {steps} steps prioritized={prioritized}: worst deviation / band = {worst}, PER index flips = {flips} of {steps * B}")
     assert all(np.isfinite(v) and v <= 1.0 for v in worst.values()), worst
-    assert flips <= 0.02 * steps * B
+    assert flips <= 0.002 * steps * B
 
 
 # ---- device RNG: distribution tests at n >= 1e5 -----------------------------------------------------------------------------------
