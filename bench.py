@@ -406,8 +406,9 @@ def run_ours(args):
         blk = torch.randn(D.TRANSITIONS_PER_EPISODE, T, device="cuda")
         blk[:, -1] = 0
         ex.warm(flat.numel(), D.TRANSITIONS_PER_EPISODE, T)
-        episodes = 3
+        episodes = 8
         t_bc = t_ag = 0.0
+        per_ep = []
         for ep in range(episodes + 1):          # first episode is warm-up
             if ep == 1:
                 barrier()
@@ -428,11 +429,12 @@ def run_ours(args):
             if ep >= 1:
                 t_bc += e0.elapsed_time(e1)
                 t_ag += e1.elapsed_time(e2)
+                per_ep.append(e0.elapsed_time(e2))
         barrier()
         dt = time.perf_counter() - t_all
         al = {"episodes": episodes, "actors": world - 1, "learner_steps_per_s": episodes * (world - 1) * 100 / dt,
               "exchange_ms_per_episode": (t_bc + t_ag) / episodes, "broadcast_ms_per_episode": t_bc / episodes,
-              "all_gather_ms_per_episode": t_ag / episodes,
+              "all_gather_ms_per_episode": t_ag / episodes, "exchange_ms_median": float(np.median(per_ep)),
               "bytes_per_episode": {"broadcast_actor": int(flat.numel() * 4), "gather_transitions_per_actor": int(blk.numel() * 4)}}
     if rank != 0:
         if world > 1:

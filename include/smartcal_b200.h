@@ -166,6 +166,13 @@ int sc_agent_act(sc_agent* a, const float* obs_host, const float* eps_host, floa
  *      Agent.update_network_parameters (enet_sac.py:523-542) ------------------------------------------ */
 int sc_agent_learn(sc_agent* a, const sc_noise* noise_or_null, sc_learn_stats* stats_host_or_null);
 int sc_agent_soft_update(sc_agent* a, float tau);
+/* The tensor-core GEMMs read every wide weight matrix as a pair of tf32 "big / small" copies that the library keeps next
+ * to the fp32 parameters (written by its own Adam kernels).  Handing out a parameter pointer (sc_agent_tensor with
+ * SC_SLOT_PARAM) or sc_agent_soft_update marks the copies stale and the next learn() re-derives them (one small kernel), so
+ * load_state_dict-style writes through FRESHLY obtained views need nothing more.  A caller that writes parameters through a
+ * pointer it obtained EARLIER (e.g. an NCCL broadcast into a cached view, distributed_per_sac.py:84-90) calls this after
+ * the write. */
+int sc_agent_params_changed(sc_agent* a);
 /* Agent.store_transition (enet_sac.py:544-545) followed by Agent.learn() as ONE call: the packed transition, the noise and
  * the sampling randomness travel in a single pinned block / host->device copy, the kernels replay from a CUDA graph.
  * Arguments as for sc_replay_store_host + sc_agent_learn. */

@@ -78,6 +78,7 @@ SIGNATURES = {
     "sc_agent_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sc_agent_learn": (C.c_int, [C.c_void_p, C.POINTER(ScNoise), C.POINTER(ScLearnStats)]),
     "sc_agent_soft_update": (C.c_int, [C.c_void_p, C.c_float]),
+    "sc_agent_params_changed": (C.c_int, [C.c_void_p]),
     "sc_agent_store_learn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.POINTER(ScNoise), C.POINTER(ScLearnStats)]),
     "sc_agent_set_stats_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "sc_ensemble_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]),

@@ -214,6 +214,11 @@ class DeviceAgent:
     def soft_update(self, tau):
         L.check(self.lib.sc_agent_soft_update(self.h, float(tau)))
 
+    def params_changed(self):
+        """call after writing parameters through a view obtained EARLIER (views obtained by tensor() right before the write
+        need nothing): the tf32 operand copies of the wide weight matrices are re-derived by the next learn()"""
+        L.check(self.lib.sc_agent_params_changed(self.h))
+
     def launch_count(self):
         return self.lib.sc_agent_launch_count(self.h)
 

@@ -30,6 +30,7 @@ int dense_tc_max_clusters(int cs);
 int dgrad_tc_max_clusters(int cs);
 cudaError_t launch_dgrad_tc(const DenseTcParams* pp, int E, int nops, int nrb, int N, int ks, cudaStream_t st);
 cudaError_t launch_gather_mb(const GatherP* pp, int E, int B, cudaStream_t st);
+cudaError_t launch_split(const SplitP* pp, int E, int grid, cudaStream_t st);
 cudaError_t launch_soft_update(const float* src, float* dst, size_t n, float tau, cudaStream_t st);
 cudaError_t launch_replay_store(const ReplayP& rp, const float* tr, int slot, int mode, double priority, double clip, cudaStream_t st);
 cudaError_t launch_replay_store_t(const StoreP* pp, int E, cudaStream_t st);
@@ -185,7 +186,7 @@ struct KernelTimer {
 // one host->device copy of the tape plus the launches, each kernel reading its parameters from the device copy
 // (blockIdx.y = agent).  Identical plans (same records, same tape offsets) are replayed as a CUDA graph.
 enum { KID_STORE = 0, KID_PER_SAMPLE, KID_UNIFORM, KID_GATHER, KID_DENSE, KID_ROW, KID_PER_UPDATE, KID_WGRAD, KID_WGRAD_TC, KID_HINT,
-       KID_ADMM, KID_TAIL, KID_DGRAD };
+       KID_ADMM, KID_TAIL, KID_DGRAD, KID_SPLIT };
 enum { REC_KERNEL = 0, REC_DATA, REC_FORK, REC_JOIN_RECORD, REC_JOIN_WAIT, REC_TBEGIN, REC_TEND };
 struct Rec {
   int type, kid, stream;           // stream: 0 main, 1 side (PER), 2 side2 (narrow weight gradients)
@@ -264,6 +265,14 @@ struct sc_agent {
   size_t online_floats;               // actor + c1 + c2
   float *params, *adam_m, *adam_v;    // online blocks
   float* targets;                     // SAC: t1,t2 ; TD3: ta,t1,t2
+  // tf32 big / small copies of the parameter and target blocks ([2][floats]: what the tcgen05 forward / dgrad GEMMs read as W).
+  // Kept current by the Adam epilogue of k_wgrad_tc; anything else that may have written parameters (a pointer handed out by
+  // sc_agent_tensor, sc_agent_soft_update, the FP32 weight-gradient fallback) sets split_dirty and the next learn() refreshes them.
+  float *params_hl, *targets_hl;
+  size_t target_floats;
+  bool split_dirty;
+  bool tc_covers[2];                  // [critic, actor]: every wide layer of that update runs in k_wgrad_tc (whose Adam epilogue writes the copies)
+  std::map<const float*, float*> hl_of;   // fp32 activation array -> its [big | small] copy
   size_t off_actor, off_c1, off_c2;   // within the online block
   size_t toff_actor, toff_c1, toff_c2;// within the target block
   ReplayP rp;
@@ -355,7 +364,10 @@ static size_t carve(sc_agent* a, void* base) {
   a->toff_actor = 0;
   a->toff_c1 = td3 ? a->La.size : 0;
   a->toff_c2 = a->toff_c1 + a->Lc.size;
-  a->targets = cv.f((td3 ? a->La.size : 0) + 2 * a->Lc.size);
+  a->target_floats = (td3 ? a->La.size : 0) + 2 * a->Lc.size;
+  a->targets = cv.f(a->target_floats);
+  a->params_hl = cv.f(2 * a->online_floats);
+  a->targets_hl = cv.f(2 * a->target_floats);
   // replay
   ReplayP& rp = a->rp;
   rp.C = C; rp.S = S; rp.Sp = Sp; rp.A = A; rp.Ap = Ap;
@@ -377,6 +389,12 @@ static size_t carve(sc_agent* a, void* base) {
     reg(name, p, B, width, width, 4);
     return p;
   };
+  a->hl_of.clear();
+  auto hl = [&](float* base, int width) {              // [big | small] copy of a tensor-core operand
+    float* p = cv.f((size_t)2 * B * width);
+    a->hl_of[base] = p;
+    return p;
+  };
   for (int k = 0; k < 2; ++k) {
     const std::string c = k == 0 ? "c1." : "c2.";
     CriticWs& w = a->cw[k];
@@ -388,12 +406,16 @@ static size_t carve(sc_agent* a, void* base) {
     w.p_h11 = mat(c + "p_h11", H1); w.p_h12 = mat(c + "p_h12", H2);
     const std::string t = k == 0 ? "t1." : "t2.";
     a->tw[k].h11 = mat(t + "h11", H1); a->tw[k].h12 = mat(t + "h12", H2);
+    w.h11_hl = hl(w.h11, H1); w.p_h11_hl = hl(w.p_h11, H1); w.dz11_hl = hl(w.dz11, H1); w.dz12_hl = hl(w.dz12, H2);
+    a->tw[k].h11_hl = hl(a->tw[k].h11, H1);
   }
   ActorWs& aw = a->aw;
   aw.t_h1 = mat("a.t_h1", H1); aw.t_h2 = mat("a.t_h2", H2);
   aw.h1 = mat("a.h1", H1); aw.zh1 = mat("a.zh1", H1); aw.rs1 = mat("a.rs1", 1); aw.du1 = mat("a.du1", H1); aw.dz1 = mat("a.dz1", H1);
   aw.h2 = mat("a.h2", H2); aw.zh2 = mat("a.zh2", H2); aw.rs2 = mat("a.rs2", 1); aw.du2 = mat("a.du2", H2); aw.dz2 = mat("a.dz2", H2);
   aw.h3 = mat("a.h3", H3); aw.zh3 = mat("a.zh3", H3); aw.rs3 = mat("a.rs3", 1); aw.du3 = mat("a.du3", H3); aw.dz3 = mat("a.dz3", H3);
+  aw.t_h1_hl = hl(aw.t_h1, H1); aw.h1_hl = hl(aw.h1, H1); aw.dz1_hl = hl(aw.dz1, H1); aw.dz2_hl = hl(aw.dz2, H2);
+  aw.h2_hl = hl(aw.h2, H2); aw.dz3_hl = hl(aw.dz3, H3);     // fc3 of the actor (128 x 256) is a tensor-core weight gradient too
   aw.dhead = mat("a.dhead", 2 * A); aw.pi = mat("a.pi", A); aw.logp = mat("a.logp", 1); aw.qmin = mat("a.qmin", 1);
   a->y = mat("y", 1);
   a->err = mat("err", 1);
@@ -426,9 +448,11 @@ static size_t carve(sc_agent* a, void* base) {
   a->mb_s = cv.f((size_t)B * a->Sp32);
   a->mb_s2 = cv.f((size_t)B * a->Sp32);
   a->mb_hl = cv.f((size_t)4 * B * a->Sp32);
+  a->hl_of[a->mb_s] = a->mb_hl;
+  a->hl_of[a->mb_s2] = a->mb_hl + (size_t)2 * B * a->Sp32;
   reg("mb_state", a->mb_s, B, S, a->Sp32, 4);
   reg("mb_new_state", a->mb_s2, B, S, a->Sp32, 4);
-  a->tmaps = (unsigned char*)cv.take(128 * 96);
+  a->tmaps = (unsigned char*)cv.take(128 * 128);
   a->obs_dev = cv.f(a->Sp32);
   a->act_eps = cv.f(round4i(A));
   a->act_out = cv.f(round4i(A));
@@ -440,7 +464,7 @@ static size_t carve(sc_agent* a, void* base) {
   a->actor_tc_ops = (WgradTcOp*)cv.take(sizeof(WgradTcOp) * 8);
   a->critic_tc_map = (int*)cv.take(sizeof(int) * 512);
   a->actor_tc_map = (int*)cv.take(sizeof(int) * 512);
-  a->tmaps_tc = (unsigned char*)cv.take(128 * 32);
+  a->tmaps_tc = (unsigned char*)cv.take(128 * 48);
   a->critic_ops = (WgradOp*)cv.take(sizeof(WgradOp) * 16);
   a->actor_ops = (WgradOp*)cv.take(sizeof(WgradOp) * 8);
   a->critic_vops = (VecOp*)cv.take(sizeof(VecOp) * 32);
@@ -549,7 +573,7 @@ static int encode_map(CUtensorMap* out, const void* base, int ld, int rows, int 
 
 static int build_tensor_maps(sc_agent* a) {
   std::vector<CUtensorMap> host;
-  host.reserve(96);
+  host.reserve(128);
   int rc = SC_OK;
   auto add = [&](const void* base, int ld, int rows, int box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) -> const void* {
     alignas(64) CUtensorMap m;
@@ -603,6 +627,21 @@ static int build_tensor_maps(sc_agent* a) {
   const void *d_on_w1 = nullptr, *d_on_w2 = nullptr, *d_tg_w1 = nullptr, *d_tg_w2 = nullptr;
   {
     const int DB = 128, DW = 64;               // box rows: 128 batch rows, 64 output features (sc_dense_tc.cu tile)
+    // every tensor-core operand is read as its tf32 big / small parts: two consecutive maps (big, then small) per matrix
+    auto add2 = [&](const float* hlbase, size_t plane, int ld, int rows, int box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) -> const void* {
+      const void* first = add(hlbase, ld, rows, box_rows, swz);
+      add(hlbase + plane, ld, rows, box_rows, swz);
+      return first;
+    };
+    auto act2 = [&](const float* fp32, int width, int box_rows) { return add2(a->hl_of.at(fp32), (size_t)B * width, width, B, box_rows); };
+    auto w_hl = [&](const float* W) -> const float* {            // big part of a weight matrix; the small part is one block further
+      if (W >= a->params && W < a->params + a->online_floats) return a->params_hl + (W - a->params);
+      return a->targets_hl + (W - a->targets);
+    };
+    auto w_plane = [&](const float* W) -> size_t { return (W >= a->params && W < a->params + a->online_floats) ? a->online_floats : a->target_floats; };
+    auto wt2 = [&](const float* W, int ld, int rows, int box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+      return add2(w_hl(W), w_plane(W), ld, rows, box_rows, swz);
+    };
     d.mb_s = add(a->mb_s, K1, B, DB);
     d.mb_s2 = add(a->mb_s2, K1, B, DB);
     const size_t plane = (size_t)B * K1;
@@ -610,34 +649,34 @@ static int build_tensor_maps(sc_agent* a) {
     a->tmd_s_lo = add(a->mb_hl + plane, K1, B, DB);
     a->tmd_s2_hi = add(a->mb_hl + 2 * plane, K1, B, DB);
     a->tmd_s2_lo = add(a->mb_hl + 3 * plane, K1, B, DB);
-    d.t_h1 = add(a->aw.t_h1, H1, B, DB);
-    d.h1 = add(a->aw.h1, H1, B, DB);
+    d.t_h1 = act2(a->aw.t_h1, H1, DB);
+    d.h1 = act2(a->aw.h1, H1, DB);
     for (int k = 0; k < 2; ++k) {
-      d.th11[k] = add(a->tw[k].h11, H1, B, DB);
-      d.ch11[k] = add(a->cw[k].h11, H1, B, DB);
-      d.ph11[k] = add(a->cw[k].p_h11, H1, B, DB);
-      d.crit_w11[k] = add(C[k].w11, K1, H1, DW);
-      d.crit_w12[k] = add(C[k].w12, H1, H2, DW);
-      d.targ_w11[k] = add(T[k].w11, K1, H1, DW);
-      d.targ_w12[k] = add(T[k].w12, H1, H2, DW);
+      d.th11[k] = act2(a->tw[k].h11, H1, DB);
+      d.ch11[k] = act2(a->cw[k].h11, H1, DB);
+      d.ph11[k] = act2(a->cw[k].p_h11, H1, DB);
+      d.crit_w11[k] = wt2(C[k].w11, K1, H1, DW);
+      d.crit_w12[k] = wt2(C[k].w12, H1, H2, DW);
+      d.targ_w11[k] = wt2(T[k].w11, K1, H1, DW);
+      d.targ_w12[k] = wt2(T[k].w12, H1, H2, DW);
     }
-    d_on_w1 = add(on.w1, K1, H1, DW);
-    d_on_w2 = add(on.w2, H1, H2, DW);
+    d_on_w1 = wt2(on.w1, K1, H1, DW);
+    d_on_w2 = wt2(on.w2, H1, H2, DW);
     for (int k = 0; k < 2; ++k) {
-      a->tmg_dz12[k] = add(a->cw[k].dz12, H2, B, DB);
-      a->tmg_w12p[k] = add(C[k].w12, H1, H2, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+      a->tmg_dz12[k] = act2(a->cw[k].dz12, H2, DB);
+      a->tmg_w12p[k] = wt2(C[k].w12, H1, H2, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     }
-    a->tmg_dz2 = add(a->aw.dz2, H2, B, DB);
-    a->tmg_w2p = add(on.w2, H1, H2, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    a->tmg_dz2 = act2(a->aw.dz2, H2, DB);
+    a->tmg_w2p = wt2(on.w2, H1, H2, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     d_tg_w1 = d_on_w1; d_tg_w2 = d_on_w2;
     if (td3) {
       ActorP tg = actor_ptrs(a->targets + a->toff_actor, a->La, a->cfg.kind);
-      d_tg_w1 = add(tg.w1, K1, H1, DW);
-      d_tg_w2 = add(tg.w2, H1, H2, DW);
+      d_tg_w1 = wt2(tg.w1, K1, H1, DW);
+      d_tg_w2 = wt2(tg.w2, H1, H2, DW);
     }
   }
   if (rc != SC_OK) return rc;
-  if (host.size() > 96) return fail(SC_ERR_STATE, "tensor map table overflow");
+  if (host.size() > 128) return fail(SC_ERR_STATE, "tensor map table overflow");
   a->tmd_critic = d; a->tmd_actor = d;
   a->tmd_critic.actor_w1 = td3 ? d_tg_w1 : d_on_w1;
   a->tmd_critic.actor_w2 = td3 ? d_tg_w2 : d_on_w2;
@@ -660,15 +699,25 @@ static int upload_tc_tables(sc_agent* a, const std::vector<TcCand>& cand, WgradT
   int tiles = 0;
   for (const TcCand& c : cand) {
     WgradTcOp o;
-    alignas(64) CUtensorMap md, mx;
-    int rc = encode_map(&md, c.D, c.ldd, a->B, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-    if (rc == SC_OK) rc = encode_map(&mx, c.X, c.ldx, a->B, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    // operands as tf32 big / small parts: two consecutive maps each (the kernel addresses the small part as map + 1)
+    alignas(64) CUtensorMap md[2], mx[2];
+    auto dh = a->hl_of.find(c.D), xh = a->hl_of.find(c.X);
+    if (dh == a->hl_of.end() || xh == a->hl_of.end()) return fail(SC_ERR_STATE, "tcgen05 wgrad operand without a big / small copy");
+    int rc = SC_OK;
+    for (int part = 0; part < 2 && rc == SC_OK; ++part) {
+      rc = encode_map(&md[part], dh->second + (size_t)part * a->B * c.ldd, c.ldd, a->B, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+      if (rc == SC_OK) rc = encode_map(&mx[part], xh->second + (size_t)part * a->B * c.ldx, c.ldx, a->B, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    }
     if (rc != SC_OK) return rc;
-    maps.push_back(md);
+    maps.push_back(md[0]);
     o.mapD = a->tmaps_tc + (maps.size() - 1) * sizeof(CUtensorMap);
-    maps.push_back(mx);
+    maps.push_back(md[1]);
+    maps.push_back(mx[0]);
     o.mapX = a->tmaps_tc + (maps.size() - 1) * sizeof(CUtensorMap);
+    maps.push_back(mx[1]);
     o.N = c.N; o.K = c.K; o.W = c.W; o.M = c.M; o.V = c.V; o.T = c.T; o.ldw = c.ldw; o.opt = c.opt;
+    o.Whi = a->params_hl + (c.W - a->params); o.Wlo = o.Whi + a->online_floats;
+    o.Thi = c.T ? a->targets_hl + (c.T - a->targets) : nullptr; o.Tlo = c.T ? o.Thi + a->target_floats : nullptr;
     o.tiles_k = (c.K + 63) / 64;
     o.tile_base = tiles;
     o.tile_count = (c.N / 128) * o.tiles_k;
@@ -676,7 +725,7 @@ static int upload_tc_tables(sc_agent* a, const std::vector<TcCand>& cand, WgradT
     tiles += o.tile_count;
     ops.push_back(o);
   }
-  if (ops.size() > 8 || tiles > 512 || maps.size() > 32) return fail(SC_ERR_STATE, "tcgen05 wgrad table overflow");
+  if (ops.size() > 8 || tiles > 512 || maps.size() > 48) return fail(SC_ERR_STATE, "tcgen05 wgrad table overflow");
   nops = (int)ops.size(); ntiles = tiles;
   if (!ops.empty()) {
     CK(cudaMemcpyAsync(dev_ops, ops.data(), ops.size() * sizeof(WgradTcOp), cudaMemcpyHostToDevice, a->st));
@@ -782,6 +831,14 @@ static int build_op_tables(sc_agent* a) {
     if (!td3) add_v(avv, tiles, w.dhead + A, nullptr, ldh, A, P.bls, M.bls, V.bls, T.bls, 0);
   }
   g_tc_sink = nullptr;
+  {
+    // are all the weights k_dense_tc reads (fc1 / fc2 of every network) updated by the tensor-core kernel?
+    int nc = 0, na = 0;
+    for (const TcCand& c : tc_critic) nc += (c.K == a->S || c.K == H1) ? 1 : 0;
+    for (const TcCand& c : tc_actor) na += (c.N == H1 || c.N == H2) ? 1 : 0;
+    a->tc_covers[0] = nc == 4;
+    a->tc_covers[1] = na == 2;
+  }
   a->n_actor_ops = (int)awv.size(); a->n_actor_vops = (int)avv.size(); a->actor_tiles = tiles;
   {
     int rc = upload_tc_tables(a, tc_critic, a->critic_tc_ops, a->critic_tc_map, a->n_critic_tc, a->critic_tc_tiles, tc_maps);
@@ -896,6 +953,7 @@ int sc_agent_create(const sc_config* cfg, void* arena, size_t arena_bytes, void*
   a->per_beta = 0.4;   // PER.beta, enet_sac.py:210
   a->batch_ready = false;
   a->presampled = false; a->quiet = false; a->presample_beta = 0.0; a->sample_ctr = 0;
+  a->split_dirty = true;
   a->alpha = (float)cfg->alpha;
   a->rho = 0.f;
   a->admm_rho = cfg->admm_rho;
@@ -964,6 +1022,7 @@ int sc_agent_tensor(sc_agent* a, int net, int slot, const char* name, sc_tensor_
   const NetLayout* L = nullptr;
   float* base = net_base(a, net, slot, &L);
   if (!base) return fail(SC_ERR_ARG, "network %d / slot %d does not exist for this agent kind", net, slot);
+  if (slot == SC_SLOT_PARAM) a->split_dirty = true;    // the caller may write through this pointer: re-derive the tf32 operand copies before the next step
   if (strcmp(name, "*") == 0) {
     out->dev_ptr = base; out->rows = 1; out->cols = (int64_t)L->size; out->pitch = (int64_t)L->size; out->elem_bytes = 4; out->is_int = 0;
     return SC_OK;
@@ -1320,6 +1379,34 @@ static int emit_ctl(sc_agent* a, int type, int which) {
 }
 #define PL(ptr) do { if ((ptr) == nullptr) return SC_ERR_STATE; } while (0)
 
+// tf32 big / small copies written by k_split: the paths whose producer kernel does not write them itself (fallback kernels
+// selected by SMARTCAL_DENSE / _TAIL / _DGRAD / _WGRAD, parameters written from outside)
+struct SplitItem { const float* src; float* hl; size_t count, plane; };
+static int plan_split(sc_agent* a, const std::vector<SplitItem>& items) {
+  if (items.empty()) return SC_OK;
+  if (items.size() > 12) return fail(SC_ERR_STATE, "split list overflow");
+  size_t total = 0;
+  for (const SplitItem& it : items) total += it.count;
+  int grid = (int)((total / 4 + 1023) / 1024);
+  if (grid < 1) grid = 1;
+  if (grid > 2 * a->sm_count) grid = 2 * a->sm_count;
+  SplitP* sp = emit_kernel<SplitP>(a, KID_SPLIT, 0, grid);
+  PL(sp);
+  memset(sp, 0, sizeof(SplitP));
+  sp->n = (int)items.size();
+  for (size_t i = 0; i < items.size(); ++i) {
+    sp->src[i] = items[i].src; sp->hl[i] = items[i].hl; sp->count[i] = (unsigned)items[i].count; sp->plane[i] = (unsigned)items[i].plane;
+  }
+  return SC_OK;
+}
+static int plan_split_weights(sc_agent* a) {
+  return plan_split(a, {SplitItem{a->params, a->params_hl, a->online_floats, a->online_floats},
+                        SplitItem{a->targets, a->targets_hl, a->target_floats, a->target_floats}});
+}
+static void split_act(const sc_agent* a, std::vector<SplitItem>& v, const float* fp32, int width) {
+  v.push_back(SplitItem{fp32, a->hl_of.at(fp32), (size_t)a->B * width, (size_t)a->B * width});
+}
+
 // The two wide forward layers of a batched phase as tcgen05 launches (sc_dense_tc.cu); the op lists mirror the dense(...)
 // tables of k_rowphase (sc_rowphase_impl.cuh, PROG_CRITIC / PROG_ACTOR).
 static int plan_dense_tc(sc_agent* a, const RowPhaseParams& p) {
@@ -1339,8 +1426,9 @@ static int plan_dense_tc(sc_agent* a, const RowPhaseParams& p) {
   auto op = [&](const void* mx1, const void* mw1, const float* b1, const float* g1, const float* be1, float* h1, float* zh1, float* rs1,
                 const void* mx2, const void* mw2, const float* b2, const float* g2, const float* be2, float* h2, float* zh2, float* rs2) {
     const bool next = mx1 == m.mb_s2;
-    d1.ops[n] = DenseTcOp{next ? a->tmd_s2_hi : a->tmd_s_hi, next ? a->tmd_s2_lo : a->tmd_s_lo, mw1, b1, g1, be1, h1, zh1, rs1, K1};
-    d2.ops[n] = DenseTcOp{mx2, nullptr, mw2, b2, g2, be2, h2, zh2, rs2, H1};
+    // (tmd_s*_hi / _lo are consecutive table entries, like every big / small pair)
+    d1.ops[n] = DenseTcOp{next ? a->tmd_s2_hi : a->tmd_s_hi, mw1, b1, g1, be1, h1, zh1, rs1, K1, nullptr, nullptr, a->hl_of.at(h1)};
+    d2.ops[n] = DenseTcOp{mx2, mw2, b2, g2, be2, h2, zh2, rs2, H1, nullptr, nullptr, a->hl_of.count(h2) ? a->hl_of.at(h2) : nullptr};
     ++n;
   };
   if (critic) {
@@ -1416,12 +1504,12 @@ static int plan_rowphase(sc_agent* a, const RowPhaseParams& p_in, int timer_id) 
         g.N = H1; g.B = p.B; g.nrb = (p.B + 127) / 128; g.ks = 1; g.late_trigger = 0;
         if (p.program == PROG_CRITIC) {
           for (int k = 0; k < 2; ++k) {
-            g.ops[k] = DenseTcOp{a->tmg_dz12[k], nullptr, a->tmg_w12p[k], nullptr, p.crit[k].g11, nullptr, p.cw[k].h11, p.cw[k].zh11, p.cw[k].rs11, H2,
-                                 p.cw[k].du11, p.cw[k].dz11};
+            g.ops[k] = DenseTcOp{a->tmg_dz12[k], a->tmg_w12p[k], nullptr, p.crit[k].g11, nullptr, p.cw[k].h11, p.cw[k].zh11, p.cw[k].rs11, H2,
+                                 p.cw[k].du11, p.cw[k].dz11, p.cw[k].dz11_hl};
           }
           g.nops = 2;
         } else {
-          g.ops[0] = DenseTcOp{a->tmg_dz2, nullptr, a->tmg_w2p, nullptr, p.actor.g1, nullptr, p.aw.h1, p.aw.zh1, p.aw.rs1, H2, p.aw.du1, p.aw.dz1};
+          g.ops[0] = DenseTcOp{a->tmg_dz2, a->tmg_w2p, nullptr, p.actor.g1, nullptr, p.aw.h1, p.aw.zh1, p.aw.rs1, H2, p.aw.du1, p.aw.dz1, p.aw.dz1_hl};
           g.nops = 1;
         }
         DenseTcParams* gp = emit_kernel<DenseTcParams>(a, KID_DGRAD, 0, g.nops, g.nrb, g.N, g.ks);
@@ -1435,6 +1523,23 @@ static int plan_rowphase(sc_agent* a, const RowPhaseParams& p_in, int timer_id) 
   RowPhaseParams* t = emit_kernel<RowPhaseParams>(a, KID_ROW, 0, a->row_variant, a->cluster_size, a->nclusters, a->tile_tm);
   PL(t);
   *t = p;
+  if (a->use_tc && p.program != PROG_ACT) {
+    // k_rowphase writes fp32 only: the tcgen05 weight-gradient kernel reads big / small parts
+    std::vector<SplitItem> v;
+    const bool critic = p.program == PROG_CRITIC;
+    if (!p.skip_dense) {
+      v.push_back(SplitItem{a->mb_s, a->mb_hl, (size_t)a->B * a->Sp32, (size_t)a->B * a->Sp32});
+      if (critic) { split_act(a, v, a->cw[0].h11, H1); split_act(a, v, a->cw[1].h11, H1); }
+      else { split_act(a, v, a->aw.h1, H1); split_act(a, v, a->aw.h2, H2); }
+    }
+    if (!p.skip_tail) {
+      if (critic) { split_act(a, v, a->cw[0].dz12, H2); split_act(a, v, a->cw[1].dz12, H2); }
+      else { split_act(a, v, a->aw.dz2, H2); split_act(a, v, a->aw.dz3, H3); }
+    }
+    if (critic) { split_act(a, v, a->cw[0].dz11, H1); split_act(a, v, a->cw[1].dz11, H1); }
+    else split_act(a, v, a->aw.dz1, H1);
+    if ((rc = plan_split(a, v))) return rc;
+  }
   if (timer_id >= 0 && a->timing && (rc = emit_ctl(a, REC_TEND, timer_id))) return rc;
   return SC_OK;
 }
@@ -1489,6 +1594,8 @@ static int plan_wgrad(sc_agent* a, const WgradParams& w, int timer_id) {
     PL(wp);
     *wp = w;
   }
+  // wide layers updated by the FP32 kernel (SMARTCAL_WGRAD=ffma, or a layer too small for the tensor-core tiles): refresh the operand copies
+  if (a->dense_tc && !a->tc_covers[actor ? 1 : 0] && (rc = plan_split_weights(a))) return rc;
   if (a->timing && (rc = emit_ctl(a, REC_TEND, timer_id))) return rc;
   return SC_OK;
 }
@@ -1545,6 +1652,12 @@ int sc_agent_soft_update(sc_agent* a, float tau) {
     CK(launch_soft_update(a->params + a->off_actor, a->targets + a->toff_actor, a->La.size, tau, a->st));
     a->launches++;
   }
+  a->split_dirty = true;
+  return SC_OK;
+}
+int sc_agent_params_changed(sc_agent* a) {
+  if (!a) return fail(SC_ERR_ARG, "null agent");
+  a->split_dirty = true;
   return SC_OK;
 }
 
@@ -1616,6 +1729,10 @@ static int plan_step(sc_agent* a, const StepArgs& sa, StepOut& so) {
   }
   if (a->mem_cntr < a->B) return SC_OK;   // enet_sac.py:556-557
   so.did_learn = true;
+  if (a->split_dirty) {                   // parameters may have been written from outside since the last step (group_step levels the flag across an ensemble)
+    if (a->dense_tc && (rc = plan_split_weights(a))) return rc;
+    a->split_dirty = false;
+  }
   const bool sac = a->cfg.kind == SC_KIND_SAC;
   const bool per = a->cfg.prioritized != 0;
   const bool was_quiet = a->quiet;          // nothing touched the replay state since the previous learn() returned
@@ -1871,6 +1988,7 @@ static cudaError_t issue_recs(sc_group* g, cudaStream_t st0) {
           case KID_ADMM: e = launch_admm_update(reinterpret_cast<const AdmmP*>(pp), g->E, st); break;
           case KID_TAIL: e = launch_tail(reinterpret_cast<const RowPhaseParams*>(pp), g->E, r.g[0], st); break;
           case KID_DGRAD: e = launch_dgrad_tc(reinterpret_cast<const DenseTcParams*>(pp), g->E, r.g[0], r.g[1], r.g[2], r.g[3], st); break;
+          case KID_SPLIT: e = launch_split(reinterpret_cast<const SplitP*>(pp), g->E, r.g[0], st); break;
           default: e = cudaErrorInvalidValue;
         }
         break;
@@ -1970,6 +2088,11 @@ static int group_step(sc_group* g, const StepArgs* args, sc_learn_stats* stats_h
   int rc = group_begin(g);
   if (rc) return rc;
   std::vector<StepOut> so(g->E);
+  {
+    bool dirty = false;
+    for (int i = 0; i < g->E; ++i) dirty = dirty || g->ag[i]->split_dirty;
+    for (int i = 0; i < g->E; ++i) g->ag[i]->split_dirty = dirty;
+  }
   for (int i = 0; i < g->E; ++i) {
     if (stats_host) memset(&stats_host[i], 0, sizeof(sc_learn_stats));
     if ((rc = plan_step(g->ag[i], args[i], so[i]))) break;

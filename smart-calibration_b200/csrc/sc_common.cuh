@@ -129,6 +129,22 @@ __device__ __forceinline__ float group8_sum(float v) {  // sum over aligned grou
 
 // ---- activation -----------------------------------------------------------------------------------------
 // F.elu, alpha = 1: x > 0 ? x : exp(x) - 1   (ATen computes exp(x) - 1, not expm1)
+// x = big + small with big = x rounded to tf32 (so the tensor core's truncation leaves it unchanged) and small = the
+// remainder rounded to tf32: the operand pair of the 3xTF32 products.  Every producer of a tensor-core operand (gather,
+// dense / dgrad epilogues, tail, Adam epilogue, k_split) writes the two parts next to the fp32 array ("hl" = [big | small]).
+__device__ __forceinline__ void split_rn(float x, float& big, float& small) {
+  uint32_t b, s;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(x));
+  big = __uint_as_float(b);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(s) : "f"(x - big));
+  small = __uint_as_float(s);
+}
+__device__ __forceinline__ void split_rn4(const float4 x, float4& big, float4& small) {
+  split_rn(x.x, big.x, small.x);
+  split_rn(x.y, big.y, small.y);
+  split_rn(x.z, big.z, small.z);
+  split_rn(x.w, big.w, small.w);
+}
 __device__ __forceinline__ float elu(float x) { return x > 0.f ? x : expf(x) - 1.f; }
 // d elu / dx expressed through the OUTPUT h: 1 for h > 0, exp(x) = h + 1 otherwise
 __device__ __forceinline__ float elu_grad_from_out(float h) { return h > 0.f ? 1.f : h + 1.f; }

@@ -7,14 +7,14 @@
 //
 // Both operands are K-major (X [rows][K], W [features][K]): TMA boxes of [128 rows][32 floats] with the 128-byte swizzle,
 // described to the MMA as 8-row atoms of 1024 B (SBO), +32 B per 8-deep k-step.  kind::tf32 truncates its fp32 inputs to 10
-// mantissa bits, so fp32 fidelity is restored with three products per k-step, X_lo W + X W_lo + X W: the splitter warps
-// round every raw box to tf32 in place (big part) and write the rounded remainder (small part) next to it.
+// mantissa bits, so fp32 fidelity is restored with three products per k-step, X_lo W + X W_lo + X W.  Both operands arrive
+// already split into tf32 big / small parts: whoever produces a tensor-core operand (k_gather_mb, the epilogues below, k_tail,
+// the Adam epilogue of k_wgrad_tc, k_split) writes the two parts once, so the K loop here is TMA -> MMA with nothing in between.
 //
-// Warp roles (512 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue (one thread), warps 2..15 =
-// big/small split; epilogue on all 16 warps: warp w reads TMEM lanes 32 (w & 3).. (its rows) x columns 16 (w >> 2).. (its features).
-// The operand traffic of three SS-mode products per k-step makes the loop shared-memory-bandwidth bound (per 8-deep k-step
-// the tensor core reads 3 (M + N) 32 B, TMA and the split move another 4 (M + N) 32 B), which is why the tile is only 64 wide:
-// more, smaller CTAs put more SMs' shared memory to work.  For the same reason the reduction can be split over a CTA pair
+// Warp roles (512 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue (one thread); epilogue on all 16
+// warps: warp w reads TMEM lanes 32 (w & 3).. (its rows) x columns 16 (w >> 2).. (its features).
+// A CTA's K loop is a chain of TMA round trips, which is why the tile is only 64 wide: more, smaller CTAs run more of those
+// chains side by side.  For the same reason the reduction can be split over a CTA pair
 // (DenseTcParams.ks = 2: cluster = feature blocks x 2, the second CTA's accumulators travel through distributed shared memory).
 // Launched with programmatic dependent launch: everything up to pdl_wait() overlaps the previous kernel.
 #include "sc_common.cuh"
@@ -26,8 +26,8 @@ constexpr int DT_M = 128, DT_N = 64;                         // batch rows / out
 constexpr int DT_STAGES = 3;
 constexpr int DT_CW = DT_N / 4;                              // epilogue: features per thread
 constexpr int DT_X_BYTES = DT_M * 128, DT_W_BYTES = DT_N * 128;   // one k-chunk of 32 floats
-constexpr int DT_STAGE_BYTES = 2 * (DT_X_BYTES + DT_W_BYTES);     // raw + lo: 64 KB
-constexpr int DT_THREADS = 512, DT_SPLIT_THREADS = DT_THREADS - 64;
+constexpr int DT_STAGE_BYTES = 2 * (DT_X_BYTES + DT_W_BYTES);     // big + small parts: 48 KB
+constexpr int DT_THREADS = 512;
 constexpr int DT_MAXCS = 8;
 constexpr int DT_TP = DT_N + 4;                              // output tile pitch (floats)
 static_assert(2 * DT_M * DT_TP * 4 <= DT_STAGE_BYTES * DT_STAGES, "output tiles must fit in the operand ring");
@@ -59,15 +59,6 @@ __device__ __forceinline__ void dt_mma(uint32_t tmem_d, uint64_t da, uint64_t db
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// x = big + small with big = x rounded to tf32 (so the tensor core's truncation leaves it unchanged) and small = the
-// remainder rounded to tf32 (round-to-nearest halves the dropped small*small term against a truncating split)
-__device__ __forceinline__ void split_rn(float x, float& big, float& small) {
-  uint32_t b, s;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(x));
-  big = __uint_as_float(b);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(s) : "f"(x - big));
-  small = __uint_as_float(s);
-}
 __device__ __forceinline__ void dt_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -82,7 +73,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc_t(const DenseTcParam
   const DenseTcParams& p = load_params(pp, &p_sm);             // blockIdx.y = agent of the ensemble
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_raw[DT_STAGES], full_lo[DT_STAGES], empty[DT_STAGES], acc_done;
+  __shared__ __align__(8) uint64_t full[DT_STAGES], empty[DT_STAGES], acc_done;
   __shared__ uint32_t tmem_slot;
   __shared__ float psum[4][DT_M], pm2[4][DT_M];
   __shared__ __align__(16) float svec[3][DT_N];             // bias, gamma, beta of this CTA's features
@@ -120,8 +111,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc_t(const DenseTcParam
   if (tid < 3) tln[tid] = 0;
   if (tid == 0) {
     for (int i = 0; i < DT_STAGES; ++i) {
-      mbar_init(full_raw + i, 1);
-      mbar_init(full_lo + i, DT_SPLIT_THREADS / 32);
+      mbar_init(full + i, 1);
       mbar_init(empty + i, 1);
     }
     mbar_init(&acc_done, 1);
@@ -150,18 +140,22 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc_t(const DenseTcParam
       uint8_t* st = smem + (size_t)slot * DT_STAGE_BYTES;
       if (lane == 0) {
         mark(0, 1);
-        mbar_expect_tx(full_raw + slot, DT_X_BYTES + DT_W_BYTES + (op.mapXlo ? DT_X_BYTES : 0));
-        tma_load_2d(reinterpret_cast<float*>(st), op.mapX, 32 * (kc0 + s), r0, full_raw + slot);
-        if constexpr (MODE == 0) {
-          tma_load_2d(reinterpret_cast<float*>(st + DT_X_BYTES), op.mapW, 32 * (kc0 + s), n0, full_raw + slot);
-        } else {          // two panels [32 reduction rows][32 output columns]
-          tma_load_2d(reinterpret_cast<float*>(st + DT_X_BYTES), op.mapW, n0, 32 * (kc0 + s), full_raw + slot);
-          tma_load_2d(reinterpret_cast<float*>(st + DT_X_BYTES + 4096), op.mapW, n0 + 32, 32 * (kc0 + s), full_raw + slot);
-        }
-        if (op.mapXlo)        // pre-split X: the small part goes straight to where the splitter would have written it
-          tma_load_2d(reinterpret_cast<float*>(st + DT_X_BYTES + DT_W_BYTES), op.mapXlo, 32 * (kc0 + s), r0, full_raw + slot);
+        mbar_expect_tx(full + slot, DT_STAGE_BYTES);
       }
       __syncwarp();
+      // stage layout: [X big | W big | X small | W small]; lanes 0 / 1 fetch the big / small parts (the small part's map follows the big part's)
+      if (lane < 2) {
+        const void* mx = reinterpret_cast<const uint8_t*>(op.mapX) + 128 * lane;
+        const void* mw = reinterpret_cast<const uint8_t*>(op.mapW) + 128 * lane;
+        uint8_t* sp = st + lane * (DT_X_BYTES + DT_W_BYTES);
+        tma_load_2d(reinterpret_cast<float*>(sp), mx, 32 * (kc0 + s), r0, full + slot);
+        if constexpr (MODE == 0) {
+          tma_load_2d(reinterpret_cast<float*>(sp + DT_X_BYTES), mw, 32 * (kc0 + s), n0, full + slot);
+        } else {          // two panels [32 reduction rows][32 output columns]
+          tma_load_2d(reinterpret_cast<float*>(sp + DT_X_BYTES), mw, n0, 32 * (kc0 + s), full + slot);
+          tma_load_2d(reinterpret_cast<float*>(sp + DT_X_BYTES + 4096), mw, n0 + 32, 32 * (kc0 + s), full + slot);
+        }
+      }
     }
   } else if (warp == 1) {
     // ---------------- MMA issue (one thread) ----------------
@@ -177,7 +171,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc_t(const DenseTcParam
     constexpr uint64_t WSTEP = MODE == 0 ? 2 : 64;             // B operand advance per 8-deep k-step: +32 B (K-major) / +1024 B (MN-major)
     for (int s = 0; s < nk; ++s) {
       const int slot = s % DT_STAGES;
-      mbar_wait(full_lo + slot, (s / DT_STAGES) & 1u);
+      mbar_wait(full + slot, (s / DT_STAGES) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (leader) {
         mark(1, 2);
@@ -196,34 +190,12 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc_t(const DenseTcParam
       __syncwarp();
     }
   } else {
-    // ---------------- splitter warps: big = rna_tf32(x) in place, small = rna_tf32(x - big) next to it (same swizzled layout) ----------------
+    // ---------------- the other warps: this CTA's bias / LayerNorm vectors ----------------
     const int wl = tid - 64;
     if (wl < 3 * DT_N) {
       const int a = wl / DT_N, j = wl - a * DT_N;
       const float* src = a == 0 ? op.bias : a == 1 ? op.gamma : op.beta;
       svec[a][j] = src ? ld_w(src + n0 + j) : 0.f;            // (made visible to the epilogue by its first __syncthreads)
-    }
-    for (int s = 0; s < nk; ++s) {
-      const int slot = s % DT_STAGES;
-      mbar_wait(full_raw + slot, (s / DT_STAGES) & 1u);
-      if (wl == 0) mark(2, 4);
-      float4* raw = reinterpret_cast<float4*>(smem + (size_t)slot * DT_STAGE_BYTES);
-      float4* lo = reinterpret_cast<float4*>(smem + (size_t)slot * DT_STAGE_BYTES + DT_X_BYTES + DT_W_BYTES);
-#pragma unroll 5
-      for (int i = (op.mapXlo ? DT_X_BYTES / 16 : 0) + wl; i < (DT_X_BYTES + DT_W_BYTES) / 16; i += DT_SPLIT_THREADS) {
-        const float4 x = raw[i];
-        float4 h, y;
-        split_rn(x.x, h.x, y.x);
-        split_rn(x.y, h.y, y.y);
-        split_rn(x.z, h.z, y.z);
-        split_rn(x.w, h.w, y.w);
-        raw[i] = h;
-        lo[i] = y;
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic stores -> visible to the tensor core's reads
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full_lo + slot);
-      if (wl == 0) mark(2, 5);
     }
   }
   // ---------------- epilogue (all warps): bias, LayerNorm across the cluster, ELU, stores ----------------
@@ -353,7 +325,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc_t(const DenseTcParam
       if (r0 + r < p.B) {
         const size_t off = (size_t)(r0 + r) * p.N + n0 + 4 * c4;
         *reinterpret_cast<float4*>(op.DU + off) = *reinterpret_cast<const float4*>(tile_u + r * DT_TP + 4 * c4);
-        *reinterpret_cast<float4*>(op.DZ + off) = *reinterpret_cast<const float4*>(tile_d + r * DT_TP + 4 * c4);
+        const float4 d4 = *reinterpret_cast<const float4*>(tile_d + r * DT_TP + 4 * c4);
+        *reinterpret_cast<float4*>(op.DZ + off) = d4;
+        if (op.OUThl != nullptr) {                            // dZ is the next operand of the layer-1 weight gradient
+          float4 big, small;
+          split_rn4(d4, big, small);
+          *reinterpret_cast<float4*>(op.OUThl + off) = big;
+          *reinterpret_cast<float4*>(op.OUThl + (size_t)p.B * p.N + off) = small;
+        }
       }
     }
   } else {
@@ -428,7 +407,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) k_dense_tc_t(const DenseTcParam
     const int f = tid + u * DT_THREADS, r = f / (DT_N / 4), c4 = f % (DT_N / 4);
     if (r0 + r < p.B) {
       const size_t off = (size_t)(r0 + r) * p.N + n0 + 4 * c4;
-      *reinterpret_cast<float4*>(op.H + off) = *reinterpret_cast<const float4*>(tile_h + r * DT_TP + 4 * c4);
+      const float4 h4 = *reinterpret_cast<const float4*>(tile_h + r * DT_TP + 4 * c4);
+      *reinterpret_cast<float4*>(op.H + off) = h4;
+      if (op.OUThl != nullptr) {                              // H is the X operand of the next layer and of its weight gradient
+        float4 big, small;
+        split_rn4(h4, big, small);
+        *reinterpret_cast<float4*>(op.OUThl + off) = big;
+        *reinterpret_cast<float4*>(op.OUThl + (size_t)p.B * p.N + off) = small;
+      }
       if (op.ZH != nullptr) *reinterpret_cast<float4*>(op.ZH + off) = *reinterpret_cast<const float4*>(tile_z + r * DT_TP + 4 * c4);
     }
   }
@@ -470,14 +456,43 @@ __global__ void __launch_bounds__(128) k_gather_mb(const GatherP* __restrict__ p
     *reinterpret_cast<float4*>(dst + 4 * c4) = v;
     if (hl != nullptr) {
       float4 h, y;
-      split_rn(v.x, h.x, y.x);
-      split_rn(v.y, h.y, y.y);
-      split_rn(v.z, h.z, y.z);
-      split_rn(v.w, h.w, y.w);
+      split_rn4(v, h, y);
       *reinterpret_cast<float4*>(dhi + 4 * c4) = h;
       *reinterpret_cast<float4*>(dlo + 4 * c4) = y;
     }
   }
+}
+
+// big / small parts of whole arrays: parameter arenas after they were written from outside (load_state_dict, soft update,
+// the FP32 weight-gradient kernel) and the activations of the fallback kernels that do not write them themselves
+__global__ void __launch_bounds__(256) k_split(const SplitP* __restrict__ pp) {
+  const SplitP& P = pp[blockIdx.y];
+  pdl_launch();
+  pdl_wait();
+  for (int e = 0; e < P.n; ++e) {
+    const float4* __restrict__ src = reinterpret_cast<const float4*>(P.src[e]);
+    float4* hi = reinterpret_cast<float4*>(P.hl[e]);
+    float4* lo = reinterpret_cast<float4*>(P.hl[e] + P.plane[e]);
+    const unsigned n4 = P.count[e] >> 2;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+      float4 big, small;
+      split_rn4(__ldcg(src + i), big, small);
+      hi[i] = big;
+      lo[i] = small;
+    }
+  }
+}
+cudaError_t launch_split(const SplitP* pp, int E, int grid, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = cudaLaunchConfig_t{};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3(grid, E, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_split, pp);
 }
 
 size_t dense_tc_smem_bytes() { return (size_t)DT_STAGES * DT_STAGE_BYTES + DT_PART_BYTES + 1024; }

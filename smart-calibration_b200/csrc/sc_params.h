@@ -24,8 +24,10 @@ struct CriticWs {                  // activation / gradient workspace of one ONL
   float *h22, *zh22, *rs22, *du22, *dz22;    // width HA2
   float *q, *dq;                             // [B]
   float *p_h11, *p_h12;                      // state-branch forward with the UPDATED weights (actor phase)
+  // tf32 big / small parts [2][B][width] of the arrays that are tensor-core operands (written by their producers)
+  float *h11_hl, *p_h11_hl, *dz11_hl, *dz12_hl;
 };
-struct TargetWs { float *h11, *h12; };
+struct TargetWs { float *h11, *h12, *h11_hl; };
 struct ActorWs {
   float *t_h1, *t_h2;                        // pass on s' (critic phase): SAC online actor / TD3 target actor
   float *h1, *zh1, *rs1, *du1, *dz1;         // pass on s (actor phase)
@@ -33,6 +35,7 @@ struct ActorWs {
   float *h3, *zh3, *rs3, *du3, *dz3;
   float *dhead;                              // [B][2A] (SAC: dmu | dlogsigma) or [B][A] (TD3: d pre-tanh)
   float *pi, *logp, *qmin;                   // [B][A], [B], [B] (min_k Q_k(s,pi(s)) or Q_1 for TD3)
+  float *t_h1_hl, *h1_hl, *h2_hl, *dz1_hl, *dz2_hl, *dz3_hl;  // tf32 big / small parts [2][B][width] (tensor-core operands)
 };
 
 struct ReplayP {
@@ -123,10 +126,11 @@ struct WgradOp {
   int opt;                         // index into AdamHyper[3] (0 actor, 1 critic_1, 2 critic_2)
 };
 struct WgradTcOp {                 // wide-layer weight gradient on tcgen05 (sc_wgrad_tc.cu): 128 (n) x 64 (k) tiles
-  const void* mapD;                // dZ [B][N], boxes {32 floats, 32 rows}, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
-  const void* mapX;                // X  [B][K], same box
+  const void* mapD;                // dZ [B][N] big part, boxes {32 floats, 32 rows}, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; the small part's map follows it
+  const void* mapX;                // X  [B][K] big part, same box; small part's map follows
   int N, K;
   float *W, *M, *V, *T; int ldw;
+  float *Whi, *Wlo, *Thi, *Tlo;    // tf32 big / small copies of W and T kept for the forward / dgrad GEMMs (same pitch)
   int tiles_k;                     // number of 64-wide k tiles
   int tile_base, tile_count;
   int opt;
@@ -158,8 +162,8 @@ struct WgradParams {
 
 // ---- dense forward stages on tcgen05 (sc_dense_tc.cu): H = ELU(LN(X W^T + b)) for up to 5 layers of equal width ----
 struct DenseTcOp {
+  // every operand arrives split into tf32 big / small parts by its producer: map = big part, the CUtensorMap after it = small part
   const void* mapX;                // X [B][K], boxes {32 floats, 128 rows}, CU_TENSOR_MAP_SWIZZLE_128B
-  const void* mapXlo;              // nullptr, or: X arrives already split (mapX = tf32-rounded big part, mapXlo = small part)
   const void* mapW;                // W [N][K] (PyTorch layout), boxes {32 floats, 64 rows}
   const float *bias, *gamma, *beta;
   float *H, *ZH, *RS;              // forward: outputs [B][N] (ZH, RS nullable) as the tail reads them; dgrad: the PRODUCING layer's h / zh / 1/std (inputs)
@@ -167,6 +171,7 @@ struct DenseTcOp {
   // dgrad mode (k_dgrad_tc): X = dZ [B][K] of the layer above, W = that layer's weight [K][N] as MN-major panels (boxes {32 floats, 32 rows},
   // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), gamma = LayerNorm weight of the producing layer; outputs dU = dH * ELU'(h) and dZ (LayerNorm backward)
   float *DU, *DZ;
+  float *OUThl;                    // nullable: tf32 big / small parts [2][B][N] of the output the next GEMM consumes (forward: H, dgrad: DZ)
 };
 struct DenseTcParams {
   DenseTcOp ops[5];
@@ -213,6 +218,10 @@ struct AdmmP {                     // k_admm_update
   float *lambda, *y0, *a0, *rho;
   float rho0, corr_min;
   float* stats_rho;                // nullable: current penalty for the host-side diagnostics block
+};
+struct SplitP {                    // k_split: hl = [big | small] parts of up to 12 arrays (fallback / refresh paths)
+  int n;
+  const float* src[12]; float* hl[12]; unsigned count[12], plane[12];   // floats (multiples of 4); small part at hl + plane
 };
 struct StoreP {                    // k_replay_store
   ReplayP rp;

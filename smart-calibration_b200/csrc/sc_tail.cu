@@ -316,6 +316,20 @@ __device__ __forceinline__ void t_store_rows(float* dst, const float* src, int N
       *reinterpret_cast<float4*>(dst + (size_t)rs.row[t] * N + 4 * c4) = *reinterpret_cast<const float4*>(src + t * N + 4 * c4);
   }
 }
+// the same rows as tf32 big / small parts (hl = [big | small], `plane` floats apart): operands of the tcgen05 dgrad / wgrad GEMMs
+__device__ __forceinline__ void t_store_rows_hl(float* hl, size_t plane, const float* src, int N, const TRows& rs) {
+  if (hl == nullptr) return;
+  for (int e = threadIdx.x; e < TR * (N >> 2); e += TL_THREADS) {
+    const int t = e / (N >> 2), c4 = e - t * (N >> 2);
+    if (rs.row[t] >= 0) {
+      float4 big, small;
+      split_rn4(*reinterpret_cast<const float4*>(src + t * N + 4 * c4), big, small);
+      float* d = hl + (size_t)rs.row[t] * N + 4 * c4;
+      *reinterpret_cast<float4*>(d) = big;
+      *reinterpret_cast<float4*>(d + plane) = small;
+    }
+  }
+}
 
 // action branches (fc21 -> LN -> ELU -> fc22 -> LN -> ELU) of `nn` critics at once; net i reads actions an_sel[i] ([TR][AMAX]).
 // Leaves h21/zh21/h22/zh22 in s.v21.. and 1/std in s.rsn[(net*TR+t)*2 + {0,1}].
@@ -546,6 +560,7 @@ __device__ void t_critic(const RowPhaseParams& p, const TailS& s, const TRows& r
   for (int k = 0; k < 2; ++k) {
     t_store_rows(p.cw[k].du12, s.ga + k * TR * H2, H2, rs);
     t_store_rows(p.cw[k].dz12, s.gb + k * TR * H2, H2, rs);
+    t_store_rows_hl(p.cw[k].dz12_hl, (size_t)p.B * H2, s.gb + k * TR * H2, H2, rs);
     t_store_rows(p.cw[k].du22, s.ge + k * TR * HA2, HA2, rs);
     t_store_rows(p.cw[k].dz22, s.gf + k * TR * HA2, HA2, rs);
   }
@@ -700,12 +715,14 @@ __device__ void t_actor(const RowPhaseParams& p, const TailS& s, const TRows& rs
     tsync();
     t_store_rows(p.aw.du3, s.ga, H3, rs);
     t_store_rows(p.aw.dz3, s.gb, H3, rs);
+    t_store_rows_hl(p.aw.dz3_hl, (size_t)p.B * H3, s.gb, H3, rs);
     LinJob jb{H3, nullptr, s.gb, nullptr};
     linear_bwd<H2>(jb, s.gc, st, cur, s);                            // s.gc has room for [TR][H2] (2*TR*HA1 floats)
     t_ln_bwd(1, s.gc, s.xh2, s.zh2, H2, g2, s.rsx + 3, 8, s.gd);
     tsync();
     t_store_rows(p.aw.du2, s.gc, H2, rs);
     t_store_rows(p.aw.dz2, s.gd, H2, rs);
+    t_store_rows_hl(p.aw.dz2_hl, (size_t)p.B * H2, s.gd, H2, rs);
   }
 }
 

@@ -7,10 +7,11 @@
 // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, described to the MMA with leading-byte-offset = one box (next 32 n / k), stride-byte-
 // offset = 512 B (next 4 batch rows) and a start address that advances 1024 B per 8-row k-step (validated against a CPU GEMM
 // with tools/probe/tc_probe.cu).  kind::tf32 truncates its fp32 inputs to 10 mantissa bits, so fp32 fidelity is restored with
-// three products per k-step: A*B + A_lo*B + A*B_lo, where X_lo = X - trunc(X) is written next to the raw tile by four
-// "splitter" warps (the raw tile itself serves as the big part).
+// three products per k-step: A*B + A_lo*B + A*B_lo.  Both operands arrive already split into tf32 big / small parts by their
+// producers (k_gather_mb, the k_dense_tc epilogues, k_tail), so the K loop is TMA -> MMA; the Adam epilogue in turn writes the
+// big / small parts of the updated weights (and targets) that the forward and dgrad GEMMs of the next pass read.
 //
-// Warp roles (512 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue (one thread), warps 2..15 = lo-split;
+// Warp roles (512 threads): warp 0 = TMA producer, warp 1 = TMEM allocation + MMA issue (one thread);
 // epilogue: warps 2..5 move the accumulator TMEM -> registers -> shared tile, then ALL warps apply Adam (its IEEE divisions and
 // square roots make the epilogue latency-bound on few threads).  Three 48 KB stages of 32 batch rows.
 #include <stdlib.h>
@@ -23,7 +24,7 @@ constexpr int TC_M = 128, TC_N = 64, TC_BR = 32;            // tile rows (n), ti
 constexpr int TC_STAGES = 3;
 constexpr int TC_A_BYTES = (TC_M / 32) * TC_BR * 128;       // 16 KB: 4 boxes of [32 b][32 n]
 constexpr int TC_B_BYTES = (TC_N / 32) * TC_BR * 128;       // 8 KB
-constexpr int TC_STAGE_BYTES = 2 * (TC_A_BYTES + TC_B_BYTES);   // raw + lo
+constexpr int TC_STAGE_BYTES = 2 * (TC_A_BYTES + TC_B_BYTES);   // big + small parts
 constexpr int TC_TILE_PITCH = TC_N + 4;
 constexpr int TC_THREADS = 512;
 constexpr int TC_SPLIT_THREADS = TC_THREADS - 64;          // warps 2..11
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const WgradTcParams*
   const WgradTcParams& p = load_params(pp, &p_sm);            // blockIdx.y = agent of the ensemble
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_raw[TC_STAGES], full_lo[TC_STAGES], empty[TC_STAGES], acc_done;
+  __shared__ __align__(8) uint64_t full[TC_STAGES], empty[TC_STAGES], acc_done;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // debug timeline: thread `who` of CTA 0 appends (globaltimer << 8 | tag) at tl[1 + 64 * who_slot + n]
@@ -76,8 +77,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const WgradTcParams*
   if (p.tl != nullptr && blockIdx.x == 0 && tid < 3) p.tl[64 * tid] = 0;
   if (tid == 0) {
     for (int i = 0; i < TC_STAGES; ++i) {
-      mbar_init(full_raw + i, 1);
-      mbar_init(full_lo + i, TC_SPLIT_THREADS / 32);
+      mbar_init(full + i, 1);
       mbar_init(empty + i, 1);
     }
     mbar_init(&acc_done, 1);
@@ -107,11 +107,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const WgradTcParams*
         const unsigned g = it + s, slot = g % TC_STAGES;
         if (g >= TC_STAGES) mbar_wait(empty + slot, ((g / TC_STAGES) - 1) & 1u);
         uint8_t* st = smem + (size_t)slot * TC_STAGE_BYTES;
-        if (lane == 0) { mark(0, 1); mbar_expect_tx(full_raw + slot, TC_A_BYTES + TC_B_BYTES); }
+        if (lane == 0) { mark(0, 1); mbar_expect_tx(full + slot, TC_STAGE_BYTES); }
         __syncwarp();
-        if (lane < TC_M / 32) tma_load_2d(reinterpret_cast<float*>(st + lane * 4096), op.mapD, n0 + 32 * lane, s * TC_BR, full_raw + slot);
-        else if (lane < TC_M / 32 + TC_N / 32)
-          tma_load_2d(reinterpret_cast<float*>(st + TC_A_BYTES + (lane - TC_M / 32) * 4096), op.mapX, k0 + 32 * (lane - TC_M / 32), s * TC_BR, full_raw + slot);
+        // stage layout [dZ big | X big | dZ small | X small], 4 KB boxes; lanes 0..5 fetch the big parts, 6..11 the small parts
+        constexpr int NBOX = TC_M / 32 + TC_N / 32;
+        if (lane < 2 * NBOX) {
+          const int part = lane / NBOX, b = lane - part * NBOX;
+          uint8_t* sp = st + part * (TC_A_BYTES + TC_B_BYTES);
+          if (b < TC_M / 32)
+            tma_load_2d(reinterpret_cast<float*>(sp + b * 4096), reinterpret_cast<const uint8_t*>(op.mapD) + 128 * part, n0 + 32 * b, s * TC_BR, full + slot);
+          else
+            tma_load_2d(reinterpret_cast<float*>(sp + TC_A_BYTES + (b - TC_M / 32) * 4096), reinterpret_cast<const uint8_t*>(op.mapX) + 128 * part,
+                        k0 + 32 * (b - TC_M / 32), s * TC_BR, full + slot);
+        }
       }
     } else if (warp == 1) {
       // ---------------- MMA issue (one thread) ----------------
@@ -119,7 +127,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const WgradTcParams*
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
       for (int s = 0; s < nstages; ++s) {
         const unsigned g = it + s, slot = g % TC_STAGES;
-        mbar_wait(full_lo + slot, (g / TC_STAGES) & 1u);
+        mbar_wait(full + slot, (g / TC_STAGES) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lane == 0) {
           mark(1, 2);
@@ -149,29 +157,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const WgradTcParams*
             asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)(n0 + r) * op.ldw + k0 + 32 * half));
         }
       }
-      // ---------------- splitter warps: X_lo = X - trunc_tf32(X), same swizzled layout ----------------
       const int wl = tid - 64;                                // 0..447
-      for (int s = 0; s < nstages; ++s) {
-        const unsigned g = it + s, slot = g % TC_STAGES;
-        mbar_wait(full_raw + slot, (g / TC_STAGES) & 1u);
-        if (wl == 0) mark(2, 4);
-        float4* raw = reinterpret_cast<float4*>(smem + (size_t)slot * TC_STAGE_BYTES);
-        float4* lo = raw + (TC_A_BYTES + TC_B_BYTES) / 16;
-#pragma unroll 4
-        for (int i = wl; i < (TC_A_BYTES + TC_B_BYTES) / 16; i += TC_SPLIT_THREADS) {
-          const float4 x = raw[i];
-          float4 y;
-          y.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-          y.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-          y.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
-          y.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-          lo[i] = y;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic stores -> visible to the tensor core's reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_lo + slot);
-        if (wl == 0) mark(2, 5);
-      }
       // ---------------- epilogue part 1 (warps 2..5): TMEM -> shared tile ----------------
       if (warp < 6) {
         mbar_wait(&acc_done, tiles_done & 1u);
@@ -241,6 +227,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const WgradTcParams*
           __stcs(reinterpret_cast<float4*>(op.M + idx[u]), m);
           __stcs(reinterpret_cast<float4*>(op.V + idx[u]), v);
           *reinterpret_cast<float4*>(op.W + idx[u]) = w;
+          if (op.Whi != nullptr) {                            // operand copies for the next forward / dgrad GEMMs
+            float4 big, small;
+            split_rn4(w, big, small);
+            *reinterpret_cast<float4*>(op.Whi + idx[u]) = big;
+            *reinterpret_cast<float4*>(op.Wlo + idx[u]) = small;
+          }
           if (soft) {
             float4 t = pt[u];
             t.x = __fadd_rn(__fmul_rn(p.tau, w.x), __fmul_rn(p.one_minus_tau, t.x));
@@ -248,6 +240,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const WgradTcParams*
             t.z = __fadd_rn(__fmul_rn(p.tau, w.z), __fmul_rn(p.one_minus_tau, t.z));
             t.w = __fadd_rn(__fmul_rn(p.tau, w.w), __fmul_rn(p.one_minus_tau, t.w));
             *reinterpret_cast<float4*>(op.T + idx[u]) = t;
+            if (op.Thi != nullptr) {
+              float4 big, small;
+              split_rn4(t, big, small);
+              *reinterpret_cast<float4*>(op.Thi + idx[u]) = big;
+              *reinterpret_cast<float4*>(op.Tlo + idx[u]) = small;
+            }
           }
         }
       }

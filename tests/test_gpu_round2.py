@@ -338,3 +338,37 @@ def test_deferred_stats_are_the_previous_steps_losses():
     for n in range(7):
         for k in ("critic_1_loss", "critic_2_loss", "actor_loss", "q1_mean", "learn_counter"):
             assert deferred[n + 1][k] == sync[n][k], (n, k)
+
+
+@pytest.mark.parametrize("S", [24, 96])
+def test_operand_copies_follow_parameter_writes(S):
+    """The tcgen05 GEMMs read the wide weights as tf32 big / small copies kept next to the fp32 parameters.  Writing parameters
+    from outside -- load_state_dict through fresh views, or an in-place write through a view taken earlier followed by
+    params_changed() -- must give the same trajectory as an agent that was built with those weights (S = 24: layer 1 is
+    updated by the FP32 kernel, S = 96: by the tensor-core kernel)."""
+    def run(agent, n):
+        for _ in range(n):
+            agent.learn()
+        agent._dev.sync()
+    a, b, c = (_make(31, True, input_dims=[S]) for _ in range(3))
+    cached = b._dev.tensor(L.NET_CRITIC_1, "fc12.weight")         # a view b's owner holds on to
+    cached_a = b._dev.tensor(L.NET_ACTOR, "fc1.weight")
+    run(a, 3), run(b, 3), run(c, 3)
+    assert all(torch.equal(v, _state(b)[k]) for k, v in _state(a).items())
+    g = torch.Generator().manual_seed(5)
+    d12 = 0.01 * torch.randn(cached.shape, generator=g)
+    d1 = 0.01 * torch.randn(cached_a.shape, generator=g)
+    # a: load_state_dict (fresh views)
+    sd = a.critic_1.state_dict(); sd["fc12.weight"] = sd["fc12.weight"] + d12.to(sd["fc12.weight"].device); a.critic_1.load_state_dict(sd)
+    sd = a.actor.state_dict(); sd["fc1.weight"] = sd["fc1.weight"] + d1.to(sd["fc1.weight"].device); a.actor.load_state_dict(sd)
+    # b: in-place through the cached views + explicit notification
+    b._dev.flush()
+    cached.add_(d12.to(cached.device)); cached_a.add_(d1.to(cached_a.device))
+    b._dev.params_changed()
+    run(a, 3), run(b, 3)
+    sa, sb = _state(a), _state(b)
+    assert all(torch.equal(v, sb[k]) for k, v in sa.items())
+    # and the write did change the trajectory (c never saw it)
+    run(c, 3)
+    sc = _state(c)
+    assert any(not torch.equal(v, sc[k]) for k, v in sa.items())
