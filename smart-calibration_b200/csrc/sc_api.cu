@@ -571,6 +571,15 @@ static int encode_map(CUtensorMap* out, const void* base, int ld, int rows, int 
   return SC_OK;
 }
 
+extern "C++" {
+namespace sc {
+// shared with sc_calib.cu: row-major float matrix [rows][ld], box {32 floats, box_rows}, 128-byte swizzle, out-of-range elements read as 0
+int encode_map_f32_2d(void* out, const void* base, int ld, int rows, int box_rows) {
+  return encode_map(reinterpret_cast<CUtensorMap*>(out), base, ld, rows, box_rows);
+}
+}  // namespace sc
+}
+
 static int build_tensor_maps(sc_agent* a) {
   std::vector<CUtensorMap> host;
   host.reserve(128);

@@ -14,11 +14,13 @@
 
 #include "../../include/smartcal_b200.h"
 #include "sc_calib_kernels.cuh"
+#include "sc_conv_tc.cuh"
 
 namespace sc {
 cudaError_t launch_soft_update(const float* src, float* dst, size_t n, float tau, cudaStream_t st);
 cudaError_t launch_fill_normal(float* out, int n, uint64_t seed, uint64_t stream, cudaStream_t st);
 cudaError_t launch_fill_normal_p(float* out, int n, uint64_t seed, const unsigned long long* stream_dev, cudaStream_t st);
+int encode_map_f32_2d(void* out, const void* base, int ld, int rows, int box_rows);      // sc_api.cu
 }  // namespace sc
 
 using namespace sc;
@@ -377,6 +379,11 @@ struct sc_calib {
   float *params, *grads, *adam_m, *adam_v, *targets;     // targets: [t1 | t2] in critic layout
   size_t off_net[3], n_params;
   float* bnbuf[5];                    // per net: rm1 rv1 rm2 rv2 rm3 rv3 (16,16,32,32,32,32 floats)
+  // conv2 / conv3 on tcgen05 (sc_conv_tc.cuh): tf32 big / small copies of the two weight tensors of every network
+  // ([2][32 x 400] then [2][32 x 800] floats) and their tensor maps [net][layer - 1][big, small]
+  float* conv_hl[5];
+  CUtensorMap conv_map[5][2][2];
+  bool conv_tc;
   long long* nbt[5];                  // per net: 3 counters
   // replay
   float *r_img, *r_img2, *r_sky, *r_sky2, *r_act, *r_hint, *r_rew, *r_done;
@@ -404,7 +411,7 @@ struct sc_calib {
   int64_t mem_cntr, learn_counter, t_actor, t_critic, launches, noise_ctr;
   bool batch_ready;
   float admm_rho;
-  int wg_blocks, nch;
+  int wg_blocks, nch, sm_count;
   // per-step scalars in device memory (Adam bias corrections of the three optimizers, Philox stream ids of the noise draws): one
   // small copy per step; with them the launch sequence of learn() is identical from step to step and replays from a CUDA graph
   struct StepScalars { AdamP adam[3]; unsigned long long noise[4]; };
@@ -486,6 +493,7 @@ static size_t carve_c(sc_calib* a, char* base) {
   a->params = cv.f(a->n_params); a->grads = cv.f(a->n_params); a->adam_m = cv.f(a->n_params); a->adam_v = cv.f(a->n_params);
   a->targets = cv.f(2 * a->Lc.size);
   for (int n = 0; n < 5; ++n) { a->bnbuf[n] = cv.f(160); a->nbt[n] = (long long*)cv.take(4 * sizeof(long long)); }
+  for (int n = 0; n < 5; ++n) a->conv_hl[n] = cv.f(a->trunk ? (size_t)2 * C2 * C1 * TAPS + (size_t)2 * C3 * C2 * TAPS : 4);
   const size_t NIMG = a->trunk ? (size_t)IMG * IMG : 0;       // no influence maps without the conv trunk
   const size_t FEATR = a->feat, SIDER = a->side;
   a->r_img = cv.f(C * NIMG); a->r_img2 = cv.f(C * NIMG);
@@ -553,6 +561,7 @@ static void init_dims_c(sc_calib* a, const sc_calib_config* c) {
   a->La = actor_layout_c(a->SKY, a->A, a->trunk, a->side, a->feat, a->sigma_mode);
   a->Lc = critic_layout_c(a->K1C, a->trunk, a->side, a->feat);
   a->wg_blocks = 296;
+  a->sm_count = 148;
   a->nch = a->B < 32 ? a->B : 32;
 }
 
@@ -598,6 +607,22 @@ static int trunk_forward(sc_calib* a, TrunkWs& t, const NetP& P, int net, const 
   LAUNCH_OK(a);
   int rc = bn_forward(a, t, P, net, 0, C1, H1C * H1C, act, train, Bn);
   if (rc) return rc;
+  if (a->conv_tc) {
+    // conv2 / conv3 as implicit GEMMs on tcgen05: this network's weights as tf32 big / small parts first (they change every step)
+    float* hl2 = a->conv_hl[net];
+    float* hl3 = hl2 + (size_t)2 * C2 * C1 * TAPS;
+    k_conv_w_split<<<38, 256, 0, a->st>>>(P.cw[1], hl2, C2 * C1 * TAPS, P.cw[2], hl3, C3 * C2 * TAPS);
+    LAUNCH_OK(a);
+    const int t2 = (Bn * H2C * H2C + CT_M - 1) / CT_M, t3 = (Bn * H3C * H3C + CT_M - 1) / CT_M;
+    k_conv_fwd_tc<C1, H1C, H2C><<<t2 < a->sm_count ? t2 : a->sm_count, CT_THREADS, conv_tc_smem_bytes(), a->st>>>(
+        ConvTcP{t.a[0], (size_t)C1 * H1C * H1C, P.cb[1], t.z[1], Bn}, a->conv_map[net][0][0], a->conv_map[net][0][1]);
+    LAUNCH_OK(a);
+    if ((rc = bn_forward(a, t, P, net, 1, C2, H2C * H2C, act, train, Bn))) return rc;
+    k_conv_fwd_tc<C2, H2C, H3C><<<t3 < a->sm_count ? t3 : a->sm_count, CT_THREADS, conv_tc_smem_bytes(), a->st>>>(
+        ConvTcP{t.a[1], (size_t)C2 * H2C * H2C, P.cb[2], t.z[2], Bn}, a->conv_map[net][1][0], a->conv_map[net][1][1]);
+    LAUNCH_OK(a);
+    return bn_forward(a, t, P, net, 2, C3, H3C * H3C, act, train, Bn);
+  }
   k_conv_fwd<C1, C2, H1C, H2C><<<dim3(G2::BLOCKS_PER_IMG, Bn), 256, 0, a->st>>>(t.a[0], (size_t)C1 * H1C * H1C, P.cw[1], P.cb[1], t.z[1]);
   LAUNCH_OK(a);
   if ((rc = bn_forward(a, t, P, net, 1, C2, H2C * H2C, act, train, Bn))) return rc;
@@ -780,6 +805,22 @@ int sc_calib_create(const sc_calib_config* cfg, void* arena, size_t arena_bytes,
   CKC(cudaHostAlloc((void**)&a->h_idx, (size_t)a->B * sizeof(int), cudaHostAllocDefault));
   CKC(cudaFuncSetAttribute(k_conv_wgrad<C1, C2, H1C, H2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024));
   CKC(cudaFuncSetAttribute(k_conv_wgrad<C2, C3, H2C, H3C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 101 * 1024));
+  {
+    const char* e = getenv("SMARTCAL_CONV");                    // "ffma" keeps the direct FP32 convolutions (A/B runs)
+    a->conv_tc = a->trunk && !(e && !strcmp(e, "ffma"));
+    if (a->conv_tc) {
+      for (int n = 0; n < 5; ++n) {
+        float* hl2 = a->conv_hl[n];
+        float* hl3 = hl2 + (size_t)2 * C2 * C1 * TAPS;
+        for (int part = 0; part < 2; ++part) {
+          if ((rc = encode_map_f32_2d(&a->conv_map[n][0][part], hl2 + (size_t)part * C2 * C1 * TAPS, C1 * TAPS, C2, 32))) return rc;
+          if ((rc = encode_map_f32_2d(&a->conv_map[n][1][part], hl3 + (size_t)part * C3 * C2 * TAPS, C2 * TAPS, C3, 32))) return rc;
+        }
+      }
+      CKC(cudaFuncSetAttribute(k_conv_fwd_tc<C1, H1C, H2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_tc_smem_bytes()));
+      CKC(cudaFuncSetAttribute(k_conv_fwd_tc<C2, H2C, H3C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_tc_smem_bytes()));
+    }
+  }
   CKC(cudaMalloc((void**)&a->step_dev, sizeof(sc_calib::StepScalars)));
   CKC(cudaHostAlloc((void**)&a->step_host, 2 * sizeof(sc_calib::StepScalars), cudaHostAllocDefault));
   for (auto& e : a->ev_step) CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));

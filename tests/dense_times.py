@@ -10,7 +10,7 @@ for _ in range(5):
     dev.learn()
 torch.cuda.synchronize()
 tl = dev.buffer("debug_ts").view(torch.int64).cpu().numpy().reshape(-1)[2880 * 8:2880 * 8 + 192]
-names = {1: "producer: issue stage", 2: "mma: stage ready (lo done)", 3: "mma: issued", 4: "split: raw landed", 5: "split: lo written",
+names = {1: "producer: issue stage", 2: "mma: stage landed", 3: "mma: issued", 4: "split: raw landed", 5: "split: lo written",
          6: "epilogue: accumulator done", 8: "epilogue: tmem read, vectors ready", 9: "epilogue: CTA stats done",
          10: "epilogue: cluster exchange done", 7: "epilogue: stored"}
 evs = []
@@ -32,12 +32,8 @@ spans = []
 for name, lo in [("critic dense 1", 1280), ("critic dense 2", 1408), ("actor dense 1", 1792), ("actor dense 2", 1920)]:
     r = rows(lo, 128)
     spans.append((name, r[:, 0].min(), r[:, 1].min(), r[:, 1].max(), r[:, 2].max(), r[:, 3].max(), len(r)))
-c = rows(0, 256)
-a = rows(1536, 256)
 t0 = spans[0][1]
 print("in-situ spans (us since the first CTA of critic dense 1 entered): entry | dependency met (min..max) | accumulators done | end")
 for name, e, d0, d1, acc, end, n in spans:
     print(f"  {name:16s} {n:4d} CTAs  entry {(e - t0) / 1e3:7.1f}  dep {(d0 - t0) / 1e3:7.1f}..{(d1 - t0) / 1e3:7.1f}  acc {(acc - t0) / 1e3:7.1f}  end {(end - t0) / 1e3:7.1f}")
-    if name == "critic dense 2":
-        print(f"  critic row-phase  256 CTAs  start {(c[:, 0].min() - t0) / 1e3:7.1f}..{(c[:, 0].max() - t0) / 1e3:7.1f}  tail done {(c[:, 3].max() - t0) / 1e3:7.1f}  end {(c[:, 5].max() - t0) / 1e3:7.1f}")
-print(f"  actor row-phase   256 CTAs  start {(a[:, 0].min() - t0) / 1e3:7.1f}..{(a[:, 0].max() - t0) / 1e3:7.1f}  tail done {(a[:, 3].max() - t0) / 1e3:7.1f}  end {(a[:, 5].max() - t0) / 1e3:7.1f}")
+

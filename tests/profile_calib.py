@@ -17,8 +17,13 @@ for name, key in (("state_memory_img", "img"), ("new_state_memory_img", "img2"),
     dev.buffer(name).copy_(torch.as_tensor(tr[key].reshape(C, -1)).to(dev.device))
 dev.set_counters(C, 0)
 rs = np.random.RandomState(1)
-for _ in range(steps):
+import time
+for i in range(steps):
+    if i == steps // 2:
+        torch.cuda.synchronize(); t0 = time.perf_counter()
     dev.set_batch(rs.choice(C, B, replace=False))
     dev.learn()
 torch.cuda.synchronize()
+if steps >= 4:
+    print(f"{(time.perf_counter() - t0) / (steps - steps // 2) * 1e3:.3f} ms/step (second half of {steps} steps, wall clock)")
 print("done", dev.launch_count())
