@@ -384,6 +384,8 @@ struct sc_calib {
   float* conv_hl[5];
   CUtensorMap conv_map[5][2][2];
   bool conv_tc;
+  int conv_dbg;
+  unsigned long long* conv_ts;        // debug timeline of k_conv_fwd_tc (SMARTCAL_STAMPS), "debug_ts"
   long long* nbt[5];                  // per net: 3 counters
   // replay
   float *r_img, *r_img2, *r_sky, *r_sky2, *r_act, *r_hint, *r_rew, *r_done;
@@ -493,6 +495,8 @@ static size_t carve_c(sc_calib* a, char* base) {
   a->params = cv.f(a->n_params); a->grads = cv.f(a->n_params); a->adam_m = cv.f(a->n_params); a->adam_v = cv.f(a->n_params);
   a->targets = cv.f(2 * a->Lc.size);
   for (int n = 0; n < 5; ++n) { a->bnbuf[n] = cv.f(160); a->nbt[n] = (long long*)cv.take(4 * sizeof(long long)); }
+  a->conv_ts = (unsigned long long*)cv.take(sizeof(unsigned long long) * 1024);
+  reg("debug_ts", a->conv_ts, 1024, 1, 8);
   for (int n = 0; n < 5; ++n) a->conv_hl[n] = cv.f(a->trunk ? (size_t)2 * C2 * C1 * TAPS + (size_t)2 * C3 * C2 * TAPS : 4);
   const size_t NIMG = a->trunk ? (size_t)IMG * IMG : 0;       // no influence maps without the conv trunk
   const size_t FEATR = a->feat, SIDER = a->side;
@@ -615,11 +619,11 @@ static int trunk_forward(sc_calib* a, TrunkWs& t, const NetP& P, int net, const 
     LAUNCH_OK(a);
     const int t2 = (Bn * H2C * H2C + CT_M - 1) / CT_M, t3 = (Bn * H3C * H3C + CT_M - 1) / CT_M;
     k_conv_fwd_tc<C1, H1C, H2C><<<t2 < a->sm_count ? t2 : a->sm_count, CT_THREADS, conv_tc_smem_bytes(), a->st>>>(
-        ConvTcP{t.a[0], (size_t)C1 * H1C * H1C, P.cb[1], t.z[1], Bn}, a->conv_map[net][0][0], a->conv_map[net][0][1]);
+        ConvTcP{t.a[0], (size_t)C1 * H1C * H1C, P.cb[1], t.z[1], Bn, a->conv_ts, a->conv_dbg}, a->conv_map[net][0][0], a->conv_map[net][0][1]);
     LAUNCH_OK(a);
     if ((rc = bn_forward(a, t, P, net, 1, C2, H2C * H2C, act, train, Bn))) return rc;
     k_conv_fwd_tc<C2, H2C, H3C><<<t3 < a->sm_count ? t3 : a->sm_count, CT_THREADS, conv_tc_smem_bytes(), a->st>>>(
-        ConvTcP{t.a[1], (size_t)C2 * H2C * H2C, P.cb[2], t.z[2], Bn}, a->conv_map[net][1][0], a->conv_map[net][1][1]);
+        ConvTcP{t.a[1], (size_t)C2 * H2C * H2C, P.cb[2], t.z[2], Bn, nullptr, a->conv_dbg}, a->conv_map[net][1][0], a->conv_map[net][1][1]);
     LAUNCH_OK(a);
     return bn_forward(a, t, P, net, 2, C3, H3C * H3C, act, train, Bn);
   }
@@ -808,6 +812,9 @@ int sc_calib_create(const sc_calib_config* cfg, void* arena, size_t arena_bytes,
   {
     const char* e = getenv("SMARTCAL_CONV");                    // "ffma" keeps the direct FP32 convolutions (A/B runs)
     a->conv_tc = a->trunk && !(e && !strcmp(e, "ffma"));
+    const char* d = getenv("SMARTCAL_CONV_DBG");
+    a->conv_dbg = d ? atoi(d) : 0;
+    if (!getenv("SMARTCAL_STAMPS")) a->conv_ts = nullptr;
     if (a->conv_tc) {
       for (int n = 0; n < 5; ++n) {
         float* hl2 = a->conv_hl[n];

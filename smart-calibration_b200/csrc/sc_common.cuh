@@ -87,6 +87,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
 }
+// the same wait for warps that are NOT on the critical path (epilogue warps waiting for a whole K loop, producers waiting for a
+// free slot): between polls the warp sleeps, so that its polling does not take issue slots from the warps that do the work
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* b, unsigned parity, unsigned ns) {
+  for (;;) {
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(b)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(ns);
+  }
+}
 __device__ __forceinline__ void bulk_g2s(float* smem_dst, const float* gsrc, unsigned bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
