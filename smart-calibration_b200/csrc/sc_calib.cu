@@ -824,6 +824,7 @@ int sc_calib_create(const sc_calib_config* cfg, void* arena, size_t arena_bytes,
           if ((rc = encode_map_f32_2d(&a->conv_map[n][1][part], hl3 + (size_t)part * C3 * C2 * TAPS, C2 * TAPS, C3, 32))) return rc;
         }
       }
+      CKC(conv_tc_upload_tables());
       CKC(cudaFuncSetAttribute(k_conv_fwd_tc<C1, H1C, H2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_tc_smem_bytes()));
       CKC(cudaFuncSetAttribute(k_conv_fwd_tc<C2, H2C, H3C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_tc_smem_bytes()));
     }

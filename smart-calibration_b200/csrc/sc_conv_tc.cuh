@@ -29,6 +29,22 @@ constexpr int CT_GWARPS = 16, CT_EWARPS = 4;
 constexpr int CT_THREADS = 64 + 32 * (CT_GWARPS + CT_EWARPS);
 constexpr int CT_TMEM_COLS = 4 * CT_N;                              // two accumulator sets of (main | correction) x 32 columns
 
+// k -> offset of x[ci][ky][kx] from a pixel's window origin, per layer shape; the same for every tile, so the gather loop carries
+// no index arithmetic.  Constant memory: the index is warp-uniform, and a uniform-address LDS.128 measured ~11 wavefronts of the
+// shared-memory data pipe this kernel is bound by.  Padded k (>= K) point at the origin: the weight operand is zero there.
+constexpr int CT_KOFF_MAX = 32 * 25;                                // conv3: K = 800
+__constant__ int c_koff[2][CT_KOFF_MAX];                            // [0]: CIN = 16 (62 -> 29), [1]: CIN = 32 (29 -> 13)
+inline cudaError_t conv_tc_upload_tables() {
+  static int h[2][CT_KOFF_MAX];
+  const int cin[2] = {16, 32}, hin[2] = {62, 29};
+  for (int t = 0; t < 2; ++t)
+    for (int k = 0; k < CT_KOFF_MAX; ++k) {
+      const int ci = k / 25, rem = k - 25 * ci, ky = rem / 5, kx = rem - 5 * ky;
+      h[t][k] = k < cin[t] * 25 ? ci * hin[t] * hin[t] + ky * hin[t] + kx : 0;
+    }
+  return cudaMemcpyToSymbol(c_koff, h, sizeof(h));
+}
+
 struct ConvTcP {
   const float* x; size_t x_img_stride;        // input activations [B][CIN][HIN][HIN] (image stride in floats)
   const float* bias;
@@ -87,16 +103,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_fwd_tc(const ConvTcP p, 
   __shared__ __align__(8) uint64_t full[CT_STAGES], empty[CT_STAGES], acc_done[2], acc_free[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float sbias[CT_N];
-  // k -> offset of x[ci][ky][kx] from a pixel's window origin; the same for every tile, so the gather loop carries no index
-  // arithmetic.  Padded k (>= K) point at the origin: the weight operand is zero there (TMA out-of-range fill)
-  __shared__ __align__(16) unsigned short koff[NK * 32];       // (16 bits: the whole kernel stays within the 164 KB shared-memory configuration, which leaves 92 KB of L1 for the gather)
-  static_assert((CIN - 1) * HW_IN + 4 * HIN + 4 < 65536, "window offsets must fit 16 bits");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Mtot = p.B * OHW, ntiles = (Mtot + CT_M - 1) / CT_M;
-  for (int k = tid; k < NK * 32; k += CT_THREADS) {
-    const int ci = k / 25, rem = k - 25 * ci, ky = rem / 5, kx = rem - 5 * ky;
-    koff[k] = (unsigned short)(k < K ? ci * HW_IN + ky * HIN + kx : 0);
-  }
+  static_assert(NK * 32 <= CT_KOFF_MAX && (CIN == 16 || CIN == 32), "offset tables are built for the two trunk shapes");
   if (tid == 0) {
     for (int i = 0; i < CT_STAGES; ++i) {
       mbar_init(full + i, CT_GWARPS / CT_STAGES + 1);     // one arrival per gather warp of the slot's group + the producer's expect_tx
@@ -215,9 +224,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_conv_fwd_tc(const ConvTcP p, 
       float v[32];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const uint2 o = *reinterpret_cast<const uint2*>(koff + 32 * kc + 4 * u);
-        v[4 * u] = __ldg(xb + (o.x & 0xffffu)); v[4 * u + 1] = __ldg(xb + (o.x >> 16));
-        v[4 * u + 2] = __ldg(xb + (o.y & 0xffffu)); v[4 * u + 3] = __ldg(xb + (o.y >> 16));
+        const int* kt = c_koff[CIN == 16 ? 0 : 1] + 32 * kc + 4 * u;
+        v[4 * u] = __ldg(xb + kt[0]); v[4 * u + 1] = __ldg(xb + kt[1]); v[4 * u + 2] = __ldg(xb + kt[2]); v[4 * u + 3] = __ldg(xb + kt[3]);
       }
       if (n > 0) mbar_wait_sleep(empty + group, (n - 1) & 1u, 40);
       if (gw == 0 && lane == 0) mark(2, 6);
