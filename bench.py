@@ -442,7 +442,7 @@ def run_ours(args):
         return
     peak, peak_src = peaks()
     traffic, traffic_src = None, None
-    for cand in ("r2_traffic.json",):
+    for cand in ("r2e_traffic.json", "r2_traffic.json"):
         tp = os.path.join(ROOT, "profiles", cand)
         if os.path.exists(tp):
             tj = json.load(open(tp))

@@ -31,6 +31,7 @@ int dgrad_tc_max_clusters(int cs);
 cudaError_t launch_dgrad_tc(const DenseTcParams* pp, int E, int nops, int nrb, int N, int ks, cudaStream_t st);
 cudaError_t launch_gather_mb(const GatherP* pp, int E, int B, cudaStream_t st);
 cudaError_t launch_split(const SplitP* pp, int E, int grid, cudaStream_t st);
+cudaError_t launch_l2_prefetch(const PrefetchP* pp, int E, int grid, cudaStream_t st);
 cudaError_t launch_soft_update(const float* src, float* dst, size_t n, float tau, cudaStream_t st);
 cudaError_t launch_replay_store(const ReplayP& rp, const float* tr, int slot, int mode, double priority, double clip, cudaStream_t st);
 cudaError_t launch_replay_store_t(const StoreP* pp, int E, cudaStream_t st);
@@ -186,7 +187,7 @@ struct KernelTimer {
 // one host->device copy of the tape plus the launches, each kernel reading its parameters from the device copy
 // (blockIdx.y = agent).  Identical plans (same records, same tape offsets) are replayed as a CUDA graph.
 enum { KID_STORE = 0, KID_PER_SAMPLE, KID_UNIFORM, KID_GATHER, KID_DENSE, KID_ROW, KID_PER_UPDATE, KID_WGRAD, KID_WGRAD_TC, KID_HINT,
-       KID_ADMM, KID_TAIL, KID_DGRAD, KID_SPLIT };
+       KID_ADMM, KID_TAIL, KID_DGRAD, KID_SPLIT, KID_PREFETCH };
 enum { REC_KERNEL = 0, REC_DATA, REC_FORK, REC_JOIN_RECORD, REC_JOIN_WAIT, REC_TBEGIN, REC_TEND };
 struct Rec {
   int type, kid, stream;           // stream: 0 main, 1 side (PER), 2 side2 (narrow weight gradients)
@@ -1742,6 +1743,22 @@ static int plan_step(sc_agent* a, const StepArgs& sa, StepOut& so) {
     if (a->dense_tc && (rc = plan_split_weights(a))) return rc;
     a->split_dirty = false;
   }
+  // Experiment, off by default (SMARTCAL_PREFETCH=1): the step's parameter traffic requested from HBM up front on side stream 2
+  // (joined before the first weight-gradient launch).  Measured on B200: 207 vs 202 us per step with the L2 flushed between
+  // steps, 192 vs 185 us back to back -- the extra launch and fork / join cost more than the cold misses they were meant to hide.
+  static const bool prefetch_on = getenv("SMARTCAL_PREFETCH") && getenv("SMARTCAL_PREFETCH")[0] == '1';
+  const bool prefetched = prefetch_on && !a->timing && a->grp->E == 1 && a->dense_tc;
+  if (prefetched) {
+    if ((rc = emit_ctl(a, REC_FORK, 2))) return rc;
+    PrefetchP* pf = emit_kernel<PrefetchP>(a, KID_PREFETCH, 2, 2 * a->sm_count);
+    PL(pf);
+    memset(pf, 0, sizeof(PrefetchP));
+    const void* ptrs[6] = {a->params_hl, a->targets_hl, a->params, a->targets, a->adam_m, a->adam_v};
+    const size_t fl[6] = {2 * a->online_floats, 2 * a->target_floats, a->online_floats, a->target_floats, a->online_floats, a->online_floats};
+    pf->n = 6;
+    for (int i = 0; i < 6; ++i) { pf->ptr[i] = ptrs[i]; pf->bytes[i] = (unsigned long long)fl[i] * sizeof(float); }
+    if ((rc = emit_ctl(a, REC_JOIN_RECORD, 2))) return rc;
+  }
   const bool sac = a->cfg.kind == SC_KIND_SAC;
   const bool per = a->cfg.prioritized != 0;
   const bool was_quiet = a->quiet;          // nothing touched the replay state since the previous learn() returned
@@ -1848,6 +1865,7 @@ static int plan_step(sc_agent* a, const StepArgs& sa, StepOut& so) {
   a->t_critic++;
   WgradParams w;
   fill_wgrad(a, w, false, actor_step ? 1 : 0, 1);
+  if (prefetched && (rc = emit_ctl(a, REC_JOIN_WAIT, 2))) return rc;      // (long done: closes the fork before stream 2 is forked again)
   if ((rc = plan_wgrad(a, w, 1))) return rc;
   // ---- actor phase ----
   if (actor_step) {
@@ -1998,6 +2016,7 @@ static cudaError_t issue_recs(sc_group* g, cudaStream_t st0) {
           case KID_TAIL: e = launch_tail(reinterpret_cast<const RowPhaseParams*>(pp), g->E, r.g[0], st); break;
           case KID_DGRAD: e = launch_dgrad_tc(reinterpret_cast<const DenseTcParams*>(pp), g->E, r.g[0], r.g[1], r.g[2], r.g[3], st); break;
           case KID_SPLIT: e = launch_split(reinterpret_cast<const SplitP*>(pp), g->E, r.g[0], st); break;
+          case KID_PREFETCH: e = launch_l2_prefetch(reinterpret_cast<const PrefetchP*>(pp), g->E, r.g[0], st); break;
           default: e = cudaErrorInvalidValue;
         }
         break;

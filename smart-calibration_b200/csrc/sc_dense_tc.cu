@@ -495,6 +495,26 @@ cudaError_t launch_split(const SplitP* pp, int E, int grid, cudaStream_t st) {
   return cudaLaunchKernelEx(&cfg, k_split, pp);
 }
 
+// Experiment behind SMARTCAL_PREFETCH=1 (off by default; sc_api.cu plan_step has the measurement): the step's parameter traffic
+// (weights as big / small parts, fp32 parameters, targets, Adam moments: ~32 MB) requested from HBM at the start of learn().
+__global__ void __launch_bounds__(256) k_l2_prefetch(const PrefetchP* __restrict__ pp) {
+  const PrefetchP& P = pp[blockIdx.y];
+  size_t base = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, me = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int e = 0; e < P.n; ++e) {
+    const size_t lines = (size_t)((P.bytes[e] + 127) >> 7);
+    const char* p = reinterpret_cast<const char*>(P.ptr[e]);
+    // (lines of all ranges are dealt round-robin over the grid in range order, so the first range is requested first)
+    for (size_t i = (me + stride - base % stride) % stride; i < lines; i += stride)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (i << 7)));
+    base += lines;
+  }
+}
+cudaError_t launch_l2_prefetch(const PrefetchP* pp, int E, int grid, cudaStream_t st) {
+  k_l2_prefetch<<<dim3(grid, E, 1), 256, 0, st>>>(pp);
+  return cudaGetLastError();
+}
+
 size_t dense_tc_smem_bytes() { return (size_t)DT_STAGES * DT_STAGE_BYTES + DT_PART_BYTES + 1024; }
 size_t dgrad_tc_smem_bytes() { return dense_tc_smem_bytes(); }
 

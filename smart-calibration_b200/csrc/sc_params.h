@@ -223,6 +223,10 @@ struct SplitP {                    // k_split: hl = [big | small] parts of up to
   int n;
   const float* src[12]; float* hl[12]; unsigned count[12], plane[12];   // floats (multiples of 4); small part at hl + plane
 };
+struct PrefetchP {                 // k_l2_prefetch: ranges pulled into L2 at the start of a step, in order of first use
+  int n;
+  const void* ptr[8]; unsigned long long bytes[8];
+};
 struct StoreP {                    // k_replay_store
   ReplayP rp;
   const float* tr;
