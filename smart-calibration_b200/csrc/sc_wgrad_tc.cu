@@ -101,6 +101,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const WgradTcParams*
     const int lt = tile - op.tile_base;
     const int tn = lt / op.tiles_k, tk = lt - tn * op.tiles_k;
     const int n0 = tn * TC_M, k0 = tk * TC_N;
+    // The Adam operands of this tile (parameter, both moments, target) do not depend on the GEMM: every thread requests its 4 x 4
+    // float4 of them before the K loop (the producer / MMA warps after theirs), so the epilogue starts with them in registers
+    const bool soft = op.T != nullptr && p.do_soft;
+    constexpr int NF = TC_M * TC_N / 4;                     // float4 elements of the tile
+    constexpr int EU = NF / TC_THREADS;                     // float4 elements per thread
+    static_assert(EU * TC_THREADS == NF, "tile / thread mismatch");
+    float4 pm[EU], pv[EU], pp[EU], pt[EU];
+    bool ok[EU];
+    size_t idx[EU];
+    auto load_adam_operands = [&]() {
+#pragma unroll
+      for (int u = 0; u < EU; ++u) {
+        const int f = tid + u * TC_THREADS, r = f >> 4, c4 = f & 15;
+        ok[u] = (n0 + r < op.N) && (k0 + 4 * c4 < op.K);
+        idx[u] = ok[u] ? (size_t)(n0 + r) * op.ldw + k0 + 4 * c4 : 0;
+        pm[u] = pv[u] = pp[u] = pt[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok[u]) {
+          pm[u] = __ldcs(reinterpret_cast<const float4*>(op.M + idx[u]));
+          pv[u] = __ldcs(reinterpret_cast<const float4*>(op.V + idx[u]));
+          pp[u] = *reinterpret_cast<const float4*>(op.W + idx[u]);
+          if (soft) pt[u] = *reinterpret_cast<const float4*>(op.T + idx[u]);
+        }
+      }
+    };
+    if (warp >= 2) load_adam_operands();
     if (warp == 0) {
       // ---------------- TMA producer ----------------
       for (int s = 0; s < nstages; ++s) {
@@ -147,16 +172,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const WgradTcParams*
         __syncwarp();
       }
     } else {
-      // the Adam operands of this tile (parameter, both moments, target: 4 x 32 KB) are pulled into L2 while the GEMM runs
-      {
-        const int q = tid - 64;                               // 0..447
-        for (int i = q; i < TC_M * 2 * 4; i += TC_SPLIT_THREADS) {
-          const int arr = i >> 8, r = (i >> 1) & 127, half = i & 1;
-          const float* base = arr == 0 ? op.W : arr == 1 ? op.M : arr == 2 ? op.V : op.T;
-          if (base != nullptr && n0 + r < op.N && k0 + 32 * half < op.K)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)(n0 + r) * op.ldw + k0 + 32 * half));
-        }
-      }
       const int wl = tid - 64;                                // 0..447
       // ---------------- epilogue part 1 (warps 2..5): TMEM -> shared tile ----------------
       if (warp < 6) {
@@ -165,55 +180,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_wgrad_tc(const WgradTcParams*
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float* tile_w = reinterpret_cast<float*>(smem);       // all MMAs of this tile are complete: stage 0 is free
         const int row = (warp & 3) * 32 + lane;               // TMEM lane this thread can read
-#pragma unroll
-        for (int c0 = 0; c0 < TC_N; c0 += 32) {
-          uint32_t v[32];
+#pragma unroll 1
+        for (int c0 = 0; c0 < TC_N; c0 += 16) {               // (16 columns at a time: the Adam operands are live in registers too)
+          uint32_t v[16];
           const uint32_t addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
           asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
-              "%26,%27,%28,%29,%30,%31}, [%32];"
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-                "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-                "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
-                "=r"(v[31])
+                "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
               : "r"(addr));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
+          for (int j = 0; j < 16; j += 4)
             *reinterpret_cast<float4*>(tile_w + row * TC_TILE_PITCH + c0 + j) =
                 make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       }
     }
+    if (warp < 2) load_adam_operands();
     __syncthreads();                                          // tile is in shared memory; every warp joins the Adam pass
     if (tid == 64) mark(2, 7);
     {
       // ---------------- epilogue part 2 (all warps): Adam (+ soft update), coalesced ----------------
       const float* tile_s = reinterpret_cast<const float*>(smem);
       const AdamHyper h = p.hyper[op.opt];
-      const bool soft = op.T != nullptr && p.do_soft;
-      constexpr int NF = TC_M * TC_N / 4;                     // float4 elements of the tile
-      constexpr int EU = NF / TC_THREADS;                     // float4 elements per thread: all their operands are requested at once
-      static_assert(EU * TC_THREADS == NF, "tile / thread mismatch");
-#pragma unroll 1
-      for (int f0 = tid; f0 < NF; f0 += EU * TC_THREADS) {
-        float4 pm[EU], pv[EU], pp[EU], pt[EU];
-        bool ok[EU];
-        size_t idx[EU];
-#pragma unroll
-        for (int u = 0; u < EU; ++u) {
-          const int f = f0 + u * TC_THREADS, r = f >> 4, c4 = f & 15;
-          ok[u] = f < NF && (n0 + r < op.N) && (k0 + 4 * c4 < op.K);
-          idx[u] = ok[u] ? (size_t)(n0 + r) * op.ldw + k0 + 4 * c4 : 0;
-          pm[u] = pv[u] = pp[u] = pt[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok[u]) {
-            pm[u] = __ldcs(reinterpret_cast<const float4*>(op.M + idx[u]));
-            pv[u] = __ldcs(reinterpret_cast<const float4*>(op.V + idx[u]));
-            pp[u] = *reinterpret_cast<const float4*>(op.W + idx[u]);
-            if (soft) pt[u] = *reinterpret_cast<const float4*>(op.T + idx[u]);
-          }
-        }
+      {
+        const int f0 = tid;
 #pragma unroll
         for (int u = 0; u < EU; ++u) {
           if (!ok[u]) continue;
