@@ -1513,6 +1513,13 @@ static int plan_rowphase(sc_agent* a, const RowPhaseParams& p_in, int timer_id) 
         DenseTcParams g;
         memset(&g, 0, sizeof(g));
         g.N = H1; g.B = p.B; g.nrb = (p.B + 127) / 128; g.ks = 1; g.late_trigger = 0;
+        {
+          // reduction split across CTA pairs (16-CTA clusters) where ONE agent's clusters are co-resident: the K loop is the latency
+          // of this launch and only 16 / 32 CTAs would run it otherwise (decided per agent: bits do not depend on the ensemble size)
+          const int nclusters = (p.program == PROG_CRITIC ? 2 : 1) * g.nrb;
+          static const bool ks1 = getenv("SMARTCAL_DGRAD_KS") != nullptr && getenv("SMARTCAL_DGRAD_KS")[0] == '1';
+          if (!ks1 && nclusters <= a->dense_cap[2] && nclusters * 16 <= a->sm_count) g.ks = 2;
+        }
         if (p.program == PROG_CRITIC) {
           for (int k = 0; k < 2; ++k) {
             g.ops[k] = DenseTcOp{a->tmg_dz12[k], a->tmg_w12p[k], nullptr, p.crit[k].g11, nullptr, p.cw[k].h11, p.cw[k].zh11, p.cw[k].rs11, H2,
