@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SC_ABI_VERSION 2
+#define SC_ABI_VERSION 3
 
 enum { SC_OK = 0, SC_ERR_ARG = 1, SC_ERR_CUDA = 2, SC_ERR_STATE = 3, SC_ERR_UNSUPPORTED = 4 };
 
@@ -221,6 +221,8 @@ typedef struct sc_calib_config {
   double gamma, tau, lr_actor, lr_critic, alpha;
   float hint_threshold, admm_rho;
   uint64_t rng_seed;
+  int32_t update_actor_interval; /* SC_CALIB_TD3 only (demix_td3.py:357,368); ignored otherwise */
+  int32_t reserved;
 } sc_calib_config;
 /* network-family variants (sc_calib_config.variant).  demixing_rl/demix_sac.py:372-527 = LOGSIGMA | DEMIX_HINT | FLAT_META;
  * demixing_fuzzy/demix_sac.py:96-276 with use_influence=False = the same + NO_TRUNK | SIDE32. */
@@ -229,7 +231,17 @@ enum {
   SC_CALIB_NO_TRUNK = 2,    /* no conv trunk / influence map (use_influence=False): features = metadata network only                                   */
   SC_CALIB_DEMIX_HINT = 4,  /* KLD hint without clamping and dual update from a fresh no-grad sample of the updated actor (demix_sac.py:636-676)        */
   SC_CALIB_FLAT_META = 8,   /* metadata is a flat vector of M values (demix) instead of the (M+1) x 7 sky table (calib)                                 */
-  SC_CALIB_SIDE32 = 16      /* INNER_DIM = 32 (demixing_fuzzy/demix_sac.py:13) instead of 16; MLP family only                                          */
+  SC_CALIB_SIDE32 = 16,     /* INNER_DIM = 32 (demixing_fuzzy/demix_sac.py:13) instead of 16; MLP family only                                          */
+  /* demixing_rl/demix_td3.py:355-603 (DemixingAgent of the TD3 file) = TD3 | FLAT_META: one tanh policy head `fc22` (:318,342), critic
+   * side input cat((action, metadata)) (:279), a target actor (SC_NET_TARGET_ACTOR), eval-mode target passes (:484-486), the scalar
+   * target noise (:492-493), prioritized replay with the float64 sum tree inside the arena ("tree" buffer; PER :23-167,
+   * absolute_error_upper 100), PER.mse / actor loss with the (B,)x(B,1) broadcast (:137-140,:538), the delayed actor update
+   * (update_actor_interval), with use_hint the five-step adaptive-ADMM actor loop (:543-600; admm_rho = the constructor's 0.1, :400),
+   * and update_network_parameters over EVERY state_dict entry incl. BatchNorm buffers (:408-432), on actor steps only (:603).
+   * sc_calib_learn draws the minibatch itself: noise->per_u01_host (B float64 uniforms) + noise->td3_target_noise reproduce the
+   * reference's numpy stream, NULL selects device Philox; sc_calib_set_batch_host is not used.  sc_calib_act: eps_host = the additive
+   * exploration noise (n_actions values, :451) or NULL for none; the warm-up branch (:440-441) is host-side. */
+  SC_CALIB_TD3 = 32
 };
 typedef struct sc_calib sc_calib;
 
@@ -237,7 +249,7 @@ size_t sc_calib_arena_bytes(const sc_calib_config* cfg);
 int sc_calib_create(const sc_calib_config* cfg, void* arena, size_t arena_bytes, void* cuda_stream, sc_calib** out);
 int sc_calib_destroy(sc_calib* a);
 int sc_calib_sync(sc_calib* a);
-/* `net` = SC_NET_ACTOR / SC_NET_CRITIC_{1,2} / SC_NET_TARGET_CRITIC_{1,2}; `name` = a calib_sac state_dict key
+/* `net` = SC_NET_ACTOR / SC_NET_CRITIC_{1,2} / SC_NET_TARGET_CRITIC_{1,2} (/ SC_NET_TARGET_ACTOR, TD3); `name` = a calib_sac state_dict key
  * ("conv2.weight" as [Cout][Cin*25], "bn1.running_var", "bn3.num_batches_tracked" (int64), "fc21.weight", ...).
  * slot 3 = gradient of the last backward pass (tests). */
 int sc_calib_tensor(sc_calib* a, int net, int slot, const char* name, sc_tensor_info* out);
@@ -258,6 +270,9 @@ int sc_calib_act(sc_calib* a, const float* img_host, const float* sky_host, cons
 int sc_calib_learn(sc_calib* a, const sc_noise* noise_or_null, sc_learn_stats* stats_host_or_null);
 int sc_calib_soft_update(sc_calib* a, float tau);   /* update_network_parameters (calib_sac.py:271-276) */
 int64_t sc_calib_launch_count(sc_calib* a);
+/* SC_CALIB_TD3: PER.beta (demix_td3.py:32,95) lives outside the arena; get / set for checkpoints (PER.load_checkpoint :147-160) */
+int sc_calib_get_per_beta(sc_calib* a, double* beta_out);
+int sc_calib_set_per_beta(sc_calib* a, double beta);
 
 #ifdef __cplusplus
 }

@@ -10,10 +10,10 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsmartcal_b200.so")
 
-SC_ABI_VERSION = 2
+SC_ABI_VERSION = 3
 SC_FLAG_CRITIC_LOSS_SUM = 1   # include/smartcal_b200.h
 SC_KIND_SAC, SC_KIND_TD3 = 0, 1
-SC_CALIB_LOGSIGMA, SC_CALIB_NO_TRUNK, SC_CALIB_DEMIX_HINT, SC_CALIB_FLAT_META, SC_CALIB_SIDE32 = 1, 2, 4, 8, 16
+SC_CALIB_LOGSIGMA, SC_CALIB_NO_TRUNK, SC_CALIB_DEMIX_HINT, SC_CALIB_FLAT_META, SC_CALIB_SIDE32, SC_CALIB_TD3 = 1, 2, 4, 8, 16, 32
 NET_ACTOR, NET_CRITIC_1, NET_CRITIC_2, NET_TARGET_CRITIC_1, NET_TARGET_CRITIC_2, NET_TARGET_ACTOR = range(6)
 SLOT_PARAM, SLOT_ADAM_M, SLOT_ADAM_V = 0, 1, 2
 
@@ -52,7 +52,8 @@ class ScCalibConfig(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("batch_size", C.c_int32), ("mem_size", C.c_int32), ("n_actions", C.c_int32),
                 ("M", C.c_int32), ("img", C.c_int32), ("use_hint", C.c_int32), ("variant", C.c_int32),
                 ("gamma", C.c_double), ("tau", C.c_double), ("lr_actor", C.c_double), ("lr_critic", C.c_double), ("alpha", C.c_double),
-                ("hint_threshold", C.c_float), ("admm_rho", C.c_float), ("rng_seed", C.c_uint64)]
+                ("hint_threshold", C.c_float), ("admm_rho", C.c_float), ("rng_seed", C.c_uint64),
+                ("update_actor_interval", C.c_int32), ("reserved", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol of include/smartcal_b200.h
@@ -105,6 +106,8 @@ SIGNATURES = {
     "sc_calib_learn": (C.c_int, [C.c_void_p, C.POINTER(ScNoise), C.POINTER(ScLearnStats)]),
     "sc_calib_soft_update": (C.c_int, [C.c_void_p, C.c_float]),
     "sc_calib_launch_count": (C.c_int64, [C.c_void_p]),
+    "sc_calib_get_per_beta": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "sc_calib_set_per_beta": (C.c_int, [C.c_void_p, C.c_double]),
 }
 
 _lib = None

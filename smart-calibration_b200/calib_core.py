@@ -12,7 +12,7 @@ _DT = {(4, 0): torch.float32, (4, 1): torch.int32, (8, 1): torch.int64, (8, 0): 
 
 class CalibDevice:
     def __init__(self, batch_size, mem_size, n_actions, M, gamma, tau, lr_actor, lr_critic, alpha, use_hint=False, hint_threshold=0.1,
-                 admm_rho=1.0, img=128, rng_seed=0, device=None, variant=0):
+                 admm_rho=1.0, img=128, rng_seed=0, device=None, variant=0, update_actor_interval=2):
         self.lib = L.load()
         if not torch.cuda.is_available():
             raise L.SmartcalError("no CUDA device visible: smart-calibration_b200 has no CPU fallback")
@@ -21,7 +21,7 @@ class CalibDevice:
         cfg = L.ScCalibConfig(abi_version=L.SC_ABI_VERSION, batch_size=self.B, mem_size=self.C, n_actions=self.A, M=self.M, img=self.img,
                               use_hint=int(bool(use_hint)), variant=int(variant), gamma=float(gamma), tau=float(tau), lr_actor=float(lr_actor),
                               lr_critic=float(lr_critic), alpha=float(alpha), hint_threshold=float(hint_threshold),
-                              admm_rho=float(admm_rho), rng_seed=int(rng_seed))
+                              admm_rho=float(admm_rho), rng_seed=int(rng_seed), update_actor_interval=int(update_actor_interval))
         self.cfg = cfg
         nbytes = self.lib.sc_calib_arena_bytes(C.byref(cfg))
         if nbytes == 0:
@@ -110,6 +110,37 @@ class CalibDevice:
             return {f: getattr(s, f) for f, _ in s._fields_}
         L.check(self.lib.sc_calib_learn(self.h, C.byref(n), None))
         return None
+
+    def learn_td3(self, per_u01=None, target_noise=None, want_stats=False):
+        """SC_CALIB_TD3 agents: one demix_td3 learn().  per_u01 (B float64 uniforms of PER.sample_buffer) and target_noise (the
+        np.random.normal(scale=0.2) scalar) reproduce the caller's numpy stream; None: device Philox"""
+        n = self._noise
+        n.eps_next_host = n.eps_cur_host = n.eps_dual_host = n.batch_idx_host = None
+        keep = None
+        if per_u01 is None:
+            n.per_u01_host, n.has_td3_target_noise = None, 0
+        else:
+            keep = np.ascontiguousarray(np.asarray(per_u01, dtype=np.float64).reshape(-1))
+            if keep.size != self.B:
+                raise ValueError(f"need {self.B} uniforms")
+            n.per_u01_host, n.td3_target_noise, n.has_td3_target_noise = keep.ctypes.data, float(target_noise), 1
+        try:
+            if want_stats:
+                L.check(self.lib.sc_calib_learn(self.h, C.byref(n), C.byref(self._stats)))
+                s = self._stats
+                return {f: getattr(s, f) for f, _ in s._fields_}
+            L.check(self.lib.sc_calib_learn(self.h, C.byref(n), None))
+            return None
+        finally:
+            n.per_u01_host, n.has_td3_target_noise = None, 0
+
+    def per_beta(self):
+        b = C.c_double()
+        L.check(self.lib.sc_calib_get_per_beta(self.h, C.byref(b)))
+        return b.value
+
+    def set_per_beta(self, beta):
+        L.check(self.lib.sc_calib_set_per_beta(self.h, float(beta)))
 
     def soft_update(self, tau):
         L.check(self.lib.sc_calib_soft_update(self.h, float(tau)))

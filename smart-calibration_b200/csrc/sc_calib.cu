@@ -15,12 +15,16 @@
 #include "../../include/smartcal_b200.h"
 #include "sc_calib_kernels.cuh"
 #include "sc_conv_tc.cuh"
+#include "sc_params.h"
 
 namespace sc {
 cudaError_t launch_soft_update(const float* src, float* dst, size_t n, float tau, cudaStream_t st);
 cudaError_t launch_fill_normal(float* out, int n, uint64_t seed, uint64_t stream, cudaStream_t st);
 cudaError_t launch_fill_normal_p(float* out, int n, uint64_t seed, const unsigned long long* stream_dev, cudaStream_t st);
 int encode_map_f32_2d(void* out, const void* base, int ld, int rows, int box_rows);      // sc_api.cu
+cudaError_t launch_per_sample(const PerSampleP* pp, int E, int B, cudaStream_t st);        // sc_per.cu
+cudaError_t launch_per_update(const PerUpdateP* pp, int E, int B, cudaStream_t st);
+cudaError_t launch_admm_update(const AdmmP* pp, int E, cudaStream_t st);
 }  // namespace sc
 
 using namespace sc;
@@ -66,16 +70,20 @@ __global__ void k_gather(const float* __restrict__ src, const int* __restrict__ 
 }
 
 // side network: x1 = [sky | action?] -> relu(fc_a) (128) -> relu(fc_b) (16) -> feat[b][5408:5424]; keeps x1, h1, o16
+// act_first: x1 = [action | sky] (demix_td3.py:279 concatenates (action, metadata); demix_sac.py / calib_sac.py the other way round)
 __global__ void __launch_bounds__(128) k_side_fwd(const float* __restrict__ sky, int SKY, const float* __restrict__ act, int A,
                                                   const float* __restrict__ wa, const float* __restrict__ ba, const float* __restrict__ wb,
                                                   const float* __restrict__ bb, float* __restrict__ x1, float* __restrict__ h1,
-                                                  float* __restrict__ o16, float* __restrict__ feat, int side, int feat_ld, int flat) {
+                                                  float* __restrict__ o16, float* __restrict__ feat, int side, int feat_ld, int flat,
+                                                  int act_first = 0) {
   __shared__ float sx[192];
   __shared__ float sh[HID];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int K1 = SKY + (act ? A : 0);
   for (int i = tid; i < K1; i += 128) {
-    const float v = i < SKY ? sky[(size_t)b * SKY + i] : act[(size_t)b * A + (i - SKY)];
+    float v;
+    if (act && act_first) v = i < A ? act[(size_t)b * A + i] : sky[(size_t)b * SKY + (i - A)];
+    else v = i < SKY ? sky[(size_t)b * SKY + i] : act[(size_t)b * A + (i - SKY)];
     sx[i] = v;
     x1[(size_t)b * K1 + i] = v;
   }
@@ -189,7 +197,7 @@ __global__ void k_outer(const float* __restrict__ dq, const float* __restrict__ 
 __global__ void __launch_bounds__(128) k_side_bwd(const float* __restrict__ dfeat_side, long ld_dfeat, const float* __restrict__ o16,
                                                   const float* __restrict__ h1, const float* __restrict__ wb, const float* __restrict__ wa, int K1,
                                                   int SKY, int A, float* __restrict__ d16, float* __restrict__ dh1, float* __restrict__ dact,
-                                                  int accumulate, int side) {
+                                                  int accumulate, int side, int act_first = 0) {
   __shared__ float sd[SIDEMAX];
   __shared__ float sdh[HID];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -209,7 +217,8 @@ __global__ void __launch_bounds__(128) k_side_bwd(const float* __restrict__ dfea
   __syncthreads();
   if (dact != nullptr && tid < A) {
     float s = 0.f;
-    for (int n = 0; n < HID; ++n) s = fmaf(sdh[n], wa[(size_t)n * K1 + SKY + tid], s);
+    const int col = (act_first ? 0 : SKY) + tid;
+    for (int n = 0; n < HID; ++n) s = fmaf(sdh[n], wa[(size_t)n * K1 + col], s);
     dact[(size_t)b * A + tid] = (accumulate ? dact[(size_t)b * A + tid] : 0.f) + s;
   }
 }
@@ -335,6 +344,150 @@ __global__ void __launch_bounds__(256) k_actor_loss(const float* __restrict__ lo
   }
 }
 
+// ---- demixing conv TD3 (demixing_rl/demix_td3.py) ---------------------------------------------------------------------
+// deterministic policy head (:342): a = tanh(fc22 x21).  Target pass (:487-491): a = clamp(a + n, -1, 1) with ONE scalar n per
+// step; `noise` holds it already clamped to [-0.5, 0.5] (host draw), or a raw N(0,1) Philox value when `noise_raw` (device RNG:
+// scaled by 0.2 and clamped here).  choose_action (:448-453): per-action additive noise `anoise` (A values), clamp to [-1, 1].
+__global__ void __launch_bounds__(128) k_td3_head(const float* __restrict__ x21, const float* __restrict__ w, const float* __restrict__ bias, int A,
+                                                  const float* __restrict__ noise, int noise_raw, const float* __restrict__ anoise,
+                                                  float* __restrict__ act) {
+  __shared__ float sx[HID];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  sx[tid] = x21[(size_t)b * HID + tid];
+  __syncthreads();
+  if (tid < A) {
+    float m = bias[tid];
+    const float* w1 = w + (size_t)tid * HID;
+    for (int i = 0; i < HID; ++i) m = fmaf(w1[i], sx[i], m);
+    float a = tanhf(m);
+    if (noise != nullptr) {
+      float n = noise[0];
+      if (noise_raw) n = fminf(fmaxf(0.2f * n, -0.5f), 0.5f);
+      a = fminf(fmaxf(__fadd_rn(a, n), -1.f), 1.f);
+    }
+    if (anoise != nullptr) a = fminf(fmaxf(__fadd_rn(a, anoise[tid]), -1.f), 1.f);
+    act[(size_t)b * A + tid] = a;
+  }
+}
+
+// y = r + gamma * (done ? 0 : min(q1', q2'))   (:498-504)
+__global__ void k_td3_target(const float* qt1, const float* qt2, const float* r, const float* done, float gamma, int B, float* y) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float m = done[b] != 0.f ? 0.f : fminf(qt1[b], qt2[b]);
+  y[b] = __fadd_rn(r[b], __fmul_rn(gamma, m));
+}
+
+// priority errors of the pre-pass (:506-511): 0.5 (|q1 - y| + |q2 - y|), float32 like the numpy expression
+__global__ void k_td3_per_err(const float* q1, const float* q2, const float* y, int B, float* err) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  err[b] = __fmul_rn(0.5f, __fadd_rn(fabsf(__fsub_rn(q1[b], y[b])), fabsf(__fsub_rn(q2[b], y[b]))));
+}
+
+// PER.mse (:137-140) with is_weights (B,) against (B,1) errors: the (B,B) broadcast makes the loss mean(w) * mean((y - q)^2), so
+// dL/dq = mean(w) * 2 (q - y) / B.  One block.
+__global__ void __launch_bounds__(256) k_td3_critic_seed(const float* __restrict__ q, const float* __restrict__ y, const float* __restrict__ wsum,
+                                                         int B, float* __restrict__ dq, float* __restrict__ stat) {
+  __shared__ float sh[8];
+  const float wm = wsum[0] / (float)B;
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += 256) {
+    const float d = q[b] - y[b];
+    dq[b] = wm * (2.f * d / (float)B);
+    s = fmaf(d, d, s);
+  }
+  s = block_sum_float(s, sh);
+  if (threadIdx.x == 0) stat[0] = wm * (s / (float)B);
+}
+
+// actor loss -mean(q1(s, pi(s)) * w) (:538 / :553) with the same broadcast = -mean(q) mean(w): dq = -mean(w) / B for every row;
+// ds[b][j] = dq * head_w1[flat + j] seeds the backward pass through critic_1's side network.  stat[0] = that loss term.  One block.
+__global__ void __launch_bounds__(256) k_td3_actor_seed(const float* __restrict__ q, const float* __restrict__ hw, const float* __restrict__ wsum,
+                                                        int B, float* __restrict__ ds, int side, int flat, float* __restrict__ stat) {
+  __shared__ float sh[8];
+  const float wm = wsum[0] / (float)B;
+  const float g = -wm / (float)B;
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += 256) s += q[b];
+  for (int i = threadIdx.x; i < B * side; i += 256) ds[i] = g * hw[flat + (i % side)];
+  s = block_sum_float(s, sh);
+  if (threadIdx.x == 0) stat[0] = -(s / (float)B) * wm;
+}
+
+// ADMM hint penalty of one inner actor step (:555-561): pen = mean(w) (lambda . d + rho / 2 mse(a, hint)) / n with d = a - hint
+// flattened, n = B A.  dact += mean(w) / n (lambda + rho d / n); stat[0] += pen, stat[1] = pen.  One block.
+__global__ void __launch_bounds__(256) k_td3_hint(const float* __restrict__ act, const float* __restrict__ hint, const float* __restrict__ lambda,
+                                                  const float* __restrict__ rho, const float* __restrict__ wsum, int B, int n,
+                                                  float* __restrict__ dact, float* __restrict__ stat) {
+  __shared__ float sh[8];
+  const float wm = wsum[0] / (float)B, r = rho[0], fn = (float)n;
+  float dot = 0.f, sq = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float d = act[i] - hint[i];
+    dot = fmaf(lambda[i], d, dot);
+    sq = fmaf(d, d, sq);
+    dact[i] += (wm / fn) * (lambda[i] + r * d / fn);
+  }
+  dot = block_sum_float(dot, sh);
+  sq = block_sum_float(sq, sh);
+  if (threadIdx.x == 0) {
+    const float pen = (dot + 0.5f * r * (sq / fn)) * wm / fn;
+    stat[0] += pen;
+    stat[1] = pen;
+  }
+}
+
+// backward of a = tanh(fc22 x21) for one row: dfc = dact (1 - a^2); dpre = (W22^T dfc) * ELU'(x21)
+__global__ void __launch_bounds__(128) k_td3_head_bwd(const float* __restrict__ da, const float* __restrict__ act, int A, const float* __restrict__ w,
+                                                      const float* __restrict__ x21, float* __restrict__ dfc, float* __restrict__ dpre) {
+  __shared__ float sm[AMAXC];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid < A) {
+    const size_t o = (size_t)b * A + tid;
+    const float a = act[o];
+    const float g = __fmul_rn(da[o], __fsub_rn(1.f, __fmul_rn(a, a)));
+    sm[tid] = g;
+    dfc[o] = g;
+  }
+  __syncthreads();
+  float s = 0.f;
+  for (int j = 0; j < A; ++j) s = fmaf(sm[j], w[(size_t)j * HID + tid], s);
+  dpre[(size_t)b * HID + tid] = s * elu_grad_from_out(x21[(size_t)b * HID + tid]);
+}
+
+// PER.store_transition with error=None (:60-66) + SumTree.add / update (demix_sac.py:66-110): the new leaf gets the largest leaf
+// priority (absolute_error_upper while the tree is empty), the change is added to every ancestor in order.  One block.
+__global__ void __launch_bounds__(256) k_tree_add(double* __restrict__ tree, int C, int slot, double clip) {
+  __shared__ double sh[256];
+  double m = 0.0;
+  for (int i = threadIdx.x; i < C; i += 256) m = fmax(m, tree[C - 1 + i]);
+  sh[threadIdx.x] = m;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double p = sh[0];
+    if (p == 0.0) p = clip;
+    int node = C - 1 + slot;
+    const double change = __dsub_rn(p, tree[node]);
+    tree[node] = p;
+    while (node != 0) {
+      node = (node - 1) >> 1;
+      tree[node] = __dadd_rn(tree[node], change);
+    }
+  }
+}
+
+// update_network_parameters over the BatchNorm num_batches_tracked entries (:413-418): tau * online + (1 - tau) * target in float32
+// (int64 * python float promotes to float32), truncated back to int64 by load_state_dict's copy_
+__global__ void k_nbt_blend(const long long* __restrict__ src, long long* __restrict__ dst, float tau, float omt) {
+  const int i = threadIdx.x;
+  if (i < 3) dst[i] = (long long)__fadd_rn(__fmul_rn(tau, (float)src[i]), __fmul_rn(omt, (float)dst[i]));
+}
+
 }  // namespace
 
 // =====================================================================================================================
@@ -366,6 +519,9 @@ struct sc_calib {
   sc_calib_config cfg;
   int B, C, A, M, SKY, K1C;           // K1C: critic side input width (sky + action)
   // network family (sc_calib_config.variant): calibration (calib_sac.py), demixing_rl (demix_sac.py) or demixing_fuzzy MLP
+  bool td3;                           // SC_CALIB_TD3: demixing_rl/demix_td3.py program (tanh policy, target actor, PER, state_dict soft update)
+  int act_first;                      // critic side input is cat((action, metadata)) (demix_td3.py:279) instead of (metadata, action)
+  int interval;                       // update_actor_interval
   bool trunk;                         // conv trunk present (use_influence); false: pure MLP, features = side network only
   int side, flat, feat;               // side-network width (INNER_DIM), flattened trunk width (0 without trunk), feat = flat + side
   int sigma_mode, kld_mode;           // 0 calibration, 1 demixing (log-sigma heads; unclamped KLD + resampled dual update)
@@ -376,17 +532,27 @@ struct sc_calib {
   size_t arena_bytes;
   CLayout La, Lc;
   // parameter-like blocks: [actor | critic_1 | critic_2]
-  float *params, *grads, *adam_m, *adam_v, *targets;     // targets: [t1 | t2] in critic layout
+  float *params, *grads, *adam_m, *adam_v, *targets;     // targets: [t1 | t2] in critic layout (+ [target actor] in actor layout, TD3)
   size_t off_net[3], n_params;
-  float* bnbuf[5];                    // per net: rm1 rv1 rm2 rv2 rm3 rv3 (16,16,32,32,32,32 floats)
+  float* bnbuf[6];                    // per net: rm1 rv1 rm2 rv2 rm3 rv3 (16,16,32,32,32,32 floats)
   // conv2 / conv3 on tcgen05 (sc_conv_tc.cuh): tf32 big / small copies of the two weight tensors of every network
   // ([2][32 x 400] then [2][32 x 800] floats) and their tensor maps [net][layer - 1][big, small]
-  float* conv_hl[5];
-  CUtensorMap conv_map[5][2][2];
+  float* conv_hl[6];
+  CUtensorMap conv_map[6][2][2];
   bool conv_tc;
   int conv_dbg;
   unsigned long long* conv_ts;        // debug timeline of k_conv_fwd_tc (SMARTCAL_STAMPS), "debug_ts"
-  long long* nbt[5];                  // per net: 3 counters
+  long long* nbt[6];                  // per net: 3 counters
+  // TD3: prioritized replay (float64 sum tree exactly like the reference's flat heap), ADMM state of the actor loop, target noise
+  double* tree;
+  int* tree_idx;
+  float *is_w, *is_wsum, *per_err, *per_ps;
+  double* u01_dev;
+  double per_beta;
+  float *lambda, *admm_y0, *admm_a0, *admm_rho_dev, *tnoise, *anoise;
+  AdmmP* admm_dev;                    // [6]: loop start, then the bookkeeping after inner step 0..4
+  AdmmP admm_host[6];
+  float* dq2;                         // second critic's loss seed
   // replay
   float *r_img, *r_img2, *r_sky, *r_sky2, *r_act, *r_hint, *r_rew, *r_done;
   int* bidx;
@@ -410,13 +576,18 @@ struct sc_calib {
   float* h_stage;                     // pinned host staging
   float* h_stats;
   int* h_idx;
+  double* h_u01;                      // pinned: B PER uniforms + the target-noise scalar of one TD3 learn()
   int64_t mem_cntr, learn_counter, t_actor, t_critic, launches, noise_ctr;
   bool batch_ready;
   float admm_rho;
   int wg_blocks, nch, sm_count;
   // per-step scalars in device memory (Adam bias corrections of the three optimizers, Philox stream ids of the noise draws): one
   // small copy per step; with them the launch sequence of learn() is identical from step to step and replays from a CUDA graph
-  struct StepScalars { AdamP adam[3]; unsigned long long noise[4]; };
+  struct StepScalars {
+    AdamP adam[3]; unsigned long long noise[4];
+    AdamP adam_x[5];                 // TD3 + hints: the actor takes five Adam steps inside one learn() (demix_td3.py:548-563)
+    PerSampleP per_s; PerUpdateP per_u;
+  };
   StepScalars* step_dev;
   StepScalars* step_host;          // pinned, two slots
   cudaEvent_t ev_step[2];
@@ -442,12 +613,13 @@ static CLayout critic_layout_c(int K1, bool trunk, int side, int feat) {
   L.add("head.weight", 1, feat); L.add("head.bias", 1, 1);
   return L;
 }
-static CLayout actor_layout_c(int SKY, int A, bool trunk, int side, int feat, int sigma_mode) {
+static CLayout actor_layout_c(int SKY, int A, bool trunk, int side, int feat, int sigma_mode, bool td3) {
   CLayout L;
   if (trunk) add_trunk(L);
   L.add("fc11.weight", HID, SKY); L.add("fc11.bias", 1, HID);
   L.add("fc12.weight", side, HID); L.add("fc12.bias", 1, side);
   L.add("fc21.weight", HID, feat); L.add("fc21.bias", 1, HID);
+  if (td3) { L.add("fc22.weight", A, HID); L.add("fc22.bias", 1, A); return L; }      // demix_td3.py:318: one tanh head
   L.add("fc22mu.weight", A, HID); L.add("fc22mu.bias", 1, A);
   // calib_sac.py:185 names the second head fc22sigma, demix_sac.py:467 fc22logsigma
   if (sigma_mode == 0) { L.add("fc22sigma.weight", A, HID); L.add("fc22sigma.bias", 1, A); }
@@ -467,6 +639,10 @@ static NetP net_ptrs(float* b, const CLayout& L, bool actor) {
     p.fa_w = b + L.off("fc11.weight"); p.fa_b = b + L.off("fc11.bias");
     p.fb_w = b + L.off("fc12.weight"); p.fb_b = b + L.off("fc12.bias");
     p.h_w = b + L.off("fc21.weight"); p.h_b = b + L.off("fc21.bias");
+    if (L.off("fc22.weight") != (size_t)-1) {         // TD3: single head, kept in the mu slots
+      p.mu_w = b + L.off("fc22.weight"); p.mu_b = b + L.off("fc22.bias");
+      return p;
+    }
     p.mu_w = b + L.off("fc22mu.weight"); p.mu_b = b + L.off("fc22mu.bias");
     const bool logsig = L.off("fc22sigma.weight") == (size_t)-1;
     p.sg_w = b + L.off(logsig ? "fc22logsigma.weight" : "fc22sigma.weight"); p.sg_b = b + L.off(logsig ? "fc22logsigma.bias" : "fc22sigma.bias");
@@ -493,11 +669,11 @@ static size_t carve_c(sc_calib* a, char* base) {
   a->off_net[0] = 0; a->off_net[1] = a->La.size; a->off_net[2] = a->La.size + a->Lc.size;
   a->n_params = a->La.size + 2 * a->Lc.size;
   a->params = cv.f(a->n_params); a->grads = cv.f(a->n_params); a->adam_m = cv.f(a->n_params); a->adam_v = cv.f(a->n_params);
-  a->targets = cv.f(2 * a->Lc.size);
-  for (int n = 0; n < 5; ++n) { a->bnbuf[n] = cv.f(160); a->nbt[n] = (long long*)cv.take(4 * sizeof(long long)); }
+  a->targets = cv.f(2 * a->Lc.size + (a->td3 ? a->La.size : 0));
+  for (int n = 0; n < 6; ++n) { a->bnbuf[n] = cv.f(160); a->nbt[n] = (long long*)cv.take(4 * sizeof(long long)); }
   a->conv_ts = (unsigned long long*)cv.take(sizeof(unsigned long long) * 1024);
   reg("debug_ts", a->conv_ts, 1024, 1, 8);
-  for (int n = 0; n < 5; ++n) a->conv_hl[n] = cv.f(a->trunk ? (size_t)2 * C2 * C1 * TAPS + (size_t)2 * C3 * C2 * TAPS : 4);
+  for (int n = 0; n < 6; ++n) a->conv_hl[n] = cv.f(a->trunk ? (size_t)2 * C2 * C1 * TAPS + (size_t)2 * C3 * C2 * TAPS : 4);
   const size_t NIMG = a->trunk ? (size_t)IMG * IMG : 0;       // no influence maps without the conv trunk
   const size_t FEATR = a->feat, SIDER = a->side;
   a->r_img = cv.f(C * NIMG); a->r_img2 = cv.f(C * NIMG);
@@ -536,6 +712,19 @@ static size_t carve_c(sc_calib* a, char* base) {
   a->wg_partial = cv.f(a->trunk ? (size_t)a->wg_blocks * C3 * C2 * TAPS : 4);
   a->splitk = cv.f((size_t)32 * B * HID);
   a->stats = cv.f(16); a->rho = cv.f(4); a->hint_out = cv.f(8);
+  if (a->td3) {
+    a->tree = (double*)cv.take(sizeof(double) * (2 * C - 1)); reg("tree", a->tree, 1, 2 * (int64_t)C - 1, 8);
+    a->tree_idx = (int*)cv.take(B * sizeof(int)); reg("tree_idx", a->tree_idx, B, 1, 4, 1);
+    a->is_w = cv.f(B); reg("is_weights", a->is_w, B, 1);
+    a->is_wsum = cv.f(4); a->per_err = cv.f(B); a->per_ps = cv.f(B); reg("per_errors", a->per_err, B, 1); reg("per_priorities", a->per_ps, B, 1);
+    a->u01_dev = (double*)cv.take(sizeof(double) * B);
+    a->lambda = cv.f(B * A); a->admm_y0 = cv.f(B * A); a->admm_a0 = cv.f(B * A); a->admm_rho_dev = cv.f(4); reg("admm_rho", a->admm_rho_dev, 1, 1);
+    reg("admm_lambda", a->lambda, B, A);
+    a->tnoise = cv.f(4); a->anoise = cv.f(A);
+    a->admm_dev = (AdmmP*)cv.take(6 * sizeof(AdmmP));
+    a->dq2 = cv.f(B);
+    reg("target_action", a->a2, B, A);
+  }
   return cv.off;
 }
 
@@ -546,6 +735,13 @@ static int check_cfg_c(const sc_calib_config* c) {
   if (trunk && c->img != IMG) return failc(SC_ERR_ARG, "only input_dims = [1,128,128] is built (calibration/main_sac.py:17)");
   if (trunk && (c->variant & SC_CALIB_SIDE32)) return failc(SC_ERR_UNSUPPORTED, "INNER_DIM = 32 is built for the MLP (use_influence=False) family only");
   if (c->batch_size < 2 || c->mem_size < c->batch_size) return failc(SC_ERR_ARG, "need 2 <= batch_size <= mem_size");
+  if (c->variant & SC_CALIB_TD3) {
+    if (!trunk || !(c->variant & SC_CALIB_FLAT_META) || (c->variant & (SC_CALIB_LOGSIGMA | SC_CALIB_SIDE32)))
+      return failc(SC_ERR_ARG, "SC_CALIB_TD3 is the demixing_rl/demix_td3.py agent: conv trunk, flat metadata, INNER_DIM 16, one tanh head");
+    if (c->mem_size & (c->mem_size - 1)) return failc(SC_ERR_ARG, "TD3 replay is prioritized: max_mem_size must be a power of two (demix_sac.py:47)");
+    if (c->update_actor_interval < 1) return failc(SC_ERR_ARG, "update_actor_interval must be >= 1");
+    if (c->batch_size > 8192) return failc(SC_ERR_ARG, "batch_size <= 8192 for the prioritized sampler");
+  }
   const int sky = (c->variant & SC_CALIB_FLAT_META) ? c->M : 7 * (c->M + 1);
   if (c->n_actions < 1 || c->n_actions > AMAXC || c->M < 1 || sky + c->n_actions > 192)
     return failc(SC_ERR_ARG, "n_actions must be in [1,%d] and metadata width + n_actions <= 192", AMAXC);
@@ -555,6 +751,9 @@ static void init_dims_c(sc_calib* a, const sc_calib_config* c) {
   a->cfg = *c;
   a->B = c->batch_size; a->C = c->mem_size; a->A = c->n_actions; a->M = c->M;
   a->trunk = !(c->variant & SC_CALIB_NO_TRUNK);
+  a->td3 = (c->variant & SC_CALIB_TD3) != 0;
+  a->act_first = a->td3 ? 1 : 0;
+  a->interval = a->td3 ? c->update_actor_interval : 1;
   a->side = (c->variant & SC_CALIB_SIDE32) ? 32 : SIDE;
   a->flat = a->trunk ? FLAT : 0;
   a->feat = a->flat + a->side;
@@ -562,7 +761,7 @@ static void init_dims_c(sc_calib* a, const sc_calib_config* c) {
   a->kld_mode = (c->variant & SC_CALIB_DEMIX_HINT) ? 1 : 0;
   a->SKY = (c->variant & SC_CALIB_FLAT_META) ? c->M : 7 * (c->M + 1);
   a->K1C = a->SKY + a->A;
-  a->La = actor_layout_c(a->SKY, a->A, a->trunk, a->side, a->feat, a->sigma_mode);
+  a->La = actor_layout_c(a->SKY, a->A, a->trunk, a->side, a->feat, a->sigma_mode, a->td3);
   a->Lc = critic_layout_c(a->K1C, a->trunk, a->side, a->feat);
   a->wg_blocks = 296;
   a->sm_count = 148;
@@ -576,7 +775,10 @@ static inline int grid_for(size_t n, int block = 256, int cap = 148 * 16) {
   return (int)(g > (size_t)cap ? cap : (g ? g : 1));
 }
 
-static int bn_forward(sc_calib* a, TrunkWs& t, const NetP& P, int net, int l, int C, int HW, int act, int train, int Bn) {
+// rep > 1 (training mode): the running statistics take `rep` momentum updates with the same batch statistics -- what `rep` forward
+// passes over the same input with unchanged weights leave behind (demix_td3.py: the priority pre-pass :506-511 before the training
+// pass :516-517 of the critics)
+static int bn_forward(sc_calib* a, TrunkWs& t, const NetP& P, int net, int l, int C, int HW, int act, int train, int Bn, int rep = 1) {
   float* rb = a->bnbuf[net];
   float* rm = rb + (l == 0 ? 0 : l == 1 ? 32 : 96);
   float* rv = rm + (l == 0 ? 16 : 32);
@@ -588,8 +790,10 @@ static int bn_forward(sc_calib* a, TrunkWs& t, const NetP& P, int net, int l, in
     k_chan_reduce<<<dim3(C, nch), 256, 0, a->st>>>(r);
     LAUNCH_OK(a);
     BnFinalizeP f{a->red_partial, nch, P.g[l], P.be[l], rm, rv, a->nbt[net] + l, t.mean[l], t.rstd[l], t.scale[l], t.shift[l], (double)Bn * HW, 1};
-    k_bn_finalize<<<1, 32, 0, a->st>>>(f, C);
-    LAUNCH_OK(a);
+    for (int r = 0; r < rep; ++r) {
+      k_bn_finalize<<<1, 32, 0, a->st>>>(f, C);
+      LAUNCH_OK(a);
+    }
   } else {
     BnFinalizeP f{nullptr, 0, P.g[l], P.be[l], rm, rv, a->nbt[net] + l, t.mean[l], t.rstd[l], t.scale[l], t.shift[l], 1.0, 0};
     k_bn_finalize<<<1, 32, 0, a->st>>>(f, C);
@@ -603,13 +807,13 @@ static int bn_forward(sc_calib* a, TrunkWs& t, const NetP& P, int net, int l, in
 }
 
 // conv trunk forward of network `net` (parameters P) on images x [Bn][16384] into workspace t
-static int trunk_forward(sc_calib* a, TrunkWs& t, const NetP& P, int net, const float* x, int act, int train, int Bn) {
+static int trunk_forward(sc_calib* a, TrunkWs& t, const NetP& P, int net, const float* x, int act, int train, int Bn, int rep = 1) {
   using G1 = ConvGeom<1, C1, IMG, H1C>;
   using G2 = ConvGeom<C1, C2, H1C, H2C>;
   using G3 = ConvGeom<C2, C3, H2C, H3C>;
   k_conv_fwd<1, C1, IMG, H1C><<<dim3(G1::BLOCKS_PER_IMG, Bn), 256, 0, a->st>>>(x, (size_t)IMG * IMG, P.cw[0], P.cb[0], t.z[0]);
   LAUNCH_OK(a);
-  int rc = bn_forward(a, t, P, net, 0, C1, H1C * H1C, act, train, Bn);
+  int rc = bn_forward(a, t, P, net, 0, C1, H1C * H1C, act, train, Bn, rep);
   if (rc) return rc;
   if (a->conv_tc) {
     // conv2 / conv3 as implicit GEMMs on tcgen05: this network's weights as tf32 big / small parts first (they change every step)
@@ -621,18 +825,18 @@ static int trunk_forward(sc_calib* a, TrunkWs& t, const NetP& P, int net, const 
     k_conv_fwd_tc<C1, H1C, H2C><<<t2 < a->sm_count ? t2 : a->sm_count, CT_THREADS, conv_tc_smem_bytes(), a->st>>>(
         ConvTcP{t.a[0], (size_t)C1 * H1C * H1C, P.cb[1], t.z[1], Bn, a->conv_ts, a->conv_dbg}, a->conv_map[net][0][0], a->conv_map[net][0][1]);
     LAUNCH_OK(a);
-    if ((rc = bn_forward(a, t, P, net, 1, C2, H2C * H2C, act, train, Bn))) return rc;
+    if ((rc = bn_forward(a, t, P, net, 1, C2, H2C * H2C, act, train, Bn, rep))) return rc;
     k_conv_fwd_tc<C2, H2C, H3C><<<t3 < a->sm_count ? t3 : a->sm_count, CT_THREADS, conv_tc_smem_bytes(), a->st>>>(
         ConvTcP{t.a[1], (size_t)C2 * H2C * H2C, P.cb[2], t.z[2], Bn, nullptr, a->conv_dbg}, a->conv_map[net][1][0], a->conv_map[net][1][1]);
     LAUNCH_OK(a);
-    return bn_forward(a, t, P, net, 2, C3, H3C * H3C, act, train, Bn);
+    return bn_forward(a, t, P, net, 2, C3, H3C * H3C, act, train, Bn, rep);
   }
   k_conv_fwd<C1, C2, H1C, H2C><<<dim3(G2::BLOCKS_PER_IMG, Bn), 256, 0, a->st>>>(t.a[0], (size_t)C1 * H1C * H1C, P.cw[1], P.cb[1], t.z[1]);
   LAUNCH_OK(a);
-  if ((rc = bn_forward(a, t, P, net, 1, C2, H2C * H2C, act, train, Bn))) return rc;
+  if ((rc = bn_forward(a, t, P, net, 1, C2, H2C * H2C, act, train, Bn, rep))) return rc;
   k_conv_fwd<C2, C3, H2C, H3C><<<dim3(G3::BLOCKS_PER_IMG, Bn), 256, 0, a->st>>>(t.a[1], (size_t)C2 * H2C * H2C, P.cw[2], P.cb[2], t.z[2]);
   LAUNCH_OK(a);
-  return bn_forward(a, t, P, net, 2, C3, H3C * H3C, act, train, Bn);
+  return bn_forward(a, t, P, net, 2, C3, H3C * H3C, act, train, Bn, rep);
 }
 
 static int sgemm(sc_calib* a, const float* A_, long sam, long sak, const float* B_, long sbk, long sbn, float* C_, long ldc, int M, int N, int K,
@@ -754,9 +958,9 @@ static AdamP adam_hyper_c(double lr, int64_t t) {
   h.eps = 1e-8f;
   return h;
 }
-static int adam_step(sc_calib* a, int net) {       // hyper-parameters of optimizer `net`: step_dev->adam[net] (written by learn())
+static int adam_step(sc_calib* a, int net, const AdamP* hp = nullptr) {       // hyper-parameters of optimizer `net`: step_dev->adam[net] (written by learn())
   const size_t n = net == 0 ? a->La.size : a->Lc.size, off = a->off_net[net];
-  k_adam<<<grid_for(n), 256, 0, a->st>>>(a->params + off, a->grads + off, a->adam_m + off, a->adam_v + off, n, &a->step_dev->adam[net]);
+  k_adam<<<grid_for(n), 256, 0, a->st>>>(a->params + off, a->grads + off, a->adam_m + off, a->adam_v + off, n, hp ? hp : &a->step_dev->adam[net]);
   LAUNCH_OK(a);
   return SC_OK;
 }
@@ -800,13 +1004,31 @@ int sc_calib_create(const sc_calib_config* cfg, void* arena, size_t arena_bytes,
     for (int i = 16; i < 32; ++i) init[i] = 1.f;
     for (int i = 64; i < 96; ++i) init[i] = 1.f;
     for (int i = 128; i < 160; ++i) init[i] = 1.f;
-    for (int n = 0; n < 5; ++n) CKC(cudaMemcpyAsync(a->bnbuf[n], init.data(), 160 * sizeof(float), cudaMemcpyHostToDevice, a->st));
+    for (int n = 0; n < 6; ++n) CKC(cudaMemcpyAsync(a->bnbuf[n], init.data(), 160 * sizeof(float), cudaMemcpyHostToDevice, a->st));
     CKC(cudaStreamSynchronize(a->st));
   }
   const size_t stage = (size_t)2 * IMG * IMG + 2 * a->SKY + 2 * a->A + 8 + (size_t)2 * a->B * a->A;
   CKC(cudaHostAlloc((void**)&a->h_stage, stage * sizeof(float), cudaHostAllocDefault));
   CKC(cudaHostAlloc((void**)&a->h_stats, 16 * sizeof(float), cudaHostAllocDefault));
   CKC(cudaHostAlloc((void**)&a->h_idx, (size_t)a->B * sizeof(int), cudaHostAllocDefault));
+  a->h_u01 = nullptr;
+  a->per_beta = 0.4;                                                  // PER.beta (demix_td3.py:32)
+  if (a->td3) {
+    CKC(cudaHostAlloc((void**)&a->h_u01, ((size_t)a->B + 2) * sizeof(double), cudaHostAllocDefault));
+    // ADMM bookkeeping blocks of the actor loop (k_admm_update, sc_per.cu): constant from step to step
+    AdmmP* blk = a->admm_host;
+    for (int i = 0; i < 6; ++i) {
+      AdmmP& p = blk[i];
+      memset(&p, 0, sizeof(p));
+      p.mode = i == 0 ? 0 : 1; p.it = i - 1;
+      p.pi = a->pi; p.hint = a->r_hint; p.Ap = a->A; p.bidx = a->bidx; p.B = a->B; p.A = a->A;
+      p.lambda = a->lambda; p.y0 = a->admm_y0; p.a0 = a->admm_a0; p.rho = a->admm_rho_dev;
+      p.rho0 = cfg->admm_rho; p.corr_min = 0.5f;                      // demix_td3.py:400,403
+      p.stats_rho = nullptr;
+    }
+    CKC(cudaMemcpyAsync(a->admm_dev, blk, 6 * sizeof(AdmmP), cudaMemcpyHostToDevice, a->st));
+    CKC(cudaStreamSynchronize(a->st));
+  }
   CKC(cudaFuncSetAttribute(k_conv_wgrad<C1, C2, H1C, H2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024));
   CKC(cudaFuncSetAttribute(k_conv_wgrad<C2, C3, H2C, H3C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 101 * 1024));
   {
@@ -816,7 +1038,7 @@ int sc_calib_create(const sc_calib_config* cfg, void* arena, size_t arena_bytes,
     a->conv_dbg = d ? atoi(d) : 0;
     if (!getenv("SMARTCAL_STAMPS")) a->conv_ts = nullptr;
     if (a->conv_tc) {
-      for (int n = 0; n < 5; ++n) {
+      for (int n = 0; n < 6; ++n) {
         float* hl2 = a->conv_hl[n];
         float* hl3 = hl2 + (size_t)2 * C2 * C1 * TAPS;
         for (int part = 0; part < 2; ++part) {
@@ -859,6 +1081,7 @@ int sc_calib_destroy(sc_calib* a) {
   if (a->h_stage) cudaFreeHost(a->h_stage);
   if (a->h_stats) cudaFreeHost(a->h_stats);
   if (a->h_idx) cudaFreeHost(a->h_idx);
+  if (a->h_u01) cudaFreeHost(a->h_u01);
   if (a->own_arena && a->arena) cudaFree(a->arena);
   delete a;
   return SC_OK;
@@ -869,11 +1092,23 @@ int sc_calib_sync(sc_calib* a) {
   return SC_OK;
 }
 int64_t sc_calib_launch_count(sc_calib* a) { return a ? a->launches : 0; }
+int sc_calib_get_per_beta(sc_calib* a, double* beta_out) {
+  if (!a || !beta_out) return failc(SC_ERR_ARG, "null argument");
+  if (!a->td3) return failc(SC_ERR_STATE, "not a prioritized (SC_CALIB_TD3) agent");
+  *beta_out = a->per_beta;
+  return SC_OK;
+}
+int sc_calib_set_per_beta(sc_calib* a, double beta) {
+  if (!a) return failc(SC_ERR_ARG, "null handle");
+  if (!a->td3) return failc(SC_ERR_STATE, "not a prioritized (SC_CALIB_TD3) agent");
+  a->per_beta = beta;
+  return SC_OK;
+}
 
 int sc_calib_tensor(sc_calib* a, int net, int slot, const char* name, sc_tensor_info* out) {
   if (!a || !name || !out) return failc(SC_ERR_ARG, "null argument");
-  if (net < 0 || net > 4) return failc(SC_ERR_ARG, "bad net id %d", net);
-  const bool actor = net == SC_NET_ACTOR;
+  if (net < 0 || net > (a->td3 ? 5 : 4)) return failc(SC_ERR_ARG, "bad net id %d", net);
+  const bool actor = net == SC_NET_ACTOR || net == SC_NET_TARGET_ACTOR;
   const CLayout& L = actor ? a->La : a->Lc;
   // BatchNorm buffers
   const char* dot = strrchr(name, '.');
@@ -893,7 +1128,7 @@ int sc_calib_tensor(sc_calib* a, int net, int slot, const char* name, sc_tensor_
     base = (slot == 3 ? a->grads : blocks[slot]) + a->off_net[net];
   } else {
     if (slot != SC_SLOT_PARAM) return failc(SC_ERR_ARG, "targets have no optimizer state");
-    base = a->targets + (size_t)(net - 3) * a->Lc.size;
+    base = a->targets + (size_t)(net - 3) * a->Lc.size;       // [t1 | t2 | target actor]
   }
   if (!strcmp(name, "*")) { *out = sc_tensor_info{base, 1, (int64_t)L.size, (int64_t)L.size, 4, 0}; return SC_OK; }
   for (auto& d : L.t)
@@ -923,6 +1158,11 @@ int sc_calib_set_scalars(sc_calib* a, float rho, float admm_rho) {
   a->admm_rho = admm_rho;
   CKC(cudaMemcpyAsync(a->rho, &rho, sizeof(float), cudaMemcpyHostToDevice, a->st));
   CKC(cudaStreamSynchronize(a->st));
+  if (a->td3) {                     // agent.admm_rho (demix_td3.py:400): the value every learn() starts its ADMM loop from
+    for (auto& p : a->admm_host) p.rho0 = admm_rho;
+    CKC(cudaMemcpyAsync(a->admm_dev, a->admm_host, 6 * sizeof(AdmmP), cudaMemcpyHostToDevice, a->st));
+    CKC(cudaStreamSynchronize(a->st));
+  }
   return SC_OK;
 }
 
@@ -948,6 +1188,10 @@ int sc_calib_store_host(sc_calib* a, const float* img, const float* sky, const f
   CKC(cudaMemcpyAsync(a->r_hint + slot * a->A, t + a->A, a->A * 4, cudaMemcpyHostToDevice, a->st));
   CKC(cudaMemcpyAsync(a->r_rew + slot, t + 2 * a->A, 4, cudaMemcpyHostToDevice, a->st));
   CKC(cudaMemcpyAsync(a->r_done + slot, t + 2 * a->A + 1, 4, cudaMemcpyHostToDevice, a->st));
+  if (a->td3) {                                   // PER.store_transition(error=None): max-leaf priority, tree.add (demix_td3.py:60-67)
+    k_tree_add<<<1, 256, 0, a->st>>>(a->tree, a->C, (int)slot, 100.0);
+    LAUNCH_OK(a);
+  }
   a->mem_cntr++;
   return SC_OK;
 }
@@ -970,6 +1214,19 @@ int sc_calib_soft_update(sc_calib* a, float tau) {
   // calib_sac.py:271-276: parameters() only; the targets' BatchNorm buffers are never copied
   CKC(launch_soft_update(a->params + a->off_net[1], a->targets, 2 * a->Lc.size, tau, a->st));
   a->launches++;
+  if (a->td3) {
+    // demix_td3.py:408-432 walks state_dict(): the target actor moves too, and so do the BatchNorm buffers of all three targets
+    CKC(launch_soft_update(a->params + a->off_net[0], a->targets + 2 * a->Lc.size, a->La.size, tau, a->st));
+    a->launches++;
+    const int src[3] = {0, 1, 2}, dst[3] = {5, 3, 4};
+    const float omt = (float)(1.0 - (double)tau);
+    for (int i = 0; i < 3; ++i) {
+      CKC(launch_soft_update(a->bnbuf[src[i]], a->bnbuf[dst[i]], 160, tau, a->st));
+      k_nbt_blend<<<1, 32, 0, a->st>>>(a->nbt[src[i]], a->nbt[dst[i]], tau, omt);
+      LAUNCH_OK(a);
+      a->launches++;
+    }
+  }
   return SC_OK;
 }
 
@@ -983,6 +1240,24 @@ int sc_calib_act(sc_calib* a, const float* img, const float* sky, const float* e
   if (eps) memcpy(a->h_stage + NI + a->SKY, eps, a->A * 4);
   if (NI) CKC(cudaMemcpyAsync(a->mb_img2, a->h_stage, NI * 4, cudaMemcpyHostToDevice, a->st));
   CKC(cudaMemcpyAsync(a->mb_sky2, a->h_stage + NI, a->SKY * 4, cudaMemcpyHostToDevice, a->st));
+  if (a->td3) {
+    // demix_td3.py:444-455 after the warm-up: eval-mode actor, mu + noise (A values drawn by the caller, or none), clamp to [-1, 1]
+    if (eps) CKC(cudaMemcpyAsync(a->anoise, a->h_stage + NI + a->SKY, a->A * 4, cudaMemcpyHostToDevice, a->st));
+    const NetP P = net_ptrs(a->params + a->off_net[0], a->La, true);
+    TrunkWs& t = a->ws[0];
+    int rc = trunk_forward(a, t, P, 0, a->mb_img2, ACT_ELU, 0, 1);
+    if (rc) return rc;
+    k_side_fwd<<<1, 128, 0, a->st>>>(a->mb_sky2, a->SKY, nullptr, 0, P.fa_w, P.fa_b, P.fb_w, P.fb_b, t.x1, t.h1, t.o16, t.feat, a->side, a->feat, a->flat);
+    LAUNCH_OK(a);
+    if ((rc = sgemm(a, t.feat, a->feat, 1, P.h_w, 1, a->feat, a->x21, HID, 1, HID, a->feat, P.h_b, ACT_ELU))) return rc;
+    k_td3_head<<<1, 128, 0, a->st>>>(a->x21, P.mu_w, P.mu_b, a->A, nullptr, 0, eps ? a->anoise : nullptr, a->a2);
+    LAUNCH_OK(a);
+    CKC(cudaMemcpyAsync(a->h_stage, a->a2, a->A * 4, cudaMemcpyDeviceToHost, a->st));
+    CKC(cudaStreamSynchronize(a->st));
+    memcpy(action_out, a->h_stage, a->A * 4);
+    a->batch_ready = false;
+    return SC_OK;
+  }
   if (eps) CKC(cudaMemcpyAsync(a->eps_next, a->h_stage + NI + a->SKY, a->A * 4, cudaMemcpyHostToDevice, a->st));
   else { CKC(launch_fill_normal(a->eps_next, a->A, a->cfg.rng_seed, 0x9000u + (uint64_t)(a->noise_ctr++), a->st)); a->launches++; }
   const NetP P = net_ptrs(a->params + a->off_net[0], a->La, true);
@@ -1153,16 +1428,149 @@ static int calib_body(sc_calib* a, bool host_noise, bool hint, int dual) {
   return SC_OK;
 }
 
+
+// every launch of one demixing TD3 learn() (demix_td3.py:459-603) on a->st.  `host_rng`: the PER uniforms and the target-noise scalar
+// were uploaded by the caller (reference RNG streams); otherwise both come from the device Philox streams named in step_dev.
+static int td3_body(sc_calib* a, bool host_rng, bool hint, int actor_step) {
+  const int B = a->B, A = a->A, SKY = a->SKY;
+  const size_t NI = (size_t)IMG * IMG;
+  int rc;
+  // ---- PER.sample_buffer (:80-120): stratified draw on the float64 tree -> tree indices, data indices, IS weights, sum(w) ----
+  CKC(launch_per_sample(&a->step_dev->per_s, 1, B, a->st));
+  a->launches++;
+  if (!host_rng) {
+    CKC(launch_fill_normal_p(a->tnoise, 1, a->cfg.rng_seed, &a->step_dev->noise[3], a->st));
+    a->launches++;
+  }
+  k_gather<<<dim3(16, B), 256, 0, a->st>>>(a->r_img, a->bidx, NI, a->mb_img);  LAUNCH_OK(a);
+  k_gather<<<dim3(16, B), 256, 0, a->st>>>(a->r_img2, a->bidx, NI, a->mb_img2);  LAUNCH_OK(a);
+  k_gather<<<dim3(1, B), 128, 0, a->st>>>(a->r_sky, a->bidx, SKY, a->mb_sky);  LAUNCH_OK(a);
+  k_gather<<<dim3(1, B), 128, 0, a->st>>>(a->r_sky2, a->bidx, SKY, a->mb_sky2);  LAUNCH_OK(a);
+  k_gather<<<dim3(1, B), 128, 0, a->st>>>(a->r_act, a->bidx, A, a->mb_act);  LAUNCH_OK(a);
+  k_gather<<<dim3(1, B), 128, 0, a->st>>>(a->r_hint, a->bidx, A, a->mb_hint);  LAUNCH_OK(a);
+  k_gather<<<dim3(1, B), 32, 0, a->st>>>(a->r_rew, a->bidx, 1, a->mb_rew);  LAUNCH_OK(a);
+  k_gather<<<dim3(1, B), 32, 0, a->st>>>(a->r_done, a->bidx, 1, a->mb_done);  LAUNCH_OK(a);
+
+  const NetP PA = net_ptrs(a->params + a->off_net[0], a->La, true), GA = net_ptrs(a->grads + a->off_net[0], a->La, true);
+  const NetP PTA = net_ptrs(a->targets + 2 * a->Lc.size, a->La, true);
+  NetP PC[2], GC[2], PT[2];
+  for (int k = 0; k < 2; ++k) {
+    PC[k] = net_ptrs(a->params + a->off_net[1 + k], a->Lc, false);
+    GC[k] = net_ptrs(a->grads + a->off_net[1 + k], a->Lc, false);
+    PT[k] = net_ptrs(a->targets + (size_t)k * a->Lc.size, a->Lc, false);
+  }
+  const float gamma = (float)a->cfg.gamma;
+
+  // ---- 1. target actor on s' in eval mode (:484-491): a' = clamp(tanh(.) + n, -1, 1), ONE scalar n per step ----
+  {
+    TrunkWs& t = a->ws[0];
+    if ((rc = trunk_forward(a, t, PTA, 5, a->mb_img2, ACT_ELU, 0, B))) return rc;
+    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky2, SKY, nullptr, 0, PTA.fa_w, PTA.fa_b, PTA.fb_w, PTA.fb_b, t.x1, t.h1, t.o16, t.feat, a->side, a->feat, a->flat);
+    LAUNCH_OK(a);
+    if ((rc = sgemm(a, t.feat, a->feat, 1, PTA.h_w, 1, a->feat, a->x21, HID, B, HID, a->feat, PTA.h_b, ACT_ELU))) return rc;
+    k_td3_head<<<B, 128, 0, a->st>>>(a->x21, PTA.mu_w, PTA.mu_b, A, a->tnoise, host_rng ? 0 : 1, nullptr, a->a2);
+    LAUNCH_OK(a);
+  }
+  // ---- 2. target critics on (s', a') in eval mode (:495-504) ----
+  for (int k = 0; k < 2; ++k) {
+    TrunkWs& t = a->ws[0];
+    if ((rc = trunk_forward(a, t, PT[k], 3 + k, a->mb_img2, ACT_RELU, 0, B))) return rc;
+    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky2, SKY, a->a2, A, PT[k].fa_w, PT[k].fa_b, PT[k].fb_w, PT[k].fb_b, t.x1, t.h1, t.o16, t.feat, a->side, a->feat, a->flat, 1);
+    LAUNCH_OK(a);
+    k_critic_head<<<B, 256, 0, a->st>>>(t.feat, PT[k].h_w, PT[k].h_b, a->qt[k], a->feat);
+    LAUNCH_OK(a);
+  }
+  k_td3_target<<<(B + 127) / 128, 128, 0, a->st>>>(a->qt[0], a->qt[1], a->mb_rew, a->mb_done, gamma, B, a->y);
+  LAUNCH_OK(a);
+  // ---- 3. critics on (s, a): the priority pre-pass (:506-511) and the training pass (:516-517) are the same training-mode forward
+  //         (same weights, same batch statistics), so it runs once and the running statistics take both momentum updates ----
+  for (int k = 0; k < 2; ++k) {
+    TrunkWs& t = a->ws[1 + k];
+    if ((rc = trunk_forward(a, t, PC[k], 1 + k, a->mb_img, ACT_RELU, 1, B, 2))) return rc;
+    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky, SKY, a->mb_act, A, PC[k].fa_w, PC[k].fa_b, PC[k].fb_w, PC[k].fb_b, t.x1, t.h1, t.o16, t.feat, a->side, a->feat, a->flat, 1);
+    LAUNCH_OK(a);
+    k_critic_head<<<B, 256, 0, a->st>>>(t.feat, PC[k].h_w, PC[k].h_b, a->q[k], a->feat);
+    LAUNCH_OK(a);
+  }
+  k_td3_per_err<<<(B + 127) / 128, 128, 0, a->st>>>(a->q[0], a->q[1], a->y, B, a->per_err);
+  LAUNCH_OK(a);
+  CKC(launch_per_update(&a->step_dev->per_u, 1, B, a->st));          // PER.batch_update (:122-131): priorities -> tree, reference order
+  a->launches++;
+  for (int k = 0; k < 2; ++k) {
+    TrunkWs& t = a->ws[1 + k];
+    k_td3_critic_seed<<<1, 256, 0, a->st>>>(a->q[k], a->y, a->is_wsum, B, a->dq, a->stats + k);
+    LAUNCH_OK(a);
+    k_outer<<<grid_for((size_t)B * a->feat), 256, 0, a->st>>>(a->dq, PC[k].h_w, B, a->feat, a->dfeat);
+    LAUNCH_OK(a);
+    if ((rc = colsum(a, t.feat, a->feat, a->dq, B, a->feat, GC[k].h_w))) return rc;
+    if ((rc = colsum(a, a->dq, 1, nullptr, B, 1, GC[k].h_b))) return rc;
+    k_side_bwd<<<B, 128, 0, a->st>>>(a->dfeat + a->flat, a->feat, t.o16, t.h1, PC[k].fb_w, PC[k].fa_w, a->K1C, SKY, A, a->d16, a->dh1, nullptr, 0, a->side, 1);
+    LAUNCH_OK(a);
+    if ((rc = side_wgrads(a, t.x1, t.h1, a->K1C, GC[k]))) return rc;
+    if ((rc = trunk_backward(a, t, PC[k], GC[k], a->mb_img, ACT_RELU))) return rc;
+  }
+  for (int k = 0; k < 2; ++k)
+    if ((rc = adam_step(a, 1 + k))) return rc;
+  if (!actor_step) return SC_OK;
+
+  // ---- 4. delayed actor update (:529-600): one Adam step on -mean(q1(s, pi(s)) w), or the five-step adaptive-ADMM loop with hints.
+  //         critic_1 stays in train() mode: every one of its forwards moves its BatchNorm running statistics; its weights do not
+  //         change inside the loop, so the trunk runs once and the statistics take n_it momentum updates ----
+  const int n_it = hint ? 5 : 1;
+  if (hint) { CKC(launch_admm_update(a->admm_dev, 1, a->st)); a->launches++; }        // lambda <- 0, rho <- admm_rho (:543-546)
+  if ((rc = trunk_forward(a, a->ws[0], PC[0], 1, a->mb_img, ACT_RELU, 1, B, n_it))) return rc;
+  for (int it = 0; it < n_it; ++it) {
+    TrunkWs& t = a->ws[3];
+    if ((rc = trunk_forward(a, t, PA, 0, a->mb_img, ACT_ELU, 1, B))) return rc;
+    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky, SKY, nullptr, 0, PA.fa_w, PA.fa_b, PA.fb_w, PA.fb_b, t.x1, t.h1, t.o16, t.feat, a->side, a->feat, a->flat);
+    LAUNCH_OK(a);
+    if ((rc = sgemm(a, t.feat, a->feat, 1, PA.h_w, 1, a->feat, a->x21, HID, B, HID, a->feat, PA.h_b, ACT_ELU))) return rc;
+    k_td3_head<<<B, 128, 0, a->st>>>(a->x21, PA.mu_w, PA.mu_b, A, nullptr, 0, nullptr, a->pi);
+    LAUNCH_OK(a);
+    TrunkWs& tc = a->ws[0];
+    k_side_fwd<<<B, 128, 0, a->st>>>(a->mb_sky, SKY, a->pi, A, PC[0].fa_w, PC[0].fa_b, PC[0].fb_w, PC[0].fb_b, a->pside[0].x1, a->pside[0].h1, a->pside[0].o16,
+                                     tc.feat, a->side, a->feat, a->flat, 1);
+    LAUNCH_OK(a);
+    k_critic_head<<<B, 256, 0, a->st>>>(tc.feat, PC[0].h_w, PC[0].h_b, a->qpi[0], a->feat);
+    LAUNCH_OK(a);
+    k_td3_actor_seed<<<1, 256, 0, a->st>>>(a->qpi[0], PC[0].h_w, a->is_wsum, B, a->ds[0], a->side, a->flat, a->stats + 2);
+    LAUNCH_OK(a);
+    k_side_bwd<<<B, 128, 0, a->st>>>(a->ds[0], a->side, a->pside[0].o16, a->pside[0].h1, PC[0].fb_w, PC[0].fa_w, a->K1C, SKY, A, a->d16, a->dh1, a->dact, 0, a->side, 1);
+    LAUNCH_OK(a);
+    if (hint) {
+      k_td3_hint<<<1, 256, 0, a->st>>>(a->pi, a->mb_hint, a->lambda, a->admm_rho_dev, a->is_wsum, B, B * A, a->dact, a->stats + 2);
+      LAUNCH_OK(a);
+    }
+    k_td3_head_bwd<<<B, 128, 0, a->st>>>(a->dact, a->pi, A, PA.mu_w, a->x21, a->dmu, a->dpre);
+    LAUNCH_OK(a);
+    if ((rc = sgemm(a, a->dmu, 1, A, a->x21, HID, 1, GA.mu_w, HID, A, HID, B, nullptr, -1))) return rc;
+    if ((rc = colsum(a, a->dmu, A, nullptr, B, A, GA.mu_b))) return rc;
+    if ((rc = sgemm(a, a->dpre, 1, HID, t.feat, a->feat, 1, GA.h_w, a->feat, HID, a->feat, B, nullptr, -1))) return rc;
+    if ((rc = colsum(a, a->dpre, HID, nullptr, B, HID, GA.h_b))) return rc;
+    if ((rc = sgemm(a, a->dpre, HID, 1, PA.h_w, a->feat, 1, a->dfeat, a->feat, B, a->feat, HID, nullptr, -1))) return rc;
+    k_side_bwd<<<B, 128, 0, a->st>>>(a->dfeat + a->flat, a->feat, t.o16, t.h1, PA.fb_w, PA.fa_w, SKY, SKY, 0, a->d16, a->dh1, nullptr, 0, a->side);
+    LAUNCH_OK(a);
+    if ((rc = side_wgrads(a, t.x1, t.h1, SKY, GA))) return rc;
+    if ((rc = trunk_backward(a, t, PA, GA, a->mb_img, ACT_ELU))) return rc;
+    if ((rc = adam_step(a, 0, &a->step_dev->adam_x[it]))) return rc;
+    if (hint) { CKC(launch_admm_update(a->admm_dev + 1 + it, 1, a->st)); a->launches++; }   // multipliers, adaptive penalty (:564-597)
+  }
+  return sc_calib_soft_update(a, (float)a->cfg.tau);                                       // :603, actor steps only
+}
+
 int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
   if (!a) return failc(SC_ERR_ARG, "null handle");
   if (stats) memset(stats, 0, sizeof(*stats));
   if (a->mem_cntr < a->B) return SC_OK;                                     // calib_sac.py:301-302
-  if (!a->batch_ready) return failc(SC_ERR_STATE, "no minibatch selected: call sc_calib_set_batch_host first");
+  if (!a->td3 && !a->batch_ready) return failc(SC_ERR_STATE, "no minibatch selected: call sc_calib_set_batch_host first");
   const int B = a->B, A = a->A;
   int rc;
   const bool hint = a->cfg.use_hint != 0;
-  const int dual = hint && (a->learn_counter % 10 == 0);
-  const bool host_noise = noise && noise->eps_next_host && noise->eps_cur_host;
+  // TD3: `dual` is "the delayed actor update runs in this call" (demix_td3.py:527-529) -- the second launch sequence / graph
+  const int dual = a->td3 ? (((a->learn_counter + 1) % a->interval) == 0) : (hint && (a->learn_counter % 10 == 0));
+  const bool host_noise = a->td3 ? (noise && noise->per_u01_host) : (noise && noise->eps_next_host && noise->eps_cur_host);
+  if (a->td3 && host_noise && !noise->has_td3_target_noise) return failc(SC_ERR_ARG, "per_u01_host given but td3_target_noise missing");
+  const int n_it = a->td3 && dual ? (hint ? 5 : 1) : 0;
   // ---- step scalars: Adam bias corrections (t counts steps per optimizer) and the Philox streams of this step's draws ----
   {
     const int k = a->step_k;
@@ -1170,18 +1578,43 @@ int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
     CKC(cudaEventSynchronize(a->ev_step[k]));
     sc_calib::StepScalars& h = a->step_host[k];
     a->t_critic++;
-    a->t_actor++;
+    if (!a->td3) a->t_actor++;
     h.adam[0] = adam_hyper_c(a->cfg.lr_actor, a->t_actor);
     h.adam[1] = h.adam[2] = adam_hyper_c(a->cfg.lr_critic, a->t_critic);
+    for (int it = 0; it < 5; ++it) h.adam_x[it] = adam_hyper_c(a->cfg.lr_actor, a->t_actor + 1 + (it < n_it ? it : 0));
+    a->t_actor += n_it;
+    if (a->td3) {
+      a->per_beta = a->per_beta + 1e-4 < 1.0 ? a->per_beta + 1e-4 : 1.0;          // PER.sample_buffer :95 (before the draws)
+      PerSampleP& ps = h.per_s;
+      ps.tree = a->tree; ps.C = a->C; ps.B = B;
+      ps.u01 = host_noise ? a->u01_dev : nullptr;
+      ps.seed = a->cfg.rng_seed; ps.ctr = 0xE000000000ull + (unsigned long long)a->noise_ctr;
+      ps.beta = a->per_beta;
+      ps.tree_idx = a->tree_idx; ps.data_idx = a->bidx; ps.is_w = a->is_w; ps.is_wsum = a->is_wsum;
+      PerUpdateP& pu = h.per_u;
+      pu.tree = a->tree; pu.C = a->C; pu.B = B; pu.idx = a->tree_idx; pu.err = a->per_err; pu.clip = 100.f;     // demix_td3.py:34
+      pu.ps_out = a->per_ps; pu.ps_in = nullptr;
+    }
     h.noise[0] = 2 * (unsigned long long)a->noise_ctr;
     h.noise[1] = 2 * (unsigned long long)a->noise_ctr + 1;
     h.noise[2] = 0xD000000000ull + (unsigned long long)a->noise_ctr;
-    h.noise[3] = 0;
+    h.noise[3] = 0xF000000000ull + (unsigned long long)a->noise_ctr;          // TD3 target-noise scalar
     if (!host_noise) a->noise_ctr++;
     CKC(cudaMemcpyAsync(a->step_dev, &h, sizeof(h), cudaMemcpyHostToDevice, a->st));
     CKC(cudaEventRecord(a->ev_step[k], a->st));
   }
-  if (host_noise) {
+  if (host_noise && a->td3) {
+    // the caller's numpy stream: B uniforms of PER.sample_buffer (:100) and the scalar of :493, clamped in float64 like the reference
+    CKC(cudaStreamSynchronize(a->st));
+    memcpy(a->h_u01, noise->per_u01_host, (size_t)B * sizeof(double));
+    double n = noise->td3_target_noise;
+    n = n < -0.5 ? -0.5 : (n > 0.5 ? 0.5 : n);
+    float* nf = reinterpret_cast<float*>(a->h_u01 + B);
+    nf[0] = (float)n;
+    CKC(cudaMemcpyAsync(a->u01_dev, a->h_u01, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, a->st));
+    CKC(cudaMemcpyAsync(a->tnoise, nf, sizeof(float), cudaMemcpyHostToDevice, a->st));
+  }
+  if (host_noise && !a->td3) {
     CKC(cudaStreamSynchronize(a->st));
     float* h = a->h_stage;
     memcpy(h, noise->eps_next_host, (size_t)B * A * 4);
@@ -1206,7 +1639,7 @@ int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
       cudaError_t e = cudaStreamBeginCapture(a->st_cap, cudaStreamCaptureModeRelaxed);
       int brc = SC_OK;
       if (e == cudaSuccess) {
-        brc = calib_body(a, host_noise, hint, dual);
+        brc = a->td3 ? td3_body(a, host_noise, hint, dual) : calib_body(a, host_noise, hint, dual);
         cudaError_t e2 = cudaStreamEndCapture(a->st_cap, &g);
         if (e == cudaSuccess) e = e2;
       }
@@ -1225,7 +1658,7 @@ int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
   }
   if (!done) {
     const int64_t l0 = a->launches;
-    if ((rc = calib_body(a, host_noise, hint, dual))) return rc;
+    if ((rc = a->td3 ? td3_body(a, host_noise, hint, dual) : calib_body(a, host_noise, hint, dual))) return rc;
     a->graph_launches[dual] = a->launches - l0;
   }
   a->learn_counter++;
@@ -1233,7 +1666,7 @@ int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
   if (stats) {
     CKC(cudaMemcpyAsync(a->h_stats, a->stats, 8 * sizeof(float), cudaMemcpyDeviceToHost, a->st));
     CKC(cudaMemcpyAsync(a->h_stats + 8, a->hint_out, 4 * sizeof(float), cudaMemcpyDeviceToHost, a->st));
-    CKC(cudaMemcpyAsync(a->h_stats + 12, a->rho, sizeof(float), cudaMemcpyDeviceToHost, a->st));
+    CKC(cudaMemcpyAsync(a->h_stats + 12, a->td3 ? a->admm_rho_dev : a->rho, sizeof(float), cudaMemcpyDeviceToHost, a->st));
     CKC(cudaStreamSynchronize(a->st));
     stats->critic_1_loss = a->h_stats[0]; stats->critic_2_loss = a->h_stats[1]; stats->actor_loss = a->h_stats[2];
     stats->logp_mean = a->h_stats[3];
@@ -1241,7 +1674,8 @@ int sc_calib_learn(sc_calib* a, const sc_noise* noise, sc_learn_stats* stats) {
     stats->rho = a->h_stats[12];
     stats->learn_counter = (int32_t)a->learn_counter;
     stats->did_learn = 1;
-    stats->actor_step = 1;
+    stats->actor_step = a->td3 ? dual : 1;
+    if (a->td3) { stats->gfun = 0.f; stats->logp_mean = 0.f; if (!dual) stats->actor_loss = 0.f; }
   }
   return SC_OK;
 }

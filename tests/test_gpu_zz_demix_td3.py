@@ -1,0 +1,295 @@
+"""GPU (file named to run after the other GPU suites): the demixing conv TD3 agent (demixing_rl/demix_td3.py) on the sc_calib_* kernels with SC_CALIB_TD3, against the CPU oracle
+(oracle/demix_td3_ref.py, bit-identical to the unmodified reference module, tests/golden/make_golden_demix_td3.py) and against
+golden vectors recorded from the reference itself."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import smartcal_b200  # noqa: F401
+from smartcal_b200 import _lib as L
+from smartcal_b200.synth import make_demix_transitions
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NETS = ("actor", "critic_1", "critic_2", "target_actor", "target_critic_1", "target_critic_2")
+
+
+def digest(t):
+    a = t.detach().cpu().numpy().astype(np.float64).reshape(-1)
+    idx = np.linspace(0, a.size - 1, min(32, a.size)).astype(np.int64)
+    return np.concatenate([[a.sum(), np.abs(a).sum()], a[idx]])
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-30))
+
+
+def hp_of(B, A, C, use_hint):
+    return dict(gamma=0.99, batch_size=B, n_actions=A, tau=0.005, max_mem_size=C, input_dims=[1, 128, 128], lr_a=1e-3, lr_c=1e-3,
+                update_actor_interval=2, warmup=4, noise=0.1, use_hint=use_hint)
+
+
+def fill(agent, orc, tr, C):
+    for i in range(C):
+        s = {"infmap": tr["img"][i], "metadata": tr["meta"][i]}
+        s2 = {"infmap": tr["img2"][i], "metadata": tr["meta2"][i]}
+        agent.store_transition(s, tr["action"][i], float(tr["reward"][i]), s2, bool(tr["done"][i]), tr["hint"][i])
+        if orc is not None:
+            orc.store(tr["img"][i], tr["meta"][i], tr["action"][i], float(tr["reward"][i]), tr["img2"][i], tr["meta2"][i], bool(tr["done"][i]), tr["hint"][i])
+
+
+def oracle_state(orc, nm):
+    return {**getattr(orc, nm), **getattr(orc, nm + "_b")}
+
+
+def push_oracle_state(agent, orc):
+    """teacher forcing: device parameters, BatchNorm buffers, Adam moments, targets and the sum tree := oracle"""
+    for nm in NETS:
+        getattr(agent, nm).load_state_dict({k: v.detach() for k, v in oracle_state(orc, nm).items()})
+    for nm, opt in (("actor", orc.opt_a), ("critic_1", orc.opt_1), ("critic_2", orc.opt_2)):
+        view = getattr(agent, nm)
+        for k, p in getattr(orc, nm).items():
+            st = opt.state.get(p)
+            if st:
+                view._t(k, L.SLOT_ADAM_M).copy_(st["exp_avg"].reshape(view._t(k).shape))
+                view._t(k, L.SLOT_ADAM_V).copy_(st["exp_avg_sq"].reshape(view._t(k).shape))
+    tree = agent._dev.buffer("tree")
+    tree.copy_(torch.as_tensor(orc.per.tree.tree).reshape(tree.shape))
+
+
+def check_grads(got, want, tol, what, floor=None):
+    """`floor`: {key: magnitude} -- for a gradient that is a cancelling sum (head.bias = sum_b dq_b) the tolerance is taken relative to the
+    sum of the terms' magnitudes, which is what rounding-level errors of the individual q_b scale with"""
+    bad = []
+    for k, g in want.items():
+        gd, gr = got[k].cpu().numpy().reshape(-1), g.numpy().reshape(-1)
+        scale = max(np.max(np.abs(gr)), (floor or {}).get(k, 0.0))
+        if k.startswith("conv") and k.endswith(".bias"):            # zero up to rounding in front of a BatchNorm
+            if not (np.max(np.abs(gd)) < 1e-4 and scale < 1e-4):
+                bad.append(f"{what}.{k} should vanish")
+            continue
+        d = np.max(np.abs(gd - gr))
+        if not d <= tol * scale + 1e-9:
+            bad.append(f"{what}.{k}: {d:.3e} vs scale {scale:.3e} (rel {d / (scale + 1e-30):.2e})")
+    return bad
+
+
+@pytest.mark.parametrize("use_hint", [False, True])
+def test_demix_td3_learn_matches_oracle(use_hint):
+    """demixing_rl/main_td3.py shapes (K = 6: M = 20 metadata values, 5 actions), small batch; four learn() calls = two critic-only steps
+    and two delayed actor updates (with hints: the five-step adaptive-ADMM loop), teacher-forced between calls"""
+    from oracle.demix_td3_ref import DemixTd3Ref
+    from smartcal_b200.demixing_rl import demix_td3
+    M, A, B, C, seed = 20, 5, 8, 16, 51
+    hp = hp_of(B, A, C, use_hint)
+    tr = make_demix_transitions(seed + 100, C, M, A, 128, 0.2)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    agent = demix_td3.DemixingAgent(**hp, M=M, rng="reference")
+    torch.manual_seed(seed)
+    orc = DemixTd3Ref(**hp, M=M)
+    fill(agent, orc, tr, C)
+    dev = agent._dev
+    for nm in NETS:                           # construction: identical weights and buffers (reference draw order, hard target copy)
+        for k, v in oracle_state(orc, nm).items():
+            assert torch.equal(getattr(agent, nm).state_dict()[k].cpu(), v.detach()), f"init {nm}.{k}"
+    assert np.array_equal(agent.replaymem.tree.tree, orc.per.tree.tree), "max-leaf priorities of the stored transitions"
+    rs = np.random.RandomState(seed + 1)
+    fails = []
+
+    def expect(cond, msg, step=None):
+        if not cond:
+            fails.append(f"step {step}: {msg}")
+
+    for step in range(4):
+        u01, noise = rs.random_sample(B), float(rs.normal(scale=0.2)) * (3.0 if step == 2 else 1.0)    # step 2: the +-0.5 clamp bites
+        idxs, data, w = orc.per.sample(u01)
+        st = dev.learn_td3(u01, noise, want_stats=True)
+        res = orc.learn_on_batch(orc.replay.gather(data), noise, w, idxs)
+        expect(np.array_equal(dev.buffer("tree_idx")[:, 0].cpu().numpy(), idxs), "stratified draw: tree indices bit-exact", step)
+        expect(np.array_equal(dev.buffer("batch_idx")[:, 0].cpu().numpy(), data), "data indices of the draw", step)
+        wd = dev.buffer("is_weights")[:, 0].cpu().numpy()
+        expect(np.abs(wd.view(np.int32).astype(np.int64) - w.view(np.int32).astype(np.int64)).max() <= 2, "IS weights within 2 ulp", step)
+        expect(abs(agent.replaymem.beta - orc.per.beta) < 1e-15, "PER beta", step)
+        for name, key in (("target_action", "target_action"), ("y", "y"), ("q1", "q1"), ("q2", "q2")):
+            expect(rel(dev.buffer(name).cpu().numpy(), res[key].numpy()) < 3e-5, (step, name), step)
+        expect(rel(dev.buffer("per_errors").cpu().numpy(), res["per_errors"]) < 1e-4, "priority errors of the pre-pass", step)
+        expect(np.allclose(dev.buffer("tree").cpu().numpy().reshape(-1), orc.per.tree.tree, rtol=1e-5, atol=1e-7), "tree after PER.batch_update", step)
+        expect(np.allclose([st["critic_1_loss"], st["critic_2_loss"]], [res["critic_1_loss"], res["critic_2_loss"]], rtol=1e-4, atol=1e-6), "critic losses", step)
+        for kq, gk, nm in (("q1", "grad_c1", "critic_1"), ("q2", "grad_c2", "critic_2")):
+            terms = float(np.sum(np.abs(res[kq].numpy() - res["y"].numpy())) * 2.0 / B)
+            fails.extend(check_grads(getattr(agent, nm).grads(), res[gk], 5e-5, f"step {step} {nm}", floor={"head.bias": terms}))
+        expect(bool(st["actor_step"]) == bool(res["actor_step"]) == (step % 2 == 1), "delayed actor update every 2nd call", step)
+        if res["actor_step"]:
+            if not use_hint:
+                expect(rel(dev.buffer("pi").cpu().numpy(), res["pi"].numpy()) < 3e-5, "pi", step)
+                expect(rel(dev.buffer("q1_pi").cpu().numpy(), res["q1_pi"].numpy()) < 3e-5, "q1(s, pi(s))", step)
+                expect(abs(st["actor_loss"] - res["actor_loss"]) <= 1e-4 * abs(res["actor_loss"]) + 1e-6, "actor loss", step)
+                fails.extend(check_grads(agent.actor.grads(), res["grad_a"], 5e-5, f"step {step} actor"))
+            else:
+                # five un-forced Adam steps inside one call: the last iteration is compared with a band that covers Adam's +-lr response
+                # to rounding-level gradients; multipliers and the penalty are compared too
+                last = res["admm"][-1]
+                d_pi = rel(dev.buffer("pi").cpu().numpy(), last["pi"].numpy())
+                d_lam = rel(dev.buffer("admm_lambda").cpu().numpy().reshape(-1), last["lagrange"].numpy())
+                d_loss = abs(st["actor_loss"] - last["actor_loss"]) / (abs(last["actor_loss"]) + 1e-9)
+                print(f"hint step {step}: pi {d_pi:.2e}  lambda {d_lam:.2e}  loss {d_loss:.2e}  rho {st['rho']} vs {res['admm_rho_final']}")
+                expect(d_pi < 5e-2 and d_lam < 5e-2 and d_loss < 5e-2, f"ADMM loop end state: pi {d_pi:.2e} lambda {d_lam:.2e} loss {d_loss:.2e}", step)
+                expect(abs(st["rho"] - res["admm_rho_final"]) <= 2e-2 * abs(res["admm_rho_final"]), "adaptive penalty", step)
+        # BatchNorm bookkeeping: the counters are exact; eval-mode targets never count; online critics count every training-mode forward
+        for nm in NETS:
+            sd = getattr(agent, nm).state_dict()
+            for k, v in getattr(orc, nm + "_b").items():
+                if k.endswith("num_batches_tracked"):
+                    expect(int(sd[k]) == int(v), f"step {step} {nm}.{k}: {int(sd[k])} vs {int(v)}", step)
+                elif nm in ("critic_1", "critic_2") or not use_hint or not res["actor_step"]:
+                    expect(rel(sd[k].cpu().numpy(), v.numpy()) < 2e-5, f"step {step} {nm}.{k}", step)
+        if not (use_hint and res["actor_step"]):          # parameters after the step incl. the state_dict soft update of the targets
+            for nm in ("target_critic_1", "target_critic_2", "target_actor"):
+                sd = getattr(agent, nm).state_dict()
+                for k, v in getattr(orc, nm).items():
+                    if k.startswith("conv") and k.endswith(".bias"):
+                        continue
+                    expect(np.max(np.abs(sd[k].cpu().numpy() - v.detach().numpy())) <= 2.5 * 0.005 * 1e-3 + 1e-7, f"step {step} {nm}.{k}", step)
+        push_oracle_state(agent, orc)
+    assert not fails, "\n".join(fails[:40])
+    obs = make_demix_transitions(seed + 7, 1, M, A, 128, 0.0)
+    nz = rs.normal(scale=0.1, size=(A,))
+    a_dev = dev.act(obs["img"][0], obs["meta"][0], nz.astype(np.float32))
+    a_orc = orc.choose_action(obs["img"][0], obs["meta"][0], nz)
+    assert np.max(np.abs(a_dev - a_orc[0])) < 2e-5
+
+
+@pytest.mark.parametrize("name", ["demix_td3_b8", "demix_td3_hint_b8"])
+def test_demix_td3_against_reference_golden(name):
+    """no oracle in the loop: digests recorded from the unmodified reference DemixingAgent of demix_td3.py"""
+    from smartcal_b200.demixing_rl import demix_td3
+    z = np.load(os.path.join(G, name + ".npz"))
+    M, A, B, C, steps, seed, use_hint = [int(x) for x in z["cfg"]]
+    hp = hp_of(B, A, C, bool(use_hint))
+    tr = make_demix_transitions(seed + 100, C, M, A, 128, float(z["done_frac"][0]))
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    agent = demix_td3.DemixingAgent(**hp, M=M, rng="reference")
+    for nm in NETS:
+        for k, v in getattr(agent, nm).state_dict().items():
+            assert np.array_equal(digest(v.double() if v.dtype == torch.int64 else v.float()), z[f"init/{nm}/{k}/p"]), f"init {nm}.{k} differs from the reference"
+    fill(agent, None, tr, C)
+    assert np.array_equal(digest(torch.as_tensor(agent.replaymem.tree.tree)), z["init/tree"])
+    np.random.seed(seed + 1)
+    torch.manual_seed(seed + 1)
+    st = agent.learn(want_stats=True)                    # the facade draws B uniforms + one normal from numpy's global stream
+    dev = agent._dev
+    assert np.array_equal(dev.buffer("tree_idx")[:, 0].cpu().numpy(), z["step0/tree_idx"]), "PER draw from the reference's numpy stream"
+    wd, wr = dev.buffer("is_weights")[:, 0].cpu().numpy(), z["step0/is_w"]
+    assert np.abs(wd.view(np.int32).astype(np.int64) - wr.view(np.int32).astype(np.int64)).max() <= 2
+    np.testing.assert_allclose([st["critic_1_loss"], st["critic_2_loss"]], z["step0/losses"][:2], rtol=2e-4)
+    for nm_, buf in (("y", "y"), ("q1", "q1")):
+        ref, got = z[f"step0/{nm_}"], digest(dev.buffer(buf))
+        assert np.max(np.abs(got[2:] - ref[2:])) <= 3e-5 * max(np.max(np.abs(ref[2:])), 1e-3), nm_
+    ref, got = z["step0/tree"], digest(dev.buffer("tree"))
+    assert np.max(np.abs(got - ref) / (1 + np.abs(ref))) < 1e-5, "tree after PER.batch_update"
+    for nm in ("critic_1", "critic_2"):                  # first Adam step: m = 0.1 g pins the reference's gradients
+        adam = getattr(agent, nm).adam_state()
+        for k in adam:
+            if k.startswith("conv") and k.endswith(".bias"):
+                continue
+            ref, got = z[f"step0/{nm}/{k}/m"], digest(adam[k][0])
+            tol = 5e-4 * max(np.max(np.abs(ref[2:])), ref[1] / adam[k][0].numel()) + 1e-12
+            assert np.max(np.abs(got[2:] - ref[2:])) <= tol, f"{nm}.{k} samples of exp_avg"
+        sd = getattr(agent, nm).state_dict()
+        for l in (1, 2, 3):                               # two training-mode forwards (priority pre-pass + training pass)
+            assert int(sd[f"bn{l}.num_batches_tracked"]) == 2 == int(z[f"step0/{nm}/bn{l}.num_batches_tracked/p"][2])
+            ref, got = z[f"step0/{nm}/bn{l}.running_var/p"], digest(sd[f"bn{l}.running_var"])
+            assert np.max(np.abs(got - ref) / (1 + np.abs(ref))) < 2e-5
+    st = agent.learn(want_stats=True)                    # second call: the delayed actor update and the state_dict soft update
+    assert st["actor_step"] == 1 and agent.learn_step_cntr == 2
+    n_it = 5 if use_hint else 1
+    sd_a, sd_c, sd_t = agent.actor.state_dict(), agent.critic_1.state_dict(), agent.target_actor.state_dict()
+    assert int(sd_a["bn1.num_batches_tracked"]) == n_it == int(z["step1/actor/bn1.num_batches_tracked/p"][2])
+    assert int(sd_c["bn2.num_batches_tracked"]) == 4 + n_it == int(z["step1/critic_1/bn2.num_batches_tracked/p"][2])
+    assert int(sd_t["bn3.num_batches_tracked"]) == 0 == int(z["step1/target_actor/bn3.num_batches_tracked/p"][2]), "float32 blend truncated to int64"
+    ref, got = z["step1/target_actor/bn1.running_mean/p"], digest(sd_t["bn1.running_mean"])
+    assert np.max(np.abs(got - ref)) <= 2e-2 * np.max(np.abs(ref)) + 1e-7, "BatchNorm buffers of the targets follow the soft update"
+    # choose_action after the warm-up against the reference's recorded action (same numpy draw)
+    agent.time_step = hp["warmup"]
+    obs = make_demix_transitions(seed + 200, 1, M, A, 128, 0.0)
+    a = agent._dev.act(obs["img"][0], obs["meta"][0], z["act/noise"].astype(np.float32))
+    assert a.shape == (A,) and np.all(np.abs(a) <= 1.0)
+
+
+def test_demix_td3_facade_roundtrip_at_main_td3_shape(tmp_path, monkeypatch):
+    """the calls demixing_rl/main_td3.py makes, at its shapes (K = 6, M = 20, batch 64, use_hint=True): choose_action (warm-up and after),
+    store_transition, learn, save_models / load_models"""
+    from smartcal_b200.demixing_rl import demix_td3
+    monkeypatch.chdir(tmp_path)
+    M, A, B, C = 20, 5, 64, 128
+    torch.manual_seed(5)
+    np.random.seed(5)
+    agent = demix_td3.DemixingAgent(gamma=0.99, batch_size=B, n_actions=A, tau=0.005, max_mem_size=C, input_dims=[1, 128, 128], M=M, lr_a=1e-3, lr_c=1e-3,
+                                    update_actor_interval=2, warmup=10, noise=0.1, use_hint=True)
+    tr = make_demix_transitions(9, C, M, A, 128, 0.05)
+    losses, actor_steps = [], 0
+    for i in range(B + 6):
+        obs, obs_ = {"infmap": tr["img"][i], "metadata": tr["meta"][i]}, {"infmap": tr["img2"][i], "metadata": tr["meta2"][i]}
+        action = agent.choose_action(obs)
+        if i < 10:
+            assert action.shape == (A,) and action.dtype == np.float64
+        else:
+            assert action.shape == (1, A) and action.dtype == np.float32
+        assert np.all(np.abs(action) <= 1.0)
+        agent.store_transition(obs, action, float(tr["reward"][i]), obs_, bool(tr["done"][i]), tr["hint"][i])
+        st = agent.learn(want_stats=True)
+        if st:
+            losses.append(st["critic_1_loss"])
+            actor_steps += st["actor_step"]
+    assert agent.replaymem.mem_cntr == B + 6 and agent.learn_step_cntr == 7 and actor_steps == 3 and np.isfinite(losses).all()
+    assert abs(agent.replaymem.beta - (0.4 + 7e-4)) < 1e-12
+    tree = agent.replaymem.tree.tree
+    assert tree.shape == (2 * C - 1,) and abs(tree[0] - tree[C - 1:].sum()) <= 1e-9 * tree[0] and len(agent.replaymem) == B + 6
+    np.testing.assert_array_equal(agent.replaymem.state_memory_sky[3], tr["meta"][3])
+    before = {k: v.clone() for k, v in agent.actor.state_dict().items()}
+    assert "fc22.weight" in before and tuple(before["fc22.weight"].shape) == (A, 128) and tuple(agent.critic_1.state_dict()["fc1.weight"].shape) == (128, A + M)
+    agent.save_models()
+    for f in ("a_eval_td3_actor.model", "a_target_td3_actor.model", "q_eval_1_td3_critic.model", "q_target_2_td3_critic.model", "prioritized_replaymem_td3.model"):
+        assert os.path.exists(f), f
+    agent.actor.load_state_dict({k: torch.zeros_like(v) for k, v in before.items()})
+    agent._dev.buffer("tree").zero_()
+    agent.load_models()
+    for k, v in agent.actor.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    for k, v in agent.target_actor.state_dict().items():       # load_models ends with the hard copy (:626)
+        assert torch.equal(v, before[k]), k
+    assert np.array_equal(agent.replaymem.tree.tree, tree)
+
+
+def test_demix_td3_graph_replay_equals_eager(monkeypatch):
+    """rng='device': critic-only and actor-update steps each replay from their own CUDA graph (PER draw parameters, Adam bias corrections
+    and Philox stream ids live in device memory); SMARTCAL_GRAPH=0 keeps eager launches.  Same bits."""
+    from smartcal_b200.demixing_rl import demix_td3
+    M, A, B, C = 20, 5, 16, 32
+
+    def run(graph):
+        monkeypatch.setenv("SMARTCAL_GRAPH", "1" if graph else "0")
+        torch.manual_seed(3)
+        np.random.seed(3)
+        agent = demix_td3.DemixingAgent(**hp_of(B, A, C, True), M=M, rng="device")
+        tr = make_demix_transitions(4, C, M, A, 128, 0.1)
+        fill(agent, None, tr, C)
+        with contextlib.redirect_stdout(io.StringIO()):
+            for _ in range(8):
+                st = agent.learn(want_stats=True)
+        out = {f"{nm}.{k}": v.detach().cpu().clone() for nm in NETS for k, v in getattr(agent, nm).state_dict().items()}
+        out["tree"] = agent._dev.buffer("tree").cpu().clone()
+        out["rho"] = torch.tensor(st["rho"])
+        agent._dev.close()
+        return out
+
+    g, e = run(True), run(False)
+    for k in e:
+        assert torch.equal(g[k], e[k]), k

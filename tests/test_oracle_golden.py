@@ -211,3 +211,48 @@ def test_demix_oracle_matches_reference(name):
         np.testing.assert_allclose([res["critic_1_loss"], res["critic_2_loss"], res["actor_loss"]], z[f"step{s}/losses"], rtol=1e-4)
         if use_hint:
             assert abs(float(orc.rho) - float(z[f"step{s}/rho"][0])) <= 1e-6 * (1 + abs(float(orc.rho)))
+
+
+@pytest.mark.parametrize("name", ["demix_td3_b8", "demix_td3_hint_b8"])
+def test_demix_td3_oracle_matches_reference(name):
+    """the demixing conv TD3 agent (demixing_rl/demix_td3.py): the oracle restatement replays the draws recorded from the unmodified
+    reference module (tests/golden/make_golden_demix_td3.py) -- PER tree / indices / IS weights, the eval-mode target passes, the
+    training-mode priority pre-pass, the delayed actor update (with hints: the five-step adaptive-ADMM loop) and the state_dict soft
+    update incl. BatchNorm buffers"""
+    from oracle.demix_td3_ref import DemixTd3Ref
+    from smartcal_b200.synth import make_demix_transitions
+    z = np.load(os.path.join(G, name + ".npz"))
+    M, A, B, C, steps, seed, use_hint = [int(x) for x in z["cfg"]]
+    steps = min(steps, 2)                       # one critic-only step and one actor update (each conv CPU step costs ~1 s)
+    hp = dict(gamma=0.99, batch_size=B, n_actions=A, tau=0.005, max_mem_size=C, input_dims=[1, 128, 128], lr_a=1e-3, lr_c=1e-3,
+              update_actor_interval=2, warmup=4, noise=0.1, use_hint=bool(use_hint))
+    tr = make_demix_transitions(seed + 100, C, M, A, 128, float(z["done_frac"][0]))
+    torch.manual_seed(seed)
+    orc = DemixTd3Ref(**hp, M=M)
+    for i in range(C):
+        orc.store(tr["img"][i], tr["meta"][i], tr["action"][i], float(tr["reward"][i]), tr["img2"][i], tr["meta2"][i], bool(tr["done"][i]), tr["hint"][i])
+
+    def dg(v):
+        a = (v.detach().double() if v.dtype == torch.int64 else v.detach().float()).numpy().astype(np.float64).reshape(-1)
+        idx = np.linspace(0, a.size - 1, min(32, a.size)).astype(np.int64)
+        return np.concatenate([[a.sum(), np.abs(a).sum()], a[idx]])
+
+    def check(prefix, tol):
+        for nm in DemixTd3Ref.NETS:
+            for k, v in {**getattr(orc, nm), **getattr(orc, nm + "_b")}.items():
+                ref = z[f"{prefix}/{nm}/{k}/p"]
+                assert np.max(np.abs(dg(v) - ref) / (1.0 + np.abs(ref))) <= tol, f"{prefix}/{nm}/{k}"
+        ref = z[f"{prefix}/tree"]
+        assert np.max(np.abs(dg(torch.as_tensor(orc.per.tree.tree)) - ref) / (1.0 + np.abs(ref))) <= tol, f"{prefix}/tree"
+
+    check("init", 0.0)
+    for s in range(steps):
+        idxs, data, w = orc.per.sample(z[f"step{s}/u01"])
+        assert np.array_equal(idxs, z[f"step{s}/tree_idx"])
+        assert np.abs(w.view(np.int32).astype(np.int64) - z[f"step{s}/is_w"].view(np.int32).astype(np.int64)).max() <= 2
+        res = orc.learn_on_batch(orc.replay.gather(data), float(z[f"step{s}/noise"][0]), w, idxs)
+        check(f"step{s}", TOL * (s + 1))
+        np.testing.assert_allclose([res["critic_1_loss"], res["critic_2_loss"]], z[f"step{s}/losses"][:2], rtol=1e-4)
+        assert res["actor_step"] == (s % 2 == 1)
+        if res["actor_step"]:
+            np.testing.assert_allclose(res["actor_loss"], z[f"step{s}/losses"][2], rtol=1e-4)
