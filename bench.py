@@ -30,6 +30,27 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+T0 = time.time()
+# the headline (value, e2e, roofline, cpu_baseline) always runs; the secondary objects of the line (ensembles, the other BASELINE configs,
+# the torch-eager bar) are skipped -- and say so -- once this much wall time has gone by, so a slow host cannot cost the line itself
+BUDGET_S = float(os.environ.get("SMARTCAL_BENCH_BUDGET_S", "150"))
+
+
+def elapsed():
+    return time.time() - T0
+
+
+def log(msg):
+    sys.stderr.write(f"[bench +{elapsed():6.1f}s] {msg}\n")
+    sys.stderr.flush()
+
+
+def over_budget(what):
+    if elapsed() > BUDGET_S:
+        log(f"{what}: skipped (time budget)")
+        return {"skipped": f"time budget: {elapsed():.0f} s of wall time gone before this object (SMARTCAL_BENCH_BUDGET_S={BUDGET_S:.0f})"}
+    log(what)
+    return None
 
 S, A, B, C = 420, 2, 256, 4096
 HP = dict(gamma=0.99, lr_a=1e-3, lr_c=1e-3, input_dims=[S], batch_size=B, n_actions=A, max_mem_size=C, tau=0.005,
@@ -163,6 +184,7 @@ def other_configs(args, peak):
         return {"value": 1.0 / dt, "unit": "learn steps/s", "cores": min(threads, os.cpu_count() or 1), "kind": "port",
                 "sample": f"{k} learn() steps after 1 warm-up"}
 
+    log("configs.sac_uniform_b256 / choose_action")
     # --- uniform-replay SAC, batch 256 (the reference's own code path) ---
     torch.manual_seed(1)
     np.random.seed(1)
@@ -189,6 +211,7 @@ def other_configs(args, peak):
     out["choose_action_us"] = {"value": (time.perf_counter() - t0) / 200 * 1e6, "unit": "us per call (host obs in, host action out, one sync)",
                                "reference_cpu_us": 1700.0, "reference_source": "SURVEY section 6 probe (8 vCPU)"}
     ag._dev.close()
+    log("configs.td3_b1024_per")
     # --- TD3 batch 1024 prioritized ---
     Bt = 1024
     torch.manual_seed(2)
@@ -211,16 +234,79 @@ def other_configs(args, peak):
     ag._dev.close()
     # --- calibration conv-SAC batch 256 ---
     try:
-        out["calib_b256"] = calib_numbers(min(args.steps, 30), 3)
+        out["calib_b256"] = over_budget("configs.calib_b256") or calib_numbers(min(args.steps, 30), 3)
     except Exception as e:      # (never lose the headline line to a secondary config)
         out["calib_b256"] = {"error": repr(e)}
     # --- the two demixing SAC agents at the shapes of their main_sac.py ---
     for key, family in (("demix_fuzzy_mlp_b256", "demixing_fuzzy"), ("demix_rl_conv_b256", "demixing_rl")):
         try:
-            out[key] = demix_numbers(family, min(args.steps, 100 if family == "demixing_fuzzy" else 30), 5)
+            out[key] = over_budget("configs." + key) or demix_numbers(family, min(args.steps, 100 if family == "demixing_fuzzy" else 30), 5)
         except Exception as e:
             out[key] = {"error": repr(e)}
+    # --- demixing conv TD3 (demix_td3.py) in a child process with a hard limit: the newest program of the library must not be able to
+    #     take the line down ---
+    try:
+        out["demix_td3_conv_b64"] = over_budget("configs.demix_td3_conv_b64") or child_object("demix_td3", min(args.steps, 30), 75)
+    except Exception as e:
+        out["demix_td3_conv_b64"] = {"error": repr(e)}
     return out
+
+
+def child_object(which, steps, limit_s):
+    """`python bench.py --only <which>` in a child process, limited to `limit_s` seconds; returns its JSON object"""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--only", which, "--steps", str(steps)], capture_output=True, text=True,
+                           timeout=limit_s, cwd=ROOT)
+    except subprocess.TimeoutExpired:
+        return {"error": f"child process exceeded {limit_s} s"}
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    if r.returncode != 0 or not lines:
+        return {"error": f"child rc {r.returncode}: {r.stderr[-300:]}"}
+    return json.loads(lines[-1])
+
+
+def demix_td3_numbers(steps, warmup):
+    """demixing_rl/main_td3.py shape (conv TD3: K = 6 -> M 20, 5 actions, batch 64, PER capacity 4096, update_actor_interval 2,
+    use_hint=True: five-step ADMM actor loop every 2nd call): device-timed steps/s (device RNG, CUDA-graph replay) averaged over an
+    even number of calls + the CPU oracle port on a bounded sample"""
+    from smartcal_b200.synth import make_demix_transitions
+    from oracle.demix_td3_ref import DemixTd3Ref
+    from smartcal_b200.demixing_rl import demix_td3
+    M, A_, Bd, Cd, fill = 20, 5, 64, 4096, 256
+    hp = dict(gamma=0.99, batch_size=Bd, n_actions=A_, tau=0.005, max_mem_size=Cd, input_dims=[1, 128, 128], lr_a=1e-3, lr_c=1e-3,
+              update_actor_interval=2, warmup=200, noise=0.1, use_hint=True)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    agent = demix_td3.DemixingAgent(**hp, M=M, rng="device")
+    tr = make_demix_transitions(100, fill, M, A_, 128, 0.0)
+    dev = agent._dev
+    for i in range(fill):                       # through the facade: PER priorities enter the device tree like in the reference loop
+        agent.store_transition({"infmap": tr["img"][i], "metadata": tr["meta"][i]}, tr["action"][i], float(tr["reward"][i]),
+                               {"infmap": tr["img2"][i], "metadata": tr["meta2"][i]}, False, tr["hint"][i])
+    steps = max(2, steps - steps % 2)
+    ms = time_agent(lambda: dev.learn_td3(), steps, warmup)
+    torch.manual_seed(0)
+    orc = DemixTd3Ref(**hp, M=M)
+    for i in range(fill):
+        orc.store(tr["img"][i], tr["meta"][i], tr["action"][i], float(tr["reward"][i]), tr["img2"][i], tr["meta2"][i], False, tr["hint"][i])
+    t = torch.get_num_threads()
+    nt = min(32, os.cpu_count() or 1)
+    torch.set_num_threads(nt)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        orc.learn()
+        orc.learn()
+        t0 = time.perf_counter()
+        orc.learn()
+        orc.learn()
+        dt = (time.perf_counter() - t0) / 2
+    torch.set_num_threads(t)
+    return {"value": 1e3 / ms, "unit": "learn steps/s", "ms_per_step": ms,
+            "workload": "demixing_rl conv TD3 (demix_td3.py): img (64,1,128,128), metadata 20, 5 actions, PER 4096, actor interval 2, use_hint=True "
+                        "(critic-only calls and calls with the five-step ADMM actor loop alternate; mean over both)",
+            "cpu_baseline": {"value": 1.0 / dt, "unit": "learn steps/s", "cores": nt, "kind": "port", "sample": "2 learn() steps (one with the actor loop) after 2 warm-up"},
+            "gpu_launches_total": int(dev.launch_count())}
 
 
 def demix_numbers(family, steps, warmup):
@@ -329,6 +415,7 @@ def run_ours(args):
         sampler.start()
     l0 = dev.launch_count()
     barrier()
+    log("headline: timed steps (L2 flushed)")
     ms_cold = timed_steps(dev, args.steps, flush)
     barrier()
     launches = dev.launch_count() - l0
@@ -363,6 +450,8 @@ def run_ours(args):
     agent2, tr2 = make_agent(200 + rank, "reference")
     obs = [{"eig": torch.from_numpy(tr2["state"][i, :20].copy()), "A": torch.from_numpy(tr2["state"][i, 20:].copy())} for i in range(64)]
     obs2 = [{"eig": torch.from_numpy(tr2["new_state"][i, :20].copy()), "A": torch.from_numpy(tr2["new_state"][i, 20:].copy())} for i in range(64)]
+
+    log("e2e")
 
     def one(i):
         j = i % 64
@@ -467,17 +556,20 @@ def run_ours(args):
                                       "2015 vs 4030 MAC/clk/SM)",
                        "note": "fp32 parity costs 3 TF32 products per MAC ('issued')"},
             "step": {"algorithmic_bytes": STEP_BYTES, "achieved": STEP_BYTES / step_s / 1e9, "frac": STEP_BYTES / step_s / 1e9 / peak}}
-    ens = ensemble_numbers(args, ms_cold / args.steps, peak) if world == 1 else None
+    ens = ensemble_numbers(args, ms_cold / args.steps, peak) if world == 1 and over_budget("ensembles") is None else None
     if ens is not None:
         b = ens["per_E"][str(ens["best_E"])]
         roof["ensemble_step"] = {"E": ens["best_E"], "algorithmic_bytes": ens["best_E"] * STEP_BYTES, "achieved": b["roofline_step"]["achieved"],
                                  "peak": peak, "unit": "GB/s", "frac": b["roofline_step"]["frac"]}
+    log("configs")
     configs = other_configs(args, peak) if world == 1 else None
+    log("cpu_baseline")
     cpu = cpu_baseline(sample_seconds=12.0)
     pvr = os.path.join(ROOT, "profiles", "r2_port_vs_reference.json")
     if os.path.exists(pvr):
         cpu["port_vs_reference"] = json.load(open(pvr))
-    eager = gpu_eager_baseline() if world == 1 else None
+    eager = gpu_eager_baseline() if world == 1 and over_budget("gpu_eager_baseline") is None else None
+    log("done")
     out = {"metric": "SAC learn() steps/sec (batch=256)", "value": world * args.steps / (ms_cold * 1e-3), "unit": "learn steps/s",
            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_cold / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -712,8 +804,11 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="enet", choices=["enet", "calib"],
                     help="enet: the headline elastic-net SAC workload (BASELINE.json configs[1]); calib: configs[2], conv SAC")
+    ap.add_argument("--only", default=None, choices=["demix_td3"], help="print ONE secondary object of the line (used by the parent run)")
     a = ap.parse_args()
-    if a.workload == "calib":
+    if a.only == "demix_td3":
+        print(json.dumps(demix_td3_numbers(a.steps, 6)))
+    elif a.workload == "calib":
         run_calib(a)
     elif a.impl == "reference":
         run_reference(a)
