@@ -150,21 +150,32 @@ class PER(object):
         with open(self.filename, 'wb') as f:
             pickle.dump(snap, f)
 
-    def load_checkpoint(self):
-        with open(self.filename, 'rb') as f:
+    @staticmethod
+    def read_checkpoint(filename):
+        """host side of load_checkpoint: reads a file written by save_checkpoint above (a dict) OR by the reference's
+        PER.save_checkpoint (:142-145: the pickled PER object, whose `tree` is a demix_sac.SumTree carrying the raw float64 heap;
+        `beta` / `mem_cntr` are instance attributes only once they were written).  Only __dict__ entries are looked at, never the
+        device-backed properties of the classes the pickle resolves to."""
+        with open(filename, 'rb') as f:
             snap = pickle.load(f)
         d = snap if isinstance(snap, dict) else snap.__dict__
-        for n in self._NAMES:
-            src = np.asarray(d[n], dtype=np.float32)
-            dst = self._dev.buffer(n)
-            dst.copy_(T.as_tensor(src.reshape(dst.shape[0], -1)[:, :dst.shape[1]]).to(dst.device))
+        out = {n: np.asarray(d[n], dtype=np.float32) for n in PER._NAMES}
         tree = d["tree"]
-        tree = tree if isinstance(tree, np.ndarray) else tree.__dict__["tree"]           # a reference-written SumTree object
+        tree = tree if isinstance(tree, np.ndarray) else tree.__dict__["tree"]
+        out["tree"] = np.asarray(tree, np.float64).reshape(-1)
+        out["mem_cntr"] = int(d.get("mem_cntr", 0))
+        out["beta"] = float(d.get("beta", 0.4))
+        return out
+
+    def load_checkpoint(self):
+        d = self.read_checkpoint(self.filename)
+        for n in self._NAMES:
+            dst = self._dev.buffer(n)
+            dst.copy_(T.as_tensor(d[n].reshape(dst.shape[0], -1)[:, :dst.shape[1]]).to(dst.device))
         dst = self._dev.buffer("tree")
-        dst.copy_(T.as_tensor(np.asarray(tree, np.float64).reshape(dst.shape)).to(dst.device))
-        self._dev.set_counters(int(d["mem_cntr"]), self._dev.counters()[1])
-        if "beta" in d:
-            self._dev.set_per_beta(float(d["beta"]))
+        dst.copy_(T.as_tensor(d["tree"].reshape(dst.shape)).to(dst.device))
+        self._dev.set_counters(d["mem_cntr"], self._dev.counters()[1])
+        self._dev.set_per_beta(d["beta"])
 
     def normalize_reward(self):
         """:163-167"""

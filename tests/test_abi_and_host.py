@@ -88,3 +88,24 @@ def test_standalone_host_replaybuffer_matches_reference_shape():
     np.random.seed(0)
     s, a, r, s2, d, h = rb.sample_buffer(4)
     assert s.shape == (4, 5) and a.shape == (4, 2) and d.dtype == bool
+
+
+def test_demix_td3_per_reads_reference_written_pickle(monkeypatch):
+    """tests/golden/ref_prioritized_replaymem_td3.model was written by the UNMODIFIED reference's demix_td3.PER.save_checkpoint
+    (tests/golden/make_ref_td3_per_pickle.py).  With the facade directory on sys.path -- the drop-in arrangement -- the pickle's
+    `demix_td3.PER` / `demix_sac.SumTree` resolve to the facade classes, and the host side of PER.load_checkpoint recovers arrays, tree,
+    counter and beta from their __dict__s (the device upload that follows is covered by the GPU round-trip test)."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.syspath_prepend(os.path.join(root, "smart-calibration_b200", "demixing_rl"))
+    for m in ("demix_td3", "demix_sac"):
+        sys.modules.pop(m, None)
+    import demix_td3
+    g = os.path.join(root, "tests", "golden")
+    d = demix_td3.PER.read_checkpoint(os.path.join(g, "ref_prioritized_replaymem_td3.model"))
+    z = np.load(os.path.join(g, "ref_prioritized_replaymem_td3.npz"))
+    assert np.array_equal(d["tree"], z["tree"]) and d["mem_cntr"] == int(z["mem_cntr"]) == 11 and d["beta"] == float(z["beta"])
+    assert np.array_equal(d["state_memory_img"], z["state_memory_img"]) and np.array_equal(d["new_state_memory_sky"], z["new_state_memory_sky"])
+    assert np.array_equal(d["reward_memory"], z["reward_memory"]) and np.array_equal(d["terminal_memory"] != 0, z["terminal_memory"])
+    for m in ("demix_td3", "demix_sac"):
+        sys.modules.pop(m, None)
