@@ -780,7 +780,9 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "SAC learn() steps/sec (batch=256)", "value": cpu["value"], "unit": "learn steps/s",
            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": cpu["ms_per_step"],
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD}, "cpu_baseline": cpu,
+           # same keys as the own arm's `config` (the workload string is identical; the other three describe how THIS arm ran it)
+           "config": {"workload": WORKLOAD, "l2": "not applicable (CPU arm; the 46 MB working set exceeds the host's per-core caches anyway)",
+                      "rng": "host numpy / torch global streams, like the reference", "parallelism": "single agent"}, "cpu_baseline": cpu,
            "e2e": {"value": cpu["value"], "unit": "learn steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
