@@ -73,6 +73,10 @@ class _TreeView(object):
         return self._per.mem_cntr % self.capacity
 
     @property
+    def data_length(self):
+        return len(self)
+
+    @property
     def total_priority(self):
         return float(self._per._dev.buffer("tree")[0, 0].item())
 
