@@ -109,3 +109,22 @@ def test_demix_td3_per_reads_reference_written_pickle(monkeypatch):
     assert np.array_equal(d["reward_memory"], z["reward_memory"]) and np.array_equal(d["terminal_memory"] != 0, z["terminal_memory"])
     for m in ("demix_td3", "demix_sac"):
         sys.modules.pop(m, None)
+
+
+def test_bench_secondary_objects_cannot_take_the_line_down(monkeypatch):
+    """bench.py runs its newest secondary object in a child process with a hard limit and skips secondary objects once its wall-time budget is
+    spent: without a GPU the child fails, and the parent gets an {"error": ...} object instead of an exception; past the budget it gets
+    {"skipped": ...}"""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    if not torch.cuda.is_available():
+        r = b.child_object("demix_td3", 2, 120)
+        assert isinstance(r, dict) and "error" in r and "value" not in r
+    r = b.child_object("demix_td3", 2, 0.01)
+    assert "error" in r and "exceeded" in r["error"]
+    assert b.over_budget("x") is None
+    monkeypatch.setattr(b, "BUDGET_S", -1.0)
+    assert "skipped" in b.over_budget("x")
