@@ -617,16 +617,21 @@ def cpu_baseline(sample_seconds=12.0, steps=None, warmup=5):
         tried[nt] = 8 / (time.perf_counter() - t0)
     best = max(tried, key=tried.get)
     torch.set_num_threads(best)
-    n, t0 = 0, time.perf_counter()
-    while True:
-        orc.learn()
-        n += 1
-        el = time.perf_counter() - t0
-        if (steps is not None and n >= steps) or (steps is None and el >= sample_seconds):
-            break
+    # a K-step sample (the --impl reference arm) is short enough for host interference to move it by +-10 % between runs (round-1 review):
+    # it is taken three times and the fastest repeat is reported -- the choice that favours the reference arm
+    reps, el, n = (3 if steps is not None else 1), None, 0
+    for _ in range(reps):
+        n, t0 = 0, time.perf_counter()
+        while True:
+            orc.learn()
+            n += 1
+            e = time.perf_counter() - t0
+            if (steps is not None and n >= steps) or (steps is None and e >= sample_seconds):
+                break
+        el = e if el is None else min(el, e)
     torch.set_num_threads(default_threads)
     return {"value": n / el, "unit": "learn steps/s", "cores": best, "kind": "port",
-            "sample": f"{n} learn() steps of the same workload in {el:.1f} s (oracle/sac_ref.py, torch {torch.__version__} CPU, "
+            "sample": f"{n} learn() steps of the same workload in {el:.1f} s{' (fastest of 3 repeats)' if reps > 1 else ''} (oracle/sac_ref.py, torch {torch.__version__} CPU, "
                       f"{best} threads = best of {{{', '.join(f'{k}: {v:.1f}/s' for k, v in sorted(tried.items()))}}}, "
                       f"{os.cpu_count()} logical cores)", "ms_per_step": el / n * 1e3}
 
