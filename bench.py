@@ -45,6 +45,17 @@ def log(msg):
     sys.stderr.flush()
 
 
+TRUNK_MFLOP = 2 * (16 * 62 * 62 * 25 + 32 * 29 * 29 * 16 * 25 + 32 * 13 * 13 * 32 * 25) / 1e6     # one conv-trunk forward pass, per sample: 33.3
+
+
+def conv_roofline(pass_equivalents, batch, ms, tf32_peak, note):
+    """tensor-bound roofline object of a conv-trunk agent step: `pass_equivalents` trunk passes (forward = 1, backward = 2: input and weight
+    gradients) x 33.3 MFLOP x batch, against the TF32 tensor peak (SURVEY 8d counts config 3 the same way: 14 passes -> 119 GFLOP)"""
+    flop = pass_equivalents * TRUNK_MFLOP * 1e6 * batch
+    ach = flop / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "algorithmic_flop": flop, "note": note}
+
+
 def over_budget(what):
     if elapsed() > BUDGET_S:
         log(f"{what}: skipped (time budget)")
@@ -302,7 +313,9 @@ def demix_td3_numbers(steps, warmup):
         orc.learn()
         dt = (time.perf_counter() - t0) / 2
     torch.set_num_threads(t)
-    return {"value": 1e3 / ms, "unit": "learn steps/s", "ms_per_step": ms,
+    # trunk passes: critic-only call 5 forwards + 2 backwards = 9; call with the hinted actor update 9 + 1 (critic_1) + 5 x (1 + 2) = 25; mean 17
+    roof = conv_roofline(17, Bd, ms, peaks_tf32(), "mean over the two kinds of call; at batch 64 the step is launch- and reduction-bound (profiles/r2g_demix_td3_summary.md)")
+    return {"value": 1e3 / ms, "unit": "learn steps/s", "ms_per_step": ms, "roofline": roof,
             "workload": "demixing_rl conv TD3 (demix_td3.py): img (64,1,128,128), metadata 20, 5 actions, PER 4096, actor interval 2, use_hint=True "
                         "(critic-only calls and calls with the five-step ADMM actor loop alternate; mean over both)",
             "cpu_baseline": {"value": 1.0 / dt, "unit": "learn steps/s", "cores": nt, "kind": "port", "sample": "2 learn() steps (one with the actor loop) after 2 warm-up"},
@@ -357,7 +370,10 @@ def demix_numbers(family, steps, warmup):
     dt = (time.perf_counter() - t0) / k
     torch.set_num_threads(t)
     launches = dev.launch_count()
-    return {"value": 1e3 / ms, "unit": "learn steps/s", "ms_per_step": ms,
+    extra = {}
+    if ui:      # 8 trunk forwards + 3 backwards, like the calibration agent
+        extra["roofline"] = conv_roofline(14, Bd, ms, peaks_tf32(), "same kernels as calib_b256 (DESIGN.md 4b)")
+    return {"value": 1e3 / ms, "unit": "learn steps/s", "ms_per_step": ms, **extra,
             "workload": ("demixing_rl conv SAC: img (256,1,128,128), metadata 20, 6 actions" if ui else
                          "demixing_fuzzy MLP SAC: metadata 32, 128 actions, batch 256 (use_influence=False)"),
             "cpu_baseline": {"value": 1.0 / dt, "unit": "learn steps/s", "cores": nt, "kind": "port", "sample": f"{k} learn() step(s) after 1 warm-up"},
@@ -703,7 +719,8 @@ def calib_numbers(steps, warmup):
     return {"value": 1e3 / ms, "unit": "learn steps/s", "ms_per_step": ms,
             "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": flop / (ms * 1e-3) / 1e12 / tf32_peak, "algorithmic_flop": flop,
-                         "note": "conv trunk still on FP32 FFMA kernels (DESIGN.md): fraction of the TF32 tensor peak it would be bound by"},
+                         "note": "conv2 / conv3 forward on tcgen05, their backward passes and the BatchNorm reductions on FP32 kernels (DESIGN.md 4b): "
+                                 "fraction of the TF32 tensor peak the step would be bound by"},
             "cpu_baseline": {"value": 1.0 / dt, "unit": "learn steps/s", "cores": nt, "kind": "port", "sample": "1 learn() step after 1 warm-up"}}
 
 

@@ -128,3 +128,15 @@ def test_bench_secondary_objects_cannot_take_the_line_down(monkeypatch):
     assert b.over_budget("x") is None
     monkeypatch.setattr(b, "BUDGET_S", -1.0)
     assert "skipped" in b.over_budget("x")
+
+
+def test_bench_conv_roofline_counts_trunk_passes():
+    """bench.py's tensor roofline of the conv agents: 14 trunk-pass equivalents x 33.3 MFLOP x 256 = the 119 GFLOP of SURVEY 8d (config 3)"""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(root, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    r = b.conv_roofline(14, 256, 8.0, 845.0, "note")
+    assert abs(r["algorithmic_flop"] - 119e9) < 1e9 and abs(r["achieved"] - r["algorithmic_flop"] / 8e-3 / 1e12) < 1e-9 and r["bound"] == "tensor"
+    assert abs(r["frac"] - r["achieved"] / 845.0) < 1e-12
